@@ -1,0 +1,214 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes/numpy front-end of the plain-C oracle (oracle/mrcnn_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  The product (maskrcnn_b200/) never does.
+
+All arrays are numpy, C-contiguous, fp32 / int32 / int64, NCHW — the reference's layout.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "mrcnn_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.orc_nms.restype = ctypes.c_int64
+        L.orc_nms.argtypes = [_f32p, ctypes.c_int64, ctypes.c_float, _i64p]
+        L.orc_crop_forward.restype = ctypes.c_int
+        L.orc_crop_forward.argtypes = [_f32p] + [ctypes.c_int] * 4 + [_f32p, _i32p, ctypes.c_int,
+                                                                    ctypes.c_float, ctypes.c_int,
+                                                                    ctypes.c_int, _f32p]
+        L.orc_crop_backward.restype = ctypes.c_int
+        L.orc_crop_backward.argtypes = [_f32p, _f32p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        _f32p] + [ctypes.c_int] * 4
+        L.orc_roi_level.restype = ctypes.c_int
+        L.orc_roi_level.argtypes = [_f32p, ctypes.c_float]
+        pp = ctypes.POINTER(_f32p)
+        ip = ctypes.POINTER(ctypes.c_int)
+        L.orc_pyramid_roi_align_fwd.restype = ctypes.c_int
+        L.orc_pyramid_roi_align_fwd.argtypes = [pp, ip, ip, ctypes.c_int, ctypes.c_int, _f32p, _i32p,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_float, _f32p, _i32p]
+        L.orc_pyramid_roi_align_bwd.restype = ctypes.c_int
+        L.orc_pyramid_roi_align_bwd.argtypes = [_f32p, ip, ip, ctypes.c_int, ctypes.c_int, _f32p, _i32p,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_float, pp]
+        L.orc_proposal_layer.restype = ctypes.c_int64
+        L.orc_proposal_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.c_float, _f32p, ctypes.c_float,
+                                         ctypes.c_float, _f32p, _f32p, _i64p]
+        L.orc_detection_layer.restype = ctypes.c_int64
+        L.orc_detection_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64, _f32p,
+                                          ctypes.c_float, ctypes.c_float, ctypes.c_int64, _f32p,
+                                          ctypes.c_float, ctypes.c_float, _f32p, _i64p]
+        L.orc_boxes_refine.restype = None
+        L.orc_boxes_refine.argtypes = [_f32p, _f32p, ctypes.c_int64, _f32p]
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=_f32p):
+    return a.ctypes.data_as(t)
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def nms(dets, threshold):
+    """c++ext/maskrcnn/__init__.py:21-22 -> nms_cpu.cpp:11-70.  dets [N,5] -> int64 [K] ascending."""
+    dets = _f32(dets).reshape(-1, 5)
+    n = dets.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    k = lib().orc_nms(_p(dets), n, float(threshold), _p(keep, _i64p))
+    return keep[:k].copy()
+
+
+def crop_forward(image, boxes, box_index, crop_h, crop_w, extrapolation_value=0.0):
+    """crop_cpu.cpp:119-164.  image [B,C,H,W] -> crops [N,C,ch,cw]."""
+    image = _f32(image)
+    boxes = _f32(boxes).reshape(-1, 4)
+    box_index = np.ascontiguousarray(box_index, dtype=np.int32)
+    B, C, H, W = image.shape
+    N = boxes.shape[0]
+    out = np.zeros((N, C, crop_h, crop_w), dtype=np.float32)
+    rc = lib().orc_crop_forward(_p(image), B, C, H, W, _p(boxes), _p(box_index, _i32p), N,
+                                float(extrapolation_value), crop_h, crop_w, _p(out))
+    if rc:
+        raise OracleError("box_index out of range")
+    return out
+
+
+def crop_backward(grads, boxes, box_index, image_shape):
+    """crop_cpu.cpp:167-265.  grads [N,C,ch,cw] -> grads_image [B,C,H,W]."""
+    grads = _f32(grads)
+    boxes = _f32(boxes).reshape(-1, 4)
+    box_index = np.ascontiguousarray(box_index, dtype=np.int32)
+    B, C, H, W = image_shape
+    N, _, ch, cw = grads.shape
+    gi = np.empty((B, C, H, W), dtype=np.float32)
+    rc = lib().orc_crop_backward(_p(grads), _p(boxes), _p(box_index, _i32p), N, ch, cw, _p(gi), B, C, H, W)
+    if rc:
+        raise OracleError("box_index out of range")
+    return gi
+
+
+def roi_levels(boxes, image_area):
+    boxes = _f32(boxes).reshape(-1, 4)
+    return np.array([lib().orc_roi_level(_p(boxes[i:i + 1]), float(image_area)) for i in range(len(boxes))],
+                    dtype=np.int32)
+
+
+def _pyr_args(fms):
+    fms = [_f32(f) for f in fms]
+    assert len(fms) == 4
+    B, C = fms[0].shape[:2]
+    H = (ctypes.c_int * 4)(*[f.shape[2] for f in fms])
+    W = (ctypes.c_int * 4)(*[f.shape[3] for f in fms])
+    ptrs = (_f32p * 4)(*[_p(f) for f in fms])
+    return fms, B, C, H, W, ptrs
+
+
+def pyramid_roi_align_fwd(fms, boxes, box_ind, pool, image_area):
+    """model.py:276-393 (batched over box_ind).  fms: 4 arrays [B,C,Hl,Wl] -> ([N,C,p,p], levels[N])."""
+    fms, B, C, H, W, ptrs = _pyr_args(fms)
+    boxes = _f32(boxes).reshape(-1, 4)
+    N = boxes.shape[0]
+    box_ind = np.zeros(N, np.int32) if box_ind is None else np.ascontiguousarray(box_ind, dtype=np.int32)
+    out = np.zeros((N, C, pool, pool), dtype=np.float32)
+    lv = np.zeros(N, dtype=np.int32)
+    rc = lib().orc_pyramid_roi_align_fwd(ptrs, H, W, B, C, _p(boxes), _p(box_ind, _i32p), N, pool,
+                                         float(image_area), _p(out), _p(lv, _i32p))
+    if rc:
+        raise OracleError("box_index out of range")
+    return out, lv
+
+
+def pyramid_roi_align_bwd(grads, shapes, boxes, box_ind, image_area):
+    """Adjoint of pyramid_roi_align_fwd.  shapes: 4 tuples (B,C,Hl,Wl) -> list of 4 grad arrays."""
+    grads = _f32(grads)
+    boxes = _f32(boxes).reshape(-1, 4)
+    N, C, pool, _ = grads.shape
+    B = shapes[0][0]
+    box_ind = np.zeros(N, np.int32) if box_ind is None else np.ascontiguousarray(box_ind, dtype=np.int32)
+    gf = [np.empty(s, dtype=np.float32) for s in shapes]
+    H = (ctypes.c_int * 4)(*[s[2] for s in shapes])
+    W = (ctypes.c_int * 4)(*[s[3] for s in shapes])
+    ptrs = (_f32p * 4)(*[_p(g) for g in gf])
+    rc = lib().orc_pyramid_roi_align_bwd(_p(grads), H, W, B, C, _p(boxes), _p(box_ind, _i32p), N, pool,
+                                         float(image_area), ptrs)
+    if rc:
+        raise OracleError("box_index out of range")
+    return gf
+
+
+def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, nms_threshold,
+                   std=(0.1, 0.1, 0.2, 0.2), height=1024.0, width=1024.0, return_intermediate=False):
+    """model.py:1307-1382, one image.  rpn_class [A,2], rpn_bbox [A,4], anchors [A,4] -> rois [K,4]."""
+    rpn_class = _f32(rpn_class).reshape(-1, 2)
+    rpn_bbox = _f32(rpn_bbox).reshape(-1, 4)
+    anchors = _f32(anchors).reshape(-1, 4)
+    A = rpn_class.shape[0]
+    pre = min(int(pre_nms_limit), A)
+    rois = np.zeros((max(int(post_nms_limit), 1), 4), dtype=np.float32)
+    dets = np.zeros((max(pre, 1), 5), dtype=np.float32)
+    order = np.zeros(max(pre, 1), dtype=np.int64)
+    stdv = _f32(std)
+    k = lib().orc_proposal_layer(_p(rpn_class), _p(rpn_bbox), _p(anchors), A, pre, int(post_nms_limit),
+                                 float(nms_threshold), _p(stdv), float(height), float(width), _p(rois),
+                                 _p(dets), _p(order, _i64p))
+    if return_intermediate:
+        return rois[:k].copy(), dets[:pre].copy(), order[:pre].copy()
+    return rois[:k].copy()
+
+
+def detection_layer(rois, probs, deltas, window, min_conf, nms_threshold, max_inst,
+                    std=(0.1, 0.1, 0.2, 0.2), height=1024.0, width=1024.0, return_index=False):
+    """model.py:1389-1487, one image -> [D,6] (y1,x1,y2,x2,score,class), score-descending."""
+    rois = _f32(rois).reshape(-1, 4)
+    probs = _f32(probs)
+    N, NC = probs.shape
+    deltas = _f32(deltas).reshape(N, NC, 4)
+    window = _f32(window)
+    out = np.zeros((max(int(max_inst), 1), 6), dtype=np.float32)
+    idx = np.zeros(max(int(max_inst), 1), dtype=np.int64)
+    stdv = _f32(std)
+    d = lib().orc_detection_layer(_p(rois), _p(probs), _p(deltas), N, NC, _p(window), float(min_conf or 0.0),
+                                  float(nms_threshold), int(max_inst), _p(stdv), float(height), float(width),
+                                  _p(out), _p(idx, _i64p))
+    if return_index:
+        return out[:d].copy(), idx[:d].copy()
+    return out[:d].copy()
+
+
+def boxes_refine(boxes, deltas):
+    """data.py:124-148."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    deltas = _f32(deltas).reshape(-1, 4)
+    out = np.empty_like(boxes)
+    lib().orc_boxes_refine(_p(boxes), _p(deltas), boxes.shape[0], _p(out))
+    return out

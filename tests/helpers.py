@@ -1,0 +1,23 @@
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+
+def golden():
+    return np.load(GOLDEN)
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def rel_err(got, want):
+    """max |got-want| / max|want| — the 'relative' of north_star's 1e-5 (scale = output magnitude)."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    scale = max(np.abs(want).max(), 1e-30) if want.size else 1.0
+    return float(np.abs(got - want).max() / scale) if want.size else 0.0

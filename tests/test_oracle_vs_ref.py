@@ -1,0 +1,175 @@
+"""Pins the plain-C oracle (oracle/mrcnn_oracle.c) against the reference itself, executed here:
+the reference's compiled CPU extension (oracle/_ref, built unmodified from /root/reference) and the
+reference's unmodified model.py.  Skipped where the reference is absent (the GPU box); the same
+comparisons are frozen as golden vectors in tests/golden/ (tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import reference
+from maskrcnn_b200 import synth
+
+pytestmark = pytest.mark.skipif(not reference.ref_C_available(), reason="oracle/_ref not built")
+
+
+def _ref_crop_fwd(img, boxes, ind, ch, cw, ev):
+    C = reference.ref_C()
+    out = torch.zeros(1)
+    with reference.quiet_stdout():
+        C.crop_forward(torch.from_numpy(img), torch.from_numpy(boxes), torch.from_numpy(ind), ev, ch, cw, out)
+    return out.numpy()
+
+
+def _ref_crop_bwd(g, boxes, ind, shape):
+    C = reference.ref_C()
+    gi = torch.empty(shape)
+    C.crop_backward(torch.from_numpy(g), torch.from_numpy(boxes), torch.from_numpy(ind), gi)
+    return gi.numpy()
+
+
+def _boxes_px(n, seed, size=1024.0):
+    b = synth.random_rois(n, seed, image=size, min_size=size / 64, max_size=size * 0.7) * size
+    return b
+
+
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (63, 0.3), (64, 0.7), (65, 0.5), (1000, 0.3), (3000, 0.7)])
+def test_nms_bit_exact(n, thr):
+    rng = np.random.default_rng(n)
+    b = _boxes_px(n, n)
+    # cluster boxes so that a good share is suppressed
+    b[n // 2:] = b[: n - n // 2] + rng.uniform(-6, 6, (n - n // 2, 4)).astype(np.float32)
+    dets = np.concatenate([b, synth.unique_scores(n, n)[:, None]], 1).astype(np.float32)
+    want = reference.ref_C().nms(torch.from_numpy(dets), thr).numpy()
+    got = oracle.nms(dets, thr)
+    assert got.dtype == np.int64
+    np.testing.assert_array_equal(got, want)
+    assert 0 < len(want) <= n
+
+
+def test_nms_edge_cases():
+    C = reference.ref_C()
+    assert len(oracle.nms(np.zeros((0, 5), np.float32), 0.5)) == 0
+    assert C.nms(torch.zeros(0, 5), 0.5).numel() == 0
+    # degenerate / inverted boxes, exact-threshold IoU, NaN IoU (0/0)
+    dets = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 9, 0.8], [0, 0, 9, 4, 0.7],   # IoU = 0.5 exactly
+                     [5, 5, 2, 2, 0.6], [5, 5, 2, 2, 0.5],                       # y2<y1
+                     [0, 0, -1, -1, 0.4], [0, 0, -1, -1, 0.3],                   # area 0 -> 0/0
+                     [100, 100, 120, 130, 0.2]], np.float32)
+    for thr in (0.5, 0.3, 0.0, 1.0):
+        np.testing.assert_array_equal(oracle.nms(dets, thr), C.nms(torch.from_numpy(dets), thr).numpy())
+
+
+@pytest.mark.parametrize("B,C,H,W,N,ch,cw,ev", [
+    (1, 3, 16, 16, 7, 7, 7, 0.0), (2, 5, 32, 24, 33, 14, 14, 0.0), (3, 1, 64, 64, 9, 28, 28, 0.0),
+    (1, 4, 8, 8, 5, 1, 1, 0.0), (2, 2, 9, 13, 6, 1, 5, -1.5), (1, 2, 33, 17, 11, 3, 1, 2.0)])
+def test_crop_fwd_bwd_bit_exact(B, C, H, W, N, ch, cw, ev):
+    rng = np.random.default_rng(B * 1000 + N)
+    img = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    boxes = synth.random_rois(N, N, image=64.0, min_size=4, max_size=60)
+    # some boxes leave the image (extrapolation), one is inverted, one is a point
+    boxes[0] += 0.3
+    boxes[1] -= 0.25
+    if N > 4:
+        boxes[2] = boxes[2][[2, 3, 0, 1]]
+        boxes[3] = [0.5, 0.5, 0.5, 0.5]
+        boxes[4] = [0.0, 0.0, 1.0, 1.0]
+    ind = rng.integers(0, B, N).astype(np.int32)
+    want = _ref_crop_fwd(img, boxes, ind, ch, cw, ev)
+    got = oracle.crop_forward(img, boxes, ind, ch, cw, ev)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    g = rng.standard_normal(want.shape, dtype=np.float32)
+    np.testing.assert_array_equal(oracle.crop_backward(g, boxes, ind, img.shape),
+                                  _ref_crop_bwd(g, boxes, ind, img.shape))
+
+
+def test_crop_bad_box_index():
+    img = np.zeros((1, 1, 4, 4), np.float32)
+    with pytest.raises(oracle.OracleError):
+        oracle.crop_forward(img, np.array([[0, 0, 1, 1]], np.float32), np.array([1], np.int32), 2, 2)
+
+
+needs_model = pytest.mark.skipif(not reference.available(), reason="/root/reference absent")
+
+
+def _small_pyramid(C, size, seed):
+    return synth.feature_pyramid(1, C, seed, image=size)
+
+
+@needs_model
+@pytest.mark.parametrize("pool", [7, 14])
+def test_pyramid_roi_align_matches_model_py(pool):
+    ref = reference.load()
+    size, C, N = 512, 6, 300
+    fms = _small_pyramid(C, size, 3)
+    boxes = synth.random_rois(N, 5, image=float(size), min_size=8, max_size=size * 0.9)
+    t_fms = [torch.from_numpy(f).clone().requires_grad_(True) for f in fms]
+    inputs = [torch.from_numpy(boxes).unsqueeze(0)] + list(t_fms)
+    want = ref.model.roi_align(inputs, pool, [size, size, 3])
+    got, lv = oracle.pyramid_roi_align_fwd(fms, boxes, None, pool, float(size * size))
+    assert set(np.unique(lv)) == {2, 3, 4, 5}
+    np.testing.assert_array_equal(got, want.detach().numpy())
+    g = np.random.default_rng(9).standard_normal(got.shape, dtype=np.float32)
+    want.backward(torch.from_numpy(g))
+    gf = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, None, float(size * size))
+    for a, b in zip(gf, t_fms):
+        np.testing.assert_array_equal(a, b.grad.numpy())
+
+
+@needs_model
+def test_roi_level_matches_model_py_at_full_scale():
+    ref = reference.load()
+    boxes = synth.random_rois(20000, 77)
+    b = torch.from_numpy(boxes)
+    h = b[:, 2] - b[:, 0]
+    w = b[:, 3] - b[:, 1]
+    area = torch.FloatTensor([1024.0 * 1024.0])
+    want = (4 + torch.log2(torch.sqrt(h * w) / (224.0 / torch.sqrt(area)))).round().int().clamp(2, 5)  # model.py:331-338
+    got = oracle.roi_levels(boxes, 1024.0 * 1024.0)
+    np.testing.assert_array_equal(got, want.numpy())
+
+
+def _ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+@needs_model
+def test_proposal_layer_matches_model_py():
+    ref = reference.load()
+    import types
+    anchors = synth.pyramid_anchors((256, 256))
+    rc, rb = synth.rpn_outputs(anchors, 11, image=256.0, n_clusters=6)
+    cfg = types.SimpleNamespace(RPN_NMS_MAX_ROIS_NUM=200, RPN_NMS_THRESHOLD=0.7,
+                                RPN_BBOX_STD_DEV=[0.1, 0.1, 0.2, 0.2], IMAGE_SHAPE=np.array([256, 256, 3]),
+                                GPU_COUNT=0)
+    stub = types.SimpleNamespace(config=cfg, anchors=torch.from_numpy(anchors))
+    want = ref.model.MaskRCNN.rpn_refine(stub, torch.from_numpy(rc).unsqueeze(0),
+                                         torch.from_numpy(rb).unsqueeze(0))[0].numpy()
+    got = oracle.proposal_layer(rc, rb, anchors, 500, 200, 0.7, height=256.0, width=256.0)  # model.py:1345
+    assert got.shape == want.shape and 20 < len(got) <= 200
+    assert _ulp_diff(got, want).max() <= 4   # torch.exp on CPU is not correctly rounded
+
+
+@needs_model
+def test_detection_layer_matches_model_py():
+    ref = reference.load()
+    import types
+    N, NC = 400, 81
+    rois = synth.random_rois(N, 21)
+    probs, deltas = synth.head_outputs(N, NC, 22)
+    window = np.array([0, 0, 1024, 1024], np.float32)
+    for min_conf, max_inst in ((0, 100), (0.7, 50)):
+        cfg = types.SimpleNamespace(RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), IMAGE_SHAPE=np.array([1024, 1024, 3]),
+                                    GPU_COUNT=0, DETECTION_MIN_CONFIDENCE=min_conf, DETECTION_NMS_THRESHOLD=0.3,
+                                    DETECTION_MAX_INSTANCES=max_inst)
+        stub = types.SimpleNamespace(config=cfg)
+        ci, sc, bx = ref.model.MaskRCNN.mrn_refine(stub, torch.from_numpy(rois).unsqueeze(0), torch.from_numpy(probs),
+                                                   torch.from_numpy(deltas), window)
+        got = oracle.detection_layer(rois, probs, deltas, window, min_conf, 0.3, max_inst)
+        assert len(got) == ci.shape[1] and len(got) > 10
+        np.testing.assert_array_equal(got[:, 5].astype(np.int64), ci[0].numpy())
+        np.testing.assert_array_equal(got[:, 4], sc[0].numpy())
+        np.testing.assert_array_equal(got[:, :4], bx[0].numpy())
