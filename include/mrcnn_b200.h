@@ -1,0 +1,137 @@
+/*
+ * mrcnn_b200.h — C ABI of libmrcnn_b200.so: the B200-native (sm_100a) RoI hot path of Mask R-CNN.
+ *
+ * This is the drop-in boundary for the native layer of delldu/MaskRCNN:
+ *     c++ext/maskrcnn/csrc/vision.cpp:11-15   pybind module `maskrcnn._C` { nms, crop_forward, crop_backward }
+ *     c++ext/maskrcnn/csrc/nms.h:15-30        at::Tensor nms(const at::Tensor& dets, float threshold)
+ *     c++ext/maskrcnn/csrc/crop.h:14-34       void crop_forward(image, boxes, box_index, extrapolation_value,
+ *                                                               crop_height, crop_width, crops&)
+ *     c++ext/maskrcnn/csrc/crop.h:36-53       void crop_backward(grads, boxes, box_index, grads_image&)
+ * plus fused entry points for the Python-level callers of those ops (model.py:276-393 roi_align,
+ * :1307-1382 rpn_refine, :1389-1487 mrn_refine), which the reference runs as dozens of small launches.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers + sizes + a CUDA stream (cudaStream_t passed as void*); no torch types.
+ *   - every function returns MRCNN_OK (0) or a negative MRCNN_E_* code; mrcnn_last_error() gives the text.
+ *     Nothing ever calls exit() (the reference does: cpu/crop_cpu.cpp:47-50).
+ *   - all work is enqueued on `stream`; no call synchronises the device or copies to the host.
+ *     Data-dependent sizes (number of kept boxes) are written to device counters supplied by the caller.
+ *   - the caller owns every buffer, including workspaces (size them with the *_workspace_bytes calls).
+ *   - fp32 boxes are (y1, x1, y2, x2); box_index is int32; keep indices are int64 — as in the reference.
+ *   - there is NO CPU implementation behind this ABI: host pointers are rejected (MRCNN_E_NOT_DEVICE_PTR).
+ */
+#ifndef MRCNN_B200_H_
+#define MRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRCNN_ABI_VERSION 1
+
+#define MRCNN_OK 0
+#define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */
+#define MRCNN_E_NOT_DEVICE_PTR (-2) /* a data pointer is not device memory (no CPU fallback exists) */
+#define MRCNN_E_WORKSPACE (-3)      /* workspace too small                                          */
+#define MRCNN_E_CUDA (-4)           /* a CUDA runtime call / launch failed                          */
+#define MRCNN_E_BOX_INDEX (-5)      /* reported by mrcnn_poll_device_errors: box_index out of range */
+
+/* Memory layout of 4-D tensors.  Logical shape is always [N, C, H, W] as in the reference;
+ * NHWC means the same tensor stored channels-last (torch.channels_last), which is what the
+ * 128-bit channel-vectorised kernels want. */
+#define MRCNN_NCHW 0
+#define MRCNN_NHWC 1
+
+typedef void* mrcnn_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define MRCNN_API __attribute__((visibility("default")))
+#else
+#define MRCNN_API
+#endif
+
+MRCNN_API int mrcnn_abi_version(void);
+MRCNN_API const char* mrcnn_last_error(void); /* thread-local, valid until the next failing call on this thread */
+
+/* Kernels flag recoverable data errors (box_index out of range: the reference exit(-1)s on CPU,
+ * cpu/crop_cpu.cpp:47-50, and silently skips on CUDA, cuda/crop_cuda.cu:41-44) in a device word;
+ * offending boxes produce extrapolation_value / contribute no gradient.  This call synchronises
+ * `stream`, returns MRCNN_E_BOX_INDEX if the flag was raised since the last poll, and clears it. */
+MRCNN_API int mrcnn_poll_device_errors(mrcnn_stream_t stream);
+
+/* ---- crop_and_resize (replaces crop_forward / crop_backward, crop.h:14-53) -------------------- */
+
+/* image [B,C,H,W] (image_layout), boxes [N,4] normalised, box_index [N] in [0,B),
+ * crops [N,C,crop_h,crop_w] (crops_layout) — every element is written (no pre-zeroing needed). */
+MRCNN_API int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout,
+                       const float* boxes, const int32_t* box_index, int N,
+                       float extrapolation_value, int crop_h, int crop_w,
+                       float* crops, int crops_layout, mrcnn_stream_t stream);
+
+/* grads [N,C,crop_h,crop_w] (grads_layout) scatter-added into grads_image [B,C,H,W] (image_layout).
+ * zero_fill != 0: grads_image is cleared first, as crop_cpu.cpp:197 does.  No gradient w.r.t. boxes. */
+MRCNN_API int mrcnn_crop_backward(const float* grads, int grads_layout, const float* boxes,
+                        const int32_t* box_index, int N, int crop_h, int crop_w,
+                        float* grads_image, int B, int C, int H, int W, int image_layout,
+                        int zero_fill, mrcnn_stream_t stream);
+
+/* ---- PyramidROIAlign (replaces model.py:276-393 roi_align and its autograd backward) ---------- */
+
+/* fm[l] = pyramid level P(l+2), l = 0..3: [B,C,H[l],W[l]] in fm_layout.  boxes [N,4] normalised;
+ * box_index [N] = image of each box, or NULL for all-zero (the reference is batch-1, model.py:369).
+ * image_area = float(image_height * image_width) (model.py:331).  out [N,C,pool,pool] (out_layout) in
+ * INPUT box order.  levels_out: optional int32 [N] receiving the assigned level (2..5). */
+MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], const int W[4],
+                                    int B, int C, int fm_layout,
+                                    const float* boxes, const int32_t* box_index, int N, int pool,
+                                    float image_area, float* out, int out_layout,
+                                    int32_t* levels_out, mrcnn_stream_t stream);
+
+MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout,
+                                     const int H[4], const int W[4], int B, int C,
+                                     const float* boxes, const int32_t* box_index, int N, int pool,
+                                     float image_area, float* const gfm[4], int gfm_layout,
+                                     int zero_fill, mrcnn_stream_t stream);
+
+/* ---- NMS (replaces nms(), nms.h:15-30 -> cpu/nms_cpu.cpp:11-70) -------------------------------- */
+
+/* dets [N,5] = (y1,x1,y2,x2,score), any order.  Suppress iff IoU >= threshold (the CPU rule,
+ * nms_cpu.cpp:65 — the reference's own CUDA kernel uses '>').  keep_out: int64 [N], receives the
+ * ASCENDING original indices of the survivors in its first *count_out entries (device int32). */
+MRCNN_API size_t mrcnn_nms_workspace_bytes(int N);
+MRCNN_API int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int32_t* count_out,
+              void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+/* ---- proposal layer (replaces MaskRCNN.rpn_refine, model.py:1307-1382; batched) ---------------- */
+
+/* rpn_class [B,A,2] (bg,fg), rpn_bbox [B,A,4], anchors [A,4] px, std[4] = RPN_BBOX_STD_DEV (host ptr).
+ * Top-pre_nms by fg score -> decode -> clip to [0,height]x[0,width] -> NMS(threshold) -> first post_nms
+ * -> normalise.  rois_out [B,post_nms,4] (rows >= count are zero), counts_out int32 [B]. */
+MRCNN_API size_t mrcnn_proposal_workspace_bytes(int B, int A, int pre_nms);
+MRCNN_API int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors,
+                         int B, int A, int pre_nms, int post_nms, float nms_threshold,
+                         const float* std4_host, float height, float width,
+                         float* rois_out, int32_t* counts_out,
+                         void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+/* ---- detection layer (replaces MaskRCNN.mrn_refine, model.py:1389-1487; batched) --------------- */
+
+/* rois [B,N,4] normalised, probs [B,N,NC], deltas [B,N,NC,4], windows [B,4] px (device).
+ * min_confidence <= 0 disables the score filter (model.py:1441).  dets_out [B,max_inst,6] =
+ * (y1,x1,y2,x2,score,class) score-descending, zero padded; counts_out int32 [B] (0 = the reference's
+ * (None,None,None)); index_out optional int32 [B,max_inst] = source RoI of each detection. */
+MRCNN_API size_t mrcnn_detection_workspace_bytes(int B, int N);
+MRCNN_API int mrcnn_detection_layer(const float* rois, const float* probs, const float* deltas,
+                          const float* windows, int B, int N, int NC,
+                          float min_confidence, float nms_threshold, int max_inst,
+                          const float* std4_host, float height, float width,
+                          float* dets_out, int32_t* counts_out, int32_t* index_out,
+                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRCNN_B200_H_ */

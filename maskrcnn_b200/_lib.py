@@ -1,0 +1,77 @@
+"""ctypes binding of libmrcnn_b200.so (include/mrcnn_b200.h).  There is no fallback: if the library
+is missing or a call fails, an exception is raised."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmrcnn_b200.so")
+
+NCHW, NHWC = 0, 1
+OK = 0
+E_INVALID_ARG, E_NOT_DEVICE_PTR, E_WORKSPACE, E_CUDA, E_BOX_INDEX = -1, -2, -3, -4, -5
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_sz = ctypes.c_size_t
+_i4 = ctypes.c_int * 4
+_vp4 = ctypes.c_void_p * 4
+_f4 = ctypes.c_float * 4
+
+# name -> (restype, argtypes); must list every symbol include/mrcnn_b200.h declares (tests/test_abi.py)
+SIGNATURES = {
+    "mrcnn_abi_version": (_i, []),
+    "mrcnn_last_error": (ctypes.c_char_p, []),
+    "mrcnn_poll_device_errors": (_i, [_vp]),
+    "mrcnn_crop_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _i, _vp]),
+    "mrcnn_crop_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrcnn_pyramid_roi_align_forward": (_i, [_vp4, _i4, _i4, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp]),
+    "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp]),
+    "mrcnn_nms_workspace_bytes": (_sz, [_i]),
+    "mrcnn_nms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_proposal_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mrcnn_proposal_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f4, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_detection_workspace_bytes": (_sz, [_i, _i]),
+    "mrcnn_detection_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f4, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+
+class MrcnnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmrcnn_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "maskrcnn_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C maskrcnn_b200/csrc`.  There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mrcnn_abi_version() != 1:
+        raise ImportError("maskrcnn_b200: ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != OK:
+        raise MrcnnError(rc, lib.mrcnn_last_error().decode("utf-8", "replace"))
+
+
+def i4(vals):
+    return _i4(*[int(v) for v in vals])
+
+
+def vp4(vals):
+    return _vp4(*[int(v) for v in vals])
+
+
+def f4(vals):
+    return _f4(*[float(v) for v in vals])

@@ -1,0 +1,274 @@
+// detection.cu — the detection layer for sm_100a, batched over images: ONE launch, one CTA per image.
+//
+// Replaces MaskRCNN.mrn_refine (model.py:1389-1487), which loops over classes in Python with a
+// nonzero + sort + C++ nms + unique per class and a .tolist() host sync:
+//   per-RoI argmax class -> class-specific delta decode -> scale to pixels -> clip to window -> round
+//   -> drop background / low confidence -> per-class NMS -> top max_inst by score.
+//
+// Per-class NMS is done as ONE class-aware NMS over all kept RoIs sorted by score: a box may only be
+// suppressed by a higher-scoring box of the SAME class, which is exactly the union of the per-class
+// results (model.py:1454-1474); the final top-D (:1478-1480) is then a prefix of the sorted survivors.
+#include <limits.h>
+
+#include "api_util.h"
+#include "nms_core.cuh"
+
+namespace mrcnn {
+
+constexpr int kDetThreads = 1024;
+constexpr int kDetMaxN = 4096;
+constexpr int kDetSmemMaskMaxN = 1024;  // suppression words kept in shared memory up to this many RoIs
+
+struct DetParams {
+    const float* rois;     // [B,N,4] normalised
+    const float* probs;    // [B,N,NC]
+    const float* deltas;   // [B,N,NC,4]
+    const float* windows;  // [B,4]
+    int B, N, NC, P, N64, W;
+    float min_conf, thr;
+    int max_inst;
+    float std0, std1, std2, std3;
+    float height, width;
+    float* dets_out;      // [B,max_inst,6]
+    int32_t* counts_out;  // [B]
+    int32_t* index_out;   // [B,max_inst] or null
+    uint64_t* gmask;      // [B][N64][W] (used when N > kDetSmemMaskMaxN)
+    int mask_in_smem;
+};
+
+__global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const DetParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ int s_total;
+    __shared__ int s_count;
+    __shared__ int s_prefix[kDetMaxN / 64 + 1];
+
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, NC = p.NC;
+
+    // shared-memory carve-up
+    unsigned char* ptr = smem_raw;
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(ptr);  ptr += (size_t)p.P * 8;
+    float4* rbox = reinterpret_cast<float4*>(ptr);          ptr += (size_t)N * 16;   // refined box per RoI (input order)
+    float4* sbox = reinterpret_cast<float4*>(ptr);          ptr += (size_t)N * 16;   // boxes in score order
+    float* sarea = reinterpret_cast<float*>(ptr);           ptr += (size_t)N * 4;
+    int* scls = reinterpret_cast<int*>(ptr);                ptr += (size_t)N * 4;
+    int* rcls = reinterpret_cast<int*>(ptr);                ptr += (size_t)N * 4;    // class per RoI (input order)
+    float* rscore = reinterpret_cast<float*>(ptr);          ptr += (size_t)N * 4;
+    uint64_t* remv = reinterpret_cast<uint64_t*>(ptr);      ptr += (size_t)p.W * 8;
+    uint64_t* kept = reinterpret_cast<uint64_t*>(ptr);      ptr += (size_t)p.W * 8;
+    uint64_t* smask = reinterpret_cast<uint64_t*>(ptr);     // [N64][W] when mask_in_smem
+
+    const float* rois = p.rois + (size_t)img * N * 4;
+    const float* probs = p.probs + (size_t)img * N * NC;
+    const float* deltas = p.deltas + (size_t)img * N * NC * 4;
+    const float* win = p.windows + (size_t)img * 4;
+
+    if (tid == 0) s_count = 0;
+
+    // ---- A. argmax over classes, one warp per RoI (model.py:1407, :1414) ----
+    for (int n = warp; n < N; n += kDetThreads / 32) {
+        const float* row = probs + (size_t)n * NC;
+        float best = -INFINITY;
+        int bi = INT_MAX;
+        for (int j = lane; j < NC; j += 32) {
+            const float v = __ldg(row + j);
+            if (v > best || bi == INT_MAX) {  // the lane's first element initialises (handles -inf rows)
+                best = v;
+                bi = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) {  // first maximum wins ties
+                best = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            rcls[n] = (bi == INT_MAX) ? 0 : bi;
+            rscore[n] = best;
+        }
+    }
+    __syncthreads();
+
+    // ---- B. decode / scale / clip / round / filter, one thread per RoI (model.py:1415-1443) ----
+    const float wy1 = __ldg(win + 0), wx1 = __ldg(win + 1), wy2 = __ldg(win + 2), wx2 = __ldg(win + 3);
+    for (int n = tid; n < p.P; n += kDetThreads) {
+        uint64_t key = 0ull;
+        if (n < N) {
+            const int c = rcls[n];
+            const float sc = rscore[n];
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rois) + n);
+            const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + (size_t)n * NC + c);
+            const float b[4] = {r.x, r.y, r.z, r.w};
+            const float d[4] = {__fmul_rn(dl.x, p.std0), __fmul_rn(dl.y, p.std1), __fmul_rn(dl.z, p.std2),
+                                __fmul_rn(dl.w, p.std3)};
+            float o[4];
+            box_refine(b, d, o);
+            float4 q;
+            q.x = rintf(clampf(__fmul_rn(o[0], p.height), wy1, wy2));  // :1426, :1429, :1432 (half to even)
+            q.y = rintf(clampf(__fmul_rn(o[1], p.width), wx1, wx2));
+            q.z = rintf(clampf(__fmul_rn(o[2], p.height), wy1, wy2));
+            q.w = rintf(clampf(__fmul_rn(o[3], p.width), wx1, wx2));
+            rbox[n] = q;
+            bool keep = c > 0;                                         // :1437
+            if (p.min_conf > 0.0f) keep = keep && (sc >= p.min_conf);  // :1441-1442
+            if (keep) {
+                key = make_sort_key(sc, (uint32_t)n);
+                atomicAdd(&s_count, 1);
+            }
+        }
+        sortbuf[n] = key;
+    }
+    __syncthreads();
+    const int M = s_count;  // RoIs entering NMS
+
+    // ---- C. sort by score (descending; ties -> lower RoI index) and gather ----
+    block_bitonic_desc(sortbuf, p.P, 0u, 2u, 1u, (unsigned)p.P);
+    for (int i = tid; i < M; i += kDetThreads) {
+        const int n = (int)sort_key_index(sortbuf[i]);
+        const float4 b = rbox[n];
+        sbox[i] = b;
+        sarea[i] = box_area_p1(b);
+        scls[i] = rcls[n];
+    }
+    __syncthreads();
+
+    // ---- D. class-aware suppression words, upper triangle ----
+    const int W = (M + 63) >> 6;
+    uint64_t* mask = p.mask_in_smem ? smask : (p.gmask + (size_t)img * p.N64 * p.W);
+    for (int item = tid; item < M * W; item += kDetThreads) {
+        const int row = item / W;
+        const int cb = item - row * W;
+        if (cb < (row >> 6)) continue;
+        const int col0 = cb << 6;
+        const int ncols = min(64, M - col0);
+        mask[(size_t)row * W + cb] =
+            suppression_word<true>(sbox[row], sarea[row], scls[row], row, sbox + col0, sarea + col0, scls + col0, col0, ncols, p.thr);
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- E. greedy sweep; only the first max_inst survivors are needed (:1478-1480) ----
+    SweepSmem sm;
+    sm.stage = nullptr;
+    sm.remv = remv;
+    sm.kept = kept;
+    sm.bars = bars;
+    sm.total = &s_total;
+    block_nms_sweep(mask, M, W, sm, false, p.max_inst);
+
+    // ---- F. emit ----
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < W; ++w) {
+            s_prefix[w] = run;
+            run += __popcll(kept[w]);
+        }
+        s_prefix[W] = run;
+    }
+    __syncthreads();
+    const int D = min(s_prefix[W], p.max_inst);
+    float* out = p.dets_out + (size_t)img * p.max_inst * 6;
+    int32_t* iout = p.index_out ? p.index_out + (size_t)img * p.max_inst : nullptr;
+    for (int i = tid; i < M; i += kDetThreads) {
+        const uint64_t kw = kept[i >> 6];
+        if ((kw >> (i & 63)) & 1ull) {
+            const int r = s_prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+            if (r < p.max_inst) {
+                const float4 b = sbox[i];
+                float* o = out + (size_t)r * 6;
+                o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+                o[4] = sort_key_score(sortbuf[i]);
+                o[5] = (float)scls[i];
+                if (iout) iout[r] = (int32_t)sort_key_index(sortbuf[i]);
+            }
+        }
+    }
+    for (int e = D * 6 + tid; e < p.max_inst * 6; e += kDetThreads) out[e] = 0.f;
+    if (iout)
+        for (int r = D + tid; r < p.max_inst; r += kDetThreads) iout[r] = -1;
+    if (tid == 0) p.counts_out[img] = D;
+}
+
+__global__ void detection_empty_kernel(float* dets, size_t n, int32_t* counts, int32_t* index, int B, int max_inst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dets[i] = 0.f;
+    if (i < (size_t)B) counts[i] = 0;
+    if (index && i < (size_t)B * max_inst) index[i] = -1;
+}
+
+static size_t det_smem_bytes(int N, int P, int W, bool mask_in_smem) {
+    size_t b = (size_t)P * 8 + (size_t)N * (16 + 16 + 4 + 4 + 4 + 4) + (size_t)W * 16;
+    if (mask_in_smem) b += (size_t)(W * 64) * W * 8;
+    return align_up(b, 16);
+}
+
+}  // namespace mrcnn
+
+using namespace mrcnn;
+
+extern "C" {
+
+size_t mrcnn_detection_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= kDetSmemMaskMaxN) return 256;
+    const size_t N64 = align_up((size_t)N, 64);
+    return align_up((size_t)B * N64 * (N64 / 64) * 8, 256);
+}
+
+int mrcnn_detection_layer(const float* rois, const float* probs, const float* deltas, const float* windows, int B, int N,
+                          int NC, float min_confidence, float nms_threshold, int max_inst, const float* std4_host,
+                          float height, float width, float* dets_out, int32_t* counts_out, int32_t* index_out,
+                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRCNN_REQUIRE(B > 0 && N >= 0 && NC > 0 && max_inst > 0, "mrcnn_detection_layer: bad sizes");
+    MRCNN_REQUIRE(N <= kDetMaxN, "mrcnn_detection_layer: N = %d RoIs per image exceeds the supported %d", N, kDetMaxN);
+    MRCNN_REQUIRE(std4_host != nullptr, "mrcnn_detection_layer: std4_host is null");
+    MRCNN_REQUIRE_DEV(dets_out);
+    MRCNN_REQUIRE_DEV(counts_out);
+    if (index_out) MRCNN_REQUIRE_DEV(index_out);
+    if (N == 0) {
+        const size_t n = (size_t)B * max_inst * 6;
+        detection_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dets_out, n, counts_out, index_out, B, max_inst);
+        MRCNN_LAUNCH_CHECK();
+        return MRCNN_OK;
+    }
+    MRCNN_REQUIRE_DEV(rois);
+    MRCNN_REQUIRE_DEV(probs);
+    MRCNN_REQUIRE_DEV(deltas);
+    MRCNN_REQUIRE_DEV(windows);
+    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(rois) & 15u) == 0 && (reinterpret_cast<uintptr_t>(deltas) & 15u) == 0,
+                  "mrcnn_detection_layer: rois and deltas must be 16-byte aligned");
+    DetParams p;
+    p.rois = rois; p.probs = probs; p.deltas = deltas; p.windows = windows;
+    p.B = B; p.N = N; p.NC = NC;
+    p.P = 32;
+    while (p.P < N) p.P <<= 1;
+    p.N64 = (int)align_up((size_t)N, 64);
+    p.W = p.N64 / 64;
+    p.min_conf = min_confidence; p.thr = nms_threshold; p.max_inst = max_inst;
+    p.std0 = std4_host[0]; p.std1 = std4_host[1]; p.std2 = std4_host[2]; p.std3 = std4_host[3];
+    p.height = height; p.width = width;
+    p.dets_out = dets_out; p.counts_out = counts_out; p.index_out = index_out;
+    p.mask_in_smem = N <= kDetSmemMaskMaxN ? 1 : 0;
+    p.gmask = nullptr;
+    if (!p.mask_in_smem) {
+        const size_t need = mrcnn_detection_workspace_bytes(B, N);
+        MRCNN_REQUIRE_DEV(workspace);
+        if (workspace_bytes < need)
+            return fail(MRCNN_E_WORKSPACE, "mrcnn_detection_layer: workspace of %zu bytes < required %zu", workspace_bytes, need);
+        p.gmask = (uint64_t*)workspace;
+    }
+    const size_t smem = det_smem_bytes(N, p.P, p.W, p.mask_in_smem != 0);
+    MRCNN_REQUIRE(smem <= 220 * 1024, "mrcnn_detection_layer: shared memory need %zu exceeds the SM", smem);
+    MRCNN_CUDA(cudaFuncSetAttribute(detection_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    detection_layer_kernel<<<B, kDetThreads, smem, stream>>>(p);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+}  // extern "C"

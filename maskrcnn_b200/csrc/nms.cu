@@ -1,0 +1,274 @@
+// nms.cu — greedy NMS for sm_100a, fully on the device.
+//
+// Replaces c++ext/maskrcnn/csrc/nms.h:15-30 -> cpu/nms_cpu.cpp:11-70 (and cuda/nms_cuda.cu:29-137).
+// Semantics follow the CPU implementation, which is the parity oracle: order = scores descending,
+// suppress iff IoU >= threshold with the (+1) pixel convention, result = ASCENDING original indices.
+//
+// Pipeline (all on `stream`, no host round trip — the reference's CUDA path copies the whole mask to
+// the host and sweeps there):
+//   1. prepare : composite keys (score, index) -> bitonic sort -> boxes/areas gathered in score order
+//   2. mask    : 64x64 tiles of IoU>=thr suppression words, upper triangle only
+//   3. sweep   : one CTA, mask row-blocks streamed through shared memory by bulk async copies,
+//                then an in-CTA prefix scan emits the surviving original indices in ascending order.
+#include <limits.h>
+
+#include "api_util.h"
+#include "nms_core.cuh"
+
+namespace mrcnn {
+
+constexpr int kSortTile = 8192;  // elements sorted per CTA in shared memory (64 KB)
+
+struct NmsWorkspace {
+    uint64_t* sortbuf;  // [P]
+    float4* sbox;       // [N64] boxes in score order
+    float* sarea;       // [N64]
+    int32_t* order;     // [N64] original index of the i-th best box
+    uint64_t* mask;     // [N64][W]
+    uint8_t* flags;     // [N64] survivor flag per ORIGINAL index
+    size_t bytes;
+};
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static NmsWorkspace carve_nms(void* base, int N) {
+    NmsWorkspace w;
+    const size_t N64 = align_up((size_t)(N > 0 ? N : 1), 64);
+    const size_t W = N64 / 64;
+    const size_t P = (size_t)next_pow2(N > 0 ? N : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? (void*)((char*)base + off) : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.sortbuf = (uint64_t*)take(P * 8);
+    w.sbox = (float4*)take(N64 * 16);
+    w.sarea = (float*)take(N64 * 4);
+    w.order = (int32_t*)take(N64 * 4);
+    w.mask = (uint64_t*)take(N64 * W * 8);
+    w.flags = (uint8_t*)take(N64);
+    w.bytes = off;
+    return w;
+}
+
+// ---- 1. prepare ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ void gather_sorted(const float* dets, uint64_t key, int i, float4* sbox, float* sarea,
+                                              int32_t* order) {
+    const uint32_t src = sort_key_index(key);
+    const float* d = dets + (size_t)src * 5;
+    const float4 b = make_float4(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3));
+    sbox[i] = b;
+    sarea[i] = box_area_p1(b);
+    order[i] = (int32_t)src;
+}
+
+// N <= kSortTile: keys, sort and gather in one CTA.
+__global__ void __launch_bounds__(1024) nms_prepare_small_kernel(const float* __restrict__ dets, int N, int P, float4* sbox,
+                                                                 float* sarea, int32_t* order) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        skeys[i] = (i < N) ? make_sort_key(__ldg(dets + (size_t)i * 5 + 4), (uint32_t)i) : 0ull;
+    __syncthreads();
+    block_bitonic_desc(skeys, P, 0u, 2u, 1u, (unsigned)P);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) gather_sorted(dets, skeys[i], i, sbox, sarea, order);
+}
+
+// N > kSortTile: multi-CTA bitonic network over a global key buffer.
+__global__ void nms_fill_keys_kernel(const float* __restrict__ dets, int N, int P, uint64_t* keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) keys[i] = (i < N) ? make_sort_key(__ldg(dets + (size_t)i * 5 + 4), (uint32_t)i) : 0ull;
+}
+
+// sorts each tile completely (k = 2..tile), direction taken from the global index
+__global__ void __launch_bounds__(1024) bitonic_tile_sort_kernel(uint64_t* keys) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    uint64_t* g = keys + (size_t)blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) skeys[i] = g[i];
+    __syncthreads();
+    block_bitonic_desc(skeys, kSortTile, blockIdx.x * (unsigned)kSortTile, 2u, 1u, (unsigned)kSortTile);
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) g[i] = skeys[i];
+}
+
+// one compare-exchange stage (j >= tile) of merge size k over the global buffer
+__global__ void bitonic_global_step_kernel(uint64_t* keys, unsigned P, unsigned j, unsigned k) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (P >> 1)) return;
+    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const unsigned l = i | j;
+    const bool desc = ((i & k) == 0);
+    const uint64_t a = keys[i], b = keys[l];
+    if ((a < b) == desc && a != b) {
+        keys[i] = b;
+        keys[l] = a;
+    }
+}
+
+// finishes merge size k inside each tile (j = tile/2 .. 1)
+__global__ void __launch_bounds__(1024) bitonic_tile_merge_kernel(uint64_t* keys, unsigned k) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    uint64_t* g = keys + (size_t)blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) skeys[i] = g[i];
+    __syncthreads();
+    block_bitonic_desc(skeys, kSortTile, blockIdx.x * (unsigned)kSortTile, k, (unsigned)kSortTile >> 1, k);
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) g[i] = skeys[i];
+}
+
+__global__ void nms_gather_kernel(const float* __restrict__ dets, const uint64_t* __restrict__ keys, int N, float4* sbox,
+                                  float* sarea, int32_t* order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) gather_sorted(dets, keys[i], i, sbox, sarea, order);
+}
+
+// ---- 2. mask ------------------------------------------------------------------------------------
+
+// grid = (W, W) (column block, row block), block = 64 threads = the 64 row boxes of the tile.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
+                                                      int W, float thr, uint64_t* __restrict__ mask) {
+    const int cb = blockIdx.x, rb = blockIdx.y;
+    if (cb < rb) return;  // lower triangle is never read
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const int t = threadIdx.x;
+    const int col0 = cb * 64;
+    const int ncols = min(64, N - col0);
+    if (t < ncols) {
+        cbox[t] = sbox[col0 + t];
+        carea[t] = sarea[col0 + t];
+    }
+    __syncthreads();
+    const int row = rb * 64 + t;
+    if (row >= N) return;
+    const uint64_t w = suppression_word<false>(sbox[row], sarea[row], 0, row, cbox, carea, nullptr, col0, ncols, thr);
+    mask[(size_t)row * W + cb] = w;
+}
+
+// ---- 3. sweep + ascending emit ------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024) nms_sweep_kernel(const uint64_t* __restrict__ mask, const int32_t* __restrict__ order,
+                                                         int N, int W, int staged, uint8_t* __restrict__ flags,
+                                                         int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
+    extern __shared__ __align__(16) uint64_t sm_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ int s_total;
+    __shared__ int s_warp_sums[32];
+    SweepSmem sm;
+    sm.stage = sm_raw;  // [2*64*W] when staged
+    sm.remv = sm_raw + (staged ? (size_t)2 * 64 * W : 0);
+    sm.kept = sm.remv + W;
+    sm.bars = bars;
+    sm.total = &s_total;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < N; i += nt) flags[i] = 0;
+    block_nms_sweep(mask, N, W, sm, staged != 0, INT_MAX);
+    // survivors (score order) -> flags by original index
+    for (int i = tid; i < N; i += nt)
+        if ((sm.kept[i >> 6] >> (i & 63)) & 1ull) flags[order[i]] = 1;
+    __syncthreads();
+    // ascending compaction: thread t owns the contiguous range [t*per, (t+1)*per)
+    const int per = (N + nt - 1) / nt;
+    const int beg = min(N, tid * per), end = min(N, beg + per);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) cnt += flags[i];
+    int incl = cnt;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = (lane < (nt >> 5)) ? s_warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        s_warp_sums[lane] = v;  // inclusive over warps
+    }
+    __syncthreads();
+    int pos = incl - cnt + (warp > 0 ? s_warp_sums[warp - 1] : 0);
+    for (int i = beg; i < end; ++i)
+        if (flags[i]) keep_out[pos++] = (int64_t)i;
+    if (tid == nt - 1) *count_out = pos;  // the last thread's end position is the total
+}
+
+__global__ void nms_empty_kernel(int32_t* count_out) { *count_out = 0; }
+
+static size_t sweep_smem_bytes(int W, bool staged) {
+    return (size_t)8 * ((staged ? (size_t)2 * 64 * W : 0) + 2 * (size_t)W);
+}
+
+}  // namespace mrcnn
+
+using namespace mrcnn;
+
+extern "C" {
+
+size_t mrcnn_nms_workspace_bytes(int N) { return carve_nms(nullptr, N).bytes; }
+
+int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int32_t* count_out, void* workspace,
+              size_t workspace_bytes, mrcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRCNN_REQUIRE(N >= 0, "mrcnn_nms: N must be >= 0");
+    MRCNN_REQUIRE(N <= (1 << 17), "mrcnn_nms: N = %d exceeds the supported maximum of 131072 boxes", N);
+    MRCNN_REQUIRE_DEV(count_out);
+    if (N == 0) {  // nms_cpu.cpp:16-18
+        nms_empty_kernel<<<1, 1, 0, stream>>>(count_out);
+        MRCNN_LAUNCH_CHECK();
+        return MRCNN_OK;
+    }
+    MRCNN_REQUIRE_DEV(dets);
+    MRCNN_REQUIRE_DEV(keep_out);
+    MRCNN_REQUIRE_DEV(workspace);
+    const NmsWorkspace ws = carve_nms(workspace, N);
+    if (workspace_bytes < ws.bytes)
+        return fail(MRCNN_E_WORKSPACE, "mrcnn_nms: workspace of %zu bytes < required %zu", workspace_bytes, ws.bytes);
+    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "mrcnn_nms: workspace must be 256-byte aligned");
+    const int P = next_pow2(N);
+    const int W = (N + 63) / 64;
+
+    if (P <= kSortTile) {
+        const size_t smem = (size_t)P * 8;
+        MRCNN_CUDA(cudaFuncSetAttribute(nms_prepare_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8));
+        const int threads = P >= 2048 ? 1024 : (P >= 64 ? P / 2 : 32);
+        nms_prepare_small_kernel<<<1, threads, smem, stream>>>(dets, N, P, ws.sbox, ws.sarea, ws.order);
+        MRCNN_LAUNCH_CHECK();
+    } else {
+        const size_t smem = (size_t)kSortTile * 8;
+        MRCNN_CUDA(cudaFuncSetAttribute(bitonic_tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MRCNN_CUDA(cudaFuncSetAttribute(bitonic_tile_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_fill_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(dets, N, P, ws.sortbuf);
+        const int tiles = P / kSortTile;
+        bitonic_tile_sort_kernel<<<tiles, 1024, smem, stream>>>(ws.sortbuf);
+        for (unsigned k = 2u * kSortTile; k <= (unsigned)P; k <<= 1) {
+            for (unsigned j = k >> 1; j >= (unsigned)kSortTile; j >>= 1)
+                bitonic_global_step_kernel<<<(P / 2 + 255) / 256, 256, 0, stream>>>(ws.sortbuf, (unsigned)P, j, k);
+            bitonic_tile_merge_kernel<<<tiles, 1024, smem, stream>>>(ws.sortbuf, k);
+        }
+        nms_gather_kernel<<<(N + 255) / 256, 256, 0, stream>>>(dets, ws.sortbuf, N, ws.sbox, ws.sarea, ws.order);
+        MRCNN_LAUNCH_CHECK();
+    }
+
+    nms_mask_kernel<<<dim3(W, W), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask);
+    MRCNN_LAUNCH_CHECK();
+
+    const bool staged = W <= kSweepStageMaxW;
+    const size_t smem = sweep_smem_bytes(W, staged);
+    MRCNN_REQUIRE(smem <= 220 * 1024, "mrcnn_nms: N too large for the single-CTA sweep");
+    MRCNN_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int threads = (W + 31) / 32 * 32;
+    threads = threads < 128 ? 128 : (threads > 1024 ? 1024 : threads);
+    nms_sweep_kernel<<<1, threads, smem, stream>>>(ws.mask, ws.order, N, W, staged ? 1 : 0, ws.flags, keep_out, count_out);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// nms_core.cuh — building blocks shared by nms.cu, proposal.cu and detection.cu:
+//   * block-wide bitonic sort of 64-bit composite keys (score key << 32 | ~index) in shared memory,
+//   * the 64x64 IoU suppression-word tile (upper triangle only),
+//   * the sequential greedy sweep over suppression words, run by ONE CTA entirely on the device
+//     (the reference copies the N x N/64 mask to the host and sweeps on the CPU, nms_cuda.cu:107-131).
+//     Row blocks of the mask are streamed into shared memory with 1-D bulk async copies (TMA,
+//     cp.async.bulk + mbarrier), double-buffered, so the sweep never waits on L2 latency.
+#pragma once
+#include "common.cuh"
+
+namespace mrcnn {
+
+// ---------------------------------------------------------------------------------------------
+// composite sort key: larger score first, ties -> smaller index first (a stable descending sort)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_sort_key(float score, uint32_t idx) {
+    return ((uint64_t)float_to_key(score) << 32) | (uint64_t)(0xffffffffu - idx);
+}
+__device__ __forceinline__ uint32_t sort_key_index(uint64_t k) { return 0xffffffffu - (uint32_t)(k & 0xffffffffu); }
+__device__ __forceinline__ float sort_key_score(uint64_t k) { return key_to_float((uint32_t)(k >> 32)); }
+
+// Sorts s[0..P) (P a power of two) descending.  `gbase` is the global index of s[0] when the tile is
+// part of a larger bitonic network (direction bit taken from the global index); stages k in
+// [k_first, k_last], and for k == k_first only j <= j_first (used by the multi-tile merge).
+__device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P, unsigned gbase, unsigned k_first,
+                                                   unsigned j_first, unsigned k_last) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (unsigned k = k_first; k <= k_last; k <<= 1) {
+        for (unsigned j = (k == k_first) ? j_first : (k >> 1); j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nt) {
+                const unsigned i = (((unsigned)t & ~(j - 1)) << 1) | ((unsigned)t & (j - 1));
+                const unsigned l = i | j;
+                const bool desc = (((gbase + i) & k) == 0);
+                const uint64_t a = s[i], b = s[l];
+                if ((a < b) == desc && a != b) {
+                    s[i] = b;
+                    s[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// suppression word: bit c set iff box (col0 + c) is suppressed by `rowbox` (IoU >= thr) and comes
+// later in the order (col index > row index).  Column boxes/areas are read from shared memory.
+// `same_class` optionally restricts suppression to equal class ids (detection layer).
+// ---------------------------------------------------------------------------------------------
+template <bool kClassAware>
+__device__ __forceinline__ uint64_t suppression_word(const float4 rowbox, float rowarea, int rowcls, int row,
+                                                     const float4* cbox, const float* carea, const int* ccls,
+                                                     int col0, int ncols, float thr) {
+    uint64_t w = 0;
+    const int start = (row >= col0) ? (row - col0 + 1) : 0;
+    for (int c = start; c < ncols; ++c) {
+        bool s = iou_ge(rowbox, rowarea, cbox[c], carea[c], thr);
+        if (kClassAware) s = s && (ccls[c] == rowcls);
+        if (s) w |= (1ull << c);
+    }
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Greedy sweep.  mask: [rows padded to 64][W] suppression words in GLOBAL memory (only words at or
+// right of the diagonal are meaningful).  n boxes in score order, W = ceil(n/64).
+// Shared memory supplied by the caller:
+//   remv  [W] words   — suppressed-so-far bitmap (working state)
+//   kept  [W] words   — OUT: bit set = box survives
+//   stage 2 * 64 * W words (16 B aligned) if `staged`, else unused
+//   bars  2 mbarriers
+// Stops early once max_keep survivors are found (later words of kept[] are zero).
+// Returns the number of survivors found (>= max_keep possible by up to 63).  All threads must call.
+// ---------------------------------------------------------------------------------------------
+struct SweepSmem {
+    uint64_t* remv;
+    uint64_t* kept;
+    uint64_t* stage;
+    uint64_t* bars;
+    int* total;  // one int
+};
+
+__device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int W, const SweepSmem sm,
+                                               bool staged, int max_keep) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int w = tid; w < W; w += nt) {
+        sm.remv[w] = 0;
+        sm.kept[w] = 0;
+    }
+    const uint32_t block_bytes = (uint32_t)(64u * (unsigned)W * 8u);
+    if (tid == 0) {
+        *sm.total = 0;
+        if (staged) {
+            mbar_init(&sm.bars[0], 1);
+            mbar_init(&sm.bars[1], 1);
+            fence_barrier_init();
+        }
+    }
+    __syncthreads();
+    if (staged && tid == 0 && W > 0) {
+        mbar_expect_tx(&sm.bars[0], block_bytes);
+        bulk_g2s(sm.stage, mask, block_bytes, &sm.bars[0]);
+    }
+    int total = 0;
+    for (int c = 0; c < W; ++c) {
+        const uint64_t* rows;  // 64 rows x W words of chunk c
+        if (staged) {
+            const int buf = c & 1;
+            if (tid == 0 && c + 1 < W) {  // prefetch the next row block into the other buffer
+                fence_proxy_async();
+                mbar_expect_tx(&sm.bars[buf ^ 1], block_bytes);
+                bulk_g2s(sm.stage + (size_t)(buf ^ 1) * 64 * W, mask + (size_t)(c + 1) * 64 * W, block_bytes,
+                         &sm.bars[buf ^ 1]);
+            }
+            mbar_wait(&sm.bars[buf], (uint32_t)((c >> 1) & 1));
+            rows = sm.stage + (size_t)buf * 64 * W;
+        } else {
+            rows = mask + (size_t)c * 64 * W;
+        }
+        // --- resolve the 64 boxes of this chunk against each other (warp 0, all lanes redundantly) ---
+        if (tid < 32) {
+            const int nrows = min(64, n - c * 64);
+            const uint64_t d_lo = (tid < nrows) ? rows[(size_t)tid * W + c] : 0ull;
+            const uint64_t d_hi = (tid + 32 < nrows) ? rows[(size_t)(tid + 32) * W + c] : 0ull;
+            uint64_t alive = ~sm.remv[c];
+            if (nrows < 64) alive &= ((1ull << nrows) - 1ull);
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const uint64_t d = __shfl_sync(0xffffffffu, d_lo, l);
+                if ((alive >> l) & 1ull) alive &= ~d;
+            }
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const uint64_t d = __shfl_sync(0xffffffffu, d_hi, l);
+                if ((alive >> (l + 32)) & 1ull) alive &= ~d;
+            }
+            if (tid == 0) {
+                sm.kept[c] = alive;
+                *sm.total += __popcll(alive);
+            }
+        }
+        __syncthreads();
+        const uint64_t kept = sm.kept[c];
+        total = *sm.total;
+        if (total >= max_keep) {
+            // never leave a bulk copy in flight behind us: drain the prefetch of chunk c + 1
+            if (staged && c + 1 < W) mbar_wait(&sm.bars[(c + 1) & 1], (uint32_t)(((c + 1) >> 1) & 1));
+            break;
+        }
+        // --- propagate: every later word ORs in the rows of the survivors of this chunk ---
+        for (int w = c + 1 + tid; w < W; w += nt) {
+            uint64_t acc = 0;
+            uint64_t k = kept;
+            while (k) {
+                const int r = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                acc |= rows[(size_t)r * W + w];
+            }
+            sm.remv[w] |= acc;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    return total;
+}
+
+// Largest W for which the double-buffered staging (2 * 64 * W * 8 bytes) fits next to the rest.
+constexpr int kSweepStageMaxW = 160;  // 160 KB of staging
+
+}  // namespace mrcnn

@@ -1,0 +1,453 @@
+// proposal.cu — the RPN proposal layer for sm_100a, batched over images.
+//
+// Replaces MaskRCNN.rpn_refine (model.py:1307-1382) + data.boxes_scale/refine/clamp_ (data.py:86-148):
+//   fg score -> top pre_nms (the reference full-sorts all 261,888 anchors, :1346) -> decode -> clip
+//   -> NMS(thr) -> first post_nms -> normalise.
+//
+// Three launches per batch, no host synchronisation:
+//   1. proposal_select_kernel : one 8-CTA thread-block CLUSTER per image.  Each CTA stages its 1/8 of the
+//      fg-score keys in shared memory ONCE (the only HBM pass over rpn_class), then a 4-pass 8-bit radix
+//      SELECT finds the exact k-th key; per-pass 256-bin histograms are combined across the cluster
+//      through distributed shared memory.  Survivors are compacted, rank 0 bitonic-sorts the <= 8192
+//      winners, gathers their anchors/deltas, decodes (fp64 exp, correctly rounded) and clips.
+//   2. proposal_mask_kernel   : upper-triangular IoU>=thr suppression words, all images in one grid.
+//   3. proposal_sweep_kernel  : one CTA per image: TMA-staged greedy sweep with early exit at post_nms,
+//      emits normalised RoIs (zero padded) + counts.
+#include <cooperative_groups.h>
+
+#include "api_util.h"
+#include "nms_core.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mrcnn {
+
+constexpr int kClusterSize = 8;
+constexpr int kSelThreads = 1024;
+constexpr int kMaxPreNms = 8192;
+
+struct ProposalParams {
+    const float* rpn_class;  // [B,A,2]
+    const float* rpn_bbox;   // [B,A,4]
+    const float* anchors;    // [A,4]
+    int B, A;
+    int pre;   // min(pre_nms, A)
+    int P;     // next pow2 >= pre
+    int per;   // anchors per CTA = ceil(A / 8)
+    int staged;
+    float std0, std1, std2, std3;
+    float height, width;
+    // workspace
+    uint64_t* cand;   // [B][P]
+    float4* sbox;     // [B][pre64]
+    float* sarea;     // [B][pre64]
+    float* sscore;    // [B][pre64]
+    int32_t* sorder;  // [B][pre64] anchor index
+    int pre64;
+};
+
+struct ProposalWorkspace {
+    uint64_t* cand;
+    float4* sbox;
+    float* sarea;
+    float* sscore;
+    int32_t* sorder;
+    uint64_t* mask;  // [B][pre64][W]
+    size_t bytes;
+};
+
+static int next_pow2_i(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static ProposalWorkspace carve_proposal(void* base, int B, int A, int pre_nms) {
+    ProposalWorkspace w;
+    const int pre = pre_nms < A ? pre_nms : A;
+    const size_t pre64 = align_up((size_t)(pre > 0 ? pre : 1), 64);
+    const size_t W = pre64 / 64;
+    const size_t P = (size_t)next_pow2_i(pre > 0 ? pre : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? (void*)((char*)base + off) : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.cand = (uint64_t*)take((size_t)B * P * 8);
+    w.sbox = (float4*)take((size_t)B * pre64 * 16);
+    w.sarea = (float*)take((size_t)B * pre64 * 4);
+    w.sscore = (float*)take((size_t)B * pre64 * 4);
+    w.sorder = (int32_t*)take((size_t)B * pre64 * 4);
+    w.mask = (uint64_t*)take((size_t)B * pre64 * W * 8);
+    w.bytes = off;
+    return w;
+}
+
+// ---- 1. select + sort + decode --------------------------------------------------------------------
+
+struct SelShared {
+    int hist[256];
+    int tot[256];
+    int loc_above[256];  // # local keys (matching the prefix) with a digit greater than d
+    int warp_sums[32];
+    int base;      // output offset of this CTA in the candidate list
+    int eq_take;   // how many of this CTA's == T keys are selected
+    int digit;
+    int above;
+    int gt_local;  // published: # keys > T in this CTA
+    int eq_local;  // published: # keys == T in this CTA
+    int counter;   // local compaction cursor
+};
+
+__global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const ProposalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SelShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int img = blockIdx.x / kClusterSize;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);
+    const int lo = min(p.A, rank * p.per);
+    const int hi = min(p.A, lo + p.per);
+    const int n_local = hi - lo;
+    const float* scores = p.rpn_class + ((size_t)img * p.A + lo) * 2 + 1;  // fg prob, model.py:1336
+
+    auto key_at = [&](int i) -> uint32_t { return p.staged ? keys[i] : float_to_key(__ldg(scores + (size_t)i * 2)); };
+
+    if (p.staged) {
+        const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
+        for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(s2 + i).y);
+    }
+    if (tid == 0) sh.gt_local = 0;
+    __syncthreads();
+
+    // ---- radix select: 4 passes of 8 bits, most significant first ----
+    uint32_t prefix = 0;
+    int k_rem = p.pre;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += kSelThreads) sh.hist[i] = 0;
+        __syncthreads();
+        const int iters = (n_local + kSelThreads - 1) / kSelThreads;
+        for (int it = 0; it < iters; ++it) {
+            const int i = it * kSelThreads + tid;
+            uint32_t key = 0;
+            bool in = false;
+            if (i < n_local) {
+                key = key_at(i);
+                in = (pass == 0) || ((key >> (shift + 8)) == prefix);
+            }
+            const unsigned digit = (key >> shift) & 255u;
+            // warp-aggregated histogram update: one shared-memory atomic per distinct digit in the warp
+            const unsigned active = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(active, digit);
+                if (lane == (__ffs(peers) - 1)) atomicAdd(&sh.hist[digit], __popc(peers));
+            }
+        }
+        cluster.sync();  // every CTA's histogram of this pass is complete and visible
+        if (tid < 256) {
+            int s = 0;
+#pragma unroll
+            for (int r = 0; r < kClusterSize; ++r) s += *cluster.map_shared_rank(&sh.hist[tid], r);
+            sh.tot[tid] = s;
+        }
+        __syncthreads();
+        // suffix sums S(d) = sum_{x >= d} v[x]: warps 0-7 scan the cluster totals and choose d with
+        // S(d) >= k_rem > S(d+1); warps 8-15 scan this CTA's own histogram (its share of the keys above d).
+        if (tid < 512) {
+            const int half = tid >> 8;     // 0: totals, 1: local
+            const int t = tid & 255;
+            const int d = 255 - t;         // thread order = descending digit, so a prefix scan is a suffix sum
+            const int v = half ? sh.hist[d] : sh.tot[d];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) sh.warp_sums[tid >> 5] = incl;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            int wb = 0;
+            for (int w = half * 8; w < (tid >> 5); ++w) wb += sh.warp_sums[w];
+            incl += wb;                 // = S(d)
+            const int excl = incl - v;  // = S(d+1)
+            if (half) {
+                sh.loc_above[d] = excl;
+            } else if (incl >= k_rem && excl < k_rem) {
+                sh.digit = d;
+                sh.above = excl;
+            }
+        }
+        __syncthreads();
+        const int d = sh.digit;
+        if (tid == 0) {
+            sh.gt_local += sh.loc_above[d];
+            if (pass == 3) sh.eq_local = sh.hist[d];
+        }
+        k_rem -= sh.above;
+        prefix = (prefix << 8) | (uint32_t)d;
+        cluster.sync();  // all remote reads of hist done before it is cleared / gt,eq published
+    }
+    const uint32_t T = prefix;  // the k-th largest key; k_rem (>= 1) keys equal to T are still needed
+
+    // ---- output offsets: ranks in order, keys > T first then this rank's share of the == T keys ----
+    if (tid == 0) {
+        int b = 0, eq_before = 0;
+        for (int r = 0; r < rank; ++r) {
+            const int g = *cluster.map_shared_rank(&sh.gt_local, r);
+            const int e = *cluster.map_shared_rank(&sh.eq_local, r);
+            b += g + max(0, min(e, k_rem - eq_before));
+            eq_before += e;
+        }
+        sh.base = b;
+        sh.eq_take = max(0, min(sh.eq_local, k_rem - eq_before));
+        sh.counter = 0;
+    }
+    __syncthreads();
+    const int base = sh.base;
+    const int eq_take = sh.eq_take;
+    const bool eq_all = (eq_take == sh.eq_local);
+
+    uint64_t* cand = p.cand + (size_t)img * p.P;
+    {
+        const int iters = (n_local + kSelThreads - 1) / kSelThreads;
+        for (int it = 0; it < iters; ++it) {
+            const int i = it * kSelThreads + tid;
+            bool sel = false;
+            uint32_t key = 0;
+            if (i < n_local) {
+                key = key_at(i);
+                sel = (key > T) || (eq_all && key == T);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, sel);
+            if (m) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&sh.counter, __popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (sel) {
+                    const int pos = base + wbase + __popc(m & ((1u << lane) - 1u));
+                    cand[pos] = ((uint64_t)key << 32) | (uint64_t)(0xffffffffu - (uint32_t)(lo + i));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!eq_all && eq_take > 0 && tid < 32) {
+        // partial share of the tied keys: the eq_take ones with the smallest anchor index, in order
+        int taken = 0;
+        const int start = base + sh.counter;
+        for (int i0 = 0; i0 < n_local && taken < eq_take; i0 += 32) {
+            const int i = i0 + lane;
+            const bool e = (i < n_local) && (key_at(i) == T);
+            const unsigned m = __ballot_sync(0xffffffffu, e);
+            const int my = taken + __popc(m & ((1u << lane) - 1u));
+            if (e && my < eq_take) cand[start + my] = ((uint64_t)T << 32) | (uint64_t)(0xffffffffu - (uint32_t)(lo + i));
+            taken += __popc(m);
+        }
+    }
+    cluster.sync();  // all candidates of this image are in global memory
+    if (rank != 0) return;
+
+    // ---- rank 0: sort the winners, decode and clip ----
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(smem_raw);  // the key staging area is free now
+    for (int i = tid; i < p.P; i += kSelThreads) sortbuf[i] = (i < p.pre) ? cand[i] : 0ull;
+    __syncthreads();
+    block_bitonic_desc(sortbuf, p.P, 0u, 2u, 1u, (unsigned)p.P);
+    float4* sbox = p.sbox + (size_t)img * p.pre64;
+    float* sarea = p.sarea + (size_t)img * p.pre64;
+    float* sscore = p.sscore + (size_t)img * p.pre64;
+    int32_t* sorder = p.sorder + (size_t)img * p.pre64;
+    for (int i = tid; i < p.pre; i += kSelThreads) {
+        const uint64_t kv = sortbuf[i];
+        const uint32_t a = sort_key_index(kv);
+        const float4 an = __ldg(reinterpret_cast<const float4*>(p.anchors) + a);
+        const float4 dl = __ldg(reinterpret_cast<const float4*>(p.rpn_bbox) + (size_t)img * p.A + a);
+        const float b[4] = {an.x, an.y, an.z, an.w};
+        const float d[4] = {__fmul_rn(dl.x, p.std0), __fmul_rn(dl.y, p.std1), __fmul_rn(dl.z, p.std2),
+                            __fmul_rn(dl.w, p.std3)};  // model.py:1341
+        float o[4];
+        box_refine(b, d, o);  // model.py:1354
+        float4 r;
+        r.x = clampf(o[0], 0.0f, p.height);  // model.py:1358
+        r.y = clampf(o[1], 0.0f, p.width);
+        r.z = clampf(o[2], 0.0f, p.height);
+        r.w = clampf(o[3], 0.0f, p.width);
+        sbox[i] = r;
+        sarea[i] = box_area_p1(r);
+        sscore[i] = sort_key_score(kv);
+        sorder[i] = (int32_t)a;
+    }
+}
+
+// ---- 2. mask (batched) -----------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(64) proposal_mask_kernel(const float4* __restrict__ sbox_all,
+                                                           const float* __restrict__ sarea_all, int n, int pre64, int W,
+                                                           float thr, uint64_t* __restrict__ mask_all) {
+    const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z;
+    if (cb < rb) return;
+    const float4* sbox = sbox_all + (size_t)img * pre64;
+    const float* sarea = sarea_all + (size_t)img * pre64;
+    uint64_t* mask = mask_all + (size_t)img * pre64 * W;
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const int t = threadIdx.x;
+    const int col0 = cb * 64;
+    const int ncols = min(64, n - col0);
+    if (t < ncols) {
+        cbox[t] = sbox[col0 + t];
+        carea[t] = sarea[col0 + t];
+    }
+    __syncthreads();
+    const int row = rb * 64 + t;
+    if (row >= n) return;
+    mask[(size_t)row * W + cb] = suppression_word<false>(sbox[row], sarea[row], 0, row, cbox, carea, nullptr, col0, ncols, thr);
+}
+
+// ---- 3. sweep + emit -------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024) proposal_sweep_kernel(const uint64_t* __restrict__ mask_all,
+                                                              const float4* __restrict__ sbox_all, int n, int pre64, int W,
+                                                              int staged, int post, float height, float width,
+                                                              float* __restrict__ rois_out, int32_t* __restrict__ counts_out) {
+    extern __shared__ __align__(16) uint64_t sm_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ int s_total;
+    __shared__ int s_prefix[kMaxPreNms / 64 + 1];
+    const int img = blockIdx.x;
+    const uint64_t* mask = mask_all + (size_t)img * pre64 * W;
+    const float4* sbox = sbox_all + (size_t)img * pre64;
+    float* rois = rois_out + (size_t)img * post * 4;
+    SweepSmem sm;
+    sm.stage = sm_raw;
+    sm.remv = sm_raw + (staged ? (size_t)2 * 64 * W : 0);
+    sm.kept = sm.remv + W;
+    sm.bars = bars;
+    sm.total = &s_total;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    block_nms_sweep(mask, n, W, sm, staged != 0, post);
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < W; ++w) {
+            s_prefix[w] = run;
+            run += __popcll(sm.kept[w]);
+        }
+        s_prefix[W] = run;
+    }
+    __syncthreads();
+    const int total = min(s_prefix[W], post);  // model.py:1366 keep[:proposal_count]
+    for (int i = tid; i < n; i += nt) {
+        const uint64_t kw = sm.kept[i >> 6];
+        if ((kw >> (i & 63)) & 1ull) {
+            const int r = s_prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+            if (r < post) {
+                const float4 b = sbox[i];
+                float4 o;  // model.py:1371-1374 boxes / [h, w, h, w]
+                o.x = __fdiv_rn(b.x, height);
+                o.y = __fdiv_rn(b.y, width);
+                o.z = __fdiv_rn(b.z, height);
+                o.w = __fdiv_rn(b.w, width);
+                reinterpret_cast<float4*>(rois)[r] = o;
+            }
+        }
+    }
+    for (int r = total + tid; r < post; r += nt) reinterpret_cast<float4*>(rois)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) counts_out[img] = total;
+}
+
+__global__ void proposal_empty_kernel(float* rois, size_t n, int32_t* counts, int B) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rois[i] = 0.f;
+    if (i < (size_t)B) counts[i] = 0;
+}
+
+}  // namespace mrcnn
+
+using namespace mrcnn;
+
+extern "C" {
+
+size_t mrcnn_proposal_workspace_bytes(int B, int A, int pre_nms) {
+    if (B <= 0 || A <= 0 || pre_nms <= 0) return 256;
+    return carve_proposal(nullptr, B, A, pre_nms).bytes;
+}
+
+int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors, int B, int A, int pre_nms,
+                         int post_nms, float nms_threshold, const float* std4_host, float height, float width,
+                         float* rois_out, int32_t* counts_out, void* workspace, size_t workspace_bytes,
+                         mrcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRCNN_REQUIRE(B > 0 && A >= 0 && pre_nms >= 0 && post_nms > 0, "mrcnn_proposal_layer: bad sizes");
+    MRCNN_REQUIRE(std4_host != nullptr, "mrcnn_proposal_layer: std4_host is null");
+    MRCNN_REQUIRE_DEV(rois_out);
+    MRCNN_REQUIRE_DEV(counts_out);
+    const int pre = pre_nms < A ? pre_nms : A;  // model.py:1345
+    if (pre == 0) {
+        const size_t n = (size_t)B * post_nms * 4;
+        proposal_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rois_out, n, counts_out, B);
+        MRCNN_LAUNCH_CHECK();
+        return MRCNN_OK;
+    }
+    MRCNN_REQUIRE(pre <= kMaxPreNms, "mrcnn_proposal_layer: pre_nms limit %d exceeds the supported %d", pre, kMaxPreNms);
+    MRCNN_REQUIRE_DEV(rpn_class);
+    MRCNN_REQUIRE_DEV(rpn_bbox);
+    MRCNN_REQUIRE_DEV(anchors);
+    MRCNN_REQUIRE_DEV(workspace);
+    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "mrcnn_proposal_layer: workspace must be 256-byte aligned");
+    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(rpn_class) & 7u) == 0 && (reinterpret_cast<uintptr_t>(rpn_bbox) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(anchors) & 15u) == 0 && (reinterpret_cast<uintptr_t>(rois_out) & 15u) == 0,
+                  "mrcnn_proposal_layer: rpn_class/rpn_bbox/anchors/rois_out must be 8/16/16/16-byte aligned");
+    const ProposalWorkspace ws = carve_proposal(workspace, B, A, pre_nms);
+    if (workspace_bytes < ws.bytes)
+        return fail(MRCNN_E_WORKSPACE, "mrcnn_proposal_layer: workspace of %zu bytes < required %zu", workspace_bytes, ws.bytes);
+
+    ProposalParams p;
+    p.rpn_class = rpn_class; p.rpn_bbox = rpn_bbox; p.anchors = anchors;
+    p.B = B; p.A = A; p.pre = pre; p.P = next_pow2_i(pre);
+    p.per = (A + kClusterSize - 1) / kClusterSize;
+    p.std0 = std4_host[0]; p.std1 = std4_host[1]; p.std2 = std4_host[2]; p.std3 = std4_host[3];
+    p.height = height; p.width = width;
+    p.cand = ws.cand; p.sbox = ws.sbox; p.sarea = ws.sarea; p.sscore = ws.sscore; p.sorder = ws.sorder;
+    p.pre64 = (int)align_up((size_t)pre, 64);
+    const size_t sort_bytes = (size_t)p.P * 8;
+    const size_t key_bytes = (size_t)p.per * 4;
+    // (A*2) % 2 == 0 always; float2 loads need the per-CTA start ((img*A + lo)*2 floats) 8-byte aligned: true.
+    p.staged = key_bytes <= 200 * 1024 ? 1 : 0;
+    size_t smem = p.staged ? (key_bytes > sort_bytes ? key_bytes : sort_bytes) : sort_bytes;
+    smem = align_up(smem, 16);
+
+    MRCNN_CUDA(cudaFuncSetAttribute(proposal_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kClusterSize * B);
+    cfg.blockDim = dim3(kSelThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MRCNN_CUDA(cudaLaunchKernelEx(&cfg, proposal_select_kernel, p));
+
+    const int W = p.pre64 / 64;
+    proposal_mask_kernel<<<dim3(W, W, B), 64, 0, stream>>>(ws.sbox, ws.sarea, pre, p.pre64, W, nms_threshold, ws.mask);
+    MRCNN_LAUNCH_CHECK();
+
+    const bool staged = W <= kSweepStageMaxW;
+    const size_t smem2 = (size_t)8 * ((staged ? (size_t)2 * 64 * W : 0) + 2 * (size_t)W);
+    MRCNN_CUDA(cudaFuncSetAttribute(proposal_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int threads = (W + 31) / 32 * 32;
+    threads = threads < 256 ? 256 : (threads > 1024 ? 1024 : threads);
+    proposal_sweep_kernel<<<B, threads, smem2, stream>>>(ws.mask, ws.sbox, pre, p.pre64, W, staged ? 1 : 0, post_nms, height,
+                                                         width, rois_out, counts_out);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,578 @@
+// roialign.cu — crop_and_resize / PyramidROIAlign forward and scatter-add backward for sm_100a.
+//
+// Replaces (reference, /root/reference):
+//   c++ext/maskrcnn/csrc/cpu/crop_cpu.cpp:13-164 / cuda/crop_cuda.cu:17-88     crop forward
+//   c++ext/maskrcnn/csrc/cpu/crop_cpu.cpp:167-265 / cuda/crop_cuda.cu:90-170   crop backward
+//   model.py:276-393 roi_align (level assignment + 4 per-level crops + cat/sort/gather) and its autograd.
+//
+// Two families of kernels:
+//   * channels-last ("nhwc") kernels — the fast path.  One CTA = one RoI x 64 channels.  The box, its
+//     pyramid level and the p+p axis taps are computed once and staged in shared memory; 16 lanes cover
+//     the 64 channels with one 128-bit load per bilinear tap (a 256 B contiguous segment per tap), 16
+//     bins are in flight per CTA.  NCHW outputs / output-gradients are transposed through a shared
+//     memory tile so that global traffic is fully coalesced on both sides.  Backward aggregates, in
+//     shared memory, all bins of a RoI that fall on the same feature-map column pair before issuing
+//     128-bit vector reductions (red.global.add.v4.f32) to the channels-last gradient pyramid.
+//   * strided ("generic") kernels — any layout, any C, one thread per output scalar.  Used for NCHW
+//     feature maps and the C=1 mask-target crop (model.py:501-502).
+//
+// HBM-bound: algorithmic bytes per RoI = C*p*p*4 (output) + unique taps*C*4, see DESIGN.md.
+#include "api_util.h"
+#include "common.cuh"
+
+namespace mrcnn {
+
+struct PyrLevel {
+    float* ptr;  // [B, H, W, C] (nhwc kernels) or layout-dependent (generic kernels)
+    int H, W;
+};
+
+struct RoiParams {
+    PyrLevel lv[4];
+    int pyramid;  // 1: level chosen per box (P2..P5); 0: single image tensor lv[0]
+    LevelRule rule;
+    int B, C;
+    const float* boxes;        // [N,4]
+    const int32_t* box_index;  // [N] or null (all zero)
+    int N;
+    int ph, pw;
+    float extrap;
+    float* crops;  // forward: output; backward: incoming gradient (read-only)
+    int32_t* levels_out;
+    int* err;
+};
+
+constexpr int kChunk = 64;     // channels per CTA
+constexpr int kLanes = 16;     // float4 lanes covering a chunk
+constexpr int kSlots = 16;     // bins in flight per CTA
+constexpr int kThreads = 256;  // kLanes * kSlots
+
+struct RoiCtx {
+    float* base;  // start of the selected image in the selected level
+    int H, W;
+    bool ok;
+};
+
+__device__ __forceinline__ RoiCtx select_level(const RoiParams& p, int n, float4& box) {
+    box.x = __ldg(p.boxes + 4 * n + 0);
+    box.y = __ldg(p.boxes + 4 * n + 1);
+    box.z = __ldg(p.boxes + 4 * n + 2);
+    box.w = __ldg(p.boxes + 4 * n + 3);
+    const int bi = p.box_index ? __ldg(p.box_index + n) : 0;
+    int l = 0;
+    if (p.pyramid) l = roi_level(box.x, box.y, box.z, box.w, p.rule) - 2;
+    const PyrLevel L = (l == 0) ? p.lv[0] : (l == 1) ? p.lv[1] : (l == 2) ? p.lv[2] : p.lv[3];
+    RoiCtx c;
+    c.H = L.H;
+    c.W = L.W;
+    c.ok = (unsigned)bi < (unsigned)p.B;
+    c.base = L.ptr + (size_t)(c.ok ? bi : 0) * L.H * L.W * p.C;
+    if (threadIdx.x == 0 && blockIdx.y == 0) {
+        if (!c.ok) atomicOr(p.err, 1);
+        if (p.levels_out) p.levels_out[n] = l + 2;
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, channels-last input.  grid = (N, ceil(C/64)), block = 256, dyn smem = 64*(P2|1)*4 (NCHW out).
+// ------------------------------------------------------------------------------------------------
+template <bool kOutNHWC>
+__global__ void __launch_bounds__(kThreads) roialign_fwd_nhwc_kernel(const RoiParams p) {
+    extern __shared__ __align__(16) float tile[];
+    __shared__ AxisTap s_ty[kMaxPool];
+    __shared__ AxisTap s_tx[kMaxPool];
+
+    const int n = blockIdx.x;
+    const int c0 = blockIdx.y * kChunk;
+    const int tid = threadIdx.x;
+    const int P2 = p.ph * p.pw;
+    const int P2pad = P2 | 1;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    if (tid < p.ph) s_ty[tid] = axis_tap(box.x, box.z, ctx.H, p.ph, tid);
+    if (tid >= 64 && tid < 64 + p.pw) s_tx[tid - 64] = axis_tap(box.y, box.w, ctx.W, p.pw, tid - 64);
+    __syncthreads();
+
+    const int lane = tid & (kLanes - 1);
+    const int slot = tid >> 4;
+    const int c = c0 + 4 * lane;
+    const bool c_ok = c < p.C;  // C % 4 == 0 is guaranteed by the launcher
+    const float* src = ctx.base + c;
+    const int C = p.C;
+    const int W = ctx.W;
+
+    for (int b0 = slot; b0 < P2; b0 += 2 * kSlots) {
+        float4 tl[2], tr[2], bl[2], br[2];
+        float xl[2], yl[2];
+        bool live[2], inside[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int b = b0 + u * kSlots;
+            live[u] = (b < P2) && c_ok;
+            inside[u] = false;
+            if (live[u]) {
+                const int y = b / p.pw;
+                const int x = b - y * p.pw;
+                const AxisTap ty = s_ty[y];
+                const AxisTap tx = s_tx[x];
+                inside[u] = ctx.ok && ty.lo >= 0 && tx.lo >= 0;
+                if (inside[u]) {
+                    const float* r0 = src + (size_t)ty.lo * W * C;
+                    const float* r1 = src + (size_t)ty.hi * W * C;
+                    tl[u] = ldg_f4(r0 + (size_t)tx.lo * C);
+                    tr[u] = ldg_f4(r0 + (size_t)tx.hi * C);
+                    bl[u] = ldg_f4(r1 + (size_t)tx.lo * C);
+                    br[u] = ldg_f4(r1 + (size_t)tx.hi * C);
+                    xl[u] = tx.lerp;
+                    yl[u] = ty.lerp;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            const int b = b0 + u * kSlots;
+            float4 v;
+            if (inside[u]) {
+                v.x = bilerp(tl[u].x, tr[u].x, bl[u].x, br[u].x, xl[u], yl[u]);
+                v.y = bilerp(tl[u].y, tr[u].y, bl[u].y, br[u].y, xl[u], yl[u]);
+                v.z = bilerp(tl[u].z, tr[u].z, bl[u].z, br[u].z, xl[u], yl[u]);
+                v.w = bilerp(tl[u].w, tr[u].w, bl[u].w, br[u].w, xl[u], yl[u]);
+            } else {
+                v = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+            }
+            if (kOutNHWC) {
+                stg_f4_stream(p.crops + ((size_t)n * P2 + b) * C + c, v);
+            } else {
+                float* t = tile + (4 * lane) * P2pad + b;
+                t[0] = v.x;
+                t[P2pad] = v.y;
+                t[2 * P2pad] = v.z;
+                t[3 * P2pad] = v.w;
+            }
+        }
+    }
+    if (!kOutNHWC) {
+        __syncthreads();
+        const int cc = min(kChunk, C - c0);
+        const int total = cc * P2;
+        float* dst = p.crops + ((size_t)n * C + c0) * P2;  // contiguous [cc][P2] block of the NCHW output
+        for (int e = tid; e < total; e += kThreads) {
+            const int ch = e / P2;
+            const int b = e - ch * P2;
+            __stcs(dst + e, tile[ch * P2pad + b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward, channels-last gradient pyramid.  Same CTA shape as the forward.
+//
+// Column aggregation: for one output row y of the RoI, all pw bins share (y_lo, y_hi, y_lerp) and hit
+// columns x_lo(x), x_hi(x), which are non-decreasing in x.  Each (slot, lane) owner walks the bins of
+// its row in x order and keeps a running float4 sum per feature-map column; it flushes one
+// red.v4 per DISTINCT column (times two rows) instead of four per bin.  When the RoI is up-sampled
+// (fewer feature columns than bins, the common case for the 14x14 mask head) this removes most atomics.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flush_col(float* row0, float* row1, int col, int C, float4 acc, float yl, bool two_rows) {
+    // d(top) = (1 - yl) * g-weighted, d(bottom) = yl * g-weighted  (crop_cpu.cpp:254-260, regrouped)
+    const float w0 = __fsub_rn(1.0f, yl);
+    float4 a = make_float4(acc.x * w0, acc.y * w0, acc.z * w0, acc.w * w0);
+    red_add_f4(row0 + (size_t)col * C, a);
+    if (two_rows) {
+        float4 b = make_float4(acc.x * yl, acc.y * yl, acc.z * yl, acc.w * yl);
+        red_add_f4(row1 + (size_t)col * C, b);
+    }
+}
+
+template <bool kGradNHWC>
+__global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiParams p) {
+    extern __shared__ __align__(16) float tile[];
+    __shared__ AxisTap s_ty[kMaxPool];
+    __shared__ AxisTap s_tx[kMaxPool];
+
+    const int n = blockIdx.x;
+    const int c0 = blockIdx.y * kChunk;
+    const int tid = threadIdx.x;
+    const int P2 = p.ph * p.pw;
+    const int P2pad = P2 | 1;
+    const int C = p.C;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    if (tid < p.ph) s_ty[tid] = axis_tap(box.x, box.z, ctx.H, p.ph, tid);
+    if (tid >= 64 && tid < 64 + p.pw) s_tx[tid - 64] = axis_tap(box.y, box.w, ctx.W, p.pw, tid - 64);
+    if (!kGradNHWC) {
+        const int cc = min(kChunk, C - c0);
+        const int total = cc * P2;
+        const float* g = p.crops + ((size_t)n * C + c0) * P2;
+        for (int e = tid; e < total; e += kThreads) {
+            const int ch = e / P2;
+            const int b = e - ch * P2;
+            tile[ch * P2pad + b] = __ldcs(g + e);
+        }
+    }
+    __syncthreads();
+    if (!ctx.ok) return;
+
+    const int lane = tid & (kLanes - 1);
+    const int slot = tid >> 4;
+    const int c = c0 + 4 * lane;
+    if (c >= C) return;
+    float* dst = ctx.base + c;
+    const int W = ctx.W;
+
+    // Work items = (output row, column segment).  With few rows (7x7) each row is split into segments so
+    // that all 16 slots have work; aggregation then happens within a segment.
+    const int segs = (p.ph >= kSlots) ? 1 : min(p.pw, kSlots / p.ph);
+    const int items = p.ph * segs;
+    for (int it = slot; it < items; it += kSlots) {
+        const int y = it / segs;
+        const int seg = it - y * segs;
+        const int xbeg = (seg * p.pw) / segs;
+        const int xend = ((seg + 1) * p.pw) / segs;
+        const AxisTap ty = s_ty[y];
+        if (ty.lo < 0) continue;
+        float* row0 = dst + (size_t)ty.lo * W * C;
+        float* row1 = dst + (size_t)ty.hi * W * C;
+        const bool two_rows = ty.lerp != 0.0f;  // lerp == 0 <=> hi == lo: nothing goes to a second row
+        int cur = -1;                           // feature column accumulated in acc; nxt is column cur + 1
+        bool has_nxt = false;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int x = xbeg; x < xend; ++x) {
+            const AxisTap tx = s_tx[x];
+            if (tx.lo < 0) continue;
+            float4 g;
+            const int b = y * p.pw + x;
+            if (kGradNHWC) {
+                g = ldg_f4_stream(p.crops + ((size_t)n * P2 + b) * C + c);
+            } else {
+                const float* t = tile + (4 * lane) * P2pad + b;
+                g = make_float4(t[0], t[P2pad], t[2 * P2pad], t[3 * P2pad]);
+            }
+            if (tx.lo != cur) {
+                if (cur >= 0) {
+                    flush_col(row0, row1, cur, C, acc, ty.lerp, two_rows);
+                    if (has_nxt && tx.lo != cur + 1) flush_col(row0, row1, cur + 1, C, nxt, ty.lerp, two_rows);
+                }
+                acc = (cur >= 0 && has_nxt && tx.lo == cur + 1) ? nxt : make_float4(0.f, 0.f, 0.f, 0.f);
+                nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+                has_nxt = false;
+                cur = tx.lo;
+            }
+            const float wl = __fsub_rn(1.0f, tx.lerp);
+            acc.x += wl * g.x;
+            acc.y += wl * g.y;
+            acc.z += wl * g.z;
+            acc.w += wl * g.w;
+            if (tx.lerp != 0.0f) {  // <=> hi == lo + 1
+                nxt.x += tx.lerp * g.x;
+                nxt.y += tx.lerp * g.y;
+                nxt.z += tx.lerp * g.z;
+                nxt.w += tx.lerp * g.w;
+                has_nxt = true;
+            }
+        }
+        if (cur >= 0) {
+            flush_col(row0, row1, cur, C, acc, ty.lerp, two_rows);
+            if (has_nxt) flush_col(row0, row1, cur + 1, C, nxt, ty.lerp, two_rows);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic strided kernels: one thread per output scalar, any layout.  Element strides in floats.
+// ------------------------------------------------------------------------------------------------
+struct Strides4 {
+    long long n, c, h, w;
+};
+
+__device__ __forceinline__ Strides4 strides_of(int layout, int C, int H, int W) {
+    Strides4 s;
+    if (layout == MRCNN_NHWC) {
+        s.n = (long long)H * W * C;
+        s.c = 1;
+        s.h = (long long)W * C;
+        s.w = C;
+    } else {
+        s.n = (long long)C * H * W;
+        s.c = (long long)H * W;
+        s.h = W;
+        s.w = 1;
+    }
+    return s;
+}
+
+struct GenericParams {
+    RoiParams r;
+    int image_layout;
+    int crops_layout;
+};
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256) crop_generic_kernel(const GenericParams gp) {
+    const RoiParams& p = gp.r;
+    const long long total = (long long)p.N * p.C * p.ph * p.pw;
+    const Strides4 so = strides_of(gp.crops_layout, p.C, p.ph, p.pw);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % p.pw);
+        long long t = idx / p.pw;
+        const int y = (int)(t % p.ph);
+        t /= p.ph;
+        const int c = (int)(t % p.C);
+        const int n = (int)(t / p.C);
+        const float y1 = __ldg(p.boxes + 4 * n + 0), x1 = __ldg(p.boxes + 4 * n + 1);
+        const float y2 = __ldg(p.boxes + 4 * n + 2), x2 = __ldg(p.boxes + 4 * n + 3);
+        const int bi = p.box_index ? __ldg(p.box_index + n) : 0;
+        int l = 0;
+        if (p.pyramid) l = roi_level(y1, x1, y2, x2, p.rule) - 2;
+        const PyrLevel L = (l == 0) ? p.lv[0] : (l == 1) ? p.lv[1] : (l == 2) ? p.lv[2] : p.lv[3];
+        float* cp = p.crops + n * so.n + c * so.c + y * so.h + x * so.w;
+        const bool ok = (unsigned)bi < (unsigned)p.B;
+        if (!ok) {
+            if (c == 0 && y == 0 && x == 0) atomicOr(p.err, 1);
+            if (!kBackward) *cp = p.extrap;
+            continue;
+        }
+        if (!kBackward && p.levels_out && c == 0 && y == 0 && x == 0) p.levels_out[n] = l + 2;
+        const AxisTap ty = axis_tap(y1, y2, L.H, p.ph, y);
+        const AxisTap tx = axis_tap(x1, x2, L.W, p.pw, x);
+        if (ty.lo < 0 || tx.lo < 0) {
+            if (!kBackward) *cp = p.extrap;
+            continue;
+        }
+        const Strides4 si = strides_of(gp.image_layout, p.C, L.H, L.W);
+        float* img = L.ptr + bi * si.n + c * si.c;
+        float* ptl = img + ty.lo * si.h + tx.lo * si.w;
+        float* ptr = img + ty.lo * si.h + tx.hi * si.w;
+        float* pbl = img + ty.hi * si.h + tx.lo * si.w;
+        float* pbr = img + ty.hi * si.h + tx.hi * si.w;
+        if (!kBackward) {
+            *cp = bilerp(__ldg(ptl), __ldg(ptr), __ldg(pbl), __ldg(pbr), tx.lerp, ty.lerp);
+        } else {
+            // crop_cpu.cpp:254-260
+            const float g = __ldg(cp);
+            const float dtop = __fmul_rn(__fsub_rn(1.0f, ty.lerp), g);
+            atomicAdd(ptl, __fmul_rn(__fsub_rn(1.0f, tx.lerp), dtop));
+            if (tx.lerp != 0.0f) atomicAdd(ptr, __fmul_rn(tx.lerp, dtop));
+            if (ty.lerp != 0.0f) {
+                const float dbot = __fmul_rn(ty.lerp, g);
+                atomicAdd(pbl, __fmul_rn(__fsub_rn(1.0f, tx.lerp), dbot));
+                if (tx.lerp != 0.0f) atomicAdd(pbr, __fmul_rn(tx.lerp, dbot));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+
+// The reference's level formula (model.py:331-338) as a function of q, with correctly rounded log2.
+static int level_of_q(float q) {
+    const float v = 4.0f + (float)log2((double)q);
+    if (!(v == v) || isinf(v)) return 2;
+    int lv = (int)nearbyintf(v);
+    return lv < 2 ? 2 : (lv > 5 ? 5 : lv);
+}
+
+// Smallest positive float q with level_of_q(q) >= k (level_of_q is non-decreasing in q).
+static float level_threshold(int k) {
+    uint32_t lo = 0x00000001u, hi = 0x7f7fffffu;  // positive finite floats are ordered like their bits
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        float q;
+        memcpy(&q, &mid, 4);
+        if (level_of_q(q) >= k) hi = mid; else lo = mid + 1;
+    }
+    float q;
+    memcpy(&q, &lo, 4);
+    return q;
+}
+
+static LevelRule make_level_rule(float image_area) {
+    static float t3 = 0.f, t4 = 0.f, t5 = 0.f;
+    if (t3 == 0.f) {
+        t3 = level_threshold(3);
+        t4 = level_threshold(4);
+        t5 = level_threshold(5);
+    }
+    LevelRule r;
+    r.denom = 224.0f / sqrtf(image_area);  // model.py:335-336: 224.0 / torch.sqrt(image_area), fp32
+    r.t3 = t3;
+    r.t4 = t4;
+    r.t5 = t5;
+    return r;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_roi(const RoiParams& p, int image_layout, int crops_layout, bool backward, cudaStream_t stream) {
+    if (p.N == 0) return MRCNN_OK;
+    bool fast = image_layout == MRCNN_NHWC && (p.C % 4) == 0 && p.ph <= kMaxPool && p.pw <= kMaxPool &&
+                aligned16(p.crops);
+    for (int l = 0; l < (p.pyramid ? 4 : 1); ++l) fast = fast && aligned16(p.lv[l].ptr);
+    const int P2 = p.ph * p.pw;
+    const size_t smem = (crops_layout == MRCNN_NHWC) ? 0 : sizeof(float) * kChunk * (size_t)(P2 | 1);
+    if (fast && smem > 200 * 1024) fast = false;
+    if (fast) {
+        const dim3 grid(p.N, (p.C + kChunk - 1) / kChunk);
+        if (grid.y > 65535) return fail(MRCNN_E_INVALID_ARG, "C too large");
+#define MRCNN_LAUNCH_NHWC(KERNEL)                                                                          \
+    do {                                                                                                   \
+        if (smem > 48 * 1024)                                                                              \
+            MRCNN_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KERNEL<<<grid, kThreads, smem, stream>>>(p);                                                       \
+    } while (0)
+        if (!backward) {
+            if (crops_layout == MRCNN_NHWC) MRCNN_LAUNCH_NHWC(roialign_fwd_nhwc_kernel<true>);
+            else MRCNN_LAUNCH_NHWC(roialign_fwd_nhwc_kernel<false>);
+        } else {
+            if (crops_layout == MRCNN_NHWC) MRCNN_LAUNCH_NHWC(roialign_bwd_nhwc_kernel<true>);
+            else MRCNN_LAUNCH_NHWC(roialign_bwd_nhwc_kernel<false>);
+        }
+#undef MRCNN_LAUNCH_NHWC
+    } else {
+        GenericParams gp;
+        gp.r = p;
+        gp.image_layout = image_layout;
+        gp.crops_layout = crops_layout;
+        const long long total = (long long)p.N * p.C * P2;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 64;
+        if (blocks > cap) blocks = cap;
+        if (!backward) crop_generic_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(gp);
+        else crop_generic_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(gp);
+    }
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+static int check_layout(int v, const char* what) {
+    if (v != MRCNN_NCHW && v != MRCNN_NHWC) return fail(MRCNN_E_INVALID_ARG, "%s must be MRCNN_NCHW or MRCNN_NHWC", what);
+    return MRCNN_OK;
+}
+
+}  // namespace mrcnn
+
+using namespace mrcnn;
+
+extern "C" {
+
+int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout, const float* boxes,
+                       const int32_t* box_index, int N, float extrapolation_value, int crop_h, int crop_w,
+                       float* crops, int crops_layout, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "mrcnn_crop_forward: image dims must be positive");
+    MRCNN_REQUIRE(N >= 0 && crop_h > 0 && crop_w > 0, "mrcnn_crop_forward: bad N / crop size");
+    if (int rc = check_layout(image_layout, "image_layout")) return rc;
+    if (int rc = check_layout(crops_layout, "crops_layout")) return rc;
+    if (N == 0) return MRCNN_OK;
+    MRCNN_REQUIRE_DEV(image);
+    MRCNN_REQUIRE_DEV(boxes);
+    MRCNN_REQUIRE_DEV(box_index);
+    MRCNN_REQUIRE_DEV(crops);
+    RoiParams p = {};
+    p.lv[0] = {const_cast<float*>(image), H, W};
+    p.pyramid = 0;
+    p.B = B; p.C = C;
+    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.ph = crop_h; p.pw = crop_w; p.extrap = extrapolation_value;
+    p.crops = crops;
+    p.err = device_error_word();
+    MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
+    return launch_roi(p, image_layout, crops_layout, false, (cudaStream_t)stream);
+}
+
+int mrcnn_crop_backward(const float* grads, int grads_layout, const float* boxes, const int32_t* box_index, int N,
+                        int crop_h, int crop_w, float* grads_image, int B, int C, int H, int W, int image_layout,
+                        int zero_fill, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "mrcnn_crop_backward: image dims must be positive");
+    MRCNN_REQUIRE(N >= 0 && crop_h > 0 && crop_w > 0, "mrcnn_crop_backward: bad N / crop size");
+    if (int rc = check_layout(image_layout, "image_layout")) return rc;
+    if (int rc = check_layout(grads_layout, "grads_layout")) return rc;
+    MRCNN_REQUIRE_DEV(grads_image);
+    if (zero_fill)
+        MRCNN_CUDA(cudaMemsetAsync(grads_image, 0, sizeof(float) * (size_t)B * C * H * W, (cudaStream_t)stream));
+    if (N == 0) return MRCNN_OK;
+    MRCNN_REQUIRE_DEV(grads);
+    MRCNN_REQUIRE_DEV(boxes);
+    MRCNN_REQUIRE_DEV(box_index);
+    RoiParams p = {};
+    p.lv[0] = {grads_image, H, W};
+    p.pyramid = 0;
+    p.B = B; p.C = C;
+    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.ph = crop_h; p.pw = crop_w; p.extrap = 0.f;
+    p.crops = const_cast<float*>(grads);
+    p.err = device_error_word();
+    MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
+    return launch_roi(p, image_layout, grads_layout, true, (cudaStream_t)stream);
+}
+
+int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], const int W[4], int B, int C,
+                                    int fm_layout, const float* boxes, const int32_t* box_index, int N, int pool,
+                                    float image_area, float* out, int out_layout, int32_t* levels_out,
+                                    mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(fm && H && W, "mrcnn_pyramid_roi_align_forward: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N >= 0 && pool > 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_forward: bad sizes");
+    if (int rc = check_layout(fm_layout, "fm_layout")) return rc;
+    if (int rc = check_layout(out_layout, "out_layout")) return rc;
+    if (N == 0) return MRCNN_OK;
+    RoiParams p = {};
+    for (int l = 0; l < 4; ++l) {
+        MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_forward: level %d has empty shape", l);
+        MRCNN_REQUIRE_DEV(fm[l]);
+        p.lv[l] = {const_cast<float*>(fm[l]), H[l], W[l]};
+    }
+    MRCNN_REQUIRE_DEV(boxes);
+    MRCNN_REQUIRE_DEV(out);
+    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    if (levels_out) MRCNN_REQUIRE_DEV(levels_out);
+    p.pyramid = 1;
+    p.rule = make_level_rule(image_area);
+    p.B = B; p.C = C;
+    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.ph = pool; p.pw = pool; p.extrap = 0.f;  // model.py:373 CropFunction(pool, pool, 0)
+    p.crops = out;
+    p.levels_out = levels_out;
+    p.err = device_error_word();
+    MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
+    return launch_roi(p, fm_layout, out_layout, false, (cudaStream_t)stream);
+}
+
+int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const int H[4], const int W[4], int B,
+                                     int C, const float* boxes, const int32_t* box_index, int N, int pool,
+                                     float image_area, float* const gfm[4], int gfm_layout, int zero_fill,
+                                     mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N >= 0 && pool > 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_backward: bad sizes");
+    if (int rc = check_layout(gfm_layout, "gfm_layout")) return rc;
+    if (int rc = check_layout(grads_layout, "grads_layout")) return rc;
+    RoiParams p = {};
+    for (int l = 0; l < 4; ++l) {
+        MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_backward: level %d has empty shape", l);
+        MRCNN_REQUIRE_DEV(gfm[l]);
+        p.lv[l] = {gfm[l], H[l], W[l]};
+        if (zero_fill)
+            MRCNN_CUDA(cudaMemsetAsync(gfm[l], 0, sizeof(float) * (size_t)B * C * H[l] * W[l], (cudaStream_t)stream));
+    }
+    if (N == 0) return MRCNN_OK;
+    MRCNN_REQUIRE_DEV(grads);
+    MRCNN_REQUIRE_DEV(boxes);
+    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    p.pyramid = 1;
+    p.rule = make_level_rule(image_area);
+    p.B = B; p.C = C;
+    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.ph = pool; p.pw = pool; p.extrap = 0.f;
+    p.crops = const_cast<float*>(grads);
+    p.err = device_error_word();
+    MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
+    return launch_roi(p, gfm_layout, grads_layout, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"

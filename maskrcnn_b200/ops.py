@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's operator interface for the RoI hot path, on top of the C ABI
+(include/mrcnn_b200.h).  PyTorch is used for device memory, streams and autograd plumbing only.
+
+Reference interface being mirrored (paths relative to /root/reference):
+    c++ext/maskrcnn/__init__.py:21-22   nms(dets, threshold)
+    c++ext/maskrcnn/__init__.py:25-57   CropFunction(crop_height, crop_width, extrapolation_value=0)(image, boxes, box_ind)
+    model.py:276-393                    roi_align(inputs, pool_size, image_shape)
+    model.py:1307-1382                  MaskRCNN.rpn_refine(self, rpn_class, rpn_bbox)
+    model.py:1389-1487                  MaskRCNN.mrn_refine(self, rpn_rois, probs, deltas, window)
+
+There is no CPU implementation: CPU tensors raise TypeError, a missing library raises ImportError.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NCHW, NHWC, check, lib
+
+__all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
+           "rpn_refine", "detection_layer", "mrn_refine", "check_device_errors"]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor: maskrcnn_b200 has no CPU path (got device=%s)" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
+    return t
+
+
+def _layout4(t):
+    """(tensor, layout) with the tensor dense in NCHW or channels-last memory order."""
+    if t.dim() != 4:
+        raise ValueError("expected a 4-D tensor, got %d-D" % t.dim())
+    if t.is_contiguous():
+        return t, NCHW
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t, NHWC
+    return t.contiguous(), NCHW
+
+
+def _empty4(shape, layout, like):
+    mf = torch.channels_last if layout == NHWC else torch.contiguous_format
+    return torch.empty(shape, dtype=torch.float32, device=like.device, memory_format=mf)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def check_device_errors():
+    """Synchronises and raises if a kernel saw a box_index outside [0, batch) since the last call
+    (the reference exit(-1)s, cpu/crop_cpu.cpp:47-50)."""
+    check(lib.mrcnn_poll_device_errors(_stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# nms
+# ------------------------------------------------------------------------------------------------
+def nms(dets, threshold):
+    """c++ext/maskrcnn/__init__.py:21-22.  dets [N,5] = (y1,x1,y2,x2,score) -> int64 [K] ascending indices.
+    One 4-byte device->host read (K) is the only synchronisation."""
+    _require_cuda(dets, "dets", torch.float32)
+    if dets.numel() == 0:
+        # nms.h:20-21: the reference returns an empty CPU tensor here; a CUDA one indexes equally well
+        return torch.empty(0, dtype=torch.int64, device=dets.device)
+    if dets.dim() != 2 or dets.size(1) != 5:
+        raise ValueError("dets must be [N,5]")
+    dets = dets.contiguous()
+    n = dets.size(0)
+    with torch.cuda.device(dets.device):
+        keep = torch.empty(n, dtype=torch.int64, device=dets.device)
+        count = torch.empty(1, dtype=torch.int32, device=dets.device)
+        ws_bytes = lib.mrcnn_nms_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dets.device)
+        check(lib.mrcnn_nms(dets.data_ptr(), n, float(threshold), keep.data_ptr(), count.data_ptr(), ws.data_ptr(),
+                            ws_bytes, _stream()))
+        k = int(count.item())
+    return keep[:k]
+
+
+# ------------------------------------------------------------------------------------------------
+# crop_and_resize
+# ------------------------------------------------------------------------------------------------
+def _crop_forward(image, boxes, box_ind, ch, cw, ev):
+    image, il = _layout4(image)
+    B, C, H, W = image.shape
+    N = boxes.size(0)
+    out = _empty4((N, C, ch, cw), il, image)
+    if N:
+        with torch.cuda.device(image.device):
+            check(lib.mrcnn_crop_forward(image.data_ptr(), B, C, H, W, il, boxes.data_ptr(), box_ind.data_ptr(), N,
+                                         float(ev), ch, cw, out.data_ptr(), il, _stream()))
+    return out
+
+
+def _crop_backward(grad, boxes, box_ind, im_size, image_layout):
+    grad, gl = _layout4(grad)
+    B, C, H, W = im_size
+    N, _, ch, cw = grad.shape
+    gimg = _empty4((B, C, H, W), image_layout, grad)
+    with torch.cuda.device(grad.device):
+        check(lib.mrcnn_crop_backward(_ptr(grad) if N else None, gl, _ptr(boxes) if N else None,
+                                      _ptr(box_ind) if N else None, N, ch, cw, gimg.data_ptr(), B, C, H, W,
+                                      image_layout, 1, _stream()))
+    return gimg
+
+
+class _CropAndResize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, boxes, box_ind, ch, cw, ev):
+        boxes = boxes.contiguous()
+        box_ind = box_ind.contiguous()
+        _, il = _layout4(image)
+        ctx.im_size = tuple(image.shape)
+        ctx.image_layout = il
+        ctx.save_for_backward(boxes, box_ind)
+        return _crop_forward(image, boxes, box_ind, ch, cw, ev)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        boxes, box_ind = ctx.saved_tensors
+        return _crop_backward(grad_output, boxes, box_ind, ctx.im_size, ctx.image_layout), None, None, None, None, None
+
+
+def crop_and_resize(image, boxes, box_ind, crop_height, crop_width, extrapolation_value=0.0):
+    _require_cuda(image, "image", torch.float32)
+    _require_cuda(boxes, "boxes", torch.float32)
+    _require_cuda(box_ind, "box_ind", torch.int32)  # __init__.py:34-35
+    if boxes.dim() != 2 or boxes.size(1) != 4 or box_ind.dim() != 1 or box_ind.size(0) != boxes.size(0):
+        raise ValueError("boxes must be [N,4] and box_ind [N]")
+    return _CropAndResize.apply(image, boxes, box_ind, int(crop_height), int(crop_width), float(extrapolation_value))
+
+
+class CropFunction(object):
+    """Drop-in for c++ext/maskrcnn/__init__.py:25-57: construct with the crop size, call with
+    (image [B,C,H,W] fp32, boxes [N,4] normalised fp32, box_ind [N] int32) -> crops [N,C,h,w].
+    Differentiable w.r.t. image only.  (The reference class is a legacy autograd Function that torch 2.x
+    refuses to run; instances of this class are plain callables over a static Function.)"""
+
+    def __init__(self, crop_height, crop_width, extrapolation_value=0):
+        self.crop_height = crop_height
+        self.crop_width = crop_width
+        self.extrapolation_value = extrapolation_value
+
+    def __call__(self, image, boxes, box_ind):
+        return crop_and_resize(image, boxes, box_ind, self.crop_height, self.crop_width, self.extrapolation_value)
+
+    forward = __call__
+
+
+# ------------------------------------------------------------------------------------------------
+# PyramidROIAlign
+# ------------------------------------------------------------------------------------------------
+def _pyramid_layout(fms):
+    if len(fms) != 4:
+        raise ValueError("expected the four pyramid levels P2..P5")
+    outs, layouts = zip(*[_layout4(f) for f in fms])
+    outs = list(outs)
+    if len(set(layouts)) != 1:  # mixed: settle on channels-last (the fast path)
+        outs = [f.contiguous(memory_format=torch.channels_last) for f in outs]
+        return outs, NHWC
+    # a [B,1,H,W] or [B,C,1,1] tensor is dense in both orders; prefer channels-last when any level says so
+    return outs, layouts[0]
+
+
+class _PyramidRoiAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, boxes, box_ind, pool, image_area, out_layout, p2, p3, p4, p5):
+        fms, fl = _pyramid_layout([p2, p3, p4, p5])
+        B, C = fms[0].shape[:2]
+        N = boxes.size(0)
+        ol = fl if out_layout is None else out_layout
+        out = _empty4((N, C, pool, pool), ol, fms[0])
+        Hs = [f.shape[2] for f in fms]
+        Ws = [f.shape[3] for f in fms]
+        if N:
+            with torch.cuda.device(out.device):
+                check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws),
+                                                          B, C, fl, boxes.data_ptr(), _ptr(box_ind), N, pool,
+                                                          float(image_area), out.data_ptr(), ol, None, _stream()))
+        ctx.save_for_backward(boxes, box_ind)
+        ctx.meta = (Hs, Ws, B, C, fl, pool, float(image_area))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        boxes, box_ind = ctx.saved_tensors
+        Hs, Ws, B, C, fl, pool, image_area = ctx.meta
+        grad, gl = _layout4(grad)
+        N = boxes.size(0)
+        gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
+        with torch.cuda.device(grad.device):
+            check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
+                                                       _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,
+                                                       _lib.vp4([g.data_ptr() for g in gfm]), fl, 1, _stream()))
+        return (None, None, None, None, None) + tuple(gfm)
+
+
+def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_channels_last=None):
+    """Batched PyramidROIAlign.  feature_maps: [P2,P3,P4,P5], each [B,C,Hl,Wl] (NCHW or channels-last; the
+    channels-last layout runs the 128-bit vectorised kernels).  boxes [N,4] normalised (not differentiated,
+    model.py:358), box_ind [N] int32 image index or None (all image 0).  Returns [N,C,pool,pool] in box order;
+    memory format follows the feature maps unless out_channels_last is given."""
+    for i, f in enumerate(feature_maps):
+        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
+    _require_cuda(boxes, "boxes", torch.float32)
+    if boxes.dim() != 2 or boxes.size(1) != 4:
+        raise ValueError("boxes must be [N,4]")
+    boxes = boxes.detach().contiguous()
+    if box_ind is not None:
+        _require_cuda(box_ind, "box_ind", torch.int32)
+        box_ind = box_ind.contiguous()
+    image_area = float(image_shape[0] * image_shape[1])  # model.py:331
+    ol = None if out_channels_last is None else (NHWC if out_channels_last else NCHW)
+    return _PyramidRoiAlign.apply(boxes, box_ind, int(pool_size), image_area, ol, *feature_maps)
+
+
+def roi_align(inputs, pool_size, image_shape):
+    """Drop-in for model.py:276-393: inputs = [boxes [1,N,4], P2 [1,C,H,W], P3, P4, P5] -> [N,C,pool,pool].
+    One fused launch instead of ~30 (per-level nonzero/gather/crop + cat + sort + gather)."""
+    boxes = inputs[0]
+    if boxes.dim() == 3:
+        if boxes.size(0) != 1:
+            raise ValueError("roi_align drop-in is batch-1 like the reference (model.py:296); use pyramid_roi_align")
+        boxes = boxes.squeeze(0)
+    fms = [f if f.dim() == 4 else f.unsqueeze(0) for f in inputs[1:5]]
+    return pyramid_roi_align(fms, boxes, None, pool_size, image_shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# proposal layer
+# ------------------------------------------------------------------------------------------------
+def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, nms_threshold,
+                   std=(0.1, 0.1, 0.2, 0.2), image_hw=(1024, 1024)):
+    """Batched proposal layer.  rpn_class [B,A,2], rpn_bbox [B,A,4], anchors [A,4] px ->
+    (rois [B,post,4] normalised & zero padded, counts int32 [B]).  No host synchronisation."""
+    _require_cuda(rpn_class, "rpn_class", torch.float32)
+    _require_cuda(rpn_bbox, "rpn_bbox", torch.float32)
+    _require_cuda(anchors, "anchors", torch.float32)
+    if rpn_class.dim() != 3 or rpn_class.size(2) != 2 or rpn_bbox.shape != rpn_class.shape[:2] + (4,):
+        raise ValueError("rpn_class must be [B,A,2] and rpn_bbox [B,A,4]")
+    B, A = rpn_class.shape[:2]
+    if anchors.shape != (A, 4):
+        raise ValueError("anchors must be [A,4]")
+    rpn_class, rpn_bbox, anchors = rpn_class.contiguous(), rpn_bbox.contiguous(), anchors.contiguous()
+    post = int(post_nms_limit)
+    with torch.cuda.device(rpn_class.device):
+        rois = torch.empty((B, post, 4), dtype=torch.float32, device=rpn_class.device)
+        counts = torch.empty(B, dtype=torch.int32, device=rpn_class.device)
+        ws_bytes = lib.mrcnn_proposal_workspace_bytes(B, A, int(pre_nms_limit))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rpn_class.device)
+        check(lib.mrcnn_proposal_layer(rpn_class.data_ptr(), rpn_bbox.data_ptr(), anchors.data_ptr(), B, A,
+                                       int(pre_nms_limit), post, float(nms_threshold), _lib.f4(np.float32(std)),
+                                       float(image_hw[0]), float(image_hw[1]), rois.data_ptr(), counts.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _stream()))
+    return rois, counts
+
+
+def rpn_refine(self, rpn_class, rpn_bbox, pre_nms_limit=None):
+    """Drop-in for MaskRCNN.rpn_refine (model.py:1307-1382): returns [1,K,4] normalised proposals.
+    pre_nms_limit defaults to the fork's hard-coded 500 (model.py:1345)."""
+    cfg = self.config
+    pre = min(500 if pre_nms_limit is None else pre_nms_limit, self.anchors.size(0))
+    h, w = (int(v) for v in cfg.IMAGE_SHAPE[:2])
+    rois, counts = proposal_layer(rpn_class, rpn_bbox, self.anchors, pre, cfg.RPN_NMS_MAX_ROIS_NUM,
+                                  cfg.RPN_NMS_THRESHOLD, cfg.RPN_BBOX_STD_DEV, (h, w))
+    k = int(counts[0].item())  # the reference's output is not padded -> one 4-byte read
+    return rois[:1, :k]
+
+
+# ------------------------------------------------------------------------------------------------
+# detection layer
+# ------------------------------------------------------------------------------------------------
+def detection_layer(rois, probs, deltas, windows, min_confidence, nms_threshold, max_instances,
+                    std=(0.1, 0.1, 0.2, 0.2), image_hw=(1024, 1024), return_index=False):
+    """Batched detection layer.  rois [B,N,4] normalised, probs [B,N,NC], deltas [B,N,NC,4], windows [B,4] px ->
+    (dets [B,D,6] = (y1,x1,y2,x2,score,class) score-descending zero padded, counts int32 [B][, index int32 [B,D]])."""
+    for t, name in ((rois, "rois"), (probs, "probs"), (deltas, "deltas"), (windows, "windows")):
+        _require_cuda(t, name, torch.float32)
+    if rois.dim() != 3 or rois.size(2) != 4:
+        raise ValueError("rois must be [B,N,4]")
+    B, N = rois.shape[:2]
+    NC = probs.size(-1)
+    if probs.shape != (B, N, NC) or deltas.shape != (B, N, NC, 4) or windows.shape != (B, 4):
+        raise ValueError("probs must be [B,N,NC], deltas [B,N,NC,4], windows [B,4]")
+    rois, probs, deltas, windows = rois.contiguous(), probs.contiguous(), deltas.contiguous(), windows.contiguous()
+    D = int(max_instances)
+    with torch.cuda.device(rois.device):
+        dets = torch.empty((B, D, 6), dtype=torch.float32, device=rois.device)
+        counts = torch.empty(B, dtype=torch.int32, device=rois.device)
+        index = torch.empty((B, D), dtype=torch.int32, device=rois.device) if return_index else None
+        ws_bytes = lib.mrcnn_detection_workspace_bytes(B, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rois.device)
+        check(lib.mrcnn_detection_layer(rois.data_ptr(), probs.data_ptr(), deltas.data_ptr(), windows.data_ptr(), B, N, NC,
+                                        float(min_confidence or 0.0), float(nms_threshold), D, _lib.f4(np.float32(std)),
+                                        float(image_hw[0]), float(image_hw[1]), dets.data_ptr(), counts.data_ptr(),
+                                        _ptr(index), ws.data_ptr(), ws_bytes, _stream()))
+    if return_index:
+        return dets, counts, index
+    return dets, counts
+
+
+def mrn_refine(self, rpn_rois, probs, deltas, window):
+    """Drop-in for MaskRCNN.mrn_refine (model.py:1389-1487): returns (class_ids [1,D] int64, scores [1,D],
+    boxes [1,D,4]) or (None, None, None) when nothing survives (:1445-1447)."""
+    cfg = self.config
+    dev = probs.device
+    win = torch.as_tensor(np.asarray(window, dtype=np.float32).reshape(1, 4)).to(dev) if not isinstance(window, torch.Tensor) \
+        else window.to(device=dev, dtype=torch.float32).reshape(1, 4)
+    h, w = (int(v) for v in cfg.IMAGE_SHAPE[:2])
+    rois = rpn_rois if rpn_rois.dim() == 3 else rpn_rois.unsqueeze(0)
+    dets, counts = detection_layer(rois, probs.unsqueeze(0), deltas.unsqueeze(0), win, cfg.DETECTION_MIN_CONFIDENCE,
+                                   cfg.DETECTION_NMS_THRESHOLD, cfg.DETECTION_MAX_INSTANCES,
+                                   np.asarray(cfg.RPN_BBOX_STD_DEV, dtype=np.float32).reshape(4), (h, w))
+    d = int(counts[0].item())
+    if d < 1:
+        return None, None, None
+    dets = dets[0, :d]
+    return dets[:, 5].long().unsqueeze(0), dets[:, 4].unsqueeze(0), dets[:, :4].unsqueeze(0)

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C ABI via maskrcnn_b200.ops) against the plain-C oracle
+and the committed golden vectors.  Bit-exact for indices/selections and for the forward interpolation;
+<= 1e-5 relative (scale = max |reference|) for the atomically accumulated backward."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden, rel_err
+from maskrcnn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+BWD_TOL = 1e-5  # north_star: RoIAlign forward/backward within 1e-5 relative in fp32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import maskrcnn_b200
+    return maskrcnn_b200
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------ nms
+def _dets(n, seed, thr_cluster=True):
+    rng = np.random.default_rng(seed)
+    b = synth.random_rois(n, seed, image=1024.0, min_size=16, max_size=500) * 1024.0
+    if thr_cluster and n > 3:
+        h = n // 2
+        b[h:] = b[: n - h] + rng.uniform(-8, 8, (n - h, 4)).astype(np.float32)
+    return np.concatenate([b, synth.unique_scores(n, seed)[:, None]], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (2, 0.5), (63, 0.3), (64, 0.7), (65, 0.5), (500, 0.7), (1000, 0.3),
+                                   (6000, 0.7), (8192, 0.5), (8193, 0.7), (20000, 0.6)])
+def test_nms_matches_oracle(ops, n, thr):
+    dets = _dets(n, 1000 + n)
+    want = oracle.nms(dets, thr)
+    got = ops.nms(dev(dets), thr)
+    assert got.dtype == torch.int64 and got.is_cuda
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_nms_edge_cases(ops):
+    assert ops.nms(torch.zeros(0, 5, device="cuda"), 0.5).numel() == 0
+    dets = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 9, 0.8], [0, 0, 9, 4, 0.7], [5, 5, 2, 2, 0.6], [5, 5, 2, 2, 0.5],
+                     [0, 0, -1, -1, 0.4], [0, 0, -1, -1, 0.3], [100, 100, 120, 130, 0.2]], np.float32)
+    for thr in (0.5, 0.3, 0.0, 1.0):
+        np.testing.assert_array_equal(ops.nms(dev(dets), thr).cpu().numpy(), oracle.nms(dets, thr))
+    # all suppressed but the first / none suppressed
+    same = np.tile(np.array([[10, 10, 50, 50]], np.float32), (200, 1))
+    d = np.concatenate([same, synth.unique_scores(200, 3)[:, None]], 1)
+    np.testing.assert_array_equal(ops.nms(dev(d), 0.5).cpu().numpy(), oracle.nms(d, 0.5))
+    far = np.stack([np.arange(300) * 100.0, np.zeros(300), np.arange(300) * 100.0 + 10, np.full(300, 10.0)], 1).astype(np.float32)
+    d = np.concatenate([far, synth.unique_scores(300, 4)[:, None]], 1)
+    np.testing.assert_array_equal(ops.nms(dev(d), 0.5).cpu().numpy(), np.arange(300))
+
+
+def test_nms_properties_full_size(ops):
+    dets = _dets(6000, 77)
+    keep = ops.nms(dev(dets), 0.7)
+    k = keep.cpu().numpy()
+    assert np.all(np.diff(k) > 0)                                    # ascending
+    again = ops.nms(dev(dets[k]), 0.7).cpu().numpy()                 # idempotent
+    np.testing.assert_array_equal(again, np.arange(len(k)))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_nms_golden(ops, tag):
+    g = golden()
+    got = ops.nms(dev(g[f"nms_{tag}_in_dets"]), float(g[f"nms_{tag}_in_thr"]))
+    np.testing.assert_array_equal(got.cpu().numpy(), g[f"nms_{tag}_out_keep"])
+
+
+def test_cpu_tensor_is_rejected(ops):
+    with pytest.raises(TypeError):
+        ops.nms(torch.zeros(4, 5), 0.5)
+    with pytest.raises(TypeError):
+        ops.CropFunction(7, 7)(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4), torch.zeros(1, dtype=torch.int32))
+
+
+# ------------------------------------------------------------------ crop_and_resize
+def _crop_case(B, C, H, W, N, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    boxes = synth.random_rois(N, seed, image=64.0, min_size=4, max_size=60)
+    boxes[0] += 0.3
+    boxes[1] -= 0.25
+    if N > 4:
+        boxes[2] = boxes[2][[2, 3, 0, 1]]       # inverted
+        boxes[3] = [0.5, 0.5, 0.5, 0.5]         # a point
+        boxes[4] = [0.0, 0.0, 1.0, 1.0]         # integer sample positions
+    ind = rng.integers(0, B, N).astype(np.int32)
+    return img, boxes, ind
+
+
+@pytest.mark.parametrize("B,C,H,W,N,ch,cw,ev", [
+    (1, 3, 16, 16, 7, 7, 7, 0.0), (2, 5, 32, 24, 33, 14, 14, 0.0), (3, 1, 64, 64, 9, 28, 28, 0.0),
+    (1, 4, 8, 8, 5, 1, 1, 0.0), (2, 2, 9, 13, 6, 1, 5, -1.5), (2, 8, 33, 17, 11, 3, 1, 2.0),
+    (2, 64, 20, 20, 40, 7, 7, 0.0), (1, 256, 16, 16, 10, 14, 14, 0.5), (2, 72, 12, 10, 13, 5, 9, 0.0)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_crop_fwd_bwd(ops, B, C, H, W, N, ch, cw, ev, channels_last):
+    img, boxes, ind = _crop_case(B, C, H, W, N, B * 100 + N + C)
+    want = oracle.crop_forward(img, boxes, ind, ch, cw, ev)
+    t = dev(img)
+    if channels_last:
+        t = cl(t)
+    t.requires_grad_(True)
+    out = ops.CropFunction(ch, cw, ev)(t, dev(boxes), dev(ind))
+    assert tuple(out.shape) == want.shape
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), want)          # bit-exact forward
+    g = np.random.default_rng(5).standard_normal(want.shape, dtype=np.float32)
+    gt = dev(g)
+    if channels_last:
+        gt = cl(gt)
+    out.backward(gt)
+    want_g = oracle.crop_backward(g, boxes, ind, img.shape)
+    assert rel_err(t.grad.cpu().numpy(), want_g) <= BWD_TOL
+    ops.check_device_errors()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_crop_golden(ops, tag):
+    g = golden()
+    want = g[f"crop_{tag}_out_crops"]
+    t = dev(g[f"crop_{tag}_in_image"]).requires_grad_(True)
+    out = ops.CropFunction(want.shape[2], want.shape[3], float(g[f"crop_{tag}_in_ev"]))(
+        t, dev(g[f"crop_{tag}_in_boxes"]), dev(g[f"crop_{tag}_in_ind"]))
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
+    out.backward(dev(g[f"crop_{tag}_in_grads"]))
+    assert rel_err(t.grad.cpu().numpy(), g[f"crop_{tag}_out_gimage"]) <= BWD_TOL
+
+
+def test_crop_bad_box_index_is_reported(ops):
+    img = torch.zeros(1, 4, 8, 8, device="cuda")
+    out = ops.CropFunction(2, 2, 3.0)(img, torch.tensor([[0., 0., 1., 1.]], device="cuda"),
+                                      torch.tensor([1], dtype=torch.int32, device="cuda"))
+    assert torch.all(out == 3.0)
+    with pytest.raises(ops.MrcnnError):
+        ops.check_device_errors()
+    ops.check_device_errors()   # flag is cleared
+
+
+def test_crop_adjoint_property(ops):
+    """<crop(x), g> == <x, crop_bwd(g)> at mask-target size (C=1, 28x28, model.py:501-502)."""
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((6, 1, 256, 256), dtype=np.float32)).cuda().requires_grad_(True)
+    boxes = dev(synth.random_rois(6, 9))
+    ind = torch.arange(6, dtype=torch.int32, device="cuda")
+    y = ops.CropFunction(28, 28, 0)(x, boxes, ind)
+    g = torch.randn_like(y)
+    y.backward(g)
+    lhs = (y.detach().double() * g.double()).sum().item()
+    rhs = (x.detach().double() * x.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+# ------------------------------------------------------------------ PyramidROIAlign
+@pytest.mark.parametrize("pool", [7, 14])
+@pytest.mark.parametrize("channels_last", [True, False])
+@pytest.mark.parametrize("B,C,size,N", [(1, 64, 512, 200), (3, 256, 256, 120), (2, 40, 512, 64)])
+def test_pyramid_roi_align(ops, pool, channels_last, B, C, size, N):
+    fms = synth.feature_pyramid(B, C, 3 + B, image=size)
+    boxes = synth.random_rois(N, 5 + N, image=float(size), min_size=6, max_size=size * 0.9)
+    ind = np.random.default_rng(N).integers(0, B, N).astype(np.int32)
+    want, lv = oracle.pyramid_roi_align_fwd(fms, boxes, ind, pool, float(size * size))
+    ts = []
+    for f in fms:
+        t = dev(f)
+        if channels_last:
+            t = cl(t)
+        ts.append(t.requires_grad_(True))
+    out = ops.pyramid_roi_align(ts, dev(boxes), dev(ind), pool, (size, size, 3))
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), want)          # bit-exact, input box order
+    g = np.random.default_rng(8).standard_normal(want.shape, dtype=np.float32)
+    out.backward(dev(g))                                                     # NCHW-contiguous incoming grad
+    want_g = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, ind, float(size * size))
+    for t, w in zip(ts, want_g):
+        assert rel_err(t.grad.cpu().numpy(), w) <= BWD_TOL
+    ops.check_device_errors()
+
+
+def test_roi_align_dropin_golden(ops):
+    g = golden()
+    size = int(g["pyr_in_image_size"])
+    for pool in (7, 14):
+        for chl in (False, True):
+            ts = []
+            for l in range(4):
+                t = dev(g[f"pyr_in_fm{l}"])
+                ts.append((cl(t) if chl else t).requires_grad_(True))
+            out = ops.roi_align([dev(g["pyr_in_boxes"]).unsqueeze(0)] + [t for t in ts], pool, [size, size, 3])
+            np.testing.assert_array_equal(out.detach().cpu().numpy(), g[f"pyr{pool}_out"])
+            out.backward(dev(g[f"pyr{pool}_in_grads"]))
+            for l in range(4):
+                assert rel_err(ts[l].grad.cpu().numpy(), g[f"pyr{pool}_out_gfm{l}"]) <= BWD_TOL
+
+
+def test_pyramid_levels_full_scale(ops):
+    """Level assignment on 1024^2 geometry: 20000 boxes incl. ones hugging the k+0.5 boundaries."""
+    from maskrcnn_b200 import _lib
+    boxes = synth.random_rois(20000, 77)
+    # boxes whose sqrt(h*w) sits within a few ulp of the level boundaries 224*2^(k-4-0.5)
+    extra = []
+    for k in (2, 3, 4):
+        s = 224.0 * 2.0 ** (k - 4 + 0.5) / 1024.0
+        for d in range(-3, 4):
+            v = np.nextafter(np.float32(s), np.float32(2.0 if d > 0 else 0.0)) if d else np.float32(s)
+            for _ in range(abs(d) - 1 if d else 0):
+                v = np.nextafter(v, np.float32(2.0 if d > 0 else 0.0))
+            extra.append([0.1, 0.1, 0.1 + v, 0.1 + v])
+    boxes = np.concatenate([boxes, np.array(extra, np.float32)], 0)
+    want = oracle.roi_levels(boxes, 1024.0 * 1024.0)
+    N = len(boxes)
+    fms = [torch.zeros((1, 4, s, s), device="cuda").contiguous(memory_format=torch.channels_last) for s in (256, 128, 64, 32)]
+    out = torch.empty((N, 4, 1, 1), device="cuda")
+    lv = torch.empty(N, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib.mrcnn_pyramid_roi_align_forward(
+        _lib.vp4([f.data_ptr() for f in fms]), _lib.i4([256, 128, 64, 32]), _lib.i4([256, 128, 64, 32]), 1, 4, _lib.NHWC,
+        dev(boxes).data_ptr(), None, N, 1, 1024.0 * 1024.0, out.data_ptr(), _lib.NHWC, lv.data_ptr(),
+        torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_array_equal(lv.cpu().numpy(), want)
+
+
+def test_roialign_linearity_full_size(ops):
+    """Size-independent property at BASELINE size (1000 RoIs x 256 ch, 1024^2 pyramid): linear in the feature map."""
+    torch.manual_seed(0)
+    a = [cl(torch.randn(1, 256, s, s, device="cuda")) for s in (256, 128, 64, 32)]
+    b = [cl(torch.randn(1, 256, s, s, device="cuda")) for s in (256, 128, 64, 32)]
+    boxes = dev(synth.random_rois(1000, 1234))
+    for pool in (7, 14):
+        ya = ops.pyramid_roi_align(a, boxes, None, pool, (1024, 1024, 3))
+        yb = ops.pyramid_roi_align(b, boxes, None, pool, (1024, 1024, 3))
+        yab = ops.pyramid_roi_align([x + 2.0 * y for x, y in zip(a, b)], boxes, None, pool, (1024, 1024, 3))
+        assert tuple(ya.shape) == (1000, 256, pool, pool)
+        err = (yab - (ya + 2.0 * yb)).abs().max().item()
+        assert err <= 1e-5 * yab.abs().max().item()
+
+
+# ------------------------------------------------------------------ proposal layer
+@pytest.mark.parametrize("size,pre,post,B", [(256, 500, 200, 1), (256, 1000, 300, 3), (512, 6000, 1000, 2), (128, 6000, 1000, 2)])
+def test_proposal_layer_matches_oracle(ops, size, pre, post, B):
+    anchors = synth.pyramid_anchors((size, size))
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 50 + i, image=float(size), n_clusters=8) for i in range(B)])
+    rois, counts = ops.proposal_layer(dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors), pre, post, 0.7,
+                                      image_hw=(size, size))
+    rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
+    for i in range(B):
+        want = oracle.proposal_layer(rcs[i], rbs[i], anchors, pre, post, 0.7, height=float(size), width=float(size))
+        assert counts[i] == len(want)
+        np.testing.assert_array_equal(rois[i, :counts[i]], want)       # bit-exact boxes and selection
+        assert not rois[i, counts[i]:].any()
+
+
+def test_proposal_layer_with_score_ties(ops):
+    """All-equal and heavily tied scores: the selection must be the stable one (lowest anchor index first)."""
+    size = 128
+    anchors = synth.pyramid_anchors((size, size))
+    A = len(anchors)
+    rng = np.random.default_rng(1)
+    rb = (rng.standard_normal((A, 4)) * 0.3).astype(np.float32)
+    for kind in ("all_equal", "few_values"):
+        fg = np.full(A, 0.5, np.float32) if kind == "all_equal" else rng.integers(0, 7, A).astype(np.float32) / 8
+        rc = np.stack([1 - fg, fg], 1).astype(np.float32)
+        rois, counts = ops.proposal_layer(dev(rc[None]), dev(rb[None]), dev(anchors), 600, 100, 0.7, image_hw=(size, size))
+        want = oracle.proposal_layer(rc, rb, anchors, 600, 100, 0.7, height=float(size), width=float(size))
+        assert int(counts[0]) == len(want)
+        np.testing.assert_array_equal(rois[0, :len(want)].cpu().numpy(), want)
+
+
+def test_proposal_golden_and_dropin(ops):
+    import types
+    g = golden()
+    size = int(g["prop_in_image_size"])
+    anchors = synth.pyramid_anchors((size, size))
+    cfg = types.SimpleNamespace(RPN_NMS_MAX_ROIS_NUM=200, RPN_NMS_THRESHOLD=0.7, RPN_BBOX_STD_DEV=[0.1, 0.1, 0.2, 0.2],
+                                IMAGE_SHAPE=np.array([size, size, 3]), GPU_COUNT=1)
+    stub = types.SimpleNamespace(config=cfg, anchors=dev(anchors))
+    got = ops.rpn_refine(stub, dev(g["prop_in_rpn_class"]).unsqueeze(0), dev(g["prop_in_rpn_bbox"]).unsqueeze(0))
+    want = g["prop_out_rois"]
+    assert tuple(got.shape) == (1,) + want.shape
+    from helpers import ulp_diff
+    assert ulp_diff(got[0].cpu().numpy(), want).max() <= 4      # reference torch.exp is not correctly rounded
+
+
+# ------------------------------------------------------------------ detection layer
+@pytest.mark.parametrize("N,B,min_conf,D", [(1000, 3, 0.0, 100), (400, 2, 0.7, 50), (70, 1, 0.0, 100), (1500, 2, 0.0, 100)])
+def test_detection_layer_matches_oracle(ops, N, B, min_conf, D):
+    NC = 81
+    rois = np.stack([synth.random_rois(N, 300 + i) for i in range(B)])
+    pd = [synth.head_outputs(N, NC, 400 + i) for i in range(B)]
+    probs = np.stack([p for p, _ in pd])
+    deltas = np.stack([d for _, d in pd])
+    windows = np.tile(np.array([[0, 0, 1024, 1024]], np.float32), (B, 1))
+    windows[-1] = [64, 32, 900, 1000]
+    dets, counts, index = ops.detection_layer(dev(rois), dev(probs), dev(deltas), dev(windows), min_conf, 0.3, D,
+                                              return_index=True)
+    dets, counts, index = dets.cpu().numpy(), counts.cpu().numpy(), index.cpu().numpy()
+    for i in range(B):
+        want, widx = oracle.detection_layer(rois[i], probs[i], deltas[i], windows[i], min_conf, 0.3, D, return_index=True)
+        assert counts[i] == len(want) and len(want) > 0
+        np.testing.assert_array_equal(dets[i, :counts[i]], want)
+        np.testing.assert_array_equal(index[i, :counts[i]], widx)
+        assert not dets[i, counts[i]:].any()
+
+
+def test_detection_golden_and_dropin(ops):
+    import types
+    g = golden()
+    cfg = types.SimpleNamespace(RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), IMAGE_SHAPE=np.array([1024, 1024, 3]),
+                                GPU_COUNT=1, DETECTION_MIN_CONFIDENCE=0, DETECTION_NMS_THRESHOLD=0.3,
+                                DETECTION_MAX_INSTANCES=100)
+    ci, sc, bx = ops.mrn_refine(types.SimpleNamespace(config=cfg), dev(g["det_in_rois"]).unsqueeze(0),
+                                dev(g["det_in_probs"]), dev(g["det_in_deltas"]), g["det_in_window"])
+    want = g["det_out"]
+    assert ci.dtype == torch.int64 and tuple(ci.shape) == (1, len(want))
+    np.testing.assert_array_equal(bx[0].cpu().numpy(), want[:, :4])
+    np.testing.assert_array_equal(sc[0].cpu().numpy(), want[:, 4])
+    np.testing.assert_array_equal(ci[0].cpu().numpy(), want[:, 5].astype(np.int64))
+    # nothing survives -> (None, None, None), model.py:1445-1447
+    probs = torch.zeros(10, 81, device="cuda")
+    probs[:, 0] = 1.0
+    assert ops.mrn_refine(types.SimpleNamespace(config=cfg), torch.rand(1, 10, 4, device="cuda"), probs,
+                          torch.zeros(10, 81, 4, device="cuda"), g["det_in_window"]) == (None, None, None)
