@@ -1,0 +1,543 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the RoI hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Headline workload (BASELINE.json configs[3], the one the north_star's >=60 %-of-HBM target is stated on):
+  training-mode PyramidROIAlign, batch 16 images x 512 sampled RoIs, 256 channels, P2..P5 of a 1024x1024 image:
+  7x7 forward + backward, 14x14 forward + backward, and the 28x28 mask-target crop (168 positives / image).
+  One "step" = that whole pass over one batch.  metric = RoIs/s (each RoI = all five ops above).
+
+  value      : device-resident inputs, CUDA-event timed, max over ranks (weak scaling: every rank owns a batch)
+  e2e        : same step through the C ABI with HOST (pinned) buffers: H2D of pyramid/boxes/upstream grads and
+               D2H of every result inside the timed region, pipelined per image over three streams
+  roofline   : dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the reference's own CPU extension (oracle/_ref, built from /root/reference)
+               driven the way model.roi_align + CropFunction.backward drive it, on the box's host cores
+  also       : the other BASELINE configs (proposal layer images/s, forward-only RoIs/s, detection path images/s)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGE = 1024
+CHANNELS = 256
+STRIDES = (4, 8, 16, 32)
+BATCH = 16
+ROIS_PER_IMAGE = 512
+MASK_POS = 168          # 512 * ROI_POSITIVE_RATIO(0.33)
+GT_PER_IMAGE = 8
+SEED = 1234 + 3
+LEVEL_HW = [(IMAGE // s, IMAGE // s) for s in STRIDES]
+PYR_ELEMS_PER_IMAGE = CHANNELS * sum(h * w for h, w in LEVEL_HW)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_boxes(batch, seed):
+    from maskrcnn_b200 import synth
+    boxes = np.concatenate([synth.random_rois(ROIS_PER_IMAGE, seed + 17 * i) for i in range(batch)], 0)
+    ind = np.repeat(np.arange(batch, dtype=np.int32), ROIS_PER_IMAGE)
+    mboxes = np.concatenate([synth.random_rois(MASK_POS, seed + 1000 + i) for i in range(batch)], 0)
+    rng = np.random.default_rng(seed)
+    mind = (np.repeat(np.arange(batch), MASK_POS) * GT_PER_IMAGE + rng.integers(0, GT_PER_IMAGE, batch * MASK_POS)).astype(np.int32)
+    return boxes, ind, mboxes, mind
+
+
+class Workload(object):
+    """Device-resident buffers + the five launches of one step, straight through the C ABI."""
+
+    def __init__(self, torch, device, batch=BATCH, seed=SEED):
+        from maskrcnn_b200 import _lib
+        self.torch, self.L, self.batch = torch, _lib, batch
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        cl = torch.channels_last
+        self.fm = [torch.randn((batch, CHANNELS, h, w), device=device, generator=g).contiguous(memory_format=cl) for h, w in LEVEL_HW]
+        self.gfm7 = [torch.empty_like(f) for f in self.fm]
+        self.gfm14 = [torch.empty_like(f) for f in self.fm]
+        boxes, ind, mboxes, mind = make_boxes(batch, seed)
+        self.boxes_np, self.ind_np = boxes, ind
+        self.boxes = torch.from_numpy(boxes).to(device)
+        self.ind = torch.from_numpy(ind).to(device)
+        self.N = len(boxes)
+        self.out7 = torch.empty((self.N, CHANNELS, 7, 7), device=device)
+        self.out14 = torch.empty((self.N, CHANNELS, 14, 14), device=device)
+        self.g7 = torch.randn((self.N, CHANNELS, 7, 7), device=device, generator=g)
+        self.g14 = torch.randn((self.N, CHANNELS, 14, 14), device=device, generator=g)
+        # mask targets: gt masks [batch*G,1,1024,1024] (binary rectangles), crop 28x28 by (image, instance) index
+        self.gt = torch.zeros((batch * GT_PER_IMAGE, 1, IMAGE, IMAGE), device=device)
+        rng = np.random.default_rng(seed + 5)
+        for k in range(batch * GT_PER_IMAGE):
+            y, x = rng.integers(0, IMAGE - 64, 2)
+            h, w = rng.integers(32, 512, 2)
+            self.gt[k, 0, y:y + h, x:x + w] = 1.0
+        self.mboxes = torch.from_numpy(mboxes).to(device)
+        self.mind = torch.from_numpy(mind).to(device)
+        self.mt = torch.empty((len(mboxes), 1, 28, 28), device=device)
+        self.Hs = _lib.i4([h for h, _ in LEVEL_HW])
+        self.Ws = _lib.i4([w for _, w in LEVEL_HW])
+        self.area = float(IMAGE * IMAGE)
+        self.launches = 0
+
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def fwd(self, pool, out):
+        L = self.L
+        L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in self.fm]), self.Hs, self.Ws, self.batch,
+                                                      CHANNELS, L.NHWC, self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool,
+                                                      self.area, out.data_ptr(), L.NCHW, None, self._s()))
+        self.launches += 1
+
+    def bwd(self, pool, grad, gfm):
+        L = self.L
+        L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, self.Hs, self.Ws, self.batch, CHANNELS,
+                                                       self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
+                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, self._s()))
+        self.launches += 1
+
+    def mask_targets(self):
+        L = self.L
+        L.check(L.lib.mrcnn_crop_forward(self.gt.data_ptr(), self.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, self.mboxes.data_ptr(),
+                                         self.mind.data_ptr(), self.mt.shape[0], 0.0, 28, 28, self.mt.data_ptr(), L.NCHW, self._s()))
+        self.launches += 1
+
+    def step(self):
+        self.fwd(7, self.out7)
+        self.fwd(14, self.out14)
+        self.mask_targets()
+        self.bwd(14, self.g14, self.gfm14)
+        self.bwd(7, self.g7, self.gfm7)
+
+    # ---- per-kernel CUDA-event timings (each op alone, back to back, inputs >> L2) ----
+    def time_op(self, fn, iters=20, warm=3):
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+
+def timed_steps(torch, dist, wl, steps, warmup, world):
+    for _ in range(warmup):
+        wl.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wl.launches = 0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        wl.step()
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------------------------------
+def e2e_run(torch, dist, wl, steps, warmup, world):
+    """Host buffers in, host buffers out, every step: per image H2D -> 5 launches -> D2H over three streams."""
+    L = wl.L
+    B = wl.batch
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()  # noqa: E731
+    # host side: NHWC pyramid per level, boxes, upstream grads; results
+    h_fm = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
+    for hf, f in zip(h_fm, wl.fm):
+        hf.copy_(f.permute(0, 2, 3, 1))
+    h_boxes = wl.boxes.cpu().pin_memory()
+    h_g7, h_g14 = pin(wl.g7), pin(wl.g14)
+    h_g7.copy_(wl.g7)
+    h_g14.copy_(wl.g14)
+    h_out7, h_out14 = pin(wl.out7), pin(wl.out14)
+    h_gf7 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
+    h_gf14 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
+    h_mboxes, h_mind, h_mt = wl.mboxes.cpu().pin_memory(), wl.mind.cpu().pin_memory(), pin(wl.mt)
+    R, M = ROIS_PER_IMAGE, MASK_POS
+    s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    fm_nhwc = [f.permute(0, 2, 3, 1) for f in wl.fm]        # views on the device buffers (physically NHWC)
+    gf7_nhwc = [f.permute(0, 2, 3, 1) for f in wl.gfm7]
+    gf14_nhwc = [f.permute(0, 2, 3, 1) for f in wl.gfm14]
+    h2d = sum(t.numel() * 4 for t in h_fm) + h_boxes.numel() * 4 + h_g7.numel() * 4 + h_g14.numel() * 4 + \
+        h_mboxes.numel() * 4 + h_mind.numel() * 4
+    d2h = h_out7.numel() * 4 + h_out14.numel() * 4 + h_mt.numel() * 4 + 2 * sum(t.numel() * 4 for t in h_fm)
+    launches = [0]
+
+    def one_step():
+        ev_in = [torch.cuda.Event() for _ in range(B)]
+        ev_run = [torch.cuda.Event() for _ in range(B)]
+        for i in range(B):
+            rs = slice(i * R, (i + 1) * R)
+            ms = slice(i * M, (i + 1) * M)
+            with torch.cuda.stream(s_in):
+                for l in range(4):
+                    fm_nhwc[l][i].copy_(h_fm[l][i], non_blocking=True)
+                wl.boxes[rs].copy_(h_boxes[rs], non_blocking=True)
+                wl.g7[rs].copy_(h_g7[rs], non_blocking=True)
+                wl.g14[rs].copy_(h_g14[rs], non_blocking=True)
+                wl.mboxes[ms].copy_(h_mboxes[ms], non_blocking=True)
+                wl.mind[ms].copy_(h_mind[ms], non_blocking=True)
+                ev_in[i].record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in[i])
+                st = s_run.cuda_stream
+                fmp = L.vp4([f[i].data_ptr() for f in wl.fm])
+                bp = wl.boxes[rs].data_ptr()
+                L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 7, wl.area,
+                                                              wl.out7[rs].data_ptr(), L.NCHW, None, st))
+                L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 14, wl.area,
+                                                              wl.out14[rs].data_ptr(), L.NCHW, None, st))
+                L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
+                                                 wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
+                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, st))
+                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, st))
+                launches[0] += 5
+                ev_run[i].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[i])
+                h_out7[rs].copy_(wl.out7[rs], non_blocking=True)
+                h_out14[rs].copy_(wl.out14[rs], non_blocking=True)
+                h_mt[ms].copy_(wl.mt[ms], non_blocking=True)
+                for l in range(4):
+                    h_gf7[l][i].copy_(gf7_nhwc[l][i], non_blocking=True)
+                    h_gf14[l][i].copy_(gf14_nhwc[l][i], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(warmup, 2))):
+        one_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(2, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / n
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": world * wl.N / dt, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": dt * 1e3, "steps": n,
+            "note": "PCIe-bound: every input and every result crosses the host link each step; per-image 3-stream pipeline"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU side: the reference's own extension (oracle/_ref) driven like model.roi_align / CropFunction.backward
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One image: 512 RoIs, 7x7 + 14x14 forward and backward + 168 mask-target crops.  Returns seconds."""
+    img_seed, use_ref = args
+    import torch
+    torch.set_num_threads(1)
+    from maskrcnn_b200 import synth
+    from maskrcnn_b200.roofline import roi_levels
+    rng = np.random.default_rng(img_seed)
+    fms = [rng.standard_normal((1, CHANNELS, h, w), dtype=np.float32) for h, w in LEVEL_HW]
+    boxes = synth.random_rois(ROIS_PER_IMAGE, img_seed)
+    mboxes = synth.random_rois(MASK_POS, img_seed + 1)
+    gt = np.zeros((GT_PER_IMAGE, 1, IMAGE, IMAGE), np.float32)
+    gt[:, :, 100:600, 200:700] = 1.0
+    mind = rng.integers(0, GT_PER_IMAGE, MASK_POS).astype(np.int32)
+    lv = roi_levels(boxes, float(IMAGE * IMAGE))
+    if use_ref:
+        from oracle import reference
+        C = reference.ref_C()
+        tf = [torch.from_numpy(f) for f in fms]
+        tb = torch.from_numpy(boxes)
+        sel = [torch.from_numpy(np.nonzero(lv == l)[0]) for l in (2, 3, 4, 5)]
+        t0 = time.perf_counter()
+        with reference.quiet_stdout():
+            for pool in (7, 14):
+                for l in range(4):          # model.py:347-377, one crop per populated level
+                    if len(sel[l]) == 0:
+                        continue
+                    lb = tb[sel[l]]
+                    ind = torch.zeros(len(lb), dtype=torch.int32)
+                    crops = torch.zeros_like(tf[l])                      # __init__.py:36
+                    C.crop_forward(tf[l], lb, ind, 0.0, pool, pool, crops)
+                    g = torch.ones_like(crops)
+                    gi = torch.zeros_like(g).resize_(*tf[l].shape)       # __init__.py:52
+                    C.crop_backward(g, lb, ind, gi)
+            mt = torch.zeros(1)
+            C.crop_forward(torch.from_numpy(gt), torch.from_numpy(mboxes), torch.from_numpy(mind), 0.0, 28, 28, mt)
+        return time.perf_counter() - t0
+    import oracle
+    t0 = time.perf_counter()
+    for pool in (7, 14):
+        out, _ = oracle.pyramid_roi_align_fwd(fms, boxes, None, pool, float(IMAGE * IMAGE))
+        oracle.pyramid_roi_align_bwd(np.ones_like(out), [f.shape for f in fms], boxes, None, float(IMAGE * IMAGE))
+    oracle.crop_forward(gt, mboxes, mind, 28, 28, 0.0)
+    return time.perf_counter() - t0
+
+
+def cpu_measure(images, procs):
+    """RoIs/s of the CPU path over `images` images spread over `procs` worker processes."""
+    from oracle import reference
+    use_ref = reference.ref_C_available()
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if procs <= 1:
+        for i in range(images):
+            _cpu_worker((SEED + i, use_ref))
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(_cpu_worker, [(SEED + i, use_ref) for i in range(images)])
+    dt = time.perf_counter() - t0
+    return images * ROIS_PER_IMAGE / dt, dt, ("reference" if use_ref else "port")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    per_step_images = procs                       # one image per worker per step
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_measure(min(per_step_images, 2), min(procs, 2))
+    steps = max(1, min(args.steps, 3))
+    vals, secs = [], []
+    kind = "port"
+    for _ in range(steps):
+        v, dt, kind = cpu_measure(per_step_images, procs)
+        vals.append(v)
+        secs.append(dt)
+    value = float(np.mean(vals))
+    sample = "%d images x %d RoIs per step (7x7+14x14 fwd+bwd + %d mask crops each), image-parallel over %d processes" % (
+        per_step_images, ROIS_PER_IMAGE, MASK_POS, procs)
+    line = {"impl": "reference", "metric": "roialign_train_rois_per_s", "value": value, "unit": "RoIs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": "RoIs/s", "cores": procs, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cores": cores}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "BASELINE configs[3]: training-mode PyramidROIAlign fwd+bwd, batch %d x %d RoIs x %d ch, P2-P5 of %dx%d, "
+                        "7x7 + 14x14 + %d 28x28 mask-target crops/img" % (BATCH, ROIS_PER_IMAGE, CHANNELS, IMAGE, IMAGE, MASK_POS),
+            "batch_per_gpu": BATCH, "rois_per_image": ROIS_PER_IMAGE, "channels": CHANNELS,
+            "feature_layout": "channels_last (NHWC) pyramid, NCHW crops/grads", "parallelism": "image-sharded replicas, no collective",
+            "l2": "inputs (1.43 GB pyramid + 2 GB crops per step) are larger than L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def secondary(torch, wl, hbm):
+    """The other BASELINE configs, each timed alone with CUDA events (N=1, rank 0)."""
+    import maskrcnn_b200 as m
+    from maskrcnn_b200 import synth, roofline
+    out = {}
+    dev = "cuda"
+    # configs[1]: proposal layer, batch 8, 261,888 anchors, 6000 -> NMS 0.7 -> 1000
+    anchors = synth.pyramid_anchors((IMAGE, IMAGE))
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 1235 + i) for i in range(8)])
+    rc, rb, an = torch.from_numpy(np.stack(rcs)).to(dev), torch.from_numpy(np.stack(rbs)).to(dev), torch.from_numpy(anchors).to(dev)
+    f = lambda: m.proposal_layer(rc, rb, an, 6000, 1000, 0.7)  # noqa: E731
+    t = wl.time_op(f, iters=20)
+    _, counts = f()
+    by = 8 * roofline.proposal_bytes(len(anchors), 6000, 1000)
+    out["proposal_layer"] = {"config": "configs[1]: 261,888 anchors, top-6000 -> NMS 0.7 -> 1000, batch 8", "images_per_s": 8 / t,
+                             "ms_per_batch": t * 1e3, "kept_mean": float(counts.float().mean().item()),
+                             "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+                             "note": "latency-bound (sequential sweep + multi-pass select); 3 launches per batch"}
+    # configs[2]: forward only, 1000 RoIs x 256 ch on one image
+    boxes_np = synth.random_rois(1000, 1234)
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    fm1 = [f_[:1] for f_ in wl.fm]
+    for pool in (7, 14):
+        g = lambda: m.pyramid_roi_align(fm1, boxes, None, pool, (IMAGE, IMAGE, 3), out_channels_last=False)  # noqa: E731
+        t = wl.time_op(g, iters=50)
+        U, _ = roofline.unique_taps(boxes_np, None, pool, (IMAGE, IMAGE), LEVEL_HW, 1)
+        by = roofline.roialign_fwd_bytes(1000, CHANNELS, pool, U)
+        out["roialign_fwd_%dx%d" % (pool, pool)] = {"config": "configs[2]: 1000 RoIs x 256 ch, one image (warm L2: 89 MB pyramid fits)",
+                                                    "rois_per_s": 1000 / t, "us": t * 1e6, "algorithmic_MB": by / 1e6,
+                                                    "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm}
+    # configs[4]: detection layer + mask RoIAlign on the detections, 64 images
+    B, N, NC = 64, 1000, 81
+    rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(B)])).to(dev)
+    g_ = torch.Generator(device=dev)
+    g_.manual_seed(7)
+    probs = torch.softmax(3.0 * torch.randn((B, N, NC), device=dev, generator=g_), -1)
+    deltas = 0.1 * torch.randn((B, N, NC, 4), device=dev, generator=g_)
+    win = torch.tensor([[0., 0., IMAGE, IMAGE]], device=dev).repeat(B, 1)
+    fm64 = wl.fm  # 16 images of pyramid; detections of image i read pyramid i % 16
+    def det_path():
+        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, 100)
+        b = (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4)
+        ind = (torch.arange(B, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(100)
+        return m.pyramid_roi_align(fm64, b, ind, 14, (IMAGE, IMAGE, 3)), counts
+    t = wl.time_op(det_path, iters=20)
+    t_det = wl.time_op(lambda: m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, 100), iters=20)
+    out["detection_path"] = {"config": "configs[4]: detection layer (81 classes, 1000 RoIs, NMS 0.3, top-100) + 14x14 mask RoIAlign, 64 images",
+                             "images_per_s": B / t, "ms_per_64_images": t * 1e3, "detection_layer_only_images_per_s": B / t_det,
+                             "frac_of_hbm_detection_layer": B * roofline.detection_bytes(N, NC, 100) / t_det / 1e9 / hbm}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="timed steps only (use under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm, peak_src = hbm_peak()
+    wl = Workload(torch, torch.device("cuda", local))
+
+    with ClockSampler(local) as cs:
+        ms = timed_steps(torch, dist, wl, args.steps, args.warmup, world)
+    launches = wl.launches
+    clocks = cs.summary()
+    per_step = ms / args.steps
+    value = world * wl.N / (per_step * 1e-3)
+
+    line = {"metric": "roialign_train_rois_per_s", "value": value, "unit": "RoIs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(), "clocks": clocks, "gpu_launches": launches}
+
+    if not args.no_extras:
+        from maskrcnn_b200 import roofline
+        # per-kernel breakdown, each op alone (burst), CUDA events on the launching stream
+        U7, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 7, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
+        U14, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 14, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
+        pyr = wl.batch * PYR_ELEMS_PER_IMAGE
+        ops = {
+            "roialign_fwd_nhwc_kernel<7x7>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
+            "roialign_fwd_nhwc_kernel<14x14>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
+            "memset+roialign_bwd_nhwc_kernel<7x7>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
+            "memset+roialign_bwd_nhwc_kernel<14x14>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
+            "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
+        }
+        kern = {}
+        for name, (fn, by) in ops.items():
+            t = wl.time_op(fn)
+            kern[name] = {"ms": t * 1e3, "algorithmic_MB": by / 1e6, "GBps": by / t / 1e9, "frac": by / t / 1e9 / hbm}
+        total = sum(k["ms"] for k in kern.values())
+        for k in kern.values():
+            k["share_of_step"] = k["ms"] / total
+        top = max(kern, key=lambda n: kern[n]["ms"])
+        line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": kern[top]["GBps"], "peak": hbm, "unit": "GB/s",
+                            "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
+                            "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
+                            "kernels": kern}
+        line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)
+        if rank == 0 and world == 1:
+            cores = os.cpu_count() or 1
+            v, dt, kind = cpu_measure(2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": 1, "kind": kind, "host_cores": cores,
+                                    "sample": "2 images x %d RoIs (same five ops), single thread as the reference ships, %.1f s" % (ROIS_PER_IMAGE, dt)}
+            line["also"] = secondary(torch, wl, hbm)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
