@@ -146,6 +146,7 @@ class Workload(object):
         self.Hs = _lib.i4([h for h, _ in LEVEL_HW])
         self.Ws = _lib.i4([w for _, w in LEVEL_HW])
         self.area = float(IMAGE * IMAGE)
+        self.offsets = _lib.i32_array([i * ROIS_PER_IMAGE for i in range(batch + 1)])  # host: boxes grouped by image
         self.launches = 0
 
     def _s(self):
@@ -162,8 +163,8 @@ class Workload(object):
         L = self.L
         L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, self.Hs, self.Ws, self.batch, CHANNELS,
                                                        self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
-                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, self._s()))
-        self.launches += 1
+                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, self.offsets, self._s()))
+        self.launches += 2 * self.batch   # per image: zero_levels_kernel + roialign_bwd_nhwc_kernel
 
     def mask_targets(self):
         L = self.L
@@ -272,10 +273,10 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
                                                  wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, st))
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, st))
-                launches[0] += 5
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, st))
+                launches[0] += 7
                 ev_run[i].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[i])
@@ -441,6 +442,25 @@ def secondary(torch, wl, hbm):
         out["roialign_fwd_%dx%d" % (pool, pool)] = {"config": "configs[2]: 1000 RoIs x 256 ch, one image (warm L2: 89 MB pyramid fits)",
                                                     "rois_per_s": 1000 / t, "us": t * 1e6, "algorithmic_MB": by / 1e6,
                                                     "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm}
+    # the same training step with channels-last crops and upstream gradients (a channels_last model end to end)
+    cl = torch.channels_last
+    o7, o14 = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
+    g7, g14 = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=cl)
+    L = wl.L
+    def step_nhwc():
+        for pool, o in ((7, o7), (14, o14)):
+            L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC,
+                                                          wl.boxes.data_ptr(), wl.ind.data_ptr(), wl.N, pool, wl.area, o.data_ptr(), L.NHWC,
+                                                          None, wl._s()))
+        wl.mask_targets()
+        for pool, g, gf in ((14, g14, wl.gfm14), (7, g7, wl.gfm7)):
+            L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NHWC, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
+                                                           wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gf]),
+                                                           L.NHWC, 1, wl.offsets, wl._s()))
+    t = wl.time_op(step_nhwc, iters=20)
+    out["train_step_all_channels_last"] = {"config": "configs[3] with channels-last crops and gradients", "rois_per_s": wl.N / t,
+                                           "ms_per_step": t * 1e3}
+    del o7, o14, g7, g14
     # configs[4]: detection layer + mask RoIAlign on the detections, 64 images
     B, N, NC = 64, 1000, 81
     rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(B)])).to(dev)

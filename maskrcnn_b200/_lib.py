@@ -26,7 +26,7 @@ SIGNATURES = {
     "mrcnn_crop_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _i, _vp]),
     "mrcnn_crop_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrcnn_pyramid_roi_align_forward": (_i, [_vp4, _i4, _i4, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp]),
-    "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp]),
+    "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp, _vp]),
     "mrcnn_nms_workspace_bytes": (_sz, [_i]),
     "mrcnn_nms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_proposal_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -71,6 +71,14 @@ def i4(vals):
 
 def vp4(vals):
     return _vp4(*[int(v) for v in vals])
+
+
+def i32_array(vals):
+    """Host int32 array (e.g. image_offsets_host) or None."""
+    if vals is None:
+        return None
+    arr = (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+    return arr
 
 
 def f4(vals):

@@ -53,6 +53,13 @@ struct RoiCtx {
     bool ok;
 };
 
+// Axis tap staged in shared memory with element offsets pre-multiplied (rows: y*W*C, cols: x*C).
+struct __align__(16) TapS {
+    int lo, hi;
+    float lerp;
+    int valid;
+};
+
 __device__ __forceinline__ RoiCtx select_level(const RoiParams& p, int n, float4& box) {
     box.x = __ldg(p.boxes + 4 * n + 0);
     box.y = __ldg(p.boxes + 4 * n + 1);
@@ -74,96 +81,175 @@ __device__ __forceinline__ RoiCtx select_level(const RoiParams& p, int n, float4
     return c;
 }
 
+// Stage the ph + pw taps of this RoI.  Threads [0,ph) do rows, threads [64,64+pw) do columns.
+__device__ __forceinline__ void stage_taps(const RoiParams& p, const RoiCtx& ctx, const float4 box, int ph, int pw,
+                                           TapS* s_ty, TapS* s_tx) {
+    const int tid = threadIdx.x;
+    if (tid < ph) {
+        const AxisTap t = axis_tap(box.x, box.z, ctx.H, ph, tid);
+        TapS o;
+        o.valid = (t.lo >= 0) && ctx.ok;
+        o.lo = o.valid ? t.lo * ctx.W * p.C : 0;
+        o.hi = o.valid ? t.hi * ctx.W * p.C : 0;
+        o.lerp = t.lerp;
+        s_ty[tid] = o;
+    } else if (tid >= 64 && tid < 64 + pw) {
+        const AxisTap t = axis_tap(box.y, box.w, ctx.W, pw, tid - 64);
+        TapS o;
+        o.valid = (t.lo >= 0) && ctx.ok;
+        o.lo = o.valid ? t.lo * p.C : 0;
+        o.hi = o.valid ? t.hi * p.C : 0;
+        o.lerp = t.lerp;
+        s_tx[tid - 64] = o;
+    }
+}
+
+// Linear copy between a contiguous global [rows][P2] block and the padded shared tile [rows][P2pad],
+// four consecutive elements per thread and iteration; (row, col) advance incrementally (one division
+// per thread, not per element).  kToShared: global -> tile (backward), else tile -> global (forward).
+template <bool kToShared>
+__device__ __forceinline__ void tile_copy(float* tile, float* g, int total, int P2, int P2pad) {
+    const int tid = threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
+    const int step = kThreads * 4;
+    const int step_r = step / P2, step_c = step - step_r * P2;
+    int e = tid * 4;
+    int r = e / P2, c = e - r * P2;
+    for (; e < total; e += step) {
+        int rr[4], cc[4];
+        rr[0] = r;
+        cc[0] = c;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            cc[j] = cc[j - 1] + 1;
+            rr[j] = rr[j - 1];
+            if (cc[j] == P2) {
+                cc[j] = 0;
+                rr[j] += 1;
+            }
+        }
+        if (vec && e + 3 < total) {
+            if (kToShared) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(g + e));
+                tile[rr[0] * P2pad + cc[0]] = v.x;
+                tile[rr[1] * P2pad + cc[1]] = v.y;
+                tile[rr[2] * P2pad + cc[2]] = v.z;
+                tile[rr[3] * P2pad + cc[3]] = v.w;
+            } else {
+                float4 v;
+                v.x = tile[rr[0] * P2pad + cc[0]];
+                v.y = tile[rr[1] * P2pad + cc[1]];
+                v.z = tile[rr[2] * P2pad + cc[2]];
+                v.w = tile[rr[3] * P2pad + cc[3]];
+                __stcs(reinterpret_cast<float4*>(g + e), v);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (e + j < total) {
+                    if (kToShared) tile[rr[j] * P2pad + cc[j]] = __ldcs(g + e + j);
+                    else __stcs(g + e + j, tile[rr[j] * P2pad + cc[j]]);
+                }
+            }
+        }
+        r += step_r;
+        c += step_c;
+        if (c >= P2) {
+            c -= P2;
+            r += 1;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Forward, channels-last input.  grid = (N, ceil(C/64)), block = 256, dyn smem = 64*(P2|1)*4 (NCHW out).
+// POOL > 0: compile-time pool size (7, 14); POOL == 0: runtime ph x pw.
 // ------------------------------------------------------------------------------------------------
-template <bool kOutNHWC>
-__global__ void __launch_bounds__(kThreads) roialign_fwd_nhwc_kernel(const RoiParams p) {
+template <int POOL, bool kOutNHWC>
+__global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const RoiParams p) {
     extern __shared__ __align__(16) float tile[];
-    __shared__ AxisTap s_ty[kMaxPool];
-    __shared__ AxisTap s_tx[kMaxPool];
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
 
+    const int ph = POOL ? POOL : p.ph;
+    const int pw = POOL ? POOL : p.pw;
     const int n = blockIdx.x;
     const int c0 = blockIdx.y * kChunk;
     const int tid = threadIdx.x;
-    const int P2 = p.ph * p.pw;
+    const int P2 = ph * pw;
     const int P2pad = P2 | 1;
+    const int C = p.C;
 
     float4 box;
     const RoiCtx ctx = select_level(p, n, box);
-    if (tid < p.ph) s_ty[tid] = axis_tap(box.x, box.z, ctx.H, p.ph, tid);
-    if (tid >= 64 && tid < 64 + p.pw) s_tx[tid - 64] = axis_tap(box.y, box.w, ctx.W, p.pw, tid - 64);
+    stage_taps(p, ctx, box, ph, pw, s_ty, s_tx);
     __syncthreads();
 
     const int lane = tid & (kLanes - 1);
     const int slot = tid >> 4;
     const int c = c0 + 4 * lane;
-    const bool c_ok = c < p.C;  // C % 4 == 0 is guaranteed by the launcher
+    const bool c_ok = c < C;  // C % 4 == 0 is guaranteed by the launcher
     const float* src = ctx.base + c;
-    const int C = p.C;
-    const int W = ctx.W;
+    float* out_nhwc = p.crops + (size_t)n * P2 * C + c;
 
-    for (int b0 = slot; b0 < P2; b0 += 2 * kSlots) {
-        float4 tl[2], tr[2], bl[2], br[2];
-        float xl[2], yl[2];
-        bool live[2], inside[2];
+    if (c_ok) {
+#pragma unroll 1
+        for (int b0 = slot; b0 < P2; b0 += 2 * kSlots) {
+            float4 tl[2], tr[2], bl[2], br[2];
+            float xl[2], yl[2];
+            bool inside[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int b = b0 + u * kSlots;
-            live[u] = (b < P2) && c_ok;
-            inside[u] = false;
-            if (live[u]) {
-                const int y = b / p.pw;
-                const int x = b - y * p.pw;
-                const AxisTap ty = s_ty[y];
-                const AxisTap tx = s_tx[x];
-                inside[u] = ctx.ok && ty.lo >= 0 && tx.lo >= 0;
-                if (inside[u]) {
-                    const float* r0 = src + (size_t)ty.lo * W * C;
-                    const float* r1 = src + (size_t)ty.hi * W * C;
-                    tl[u] = ldg_f4(r0 + (size_t)tx.lo * C);
-                    tr[u] = ldg_f4(r0 + (size_t)tx.hi * C);
-                    bl[u] = ldg_f4(r1 + (size_t)tx.lo * C);
-                    br[u] = ldg_f4(r1 + (size_t)tx.hi * C);
-                    xl[u] = tx.lerp;
-                    yl[u] = ty.lerp;
+            for (int u = 0; u < 2; ++u) {
+                const int b = b0 + u * kSlots;
+                inside[u] = false;
+                if (b < P2) {
+                    const int y = b / pw;
+                    const int x = b - y * pw;
+                    const TapS ty = s_ty[y];
+                    const TapS tx = s_tx[x];
+                    inside[u] = ty.valid && tx.valid;
+                    if (inside[u]) {
+                        const float* r0 = src + ty.lo;
+                        const float* r1 = src + ty.hi;
+                        tl[u] = ldg_f4(r0 + tx.lo);
+                        tr[u] = ldg_f4(r0 + tx.hi);
+                        bl[u] = ldg_f4(r1 + tx.lo);
+                        br[u] = ldg_f4(r1 + tx.hi);
+                        xl[u] = tx.lerp;
+                        yl[u] = ty.lerp;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!live[u]) continue;
-            const int b = b0 + u * kSlots;
-            float4 v;
-            if (inside[u]) {
-                v.x = bilerp(tl[u].x, tr[u].x, bl[u].x, br[u].x, xl[u], yl[u]);
-                v.y = bilerp(tl[u].y, tr[u].y, bl[u].y, br[u].y, xl[u], yl[u]);
-                v.z = bilerp(tl[u].z, tr[u].z, bl[u].z, br[u].z, xl[u], yl[u]);
-                v.w = bilerp(tl[u].w, tr[u].w, bl[u].w, br[u].w, xl[u], yl[u]);
-            } else {
-                v = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
-            }
-            if (kOutNHWC) {
-                stg_f4_stream(p.crops + ((size_t)n * P2 + b) * C + c, v);
-            } else {
-                float* t = tile + (4 * lane) * P2pad + b;
-                t[0] = v.x;
-                t[P2pad] = v.y;
-                t[2 * P2pad] = v.z;
-                t[3 * P2pad] = v.w;
+            for (int u = 0; u < 2; ++u) {
+                const int b = b0 + u * kSlots;
+                if (b >= P2) continue;
+                float4 v;
+                if (inside[u]) {
+                    v.x = bilerp(tl[u].x, tr[u].x, bl[u].x, br[u].x, xl[u], yl[u]);
+                    v.y = bilerp(tl[u].y, tr[u].y, bl[u].y, br[u].y, xl[u], yl[u]);
+                    v.z = bilerp(tl[u].z, tr[u].z, bl[u].z, br[u].z, xl[u], yl[u]);
+                    v.w = bilerp(tl[u].w, tr[u].w, bl[u].w, br[u].w, xl[u], yl[u]);
+                } else {
+                    v = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+                }
+                if (kOutNHWC) {
+                    stg_f4_stream(out_nhwc + (size_t)b * C, v);
+                } else {
+                    float* t = tile + (4 * lane) * P2pad + b;
+                    t[0] = v.x;
+                    t[P2pad] = v.y;
+                    t[2 * P2pad] = v.z;
+                    t[3 * P2pad] = v.w;
+                }
             }
         }
     }
     if (!kOutNHWC) {
         __syncthreads();
         const int cc = min(kChunk, C - c0);
-        const int total = cc * P2;
-        float* dst = p.crops + ((size_t)n * C + c0) * P2;  // contiguous [cc][P2] block of the NCHW output
-        for (int e = tid; e < total; e += kThreads) {
-            const int ch = e / P2;
-            const int b = e - ch * P2;
-            __stcs(dst + e, tile[ch * P2pad + b]);
-        }
+        // contiguous [cc][P2] block of the NCHW output
+        tile_copy<false>(tile, p.crops + ((size_t)n * C + c0) * P2, cc * P2, P2, P2pad);
     }
 }
 
@@ -172,47 +258,38 @@ __global__ void __launch_bounds__(kThreads) roialign_fwd_nhwc_kernel(const RoiPa
 //
 // Column aggregation: for one output row y of the RoI, all pw bins share (y_lo, y_hi, y_lerp) and hit
 // columns x_lo(x), x_hi(x), which are non-decreasing in x.  Each (slot, lane) owner walks the bins of
-// its row in x order and keeps a running float4 sum per feature-map column; it flushes one
+// its row (segment) in x order and keeps a running float4 sum per feature-map column; it flushes one
 // red.v4 per DISTINCT column (times two rows) instead of four per bin.  When the RoI is up-sampled
 // (fewer feature columns than bins, the common case for the 14x14 mask head) this removes most atomics.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flush_col(float* row0, float* row1, int col, int C, float4 acc, float yl, bool two_rows) {
-    // d(top) = (1 - yl) * g-weighted, d(bottom) = yl * g-weighted  (crop_cpu.cpp:254-260, regrouped)
+__device__ __forceinline__ void flush_col(float* row0, float* row1, int col_off, float4 acc, float yl, bool two_rows) {
+    // d(top) = (1 - yl) * s, d(bottom) = yl * s with s = sum_x w_x * g  (crop_cpu.cpp:254-260, regrouped)
     const float w0 = __fsub_rn(1.0f, yl);
-    float4 a = make_float4(acc.x * w0, acc.y * w0, acc.z * w0, acc.w * w0);
-    red_add_f4(row0 + (size_t)col * C, a);
-    if (two_rows) {
-        float4 b = make_float4(acc.x * yl, acc.y * yl, acc.z * yl, acc.w * yl);
-        red_add_f4(row1 + (size_t)col * C, b);
-    }
+    red_add_f4(row0 + col_off, make_float4(acc.x * w0, acc.y * w0, acc.z * w0, acc.w * w0));
+    if (two_rows) red_add_f4(row1 + col_off, make_float4(acc.x * yl, acc.y * yl, acc.z * yl, acc.w * yl));
 }
 
-template <bool kGradNHWC>
+template <int POOL, bool kGradNHWC>
 __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiParams p) {
     extern __shared__ __align__(16) float tile[];
-    __shared__ AxisTap s_ty[kMaxPool];
-    __shared__ AxisTap s_tx[kMaxPool];
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
 
+    const int ph = POOL ? POOL : p.ph;
+    const int pw = POOL ? POOL : p.pw;
     const int n = blockIdx.x;
     const int c0 = blockIdx.y * kChunk;
     const int tid = threadIdx.x;
-    const int P2 = p.ph * p.pw;
+    const int P2 = ph * pw;
     const int P2pad = P2 | 1;
     const int C = p.C;
 
     float4 box;
     const RoiCtx ctx = select_level(p, n, box);
-    if (tid < p.ph) s_ty[tid] = axis_tap(box.x, box.z, ctx.H, p.ph, tid);
-    if (tid >= 64 && tid < 64 + p.pw) s_tx[tid - 64] = axis_tap(box.y, box.w, ctx.W, p.pw, tid - 64);
+    stage_taps(p, ctx, box, ph, pw, s_ty, s_tx);
     if (!kGradNHWC) {
         const int cc = min(kChunk, C - c0);
-        const int total = cc * P2;
-        const float* g = p.crops + ((size_t)n * C + c0) * P2;
-        for (int e = tid; e < total; e += kThreads) {
-            const int ch = e / P2;
-            const int b = e - ch * P2;
-            tile[ch * P2pad + b] = __ldcs(g + e);
-        }
+        tile_copy<true>(tile, p.crops + ((size_t)n * C + c0) * P2, cc * P2, P2, P2pad);
     }
     __syncthreads();
     if (!ctx.ok) return;
@@ -222,43 +299,43 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
     const int c = c0 + 4 * lane;
     if (c >= C) return;
     float* dst = ctx.base + c;
-    const int W = ctx.W;
+    const float* g_nhwc = p.crops + (size_t)n * P2 * C + c;
 
     // Work items = (output row, column segment).  With few rows (7x7) each row is split into segments so
     // that all 16 slots have work; aggregation then happens within a segment.
-    const int segs = (p.ph >= kSlots) ? 1 : min(p.pw, kSlots / p.ph);
-    const int items = p.ph * segs;
+    const int segs = (ph >= kSlots) ? 1 : min(pw, kSlots / ph);
+    const int items = ph * segs;
     for (int it = slot; it < items; it += kSlots) {
         const int y = it / segs;
         const int seg = it - y * segs;
-        const int xbeg = (seg * p.pw) / segs;
-        const int xend = ((seg + 1) * p.pw) / segs;
-        const AxisTap ty = s_ty[y];
-        if (ty.lo < 0) continue;
-        float* row0 = dst + (size_t)ty.lo * W * C;
-        float* row1 = dst + (size_t)ty.hi * W * C;
+        const int xbeg = (seg * pw) / segs;
+        const int xend = ((seg + 1) * pw) / segs;
+        const TapS ty = s_ty[y];
+        if (!ty.valid) continue;
+        float* row0 = dst + ty.lo;
+        float* row1 = dst + ty.hi;
         const bool two_rows = ty.lerp != 0.0f;  // lerp == 0 <=> hi == lo: nothing goes to a second row
-        int cur = -1;                           // feature column accumulated in acc; nxt is column cur + 1
+        int cur = -1;                           // element offset of the column accumulated in acc; nxt is the column after it
         bool has_nxt = false;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int x = xbeg; x < xend; ++x) {
-            const AxisTap tx = s_tx[x];
-            if (tx.lo < 0) continue;
+            const TapS tx = s_tx[x];
+            if (!tx.valid) continue;
             float4 g;
-            const int b = y * p.pw + x;
+            const int b = y * pw + x;
             if (kGradNHWC) {
-                g = ldg_f4_stream(p.crops + ((size_t)n * P2 + b) * C + c);
+                g = ldg_f4_stream(g_nhwc + (size_t)b * C);
             } else {
                 const float* t = tile + (4 * lane) * P2pad + b;
                 g = make_float4(t[0], t[P2pad], t[2 * P2pad], t[3 * P2pad]);
             }
             if (tx.lo != cur) {
                 if (cur >= 0) {
-                    flush_col(row0, row1, cur, C, acc, ty.lerp, two_rows);
-                    if (has_nxt && tx.lo != cur + 1) flush_col(row0, row1, cur + 1, C, nxt, ty.lerp, two_rows);
+                    flush_col(row0, row1, cur, acc, ty.lerp, two_rows);
+                    if (has_nxt && tx.lo != cur + C) flush_col(row0, row1, cur + C, nxt, ty.lerp, two_rows);
                 }
-                acc = (cur >= 0 && has_nxt && tx.lo == cur + 1) ? nxt : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc = (cur >= 0 && has_nxt && tx.lo == cur + C) ? nxt : make_float4(0.f, 0.f, 0.f, 0.f);
                 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
                 has_nxt = false;
                 cur = tx.lo;
@@ -268,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
             acc.y += wl * g.y;
             acc.z += wl * g.z;
             acc.w += wl * g.w;
-            if (tx.lerp != 0.0f) {  // <=> hi == lo + 1
+            if (tx.lerp != 0.0f) {  // <=> hi == lo + 1 column
                 nxt.x += tx.lerp * g.x;
                 nxt.y += tx.lerp * g.y;
                 nxt.z += tx.lerp * g.z;
@@ -277,9 +354,25 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
             }
         }
         if (cur >= 0) {
-            flush_col(row0, row1, cur, C, acc, ty.lerp, two_rows);
-            if (has_nxt) flush_col(row0, row1, cur + 1, C, nxt, ty.lerp, two_rows);
+            flush_col(row0, row1, cur, acc, ty.lerp, two_rows);
+            if (has_nxt) flush_col(row0, row1, cur + C, nxt, ty.lerp, two_rows);
         }
+    }
+}
+
+// Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
+struct ZeroParams {
+    float4* ptr[4];
+    long long n4[4];  // float4 elements per buffer
+};
+
+__global__ void __launch_bounds__(256) zero_levels_kernel(const ZeroParams z) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        float4* q = z.ptr[l];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < z.n4[l]; i += stride) q[i] = zero;
     }
 }
 
@@ -428,13 +521,20 @@ static int launch_roi(const RoiParams& p, int image_layout, int crops_layout, bo
             MRCNN_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         KERNEL<<<grid, kThreads, smem, stream>>>(p);                                                       \
     } while (0)
+#define MRCNN_DISPATCH_POOL(NAME, FLAG)                                             \
+    do {                                                                            \
+        if (p.ph == 7 && p.pw == 7) MRCNN_LAUNCH_NHWC((NAME<7, FLAG>));             \
+        else if (p.ph == 14 && p.pw == 14) MRCNN_LAUNCH_NHWC((NAME<14, FLAG>));     \
+        else MRCNN_LAUNCH_NHWC((NAME<0, FLAG>));                                    \
+    } while (0)
         if (!backward) {
-            if (crops_layout == MRCNN_NHWC) MRCNN_LAUNCH_NHWC(roialign_fwd_nhwc_kernel<true>);
-            else MRCNN_LAUNCH_NHWC(roialign_fwd_nhwc_kernel<false>);
+            if (crops_layout == MRCNN_NHWC) MRCNN_DISPATCH_POOL(roialign_fwd_nhwc_kernel, true);
+            else MRCNN_DISPATCH_POOL(roialign_fwd_nhwc_kernel, false);
         } else {
-            if (crops_layout == MRCNN_NHWC) MRCNN_LAUNCH_NHWC(roialign_bwd_nhwc_kernel<true>);
-            else MRCNN_LAUNCH_NHWC(roialign_bwd_nhwc_kernel<false>);
+            if (crops_layout == MRCNN_NHWC) MRCNN_DISPATCH_POOL(roialign_bwd_nhwc_kernel, true);
+            else MRCNN_DISPATCH_POOL(roialign_bwd_nhwc_kernel, false);
         }
+#undef MRCNN_DISPATCH_POOL
 #undef MRCNN_LAUNCH_NHWC
     } else {
         GenericParams gp;
@@ -448,6 +548,25 @@ static int launch_roi(const RoiParams& p, int image_layout, int crops_layout, bo
         if (!backward) crop_generic_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(gp);
         else crop_generic_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(gp);
     }
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+static int launch_zero(float* const ptr[4], const size_t elems[4], int nbuf, cudaStream_t stream) {
+    ZeroParams z = {};
+    bool any = false, vec = true;
+    for (int l = 0; l < nbuf; ++l) vec = vec && aligned16(ptr[l]) && (elems[l] % 4 == 0);
+    if (!vec) {
+        for (int l = 0; l < nbuf; ++l) MRCNN_CUDA(cudaMemsetAsync(ptr[l], 0, sizeof(float) * elems[l], stream));
+        return MRCNN_OK;
+    }
+    for (int l = 0; l < nbuf; ++l) {
+        z.ptr[l] = reinterpret_cast<float4*>(ptr[l]);
+        z.n4[l] = (long long)(elems[l] / 4);
+        any = any || elems[l] > 0;
+    }
+    if (!any) return MRCNN_OK;
+    zero_levels_kernel<<<sm_count() * 8, 256, 0, stream>>>(z);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }
@@ -547,32 +666,67 @@ int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], co
 int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const int H[4], const int W[4], int B,
                                      int C, const float* boxes, const int32_t* box_index, int N, int pool,
                                      float image_area, float* const gfm[4], int gfm_layout, int zero_fill,
-                                     mrcnn_stream_t stream) {
+                                     const int32_t* image_offsets_host, mrcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward: null level tables");
     MRCNN_REQUIRE(B > 0 && C > 0 && N >= 0 && pool > 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_backward: bad sizes");
     if (int rc = check_layout(gfm_layout, "gfm_layout")) return rc;
     if (int rc = check_layout(grads_layout, "grads_layout")) return rc;
     RoiParams p = {};
+    size_t per_image[4];
     for (int l = 0; l < 4; ++l) {
         MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_backward: level %d has empty shape", l);
         MRCNN_REQUIRE_DEV(gfm[l]);
         p.lv[l] = {gfm[l], H[l], W[l]};
-        if (zero_fill)
-            MRCNN_CUDA(cudaMemsetAsync(gfm[l], 0, sizeof(float) * (size_t)B * C * H[l] * W[l], (cudaStream_t)stream));
+        per_image[l] = (size_t)C * H[l] * W[l];
     }
-    if (N == 0) return MRCNN_OK;
-    MRCNN_REQUIRE_DEV(grads);
-    MRCNN_REQUIRE_DEV(boxes);
-    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    if (N > 0) {
+        MRCNN_REQUIRE_DEV(grads);
+        MRCNN_REQUIRE_DEV(boxes);
+        if (box_index && !image_offsets_host) MRCNN_REQUIRE_DEV(box_index);
+    }
     p.pyramid = 1;
     p.rule = make_level_rule(image_area);
-    p.B = B; p.C = C;
-    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.C = C;
     p.ph = pool; p.pw = pool; p.extrap = 0.f;
-    p.crops = const_cast<float*>(grads);
     p.err = device_error_word();
     MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
-    return launch_roi(p, gfm_layout, grads_layout, true, (cudaStream_t)stream);
+
+    if (image_offsets_host == nullptr) {
+        if (zero_fill) {
+            size_t elems[4];
+            for (int l = 0; l < 4; ++l) elems[l] = per_image[l] * (size_t)B;
+            if (int rc = launch_zero(gfm, elems, 4, stream)) return rc;
+        }
+        if (N == 0) return MRCNN_OK;
+        p.B = B;
+        p.boxes = boxes; p.box_index = box_index; p.N = N;
+        p.crops = const_cast<float*>(grads);
+        return launch_roi(p, gfm_layout, grads_layout, true, stream);
+    }
+    // image-by-image: clear one image's pyramid slice, then scatter that image's boxes into it
+    MRCNN_REQUIRE(image_offsets_host[0] == 0 && image_offsets_host[B] == N,
+                  "mrcnn_pyramid_roi_align_backward: image_offsets_host must run from 0 to N");
+    const size_t crop_elems = (size_t)C * pool * pool;
+    for (int i = 0; i < B; ++i) {
+        const int beg = image_offsets_host[i], end = image_offsets_host[i + 1];
+        MRCNN_REQUIRE(beg <= end, "mrcnn_pyramid_roi_align_backward: image_offsets_host must be non-decreasing");
+        float* slice[4];
+        for (int l = 0; l < 4; ++l) {
+            slice[l] = gfm[l] + (size_t)i * per_image[l];
+            p.lv[l].ptr = slice[l];
+        }
+        if (zero_fill)
+            if (int rc = launch_zero(slice, per_image, 4, stream)) return rc;
+        if (end == beg) continue;
+        p.B = 1;
+        p.boxes = boxes + (size_t)4 * beg;
+        p.box_index = nullptr;
+        p.N = end - beg;
+        p.crops = const_cast<float*>(grads) + (size_t)beg * crop_elems;
+        if (int rc = launch_roi(p, gfm_layout, grads_layout, true, stream)) return rc;
+    }
+    return MRCNN_OK;
 }
 
 }  // extern "C"

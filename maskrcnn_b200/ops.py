@@ -10,6 +10,8 @@ Reference interface being mirrored (paths relative to /root/reference):
 
 There is no CPU implementation: CPU tensors raise TypeError, a missing library raises ImportError.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -172,7 +174,7 @@ def _pyramid_layout(fms):
 
 class _PyramidRoiAlign(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, boxes, box_ind, pool, image_area, out_layout, p2, p3, p4, p5):
+    def forward(ctx, boxes, box_ind, pool, image_area, out_layout, offsets, p2, p3, p4, p5):
         fms, fl = _pyramid_layout([p2, p3, p4, p5])
         B, C = fms[0].shape[:2]
         N = boxes.size(0)
@@ -186,28 +188,33 @@ class _PyramidRoiAlign(torch.autograd.Function):
                                                           B, C, fl, boxes.data_ptr(), _ptr(box_ind), N, pool,
                                                           float(image_area), out.data_ptr(), ol, None, _stream()))
         ctx.save_for_backward(boxes, box_ind)
-        ctx.meta = (Hs, Ws, B, C, fl, pool, float(image_area))
+        ctx.meta = (Hs, Ws, B, C, fl, pool, float(image_area), offsets)
         return out
 
     @staticmethod
     def backward(ctx, grad):
         boxes, box_ind = ctx.saved_tensors
-        Hs, Ws, B, C, fl, pool, image_area = ctx.meta
+        Hs, Ws, B, C, fl, pool, image_area, offsets = ctx.meta
         grad, gl = _layout4(grad)
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
         with torch.cuda.device(grad.device):
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,
-                                                       _lib.vp4([g.data_ptr() for g in gfm]), fl, 1, _stream()))
-        return (None, None, None, None, None) + tuple(gfm)
+                                                       _lib.vp4([g.data_ptr() for g in gfm]), fl, 1,
+                                                       ctypes.cast(_lib.i32_array(offsets), ctypes.c_void_p) if offsets else None,
+                                                       _stream()))
+        return (None, None, None, None, None, None) + tuple(gfm)
 
 
-def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_channels_last=None):
+def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_channels_last=None,
+                      rois_per_image=None):
     """Batched PyramidROIAlign.  feature_maps: [P2,P3,P4,P5], each [B,C,Hl,Wl] (NCHW or channels-last; the
     channels-last layout runs the 128-bit vectorised kernels).  boxes [N,4] normalised (not differentiated,
     model.py:358), box_ind [N] int32 image index or None (all image 0).  Returns [N,C,pool,pool] in box order;
-    memory format follows the feature maps unless out_channels_last is given."""
+    memory format follows the feature maps unless out_channels_last is given.
+    rois_per_image: optional host-side list of B counts (or one int) stating that boxes are grouped by image in
+    order (box_ind, if given, must agree); lets the backward clear + scatter image by image (L2-resident)."""
     for i, f in enumerate(feature_maps):
         _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
     _require_cuda(boxes, "boxes", torch.float32)
@@ -219,7 +226,17 @@ def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_
         box_ind = box_ind.contiguous()
     image_area = float(image_shape[0] * image_shape[1])  # model.py:331
     ol = None if out_channels_last is None else (NHWC if out_channels_last else NCHW)
-    return _PyramidRoiAlign.apply(boxes, box_ind, int(pool_size), image_area, ol, *feature_maps)
+    offsets = None
+    if rois_per_image is not None:
+        B = feature_maps[0].size(0)
+        counts = [int(rois_per_image)] * B if np.isscalar(rois_per_image) else [int(v) for v in rois_per_image]
+        if len(counts) != B or sum(counts) != boxes.size(0):
+            raise ValueError("rois_per_image must list one count per image and sum to the number of boxes")
+        offsets = tuple(int(v) for v in np.concatenate([[0], np.cumsum(counts)]))
+        if box_ind is None and B > 1:
+            box_ind = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=boxes.device),
+                                              torch.tensor(counts, device=boxes.device))
+    return _PyramidRoiAlign.apply(boxes, box_ind, int(pool_size), image_area, ol, offsets, *feature_maps)
 
 
 def roi_align(inputs, pool_size, image_shape):

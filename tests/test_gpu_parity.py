@@ -332,3 +332,25 @@ def test_detection_golden_and_dropin(ops):
     probs[:, 0] = 1.0
     assert ops.mrn_refine(types.SimpleNamespace(config=cfg), torch.rand(1, 10, 4, device="cuda"), probs,
                           torch.zeros(10, 81, 4, device="cuda"), g["det_in_window"]) == (None, None, None)
+
+
+@pytest.mark.parametrize("pool", [7, 14, 5])
+@pytest.mark.parametrize("out_cl", [True, False])
+def test_pyramid_grouped_by_image_backward(ops, pool, out_cl):
+    """rois_per_image: per-image clear + scatter in the backward; channels-last crops and upstream grads."""
+    B, C, size = 3, 128, 256
+    counts = [40, 0, 75]
+    fms = synth.feature_pyramid(B, C, 11, image=size)
+    boxes = synth.random_rois(sum(counts), 12, image=float(size), min_size=6, max_size=size * 0.9)
+    ind = np.repeat(np.arange(B), counts).astype(np.int32)
+    want, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, pool, float(size * size))
+    ts = [cl(dev(f)).requires_grad_(True) for f in fms]
+    out = ops.pyramid_roi_align(ts, dev(boxes), None, pool, (size, size, 3), out_channels_last=out_cl, rois_per_image=counts)
+    assert out.is_contiguous(memory_format=torch.channels_last if out_cl else torch.contiguous_format)
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
+    g = np.random.default_rng(8).standard_normal(want.shape, dtype=np.float32)
+    gt = dev(g)
+    out.backward(cl(gt) if out_cl else gt)
+    want_g = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, ind, float(size * size))
+    for t, w in zip(ts, want_g):
+        assert rel_err(t.grad.cpu().numpy(), w) <= BWD_TOL
