@@ -163,8 +163,8 @@ class Workload(object):
         L = self.L
         L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, self.Hs, self.Ws, self.batch, CHANNELS,
                                                        self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
-                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, self.offsets, self._s()))
-        self.launches += 2 * self.batch   # per image: zero_levels_kernel + roialign_bwd_nhwc_kernel
+                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, None, None, 0, self._s()))
+        self.launches += 2   # zero_levels_kernel + roialign_bwd_nhwc_kernel
 
     def mask_targets(self):
         L = self.L
@@ -273,9 +273,9 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
                                                  wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, st))
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, None, 0, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, st))
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, None, 0, st))
                 launches[0] += 7
                 ev_run[i].record(s_run)
             with torch.cuda.stream(s_out):
@@ -447,6 +447,7 @@ def secondary(torch, wl, hbm):
     o7, o14 = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
     g7, g14 = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=cl)
     L = wl.L
+    ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N), dtype=torch.uint8, device=dev)
     def step_nhwc():
         for pool, o in ((7, o7), (14, o14)):
             L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC,
@@ -456,7 +457,7 @@ def secondary(torch, wl, hbm):
         for pool, g, gf in ((14, g14, wl.gfm14), (7, g7, wl.gfm7)):
             L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NHWC, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
                                                            wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gf]),
-                                                           L.NHWC, 1, wl.offsets, wl._s()))
+                                                           L.NHWC, 1, None, ws.data_ptr(), ws.numel(), wl._s()))
     t = wl.time_op(step_nhwc, iters=20)
     out["train_step_all_channels_last"] = {"config": "configs[3] with channels-last crops and gradients", "rois_per_s": wl.N / t,
                                            "ms_per_step": t * 1e3}

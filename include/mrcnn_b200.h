@@ -90,17 +90,25 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
                                     float image_area, float* out, int out_layout,
                                     int32_t* levels_out, mrcnn_stream_t stream);
 
-/* Adjoint of the forward: grads [N,C,pool,pool] (grads_layout) scatter-added into gfm[l] [B,C,H[l],W[l]]
- * (gfm_layout), cleared first when zero_fill != 0 (what CropFunction.backward does per level,
- * c++ext/maskrcnn/__init__.py:52).  image_offsets_host: optional HOST array of B+1 ints; when given, the
- * boxes of image i are exactly rows [off[i], off[i+1]) (training batches are laid out like that) and
- * box_index is ignored: the call then clears and scatters image by image, so that each image's
- * gradient pyramid (89 MB at 1024^2 x 256 ch) is still L2-resident when the reductions hit it. */
+/* Adjoint of the forward: grads [N,C,pool,pool] (grads_layout) accumulated into gfm[l] [B,C,H[l],W[l]]
+ * (gfm_layout), which is cleared first when zero_fill != 0 (what CropFunction.backward does per level,
+ * c++ext/maskrcnn/__init__.py:52).
+ * Two implementations sit behind this entry point:
+ *   - pixel-owner GATHER (no atomics, every gradient pixel written exactly once, bit-reproducible): used
+ *     when grads and gfm are both MRCNN_NHWC, C % 4 == 0, N <= 8192 and a workspace of at least
+ *     mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N) bytes (256-byte aligned) is supplied;
+ *   - SCATTER with column-aggregated 128-bit vector reductions (red.global.add.v4.f32) otherwise
+ *     (channels-last gfm), or scalar atomics (NCHW gfm).  workspace may be NULL for these.
+ * image_offsets_host: optional HOST array of B+1 ints for the scatter path; when given, the boxes of
+ * image i are exactly rows [off[i], off[i+1]) and box_index is ignored: the call then clears and
+ * scatters image by image. */
+MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N);
 MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout,
                                      const int H[4], const int W[4], int B, int C,
                                      const float* boxes, const int32_t* box_index, int N, int pool,
                                      float image_area, float* const gfm[4], int gfm_layout,
                                      int zero_fill, const int32_t* image_offsets_host,
+                                     void* workspace, size_t workspace_bytes,
                                      mrcnn_stream_t stream);
 
 /* ---- NMS (replaces nms(), nms.h:15-30 -> cpu/nms_cpu.cpp:11-70) -------------------------------- */

@@ -17,8 +17,10 @@
 //     feature maps and the C=1 mask-target crop (model.py:501-502).
 //
 // HBM-bound: algorithmic bytes per RoI = C*p*p*4 (output) + unique taps*C*4, see DESIGN.md.
+#include <limits.h>
+
 #include "api_util.h"
-#include "common.cuh"
+#include "nms_core.cuh"
 
 namespace mrcnn {
 
@@ -360,6 +362,261 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward as a GATHER (pixel-owner) — channels-last gradients in, channels-last pyramid gradient out.
+//
+// Every 8x8 tile of every (image, level) gradient map is owned by one CTA, which sums the contributions
+// of all RoIs of that (image, level) that reach the tile and writes each pixel exactly once.  No atomics,
+// no separate zero fill, no read-modify-write: DRAM traffic is the algorithmic minimum (upstream gradient
+// read once, gradient pyramid written once), and the summation order is fixed -> bit-reproducible.
+//
+//   pass 1  roi_bin_kernel (one CTA): key = image*4 + level per RoI, sorted (key, index) -> CSR lists.
+//   pass 2  roialign_bwd_gather_kernel: grid = tiles; 1024 threads = 64 channel lanes (float4) x 16 pixel
+//           slots (4 pixels each).  Per tile: cull the (image, level) list by footprint, then per surviving
+//           RoI stage the separable weights wy[8][ph], wx[8][pw] of the tile's rows/columns in shared
+//           memory and accumulate  acc(y,x) += wy[y][by] * wx[x][bx] * g[r][by][bx][c]  with one 128-bit
+//           load per (pixel, bin, lane): a warp reads 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGTile = 8;             // tile side in feature-map pixels
+constexpr int kGThreads = 1024;
+constexpr int kGLanes = 64;           // float4 channel lanes -> 256 channels per pass
+constexpr int kGSlots = kGThreads / kGLanes;                  // 16
+constexpr int kGPix = kGTile * kGTile / kGSlots;              // 4 pixels per thread
+constexpr int kBinMaxN = 8192;        // RoIs sortable by the one-CTA binning kernel
+
+struct GatherParams {
+    PyrLevel lv[4];
+    int tiles_x[4], tiles_y[4];
+    int tile_base[5];  // prefix of tiles per image over levels
+    LevelRule rule;
+    int B, C, N;
+    int ph, pw;
+    const float* boxes;
+    const float* grads;       // [N][ph*pw][C]
+    const int32_t* list;      // RoI indices sorted by (image, level), ascending index inside a key
+    const int32_t* offsets;   // [4B + 1]
+    int accumulate;           // 0: overwrite (zero_fill semantics); 1: add to what is there
+};
+
+// composite keys are sorted descending -> ascending (key, index)
+__global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_index,
+                                                       int N, int P, int B, LevelRule rule, int32_t* __restrict__ list,
+                                                       int32_t* __restrict__ offsets, int* err) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(bin_smem);
+    int* cnt = reinterpret_cast<int*>(bin_smem + (size_t)P * 8);  // [4B + 1]
+    const int K = 4 * B;
+    const int tid = threadIdx.x;
+    for (int k = tid; k <= K; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    for (int n = tid; n < P; n += blockDim.x) {
+        uint64_t key = 0ull;
+        if (n < N) {
+            const float y1 = __ldg(boxes + 4 * n), x1 = __ldg(boxes + 4 * n + 1);
+            const float y2 = __ldg(boxes + 4 * n + 2), x2 = __ldg(boxes + 4 * n + 3);
+            const int bi = box_index ? __ldg(box_index + n) : 0;
+            if ((unsigned)bi < (unsigned)B) {
+                const int k = bi * 4 + roi_level(y1, x1, y2, x2, rule) - 2;
+                atomicAdd(&cnt[k], 1);
+                key = ((uint64_t)(uint32_t)(K - k) << 32) | (uint64_t)(0xffffffffu - (uint32_t)n);
+            } else {
+                atomicOr(err, 1);
+            }
+        }
+        skeys[n] = key;
+    }
+    __syncthreads();
+    block_bitonic_desc(skeys, P, 0u, 2u, 1u, (unsigned)P);
+    for (int j = tid; j < N; j += blockDim.x) {
+        const uint64_t kv = skeys[j];
+        list[j] = kv ? (int32_t)(0xffffffffu - (uint32_t)(kv & 0xffffffffu)) : -1;
+    }
+    if (tid < 32) {  // exclusive scan of cnt[0..K) by one warp
+        int carry = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + tid;
+            const int v = (k < K) ? cnt[k] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += u;
+            }
+            if (k < K) offsets[k] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) offsets[K] = carry;
+    }
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kGThreads, 1) roialign_bwd_gather_kernel(const GatherParams p) {
+    constexpr int kMaxHits = 1024;
+    __shared__ int s_hits[kMaxHits];
+    __shared__ int s_nhits;
+    __shared__ float s_wy[kGTile][kMaxPool];
+    __shared__ float s_wx[kGTile][kMaxPool];
+    __shared__ int s_yr[kGTile][2];  // [lo, hi] bin range with non-zero weight per tile row
+    __shared__ int s_xr[kGTile][2];
+
+    const int ph = POOL ? POOL : p.ph;
+    const int pw = POOL ? POOL : p.pw;
+    const int P2 = ph * pw;
+    const int tid = threadIdx.x;
+    const int lane = tid & (kGLanes - 1);
+    const int slot = tid >> 6;
+    const int warp = tid >> 5;
+    const int wl = tid & 31;
+
+    // which tile
+    const int tiles_per_image = p.tile_base[4];
+    const int img = blockIdx.x / tiles_per_image;
+    int t = blockIdx.x - img * tiles_per_image;
+    int l = 0;
+    while (l < 3 && t >= p.tile_base[l + 1]) ++l;
+    t -= p.tile_base[l];
+    const PyrLevel L = (l == 0) ? p.lv[0] : (l == 1) ? p.lv[1] : (l == 2) ? p.lv[2] : p.lv[3];
+    const int ntx = (l == 0) ? p.tiles_x[0] : (l == 1) ? p.tiles_x[1] : (l == 2) ? p.tiles_x[2] : p.tiles_x[3];
+    const int ty0 = (t / ntx) * kGTile;
+    const int tx0 = (t - (t / ntx) * ntx) * kGTile;
+    const int H = L.H, W = L.W, C = p.C;
+    float* out = L.ptr + (size_t)img * H * W * C;
+
+    const int lbeg = __ldg(p.offsets + img * 4 + l);
+    const int lend = __ldg(p.offsets + img * 4 + l + 1);
+
+    for (int cbase = 0; cbase < C; cbase += 4 * kGLanes) {
+        const int c = cbase + 4 * lane;
+        const bool c_ok = c < C;
+        float4 acc[kGPix];
+#pragma unroll
+        for (int k = 0; k < kGPix; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int chunk = lbeg; chunk < lend; chunk += kMaxHits) {
+            // ---- cull: which RoIs of this (image, level) reach the tile? ----
+            if (tid == 0) s_nhits = 0;
+            __syncthreads();
+            {
+                const int j = chunk + tid;
+                bool hit = false;
+                int r = -1;
+                if (j < lend) {
+                    r = __ldg(p.list + j);
+                    const float y1 = __ldg(p.boxes + 4 * r), x1 = __ldg(p.boxes + 4 * r + 1);
+                    const float y2 = __ldg(p.boxes + 4 * r + 2), x2 = __ldg(p.boxes + 4 * r + 3);
+                    // conservative footprint (one pixel of slack) from the first / last sample positions
+                    const float ya = y1 * (float)(H - 1), yb = (ph > 1) ? y2 * (float)(H - 1) : ya;
+                    const float xa = x1 * (float)(W - 1), xb = (pw > 1) ? x2 * (float)(W - 1) : xa;
+                    const float ylo = fminf(ya, yb) - 1.5f, yhi = fmaxf(ya, yb) + 1.5f;
+                    const float xlo = fminf(xa, xb) - 1.5f, xhi = fmaxf(xa, xb) + 1.5f;
+                    if (ph == 1 || pw == 1) hit = true;  // centre sampling: keep it simple, never cull
+                    else hit = (yhi >= (float)ty0) && (ylo <= (float)(ty0 + kGTile - 1)) && (xhi >= (float)tx0) &&
+                               (xlo <= (float)(tx0 + kGTile - 1));
+                }
+                // ordered compaction (keeps ascending RoI index -> fixed summation order)
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                __shared__ int s_wcnt[32];
+                if (wl == 0) s_wcnt[warp] = __popc(m);
+                __syncthreads();
+                if (warp == 0) {
+                    int v = s_wcnt[wl];
+                    int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (wl >= o) incl += u;
+                    }
+                    s_wcnt[wl] = incl - v;
+                    if (wl == 31) s_nhits = incl;
+                }
+                __syncthreads();
+                if (hit) s_hits[s_wcnt[warp] + __popc(m & ((1u << wl) - 1u))] = r;
+            }
+            __syncthreads();
+            const int nh = s_nhits;
+
+            // ---- accumulate the surviving RoIs one after another ----
+            for (int h = 0; h < nh; ++h) {
+                const int r = s_hits[h];
+                // weights of this RoI for the 8 rows / 8 columns of the tile: warps 0-7 rows, 8-15 columns
+                if (warp < 2 * kGTile) {
+                    const bool is_row = warp < kGTile;
+                    const int line = is_row ? warp : warp - kGTile;            // row / column inside the tile
+                    const int pix = (is_row ? ty0 : tx0) + line;               // feature-map coordinate
+                    const int nb = is_row ? ph : pw;
+                    const float a1 = __ldg(p.boxes + 4 * r + (is_row ? 0 : 1));
+                    const float a2 = __ldg(p.boxes + 4 * r + (is_row ? 2 : 3));
+                    const int size = is_row ? H : W;
+                    int lo = INT_MAX, hi = -1;
+                    for (int b0 = 0; b0 < nb; b0 += 32) {
+                        const int b = b0 + wl;
+                        float w = 0.f;
+                        if (b < nb) {
+                            const AxisTap tp = axis_tap(a1, a2, size, nb, b);
+                            if (tp.lo >= 0) {
+                                // crop_cpu.cpp:254-260: (1 - lerp) goes to the floor tap, lerp to the ceil tap
+                                if (tp.lo == pix) w = __fsub_rn(1.0f, tp.lerp);
+                                else if (tp.hi == pix) w = tp.lerp;
+                            }
+                            (is_row ? s_wy : s_wx)[line][b] = w;
+                        }
+                        const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
+                        if (nz) {
+                            lo = min(lo, b0 + __ffs(nz) - 1);
+                            hi = max(hi, b0 + 31 - __clz(nz));
+                        }
+                    }
+                    if (wl == 0) {
+                        (is_row ? s_yr : s_xr)[line][0] = lo;
+                        (is_row ? s_yr : s_xr)[line][1] = hi;
+                    }
+                }
+                __syncthreads();
+                if (c_ok) {
+                    const float* g = p.grads + (size_t)r * P2 * C + c;
+#pragma unroll
+                    for (int k = 0; k < kGPix; ++k) {
+                        const int pidx = slot + k * kGSlots;
+                        const int yy = pidx >> 3, xx = pidx & 7;
+                        const int by0 = s_yr[yy][0], by1 = s_yr[yy][1];
+                        const int bx0 = s_xr[xx][0], bx1 = s_xr[xx][1];
+                        for (int by = by0; by <= by1; ++by) {
+                            const float wy = s_wy[yy][by];
+                            const float* grow = g + (size_t)(by * pw) * C;
+                            for (int bx = bx0; bx <= bx1; ++bx) {
+                                const float w = wy * s_wx[xx][bx];
+                                const float4 v = ldg_f4(grow + (size_t)bx * C);
+                                acc[k].x = fmaf(w, v.x, acc[k].x);
+                                acc[k].y = fmaf(w, v.y, acc[k].y);
+                                acc[k].z = fmaf(w, v.z, acc[k].z);
+                                acc[k].w = fmaf(w, v.w, acc[k].w);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- every pixel of the tile is written exactly once ----
+        if (c_ok) {
+#pragma unroll
+            for (int k = 0; k < kGPix; ++k) {
+                const int pidx = slot + k * kGSlots;
+                const int y = ty0 + (pidx >> 3), x = tx0 + (pidx & 7);
+                if (y < H && x < W) {
+                    float* o = out + ((size_t)y * W + x) * C + c;
+                    float4 v = acc[k];
+                    if (p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(o);
+                        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(o) = v;
+                }
+            }
+        }
+    }
+}
+
 // Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
 struct ZeroParams {
     float4* ptr[4];
@@ -571,6 +828,59 @@ static int launch_zero(float* const ptr[4], const size_t elems[4], int nbuf, cud
     return MRCNN_OK;
 }
 
+static size_t gather_workspace_bytes(int B, int N) {
+    return align_up((size_t)(N > 0 ? N : 1) * 4, 256) + align_up((size_t)(4 * (size_t)B + 1) * 4, 256);
+}
+
+// true if the gather backward can serve this call
+static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int grads_layout, const float* grads,
+                            float* const gfm[4], const void* workspace, size_t workspace_bytes) {
+    if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
+    if ((C % 4) != 0 || pool > kMaxPool || N > kBinMaxN || N <= 0) return false;
+    if (workspace == nullptr || workspace_bytes < gather_workspace_bytes(B, N)) return false;
+    if ((size_t)(4 * (size_t)B + 1) * 4 > 96 * 1024) return false;
+    if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
+    for (int l = 0; l < 4; ++l)
+        if (!aligned16(gfm[l])) return false;
+    return true;
+}
+
+static int launch_bwd_gather(const float* grads, const int H[4], const int W[4], int B, int C, const float* boxes,
+                             const int32_t* box_index, int N, int pool, float image_area, float* const gfm[4],
+                             int accumulate, void* workspace, cudaStream_t stream) {
+    int32_t* list = reinterpret_cast<int32_t*>(workspace);
+    int32_t* offsets = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + align_up((size_t)N * 4, 256));
+    const LevelRule rule = make_level_rule(image_area);
+    int P = 32;
+    while (P < N) P <<= 1;
+    const size_t bin_smem = (size_t)P * 8 + (size_t)(4 * B + 1) * 4;
+    MRCNN_CUDA(cudaFuncSetAttribute(roi_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, P, B, rule, list, offsets, device_error_word());
+    MRCNN_LAUNCH_CHECK();
+    GatherParams g = {};
+    int total = 0;
+    for (int l = 0; l < 4; ++l) {
+        g.lv[l] = {gfm[l], H[l], W[l]};
+        g.tiles_x[l] = (W[l] + kGTile - 1) / kGTile;
+        g.tiles_y[l] = (H[l] + kGTile - 1) / kGTile;
+        g.tile_base[l] = total;
+        total += g.tiles_x[l] * g.tiles_y[l];
+    }
+    g.tile_base[4] = total;
+    g.rule = rule;
+    g.B = B; g.C = C; g.N = N;
+    g.ph = pool; g.pw = pool;
+    g.boxes = boxes; g.grads = grads; g.list = list; g.offsets = offsets;
+    g.accumulate = accumulate;
+    const long long grid = (long long)total * B;
+    MRCNN_REQUIRE(grid < (1ll << 31), "mrcnn_pyramid_roi_align_backward: too many tiles");
+    if (pool == 7) roialign_bwd_gather_kernel<7><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
+    else if (pool == 14) roialign_bwd_gather_kernel<14><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
+    else roialign_bwd_gather_kernel<0><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
 static int check_layout(int v, const char* what) {
     if (v != MRCNN_NCHW && v != MRCNN_NHWC) return fail(MRCNN_E_INVALID_ARG, "%s must be MRCNN_NCHW or MRCNN_NHWC", what);
     return MRCNN_OK;
@@ -581,6 +891,11 @@ static int check_layout(int v, const char* what) {
 using namespace mrcnn;
 
 extern "C" {
+
+size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N) {
+    if (B <= 0 || N < 0) return 256;
+    return gather_workspace_bytes(B, N);
+}
 
 int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout, const float* boxes,
                        const int32_t* box_index, int N, float extrapolation_value, int crop_h, int crop_w,
@@ -666,7 +981,8 @@ int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], co
 int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const int H[4], const int W[4], int B,
                                      int C, const float* boxes, const int32_t* box_index, int N, int pool,
                                      float image_area, float* const gfm[4], int gfm_layout, int zero_fill,
-                                     const int32_t* image_offsets_host, mrcnn_stream_t stream_) {
+                                     const int32_t* image_offsets_host, void* workspace, size_t workspace_bytes,
+                                     mrcnn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward: null level tables");
     MRCNN_REQUIRE(B > 0 && C > 0 && N >= 0 && pool > 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_backward: bad sizes");
@@ -692,6 +1008,12 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
     p.err = device_error_word();
     MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
 
+    if (image_offsets_host == nullptr &&
+        gather_eligible(B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes)) {
+        // pixel-owner gather: writes every pixel once (zero fill included), no atomics
+        return launch_bwd_gather(grads, H, W, B, C, boxes, box_index, N, pool, image_area, gfm, zero_fill ? 0 : 1, workspace,
+                                 stream);
+    }
     if (image_offsets_host == nullptr) {
         if (zero_fill) {
             size_t elems[4];

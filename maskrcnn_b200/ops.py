@@ -199,11 +199,13 @@ class _PyramidRoiAlign(torch.autograd.Function):
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
         with torch.cuda.device(grad.device):
+            ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,
                                                        _lib.vp4([g.data_ptr() for g in gfm]), fl, 1,
                                                        ctypes.cast(_lib.i32_array(offsets), ctypes.c_void_p) if offsets else None,
-                                                       _stream()))
+                                                       ws.data_ptr(), ws_bytes, _stream()))
         return (None, None, None, None, None, None) + tuple(gfm)
 
 
