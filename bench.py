@@ -447,7 +447,7 @@ def secondary(torch, wl, hbm):
     o7, o14 = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
     g7, g14 = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=cl)
     L = wl.L
-    ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N), dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, 14), dtype=torch.uint8, device=dev)
     def step_nhwc():
         for pool, o in ((7, o7), (14, o14)):
             L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC,

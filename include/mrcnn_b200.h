@@ -96,13 +96,13 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
  * Two implementations sit behind this entry point:
  *   - pixel-owner GATHER (no atomics, every gradient pixel written exactly once, bit-reproducible): used
  *     when grads and gfm are both MRCNN_NHWC, C % 4 == 0, N <= 8192 and a workspace of at least
- *     mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N) bytes (256-byte aligned) is supplied;
+ *     mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool) bytes (256-byte aligned) is supplied;
  *   - SCATTER with column-aggregated 128-bit vector reductions (red.global.add.v4.f32) otherwise
  *     (channels-last gfm), or scalar atomics (NCHW gfm).  workspace may be NULL for these.
  * image_offsets_host: optional HOST array of B+1 ints for the scatter path; when given, the boxes of
  * image i are exactly rows [off[i], off[i+1]) and box_index is ignored: the call then clears and
  * scatters image by image. */
-MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N);
+MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N, int pool);
 MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout,
                                      const int H[4], const int W[4], int B, int C,
                                      const float* boxes, const int32_t* box_index, int N, int pool,

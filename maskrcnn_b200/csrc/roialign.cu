@@ -377,30 +377,37 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
 //           memory and accumulate  acc(y,x) += wy[y][by] * wx[x][bx] * g[r][by][bx][c]  with one 128-bit
 //           load per (pixel, bin, lane): a warp reads 512 contiguous bytes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGTile = 8;             // tile side in feature-map pixels
-constexpr int kGThreads = 1024;
-constexpr int kGLanes = 64;           // float4 channel lanes -> 256 channels per pass
-constexpr int kGSlots = kGThreads / kGLanes;                  // 16
-constexpr int kGPix = kGTile * kGTile / kGSlots;              // 4 pixels per thread
-constexpr int kBinMaxN = 8192;        // RoIs sortable by the one-CTA binning kernel
+constexpr int kGTile = 8;       // tile side in feature-map pixels
+constexpr int kGThreads = 256;
+constexpr int kGLanes = 64;     // float4 channel lanes -> 256 channels per pass
+constexpr int kGSlots = kGThreads / kGLanes;      // 4 pixel slots
+constexpr int kGPix = kGTile * kGTile / kGSlots;  // 16 pixels per thread, processed one after another
+constexpr int kGMaxHits = 2048; // RoIs per tile handled in one epoch
+constexpr int kBinMaxN = 8192;  // RoIs sortable by the one-CTA binning kernel
+
+struct __align__(8) GTap {
+    int lo;      // floor tap index; the ceil tap is lo + 1 iff lerp != 0.  Invalid: a large negative number.
+    float lerp;
+};
 
 struct GatherParams {
     PyrLevel lv[4];
-    int tiles_x[4], tiles_y[4];
+    int tiles_x[4];
     int tile_base[5];  // prefix of tiles per image over levels
-    LevelRule rule;
     int B, C, N;
     int ph, pw;
-    const float* boxes;
-    const float* grads;       // [N][ph*pw][C]
-    const int32_t* list;      // RoI indices sorted by (image, level), ascending index inside a key
-    const int32_t* offsets;   // [4B + 1]
-    int accumulate;           // 0: overwrite (zero_fill semantics); 1: add to what is there
+    const float* grads;      // [N][ph*pw][C]
+    const int32_t* rid;      // [N] RoI index at sorted position j ((image, level) major, index minor); -1 = skipped
+    const int4* bbox;        // [N] {ylo, yhi, xlo, xhi} pixel footprint of position j (empty if ylo > yhi)
+    const float4* rp;        // [N] {y p0, 1/y scale, x p0, 1/x scale}: sample position of bin b ~ p0 + b*scale
+    const GTap* taps;        // [N][ph + pw]
+    const int32_t* offsets;  // [4B + 1] positions of each (image, level) segment
+    int accumulate;          // 0: overwrite (zero_fill semantics); 1: add to what is there
 };
 
-// composite keys are sorted descending -> ascending (key, index)
+// pass 1a: composite keys sorted descending -> ascending (image*4 + level, index); CSR offsets.
 __global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_index,
-                                                       int N, int P, int B, LevelRule rule, int32_t* __restrict__ list,
+                                                       int N, int P, int B, LevelRule rule, int32_t* __restrict__ rid,
                                                        int32_t* __restrict__ offsets, int* err) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(bin_smem);
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__
     block_bitonic_desc(skeys, P, 0u, 2u, 1u, (unsigned)P);
     for (int j = tid; j < N; j += blockDim.x) {
         const uint64_t kv = skeys[j];
-        list[j] = kv ? (int32_t)(0xffffffffu - (uint32_t)(kv & 0xffffffffu)) : -1;
+        rid[j] = kv ? (int32_t)(0xffffffffu - (uint32_t)(kv & 0xffffffffu)) : -1;
     }
     if (tid < 32) {  // exclusive scan of cnt[0..K) by one warp
         int carry = 0;
@@ -449,15 +456,98 @@ __global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__
     }
 }
 
+// pass 1b: one 128-thread CTA per sorted position: the ph + pw taps, the pixel footprint and the
+// affine sample-position model used to bound the bin search.
+__global__ void __launch_bounds__(128) roi_taps_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ rid,
+                                                       int N, int ph, int pw, LevelRule rule, PyrLevel l0, PyrLevel l1,
+                                                       PyrLevel l2, PyrLevel l3, int4* __restrict__ bbox,
+                                                       float4* __restrict__ rp, GTap* __restrict__ taps) {
+    __shared__ int s_min[2], s_max[2];
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int r = __ldg(rid + j);
+    if (tid < 2) {
+        s_min[tid] = INT_MAX;
+        s_max[tid] = INT_MIN;
+    }
+    __syncthreads();
+    GTap* out = taps + (size_t)j * (ph + pw);
+    if (r < 0) {
+        if (tid == 0) {
+            bbox[j] = make_int4(1, 0, 1, 0);
+            rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int b = tid; b < ph + pw; b += blockDim.x) out[b] = GTap{-(1 << 30), 0.f};
+        return;
+    }
+    const float y1 = __ldg(boxes + 4 * r), x1 = __ldg(boxes + 4 * r + 1);
+    const float y2 = __ldg(boxes + 4 * r + 2), x2 = __ldg(boxes + 4 * r + 3);
+    const int l = roi_level(y1, x1, y2, x2, rule) - 2;
+    const PyrLevel L = (l == 0) ? l0 : (l == 1) ? l1 : (l == 2) ? l2 : l3;
+    for (int b = tid; b < ph + pw; b += blockDim.x) {
+        const bool is_row = b < ph;
+        const AxisTap t = is_row ? axis_tap(y1, y2, L.H, ph, b) : axis_tap(x1, x2, L.W, pw, b - ph);
+        GTap g;
+        g.lo = (t.lo >= 0) ? t.lo : -(1 << 30);
+        g.lerp = t.lerp;
+        out[b] = g;
+        if (t.lo >= 0) {
+            atomicMin(&s_min[is_row ? 0 : 1], t.lo);
+            atomicMax(&s_max[is_row ? 0 : 1], t.hi);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bbox[j] = make_int4(s_min[0], s_max[0], s_min[1], s_max[1]);
+        // position of bin b along an axis ~ a1*(size-1) + b * ((a2-a1)*(size-1)/(crop-1))  (crop_cpu.cpp:52-60)
+        const float sy = (ph > 1) ? ((y2 - y1) * (float)(L.H - 1)) / (float)(ph - 1) : 0.f;
+        const float sx = (pw > 1) ? ((x2 - x1) * (float)(L.W - 1)) / (float)(pw - 1) : 0.f;
+        float4 q;
+        q.x = y1 * (float)(L.H - 1);
+        q.y = (ph > 1 && fabsf(sy) >= 0.01f) ? 1.0f / sy : 0.f;  // 0 => search all bins
+        q.z = x1 * (float)(L.W - 1);
+        q.w = (pw > 1 && fabsf(sx) >= 0.01f) ? 1.0f / sx : 0.f;
+        rp[j] = q;
+    }
+}
+
+// Candidate bins [b0, b1] whose sample can touch pixel `pix` (|pos - pix| < 1), with slack; every
+// candidate is verified exactly against its tap afterwards, so over-inclusion is harmless.
+__device__ __forceinline__ void bin_range(float p0, float inv, int pix, int nb, int& b0, int& b1) {
+    b0 = 0;
+    b1 = nb - 1;
+    if (inv != 0.f && inv == inv) {
+        const float u = ((float)(pix - 1) - p0) * inv;
+        const float v = ((float)(pix + 1) - p0) * inv;
+        const float lo = fminf(u, v) - 0.02f, hi = fmaxf(u, v) + 0.02f;
+        if (lo == lo && hi == hi) {
+            b0 = max(0, (int)ceilf(fmaxf(lo, -1.0f)));
+            b1 = min(nb - 1, (int)floorf(fminf(hi, (float)nb)));
+        }
+    }
+}
+
+__device__ __forceinline__ GTap ldg_tap(const GTap* q) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(q));
+    GTap t;
+    t.lo = v.x;
+    t.lerp = __int_as_float(v.y);
+    return t;
+}
+
+__device__ __forceinline__ float tap_weight(const GTap t, int pix) {
+    // crop_cpu.cpp:254-260: (1 - lerp) goes to the floor tap, lerp to the ceil tap
+    if (t.lo == pix) return __fsub_rn(1.0f, t.lerp);
+    if (t.lo + 1 == pix) return t.lerp;  // lerp == 0 when the ceil tap coincides with the floor tap
+    return 0.f;
+}
+
+// pass 2: one CTA per 8x8 tile of one (image, level) map.
 template <int POOL>
-__global__ void __launch_bounds__(kGThreads, 1) roialign_bwd_gather_kernel(const GatherParams p) {
-    constexpr int kMaxHits = 1024;
-    __shared__ int s_hits[kMaxHits];
+__global__ void __launch_bounds__(kGThreads) roialign_bwd_gather_kernel(const GatherParams p) {
+    __shared__ int s_hits[kGMaxHits];
+    __shared__ int s_wcnt[kGThreads / 32];
     __shared__ int s_nhits;
-    __shared__ float s_wy[kGTile][kMaxPool];
-    __shared__ float s_wx[kGTile][kMaxPool];
-    __shared__ int s_yr[kGTile][2];  // [lo, hi] bin range with non-zero weight per tile row
-    __shared__ int s_xr[kGTile][2];
 
     const int ph = POOL ? POOL : p.ph;
     const int pw = POOL ? POOL : p.pw;
@@ -485,136 +575,87 @@ __global__ void __launch_bounds__(kGThreads, 1) roialign_bwd_gather_kernel(const
     const int lbeg = __ldg(p.offsets + img * 4 + l);
     const int lend = __ldg(p.offsets + img * 4 + l + 1);
 
-    for (int cbase = 0; cbase < C; cbase += 4 * kGLanes) {
-        const int c = cbase + 4 * lane;
-        const bool c_ok = c < C;
-        float4 acc[kGPix];
-#pragma unroll
-        for (int k = 0; k < kGPix; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        for (int chunk = lbeg; chunk < lend; chunk += kMaxHits) {
-            // ---- cull: which RoIs of this (image, level) reach the tile? ----
-            if (tid == 0) s_nhits = 0;
-            __syncthreads();
-            {
-                const int j = chunk + tid;
-                bool hit = false;
-                int r = -1;
-                if (j < lend) {
-                    r = __ldg(p.list + j);
-                    const float y1 = __ldg(p.boxes + 4 * r), x1 = __ldg(p.boxes + 4 * r + 1);
-                    const float y2 = __ldg(p.boxes + 4 * r + 2), x2 = __ldg(p.boxes + 4 * r + 3);
-                    // conservative footprint (one pixel of slack) from the first / last sample positions
-                    const float ya = y1 * (float)(H - 1), yb = (ph > 1) ? y2 * (float)(H - 1) : ya;
-                    const float xa = x1 * (float)(W - 1), xb = (pw > 1) ? x2 * (float)(W - 1) : xa;
-                    const float ylo = fminf(ya, yb) - 1.5f, yhi = fmaxf(ya, yb) + 1.5f;
-                    const float xlo = fminf(xa, xb) - 1.5f, xhi = fmaxf(xa, xb) + 1.5f;
-                    if (ph == 1 || pw == 1) hit = true;  // centre sampling: keep it simple, never cull
-                    else hit = (yhi >= (float)ty0) && (ylo <= (float)(ty0 + kGTile - 1)) && (xhi >= (float)tx0) &&
-                               (xlo <= (float)(tx0 + kGTile - 1));
-                }
-                // ordered compaction (keeps ascending RoI index -> fixed summation order)
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                __shared__ int s_wcnt[32];
-                if (wl == 0) s_wcnt[warp] = __popc(m);
-                __syncthreads();
-                if (warp == 0) {
-                    int v = s_wcnt[wl];
-                    int incl = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (wl >= o) incl += u;
-                    }
-                    s_wcnt[wl] = incl - v;
-                    if (wl == 31) s_nhits = incl;
-                }
-                __syncthreads();
-                if (hit) s_hits[s_wcnt[warp] + __popc(m & ((1u << wl) - 1u))] = r;
+    int epoch = 0;
+    int next = lbeg;
+    do {
+        // ---- cull: which RoIs of this (image, level) reach the tile?  Ordered compaction keeps the
+        //      ascending RoI index, i.e. a fixed summation order. ----
+        if (tid == 0) s_nhits = 0;
+        __syncthreads();
+        int nh = 0;
+        while (next < lend && nh + kGThreads <= kGMaxHits) {
+            const int j = next + tid;
+            bool hit = false;
+            if (j < lend) {
+                const int4 bb = __ldg(p.bbox + j);
+                hit = bb.y >= ty0 && bb.x <= ty0 + kGTile - 1 && bb.w >= tx0 && bb.z <= tx0 + kGTile - 1;
             }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (wl == 0) s_wcnt[warp] = __popc(m);
             __syncthreads();
-            const int nh = s_nhits;
-
-            // ---- accumulate the surviving RoIs one after another ----
-            for (int h = 0; h < nh; ++h) {
-                const int r = s_hits[h];
-                // weights of this RoI for the 8 rows / 8 columns of the tile: warps 0-7 rows, 8-15 columns
-                if (warp < 2 * kGTile) {
-                    const bool is_row = warp < kGTile;
-                    const int line = is_row ? warp : warp - kGTile;            // row / column inside the tile
-                    const int pix = (is_row ? ty0 : tx0) + line;               // feature-map coordinate
-                    const int nb = is_row ? ph : pw;
-                    const float a1 = __ldg(p.boxes + 4 * r + (is_row ? 0 : 1));
-                    const float a2 = __ldg(p.boxes + 4 * r + (is_row ? 2 : 3));
-                    const int size = is_row ? H : W;
-                    int lo = INT_MAX, hi = -1;
-                    for (int b0 = 0; b0 < nb; b0 += 32) {
-                        const int b = b0 + wl;
-                        float w = 0.f;
-                        if (b < nb) {
-                            const AxisTap tp = axis_tap(a1, a2, size, nb, b);
-                            if (tp.lo >= 0) {
-                                // crop_cpu.cpp:254-260: (1 - lerp) goes to the floor tap, lerp to the ceil tap
-                                if (tp.lo == pix) w = __fsub_rn(1.0f, tp.lerp);
-                                else if (tp.hi == pix) w = tp.lerp;
-                            }
-                            (is_row ? s_wy : s_wx)[line][b] = w;
-                        }
-                        const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
-                        if (nz) {
-                            lo = min(lo, b0 + __ffs(nz) - 1);
-                            hi = max(hi, b0 + 31 - __clz(nz));
-                        }
-                    }
-                    if (wl == 0) {
-                        (is_row ? s_yr : s_xr)[line][0] = lo;
-                        (is_row ? s_yr : s_xr)[line][1] = hi;
-                    }
-                }
-                __syncthreads();
-                if (c_ok) {
-                    const float* g = p.grads + (size_t)r * P2 * C + c;
+            int before = 0, total = 0;
 #pragma unroll
-                    for (int k = 0; k < kGPix; ++k) {
-                        const int pidx = slot + k * kGSlots;
-                        const int yy = pidx >> 3, xx = pidx & 7;
-                        const int by0 = s_yr[yy][0], by1 = s_yr[yy][1];
-                        const int bx0 = s_xr[xx][0], bx1 = s_xr[xx][1];
-                        for (int by = by0; by <= by1; ++by) {
-                            const float wy = s_wy[yy][by];
-                            const float* grow = g + (size_t)(by * pw) * C;
-                            for (int bx = bx0; bx <= bx1; ++bx) {
-                                const float w = wy * s_wx[xx][bx];
-                                const float4 v = ldg_f4(grow + (size_t)bx * C);
-                                acc[k].x = fmaf(w, v.x, acc[k].x);
-                                acc[k].y = fmaf(w, v.y, acc[k].y);
-                                acc[k].z = fmaf(w, v.z, acc[k].z);
-                                acc[k].w = fmaf(w, v.w, acc[k].w);
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
+            for (int w = 0; w < kGThreads / 32; ++w) {
+                const int v = s_wcnt[w];
+                if (w < warp) before += v;
+                total += v;
             }
+            if (hit) s_hits[nh + before + __popc(m & ((1u << wl) - 1u))] = j;
+            nh += total;
+            next += kGThreads;
+            __syncthreads();
         }
-        // ---- every pixel of the tile is written exactly once ----
-        if (c_ok) {
-#pragma unroll
+
+        // ---- accumulate: each thread owns 16 pixels x 4 channels, one pixel at a time ----
+        for (int cbase = 0; cbase < C; cbase += 4 * kGLanes) {
+            const int c = cbase + 4 * lane;
+            if (c >= C) continue;
+#pragma unroll 1
             for (int k = 0; k < kGPix; ++k) {
                 const int pidx = slot + k * kGSlots;
                 const int y = ty0 + (pidx >> 3), x = tx0 + (pidx & 7);
-                if (y < H && x < W) {
-                    float* o = out + ((size_t)y * W + x) * C + c;
-                    float4 v = acc[k];
-                    if (p.accumulate) {
-                        const float4 old = *reinterpret_cast<const float4*>(o);
-                        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                if (y >= H || x >= W) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int h = 0; h < nh; ++h) {
+                    const int j = s_hits[h];
+                    const int4 bb = __ldg(p.bbox + j);
+                    if (y < bb.x || y > bb.y || x < bb.z || x > bb.w) continue;
+                    const float4 rp = __ldg(p.rp + j);
+                    int by0, by1, bx0, bx1;
+                    bin_range(rp.x, rp.y, y, ph, by0, by1);
+                    bin_range(rp.z, rp.w, x, pw, bx0, bx1);
+                    const GTap* ty = p.taps + (size_t)j * (ph + pw);
+                    const GTap* tx = ty + ph;
+                    const float* g = p.grads + (size_t)__ldg(p.rid + j) * P2 * C + c;
+                    for (int by = by0; by <= by1; ++by) {
+                        const float wy = tap_weight(ldg_tap(ty + by), y);
+                        if (wy == 0.f) continue;
+                        const float* grow = g + (size_t)(by * pw) * C;
+                        for (int bx = bx0; bx <= bx1; ++bx) {
+                            const float wx = tap_weight(ldg_tap(tx + bx), x);
+                            if (wx == 0.f) continue;
+                            const float w = wy * wx;
+                            const float4 v = ldg_f4(grow + (size_t)bx * C);
+                            acc.x = fmaf(w, v.x, acc.x);
+                            acc.y = fmaf(w, v.y, acc.y);
+                            acc.z = fmaf(w, v.z, acc.z);
+                            acc.w = fmaf(w, v.w, acc.w);
+                        }
                     }
-                    *reinterpret_cast<float4*>(o) = v;
                 }
+                // every pixel of the tile is written exactly once per epoch
+                float* o = out + ((size_t)y * W + x) * C + c;
+                if (p.accumulate || epoch > 0) {
+                    const float4 old = *reinterpret_cast<const float4*>(o);
+                    acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o) = acc;
             }
         }
-    }
+        ++epoch;
+        __syncthreads();
+    } while (next < lend);
 }
 
 // Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
@@ -828,8 +869,31 @@ static int launch_zero(float* const ptr[4], const size_t elems[4], int nbuf, cud
     return MRCNN_OK;
 }
 
-static size_t gather_workspace_bytes(int B, int N) {
-    return align_up((size_t)(N > 0 ? N : 1) * 4, 256) + align_up((size_t)(4 * (size_t)B + 1) * 4, 256);
+struct GatherWorkspace {
+    int32_t* rid;
+    int4* bbox;
+    float4* rp;
+    GTap* taps;
+    int32_t* offsets;
+    size_t bytes;
+};
+
+static GatherWorkspace carve_gather(void* base, int B, int N, int pool) {
+    GatherWorkspace w;
+    const size_t n = (size_t)(N > 0 ? N : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* q = base ? (void*)((char*)base + off) : nullptr;
+        off += align_up(bytes, 256);
+        return q;
+    };
+    w.rid = (int32_t*)take(n * 4);
+    w.bbox = (int4*)take(n * 16);
+    w.rp = (float4*)take(n * 16);
+    w.taps = (GTap*)take(n * 2 * (size_t)pool * sizeof(GTap));
+    w.offsets = (int32_t*)take((size_t)(4 * (size_t)B + 1) * 4);
+    w.bytes = off;
+    return w;
 }
 
 // true if the gather backward can serve this call
@@ -837,7 +901,7 @@ static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int g
                             float* const gfm[4], const void* workspace, size_t workspace_bytes) {
     if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
     if ((C % 4) != 0 || pool > kMaxPool || N > kBinMaxN || N <= 0) return false;
-    if (workspace == nullptr || workspace_bytes < gather_workspace_bytes(B, N)) return false;
+    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, B, N, pool).bytes) return false;
     if ((size_t)(4 * (size_t)B + 1) * 4 > 96 * 1024) return false;
     if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
     for (int l = 0; l < 4; ++l)
@@ -848,29 +912,29 @@ static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int g
 static int launch_bwd_gather(const float* grads, const int H[4], const int W[4], int B, int C, const float* boxes,
                              const int32_t* box_index, int N, int pool, float image_area, float* const gfm[4],
                              int accumulate, void* workspace, cudaStream_t stream) {
-    int32_t* list = reinterpret_cast<int32_t*>(workspace);
-    int32_t* offsets = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + align_up((size_t)N * 4, 256));
+    const GatherWorkspace ws = carve_gather(workspace, B, N, pool);
     const LevelRule rule = make_level_rule(image_area);
     int P = 32;
     while (P < N) P <<= 1;
     const size_t bin_smem = (size_t)P * 8 + (size_t)(4 * B + 1) * 4;
     MRCNN_CUDA(cudaFuncSetAttribute(roi_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, P, B, rule, list, offsets, device_error_word());
+    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, P, B, rule, ws.rid, ws.offsets, device_error_word());
     MRCNN_LAUNCH_CHECK();
     GatherParams g = {};
     int total = 0;
     for (int l = 0; l < 4; ++l) {
         g.lv[l] = {gfm[l], H[l], W[l]};
         g.tiles_x[l] = (W[l] + kGTile - 1) / kGTile;
-        g.tiles_y[l] = (H[l] + kGTile - 1) / kGTile;
         g.tile_base[l] = total;
-        total += g.tiles_x[l] * g.tiles_y[l];
+        total += g.tiles_x[l] * ((H[l] + kGTile - 1) / kGTile);
     }
     g.tile_base[4] = total;
-    g.rule = rule;
+    roi_taps_kernel<<<N, 128, 0, stream>>>(boxes, ws.rid, N, pool, pool, rule, g.lv[0], g.lv[1], g.lv[2], g.lv[3], ws.bbox,
+                                          ws.rp, ws.taps);
+    MRCNN_LAUNCH_CHECK();
     g.B = B; g.C = C; g.N = N;
     g.ph = pool; g.pw = pool;
-    g.boxes = boxes; g.grads = grads; g.list = list; g.offsets = offsets;
+    g.grads = grads; g.rid = ws.rid; g.bbox = ws.bbox; g.rp = ws.rp; g.taps = ws.taps; g.offsets = ws.offsets;
     g.accumulate = accumulate;
     const long long grid = (long long)total * B;
     MRCNN_REQUIRE(grid < (1ll << 31), "mrcnn_pyramid_roi_align_backward: too many tiles");
@@ -892,9 +956,9 @@ using namespace mrcnn;
 
 extern "C" {
 
-size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N) {
-    if (B <= 0 || N < 0) return 256;
-    return gather_workspace_bytes(B, N);
+size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N, int pool) {
+    if (B <= 0 || N < 0 || pool <= 0) return 256;
+    return carve_gather(nullptr, B, N, pool).bytes;
 }
 
 int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout, const float* boxes,

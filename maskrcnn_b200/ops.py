@@ -41,6 +41,9 @@ def _layout4(t):
     if t.dim() != 4:
         raise ValueError("expected a 4-D tensor, got %d-D" % t.dim())
     if t.is_contiguous():
+        # [N,C,1,1] is dense in both orders: call it channels-last so that it can take the vectorised kernels
+        if t.size(2) == 1 and t.size(3) == 1 and t.size(1) % 4 == 0 and t.is_contiguous(memory_format=torch.channels_last):
+            return t, NHWC
         return t, NCHW
     if t.is_contiguous(memory_format=torch.channels_last):
         return t, NHWC
@@ -199,7 +202,7 @@ class _PyramidRoiAlign(torch.autograd.Function):
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
         with torch.cuda.device(grad.device):
-            ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N)
+            ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,

@@ -11,7 +11,7 @@ g7c, g14c = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=
 o7c, o14c = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
 
 
-ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N), dtype=torch.uint8, device="cuda")
+ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, 14), dtype=torch.uint8, device="cuda")
 
 
 def bwd(pool, g, gl, gfm, offs, gather=False):
