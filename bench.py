@@ -115,9 +115,12 @@ def make_boxes(batch, seed):
 class Workload(object):
     """Device-resident buffers + the five launches of one step, straight through the C ABI."""
 
-    def __init__(self, torch, device, batch=BATCH, seed=SEED):
+    def __init__(self, torch, device, batch=BATCH, seed=SEED, crops_channels_last=True):
         from maskrcnn_b200 import _lib
         self.torch, self.L, self.batch = torch, _lib, batch
+        self.cl_crops = crops_channels_last
+        self.crop_layout = _lib.NHWC if crops_channels_last else _lib.NCHW
+        cfmt = torch.channels_last if crops_channels_last else torch.contiguous_format
         g = torch.Generator(device=device)
         g.manual_seed(seed)
         cl = torch.channels_last
@@ -129,10 +132,10 @@ class Workload(object):
         self.boxes = torch.from_numpy(boxes).to(device)
         self.ind = torch.from_numpy(ind).to(device)
         self.N = len(boxes)
-        self.out7 = torch.empty((self.N, CHANNELS, 7, 7), device=device)
-        self.out14 = torch.empty((self.N, CHANNELS, 14, 14), device=device)
-        self.g7 = torch.randn((self.N, CHANNELS, 7, 7), device=device, generator=g)
-        self.g14 = torch.randn((self.N, CHANNELS, 14, 14), device=device, generator=g)
+        self.out7 = torch.empty((self.N, CHANNELS, 7, 7), device=device, memory_format=cfmt)
+        self.out14 = torch.empty((self.N, CHANNELS, 14, 14), device=device, memory_format=cfmt)
+        self.g7 = torch.randn((self.N, CHANNELS, 7, 7), device=device, generator=g).contiguous(memory_format=cfmt)
+        self.g14 = torch.randn((self.N, CHANNELS, 14, 14), device=device, generator=g).contiguous(memory_format=cfmt)
         # mask targets: gt masks [batch*G,1,1024,1024] (binary rectangles), crop 28x28 by (image, instance) index
         self.gt = torch.zeros((batch * GT_PER_IMAGE, 1, IMAGE, IMAGE), device=device)
         rng = np.random.default_rng(seed + 5)
@@ -156,12 +159,12 @@ class Workload(object):
         L = self.L
         L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in self.fm]), self.Hs, self.Ws, self.batch,
                                                       CHANNELS, L.NHWC, self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool,
-                                                      self.area, out.data_ptr(), L.NCHW, None, self._s()))
+                                                      self.area, out.data_ptr(), self.crop_layout, None, self._s()))
         self.launches += 1
 
     def bwd(self, pool, grad, gfm):
         L = self.L
-        L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, self.Hs, self.Ws, self.batch, CHANNELS,
+        L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), self.crop_layout, self.Hs, self.Ws, self.batch, CHANNELS,
                                                        self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
                                                        L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, None, None, 0, self._s()))
         self.launches += 2   # zero_levels_kernel + roialign_bwd_nhwc_kernel
@@ -229,10 +232,13 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
     for hf, f in zip(h_fm, wl.fm):
         hf.copy_(f.permute(0, 2, 3, 1))
     h_boxes = wl.boxes.cpu().pin_memory()
-    h_g7, h_g14 = pin(wl.g7), pin(wl.g14)
-    h_g7.copy_(wl.g7)
-    h_g14.copy_(wl.g14)
-    h_out7, h_out14 = pin(wl.out7), pin(wl.out14)
+    # crops / upstream gradients: host buffers in the device's physical order (views make both sides plain memcpys)
+    phys = (lambda t: t.permute(0, 2, 3, 1)) if wl.cl_crops else (lambda t: t)
+    d_g7, d_g14, d_out7, d_out14 = phys(wl.g7), phys(wl.g14), phys(wl.out7), phys(wl.out14)
+    h_g7, h_g14 = pin(d_g7), pin(d_g14)
+    h_g7.copy_(d_g7)
+    h_g14.copy_(d_g14)
+    h_out7, h_out14 = pin(d_out7), pin(d_out14)
     h_gf7 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
     h_gf14 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
     h_mboxes, h_mind, h_mt = wl.mboxes.cpu().pin_memory(), wl.mind.cpu().pin_memory(), pin(wl.mt)
@@ -256,8 +262,8 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 for l in range(4):
                     fm_nhwc[l][i].copy_(h_fm[l][i], non_blocking=True)
                 wl.boxes[rs].copy_(h_boxes[rs], non_blocking=True)
-                wl.g7[rs].copy_(h_g7[rs], non_blocking=True)
-                wl.g14[rs].copy_(h_g14[rs], non_blocking=True)
+                d_g7[rs].copy_(h_g7[rs], non_blocking=True)
+                d_g14[rs].copy_(h_g14[rs], non_blocking=True)
                 wl.mboxes[ms].copy_(h_mboxes[ms], non_blocking=True)
                 wl.mind[ms].copy_(h_mind[ms], non_blocking=True)
                 ev_in[i].record(s_in)
@@ -267,21 +273,21 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 fmp = L.vp4([f[i].data_ptr() for f in wl.fm])
                 bp = wl.boxes[rs].data_ptr()
                 L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 7, wl.area,
-                                                              wl.out7[rs].data_ptr(), L.NCHW, None, st))
+                                                              wl.out7[rs].data_ptr(), wl.crop_layout, None, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 14, wl.area,
-                                                              wl.out14[rs].data_ptr(), L.NCHW, None, st))
+                                                              wl.out14[rs].data_ptr(), wl.crop_layout, None, st))
                 L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
                                                  wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
-                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
+                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
                                                                wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, None, 0, st))
-                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), L.NCHW, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
+                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
                                                                wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, None, 0, st))
                 launches[0] += 7
                 ev_run[i].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[i])
-                h_out7[rs].copy_(wl.out7[rs], non_blocking=True)
-                h_out14[rs].copy_(wl.out14[rs], non_blocking=True)
+                h_out7[rs].copy_(d_out7[rs], non_blocking=True)
+                h_out14[rs].copy_(d_out14[rs], non_blocking=True)
                 h_mt[ms].copy_(wl.mt[ms], non_blocking=True)
                 for l in range(4):
                     h_gf7[l][i].copy_(gf7_nhwc[l][i], non_blocking=True)
@@ -407,7 +413,7 @@ def workload_config():
     return {"workload": "BASELINE configs[3]: training-mode PyramidROIAlign fwd+bwd, batch %d x %d RoIs x %d ch, P2-P5 of %dx%d, "
                         "7x7 + 14x14 + %d 28x28 mask-target crops/img" % (BATCH, ROIS_PER_IMAGE, CHANNELS, IMAGE, IMAGE, MASK_POS),
             "batch_per_gpu": BATCH, "rois_per_image": ROIS_PER_IMAGE, "channels": CHANNELS,
-            "feature_layout": "channels_last (NHWC) pyramid, NCHW crops/grads", "parallelism": "image-sharded replicas, no collective",
+            "feature_layout": "channels_last (NHWC) pyramid, crops and gradients (logical shapes are the reference's [N,C,h,w])", "parallelism": "image-sharded replicas, no collective",
             "l2": "inputs (1.43 GB pyramid + 2 GB crops per step) are larger than L2; no explicit flush"}
 
 
@@ -442,25 +448,24 @@ def secondary(torch, wl, hbm):
         out["roialign_fwd_%dx%d" % (pool, pool)] = {"config": "configs[2]: 1000 RoIs x 256 ch, one image (warm L2: 89 MB pyramid fits)",
                                                     "rois_per_s": 1000 / t, "us": t * 1e6, "algorithmic_MB": by / 1e6,
                                                     "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm}
-    # the same training step with channels-last crops and upstream gradients (a channels_last model end to end)
-    cl = torch.channels_last
-    o7, o14 = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
-    g7, g14 = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=cl)
+    # the same training step with NCHW-contiguous crops and upstream gradients (the reference's physical layout;
+    # the kernels then transpose through shared memory)
+    o7, o14 = wl.out7.contiguous(), wl.out14.contiguous()
+    g7, g14 = wl.g7.contiguous(), wl.g14.contiguous()
     L = wl.L
-    ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, 14), dtype=torch.uint8, device=dev)
-    def step_nhwc():
+    def step_nchw():
         for pool, o in ((7, o7), (14, o14)):
             L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC,
-                                                          wl.boxes.data_ptr(), wl.ind.data_ptr(), wl.N, pool, wl.area, o.data_ptr(), L.NHWC,
+                                                          wl.boxes.data_ptr(), wl.ind.data_ptr(), wl.N, pool, wl.area, o.data_ptr(), L.NCHW,
                                                           None, wl._s()))
         wl.mask_targets()
         for pool, g, gf in ((14, g14, wl.gfm14), (7, g7, wl.gfm7)):
-            L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NHWC, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
+            L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NCHW, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
                                                            wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gf]),
-                                                           L.NHWC, 1, None, ws.data_ptr(), ws.numel(), wl._s()))
-    t = wl.time_op(step_nhwc, iters=20)
-    out["train_step_all_channels_last"] = {"config": "configs[3] with channels-last crops and gradients", "rois_per_s": wl.N / t,
-                                           "ms_per_step": t * 1e3}
+                                                           L.NHWC, 1, None, None, 0, wl._s()))
+    t = wl.time_op(step_nchw, iters=20)
+    out["train_step_nchw_crops"] = {"config": "configs[3] with NCHW-contiguous crops and gradients (smem-transposed)", "rois_per_s": wl.N / t,
+                                    "ms_per_step": t * 1e3}
     del o7, o14, g7, g14
     # configs[4]: detection layer + mask RoIAlign on the detections, 64 images
     B, N, NC = 64, 1000, 81
@@ -528,10 +533,10 @@ def main():
         U14, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 14, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
         pyr = wl.batch * PYR_ELEMS_PER_IMAGE
         ops = {
-            "roialign_fwd_nhwc_kernel<7x7>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
-            "roialign_fwd_nhwc_kernel<14x14>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
-            "memset+roialign_bwd_nhwc_kernel<7x7>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
-            "memset+roialign_bwd_nhwc_kernel<14x14>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
+            "roialign_fwd_nhwc_kernel<7,nhwc>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
+            "roialign_fwd_nhwc_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
+            "zero_levels_kernel+roialign_bwd_nhwc_kernel<7,nhwc>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
+            "zero_levels_kernel+roialign_bwd_nhwc_kernel<14,nhwc>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
         }
         kern = {}

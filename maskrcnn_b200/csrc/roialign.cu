@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
     const float* src = ctx.base + c;
     float* out_nhwc = p.crops + (size_t)n * P2 * C + c;
 
+    // All per-bin addressing is 32-bit element offsets from `src` / `out_nhwc` (the launcher guarantees
+    // H*W*C and P2*C fit in an int): one IMAD.WIDE per access instead of 64-bit pointer chains.
     if (c_ok) {
 #pragma unroll 1
         for (int b0 = slot; b0 < P2; b0 += 2 * kSlots) {
@@ -211,12 +213,10 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
                     const TapS tx = s_tx[x];
                     inside[u] = ty.valid && tx.valid;
                     if (inside[u]) {
-                        const float* r0 = src + ty.lo;
-                        const float* r1 = src + ty.hi;
-                        tl[u] = ldg_f4(r0 + tx.lo);
-                        tr[u] = ldg_f4(r0 + tx.hi);
-                        bl[u] = ldg_f4(r1 + tx.lo);
-                        br[u] = ldg_f4(r1 + tx.hi);
+                        tl[u] = ldg_f4(src + (ty.lo + tx.lo));
+                        tr[u] = ldg_f4(src + (ty.lo + tx.hi));
+                        bl[u] = ldg_f4(src + (ty.hi + tx.lo));
+                        br[u] = ldg_f4(src + (ty.hi + tx.hi));
                         xl[u] = tx.lerp;
                         yl[u] = ty.lerp;
                     }
@@ -236,9 +236,9 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
                     v = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
                 }
                 if (kOutNHWC) {
-                    stg_f4_stream(out_nhwc + (size_t)b * C, v);
+                    stg_f4_stream(out_nhwc + b * C, v);
                 } else {
-                    float* t = tile + (4 * lane) * P2pad + b;
+                    float* t = tile + ((4 * lane) * P2pad + b);
                     t[0] = v.x;
                     t[P2pad] = v.y;
                     t[2 * P2pad] = v.z;
@@ -321,17 +321,22 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
         bool has_nxt = false;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* tl_ = tile + ((4 * lane) * P2pad + y * pw);
+        const float* gl_ = g_nhwc + (y * pw) * C;
+        // software pipeline: the gradient of bin x + 1 is in flight while bin x is accumulated
+        float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kGradNHWC && xbeg < xend) g_next = ldg_f4_stream(gl_ + xbeg * C);
         for (int x = xbeg; x < xend; ++x) {
             const TapS tx = s_tx[x];
-            if (!tx.valid) continue;
             float4 g;
-            const int b = y * pw + x;
             if (kGradNHWC) {
-                g = ldg_f4_stream(g_nhwc + (size_t)b * C);
+                g = g_next;
+                if (x + 1 < xend) g_next = ldg_f4_stream(gl_ + (x + 1) * C);
             } else {
-                const float* t = tile + (4 * lane) * P2pad + b;
+                const float* t = tl_ + x;
                 g = make_float4(t[0], t[P2pad], t[2 * P2pad], t[3 * P2pad]);
             }
+            if (!tx.valid) continue;
             if (tx.lo != cur) {
                 if (cur >= 0) {
                     flush_col(row0, row1, cur, acc, ty.lerp, two_rows);
@@ -379,9 +384,6 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
 // ------------------------------------------------------------------------------------------------
 constexpr int kGTile = 8;       // tile side in feature-map pixels
 constexpr int kGThreads = 256;
-constexpr int kGLanes = 64;     // float4 channel lanes -> 256 channels per pass
-constexpr int kGSlots = kGThreads / kGLanes;      // 4 pixel slots
-constexpr int kGPix = kGTile * kGTile / kGSlots;  // 16 pixels per thread, processed one after another
 constexpr int kGMaxHits = 2048; // RoIs per tile handled in one epoch
 constexpr int kBinMaxN = 8192;  // RoIs sortable by the one-CTA binning kernel
 
@@ -542,19 +544,27 @@ __device__ __forceinline__ float tap_weight(const GTap t, int pix) {
     return 0.f;
 }
 
-// pass 2: one CTA per 8x8 tile of one (image, level) map.
+// pass 2: one CTA per 8x8 tile of one (image, level) map.  256 threads = 8 warps; warp w owns tile column w
+// and walks its 8 rows; a lane carries 8 channels (two float4), so one warp covers 256 channels and the
+// per-(pixel, RoI) bookkeeping is paid once per 256 channels.
+constexpr int kGTapBytes = 32 * 1024;  // shared-memory budget for the staged taps of one batch of RoIs
+constexpr int kGBatchMax = 64;
+
 template <int POOL>
 __global__ void __launch_bounds__(kGThreads) roialign_bwd_gather_kernel(const GatherParams p) {
     __shared__ int s_hits[kGMaxHits];
     __shared__ int s_wcnt[kGThreads / 32];
-    __shared__ int s_nhits;
+    __shared__ __align__(16) unsigned char s_tapmem[kGTapBytes];
+    __shared__ short2 s_rng[kGBatchMax][2 * kGTile];  // candidate bin range per (RoI, tile row | tile column)
+    __shared__ int s_goff[kGBatchMax];                // rid * P2
 
     const int ph = POOL ? POOL : p.ph;
     const int pw = POOL ? POOL : p.pw;
     const int P2 = ph * pw;
+    const int ntap = ph + pw;
+    const int batch_cap = min(kGBatchMax, kGTapBytes / (ntap * (int)sizeof(GTap)));
+    GTap* s_taps = reinterpret_cast<GTap*>(s_tapmem);
     const int tid = threadIdx.x;
-    const int lane = tid & (kGLanes - 1);
-    const int slot = tid >> 6;
     const int warp = tid >> 5;
     const int wl = tid & 31;
 
@@ -580,7 +590,6 @@ __global__ void __launch_bounds__(kGThreads) roialign_bwd_gather_kernel(const Ga
     do {
         // ---- cull: which RoIs of this (image, level) reach the tile?  Ordered compaction keeps the
         //      ascending RoI index, i.e. a fixed summation order. ----
-        if (tid == 0) s_nhits = 0;
         __syncthreads();
         int nh = 0;
         while (next < lend && nh + kGThreads <= kGMaxHits) {
@@ -606,55 +615,94 @@ __global__ void __launch_bounds__(kGThreads) roialign_bwd_gather_kernel(const Ga
             __syncthreads();
         }
 
-        // ---- accumulate: each thread owns 16 pixels x 4 channels, one pixel at a time ----
-        for (int cbase = 0; cbase < C; cbase += 4 * kGLanes) {
-            const int c = cbase + 4 * lane;
-            if (c >= C) continue;
+        for (int h0 = 0; h0 < nh || (h0 == 0 && epoch == 0); h0 += batch_cap) {
+            const int nb = max(0, min(batch_cap, nh - h0));
+            // ---- plan: stage the taps of this batch and the candidate bin ranges per tile row / column ----
+            for (int i = tid; i < nb * ntap; i += kGThreads) {
+                const int h = i / ntap, b = i - h * ntap;
+                s_taps[i] = ldg_tap(p.taps + (size_t)s_hits[h0 + h] * ntap + b);
+            }
+            for (int i = tid; i < nb * 2 * kGTile; i += kGThreads) {
+                const int h = i >> 4, line = i & 15;
+                const int j = s_hits[h0 + h];
+                const int4 bb = __ldg(p.bbox + j);
+                const float4 rp = __ldg(p.rp + j);
+                int b0 = 1, b1 = 0;
+                if (line < kGTile) {
+                    const int y = ty0 + line;
+                    if (y >= bb.x && y <= bb.y) bin_range(rp.x, rp.y, y, ph, b0, b1);
+                } else {
+                    const int x = tx0 + line - kGTile;
+                    if (x >= bb.z && x <= bb.w) bin_range(rp.z, rp.w, x, pw, b0, b1);
+                }
+                s_rng[h][line] = make_short2((short)b0, (short)b1);
+                if (line == 0) s_goff[h] = __ldg(p.rid + j) * P2;
+            }
+            __syncthreads();
+
+            // ---- accumulate: warp = tile column, 8 rows one after another, 8 channels per lane ----
+            const int x = tx0 + warp;
+            if (x < W) {
+                for (int cbase = 0; cbase < C; cbase += 8 * 32) {
+                    const int c = cbase + 8 * wl;
+                    if (c >= C) continue;
+                    const bool two = (c + 4 < C);
 #pragma unroll 1
-            for (int k = 0; k < kGPix; ++k) {
-                const int pidx = slot + k * kGSlots;
-                const int y = ty0 + (pidx >> 3), x = tx0 + (pidx & 7);
-                if (y >= H || x >= W) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < kGTile; ++k) {
+                        const int y = ty0 + k;
+                        if (y >= H) break;
+                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
 #pragma unroll 1
-                for (int h = 0; h < nh; ++h) {
-                    const int j = s_hits[h];
-                    const int4 bb = __ldg(p.bbox + j);
-                    if (y < bb.x || y > bb.y || x < bb.z || x > bb.w) continue;
-                    const float4 rp = __ldg(p.rp + j);
-                    int by0, by1, bx0, bx1;
-                    bin_range(rp.x, rp.y, y, ph, by0, by1);
-                    bin_range(rp.z, rp.w, x, pw, bx0, bx1);
-                    const GTap* ty = p.taps + (size_t)j * (ph + pw);
-                    const GTap* tx = ty + ph;
-                    const float* g = p.grads + (size_t)__ldg(p.rid + j) * P2 * C + c;
-                    for (int by = by0; by <= by1; ++by) {
-                        const float wy = tap_weight(ldg_tap(ty + by), y);
-                        if (wy == 0.f) continue;
-                        const float* grow = g + (size_t)(by * pw) * C;
-                        for (int bx = bx0; bx <= bx1; ++bx) {
-                            const float wx = tap_weight(ldg_tap(tx + bx), x);
-                            if (wx == 0.f) continue;
-                            const float w = wy * wx;
-                            const float4 v = ldg_f4(grow + (size_t)bx * C);
-                            acc.x = fmaf(w, v.x, acc.x);
-                            acc.y = fmaf(w, v.y, acc.y);
-                            acc.z = fmaf(w, v.z, acc.z);
-                            acc.w = fmaf(w, v.w, acc.w);
+                        for (int h = 0; h < nb; ++h) {
+                            const short2 ry = s_rng[h][k];
+                            const short2 rx = s_rng[h][kGTile + warp];
+                            if (ry.y < ry.x || rx.y < rx.x) continue;
+                            const GTap* ty = s_taps + h * ntap;
+                            const GTap* tx = ty + ph;
+                            const float* g = p.grads + (size_t)s_goff[h] * C + c;
+                            for (int by = ry.x; by <= ry.y; ++by) {
+                                const float wy = tap_weight(ty[by], y);
+                                if (wy == 0.f) continue;
+                                const float* grow = g + (size_t)(by * pw) * C;
+                                for (int bx = rx.x; bx <= rx.y; ++bx) {
+                                    const float wx = tap_weight(tx[bx], x);
+                                    if (wx == 0.f) continue;
+                                    const float w = wy * wx;
+                                    const float* q = grow + (size_t)bx * C;
+                                    const float4 v0 = ldg_f4(q);
+                                    a0.x = fmaf(w, v0.x, a0.x);
+                                    a0.y = fmaf(w, v0.y, a0.y);
+                                    a0.z = fmaf(w, v0.z, a0.z);
+                                    a0.w = fmaf(w, v0.w, a0.w);
+                                    if (two) {
+                                        const float4 v1 = ldg_f4(q + 4);
+                                        a1.x = fmaf(w, v1.x, a1.x);
+                                        a1.y = fmaf(w, v1.y, a1.y);
+                                        a1.z = fmaf(w, v1.z, a1.z);
+                                        a1.w = fmaf(w, v1.w, a1.w);
+                                    }
+                                }
+                            }
                         }
+                        // every pixel of the tile is written exactly once per batch (only the first overwrites)
+                        float* o = out + ((size_t)y * W + x) * C + c;
+                        if (p.accumulate || epoch > 0 || h0 > 0) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(o);
+                            a0.x += o0.x; a0.y += o0.y; a0.z += o0.z; a0.w += o0.w;
+                            if (two) {
+                                const float4 o1 = *reinterpret_cast<const float4*>(o + 4);
+                                a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
+                            }
+                        }
+                        *reinterpret_cast<float4*>(o) = a0;
+                        if (two) *reinterpret_cast<float4*>(o + 4) = a1;
                     }
                 }
-                // every pixel of the tile is written exactly once per epoch
-                float* o = out + ((size_t)y * W + x) * C + c;
-                if (p.accumulate || epoch > 0) {
-                    const float4 old = *reinterpret_cast<const float4*>(o);
-                    acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o) = acc;
             }
+            __syncthreads();
+            if (nb == 0) break;
         }
         ++epoch;
-        __syncthreads();
     } while (next < lend);
 }
 
@@ -810,6 +858,9 @@ static int launch_roi(const RoiParams& p, int image_layout, int crops_layout, bo
     const int P2 = p.ph * p.pw;
     const size_t smem = (crops_layout == MRCNN_NHWC) ? 0 : sizeof(float) * kChunk * (size_t)(P2 | 1);
     if (fast && smem > 200 * 1024) fast = false;
+    for (int l = 0; l < (p.pyramid ? 4 : 1); ++l)  // the vectorised kernels use 32-bit element offsets inside one image
+        if ((long long)p.lv[l].H * p.lv[l].W * p.C >= (1ll << 31)) fast = false;
+    if ((long long)P2 * p.C >= (1ll << 31)) fast = false;
     if (fast) {
         const dim3 grid(p.N, (p.C + kChunk - 1) / kChunk);
         if (grid.y > 65535) return fail(MRCNN_E_INVALID_ARG, "C too large");
