@@ -489,6 +489,51 @@ def secondary(torch, wl, hbm):
     return out
 
 
+def sharded_detection(torch, dist, wl, world, rank, hbm):
+    """BASELINE configs[4]: 64 images sharded over the ranks (strong scaling): detection layer + 14x14 mask RoIAlign on
+    the detections, then ONE all-gather of the padded detections (NCCL over NVLink).  Max over ranks."""
+    import maskrcnn_b200 as m
+    from maskrcnn_b200 import synth, dist as mdist
+    dev = "cuda"
+    TOTAL, N, NC, D = 64, 1000, 81, 100
+    b, e = mdist.shard_range(TOTAL, rank, world)
+    Bl = e - b
+    rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(b, e)])).to(dev)
+    g_ = torch.Generator(device=dev)
+    g_.manual_seed(7 + rank)
+    probs = torch.softmax(3.0 * torch.randn((Bl, N, NC), device=dev, generator=g_), -1)
+    deltas = 0.1 * torch.randn((Bl, N, NC, 4), device=dev, generator=g_)
+    win = torch.tensor([[0., 0., IMAGE, IMAGE]], device=dev).repeat(Bl, 1)
+    ind = (torch.arange(Bl, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(D)
+
+    def run():
+        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
+        masks_in = m.pyramid_roi_align(wl.fm, (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4), ind, 14, (IMAGE, IMAGE, 3))
+        all_dets, all_counts = mdist.gather_detections(dets, counts, n_images=TOTAL)
+        return masks_in, all_dets, all_counts
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    a.record()
+    for _ in range(iters):
+        out = run()
+    bb.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(bb) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"config": "configs[4]: 64 images sharded over %d GPU(s): detection layer + 14x14 mask RoIAlign + one all-gather" % world,
+            "images_per_s": TOTAL / (ms * 1e-3), "ms_per_64_images": ms, "scaling": "strong",
+            "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -552,6 +597,7 @@ def main():
                             "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
                             "kernels": kern}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)
+        line["detection_path_sharded"] = sharded_detection(torch, dist, wl, world, rank, hbm)
         if rank == 0 and world == 1:
             cores = os.cpu_count() or 1
             v, dt, kind = cpu_measure(2, 1)
