@@ -150,6 +150,8 @@ class Workload(object):
         self.Ws = _lib.i4([w for _, w in LEVEL_HW])
         self.area = float(IMAGE * IMAGE)
         self.offsets = _lib.i32_array([i * ROIS_PER_IMAGE for i in range(batch + 1)])  # host: boxes grouped by image
+        self.ws = torch.empty(_lib.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(batch, self.N, 14),
+                              dtype=torch.uint8, device=device)
         self.launches = 0
 
     def _s(self):
@@ -166,8 +168,8 @@ class Workload(object):
         L = self.L
         L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), self.crop_layout, self.Hs, self.Ws, self.batch, CHANNELS,
                                                        self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
-                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, None, None, 0, self._s()))
-        self.launches += 2   # zero_levels_kernel + roialign_bwd_nhwc_kernel
+                                                       L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, None, L.BWD_AUTO, self.ws.data_ptr(), self.ws.numel(), self._s()))
+        self.launches += 2   # roialign_bwd_nhwc_kernel (first-touch clearing) + zero_untouched_kernel
 
     def mask_targets(self):
         L = self.L
@@ -279,9 +281,9 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
                                                  wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, None, 0, st))
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
                 L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, None, 0, st))
+                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
                 launches[0] += 7
                 ev_run[i].record(s_run)
             with torch.cuda.stream(s_out):
@@ -462,7 +464,7 @@ def secondary(torch, wl, hbm):
         for pool, g, gf in ((14, g14, wl.gfm14), (7, g7, wl.gfm7)):
             L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NCHW, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
                                                            wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gf]),
-                                                           L.NHWC, 1, None, None, 0, wl._s()))
+                                                           L.NHWC, 1, None, L.BWD_AUTO, wl.ws.data_ptr(), wl.ws.numel(), wl._s()))
     t = wl.time_op(step_nchw, iters=20)
     out["train_step_nchw_crops"] = {"config": "configs[3] with NCHW-contiguous crops and gradients (smem-transposed)", "rois_per_s": wl.N / t,
                                     "ms_per_step": t * 1e3}
@@ -580,8 +582,8 @@ def main():
         ops = {
             "roialign_fwd_nhwc_kernel<7,nhwc>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
             "roialign_fwd_nhwc_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
-            "zero_levels_kernel+roialign_bwd_nhwc_kernel<7,nhwc>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
-            "zero_levels_kernel+roialign_bwd_nhwc_kernel<14,nhwc>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
+            "roialign_bwd_nhwc_kernel<7,nhwc>+zero_untouched_kernel": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
+            "roialign_bwd_nhwc_kernel<14,nhwc>+zero_untouched_kernel": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
         }
         kern = {}

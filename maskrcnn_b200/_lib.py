@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libmrcnn_b200.so")
 
 NCHW, NHWC = 0, 1
 OK = 0
+BWD_AUTO, BWD_GATHER, BWD_SCATTER = 0, 1, 2
 E_INVALID_ARG, E_NOT_DEVICE_PTR, E_WORKSPACE, E_CUDA, E_BOX_INDEX = -1, -2, -3, -4, -5
 
 _vp = ctypes.c_void_p
@@ -27,7 +28,7 @@ SIGNATURES = {
     "mrcnn_crop_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrcnn_pyramid_roi_align_forward": (_i, [_vp4, _i4, _i4, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp]),
     "mrcnn_pyramid_roi_align_backward_workspace_bytes": (_sz, [_i, _i, _i]),
-    "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp, _vp, _sz, _vp]),
+    "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "mrcnn_nms_workspace_bytes": (_sz, [_i]),
     "mrcnn_nms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_proposal_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -368,24 +368,21 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward as a GATHER (pixel-owner) — channels-last gradients in, channels-last pyramid gradient out.
+// Backward as a GATHER (tile-owner) — channels-last gradients in, channels-last pyramid gradient out.
 //
 // Every 8x8 tile of every (image, level) gradient map is owned by one CTA, which sums the contributions
 // of all RoIs of that (image, level) that reach the tile and writes each pixel exactly once.  No atomics,
 // no separate zero fill, no read-modify-write: DRAM traffic is the algorithmic minimum (upstream gradient
 // read once, gradient pyramid written once), and the summation order is fixed -> bit-reproducible.
 //
-//   pass 1  roi_bin_kernel (one CTA): key = image*4 + level per RoI, sorted (key, index) -> CSR lists.
-//   pass 2  roialign_bwd_gather_kernel: grid = tiles; 1024 threads = 64 channel lanes (float4) x 16 pixel
-//           slots (4 pixels each).  Per tile: cull the (image, level) list by footprint, then per surviving
-//           RoI stage the separable weights wy[8][ph], wx[8][pw] of the tile's rows/columns in shared
-//           memory and accumulate  acc(y,x) += wy[y][by] * wx[x][bx] * g[r][by][bx][c]  with one 128-bit
-//           load per (pixel, bin, lane): a warp reads 512 contiguous bytes.
+//   pass 1a roi_bin_kernel (one CTA): key = image*4 + level per RoI, sorted (key, index) -> CSR lists.
+//   pass 1b roi_taps_kernel: per RoI the ph + pw axis taps, the pixel footprint, the affine bin-position model.
+//   pass 2  roialign_bwd_gather_kernel: grid = tiles (coarse levels first); see the kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGTile = 8;       // tile side in feature-map pixels
 constexpr int kGThreads = 256;
-constexpr int kGMaxHits = 2048; // RoIs per tile handled in one epoch
-constexpr int kBinMaxN = 8192;  // RoIs sortable by the one-CTA binning kernel
+constexpr int kBinMaxN = 8192;  // RoIs per call (uint16 positions, per-tile hit list in shared memory)
+constexpr size_t kBinSmemMax = 200 * 1024;
 
 struct __align__(8) GTap {
     int lo;      // floor tap index; the ceil tap is lo + 1 iff lerp != 0.  Invalid: a large negative number.
@@ -395,7 +392,8 @@ struct __align__(8) GTap {
 struct GatherParams {
     PyrLevel lv[4];
     int tiles_x[4];
-    int tile_base[5];  // prefix of tiles per image over levels
+    int tiles_n[4];   // tiles per image of each level
+    int blk_base[4];  // blockIdx layout: level 3 first ... level 0 last; blk_base[i] = first block of the i-th group
     int B, C, N;
     int ph, pw;
     const float* grads;      // [N][ph*pw][C]
@@ -404,58 +402,95 @@ struct GatherParams {
     const float4* rp;        // [N] {y p0, 1/y scale, x p0, 1/x scale}: sample position of bin b ~ p0 + b*scale
     const GTap* taps;        // [N][ph + pw]
     const int32_t* offsets;  // [4B + 1] positions of each (image, level) segment
-    int accumulate;          // 0: overwrite (zero_fill semantics); 1: add to what is there
 };
 
-// pass 1a: composite keys sorted descending -> ascending (image*4 + level, index); CSR offsets.
+// pass 1a: stable counting sort of the RoIs by key = image*4 + level (one CTA, 32 warps): warp w owns the
+// contiguous index range [w*chunk, (w+1)*chunk) and walks it 32 RoIs at a time; __match_any_sync ranks equal
+// keys inside a step, a per-(key, warp) histogram in shared memory carries the rank across steps, and one
+// block scan over the (key-major, warp-minor) histogram turns ranks into positions - so rid lists every
+// (image, level) segment in ascending RoI index.  RoIs with a bad box_index are left out (rid tail = -1).
+constexpr int kBinWarps = 32;
+
 __global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_index,
-                                                       int N, int P, int B, LevelRule rule, int32_t* __restrict__ rid,
+                                                       int N, int B, LevelRule rule, int32_t* __restrict__ rid,
                                                        int32_t* __restrict__ offsets, int* err) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(bin_smem);
-    int* cnt = reinterpret_cast<int*>(bin_smem + (size_t)P * 8);  // [4B + 1]
     const int K = 4 * B;
-    const int tid = threadIdx.x;
-    for (int k = tid; k <= K; k += blockDim.x) cnt[k] = 0;
+    int* hist = reinterpret_cast<int*>(bin_smem);                 // [K][32]
+    uint32_t* packed = reinterpret_cast<uint32_t*>(hist + (size_t)K * kBinWarps);  // [N] key << 16 | rank in (key, warp)
+    __shared__ int s_warp_tot[kBinWarps];
+    const int tid = threadIdx.x, warp = tid >> 5, wl = tid & 31;
+    for (int i = tid; i < K * kBinWarps; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int n = tid; n < P; n += blockDim.x) {
-        uint64_t key = 0ull;
-        if (n < N) {
+
+    const int chunk = ((N + kBinWarps - 1) / kBinWarps + 31) & ~31;
+    const int nbeg = warp * chunk, nend = min(N, nbeg + chunk);
+    for (int n0 = nbeg; n0 < nend; n0 += 32) {
+        const int n = n0 + wl;
+        int k = -1;
+        if (n < nend) {
             const float y1 = __ldg(boxes + 4 * n), x1 = __ldg(boxes + 4 * n + 1);
             const float y2 = __ldg(boxes + 4 * n + 2), x2 = __ldg(boxes + 4 * n + 3);
             const int bi = box_index ? __ldg(box_index + n) : 0;
-            if ((unsigned)bi < (unsigned)B) {
-                const int k = bi * 4 + roi_level(y1, x1, y2, x2, rule) - 2;
-                atomicAdd(&cnt[k], 1);
-                key = ((uint64_t)(uint32_t)(K - k) << 32) | (uint64_t)(0xffffffffu - (uint32_t)n);
-            } else {
-                atomicOr(err, 1);
-            }
+            if ((unsigned)bi < (unsigned)B) k = bi * 4 + roi_level(y1, x1, y2, x2, rule) - 2;
+            else atomicOr(err, 1);
         }
-        skeys[n] = key;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (k >= 0 && wl == leader) {
+            base = hist[k * kBinWarps + warp];
+            hist[k * kBinWarps + warp] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (n < nend) packed[n] = (k >= 0) ? (((uint32_t)k << 16) | (uint32_t)(base + __popc(peers & ((1u << wl) - 1u)))) : 0xffffffffu;
+        __syncwarp();
     }
     __syncthreads();
-    block_bitonic_desc(skeys, P, 0u, 2u, 1u, (unsigned)P);
-    for (int j = tid; j < N; j += blockDim.x) {
-        const uint64_t kv = skeys[j];
-        rid[j] = kv ? (int32_t)(0xffffffffu - (uint32_t)(kv & 0xffffffffu)) : -1;
-    }
-    if (tid < 32) {  // exclusive scan of cnt[0..K) by one warp
-        int carry = 0;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + tid;
-            const int v = (k < K) ? cnt[k] : 0;
-            int incl = v;
+
+    // exclusive scan of hist in (key, warp) order
+    const int E = K * kBinWarps;
+    const int per = (E + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int ebeg = min(E, tid * per), eend = min(E, ebeg + per);
+    int local = 0;
+    for (int e = ebeg; e < eend; ++e) local += hist[e];
+    int incl = local;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= o) incl += u;
-            }
-            if (k < K) offsets[k] = carry + incl - v;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (tid == 0) offsets[K] = carry;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (wl >= o) incl += u;
     }
+    if (wl == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = s_warp_tot[wl];
+        int inc2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (wl >= o) inc2 += u;
+        }
+        s_warp_tot[wl] = inc2 - v;
+    }
+    __syncthreads();
+    int run = s_warp_tot[warp] + incl - local;
+    for (int e = ebeg; e < eend; ++e) {
+        const int v = hist[e];
+        hist[e] = run;
+        run += v;
+    }
+    __syncthreads();
+    const int total = s_warp_tot[kBinWarps - 1] + __shfl_sync(0xffffffffu, incl, 31);  // valid only in the last warp
+    if (tid == blockDim.x - 1) offsets[K] = total;
+    for (int k = tid; k < K; k += blockDim.x) offsets[k] = hist[k * kBinWarps];
+    __shared__ int s_total;
+    if (tid == blockDim.x - 1) s_total = total;
+    __syncthreads();
+    for (int n = tid; n < N; n += blockDim.x) {
+        const uint32_t pk = packed[n];
+        if (pk != 0xffffffffu) rid[hist[(pk >> 16) * kBinWarps + n / chunk] + (int)(pk & 0xffffu)] = n;
+    }
+    for (int j = s_total + tid; j < N; j += blockDim.x) rid[j] = -1;
 }
 
 // pass 1b: one 128-thread CTA per sorted position: the ph + pw taps, the pixel footprint and the
@@ -513,14 +548,14 @@ __global__ void __launch_bounds__(128) roi_taps_kernel(const float* __restrict__
     }
 }
 
-// Candidate bins [b0, b1] whose sample can touch pixel `pix` (|pos - pix| < 1), with slack; every
-// candidate is verified exactly against its tap afterwards, so over-inclusion is harmless.
-__device__ __forceinline__ void bin_range(float p0, float inv, int pix, int nb, int& b0, int& b1) {
+// Candidate bins [b0, b1] whose sample can touch a pixel of [pix_lo, pix_hi] (position within 1 of it), with
+// slack; every candidate is verified exactly against its tap afterwards, so over-inclusion is harmless.
+__device__ __forceinline__ void bin_range(float p0, float inv, int pix_lo, int pix_hi, int nb, int& b0, int& b1) {
     b0 = 0;
     b1 = nb - 1;
     if (inv != 0.f && inv == inv) {
-        const float u = ((float)(pix - 1) - p0) * inv;
-        const float v = ((float)(pix + 1) - p0) * inv;
+        const float u = ((float)(pix_lo - 1) - p0) * inv;
+        const float v = ((float)(pix_hi + 1) - p0) * inv;
         const float lo = fminf(u, v) - 0.02f, hi = fmaxf(u, v) + 0.02f;
         if (lo == lo && hi == hi) {
             b0 = max(0, (int)ceilf(fmaxf(lo, -1.0f)));
@@ -544,166 +579,289 @@ __device__ __forceinline__ float tap_weight(const GTap t, int pix) {
     return 0.f;
 }
 
-// pass 2: one CTA per 8x8 tile of one (image, level) map.  256 threads = 8 warps; warp w owns tile column w
-// and walks its 8 rows; a lane carries 8 channels (two float4), so one warp covers 256 channels and the
-// per-(pixel, RoI) bookkeeping is paid once per 256 channels.
-constexpr int kGTapBytes = 32 * 1024;  // shared-memory budget for the staged taps of one batch of RoIs
-constexpr int kGBatchMax = 64;
+// pass 2: one CTA per 8x8 tile of one (image, level) map.  256 threads = 8 warps; warp w owns tile ROW w, a lane
+// carries 4 NV channels of all 8 pixels of that row in registers, so a warp covers 128 NV channels and every
+// gradient load is a 512-byte contiguous warp access.  More channels take ceil(C / (128 NV)) passes.
+//
+// Work is enumerated from the RoI side, never searched from the pixel side:
+//   plan      (CTA, once per batch of <= 32 RoIs reaching the tile) stage the row taps and the column items
+//             {bin column offset, tile column, weights} and trim, per tile row, the range of bin rows whose taps
+//             land on it and, for the tile, the range of bin columns whose taps land in its 8 columns;
+//   generate  (warp, lane = RoI) expand (RoI, bin row, bin column) into a flat per-warp queue of work items
+//             {gradient offset, tile column, wy * (1 - xl), wy * xl}; a warp scan places the items in RoI order;
+//   consume   (warp) a branch-light pipelined loop: four items, four 128-bit loads in flight, then a warp-uniform
+//             switch on the tile column adds the bin into the one or two accumulators it touches (no dynamic
+//             register indexing, no wasted FMAs).
+constexpr int kOBatchMax = 32;   // RoIs per plan = lanes of the generating warp
+constexpr int kOQueue = 256;     // work items per warp queue; needs ph * pw <= kOQueue
+constexpr int kOMaxPool = 16;
+constexpr int kONoop = 9;
 
-template <int POOL>
-__global__ void __launch_bounds__(kGThreads) roialign_bwd_gather_kernel(const GatherParams p) {
-    __shared__ int s_hits[kGMaxHits];
-    __shared__ int s_wcnt[kGThreads / 32];
-    __shared__ __align__(16) unsigned char s_tapmem[kGTapBytes];
-    __shared__ short2 s_rng[kGBatchMax][2 * kGTile];  // candidate bin range per (RoI, tile row | tile column)
-    __shared__ int s_goff[kGBatchMax];                // rid * P2
+struct __align__(16) ColItem {
+    int off;  // bin column * C (element offset inside a bin row)
+    int idx;  // floor column relative to the tile + 1, 0..8 (kONoop: no contribution)
+    float wa, wb;
+};
+
+struct __align__(16) QItem {
+    int off;  // element offset of the bin in grads (32-bit by eligibility)
+    int idx;  // as ColItem.idx
+    float wa, wb;
+};
+
+template <int NV>
+struct AccRow {
+    float4 a[kGTile][NV];
+};
+
+template <int NV>
+__device__ __forceinline__ void fma_px(float4 (&a)[NV], float w, const float4 (&v)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        a[k].x = fmaf(w, v[k].x, a[k].x);
+        a[k].y = fmaf(w, v[k].y, a[k].y);
+        a[k].z = fmaf(w, v[k].z, a[k].z);
+        a[k].w = fmaf(w, v[k].w, a[k].w);
+    }
+}
+
+// Adds one bin into the row accumulators: tile column idx - 1 gets wa, column idx gets wb.
+template <int NV>
+__device__ __forceinline__ void owner_accumulate(AccRow<NV>& r, int idx, float wa, float wb, const float4 (&v)[NV]) {
+    switch (idx) {
+        case 0: fma_px<NV>(r.a[0], wb, v); break;
+        case 1: fma_px<NV>(r.a[0], wa, v); fma_px<NV>(r.a[1], wb, v); break;
+        case 2: fma_px<NV>(r.a[1], wa, v); fma_px<NV>(r.a[2], wb, v); break;
+        case 3: fma_px<NV>(r.a[2], wa, v); fma_px<NV>(r.a[3], wb, v); break;
+        case 4: fma_px<NV>(r.a[3], wa, v); fma_px<NV>(r.a[4], wb, v); break;
+        case 5: fma_px<NV>(r.a[4], wa, v); fma_px<NV>(r.a[5], wb, v); break;
+        case 6: fma_px<NV>(r.a[5], wa, v); fma_px<NV>(r.a[6], wb, v); break;
+        case 7: fma_px<NV>(r.a[6], wa, v); fma_px<NV>(r.a[7], wb, v); break;
+        case 8: fma_px<NV>(r.a[7], wa, v); break;
+        default: break;
+    }
+}
+
+// dynamic shared memory layout of the gather kernel
+struct GatherSmem {
+    QItem queue[kGThreads / 32][kOQueue + 4];
+    unsigned char taps[kOBatchMax * (kOMaxPool * (sizeof(GTap) + sizeof(ColItem)))];  // per RoI: row taps, column items
+    uint16_t hits[kBinMaxN];  // sorted positions of the RoIs that reach this tile, ascending
+    short2 rng[kOBatchMax][kGTile + 1];  // per RoI: bin-row range per tile row, then the bin-column range
+    int goff[kOBatchMax];                // rid * P2 * C
+    int wcnt[kGThreads / 32];
+};
+
+template <int POOL, int NV, bool kAccumulate>  // NV float4 per lane and pixel
+__global__ void __launch_bounds__(kGThreads, (NV == 1) ? 3 : 2) roialign_bwd_gather_kernel(const GatherParams p) {
+    extern __shared__ __align__(16) unsigned char gather_smem_raw[];
+    GatherSmem& S = *reinterpret_cast<GatherSmem*>(gather_smem_raw);
 
     const int ph = POOL ? POOL : p.ph;
     const int pw = POOL ? POOL : p.pw;
     const int P2 = ph * pw;
     const int ntap = ph + pw;
-    const int batch_cap = min(kGBatchMax, kGTapBytes / (ntap * (int)sizeof(GTap)));
-    GTap* s_taps = reinterpret_cast<GTap*>(s_tapmem);
+    const int row_bytes = kOMaxPool * (int)sizeof(GTap);
+    const int roi_bytes = kOMaxPool * (int)(sizeof(GTap) + sizeof(ColItem));
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int wl = tid & 31;
 
-    // which tile
-    const int tiles_per_image = p.tile_base[4];
-    const int img = blockIdx.x / tiles_per_image;
-    int t = blockIdx.x - img * tiles_per_image;
-    int l = 0;
-    while (l < 3 && t >= p.tile_base[l + 1]) ++l;
-    t -= p.tile_base[l];
+    // which tile: coarse levels first (their tiles collect the most RoIs), image-major inside a level
+    int b = blockIdx.x;
+    const int l = (b < p.blk_base[1]) ? 3 : (b < p.blk_base[2]) ? 2 : (b < p.blk_base[3]) ? 1 : 0;
+    b -= (l == 3) ? 0 : (l == 2) ? p.blk_base[1] : (l == 1) ? p.blk_base[2] : p.blk_base[3];
     const PyrLevel L = (l == 0) ? p.lv[0] : (l == 1) ? p.lv[1] : (l == 2) ? p.lv[2] : p.lv[3];
     const int ntx = (l == 0) ? p.tiles_x[0] : (l == 1) ? p.tiles_x[1] : (l == 2) ? p.tiles_x[2] : p.tiles_x[3];
-    const int ty0 = (t / ntx) * kGTile;
-    const int tx0 = (t - (t / ntx) * ntx) * kGTile;
+    const int tiles_l = (l == 0) ? p.tiles_n[0] : (l == 1) ? p.tiles_n[1] : (l == 2) ? p.tiles_n[2] : p.tiles_n[3];
+    const int img = b / tiles_l;
+    const int t = b - img * tiles_l;
+    const int tyi = t / ntx;
+    const int ty0 = tyi * kGTile;
+    const int tx0 = (t - tyi * ntx) * kGTile;
     const int H = L.H, W = L.W, C = p.C;
-    float* out = L.ptr + (size_t)img * H * W * C;
 
     const int lbeg = __ldg(p.offsets + img * 4 + l);
     const int lend = __ldg(p.offsets + img * 4 + l + 1);
 
-    int epoch = 0;
-    int next = lbeg;
-    do {
-        // ---- cull: which RoIs of this (image, level) reach the tile?  Ordered compaction keeps the
-        //      ascending RoI index, i.e. a fixed summation order. ----
+    // ---- cull: which RoIs of this (image, level) reach the tile?  Ordered compaction keeps the ascending
+    //      RoI index, i.e. a fixed summation order. ----
+    int nh = 0;
+    for (int next = lbeg; next < lend; next += kGThreads) {
+        const int j = next + tid;
+        bool hit = false;
+        if (j < lend) {
+            const int4 bb = __ldg(p.bbox + j);
+            hit = bb.y >= ty0 && bb.x <= ty0 + kGTile - 1 && bb.w >= tx0 && bb.z <= tx0 + kGTile - 1;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (wl == 0) S.wcnt[warp] = __popc(m);
         __syncthreads();
-        int nh = 0;
-        while (next < lend && nh + kGThreads <= kGMaxHits) {
-            const int j = next + tid;
-            bool hit = false;
-            if (j < lend) {
-                const int4 bb = __ldg(p.bbox + j);
-                hit = bb.y >= ty0 && bb.x <= ty0 + kGTile - 1 && bb.w >= tx0 && bb.z <= tx0 + kGTile - 1;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (wl == 0) s_wcnt[warp] = __popc(m);
-            __syncthreads();
-            int before = 0, total = 0;
+        int before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < kGThreads / 32; ++w) {
-                const int v = s_wcnt[w];
-                if (w < warp) before += v;
-                total += v;
+        for (int w = 0; w < kGThreads / 32; ++w) {
+            const int v = S.wcnt[w];
+            if (w < warp) before += v;
+            total += v;
+        }
+        if (hit) S.hits[nh + before + __popc(m & ((1u << wl) - 1u))] = (uint16_t)j;
+        nh += total;
+        __syncthreads();
+    }
+
+    const int y = ty0 + warp;  // this warp's feature-map row
+    const bool replan = nh > kOBatchMax;
+    bool planned = false;
+    QItem* queue = S.queue[warp];
+    for (int cbase = 0; cbase < C; cbase += 128 * NV) {
+        // lane wl owns channels cbase + 4 wl + 128 k, k < NV: each k is one 512-byte warp access
+        const int c = cbase + 4 * wl;
+        AccRow<NV> acc;
+#pragma unroll
+        for (int j = 0; j < kGTile; ++j)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc.a[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool live[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) live[k] = (c + 128 * k) < C;
+        const float* gbase = p.grads + (live[0] ? c : 0);
+        const bool row_ok = y < H && cbase < C;  // warp-uniform
+
+        for (int h0 = 0; h0 < nh; h0 += kOBatchMax) {
+            const int nb = min(kOBatchMax, nh - h0);
+            if (replan || !planned) {
+                // ---- plan ----
+                if (planned) __syncthreads();  // everyone is done with the previous plan
+                for (int i = tid; i < nb * ntap; i += kGThreads) {
+                    const int h = i / ntap, bq = i - h * ntap;
+                    const GTap tp = ldg_tap(p.taps + (size_t)S.hits[h0 + h] * ntap + bq);
+                    unsigned char* base = S.taps + h * roi_bytes;
+                    if (bq < ph) {
+                        reinterpret_cast<GTap*>(base)[bq] = tp;
+                    } else {
+                        ColItem it;
+                        const int j0 = tp.lo - tx0;
+                        it.off = (bq - ph) * C;
+                        it.idx = ((unsigned)(j0 + 1) <= (unsigned)kGTile) ? j0 + 1 : kONoop;
+                        it.wa = __fsub_rn(1.0f, tp.lerp);
+                        it.wb = tp.lerp;
+                        reinterpret_cast<ColItem*>(base + row_bytes)[bq - ph] = it;
+                    }
+                }
+                for (int i = tid; i < nb * (kGTile + 1); i += kGThreads) {
+                    const int h = i / (kGTile + 1), line = i - h * (kGTile + 1);
+                    const int j = S.hits[h0 + h];
+                    const int4 bb = __ldg(p.bbox + j);
+                    const float4 rp = __ldg(p.rp + j);
+                    const GTap* tp = p.taps + (size_t)j * ntap;
+                    int b0 = 1, b1 = 0;
+                    if (line < kGTile) {
+                        const int yy = ty0 + line;
+                        if (yy >= bb.x && yy <= bb.y) {
+                            bin_range(rp.x, rp.y, yy, yy, ph, b0, b1);
+                            while (b0 <= b1 && tap_weight(ldg_tap(tp + b0), yy) == 0.f) ++b0;
+                            while (b1 >= b0 && tap_weight(ldg_tap(tp + b1), yy) == 0.f) --b1;
+                        }
+                    } else {
+                        bin_range(rp.z, rp.w, tx0, tx0 + kGTile - 1, pw, b0, b1);
+                        // a column tap reaches the tile iff its floor column is in [tx0 - 1, tx0 + 7]
+                        while (b0 <= b1 && (unsigned)(ldg_tap(tp + ph + b0).lo - tx0 + 1) > (unsigned)kGTile) ++b0;
+                        while (b1 >= b0 && (unsigned)(ldg_tap(tp + ph + b1).lo - tx0 + 1) > (unsigned)kGTile) --b1;
+                        S.goff[h] = __ldg(p.rid + j) * P2 * C;
+                    }
+                    S.rng[h][line] = make_short2((short)b0, (short)b1);
+                }
+                __syncthreads();
+                planned = true;
             }
-            if (hit) s_hits[nh + before + __popc(m & ((1u << wl) - 1u))] = j;
-            nh += total;
-            next += kGThreads;
-            __syncthreads();
+            if (!row_ok) continue;
+
+            // ---- generate + consume, in rounds of as many RoIs as fit the queue (RoIs in ascending index order) ----
+            int hdone = 0;
+            while (hdone < nb) {
+                const int h = hdone + wl;
+                short2 ry = make_short2(1, 0), rx = make_short2(1, 0);
+                if (h < nb) {
+                    ry = S.rng[h][warp];
+                    rx = S.rng[h][kGTile];
+                }
+                const int nby = max(0, ry.y - ry.x + 1), nbx = max(0, rx.y - rx.x + 1);
+                const int cnt = nby * nbx;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (wl >= o) incl += u;
+                }
+                // lanes whose items still fit; incl is non-decreasing, cnt <= kOQueue, so lane 0 always fits
+                const unsigned fit = __ballot_sync(0xffffffffu, incl <= kOQueue);
+                const int m = min(nb - hdone, __ffs(~fit) ? __ffs(~fit) - 1 : 32);
+                const int n = __shfl_sync(0xffffffffu, incl, m - 1);
+                if (wl < m && cnt > 0) {
+                    int pos = incl - cnt;
+                    const GTap* ty = reinterpret_cast<const GTap*>(S.taps + h * roi_bytes);
+                    const ColItem* cols = reinterpret_cast<const ColItem*>(S.taps + h * roi_bytes + row_bytes);
+                    const int goff = S.goff[h];
+                    for (int by = ry.x; by <= ry.y; ++by) {
+                        const float wy = tap_weight(ty[by], y);
+                        const int rowoff = goff + (by * pw) * C;
+                        for (int bx = rx.x; bx <= rx.y; ++bx) {
+                            const ColItem ci = cols[bx];
+                            QItem q;
+                            q.off = rowoff + ci.off;
+                            q.idx = (wy != 0.f) ? ci.idx : kONoop;
+                            q.wa = wy * ci.wa;
+                            q.wb = wy * ci.wb;
+                            queue[pos++] = q;
+                        }
+                    }
+                }
+                if (wl < 4) {  // pad to a multiple of four with no-ops (offset 0 is a valid address)
+                    QItem q;
+                    q.off = 0; q.idx = kONoop; q.wa = 0.f; q.wb = 0.f;
+                    queue[n + wl] = q;
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int i = 0; i < n; i += 4) {
+                    QItem it[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) it[u] = queue[i + u];
+                    float4 v[4][NV];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < NV; ++k)
+                            v[u][k] = live[k] ? ldg_f4(gbase + it[u].off + 128 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) owner_accumulate<NV>(acc, it[u].idx, it[u].wa, it[u].wb, v[u]);
+                }
+                __syncwarp();
+                hdone += m;
+            }
         }
 
-        for (int h0 = 0; h0 < nh || (h0 == 0 && epoch == 0); h0 += batch_cap) {
-            const int nb = max(0, min(batch_cap, nh - h0));
-            // ---- plan: stage the taps of this batch and the candidate bin ranges per tile row / column ----
-            for (int i = tid; i < nb * ntap; i += kGThreads) {
-                const int h = i / ntap, b = i - h * ntap;
-                s_taps[i] = ldg_tap(p.taps + (size_t)s_hits[h0 + h] * ntap + b);
-            }
-            for (int i = tid; i < nb * 2 * kGTile; i += kGThreads) {
-                const int h = i >> 4, line = i & 15;
-                const int j = s_hits[h0 + h];
-                const int4 bb = __ldg(p.bbox + j);
-                const float4 rp = __ldg(p.rp + j);
-                int b0 = 1, b1 = 0;
-                if (line < kGTile) {
-                    const int y = ty0 + line;
-                    if (y >= bb.x && y <= bb.y) bin_range(rp.x, rp.y, y, ph, b0, b1);
-                } else {
-                    const int x = tx0 + line - kGTile;
-                    if (x >= bb.z && x <= bb.w) bin_range(rp.z, rp.w, x, pw, b0, b1);
-                }
-                s_rng[h][line] = make_short2((short)b0, (short)b1);
-                if (line == 0) s_goff[h] = __ldg(p.rid + j) * P2;
-            }
-            __syncthreads();
-
-            // ---- accumulate: warp = tile column, 8 rows one after another, 8 channels per lane ----
-            const int x = tx0 + warp;
-            if (x < W) {
-                for (int cbase = 0; cbase < C; cbase += 8 * 32) {
-                    const int c = cbase + 8 * wl;
-                    if (c >= C) continue;
-                    const bool two = (c + 4 < C);
-#pragma unroll 1
-                    for (int k = 0; k < kGTile; ++k) {
-                        const int y = ty0 + k;
-                        if (y >= H) break;
-                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-#pragma unroll 1
-                        for (int h = 0; h < nb; ++h) {
-                            const short2 ry = s_rng[h][k];
-                            const short2 rx = s_rng[h][kGTile + warp];
-                            if (ry.y < ry.x || rx.y < rx.x) continue;
-                            const GTap* ty = s_taps + h * ntap;
-                            const GTap* tx = ty + ph;
-                            const float* g = p.grads + (size_t)s_goff[h] * C + c;
-                            for (int by = ry.x; by <= ry.y; ++by) {
-                                const float wy = tap_weight(ty[by], y);
-                                if (wy == 0.f) continue;
-                                const float* grow = g + (size_t)(by * pw) * C;
-                                for (int bx = rx.x; bx <= rx.y; ++bx) {
-                                    const float wx = tap_weight(tx[bx], x);
-                                    if (wx == 0.f) continue;
-                                    const float w = wy * wx;
-                                    const float* q = grow + (size_t)bx * C;
-                                    const float4 v0 = ldg_f4(q);
-                                    a0.x = fmaf(w, v0.x, a0.x);
-                                    a0.y = fmaf(w, v0.y, a0.y);
-                                    a0.z = fmaf(w, v0.z, a0.z);
-                                    a0.w = fmaf(w, v0.w, a0.w);
-                                    if (two) {
-                                        const float4 v1 = ldg_f4(q + 4);
-                                        a1.x = fmaf(w, v1.x, a1.x);
-                                        a1.y = fmaf(w, v1.y, a1.y);
-                                        a1.z = fmaf(w, v1.z, a1.z);
-                                        a1.w = fmaf(w, v1.w, a1.w);
-                                    }
-                                }
-                            }
+        // ---- every pixel of the tile is written exactly once ----
+        if (row_ok) {
+            float* o = L.ptr + (((size_t)img * H + y) * W + tx0) * C + c;
+#pragma unroll
+            for (int j = 0; j < kGTile; ++j) {
+                if (tx0 + j < W) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        if (!live[k]) continue;
+                        float4 a = acc.a[j][k];
+                        float* q = o + j * C + 128 * k;
+                        if (kAccumulate) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(q);
+                            a.x += o0.x; a.y += o0.y; a.z += o0.z; a.w += o0.w;
                         }
-                        // every pixel of the tile is written exactly once per batch (only the first overwrites)
-                        float* o = out + ((size_t)y * W + x) * C + c;
-                        if (p.accumulate || epoch > 0 || h0 > 0) {
-                            const float4 o0 = *reinterpret_cast<const float4*>(o);
-                            a0.x += o0.x; a0.y += o0.y; a0.z += o0.z; a0.w += o0.w;
-                            if (two) {
-                                const float4 o1 = *reinterpret_cast<const float4*>(o + 4);
-                                a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
-                            }
-                        }
-                        *reinterpret_cast<float4*>(o) = a0;
-                        if (two) *reinterpret_cast<float4*>(o + 4) = a1;
+                        stg_f4_stream(q, a);
                     }
                 }
             }
-            __syncthreads();
-            if (nb == 0) break;
         }
-        ++epoch;
-    } while (next < lend);
+    }
 }
 
 // Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
@@ -951,9 +1109,10 @@ static GatherWorkspace carve_gather(void* base, int B, int N, int pool) {
 static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int grads_layout, const float* grads,
                             float* const gfm[4], const void* workspace, size_t workspace_bytes) {
     if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
-    if ((C % 4) != 0 || pool > kMaxPool || N > kBinMaxN || N <= 0) return false;
+    if ((C % 4) != 0 || pool > kOMaxPool || N > kBinMaxN || N <= 0) return false;
+    if ((long long)N * pool * pool * C >= (1ll << 31)) return false;  // 32-bit element offsets into grads
     if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, B, N, pool).bytes) return false;
-    if ((size_t)(4 * (size_t)B + 1) * 4 > 96 * 1024) return false;
+    if ((size_t)4 * B * kBinWarps * 4 + (size_t)N * 4 > kBinSmemMax || 4 * (long long)B >= 65536) return false;
     if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
     for (int l = 0; l < 4; ++l)
         if (!aligned16(gfm[l])) return false;
@@ -965,33 +1124,47 @@ static int launch_bwd_gather(const float* grads, const int H[4], const int W[4],
                              int accumulate, void* workspace, cudaStream_t stream) {
     const GatherWorkspace ws = carve_gather(workspace, B, N, pool);
     const LevelRule rule = make_level_rule(image_area);
-    int P = 32;
-    while (P < N) P <<= 1;
-    const size_t bin_smem = (size_t)P * 8 + (size_t)(4 * B + 1) * 4;
-    MRCNN_CUDA(cudaFuncSetAttribute(roi_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, P, B, rule, ws.rid, ws.offsets, device_error_word());
+    const size_t bin_smem = (size_t)4 * B * kBinWarps * 4 + (size_t)N * 4;
+    MRCNN_CUDA(cudaFuncSetAttribute(roi_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemMax));
+    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, B, rule, ws.rid, ws.offsets, device_error_word());
     MRCNN_LAUNCH_CHECK();
     GatherParams g = {};
-    int total = 0;
+    long long total = 0;
     for (int l = 0; l < 4; ++l) {
         g.lv[l] = {gfm[l], H[l], W[l]};
         g.tiles_x[l] = (W[l] + kGTile - 1) / kGTile;
-        g.tile_base[l] = total;
-        total += g.tiles_x[l] * ((H[l] + kGTile - 1) / kGTile);
+        g.tiles_n[l] = g.tiles_x[l] * ((H[l] + kGTile - 1) / kGTile);
+        total += (long long)g.tiles_n[l] * B;
     }
-    g.tile_base[4] = total;
+    MRCNN_REQUIRE(total < (1ll << 31), "mrcnn_pyramid_roi_align_backward: too many tiles");
+    g.blk_base[0] = 0;  // groups: level 3, 2, 1, 0
+    for (int i = 1; i < 4; ++i) g.blk_base[i] = g.blk_base[i - 1] + g.tiles_n[4 - i] * B;
     roi_taps_kernel<<<N, 128, 0, stream>>>(boxes, ws.rid, N, pool, pool, rule, g.lv[0], g.lv[1], g.lv[2], g.lv[3], ws.bbox,
                                           ws.rp, ws.taps);
     MRCNN_LAUNCH_CHECK();
     g.B = B; g.C = C; g.N = N;
     g.ph = pool; g.pw = pool;
     g.grads = grads; g.rid = ws.rid; g.bbox = ws.bbox; g.rp = ws.rp; g.taps = ws.taps; g.offsets = ws.offsets;
-    g.accumulate = accumulate;
-    const long long grid = (long long)total * B;
-    MRCNN_REQUIRE(grid < (1ll << 31), "mrcnn_pyramid_roi_align_backward: too many tiles");
-    if (pool == 7) roialign_bwd_gather_kernel<7><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
-    else if (pool == 14) roialign_bwd_gather_kernel<14><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
-    else roialign_bwd_gather_kernel<0><<<(unsigned)grid, kGThreads, 0, stream>>>(g);
+    const unsigned grid = (unsigned)total;
+    const bool wide = C > 128;  // 8 channels per lane: one pass covers 256 channels
+    const size_t smem = sizeof(GatherSmem);
+#define MRCNN_LAUNCH_GATHER_K(KERNEL)                                                                       \
+    do {                                                                                                    \
+        MRCNN_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        KERNEL<<<grid, kGThreads, smem, stream>>>(g);                                                       \
+    } while (0)
+#define MRCNN_LAUNCH_GATHER(POOL)                                                                           \
+    do {                                                                                                    \
+        if (wide && accumulate) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 2, true>));         \
+        else if (wide) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 2, false>));                 \
+        else if (accumulate) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 1, true>));            \
+        else MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 1, false>));                           \
+    } while (0)
+    if (pool == 7) MRCNN_LAUNCH_GATHER(7);
+    else if (pool == 14) MRCNN_LAUNCH_GATHER(14);
+    else MRCNN_LAUNCH_GATHER(0);
+#undef MRCNN_LAUNCH_GATHER_K
+#undef MRCNN_LAUNCH_GATHER
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }
@@ -1096,7 +1269,7 @@ int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], co
 int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const int H[4], const int W[4], int B,
                                      int C, const float* boxes, const int32_t* box_index, int N, int pool,
                                      float image_area, float* const gfm[4], int gfm_layout, int zero_fill,
-                                     const int32_t* image_offsets_host, void* workspace, size_t workspace_bytes,
+                                     const int32_t* image_offsets_host, int algo, void* workspace, size_t workspace_bytes,
                                      mrcnn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward: null level tables");
@@ -1123,9 +1296,17 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
     p.err = device_error_word();
     MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
 
-    if (image_offsets_host == nullptr &&
-        gather_eligible(B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes)) {
-        // pixel-owner gather: writes every pixel once (zero fill included), no atomics
+    MRCNN_REQUIRE(algo == MRCNN_BWD_AUTO || algo == MRCNN_BWD_GATHER || algo == MRCNN_BWD_SCATTER,
+                  "mrcnn_pyramid_roi_align_backward: unknown algo %d", algo);
+    const bool can_gather = image_offsets_host == nullptr &&
+                            gather_eligible(B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
+    if (algo == MRCNN_BWD_GATHER)
+        MRCNN_REQUIRE(can_gather,
+                      "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs channels-last grads and gfm, C %% 4 == 0, "
+                      "0 < N <= %d, no image_offsets_host and a 256-byte aligned workspace of "
+                      "mrcnn_pyramid_roi_align_backward_workspace_bytes()", kBinMaxN);
+    if (can_gather && algo == MRCNN_BWD_GATHER) {
+        // tile-owner gather: writes every pixel once (zero fill included), no atomics
         return launch_bwd_gather(grads, H, W, B, C, boxes, box_index, N, pool, image_area, gfm, zero_fill ? 0 : 1, workspace,
                                  stream);
     }

@@ -22,14 +22,16 @@ __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_a
            "rpn_refine", "detection_layer", "mrn_refine", "check_device_errors", "set_deterministic_backward"]
 
 
-# Backward of the channels-last PyramidROIAlign: False = column-aggregated vector reductions (fastest, fp32
-# atomics -> last-bit run-to-run differences); True = pixel-owner gather (no atomics, bit-reproducible, ~2x slower).
-DETERMINISTIC_BACKWARD = False
+# Backward of the channels-last PyramidROIAlign.  None (default) = MRCNN_BWD_AUTO: the library picks the faster
+# algorithm for the call.  True = the tile-owner gather where eligible (no atomics, every gradient pixel written
+# once, bit-reproducible); False = always the scatter (clear + column-aggregated vector reductions; fp32 atomics
+# -> last-bit run-to-run differences).
+DETERMINISTIC_BACKWARD = None
 
 
 def set_deterministic_backward(flag):
     global DETERMINISTIC_BACKWARD
-    DETERMINISTIC_BACKWARD = bool(flag)
+    DETERMINISTIC_BACKWARD = None if flag is None else bool(flag)
 
 
 def _stream():
@@ -212,15 +214,18 @@ class _PyramidRoiAlign(torch.autograd.Function):
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
         with torch.cuda.device(grad.device):
-            ws_bytes, ws = 0, None
-            if DETERMINISTIC_BACKWARD:
-                ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
+            ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
+            gather_ok = fl == NHWC and gl == NHWC and C % 4 == 0 and 0 < N <= 8192 and not offsets
+            if DETERMINISTIC_BACKWARD is None:
+                algo = _lib.BWD_AUTO
+            else:
+                algo = _lib.BWD_GATHER if (DETERMINISTIC_BACKWARD and gather_ok) else _lib.BWD_SCATTER
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,
                                                        _lib.vp4([g.data_ptr() for g in gfm]), fl, 1,
                                                        ctypes.cast(_lib.i32_array(offsets), ctypes.c_void_p) if offsets else None,
-                                                       _ptr(ws), ws_bytes, _stream()))
+                                                       algo, _ptr(ws), ws_bytes, _stream()))
         return (None, None, None, None, None, None) + tuple(gfm)
 
 

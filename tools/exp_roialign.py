@@ -9,15 +9,17 @@ wl = bench.Workload(torch, torch.device("cuda", 0))
 cl = torch.channels_last
 g7c, g14c = wl.g7.contiguous(memory_format=cl), wl.g14.contiguous(memory_format=cl)
 o7c, o14c = wl.out7.contiguous(memory_format=cl), wl.out14.contiguous(memory_format=cl)
+wl.g7n, wl.g14n = wl.g7.contiguous(), wl.g14.contiguous()
+o7n, o14n = wl.out7.contiguous(), wl.out14.contiguous()
 
 
 ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, 14), dtype=torch.uint8, device="cuda")
 
 
-def bwd(pool, g, gl, gfm, offs, gather=False):
+def bwd(pool, g, gl, gfm, offs, gather=False, ft=False):
     L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), gl, wl.Hs, wl.Ws, wl.batch, bench.CHANNELS, wl.boxes.data_ptr(),
                                                    wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gfm]),
-                                                   L.NHWC, 1, offs, ws.data_ptr() if gather else None, ws.numel() if gather else 0, wl._s()))
+                                                   L.NHWC, 1, offs, L.BWD_GATHER if gather else L.BWD_SCATTER, ws.data_ptr() if gather else None, ws.numel() if gather else 0, wl._s()))
 
 
 def fwd(pool, o, ol):
@@ -31,11 +33,11 @@ def zero_only():
 
 
 cases = {
-    "fwd7  nchw": lambda: fwd(7, wl.out7, L.NCHW), "fwd7  nhwc": lambda: fwd(7, o7c, L.NHWC),
-    "fwd14 nchw": lambda: fwd(14, wl.out14, L.NCHW), "fwd14 nhwc": lambda: fwd(14, o14c, L.NHWC),
-    "bwd7  nchw all": lambda: bwd(7, wl.g7, L.NCHW, wl.gfm7, None), "bwd7  nchw per-image": lambda: bwd(7, wl.g7, L.NCHW, wl.gfm7, wl.offsets),
+    "fwd7  nchw": lambda: fwd(7, o7n, L.NCHW), "fwd7  nhwc": lambda: fwd(7, o7c, L.NHWC),
+    "fwd14 nchw": lambda: fwd(14, o14n, L.NCHW), "fwd14 nhwc": lambda: fwd(14, o14c, L.NHWC),
+    "bwd7  nchw all": lambda: bwd(7, wl.g7n, L.NCHW, wl.gfm7, None), "bwd7  nchw per-image": lambda: bwd(7, wl.g7n, L.NCHW, wl.gfm7, wl.offsets),
     "bwd7  nhwc all": lambda: bwd(7, g7c, L.NHWC, wl.gfm7, None), "bwd7  nhwc per-image": lambda: bwd(7, g7c, L.NHWC, wl.gfm7, wl.offsets),
-    "bwd14 nchw all": lambda: bwd(14, wl.g14, L.NCHW, wl.gfm14, None), "bwd14 nchw per-image": lambda: bwd(14, wl.g14, L.NCHW, wl.gfm14, wl.offsets),
+    "bwd14 nchw all": lambda: bwd(14, wl.g14n, L.NCHW, wl.gfm14, None), "bwd14 nchw per-image": lambda: bwd(14, wl.g14n, L.NCHW, wl.gfm14, wl.offsets),
     "bwd14 nhwc all": lambda: bwd(14, g14c, L.NHWC, wl.gfm14, None), "bwd14 nhwc per-image": lambda: bwd(14, g14c, L.NHWC, wl.gfm14, wl.offsets),
     "bwd7  nhwc GATHER": lambda: bwd(7, g7c, L.NHWC, wl.gfm7, None, True), "bwd14 nhwc GATHER": lambda: bwd(14, g14c, L.NHWC, wl.gfm14, None, True),
     "torch zero_ of one pyramid": zero_only,

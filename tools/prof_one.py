@@ -8,6 +8,7 @@ from maskrcnn_b200 import _lib as L
 kind, pool, lay = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 gather = len(sys.argv) > 4 and sys.argv[4] == "gather"
 perimage = len(sys.argv) > 4 and sys.argv[4] == "perimage"
+ft = len(sys.argv) > 4 and sys.argv[4] == "ft"
 wl = bench.Workload(torch, torch.device("cuda", 0))
 cl = torch.channels_last
 lay_id = L.NHWC if lay == "nhwc" else L.NCHW
@@ -23,6 +24,6 @@ for _ in range(3):
     else:
         L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), lay_id, wl.Hs, wl.Ws, wl.batch, bench.CHANNELS, wl.boxes.data_ptr(),
                                                        wl.ind.data_ptr(), wl.N, pool, wl.area, L.vp4([x.data_ptr() for x in gf]), L.NHWC, 1,
-                                                       wl.offsets if perimage else None, ws.data_ptr() if gather else None, ws.numel() if gather else 0, wl._s()))
+                                                       wl.offsets if perimage else None, L.BWD_GATHER if gather else L.BWD_SCATTER, ws.data_ptr() if gather else None, ws.numel() if gather else 0, wl._s()))
 torch.cuda.synchronize()
 print("done")
