@@ -150,7 +150,7 @@ class Workload(object):
         self.Ws = _lib.i4([w for _, w in LEVEL_HW])
         self.area = float(IMAGE * IMAGE)
         self.offsets = _lib.i32_array([i * ROIS_PER_IMAGE for i in range(batch + 1)])  # host: boxes grouped by image
-        self.ws = torch.empty(_lib.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(batch, self.N, 14),
+        self.ws = torch.empty(_lib.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(self.Hs, self.Ws, batch, self.N, 14),
                               dtype=torch.uint8, device=device)
         self.launches = 0
 
@@ -169,7 +169,7 @@ class Workload(object):
         L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), self.crop_layout, self.Hs, self.Ws, self.batch, CHANNELS,
                                                        self.boxes.data_ptr(), self.ind.data_ptr(), self.N, pool, self.area,
                                                        L.vp4([g.data_ptr() for g in gfm]), L.NHWC, 1, None, L.BWD_AUTO, self.ws.data_ptr(), self.ws.numel(), self._s()))
-        self.launches += 2   # roialign_bwd_nhwc_kernel (first-touch clearing) + zero_untouched_kernel
+        self.launches += 4   # bwd_items_kernel<count>, bwd_alloc_kernel, bwd_items_kernel<fill>, roialign_bwd_gather_kernel
 
     def mask_targets(self):
         L = self.L
@@ -582,8 +582,8 @@ def main():
         ops = {
             "roialign_fwd_nhwc_kernel<7,nhwc>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
             "roialign_fwd_nhwc_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
-            "roialign_bwd_nhwc_kernel<7,nhwc>+zero_untouched_kernel": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
-            "roialign_bwd_nhwc_kernel<14,nhwc>+zero_untouched_kernel": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
+            "bwd_items x2+bwd_alloc+roialign_bwd_gather_kernel<7,nhwc>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
+            "bwd_items x2+bwd_alloc+roialign_bwd_gather_kernel<14,nhwc>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
         }
         kern = {}

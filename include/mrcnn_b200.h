@@ -94,21 +94,23 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
  * (gfm_layout), which is cleared first when zero_fill != 0 (what CropFunction.backward does per level,
  * c++ext/maskrcnn/__init__.py:52).  No gradient w.r.t. boxes (model.py:358).
  * algo:
- *   MRCNN_BWD_GATHER   tile-owner gather: every 8x8 tile of every gradient map is owned by one CTA that sums, in
- *                      registers, the RoIs reaching it and writes each pixel exactly once - no atomics, no zero
- *                      fill pass, bit-reproducible run to run.  Needs channels-last grads and gfm, C % 4 == 0,
- *                      0 < N <= 8192, image_offsets_host == NULL and a 256-byte aligned workspace of
- *                      mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool) bytes.
+ *   MRCNN_BWD_GATHER   row-owner gather: every run of 8 pixels of every gradient-map row is owned by one warp that
+ *                      sums, in registers, the bins reaching it and writes each pixel exactly once - no atomics on
+ *                      gradient data, no zero-fill pass, no read-modify-write of the pyramid.  Needs channels-last
+ *                      grads and gfm, C % 4 == 0, N > 0, N * pool^2 * C < 2^31, image_offsets_host == NULL and a
+ *                      256-byte aligned workspace of mrcnn_pyramid_roi_align_backward_workspace_bytes() bytes.
  *   MRCNN_BWD_SCATTER  clear, then scatter with column-aggregated 128-bit vector reductions
  *                      (red.global.add.v4.f32) for a channels-last gfm, scalar atomics for an NCHW gfm.
  *                      workspace may be NULL.
- *   MRCNN_BWD_AUTO     the faster of the two for the call (currently SCATTER).
+ *   MRCNN_BWD_AUTO     GATHER when its requirements are met (it is the faster one),
+ *                      SCATTER otherwise.
  * image_offsets_host: optional HOST array of B+1 ints (scatter only): boxes of image i are rows
  * [off[i], off[i+1]), box_index is ignored, and the call clears + scatters image by image. */
 #define MRCNN_BWD_AUTO 0
 #define MRCNN_BWD_GATHER 1
 #define MRCNN_BWD_SCATTER 2
-MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N, int pool);
+MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const int W[4], int B, int N,
+                                                                  int pool);
 MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout,
                                      const int H[4], const int W[4], int B, int C,
                                      const float* boxes, const int32_t* box_index, int N, int pool,

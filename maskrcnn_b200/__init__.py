@@ -8,7 +8,7 @@
 All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.h).  No CPU fallback.
 """
 from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, mrn_refine, nms,  # noqa: F401
-                  proposal_layer, pyramid_roi_align, roi_align, rpn_refine, set_deterministic_backward)
+                  proposal_layer, pyramid_roi_align, roi_align, rpn_refine, set_backward_algorithm)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 
 __version__ = "0.1.0"

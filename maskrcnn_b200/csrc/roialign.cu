@@ -368,246 +368,148 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward as a GATHER (tile-owner) — channels-last gradients in, channels-last pyramid gradient out.
+// Backward as a GATHER (row-owner) — channels-last gradients in, channels-last pyramid gradient out.
 //
-// Every 8x8 tile of every (image, level) gradient map is owned by one CTA, which sums the contributions
-// of all RoIs of that (image, level) that reach the tile and writes each pixel exactly once.  No atomics,
-// no separate zero fill, no read-modify-write: DRAM traffic is the algorithmic minimum (upstream gradient
-// read once, gradient pyramid written once), and the summation order is fixed -> bit-reproducible.
+// The adjoint of bilinear sampling is a sparse-matrix product  dImage[pixels x C] = A * g[bins x C]  with four
+// non-zeros per bin.  The scatter kernel walks A by columns (bins) and needs atomics, a zero-fill pass and a
+// read-modify-write of the whole gradient pyramid.  This path walks A by ROWS: a "unit" is one row of 8
+// consecutive pixels of one (image, level) gradient map, owned by exactly one warp, which keeps the 8 x 256
+// channel sums in registers and writes every pixel exactly once - no atomics on gradient data, no zero-fill
+// pass, no read-modify-write: DRAM traffic is the algorithmic minimum (upstream gradient read once, gradient
+// pyramid written once).
 //
-//   pass 1a roi_bin_kernel (one CTA): key = image*4 + level per RoI, sorted (key, index) -> CSR lists.
-//   pass 1b roi_taps_kernel: per RoI the ph + pw axis taps, the pixel footprint, the affine bin-position model.
-//   pass 2  roialign_bwd_gather_kernel: grid = tiles (coarse levels first); see the kernel.
+//   pass 1  bwd_items_kernel<false>  every (RoI, bin row, floor|ceil tap) thread walks its bin columns and
+//                                    counts the work items each unit will receive (run-aggregated atomics).
+//   pass 2  bwd_alloc_kernel         a slice of the item array per unit (warp-aggregated cursor).
+//   pass 3  bwd_items_kernel<true>   the same walk writes the items {gradient offset, wy(1-xl), wy xl, column}.
+//   pass 4  roialign_bwd_gather_kernel  one warp per unit, coarse levels first: items are fetched 32 at a time
+//                                    (one coalesced 512-byte read) and broadcast through shared memory; the
+//                                    gradients stream through a 4-stage cp.async pipeline; a warp-uniform switch
+//                                    on the column adds a bin into the one or two accumulators it touches.
+// Passes 1-3 move ~16 bytes per non-zero of A (a few % of the gradient bytes) and replace all per-tile searching.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGTile = 8;       // tile side in feature-map pixels
-constexpr int kGThreads = 256;
-constexpr int kBinMaxN = 8192;  // RoIs per call (uint16 positions, per-tile hit list in shared memory)
-constexpr size_t kBinSmemMax = 200 * 1024;
+constexpr int kGTile = 8;       // pixels per unit
+constexpr int kONoop = 9;
 
-struct __align__(8) GTap {
-    int lo;      // floor tap index; the ceil tap is lo + 1 iff lerp != 0.  Invalid: a large negative number.
-    float lerp;
+struct __align__(16) QItem {
+    int off;    // element offset of the bin in grads (32-bit by eligibility)
+    float wa;   // weight of pixel idx - 1 of the unit
+    float wb;   // weight of pixel idx
+    int idx;    // floor column relative to the unit + 1, 0..8 (kONoop: no contribution)
+};
+
+struct UnitGeom {
+    float* ptr;
+    int H, W;
+    int segs;       // units per pixel row: ceil(W / 8)
+    int unit_base;  // first unit of the level; levels are laid out coarse to fine (P5 first)
 };
 
 struct GatherParams {
-    PyrLevel lv[4];
-    int tiles_x[4];
-    int tiles_n[4];   // tiles per image of each level
-    int blk_base[4];  // blockIdx layout: level 3 first ... level 0 last; blk_base[i] = first block of the i-th group
+    UnitGeom g[4];
+    LevelRule rule;
     int B, C, N;
     int ph, pw;
-    const float* grads;      // [N][ph*pw][C]
-    const int32_t* rid;      // [N] RoI index at sorted position j ((image, level) major, index minor); -1 = skipped
-    const int4* bbox;        // [N] {ylo, yhi, xlo, xhi} pixel footprint of position j (empty if ylo > yhi)
-    const float4* rp;        // [N] {y p0, 1/y scale, x p0, 1/x scale}: sample position of bin b ~ p0 + b*scale
-    const GTap* taps;        // [N][ph + pw]
-    const int32_t* offsets;  // [4B + 1] positions of each (image, level) segment
+    int units;
+    const float* boxes;
+    const int32_t* box_index;
+    const float* grads;  // [N][ph*pw][C]
+    int* cnt;            // [units] items per unit
+    int* pos;            // [units] after alloc: first item; after fill: one past the last item
+    unsigned int* cursor;
+    QItem* items;
+    int* err;
 };
 
-// pass 1a: stable counting sort of the RoIs by key = image*4 + level (one CTA, 32 warps): warp w owns the
-// contiguous index range [w*chunk, (w+1)*chunk) and walks it 32 RoIs at a time; __match_any_sync ranks equal
-// keys inside a step, a per-(key, warp) histogram in shared memory carries the rank across steps, and one
-// block scan over the (key-major, warp-minor) histogram turns ranks into positions - so rid lists every
-// (image, level) segment in ascending RoI index.  RoIs with a bad box_index are left out (rid tail = -1).
-constexpr int kBinWarps = 32;
-
-__global__ void __launch_bounds__(1024) roi_bin_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ box_index,
-                                                       int N, int B, LevelRule rule, int32_t* __restrict__ rid,
-                                                       int32_t* __restrict__ offsets, int* err) {
-    extern __shared__ __align__(16) unsigned char bin_smem[];
-    const int K = 4 * B;
-    int* hist = reinterpret_cast<int*>(bin_smem);                 // [K][32]
-    uint32_t* packed = reinterpret_cast<uint32_t*>(hist + (size_t)K * kBinWarps);  // [N] key << 16 | rank in (key, warp)
-    __shared__ int s_warp_tot[kBinWarps];
-    const int tid = threadIdx.x, warp = tid >> 5, wl = tid & 31;
-    for (int i = tid; i < K * kBinWarps; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-
-    const int chunk = ((N + kBinWarps - 1) / kBinWarps + 31) & ~31;
-    const int nbeg = warp * chunk, nend = min(N, nbeg + chunk);
-    for (int n0 = nbeg; n0 < nend; n0 += 32) {
-        const int n = n0 + wl;
-        int k = -1;
-        if (n < nend) {
-            const float y1 = __ldg(boxes + 4 * n), x1 = __ldg(boxes + 4 * n + 1);
-            const float y2 = __ldg(boxes + 4 * n + 2), x2 = __ldg(boxes + 4 * n + 3);
-            const int bi = box_index ? __ldg(box_index + n) : 0;
-            if ((unsigned)bi < (unsigned)B) k = bi * 4 + roi_level(y1, x1, y2, x2, rule) - 2;
-            else atomicOr(err, 1);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, k);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (k >= 0 && wl == leader) {
-            base = hist[k * kBinWarps + warp];
-            hist[k * kBinWarps + warp] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (n < nend) packed[n] = (k >= 0) ? (((uint32_t)k << 16) | (uint32_t)(base + __popc(peers & ((1u << wl) - 1u)))) : 0xffffffffu;
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // exclusive scan of hist in (key, warp) order
-    const int E = K * kBinWarps;
-    const int per = (E + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int ebeg = min(E, tid * per), eend = min(E, ebeg + per);
-    int local = 0;
-    for (int e = ebeg; e < eend; ++e) local += hist[e];
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (wl >= o) incl += u;
-    }
-    if (wl == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int v = s_warp_tot[wl];
-        int inc2 = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc2, o);
-            if (wl >= o) inc2 += u;
-        }
-        s_warp_tot[wl] = inc2 - v;
-    }
-    __syncthreads();
-    int run = s_warp_tot[warp] + incl - local;
-    for (int e = ebeg; e < eend; ++e) {
-        const int v = hist[e];
-        hist[e] = run;
-        run += v;
-    }
-    __syncthreads();
-    const int total = s_warp_tot[kBinWarps - 1] + __shfl_sync(0xffffffffu, incl, 31);  // valid only in the last warp
-    if (tid == blockDim.x - 1) offsets[K] = total;
-    for (int k = tid; k < K; k += blockDim.x) offsets[k] = hist[k * kBinWarps];
-    __shared__ int s_total;
-    if (tid == blockDim.x - 1) s_total = total;
-    __syncthreads();
-    for (int n = tid; n < N; n += blockDim.x) {
-        const uint32_t pk = packed[n];
-        if (pk != 0xffffffffu) rid[hist[(pk >> 16) * kBinWarps + n / chunk] + (int)(pk & 0xffffu)] = n;
-    }
-    for (int j = s_total + tid; j < N; j += blockDim.x) rid[j] = -1;
-}
-
-// pass 1b: one 128-thread CTA per sorted position: the ph + pw taps, the pixel footprint and the
-// affine sample-position model used to bound the bin search.
-__global__ void __launch_bounds__(128) roi_taps_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ rid,
-                                                       int N, int ph, int pw, LevelRule rule, PyrLevel l0, PyrLevel l1,
-                                                       PyrLevel l2, PyrLevel l3, int4* __restrict__ bbox,
-                                                       float4* __restrict__ rp, GTap* __restrict__ taps) {
-    __shared__ int s_min[2], s_max[2];
-    const int j = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int r = __ldg(rid + j);
-    if (tid < 2) {
-        s_min[tid] = INT_MAX;
-        s_max[tid] = INT_MIN;
-    }
-    __syncthreads();
-    GTap* out = taps + (size_t)j * (ph + pw);
-    if (r < 0) {
-        if (tid == 0) {
-            bbox[j] = make_int4(1, 0, 1, 0);
-            rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int b = tid; b < ph + pw; b += blockDim.x) out[b] = GTap{-(1 << 30), 0.f};
+template <bool kFill>
+__global__ void __launch_bounds__(256) bwd_items_kernel(const GatherParams p) {
+    const int ph = p.ph, pw = p.pw;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.N * ph * 2) return;
+    const int r = (int)(t & 1);
+    const int by = (int)((t >> 1) % ph);
+    const int n = (int)((t >> 1) / ph);
+    const float y1 = __ldg(p.boxes + 4 * n), x1 = __ldg(p.boxes + 4 * n + 1);
+    const float y2 = __ldg(p.boxes + 4 * n + 2), x2 = __ldg(p.boxes + 4 * n + 3);
+    const int bi = p.box_index ? __ldg(p.box_index + n) : 0;
+    if ((unsigned)bi >= (unsigned)p.B) {
+        if (!kFill && by == 0 && r == 0) atomicOr(p.err, 1);
         return;
     }
-    const float y1 = __ldg(boxes + 4 * r), x1 = __ldg(boxes + 4 * r + 1);
-    const float y2 = __ldg(boxes + 4 * r + 2), x2 = __ldg(boxes + 4 * r + 3);
-    const int l = roi_level(y1, x1, y2, x2, rule) - 2;
-    const PyrLevel L = (l == 0) ? l0 : (l == 1) ? l1 : (l == 2) ? l2 : l3;
-    for (int b = tid; b < ph + pw; b += blockDim.x) {
-        const bool is_row = b < ph;
-        const AxisTap t = is_row ? axis_tap(y1, y2, L.H, ph, b) : axis_tap(x1, x2, L.W, pw, b - ph);
-        GTap g;
-        g.lo = (t.lo >= 0) ? t.lo : -(1 << 30);
-        g.lerp = t.lerp;
-        out[b] = g;
-        if (t.lo >= 0) {
-            atomicMin(&s_min[is_row ? 0 : 1], t.lo);
-            atomicMax(&s_max[is_row ? 0 : 1], t.hi);
+    const int l = roi_level(y1, x1, y2, x2, p.rule) - 2;
+    const UnitGeom G = (l == 0) ? p.g[0] : (l == 1) ? p.g[1] : (l == 2) ? p.g[2] : p.g[3];
+    const AxisTap ty = axis_tap(y1, y2, G.H, ph, by);
+    if (ty.lo < 0) return;
+    if (r == 1 && ty.lerp == 0.0f) return;  // the ceil tap coincides with the floor tap (crop_cpu.cpp:254-260)
+    const int y = ty.lo + r;
+    const float wy = r ? ty.lerp : __fsub_rn(1.0f, ty.lerp);
+    const int row_unit = G.unit_base + (bi * G.H + y) * G.segs;
+    const int row_off = (n * ph * pw + by * pw) * p.C;
+
+    // walk the bin columns; consecutive bins that fall into the same unit are claimed with one atomic
+    int run_seg = -1, run_beg = 0, run_len = 0;
+    for (int bx = 0; bx <= pw; ++bx) {
+        AxisTap tx;
+        tx.lo = -1; tx.hi = -1; tx.lerp = 0.f;
+        if (bx < pw) tx = axis_tap(x1, x2, G.W, pw, bx);
+        const int seg = (tx.lo >= 0) ? (tx.lo >> 3) : -1;
+        if (seg != run_seg) {
+            if (run_seg >= 0) {
+                if (!kFill) {
+                    atomicAdd(p.cnt + row_unit + run_seg, run_len);
+                } else {
+                    int q = atomicAdd(p.pos + row_unit + run_seg, run_len);
+                    for (int b2 = run_beg; b2 < run_beg + run_len; ++b2) {
+                        const AxisTap u = axis_tap(x1, x2, G.W, pw, b2);
+                        const int j = u.lo & 7;
+                        QItem it;
+                        it.off = row_off + b2 * p.C;
+                        it.wa = wy * __fsub_rn(1.0f, u.lerp);
+                        it.wb = (j < 7) ? wy * u.lerp : 0.f;
+                        it.idx = j + 1;
+                        p.items[q++] = it;
+                    }
+                }
+            }
+            run_seg = seg;
+            run_beg = bx;
+            run_len = 0;
+        }
+        if (seg >= 0) {
+            ++run_len;
+            // the ceil column of a bin whose floor column is the last of its unit belongs to the next unit
+            if ((tx.lo & 7) == 7 && tx.lerp != 0.0f) {
+                if (!kFill) {
+                    atomicAdd(p.cnt + row_unit + seg + 1, 1);
+                } else {
+                    const int q = atomicAdd(p.pos + row_unit + seg + 1, 1);
+                    QItem it;
+                    it.off = row_off + bx * p.C;
+                    it.wa = 0.f;
+                    it.wb = wy * tx.lerp;
+                    it.idx = 0;
+                    p.items[q] = it;
+                }
+            }
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        bbox[j] = make_int4(s_min[0], s_max[0], s_min[1], s_max[1]);
-        // position of bin b along an axis ~ a1*(size-1) + b * ((a2-a1)*(size-1)/(crop-1))  (crop_cpu.cpp:52-60)
-        const float sy = (ph > 1) ? ((y2 - y1) * (float)(L.H - 1)) / (float)(ph - 1) : 0.f;
-        const float sx = (pw > 1) ? ((x2 - x1) * (float)(L.W - 1)) / (float)(pw - 1) : 0.f;
-        float4 q;
-        q.x = y1 * (float)(L.H - 1);
-        q.y = (ph > 1 && fabsf(sy) >= 0.01f) ? 1.0f / sy : 0.f;  // 0 => search all bins
-        q.z = x1 * (float)(L.W - 1);
-        q.w = (pw > 1 && fabsf(sx) >= 0.01f) ? 1.0f / sx : 0.f;
-        rp[j] = q;
+}
+
+__global__ void __launch_bounds__(256) bwd_alloc_kernel(const GatherParams p) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (u < p.units) ? p.cnt[u] : 0;
+    int incl = c;
+    const int wl = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (wl >= o) incl += v;
     }
+    unsigned int base = 0;
+    if (wl == 31 && incl > 0) base = atomicAdd(p.cursor, (unsigned int)incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (u < p.units) p.pos[u] = (int)base + incl - c;
 }
-
-// Candidate bins [b0, b1] whose sample can touch a pixel of [pix_lo, pix_hi] (position within 1 of it), with
-// slack; every candidate is verified exactly against its tap afterwards, so over-inclusion is harmless.
-__device__ __forceinline__ void bin_range(float p0, float inv, int pix_lo, int pix_hi, int nb, int& b0, int& b1) {
-    b0 = 0;
-    b1 = nb - 1;
-    if (inv != 0.f && inv == inv) {
-        const float u = ((float)(pix_lo - 1) - p0) * inv;
-        const float v = ((float)(pix_hi + 1) - p0) * inv;
-        const float lo = fminf(u, v) - 0.02f, hi = fmaxf(u, v) + 0.02f;
-        if (lo == lo && hi == hi) {
-            b0 = max(0, (int)ceilf(fmaxf(lo, -1.0f)));
-            b1 = min(nb - 1, (int)floorf(fminf(hi, (float)nb)));
-        }
-    }
-}
-
-__device__ __forceinline__ GTap ldg_tap(const GTap* q) {
-    const int2 v = __ldg(reinterpret_cast<const int2*>(q));
-    GTap t;
-    t.lo = v.x;
-    t.lerp = __int_as_float(v.y);
-    return t;
-}
-
-__device__ __forceinline__ float tap_weight(const GTap t, int pix) {
-    // crop_cpu.cpp:254-260: (1 - lerp) goes to the floor tap, lerp to the ceil tap
-    if (t.lo == pix) return __fsub_rn(1.0f, t.lerp);
-    if (t.lo + 1 == pix) return t.lerp;  // lerp == 0 when the ceil tap coincides with the floor tap
-    return 0.f;
-}
-
-// pass 2: one CTA per 8x8 tile of one (image, level) map.  256 threads = 8 warps; warp w owns tile ROW w, a lane
-// carries 4 NV channels of all 8 pixels of that row in registers, so a warp covers 128 NV channels and every
-// gradient load is a 512-byte contiguous warp access.  More channels take ceil(C / (128 NV)) passes.
-//
-// Work is enumerated from the RoI side, never searched from the pixel side:
-//   plan      (CTA, once per batch of <= 32 RoIs reaching the tile) stage the row taps and the column items
-//             {bin column offset, tile column, weights} and trim, per tile row, the range of bin rows whose taps
-//             land on it and, for the tile, the range of bin columns whose taps land in its 8 columns;
-//   generate  (warp, lane = RoI) expand (RoI, bin row, bin column) into a flat per-warp queue of work items
-//             {gradient offset, tile column, wy * (1 - xl), wy * xl}; a warp scan places the items in RoI order;
-//   consume   (warp) a branch-light pipelined loop: four items, four 128-bit loads in flight, then a warp-uniform
-//             switch on the tile column adds the bin into the one or two accumulators it touches (no dynamic
-//             register indexing, no wasted FMAs).
-constexpr int kOBatchMax = 32;   // RoIs per plan = lanes of the generating warp
-constexpr int kOQueue = 256;     // work items per warp queue; needs ph * pw <= kOQueue
-constexpr int kOMaxPool = 16;
-constexpr int kONoop = 9;
-
-struct __align__(16) ColItem {
-    int off;  // bin column * C (element offset inside a bin row)
-    int idx;  // floor column relative to the tile + 1, 0..8 (kONoop: no contribution)
-    float wa, wb;
-};
-
-struct __align__(16) QItem {
-    int off;  // element offset of the bin in grads (32-bit by eligibility)
-    int idx;  // as ColItem.idx
-    float wa, wb;
-};
 
 template <int NV>
 struct AccRow {
@@ -625,7 +527,7 @@ __device__ __forceinline__ void fma_px(float4 (&a)[NV], float w, const float4 (&
     }
 }
 
-// Adds one bin into the row accumulators: tile column idx - 1 gets wa, column idx gets wb.
+// Adds one bin into the unit's accumulators: pixel idx - 1 gets wa, pixel idx gets wb.
 template <int NV>
 __device__ __forceinline__ void owner_accumulate(AccRow<NV>& r, int idx, float wa, float wb, const float4 (&v)[NV]) {
     switch (idx) {
@@ -642,221 +544,127 @@ __device__ __forceinline__ void owner_accumulate(AccRow<NV>& r, int idx, float w
     }
 }
 
-// dynamic shared memory layout of the gather kernel
-struct GatherSmem {
-    QItem queue[kGThreads / 32][kOQueue + 4];
-    unsigned char taps[kOBatchMax * (kOMaxPool * (sizeof(GTap) + sizeof(ColItem)))];  // per RoI: row taps, column items
-    uint16_t hits[kBinMaxN];  // sorted positions of the RoIs that reach this tile, ascending
-    short2 rng[kOBatchMax][kGTile + 1];  // per RoI: bin-row range per tile row, then the bin-column range
-    int goff[kOBatchMax];                // rid * P2 * C
-    int wcnt[kGThreads / 32];
-};
+// One warp (= one CTA, so a finished unit frees its slot at once) per unit.  NV float4 per lane and pixel: a warp
+// covers 128 NV channels per pass.  The gradients of U items per stage are copied straight into shared memory with
+// cp.async (each lane copies and later reads back only its own 16-byte slots, so no cross-lane synchronisation is
+// needed on the data) and ST stages are kept in flight per warp without holding them in registers.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
-template <int POOL, int NV, bool kAccumulate>  // NV float4 per lane and pixel
-__global__ void __launch_bounds__(kGThreads, (NV == 1) ? 3 : 2) roialign_bwd_gather_kernel(const GatherParams p) {
-    extern __shared__ __align__(16) unsigned char gather_smem_raw[];
-    GatherSmem& S = *reinterpret_cast<GatherSmem*>(gather_smem_raw);
+template <int NV, int U, int ST, bool kAccumulate>
+__global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherParams p) {
+    __shared__ QItem s_items[32 + U];
+    __shared__ __align__(16) float4 s_data[ST][U][NV][32];
+    const int wl = threadIdx.x;
+    const int u = blockIdx.x;
 
-    const int ph = POOL ? POOL : p.ph;
-    const int pw = POOL ? POOL : p.pw;
-    const int P2 = ph * pw;
-    const int ntap = ph + pw;
-    const int row_bytes = kOMaxPool * (int)sizeof(GTap);
-    const int roi_bytes = kOMaxPool * (int)(sizeof(GTap) + sizeof(ColItem));
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int wl = tid & 31;
+    const int l = (u < p.g[2].unit_base) ? 3 : (u < p.g[1].unit_base) ? 2 : (u < p.g[0].unit_base) ? 1 : 0;
+    const UnitGeom G = (l == 0) ? p.g[0] : (l == 1) ? p.g[1] : (l == 2) ? p.g[2] : p.g[3];
+    const int local = u - G.unit_base;
+    const int rowid = local / G.segs;  // image * H + y
+    const int seg = local - rowid * G.segs;
+    const int C = p.C;
+    const int npx = min(kGTile, G.W - seg * kGTile);
+    float* out = G.ptr + ((size_t)rowid * G.W + seg * kGTile) * C;
 
-    // which tile: coarse levels first (their tiles collect the most RoIs), image-major inside a level
-    int b = blockIdx.x;
-    const int l = (b < p.blk_base[1]) ? 3 : (b < p.blk_base[2]) ? 2 : (b < p.blk_base[3]) ? 1 : 0;
-    b -= (l == 3) ? 0 : (l == 2) ? p.blk_base[1] : (l == 1) ? p.blk_base[2] : p.blk_base[3];
-    const PyrLevel L = (l == 0) ? p.lv[0] : (l == 1) ? p.lv[1] : (l == 2) ? p.lv[2] : p.lv[3];
-    const int ntx = (l == 0) ? p.tiles_x[0] : (l == 1) ? p.tiles_x[1] : (l == 2) ? p.tiles_x[2] : p.tiles_x[3];
-    const int tiles_l = (l == 0) ? p.tiles_n[0] : (l == 1) ? p.tiles_n[1] : (l == 2) ? p.tiles_n[2] : p.tiles_n[3];
-    const int img = b / tiles_l;
-    const int t = b - img * tiles_l;
-    const int tyi = t / ntx;
-    const int ty0 = tyi * kGTile;
-    const int tx0 = (t - tyi * ntx) * kGTile;
-    const int H = L.H, W = L.W, C = p.C;
-
-    const int lbeg = __ldg(p.offsets + img * 4 + l);
-    const int lend = __ldg(p.offsets + img * 4 + l + 1);
-
-    // ---- cull: which RoIs of this (image, level) reach the tile?  Ordered compaction keeps the ascending
-    //      RoI index, i.e. a fixed summation order. ----
-    int nh = 0;
-    for (int next = lbeg; next < lend; next += kGThreads) {
-        const int j = next + tid;
-        bool hit = false;
-        if (j < lend) {
-            const int4 bb = __ldg(p.bbox + j);
-            hit = bb.y >= ty0 && bb.x <= ty0 + kGTile - 1 && bb.w >= tx0 && bb.z <= tx0 + kGTile - 1;
+    const int n = __ldg(p.cnt + u);
+    if (n == 0) {  // nothing reaches this unit: it is all zeros
+        if (!kAccumulate) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 4 * wl; i < npx * C; i += 128) stg_f4_stream(out + i, z);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (wl == 0) S.wcnt[warp] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kGThreads / 32; ++w) {
-            const int v = S.wcnt[w];
-            if (w < warp) before += v;
-            total += v;
-        }
-        if (hit) S.hits[nh + before + __popc(m & ((1u << wl) - 1u))] = (uint16_t)j;
-        nh += total;
-        __syncthreads();
+        return;
+    }
+    const QItem* items = p.items + (__ldg(p.pos + u) - n);
+    if (wl < U) {  // permanent no-op padding behind the 32 staged items
+        QItem z;
+        z.off = 0; z.wa = 0.f; z.wb = 0.f; z.idx = kONoop;
+        s_items[32 + wl] = z;
     }
 
-    const int y = ty0 + warp;  // this warp's feature-map row
-    const bool replan = nh > kOBatchMax;
-    bool planned = false;
-    QItem* queue = S.queue[warp];
     for (int cbase = 0; cbase < C; cbase += 128 * NV) {
-        // lane wl owns channels cbase + 4 wl + 128 k, k < NV: each k is one 512-byte warp access
         const int c = cbase + 4 * wl;
+        const bool live = c < C;
         AccRow<NV> acc;
 #pragma unroll
         for (int j = 0; j < kGTile; ++j)
 #pragma unroll
             for (int k = 0; k < NV; ++k) acc.a[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool live[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) live[k] = (c + 128 * k) < C;
-        const float* gbase = p.grads + (live[0] ? c : 0);
-        const bool row_ok = y < H && cbase < C;  // warp-uniform
+        const float* gbase = p.grads + (live ? c : 0);
 
-        for (int h0 = 0; h0 < nh; h0 += kOBatchMax) {
-            const int nb = min(kOBatchMax, nh - h0);
-            if (replan || !planned) {
-                // ---- plan ----
-                if (planned) __syncthreads();  // everyone is done with the previous plan
-                for (int i = tid; i < nb * ntap; i += kGThreads) {
-                    const int h = i / ntap, bq = i - h * ntap;
-                    const GTap tp = ldg_tap(p.taps + (size_t)S.hits[h0 + h] * ntap + bq);
-                    unsigned char* base = S.taps + h * roi_bytes;
-                    if (bq < ph) {
-                        reinterpret_cast<GTap*>(base)[bq] = tp;
-                    } else {
-                        ColItem it;
-                        const int j0 = tp.lo - tx0;
-                        it.off = (bq - ph) * C;
-                        it.idx = ((unsigned)(j0 + 1) <= (unsigned)kGTile) ? j0 + 1 : kONoop;
-                        it.wa = __fsub_rn(1.0f, tp.lerp);
-                        it.wb = tp.lerp;
-                        reinterpret_cast<ColItem*>(base + row_bytes)[bq - ph] = it;
-                    }
-                }
-                for (int i = tid; i < nb * (kGTile + 1); i += kGThreads) {
-                    const int h = i / (kGTile + 1), line = i - h * (kGTile + 1);
-                    const int j = S.hits[h0 + h];
-                    const int4 bb = __ldg(p.bbox + j);
-                    const float4 rp = __ldg(p.rp + j);
-                    const GTap* tp = p.taps + (size_t)j * ntap;
-                    int b0 = 1, b1 = 0;
-                    if (line < kGTile) {
-                        const int yy = ty0 + line;
-                        if (yy >= bb.x && yy <= bb.y) {
-                            bin_range(rp.x, rp.y, yy, yy, ph, b0, b1);
-                            while (b0 <= b1 && tap_weight(ldg_tap(tp + b0), yy) == 0.f) ++b0;
-                            while (b1 >= b0 && tap_weight(ldg_tap(tp + b1), yy) == 0.f) --b1;
-                        }
-                    } else {
-                        bin_range(rp.z, rp.w, tx0, tx0 + kGTile - 1, pw, b0, b1);
-                        // a column tap reaches the tile iff its floor column is in [tx0 - 1, tx0 + 7]
-                        while (b0 <= b1 && (unsigned)(ldg_tap(tp + ph + b0).lo - tx0 + 1) > (unsigned)kGTile) ++b0;
-                        while (b1 >= b0 && (unsigned)(ldg_tap(tp + ph + b1).lo - tx0 + 1) > (unsigned)kGTile) --b1;
-                        S.goff[h] = __ldg(p.rid + j) * P2 * C;
-                    }
-                    S.rng[h][line] = make_short2((short)b0, (short)b1);
-                }
-                __syncthreads();
-                planned = true;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            QItem mine;
+            mine.off = 0; mine.wa = 0.f; mine.wb = 0.f; mine.idx = kONoop;
+            if (i0 + wl < n) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(items + i0 + wl));
+                mine.off = raw.x; mine.wa = __int_as_float(raw.y); mine.wb = __int_as_float(raw.z); mine.idx = raw.w;
             }
-            if (!row_ok) continue;
-
-            // ---- generate + consume, in rounds of as many RoIs as fit the queue (RoIs in ascending index order) ----
-            int hdone = 0;
-            while (hdone < nb) {
-                const int h = hdone + wl;
-                short2 ry = make_short2(1, 0), rx = make_short2(1, 0);
-                if (h < nb) {
-                    ry = S.rng[h][warp];
-                    rx = S.rng[h][kGTile];
-                }
-                const int nby = max(0, ry.y - ry.x + 1), nbx = max(0, rx.y - rx.x + 1);
-                const int cnt = nby * nbx;
-                int incl = cnt;
+            __syncwarp();
+            s_items[wl] = mine;
+            __syncwarp();
+            const int m = min(32, n - i0);
+            const int ngroups = (m + U - 1) / U;
+            // prologue: ST - 1 stages in flight
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (wl >= o) incl += u;
-                }
-                // lanes whose items still fit; incl is non-decreasing, cnt <= kOQueue, so lane 0 always fits
-                const unsigned fit = __ballot_sync(0xffffffffu, incl <= kOQueue);
-                const int m = min(nb - hdone, __ffs(~fit) ? __ffs(~fit) - 1 : 32);
-                const int n = __shfl_sync(0xffffffffu, incl, m - 1);
-                if (wl < m && cnt > 0) {
-                    int pos = incl - cnt;
-                    const GTap* ty = reinterpret_cast<const GTap*>(S.taps + h * roi_bytes);
-                    const ColItem* cols = reinterpret_cast<const ColItem*>(S.taps + h * roi_bytes + row_bytes);
-                    const int goff = S.goff[h];
-                    for (int by = ry.x; by <= ry.y; ++by) {
-                        const float wy = tap_weight(ty[by], y);
-                        const int rowoff = goff + (by * pw) * C;
-                        for (int bx = rx.x; bx <= rx.y; ++bx) {
-                            const ColItem ci = cols[bx];
-                            QItem q;
-                            q.off = rowoff + ci.off;
-                            q.idx = (wy != 0.f) ? ci.idx : kONoop;
-                            q.wa = wy * ci.wa;
-                            q.wb = wy * ci.wb;
-                            queue[pos++] = q;
-                        }
+            for (int sgi = 0; sgi < ST - 1; ++sgi) {
+                if (sgi < ngroups) {
+#pragma unroll
+                    for (int e = 0; e < U; ++e) {
+                        const int off = s_items[sgi * U + e].off;
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[sgi][e][k][wl], gbase + off + 128 * k);
                     }
                 }
-                if (wl < 4) {  // pad to a multiple of four with no-ops (offset 0 is a valid address)
-                    QItem q;
-                    q.off = 0; q.idx = kONoop; q.wa = 0.f; q.wb = 0.f;
-                    queue[n + wl] = q;
-                }
-                __syncwarp();
+                cp_async_commit();
+            }
 #pragma unroll 1
-                for (int i = 0; i < n; i += 4) {
-                    QItem it[4];
+            for (int gi = 0; gi < ngroups; ++gi) {
+                const int nxt = gi + ST - 1;
+                if (nxt < ngroups) {
+                    const int st = nxt % ST;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) it[u] = queue[i + u];
-                    float4 v[4][NV];
+                    for (int e = 0; e < U; ++e) {
+                        const int off = s_items[nxt * U + e].off;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int k = 0; k < NV; ++k)
-                            v[u][k] = live[k] ? ldg_f4(gbase + it[u].off + 128 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) owner_accumulate<NV>(acc, it[u].idx, it[u].wa, it[u].wb, v[u]);
+                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[st][e][k][wl], gbase + off + 128 * k);
+                    }
                 }
-                __syncwarp();
-                hdone += m;
+                cp_async_commit();
+                cp_async_wait<ST - 1>();
+                const int st = gi % ST;
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    const QItem it = s_items[gi * U + e];
+                    float4 v[NV];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) v[k] = s_data[st][e][k][wl];
+                    owner_accumulate<NV>(acc, it.idx, it.wa, it.wb, v);
+                }
             }
+            cp_async_wait<0>();
         }
 
-        // ---- every pixel of the tile is written exactly once ----
-        if (row_ok) {
-            float* o = L.ptr + (((size_t)img * H + y) * W + tx0) * C + c;
+        if (live) {
+            float* o = out + c;
 #pragma unroll
             for (int j = 0; j < kGTile; ++j) {
-                if (tx0 + j < W) {
+                if (j < npx) {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        if (!live[k]) continue;
                         float4 a = acc.a[j][k];
-                        float* q = o + j * C + 128 * k;
+                        float* dst = o + j * C + 128 * k;
                         if (kAccumulate) {
-                            const float4 o0 = *reinterpret_cast<const float4*>(q);
+                            const float4 o0 = *reinterpret_cast<const float4*>(dst);
                             a.x += o0.x; a.y += o0.y; a.z += o0.z; a.w += o0.w;
                         }
-                        stg_f4_stream(q, a);
+                        stg_f4_stream(dst, a);
                     }
                 }
             }
@@ -1079,40 +887,49 @@ static int launch_zero(float* const ptr[4], const size_t elems[4], int nbuf, cud
 }
 
 struct GatherWorkspace {
-    int32_t* rid;
-    int4* bbox;
-    float4* rp;
-    GTap* taps;
-    int32_t* offsets;
+    int* cnt;
+    int* pos;
+    unsigned int* cursor;
+    QItem* items;
+    size_t clear_bytes;  // cnt + cursor are cleared before every call (they are adjacent)
     size_t bytes;
 };
 
-static GatherWorkspace carve_gather(void* base, int B, int N, int pool) {
+static long long gather_units(const int H[4], const int W[4], int B) {
+    long long units = 0;
+    for (int l = 0; l < 4; ++l) units += (long long)B * H[l] * ((W[l] + kGTile - 1) / kGTile);
+    return units;
+}
+
+static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], int B, int N, int pool) {
     GatherWorkspace w;
-    const size_t n = (size_t)(N > 0 ? N : 1);
+    const size_t units = (size_t)gather_units(H, W, B);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         void* q = base ? (void*)((char*)base + off) : nullptr;
         off += align_up(bytes, 256);
         return q;
     };
-    w.rid = (int32_t*)take(n * 4);
-    w.bbox = (int4*)take(n * 16);
-    w.rp = (float4*)take(n * 16);
-    w.taps = (GTap*)take(n * 2 * (size_t)pool * sizeof(GTap));
-    w.offsets = (int32_t*)take((size_t)(4 * (size_t)B + 1) * 4);
+    w.cursor = (unsigned int*)take(4);
+    w.cnt = (int*)take(units * 4);
+    w.clear_bytes = off;
+    w.pos = (int*)take(units * 4);
+    // every bin yields at most four work items (two rows x a unit boundary)
+    w.items = (QItem*)take((size_t)4 * (size_t)(N > 0 ? N : 1) * pool * pool * sizeof(QItem));
     w.bytes = off;
     return w;
 }
 
 // true if the gather backward can serve this call
-static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int grads_layout, const float* grads,
-                            float* const gfm[4], const void* workspace, size_t workspace_bytes) {
+static bool gather_eligible(const int H[4], const int W[4], int B, int C, int N, int pool, int gfm_layout, int grads_layout,
+                            const float* grads, float* const gfm[4], const void* workspace, size_t workspace_bytes) {
     if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
-    if ((C % 4) != 0 || pool > kOMaxPool || N > kBinMaxN || N <= 0) return false;
-    if ((long long)N * pool * pool * C >= (1ll << 31)) return false;  // 32-bit element offsets into grads
-    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, B, N, pool).bytes) return false;
-    if ((size_t)4 * B * kBinWarps * 4 + (size_t)N * 4 > kBinSmemMax || 4 * (long long)B >= 65536) return false;
+    if ((C % 4) != 0 || N <= 0) return false;
+    if ((long long)N * pool * pool * C >= (1ll << 31)) return false;      // 32-bit element offsets into grads
+    if ((long long)4 * N * pool * pool >= (1ll << 31)) return false;      // 32-bit item positions
+    if (gather_units(H, W, B) >= (1ll << 31) - 8) return false;
+    if ((long long)N * pool * 2 >= (1ll << 31) * 256) return false;
+    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, H, W, B, N, pool).bytes) return false;
     if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
     for (int l = 0; l < 4; ++l)
         if (!aligned16(gfm[l])) return false;
@@ -1122,49 +939,41 @@ static bool gather_eligible(int B, int C, int N, int pool, int gfm_layout, int g
 static int launch_bwd_gather(const float* grads, const int H[4], const int W[4], int B, int C, const float* boxes,
                              const int32_t* box_index, int N, int pool, float image_area, float* const gfm[4],
                              int accumulate, void* workspace, cudaStream_t stream) {
-    const GatherWorkspace ws = carve_gather(workspace, B, N, pool);
-    const LevelRule rule = make_level_rule(image_area);
-    const size_t bin_smem = (size_t)4 * B * kBinWarps * 4 + (size_t)N * 4;
-    MRCNN_CUDA(cudaFuncSetAttribute(roi_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemMax));
-    roi_bin_kernel<<<1, 1024, bin_smem, stream>>>(boxes, box_index, N, B, rule, ws.rid, ws.offsets, device_error_word());
-    MRCNN_LAUNCH_CHECK();
+    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, pool);
     GatherParams g = {};
-    long long total = 0;
-    for (int l = 0; l < 4; ++l) {
-        g.lv[l] = {gfm[l], H[l], W[l]};
-        g.tiles_x[l] = (W[l] + kGTile - 1) / kGTile;
-        g.tiles_n[l] = g.tiles_x[l] * ((H[l] + kGTile - 1) / kGTile);
-        total += (long long)g.tiles_n[l] * B;
+    int base = 0;
+    for (int l = 3; l >= 0; --l) {  // coarse levels first: their units collect the most work
+        g.g[l].ptr = gfm[l];
+        g.g[l].H = H[l];
+        g.g[l].W = W[l];
+        g.g[l].segs = (W[l] + kGTile - 1) / kGTile;
+        g.g[l].unit_base = base;
+        base += B * H[l] * g.g[l].segs;
     }
-    MRCNN_REQUIRE(total < (1ll << 31), "mrcnn_pyramid_roi_align_backward: too many tiles");
-    g.blk_base[0] = 0;  // groups: level 3, 2, 1, 0
-    for (int i = 1; i < 4; ++i) g.blk_base[i] = g.blk_base[i - 1] + g.tiles_n[4 - i] * B;
-    roi_taps_kernel<<<N, 128, 0, stream>>>(boxes, ws.rid, N, pool, pool, rule, g.lv[0], g.lv[1], g.lv[2], g.lv[3], ws.bbox,
-                                          ws.rp, ws.taps);
-    MRCNN_LAUNCH_CHECK();
+    g.units = base;
+    g.rule = make_level_rule(image_area);
     g.B = B; g.C = C; g.N = N;
     g.ph = pool; g.pw = pool;
-    g.grads = grads; g.rid = ws.rid; g.bbox = ws.bbox; g.rp = ws.rp; g.taps = ws.taps; g.offsets = ws.offsets;
-    const unsigned grid = (unsigned)total;
-    const bool wide = C > 128;  // 8 channels per lane: one pass covers 256 channels
-    const size_t smem = sizeof(GatherSmem);
-#define MRCNN_LAUNCH_GATHER_K(KERNEL)                                                                       \
-    do {                                                                                                    \
-        MRCNN_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        KERNEL<<<grid, kGThreads, smem, stream>>>(g);                                                       \
-    } while (0)
-#define MRCNN_LAUNCH_GATHER(POOL)                                                                           \
-    do {                                                                                                    \
-        if (wide && accumulate) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 2, true>));         \
-        else if (wide) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 2, false>));                 \
-        else if (accumulate) MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 1, true>));            \
-        else MRCNN_LAUNCH_GATHER_K((roialign_bwd_gather_kernel<POOL, 1, false>));                           \
-    } while (0)
-    if (pool == 7) MRCNN_LAUNCH_GATHER(7);
-    else if (pool == 14) MRCNN_LAUNCH_GATHER(14);
-    else MRCNN_LAUNCH_GATHER(0);
-#undef MRCNN_LAUNCH_GATHER_K
-#undef MRCNN_LAUNCH_GATHER
+    g.boxes = boxes; g.box_index = box_index; g.grads = grads;
+    g.cnt = ws.cnt; g.pos = ws.pos; g.cursor = ws.cursor; g.items = ws.items;
+    g.err = device_error_word();
+    MRCNN_CUDA(cudaMemsetAsync(workspace, 0, ws.clear_bytes, stream));
+    const long long walkers = (long long)N * pool * 2;
+    const unsigned wgrid = (unsigned)((walkers + 255) / 256);
+    const unsigned ugrid = (unsigned)((g.units + 255) / 256);
+    bwd_items_kernel<false><<<wgrid, 256, 0, stream>>>(g);
+    MRCNN_LAUNCH_CHECK();
+    bwd_alloc_kernel<<<ugrid, 256, 0, stream>>>(g);
+    MRCNN_LAUNCH_CHECK();
+    bwd_items_kernel<true><<<wgrid, 256, 0, stream>>>(g);
+    MRCNN_LAUNCH_CHECK();
+    const bool wide = (C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
+    const unsigned grid = (unsigned)g.units;
+    // U = 2 items per stage, ST = 4 stages: best of the (U, ST) grid measured on B200 (profiles/r01_*gather*)
+    if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true><<<grid, 32, 0, stream>>>(g);
+    else if (wide) roialign_bwd_gather_kernel<2, 2, 4, false><<<grid, 32, 0, stream>>>(g);
+    else if (accumulate) roialign_bwd_gather_kernel<1, 2, 4, true><<<grid, 32, 0, stream>>>(g);
+    else roialign_bwd_gather_kernel<1, 2, 4, false><<<grid, 32, 0, stream>>>(g);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }
@@ -1180,9 +989,11 @@ using namespace mrcnn;
 
 extern "C" {
 
-size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(int B, int N, int pool) {
-    if (B <= 0 || N < 0 || pool <= 0) return 256;
-    return carve_gather(nullptr, B, N, pool).bytes;
+size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const int W[4], int B, int N, int pool) {
+    if (!H || !W || B <= 0 || N < 0 || pool <= 0) return 256;
+    for (int l = 0; l < 4; ++l)
+        if (H[l] <= 0 || W[l] <= 0) return 256;
+    return carve_gather(nullptr, H, W, B, N, pool).bytes;
 }
 
 int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout, const float* boxes,
@@ -1299,13 +1110,13 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
     MRCNN_REQUIRE(algo == MRCNN_BWD_AUTO || algo == MRCNN_BWD_GATHER || algo == MRCNN_BWD_SCATTER,
                   "mrcnn_pyramid_roi_align_backward: unknown algo %d", algo);
     const bool can_gather = image_offsets_host == nullptr &&
-                            gather_eligible(B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
+                            gather_eligible(H, W, B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
     if (algo == MRCNN_BWD_GATHER)
         MRCNN_REQUIRE(can_gather,
                       "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs channels-last grads and gfm, C %% 4 == 0, "
-                      "0 < N <= %d, no image_offsets_host and a 256-byte aligned workspace of "
-                      "mrcnn_pyramid_roi_align_backward_workspace_bytes()", kBinMaxN);
-    if (can_gather && algo == MRCNN_BWD_GATHER) {
+                      "N > 0, N * pool^2 * C < 2^31, no image_offsets_host and a 256-byte aligned workspace of "
+                      "mrcnn_pyramid_roi_align_backward_workspace_bytes()");
+    if (can_gather && algo != MRCNN_BWD_SCATTER) {
         // tile-owner gather: writes every pixel once (zero fill included), no atomics
         return launch_bwd_gather(grads, H, W, B, C, boxes, box_index, N, pool, image_area, gfm, zero_fill ? 0 : 1, workspace,
                                  stream);

@@ -19,19 +19,20 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "check_device_errors", "set_deterministic_backward"]
+           "rpn_refine", "detection_layer", "mrn_refine", "check_device_errors", "set_backward_algorithm"]
 
 
-# Backward of the channels-last PyramidROIAlign.  None (default) = MRCNN_BWD_AUTO: the library picks the faster
-# algorithm for the call.  True = the tile-owner gather where eligible (no atomics, every gradient pixel written
-# once, bit-reproducible); False = always the scatter (clear + column-aggregated vector reductions; fp32 atomics
-# -> last-bit run-to-run differences).
-DETERMINISTIC_BACKWARD = None
+# Backward of the channels-last PyramidROIAlign: "auto" (MRCNN_BWD_AUTO: the row-owner gather whenever the call is
+# eligible, else the scatter), "gather" (insist on the gather where eligible: no atomics on gradient data, no
+# zero-fill pass, every gradient pixel written once) or "scatter" (clear + column-aggregated vector reductions).
+BACKWARD_ALGORITHM = "auto"
 
 
-def set_deterministic_backward(flag):
-    global DETERMINISTIC_BACKWARD
-    DETERMINISTIC_BACKWARD = None if flag is None else bool(flag)
+def set_backward_algorithm(name):
+    global BACKWARD_ALGORITHM
+    if name not in ("auto", "gather", "scatter"):
+        raise ValueError("backward algorithm must be 'auto', 'gather' or 'scatter'")
+    BACKWARD_ALGORITHM = name
 
 
 def _stream():
@@ -214,13 +215,13 @@ class _PyramidRoiAlign(torch.autograd.Function):
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
         with torch.cuda.device(grad.device):
-            ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(B, N, pool)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
-            gather_ok = fl == NHWC and gl == NHWC and C % 4 == 0 and 0 < N <= 8192 and not offsets
-            if DETERMINISTIC_BACKWARD is None:
-                algo = _lib.BWD_AUTO
-            else:
-                algo = _lib.BWD_GATHER if (DETERMINISTIC_BACKWARD and gather_ok) else _lib.BWD_SCATTER
+            gather_ok = fl == NHWC and gl == NHWC and C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets
+            algo = {"auto": _lib.BWD_AUTO, "gather": _lib.BWD_GATHER if gather_ok else _lib.BWD_SCATTER,
+                    "scatter": _lib.BWD_SCATTER}[BACKWARD_ALGORITHM]
+            ws_bytes, ws = 0, None
+            if gather_ok and algo != _lib.BWD_SCATTER:
+                ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(_lib.i4(Hs), _lib.i4(Ws), B, N, pool)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,
                                                        _lib.vp4([g.data_ptr() for g in gfm]), fl, 1,

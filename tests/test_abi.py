@@ -33,7 +33,9 @@ def test_abi_version_and_workspace_queries():
     assert L.mrcnn_proposal_workspace_bytes(8, 261888, 6000) >= 8 * 6016 * 94 * 8
     assert L.mrcnn_detection_workspace_bytes(64, 1000) == 256          # mask lives in shared memory up to 1024 RoIs
     assert L.mrcnn_detection_workspace_bytes(2, 2000) >= 2 * 2048 * 32 * 8
-    assert L.mrcnn_pyramid_roi_align_backward_workspace_bytes(16, 8192, 14) >= 8192 * (4 + 16 + 16 + 28 * 8)
+    hw = _lib.i4([256, 128, 64, 32])
+    units = 16 * (256 * 32 + 128 * 16 + 64 * 8 + 32 * 4)
+    assert L.mrcnn_pyramid_roi_align_backward_workspace_bytes(hw, hw, 16, 8192, 14) >= 8 * units + 4 * 8192 * 196 * 16
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

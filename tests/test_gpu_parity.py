@@ -356,14 +356,14 @@ def test_pyramid_grouped_by_image_backward(ops, pool, out_cl):
         assert rel_err(t.grad.cpu().numpy(), w) <= BWD_TOL
 
 
-@pytest.mark.parametrize("mode", [True, None, False])
+@pytest.mark.parametrize("mode", ["gather", "auto", "scatter"])
 @pytest.mark.parametrize("pool", [7, 14, 5, 1])
 @pytest.mark.parametrize("B,C,size,N", [(3, 128, 256, 150), (2, 320, 200, 90), (1, 40, 512, 300), (4, 256, 160, 64)])
 def test_pyramid_backward_gather(ops, pool, B, C, size, N, mode):
-    """Channels-last upstream gradient + channels-last pyramid -> the tile-owner gather backward
-    (no atomics; mode True), MRCNN_BWD_AUTO (None) or the scatter (mode False).
-    Level maps whose sides are not multiples of the 8-pixel tile, C > 128 (several channel passes),
-    inverted / out-of-image boxes, and run-to-run bit reproducibility of the gather."""
+    """Channels-last upstream gradient + channels-last pyramid -> the row-owner gather backward
+    (no atomics on gradient data), MRCNN_BWD_AUTO or the scatter.
+    Level maps whose sides are not multiples of the 8-pixel unit, C not a multiple of 128 / 256 (partial and
+    several channel passes), inverted / out-of-image boxes."""
     fms = synth.feature_pyramid(B, C, 21 + B, image=size)
     boxes = synth.random_rois(N, 22 + N, image=float(size), min_size=6, max_size=size * 0.9)
     boxes[0] += 0.4                       # partly outside
@@ -375,17 +375,16 @@ def test_pyramid_backward_gather(ops, pool, B, C, size, N, mode):
     g = np.random.default_rng(8).standard_normal(want.shape, dtype=np.float32)
     want_g = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, ind, float(size * size))
     grads = []
-    ops.set_deterministic_backward(mode)
+    ops.set_backward_algorithm(mode)
     for rep in range(2):
         ts = [cl(dev(f)).requires_grad_(True) for f in fms]
         out = ops.pyramid_roi_align(ts, dev(boxes), dev(ind), pool, (size, size, 3), out_channels_last=True)
         np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
         out.backward(cl(dev(g)))
         grads.append([t.grad.cpu().numpy() for t in ts])
-    ops.set_deterministic_backward(None)
+    ops.set_backward_algorithm("auto")
     for a, w in zip(grads[0], want_g):
         assert rel_err(a, w) <= BWD_TOL
-    if mode is True:
-        for a, b in zip(grads[0], grads[1]):
-            np.testing.assert_array_equal(a, b)      # deterministic: no atomics, fixed summation order
+    for a, b in zip(grads[0], grads[1]):             # run to run: same sums up to fp32 association order
+        assert rel_err(a, b) <= BWD_TOL
     ops.check_device_errors()

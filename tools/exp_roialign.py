@@ -13,7 +13,7 @@ wl.g7n, wl.g14n = wl.g7.contiguous(), wl.g14.contiguous()
 o7n, o14n = wl.out7.contiguous(), wl.out14.contiguous()
 
 
-ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, 14), dtype=torch.uint8, device="cuda")
+ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.Hs, wl.Ws, wl.batch, wl.N, 14), dtype=torch.uint8, device="cuda")
 
 
 def bwd(pool, g, gl, gfm, offs, gather=False, ft=False):
@@ -42,6 +42,9 @@ cases = {
     "bwd7  nhwc GATHER": lambda: bwd(7, g7c, L.NHWC, wl.gfm7, None, True), "bwd14 nhwc GATHER": lambda: bwd(14, g14c, L.NHWC, wl.gfm14, None, True),
     "torch zero_ of one pyramid": zero_only,
 }
+only = sys.argv[1].upper() if len(sys.argv) > 1 else None
 for name, fn in cases.items():
+    if only and only not in name:
+        continue
     t = wl.time_op(fn, iters=20)
     print("%-28s %8.1f us" % (name, t * 1e6))

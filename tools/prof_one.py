@@ -16,7 +16,7 @@ buf = {7: (wl.out7, wl.g7, wl.gfm7), 14: (wl.out14, wl.g14, wl.gfm14)}[pool]
 o, g, gf = buf
 if lay == "nhwc":
     o, g = o.contiguous(memory_format=cl), g.contiguous(memory_format=cl)
-ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.batch, wl.N, pool), dtype=torch.uint8, device="cuda")
+ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.Hs, wl.Ws, wl.batch, wl.N, pool), dtype=torch.uint8, device="cuda")
 for _ in range(3):
     if kind == "fwd":
         L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, bench.CHANNELS, L.NHWC,
