@@ -448,6 +448,20 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of each timed op, from the newest committed ncu summary (profiles/rNN_traffic.json):
+    {capture name: MB summed over the kernels the op launches}."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_traffic.json")))
+    if not files:
+        return {}
+    out = {}
+    for key, rec in json.load(open(files[-1])).items():
+        cap = key.split(":", 1)[0]
+        out[cap] = out.get(cap, 0.0) + rec["dram_bytes"] / 1e6
+    return out
+
+
 def workload_config():
     return {"workload": "BASELINE configs[3]: training-mode PyramidROIAlign fwd+bwd, batch %d x %d RoIs x %d ch, P2-P5 of %dx%d, "
                         "7x7 + 14x14 + %d 28x28 mask-target crops/img" % (BATCH, ROIS_PER_IMAGE, CHANNELS, IMAGE, IMAGE, MASK_POS),
@@ -623,16 +637,23 @@ def main():
             "bwd_items x2+bwd_alloc+roialign_bwd_gather_kernel<14,nhwc>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
         }
+        captures = dict(zip(ops, ("fwd7_nhwc", "fwd14_nhwc", "bwd7_nhwc", "bwd14_nhwc", None)))
+        traffic = ncu_traffic()
         kern = {}
         for name, (fn, by) in ops.items():
             t = wl.time_op(fn)
-            kern[name] = {"ms": t * 1e3, "algorithmic_MB": by / 1e6, "GBps": by / t / 1e9, "frac": by / t / 1e9 / hbm}
+            kern[name] = {"ms": t * 1e3, "algorithmic_MB": by / 1e6, "GBps": by / t / 1e9, "frac": by / t / 1e9 / hbm,
+                          "ncu_dram_MB": traffic.get(captures[name])}
         total = sum(k["ms"] for k in kern.values())
         for k in kern.values():
             k["share_of_step"] = k["ms"] / total
         top = max(kern, key=lambda n: kern[n]["ms"])
         line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": kern[top]["GBps"], "peak": hbm, "unit": "GB/s",
-                            "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
+                            "frac": kern[top]["frac"],
+                            "traffic": (kern[top]["ncu_dram_MB"] * 1e6 if kern[top]["ncu_dram_MB"] else None),
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the op's kernels, one launch each, "
+                                              "ncu --set full captures summarised in profiles/*_traffic.json",
+                            "peak_source": peak_src,
                             "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
                             "kernels": kern}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)

@@ -55,6 +55,50 @@ __device__ __forceinline__ float bilerp(float tl, float tr, float bl, float br, 
     return __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
 }
 
+// The same blend for four channels at once with Blackwell's packed fp32x2 pipe (FADD2 / FFMA2, sm_100+): half the
+// FP instructions, and still ONE rounding per reference operation.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 (unlike the scalar .rn forms), so the product is written as fma(a, b, nz) with nz = -0.0f read from
+// a kernel parameter - exact (x*y + -0 == RN(x*y), sign of zero included) and opaque to the contraction.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsigned long long b, unsigned long long nz) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+__device__ __forceinline__ unsigned long long lerp2(unsigned long long a, unsigned long long b, unsigned long long t,
+                                                    unsigned long long nz) {
+    return add2_rn(a, mul2_rn(sub2_rn(b, a), t, nz));  // a + (b - a) * t, three roundings
+}
+__device__ __forceinline__ float4 bilerp4(const float4 tl, const float4 tr, const float4 bl, const float4 br, float xl,
+                                          float yl, float negzero) {
+    const unsigned long long nz = pack2(negzero, negzero), x2 = pack2(xl, xl), y2 = pack2(yl, yl);
+    const unsigned long long top_lo = lerp2(pack2(tl.x, tl.y), pack2(tr.x, tr.y), x2, nz);
+    const unsigned long long top_hi = lerp2(pack2(tl.z, tl.w), pack2(tr.z, tr.w), x2, nz);
+    const unsigned long long bot_lo = lerp2(pack2(bl.x, bl.y), pack2(br.x, br.y), x2, nz);
+    const unsigned long long bot_hi = lerp2(pack2(bl.z, bl.w), pack2(br.z, br.w), x2, nz);
+    float4 v;
+    unpack2(lerp2(top_lo, bot_lo, y2, nz), v.x, v.y);
+    unpack2(lerp2(top_hi, bot_hi, y2, nz), v.z, v.w);
+    return v;
+}
+
 // FPN level thresholds (see host side, roialign.cu: level_thresholds()).  level(q) for
 // q = sqrt(h*w) / (224/sqrt(image_area)) is 2 + [q>=t3] + [q>=t4] + [q>=t5]: the exact step
 // function of clamp(round_half_even(4 + log2(q)), 2, 5) (model.py:331-338) with correctly rounded log2.

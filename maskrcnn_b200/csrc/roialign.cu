@@ -40,6 +40,7 @@ struct RoiParams {
     int ph, pw;
     float extrap;
     float* crops;  // forward: output; backward: incoming gradient (read-only)
+    float negzero;  // -0.0f, opaque to ptxas (see bilerp4)
     int32_t* levels_out;
     int* err;
 };
@@ -228,10 +229,7 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
                 if (b >= P2) continue;
                 float4 v;
                 if (inside[u]) {
-                    v.x = bilerp(tl[u].x, tr[u].x, bl[u].x, br[u].x, xl[u], yl[u]);
-                    v.y = bilerp(tl[u].y, tr[u].y, bl[u].y, br[u].y, xl[u], yl[u]);
-                    v.z = bilerp(tl[u].z, tr[u].z, bl[u].z, br[u].z, xl[u], yl[u]);
-                    v.w = bilerp(tl[u].w, tr[u].w, bl[u].w, br[u].w, xl[u], yl[u]);
+                    v = bilerp4(tl[u], tr[u], bl[u], br[u], xl[u], yl[u], p.negzero);
                 } else {
                     v = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
                 }
@@ -816,8 +814,10 @@ static LevelRule make_level_rule(float image_area) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int launch_roi(const RoiParams& p, int image_layout, int crops_layout, bool backward, cudaStream_t stream) {
-    if (p.N == 0) return MRCNN_OK;
+static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout, bool backward, cudaStream_t stream) {
+    if (p_in.N == 0) return MRCNN_OK;
+    RoiParams p = p_in;
+    p.negzero = -0.0f;
     bool fast = image_layout == MRCNN_NHWC && (p.C % 4) == 0 && p.ph <= kMaxPool && p.pw <= kMaxPool &&
                 aligned16(p.crops);
     for (int l = 0; l < (p.pyramid ? 4 : 1); ++l) fast = fast && aligned16(p.lv[l].ptr);

@@ -42,9 +42,9 @@ cases = {
     "bwd7  nhwc GATHER": lambda: bwd(7, g7c, L.NHWC, wl.gfm7, None, True), "bwd14 nhwc GATHER": lambda: bwd(14, g14c, L.NHWC, wl.gfm14, None, True),
     "torch zero_ of one pyramid": zero_only,
 }
-only = sys.argv[1].upper() if len(sys.argv) > 1 else None
+only = sys.argv[1].lower() if len(sys.argv) > 1 else None
 for name, fn in cases.items():
-    if only and only not in name:
+    if only and only not in name.lower():
         continue
     t = wl.time_op(fn, iters=20)
     print("%-28s %8.1f us" % (name, t * 1e6))
