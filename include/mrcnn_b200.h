@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 1
+#define MRCNN_ABI_VERSION 2
 
 #define MRCNN_OK 0
 #define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */

@@ -54,7 +54,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mrcnn_abi_version() != 1:
+    if lib.mrcnn_abi_version() != 2:
         raise ImportError("maskrcnn_b200: ABI version mismatch")
     return lib
 
