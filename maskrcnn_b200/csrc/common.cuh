@@ -147,8 +147,18 @@ __device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float
     const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
     const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-    return ovr >= thr;  // NaN -> false (kept), as on the CPU
+    // Disjoint boxes (the common case): 0 / x is 0 (or NaN), never >= a positive threshold.
+    if (inter == 0.0f && thr > 0.0f) return false;
+    const float denom = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // The decision is that of the correctly rounded quotient (NaN -> false, kept, as on the CPU).  A 2-ulp
+    // approximate quotient settles it unless it lands within ~8 ulp of the threshold; only then divide exactly.
+    if (fabsf(denom) < 1e37f && fabsf(denom) > 1e-30f) {
+        const float q = __fdividef(inter, denom);
+        const float margin = fabsf(thr) * 1e-6f + 1e-37f;
+        if (q > thr + margin) return true;
+        if (q < thr - margin) return false;
+    }
+    return __fdiv_rn(inter, denom) >= thr;
 }
 
 __device__ __forceinline__ float box_area_p1(const float4 b) {
