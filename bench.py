@@ -477,18 +477,6 @@ def secondary(torch, wl, hbm):
     from maskrcnn_b200 import synth, roofline
     out = {}
     dev = "cuda"
-    # configs[1]: proposal layer, batch 8, 261,888 anchors, 6000 -> NMS 0.7 -> 1000
-    anchors = synth.pyramid_anchors((IMAGE, IMAGE))
-    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 1235 + i) for i in range(8)])
-    rc, rb, an = torch.from_numpy(np.stack(rcs)).to(dev), torch.from_numpy(np.stack(rbs)).to(dev), torch.from_numpy(anchors).to(dev)
-    f = lambda: m.proposal_layer(rc, rb, an, 6000, 1000, 0.7)  # noqa: E731
-    t = wl.time_op(f, iters=20)
-    _, counts = f()
-    by = 8 * roofline.proposal_bytes(len(anchors), 6000, 1000)
-    out["proposal_layer"] = {"config": "configs[1]: 261,888 anchors, top-6000 -> NMS 0.7 -> 1000, batch 8", "images_per_s": 8 / t,
-                             "ms_per_batch": t * 1e3, "kept_mean": float(counts.float().mean().item()),
-                             "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
-                             "note": "latency-bound (sequential sweep + multi-pass select); 3 launches per batch"}
     # configs[2]: forward only, 1000 RoIs x 256 ch on one image
     boxes_np = synth.random_rois(1000, 1234)
     boxes = torch.from_numpy(boxes_np).to(dev)
@@ -587,6 +575,29 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
             "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item())}
 
 
+def rpn_nms(torch, dist, wl, world, rank, hbm):
+    """BASELINE configs[1] on every rank (weak scaling, no collective): proposal layer, 261,888 anchors, top-6000 ->
+    NMS 0.7 -> 1000, batch 8 per GPU.  CUDA events, max over ranks."""
+    import maskrcnn_b200 as m
+    from maskrcnn_b200 import synth, roofline
+    dev = "cuda"
+    anchors = synth.pyramid_anchors((IMAGE, IMAGE))
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 1235 + 8 * rank + i) for i in range(8)])
+    rc, rb, an = torch.from_numpy(np.stack(rcs)).to(dev), torch.from_numpy(np.stack(rbs)).to(dev), torch.from_numpy(anchors).to(dev)
+    f = lambda: m.proposal_layer(rc, rb, an, 6000, 1000, 0.7)  # noqa: E731
+    t = wl.time_op(f, iters=20)
+    _, counts = f()
+    if world > 1:
+        tt = torch.tensor([t], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    by = 8 * roofline.proposal_bytes(len(anchors), 6000, 1000)
+    return {"config": "configs[1]: 261,888 anchors, top-6000 -> NMS 0.7 -> 1000, batch 8 per GPU", "images_per_s": world * 8 / t,
+            "ms_per_batch": t * 1e3, "kept_mean": float(counts.float().mean().item()), "scaling": "weak",
+            "algorithmic_GBps_per_gpu": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+            "note": "latency-bound (sequential sweep + multi-pass select); 3 launches per batch"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -658,6 +669,7 @@ def main():
                             "kernels": kern}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)
         line["detection_path_sharded"] = sharded_detection(torch, dist, wl, world, rank, hbm)
+        line["rpn_nms"] = rpn_nms(torch, dist, wl, world, rank, hbm)
         if rank == 0 and world == 1:
             cores = os.cpu_count() or 1
             arm = CpuArm(1)
