@@ -154,6 +154,38 @@ MRCNN_API int mrcnn_detection_layer(const float* rois, const float* probs, const
                           float* dets_out, int32_t* counts_out, int32_t* index_out,
                           void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
 
+/* ---- detection-target layer (replaces mrn_samples, model.py:396-576; data.boxes_overlaps data.py:151-189;
+ *      data.boxes_deltas data.py:103-121) ------------------------------------------------------------------- */
+
+/* Step 1, batched: rois [B,N,4] and gt_boxes [B,G,4] normalised (y1,x1,y2,x2), gt_class_ids int32 [B,G] (< 0 = COCO
+ * crowd, 0 = padding; when an image has a crowd row only rows with class > 0 are matched, model.py:436-449).
+ * Outputs per image: pos_idx / neg_idx int32 [B,N] = ASCENDING indices of the proposals with max IoU >= 0.5 /
+ * < 0.5 and not on a crowd (torch.nonzero order, model.py:459, :513-516); assign int32 [B,N] = gt row of the max IoU
+ * (first maximum); iou_max optional fp32 [B,N]; counts int32 [B,2] = {positives, negatives}. */
+MRCNN_API int mrcnn_target_classify(const float* rois, const float* gt_boxes, const int32_t* gt_class_ids,
+                                    int B, int N, int G, int32_t* pos_idx, int32_t* neg_idx, int32_t* assign,
+                                    float* iou_max, int32_t* counts, mrcnn_stream_t stream);
+
+/* Step 2 (optional, replaces the two torch.randperm draws, model.py:468 and :520, without a host round trip):
+ * perm_pos[b] = stable argsort(keys_pos[b, :P_b]), perm_neg likewise; take int32 [B,2] = {min(P, pos_cap),
+ * min(Q, neg_table[kept positives])}.  neg_table: DEVICE int32 [pos_cap + 1], built by the caller as
+ * int(p / ratio - p) in double precision (model.py:518-519).  N <= 8192. */
+MRCNN_API int mrcnn_target_select(const int32_t* counts, const float* keys_pos, const float* keys_neg,
+                                  const int32_t* neg_table, int B, int N, int pos_cap, int32_t* perm_pos,
+                                  int32_t* perm_neg, int32_t* take, mrcnn_stream_t stream);
+
+/* Step 3: row t < take[b][0] is positive number t: proposal pos_idx[b][perm_pos[b][t]] (perm NULL = identity), its gt
+ * class, (boxes_deltas / std4) and the mask_h x mask_w target cropped from gt_masks [B,G,H,W] (fp32) and rounded half
+ * to even (model.py:474-507); the next take[b][1] rows are negatives (class 0, zero deltas / masks, model.py:525-541);
+ * rows up to T are zero padding.  Outputs: rois_out [B,T,4], class_out int32 [B,T], deltas_out [B,T,4],
+ * masks_out [B,T,mask_h,mask_w]. */
+MRCNN_API int mrcnn_target_emit(const float* rois, const float* gt_boxes, const int32_t* gt_class_ids,
+                                const float* gt_masks, int B, int N, int G, int H, int W, const int32_t* pos_idx,
+                                const int32_t* neg_idx, const int32_t* perm_pos, const int32_t* perm_neg,
+                                const int32_t* take, const int32_t* assign, const float* std4_host, int mask_h,
+                                int mask_w, int T, float* rois_out, int32_t* class_out, float* deltas_out,
+                                float* masks_out, mrcnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,14 +1,15 @@
 """maskrcnn_b200 — B200-native (sm_100a) RoI hot path of Mask R-CNN behind the reference's operator API.
 
     nms, CropFunction                      drop-ins for c++ext/maskrcnn/__init__.py
-    roi_align, rpn_refine, mrn_refine      drop-ins for the model.py functions that call them
-    pyramid_roi_align, proposal_layer, detection_layer   batched, sync-free variants
+    roi_align, rpn_refine, mrn_refine, mrn_samples   drop-ins for the model.py functions that call them
+    pyramid_roi_align, proposal_layer, detection_layer, detection_targets   batched, sync-free variants
     patch(model_module)                    swaps the fused versions into an unmodified reference model.py
 
 All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.h).  No CPU fallback.
 """
-from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, mrn_refine, nms,  # noqa: F401
-                  proposal_layer, pyramid_roi_align, roi_align, rpn_refine, set_backward_algorithm)
+from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets,  # noqa: F401
+                  mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, roi_align, rpn_refine,
+                  set_backward_algorithm)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 
 __version__ = "0.1.0"
@@ -16,9 +17,10 @@ __version__ = "0.1.0"
 
 def patch(model_module):
     """Monkey-patches an imported reference `model` module (model.py) so that its RoI hot path runs on
-    the fused kernels: model.roi_align, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine.  The `maskrcnn` package
+    the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine.  The `maskrcnn` package
     the module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
     model_module.roi_align = roi_align
     model_module.MaskRCNN.rpn_refine = rpn_refine
     model_module.MaskRCNN.mrn_refine = mrn_refine
+    model_module.mrn_samples = mrn_samples
     return model_module

@@ -19,7 +19,8 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "check_device_errors", "set_backward_algorithm"]
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "check_device_errors",
+           "set_backward_algorithm"]
 
 
 # Backward of the channels-last PyramidROIAlign: "auto" (MRCNN_BWD_AUTO: the row-owner gather whenever the call is
@@ -364,3 +365,115 @@ def mrn_refine(self, rpn_rois, probs, deltas, window):
         return None, None, None
     dets = dets[0, :d]
     return dets[:, 5].long().unsqueeze(0), dets[:, 4].unsqueeze(0), dets[:, :4].unsqueeze(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# detection-target layer
+# ------------------------------------------------------------------------------------------------
+def _target_classify(rois, gt_class_ids, gt_boxes, want_iou=False):
+    B, N = rois.shape[:2]
+    G = gt_boxes.size(1)
+    dev = rois.device
+    pos = torch.empty((B, max(N, 1)), dtype=torch.int32, device=dev)
+    neg = torch.empty((B, max(N, 1)), dtype=torch.int32, device=dev)
+    assign = torch.empty((B, max(N, 1)), dtype=torch.int32, device=dev)
+    iou = torch.empty((B, max(N, 1)), dtype=torch.float32, device=dev) if want_iou else None
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    check(lib.mrcnn_target_classify(_ptr(rois) if N else None, _ptr(gt_boxes) if G else None, _ptr(gt_class_ids) if G else None,
+                                    B, N, G, pos.data_ptr(), neg.data_ptr(), assign.data_ptr(), _ptr(iou), counts.data_ptr(),
+                                    _stream()))
+    return pos, neg, assign, iou, counts
+
+
+def _target_emit(rois, gt_class_ids, gt_boxes, gt_masks, pos, neg, perm_pos, perm_neg, take, assign, std, mask_shape, T):
+    B, N = rois.shape[:2]
+    G, H, W = gt_masks.shape[1:]
+    dev = rois.device
+    mh, mw = int(mask_shape[0]), int(mask_shape[1])
+    o_rois = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    o_cls = torch.empty((B, T), dtype=torch.int32, device=dev)
+    o_d = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    o_m = torch.empty((B, T, mh, mw), dtype=torch.float32, device=dev)
+    check(lib.mrcnn_target_emit(rois.data_ptr(), gt_boxes.data_ptr(), gt_class_ids.data_ptr(), gt_masks.data_ptr(), B, N, G, H, W,
+                                pos.data_ptr(), neg.data_ptr(), _ptr(perm_pos), _ptr(perm_neg), take.data_ptr(), assign.data_ptr(),
+                                _lib.f4(np.float32(std)), mh, mw, T, o_rois.data_ptr(), o_cls.data_ptr(), o_d.data_ptr(),
+                                o_m.data_ptr(), _stream()))
+    return o_rois, o_cls, o_d, o_m
+
+
+def _negatives_for(pos_kept, ratio):
+    """model.py:518-519 in Python doubles, like the reference."""
+    r = 1.0 / ratio
+    return int(r * pos_kept - pos_kept)
+
+
+def detection_targets(rois, gt_class_ids, gt_boxes, gt_masks, keys_pos, keys_neg, train_rois_per_image=512,
+                      roi_positive_ratio=0.33, std=(0.1, 0.1, 0.2, 0.2), mask_shape=(28, 28)):
+    """Batched, sync-free detection-target layer.  rois [B,N,4] and gt_boxes [B,G,4] normalised, gt_class_ids int32
+    [B,G], gt_masks fp32 [B,G,H,W]; keys_pos / keys_neg fp32 [B,N]: random keys that stand for the reference's two
+    torch.randperm draws (perm = stable argsort of the first P / Q keys).  Returns zero-padded
+    (rois [B,T,4], class_ids int32 [B,T], deltas [B,T,4], masks [B,T,mh,mw], take int32 [B,2] = kept positives /
+    negatives) with T = train_rois_per_image; positives first, then negatives (model.py:524-541)."""
+    for t, name in ((rois, "rois"), (gt_boxes, "gt_boxes"), (gt_masks, "gt_masks"), (keys_pos, "keys_pos"), (keys_neg, "keys_neg")):
+        _require_cuda(t, name, torch.float32)
+    _require_cuda(gt_class_ids, "gt_class_ids", torch.int32)
+    B, N = rois.shape[:2]
+    if rois.dim() != 3 or rois.size(2) != 4 or gt_boxes.dim() != 3 or gt_masks.dim() != 4 or keys_pos.shape != (B, N) \
+            or keys_neg.shape != (B, N) or gt_class_ids.shape != gt_boxes.shape[:2] or gt_masks.shape[:2] != gt_boxes.shape[:2]:
+        raise ValueError("rois [B,N,4], gt_class_ids [B,G], gt_boxes [B,G,4], gt_masks [B,G,H,W], keys [B,N]")
+    rois, gt_boxes, gt_masks, gt_class_ids = rois.contiguous(), gt_boxes.contiguous(), gt_masks.contiguous(), gt_class_ids.contiguous()
+    keys_pos, keys_neg = keys_pos.contiguous(), keys_neg.contiguous()
+    T = int(train_rois_per_image)
+    pos_cap = int(T * roi_positive_ratio)                                    # model.py:466-467
+    with torch.cuda.device(rois.device):
+        table = torch.tensor([_negatives_for(p, roi_positive_ratio) for p in range(pos_cap + 1)], dtype=torch.int32).to(rois.device)
+        pos, neg, assign, _, counts = _target_classify(rois, gt_class_ids, gt_boxes)
+        perm_pos, perm_neg = torch.empty_like(pos), torch.empty_like(neg)
+        take = torch.empty((B, 2), dtype=torch.int32, device=rois.device)
+        check(lib.mrcnn_target_select(counts.data_ptr(), keys_pos.data_ptr(), keys_neg.data_ptr(), table.data_ptr(), B, N, pos_cap,
+                                      perm_pos.data_ptr(), perm_neg.data_ptr(), take.data_ptr(), _stream()))
+        out = _target_emit(rois, gt_class_ids, gt_boxes, gt_masks, pos, neg, perm_pos, perm_neg, take, assign, std, mask_shape, T)
+    return out + (take,)
+
+
+def mrn_samples(rpn_rois, gt_class_ids, gt_boxes, gt_masks, config):
+    """Drop-in for mrn_samples (model.py:396-576), batch 1 like the reference: rpn_rois [1,N,4], gt_class_ids [1,G],
+    gt_boxes [1,G,4], gt_masks [1,G,H,W] -> (rois [T,4], class ids int32 [T], deltas [T,4], masks [T,mh,mw]).
+    The two permutations are drawn with torch.randperm on the CPU generator in the reference's order (:468, :520), so
+    results are identical to the reference's under the same torch seed; like the reference it reads the positive /
+    negative counts back once."""
+    dev = rpn_rois.device
+    rois = rpn_rois.float().contiguous()
+    cls = gt_class_ids.to(torch.int32).contiguous()
+    gtb = gt_boxes.float().contiguous()
+    masks = gt_masks.float().contiguous()
+    _require_cuda(rois, "rpn_rois", torch.float32)
+    if rois.dim() != 3 or rois.size(0) != 1 or masks.dim() != 4:
+        raise ValueError("mrn_samples supports batch 1 like the reference: rpn_rois [1,N,4], gt_masks [1,G,H,W]")
+    N = rois.size(1)
+    ratio = float(config.ROI_POSITIVE_RATIO)
+    empty = (torch.empty(0, device=dev), torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, device=dev),
+             torch.empty(0, device=dev))                                    # model.py:563-574
+    if N == 0 or gtb.size(1) == 0:
+        return empty
+    with torch.cuda.device(dev):
+        pos, neg, assign, _, counts = _target_classify(rois, cls, gtb)
+        P, Q = (int(v) for v in counts[0].tolist())                          # the reference syncs here too (nonzero)
+        if P == 0:
+            return empty
+        perm_pos = torch.randperm(P)[:int(config.TRAIN_ROIS_PER_IMAGE * ratio)]          # :466-471
+        tp = int(perm_pos.numel())
+        tn, perm_neg = 0, None
+        if Q > 0:
+            perm_neg = torch.randperm(Q)[:_negatives_for(tp, ratio)]                         # :518-522
+            tn = int(perm_neg.numel())
+        pp = torch.zeros((1, N), dtype=torch.int32)
+        pp[0, :tp] = perm_pos.to(torch.int32)
+        pn = torch.zeros((1, N), dtype=torch.int32)
+        if tn:
+            pn[0, :tn] = perm_neg.to(torch.int32)
+        take = torch.tensor([[tp, tn]], dtype=torch.int32)
+        o_rois, o_cls, o_d, o_m = _target_emit(rois, cls, gtb, masks, pos, neg, pp.to(dev), pn.to(dev), take.to(dev), assign,
+                                               np.asarray(config.BBOX_STD_DEV, dtype=np.float32).reshape(4), config.MASK_SHAPE,
+                                               tp + tn)
+    return o_rois[0], o_cls[0], o_d[0], o_m[0]

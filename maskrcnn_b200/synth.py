@@ -122,3 +122,33 @@ def pyramid_shapes(batch, channels, image=1024, strides=(4, 8, 16, 32)):
 def feature_pyramid(batch, channels, seed, image=1024, strides=(4, 8, 16, 32)):
     rng = np.random.default_rng(seed)
     return [rng.standard_normal(s, dtype=np.float32) for s in pyramid_shapes(batch, channels, image, strides)]
+
+
+def target_inputs(n_rois, n_gt, seed, image=1024, n_crowd=0, n_pad=0, positive_fraction=0.3):
+    """Inputs of the detection-target layer (model.py:396 mrn_samples) for one image: proposals (normalised, a
+    fraction of them jittered copies of gt boxes so that IoU >= 0.5 occurs), gt class ids (int32; `n_crowd` rows
+    negative = COCO crowds, `n_pad` trailing rows 0 = padding with zero boxes), gt boxes (normalised) and binary gt
+    masks [n_gt, image, image] (an ellipse inside each box)."""
+    rng = np.random.default_rng(seed)
+    gt = random_rois(n_gt, seed + 1, image=float(image), min_size=image / 16.0, max_size=image * 0.6)
+    cls = rng.integers(1, 81, n_gt).astype(np.int32)
+    if n_crowd:
+        cls[rng.choice(n_gt - n_pad, n_crowd, replace=False)] = -1
+    if n_pad:
+        cls[n_gt - n_pad:] = 0
+        gt[n_gt - n_pad:] = 0.0
+    rois = random_rois(n_rois, seed + 2, image=float(image), min_size=image / 64.0, max_size=image * 0.7)
+    n_pos = int(n_rois * positive_fraction)
+    real = max(n_gt - n_pad, 1)
+    src = rng.integers(0, real, n_pos)
+    hw = np.stack([gt[src, 2] - gt[src, 0], gt[src, 3] - gt[src, 1]] * 2, 1)
+    jitter = (rng.normal(0.0, 0.07, (n_pos, 4)) * hw).astype(np.float32)
+    where = rng.permutation(n_rois)[:n_pos]
+    rois[where] = np.clip(gt[src] + jitter, 0.0, 1.0)
+    masks = np.zeros((n_gt, image, image), np.float32)
+    yy, xx = np.mgrid[0:image, 0:image].astype(np.float32)
+    for g in range(n_gt - n_pad):
+        y1, x1, y2, x2 = gt[g] * image
+        cy, cx, ry, rx = (y1 + y2) / 2, (x1 + x2) / 2, max((y2 - y1) / 2, 1.0), max((x2 - x1) / 2, 1.0)
+        masks[g] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0).astype(np.float32)
+    return rois.astype(np.float32), cls, gt.astype(np.float32), masks

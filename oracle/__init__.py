@@ -57,6 +57,11 @@ def lib():
         L.orc_proposal_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_float, _f32p, ctypes.c_float,
                                          ctypes.c_float, _f32p, _f32p, _i64p]
+        L.orc_target_classify.restype = None
+        L.orc_target_classify.argtypes = [_f32p, ctypes.c_int64, _f32p, _i32p, ctypes.c_int64, _i64p, _i64p, _i32p, _f32p, _i64p]
+        L.orc_target_emit.restype = None
+        L.orc_target_emit.argtypes = [_f32p, _f32p, _i32p, _f32p, ctypes.c_int, ctypes.c_int, _i64p, ctypes.c_int64, _i64p,
+                                      ctypes.c_int64, _i32p, _f32p, ctypes.c_int, ctypes.c_int, _f32p, _i32p, _f32p, _f32p]
         L.orc_detection_layer.restype = ctypes.c_int64
         L.orc_detection_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64, _f32p,
                                           ctypes.c_float, ctypes.c_float, ctypes.c_int64, _f32p,
@@ -212,3 +217,58 @@ def boxes_refine(boxes, deltas):
     out = np.empty_like(boxes)
     lib().orc_boxes_refine(_p(boxes), _p(deltas), boxes.shape[0], _p(out))
     return out
+
+
+def target_classify(rois, gt_class_ids, gt_boxes):
+    """model.py:431-463, :513-516 -> (positive RoI indices, negative RoI indices, assigned gt row per RoI, max IoU per RoI)."""
+    rois, gt_boxes = _f32(rois), _f32(gt_boxes)
+    cls = np.ascontiguousarray(gt_class_ids, np.int32)
+    n, g = len(rois), len(gt_boxes)
+    pos, neg = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.int64)
+    assign, iou = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float32)
+    counts = np.zeros(2, np.int64)
+    lib().orc_target_classify(_p(rois), n, _p(gt_boxes), _p(cls, _i32p), g, _p(pos, _i64p), _p(neg, _i64p), _p(assign, _i32p),
+                              _p(iou), _p(counts, _i64p))
+    return pos[:counts[0]].copy(), neg[:counts[1]].copy(), assign[:n], iou[:n]
+
+
+def target_emit(rois, gt_class_ids, gt_boxes, gt_masks, sel_pos, sel_neg, assign, std_dev, mask_shape):
+    """model.py:474-541 for already chosen positives / negatives -> (rois, class ids, deltas, masks)."""
+    rois, gt_boxes, gt_masks = _f32(rois), _f32(gt_boxes), _f32(gt_masks)
+    cls = np.ascontiguousarray(gt_class_ids, np.int32)
+    sp, sn = np.ascontiguousarray(sel_pos, np.int64), np.ascontiguousarray(sel_neg, np.int64)
+    asg = np.ascontiguousarray(assign, np.int32)
+    std = _f32(std_dev)
+    mh, mw = int(mask_shape[0]), int(mask_shape[1])
+    t = len(sp) + len(sn)
+    o_rois, o_cls = np.zeros((t, 4), np.float32), np.zeros(t, np.int32)
+    o_d, o_m = np.zeros((t, 4), np.float32), np.zeros((t, mh, mw), np.float32)
+    h, w = gt_masks.shape[-2:]
+    lib().orc_target_emit(_p(rois), _p(gt_boxes), _p(cls, _i32p), _p(gt_masks), h, w, _p(sp, _i64p), len(sp), _p(sn, _i64p), len(sn),
+                          _p(asg, _i32p), _p(std), mh, mw, _p(o_rois), _p(o_cls, _i32p), _p(o_d), _p(o_m))
+    return o_rois, o_cls, o_d, o_m
+
+
+def target_counts(n_pos, n_neg, train_rois_per_image, roi_positive_ratio):
+    """How many positives / negatives mrn_samples keeps (model.py:466-471, :518-522), in Python doubles like the reference."""
+    pc = min(int(train_rois_per_image * roi_positive_ratio), n_pos)
+    if pc <= 0:
+        return 0, 0                       # model.py:517: negatives only when positive_count > 0
+    r = 1.0 / roi_positive_ratio
+    nc = min(int(r * pc - pc), n_neg)
+    return pc, max(nc, 0)
+
+
+def mrn_samples(rois, gt_class_ids, gt_boxes, gt_masks, train_rois_per_image, roi_positive_ratio, std_dev, mask_shape, randperm):
+    """model.py:396-576 for one image.  `randperm(n)` stands for the reference's torch.randperm draws, called in the
+    reference's order: positives first (:468), then negatives (:520)."""
+    pos, neg, assign, _ = target_classify(rois, gt_class_ids, gt_boxes)
+    pc, _ = target_counts(len(pos), len(neg), train_rois_per_image, roi_positive_ratio)
+    sel_pos = np.zeros(0, np.int64)
+    if len(pos) > 0:
+        sel_pos = pos[np.asarray(randperm(len(pos)), np.int64)[:int(train_rois_per_image * roi_positive_ratio)]]
+    sel_neg = np.zeros(0, np.int64)
+    if len(neg) > 0 and len(sel_pos) > 0:
+        r = 1.0 / roi_positive_ratio
+        sel_neg = neg[np.asarray(randperm(len(neg)), np.int64)[:int(r * len(sel_pos) - len(sel_pos))]]
+    return target_emit(rois, gt_class_ids, gt_boxes, gt_masks, sel_pos, sel_neg, assign, std_dev, mask_shape)

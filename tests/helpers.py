@@ -21,3 +21,21 @@ def rel_err(got, want):
     want = np.asarray(want, np.float64)
     scale = max(np.abs(want).max(), 1e-30) if want.size else 1.0
     return float(np.abs(got - want).max() / scale) if want.size else 0.0
+
+
+GOLDEN_TARGETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_targets_v1.npz")
+
+
+def golden_targets():
+    return np.load(GOLDEN_TARGETS)
+
+
+def replay_perms(perms):
+    """A stand-in for torch.randperm that replays the recorded draws in order (and checks their lengths)."""
+    it = iter(perms)
+
+    def randperm(n):
+        p = np.asarray(next(it))
+        assert len(p) == n, "permutation length differs from the reference's draw"
+        return p
+    return randperm

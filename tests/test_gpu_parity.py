@@ -388,3 +388,95 @@ def test_pyramid_backward_gather(ops, pool, B, C, size, N, mode):
     for a, b in zip(grads[0], grads[1]):             # run to run: same sums up to fp32 association order
         assert rel_err(a, b) <= BWD_TOL
     ops.check_device_errors()
+
+
+# ------------------------------------------------------------------ detection-target layer (mrn_samples)
+def _target_cfg(train_rois):
+    import types
+    return types.SimpleNamespace(GPU_COUNT=1, TRAIN_ROIS_PER_IMAGE=train_rois, ROI_POSITIVE_RATIO=0.33,
+                                 BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), MASK_SHAPE=[28, 28])
+
+
+def _check_targets(got, want):
+    g_rois, g_cls, g_d, g_m = (t.cpu().numpy() for t in got)
+    w_rois, w_cls, w_d, w_m = want
+    assert g_rois.shape == w_rois.shape and g_cls.dtype == np.int32
+    np.testing.assert_array_equal(g_rois, w_rois)
+    np.testing.assert_array_equal(g_cls, w_cls)
+    np.testing.assert_array_equal(g_d, w_d)        # dy, dx exact; dh, dw: both sides use the correctly rounded log
+    np.testing.assert_array_equal(g_m, w_m)
+
+
+@pytest.mark.parametrize("n_rois,n_gt,n_crowd,n_pad,train_rois,image,seed", [
+    (1000, 20, 0, 0, 512, 256, 1), (1000, 20, 3, 4, 512, 256, 2), (333, 7, 0, 2, 100, 200, 3), (65, 3, 1, 0, 512, 96, 4),
+    (2000, 100, 5, 10, 512, 128, 5), (500, 1, 0, 0, 64, 64, 6)])
+def test_mrn_samples_dropin_matches_oracle(ops, n_rois, n_gt, n_crowd, n_pad, train_rois, image, seed):
+    """ops.mrn_samples (reference signature; draws torch.randperm like the reference) vs the oracle under the same seed."""
+    rois, cls, gt, masks = synth.target_inputs(n_rois, n_gt, seed, image=image, n_crowd=n_crowd, n_pad=n_pad)
+    torch.manual_seed(40 + seed)
+    want = oracle.mrn_samples(rois, cls, gt, masks, train_rois, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28),
+                              lambda n: torch.randperm(n).numpy())
+    torch.manual_seed(40 + seed)
+    got = ops.mrn_samples(dev(rois)[None], dev(cls)[None], dev(gt)[None], dev(masks)[None], _target_cfg(train_rois))
+    assert len(want[0]) > 3
+    _check_targets(got, want)
+    ops.check_device_errors()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_mrn_samples_golden(ops, tag):
+    """Against what the reference's model.mrn_samples returned (tests/golden/make_golden_targets.py) under the recorded seed."""
+    from helpers import golden_targets, ulp_diff
+    g = golden_targets()
+    torch.manual_seed(int(g[f"{tag}_in_seed"]))
+    got = ops.mrn_samples(dev(g[f"{tag}_in_rois"])[None], dev(g[f"{tag}_in_cls"])[None], dev(g[f"{tag}_in_gt"])[None],
+                          dev(g[f"{tag}_in_masks"].astype(np.float32))[None], _target_cfg(int(g[f"{tag}_in_train_rois"])))
+    g_rois, g_cls, g_d, g_m = (t.cpu().numpy() for t in got)
+    np.testing.assert_array_equal(g_rois, g[f"{tag}_out_rois"])
+    np.testing.assert_array_equal(g_cls, g[f"{tag}_out_cls"])
+    np.testing.assert_array_equal(g_d[:, :2], g[f"{tag}_out_deltas"][:, :2])
+    assert ulp_diff(g_d[:, 2:], g[f"{tag}_out_deltas"][:, 2:]).max() <= 2      # torch.log on CPU is not correctly rounded
+    np.testing.assert_array_equal(g_m, g[f"{tag}_out_masks"].astype(np.float32))
+
+
+def test_mrn_samples_edge_cases(ops):
+    cfg = _target_cfg(64)
+    rois, cls, gt, masks = synth.target_inputs(50, 3, 9, image=64, positive_fraction=0.0)
+    rois[:] = [0.0, 0.0, 0.01, 0.01]                                 # no positive -> four empty tensors (model.py:563-574)
+    out = ops.mrn_samples(dev(rois)[None], dev(cls)[None], dev(gt)[None], dev(masks)[None], cfg)
+    assert all(t.numel() == 0 for t in out)
+    rois, cls, gt, masks = synth.target_inputs(40, 2, 10, image=64, positive_fraction=1.0)   # every proposal positive
+    torch.manual_seed(1)
+    want = oracle.mrn_samples(rois, cls, gt, masks, 64, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28), lambda n: torch.randperm(n).numpy())
+    torch.manual_seed(1)
+    got = ops.mrn_samples(dev(rois)[None], dev(cls)[None], dev(gt)[None], dev(masks)[None], cfg)
+    _check_targets(got, want)
+    with pytest.raises(TypeError):
+        ops.mrn_samples(torch.from_numpy(rois)[None], torch.from_numpy(cls)[None], torch.from_numpy(gt)[None],
+                        torch.from_numpy(masks)[None], cfg)          # no CPU path
+
+
+@pytest.mark.parametrize("B,n_rois,n_gt,train_rois,image", [(4, 1000, 24, 512, 128), (3, 257, 9, 100, 96), (2, 8192, 16, 512, 64)])
+def test_detection_targets_batched_matches_oracle(ops, B, n_rois, n_gt, train_rois, image):
+    """Sync-free batched layer: random keys stand for the two torch.randperm draws (perm = stable argsort of the first
+    P / Q keys); images with crowds, padding and different positive fractions in one call."""
+    rng = np.random.default_rng(B * 1000 + n_rois)
+    ins = [synth.target_inputs(n_rois, n_gt, 70 + b, image=image, n_crowd=b % 3, n_pad=(2 * b) % 5,
+                               positive_fraction=(0.0 if b == 2 else 0.1 + 0.2 * b)) for b in range(B)]
+    if B > 2:
+        ins[2][0][:] = [0.0, 0.0, 0.01, 0.01]                        # an image without positives
+    kp = rng.permutation(B * n_rois).reshape(B, n_rois).astype(np.float32) / (B * n_rois)
+    kn = rng.permutation(B * n_rois).reshape(B, n_rois).astype(np.float32) / (B * n_rois)
+    stack = lambda k: np.stack([x[k] for x in ins])  # noqa: E731
+    o_rois, o_cls, o_d, o_m, take = ops.detection_targets(dev(stack(0)), dev(stack(1)), dev(stack(2)), dev(stack(3)), dev(kp), dev(kn),
+                                                          train_rois_per_image=train_rois)
+    take = take.cpu().numpy()
+    for b in range(B):
+        draws = [lambda n, b=b: np.argsort(kp[b, :n], kind="stable"), lambda n, b=b: np.argsort(kn[b, :n], kind="stable")]
+        it = iter(draws)
+        want = oracle.mrn_samples(*ins[b], train_rois, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28), lambda n: next(it)(n))
+        t = len(want[0])
+        assert take[b].sum() == t and take[b][0] == (want[1] > 0).sum()
+        _check_targets((o_rois[b, :t], o_cls[b, :t], o_d[b, :t], o_m[b, :t]), want)
+        assert float(o_rois[b, t:].abs().sum()) == 0.0 and int(o_cls[b, t:].abs().sum()) == 0 and float(o_m[b, t:].sum()) == 0.0
+    ops.check_device_errors()

@@ -173,3 +173,44 @@ def test_detection_layer_matches_model_py():
         np.testing.assert_array_equal(got[:, 5].astype(np.int64), ci[0].numpy())
         np.testing.assert_array_equal(got[:, 4], sc[0].numpy())
         np.testing.assert_array_equal(got[:, :4], bx[0].numpy())
+
+
+@needs_model
+@pytest.mark.parametrize("n_rois,n_gt,n_crowd,n_pad,train_rois,seed", [
+    (600, 12, 0, 0, 512, 1), (600, 12, 2, 3, 512, 2), (300, 5, 0, 2, 100, 3), (64, 3, 1, 0, 512, 4), (200, 6, 0, 0, 32, 5)])
+def test_target_layer_matches_model_py(n_rois, n_gt, n_crowd, n_pad, train_rois, seed):
+    """model.mrn_samples (unmodified, CPU) vs the oracle under the same torch seed: the oracle draws its two
+    permutations with torch.randperm in the reference's order, so selections and their order must be identical."""
+    ref = reference.load()
+    import types
+    S = 256
+    rois, cls, gt, masks = synth.target_inputs(n_rois, n_gt, seed, image=S, n_crowd=n_crowd, n_pad=n_pad)
+    cfg = types.SimpleNamespace(GPU_COUNT=0, TRAIN_ROIS_PER_IMAGE=train_rois, ROI_POSITIVE_RATIO=0.33,
+                                BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), MASK_SHAPE=[28, 28])
+    torch.manual_seed(100 + seed)
+    w_rois, w_cls, w_d, w_m = ref.model.mrn_samples(torch.from_numpy(rois)[None], torch.from_numpy(cls)[None],
+                                                    torch.from_numpy(gt)[None], torch.from_numpy(masks)[None], cfg)
+    torch.manual_seed(100 + seed)
+    g_rois, g_cls, g_d, g_m = oracle.mrn_samples(rois, cls, gt, masks, train_rois, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28),
+                                                 lambda n: torch.randperm(n).numpy())
+    assert len(g_rois) == len(w_rois) and len(g_rois) > 10
+    np.testing.assert_array_equal(g_rois, w_rois.numpy())
+    np.testing.assert_array_equal(g_cls, w_cls.numpy())
+    np.testing.assert_array_equal(g_m, w_m.numpy())
+    assert (g_cls > 0).sum() >= 5 and g_m.sum() > 0
+    np.testing.assert_array_equal(g_d[:, :2], w_d.numpy()[:, :2])          # dy, dx: + - * / only
+    assert _ulp_diff(g_d[:, 2:], w_d.numpy()[:, 2:]).max() <= 2            # dh, dw: torch.log on CPU is not correctly rounded
+
+
+@needs_model
+def test_target_layer_no_positive():
+    ref = reference.load()
+    import types
+    rois, cls, gt, masks = synth.target_inputs(50, 3, 9, image=128, positive_fraction=0.0)
+    rois[:] = [0.0, 0.0, 0.01, 0.01]
+    cfg = types.SimpleNamespace(GPU_COUNT=0, TRAIN_ROIS_PER_IMAGE=64, ROI_POSITIVE_RATIO=0.33,
+                                BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), MASK_SHAPE=[28, 28])
+    w = ref.model.mrn_samples(torch.from_numpy(rois)[None], torch.from_numpy(cls)[None], torch.from_numpy(gt)[None],
+                              torch.from_numpy(masks)[None], cfg)
+    g = oracle.mrn_samples(rois, cls, gt, masks, 64, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28), lambda n: torch.randperm(n).numpy())
+    assert all(t.numel() == 0 for t in w) and all(len(a) == 0 for a in g)   # model.py:563-574
