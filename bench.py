@@ -477,6 +477,24 @@ def secondary(torch, wl, hbm):
     from maskrcnn_b200 import synth, roofline
     out = {}
     dev = "cuda"
+    # detection-target layer (mrn_samples) between the proposal layer and the training RoIAlign
+    Bt, Nt, Gt, Tt = 16, 1000, 20, ROIS_PER_IMAGE
+    ins = [synth.target_inputs(Nt, Gt, 900 + b, image=IMAGE, n_crowd=b % 2, n_pad=2) for b in range(2)]   # two distinct images, tiled
+    stack = lambda k: torch.from_numpy(np.stack([ins[b % 2][k] for b in range(Bt)])).to(dev)  # noqa: E731
+    t_rois, t_cls, t_gt, t_masks = stack(0), stack(1), stack(2), stack(3)
+    g_ = torch.Generator(device=dev)
+    g_.manual_seed(5)
+    kp, kn = torch.rand((Bt, Nt), device=dev, generator=g_), torch.rand((Bt, Nt), device=dev, generator=g_)
+    f = lambda: m.detection_targets(t_rois, t_cls, t_gt, t_masks, kp, kn, train_rois_per_image=Tt)  # noqa: E731
+    t = wl.time_op(f, iters=20)
+    take = f()[4].float().mean(0)
+    by = Bt * (Nt * 16 + Gt * 20 + Tt * (16 + 4 + 16 + 28 * 28 * 4)) + float(take[0]) * Bt * 28 * 28 * 16
+    out["detection_targets"] = {"config": "mrn_samples batched (SURVEY 8f): %d images x %d proposals x %d gt, %dx%d gt masks, %d RoIs + 28x28 "
+                                          "mask targets per image, sync-free (random keys)" % (Bt, Nt, Gt, IMAGE, IMAGE, Tt),
+                                "images_per_s": Bt / t, "ms_per_batch": t * 1e3, "kept_pos_mean": float(take[0]), "kept_neg_mean": float(take[1]),
+                                "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+                                "note": "3 launches (classify, select, emit); latency-bound: ~4 MB per image"}
+    del t_masks
     # configs[2]: forward only, 1000 RoIs x 256 ch on one image
     boxes_np = synth.random_rois(1000, 1234)
     boxes = torch.from_numpy(boxes_np).to(dev)
