@@ -40,20 +40,26 @@ def gather_detections(dets, counts, n_images=None, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         b_max = int(t.item())
     width = d * 6 + 1
-    send = torch.zeros((b_max, width), dtype=torch.float32, device=dets.device)
-    send[:b_local, :d * 6] = dets.reshape(b_local, d * 6)
-    send[:b_local, d * 6] = counts.to(torch.float32)
-    send[b_local:, d * 6] = -1.0  # padding rows
+    # pack: one concatenation, no host round trip
+    send = torch.cat((dets.reshape(b_local, d * 6), counts.to(torch.float32).unsqueeze(1)), 1)
+    if b_local < b_max:
+        pad = send.new_zeros((b_max - b_local, width))
+        pad[:, d * 6] = -1.0  # padding rows
+        send = torch.cat((send, pad), 0)
     recv = torch.empty((world * b_max, width), dtype=torch.float32, device=dets.device)
     try:
-        dist.all_gather_into_tensor(recv, send, group=group)
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
     except (RuntimeError, NotImplementedError):
         parts = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(parts, send, group=group)
+        dist.all_gather(parts, send.contiguous(), group=group)
         recv = torch.cat(parts, 0)
-    valid = recv[:, d * 6] >= 0
-    if bool(valid.all()):
-        rows = recv
+    if sizes is not None:
+        # shard sizes are known on the host: drop the padding rows without looking at device data (no sync)
+        if all(sz == b_max for sz in sizes):
+            rows = recv
+        else:
+            keep = [r * b_max + i for r, sz in enumerate(sizes) for i in range(sz)]
+            rows = recv.index_select(0, torch.tensor(keep, dtype=torch.int64).to(recv.device, non_blocking=True))
     else:
-        rows = recv[valid]
+        rows = recv[recv[:, d * 6] >= 0]
     return rows[:, :d * 6].reshape(-1, d, 6).contiguous(), rows[:, d * 6].to(torch.int32)
