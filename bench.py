@@ -477,6 +477,31 @@ def secondary(torch, wl, hbm):
     from maskrcnn_b200 import synth, roofline
     out = {}
     dev = "cuda"
+    L = wl.L
+    # both heads' backward fused into one gradient pyramid (what autograd accumulates in the reference's training step)
+    ws2 = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(wl.Hs, wl.Ws, wl.batch, wl.N, 7, 14), dtype=torch.uint8,
+                      device=dev)
+
+    def bwd_pair():
+        L.check(L.lib.mrcnn_pyramid_roi_align_backward_pair(wl.g7.data_ptr(), 7, wl.g14.data_ptr(), 14, wl.Hs, wl.Ws, wl.batch, CHANNELS,
+                                                            wl.boxes.data_ptr(), wl.ind.data_ptr(), wl.N, wl.area,
+                                                            L.vp4([x.data_ptr() for x in wl.gfm14]), 1, ws2.data_ptr(), ws2.numel(), wl._s()))
+
+    def step_fused():
+        wl.fwd(7, wl.out7)
+        wl.fwd(14, wl.out14)
+        wl.mask_targets()
+        bwd_pair()
+    if wl.cl_crops:
+        tb = wl.time_op(bwd_pair, iters=20)
+        ts = wl.time_op(step_fused, iters=20)
+        by = (wl.g7.numel() + wl.g14.numel() + wl.batch * PYR_ELEMS_PER_IMAGE) * 4
+        out["train_step_fused_backward"] = {
+            "config": "configs[3] with ONE backward for both heads: d/dP2..P5 = 7x7 head + 14x14 head, written once "
+                      "(mrcnn_pyramid_roi_align_backward_pair)", "rois_per_s": wl.N / ts, "ms_per_step": ts * 1e3,
+            "backward_pair_ms": tb * 1e3, "backward_pair_algorithmic_MB": by / 1e6, "backward_pair_frac_of_hbm": by / tb / 1e9 / hbm,
+            "note": "not the headline: the headline step returns the two heads' gradient pyramids separately, like the reference ops"}
+    del ws2
     # detection-target layer (mrn_samples) between the proposal layer and the training RoIAlign
     Bt, Nt, Gt, Tt = 16, 1000, 20, ROIS_PER_IMAGE
     ins = [synth.target_inputs(Nt, Gt, 900 + b, image=IMAGE, n_crowd=b % 2, n_pad=2) for b in range(2)]   # two distinct images, tiled

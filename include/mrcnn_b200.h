@@ -119,6 +119,19 @@ MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_lay
                                      void* workspace, size_t workspace_bytes,
                                      mrcnn_stream_t stream);
 
+/* Both heads at once.  In training the reference pools the SAME RoIs twice from the same pyramid - 7x7 for the box head
+ * (model.py:778) and 14x14 for the mask head (model.py:889) - and autograd then adds the two gradient pyramids that
+ * CropFunction.backward returned per level.  This entry point takes both upstream gradients (channels-last,
+ * grads_a [N,C,pool_a,pool_a], grads_b [N,C,pool_b,pool_b]) and writes their SUM into gfm[l] (channels-last) in one
+ * row-owner gather: one pyramid write instead of two plus an add.  zero_fill == 0 adds to what gfm holds. */
+MRCNN_API size_t mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(const int H[4], const int W[4], int B, int N,
+                                                                       int pool_a, int pool_b);
+MRCNN_API int mrcnn_pyramid_roi_align_backward_pair(const float* grads_a, int pool_a, const float* grads_b, int pool_b,
+                                                    const int H[4], const int W[4], int B, int C,
+                                                    const float* boxes, const int32_t* box_index, int N,
+                                                    float image_area, float* const gfm[4], int zero_fill,
+                                                    void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
 /* ---- NMS (replaces nms(), nms.h:15-30 -> cpu/nms_cpu.cpp:11-70) -------------------------------- */
 
 /* dets [N,5] = (y1,x1,y2,x2,score), any order.  Suppress iff IoU >= threshold (the CPU rule,

@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(kThreads) roialign_bwd_nhwc_kernel(const RoiPa
 // ------------------------------------------------------------------------------------------------
 constexpr int kGTile = 8;       // pixels per unit
 constexpr int kONoop = 9;
+constexpr int kOHead2 = 16;  // QItem.idx bit: the bin belongs to the second gradient tensor
 
 struct __align__(16) QItem {
     int off;    // element offset of the bin in grads (32-bit by eligibility)
@@ -411,8 +412,10 @@ struct GatherParams {
     int units;
     const float* boxes;
     const int32_t* box_index;
-    const float* grads;  // [N][ph*pw][C]
-    int* cnt;            // [units] items per unit
+    const float* grads;   // [N][ph*pw][C]
+    const float* grads2;  // second head of a fused two-head backward (items tagged kOHead2), else == grads
+    int head_flag;        // 0 or kOHead2: ORed into the items the fill pass writes
+    int* cnt;             // [units] items per unit
     int* pos;            // [units] after alloc: first item; after fill: one past the last item
     unsigned int* cursor;
     QItem* items;
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(256) bwd_items_kernel(const GatherParams p) {
                         it.off = row_off + b2 * p.C;
                         it.wa = wy * __fsub_rn(1.0f, u.lerp);
                         it.wb = (j < 7) ? wy * u.lerp : 0.f;
-                        it.idx = j + 1;
+                        it.idx = (j + 1) | p.head_flag;
                         p.items[q++] = it;
                     }
                 }
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(256) bwd_items_kernel(const GatherParams p) {
                     it.off = row_off + bx * p.C;
                     it.wa = 0.f;
                     it.wb = wy * tx.lerp;
-                    it.idx = 0;
+                    it.idx = p.head_flag;
                     p.items[q] = it;
                 }
             }
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
 #pragma unroll
             for (int k = 0; k < NV; ++k) acc.a[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* gbase = p.grads + (live ? c : 0);
+        const float* gbase2 = p.grads2 + (live ? c : 0);
 
         for (int i0 = 0; i0 < n; i0 += 32) {
             QItem mine;
@@ -615,9 +619,10 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
                 if (sgi < ngroups) {
 #pragma unroll
                     for (int e = 0; e < U; ++e) {
-                        const int off = s_items[sgi * U + e].off;
+                        const QItem it = s_items[sgi * U + e];
+                        const float* src = ((it.idx & kOHead2) ? gbase2 : gbase) + it.off;
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[sgi][e][k][wl], gbase + off + 128 * k);
+                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[sgi][e][k][wl], src + 128 * k);
                     }
                 }
                 cp_async_commit();
@@ -629,9 +634,10 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
                     const int st = nxt % ST;
 #pragma unroll
                     for (int e = 0; e < U; ++e) {
-                        const int off = s_items[nxt * U + e].off;
+                        const QItem it = s_items[nxt * U + e];
+                        const float* src = ((it.idx & kOHead2) ? gbase2 : gbase) + it.off;
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[st][e][k][wl], gbase + off + 128 * k);
+                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[st][e][k][wl], src + 128 * k);
                     }
                 }
                 cp_async_commit();
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
                     float4 v[NV];
 #pragma unroll
                     for (int k = 0; k < NV; ++k) v[k] = s_data[st][e][k][wl];
-                    owner_accumulate<NV>(acc, it.idx, it.wa, it.wb, v);
+                    owner_accumulate<NV>(acc, it.idx & 15, it.wa, it.wb, v);
                 }
             }
             cp_async_wait<0>();
@@ -901,7 +907,7 @@ static long long gather_units(const int H[4], const int W[4], int B) {
     return units;
 }
 
-static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], int B, int N, int pool) {
+static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], int B, int N, long long bins) {
     GatherWorkspace w;
     const size_t units = (size_t)gather_units(H, W, B);
     size_t off = 0;
@@ -914,32 +920,36 @@ static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], 
     w.cnt = (int*)take(units * 4);
     w.clear_bytes = off;
     w.pos = (int*)take(units * 4);
-    // every bin yields at most four work items (two rows x a unit boundary)
-    w.items = (QItem*)take((size_t)4 * (size_t)(N > 0 ? N : 1) * pool * pool * sizeof(QItem));
+    // every bin yields at most four work items (two rows x a unit boundary); bins = sum of pool^2 over the heads
+    w.items = (QItem*)take((size_t)4 * (size_t)(N > 0 ? N : 1) * (size_t)bins * sizeof(QItem));
     w.bytes = off;
     return w;
 }
 
-// true if the gather backward can serve this call
-static bool gather_eligible(const int H[4], const int W[4], int B, int C, int N, int pool, int gfm_layout, int grads_layout,
-                            const float* grads, float* const gfm[4], const void* workspace, size_t workspace_bytes) {
+// true if the gather backward can serve this call (bins = sum of pool^2 over the heads, max_pool the largest pool)
+static bool gather_eligible(const int H[4], const int W[4], int B, int C, int N, long long bins, int max_pool, int gfm_layout,
+                            int grads_layout, const float* grads, float* const gfm[4], const void* workspace,
+                            size_t workspace_bytes) {
     if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
     if ((C % 4) != 0 || N <= 0) return false;
-    if ((long long)N * pool * pool * C >= (1ll << 31)) return false;      // 32-bit element offsets into grads
-    if ((long long)4 * N * pool * pool >= (1ll << 31)) return false;      // 32-bit item positions
+    if ((long long)N * max_pool * max_pool * C >= (1ll << 31)) return false;  // 32-bit element offsets into grads
+    if ((long long)4 * N * bins >= (1ll << 31)) return false;                 // 32-bit item positions
     if (gather_units(H, W, B) >= (1ll << 31) - 8) return false;
-    if ((long long)N * pool * 2 >= (1ll << 31) * 256) return false;
-    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, H, W, B, N, pool).bytes) return false;
+    if ((long long)N * max_pool * 2 >= (1ll << 31) * 256) return false;
+    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, H, W, B, N, bins).bytes) return false;
     if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
     for (int l = 0; l < 4; ++l)
         if (!aligned16(gfm[l])) return false;
     return true;
 }
 
-static int launch_bwd_gather(const float* grads, const int H[4], const int W[4], int B, int C, const float* boxes,
-                             const int32_t* box_index, int N, int pool, float image_area, float* const gfm[4],
+// One or two heads (the same boxes pooled at pools[h] x pools[h], upstream gradients grads[h]) into one gradient pyramid.
+static int launch_bwd_gather(int heads, const float* const grads[2], const int pools[2], const int H[4], const int W[4], int B,
+                             int C, const float* boxes, const int32_t* box_index, int N, float image_area, float* const gfm[4],
                              int accumulate, void* workspace, cudaStream_t stream) {
-    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, pool);
+    long long bins = 0;
+    for (int h = 0; h < heads; ++h) bins += (long long)pools[h] * pools[h];
+    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, bins);
     GatherParams g = {};
     int base = 0;
     for (int l = 3; l >= 0; --l) {  // coarse levels first: their units collect the most work
@@ -953,20 +963,27 @@ static int launch_bwd_gather(const float* grads, const int H[4], const int W[4],
     g.units = base;
     g.rule = make_level_rule(image_area);
     g.B = B; g.C = C; g.N = N;
-    g.ph = pool; g.pw = pool;
-    g.boxes = boxes; g.box_index = box_index; g.grads = grads;
+    g.boxes = boxes; g.box_index = box_index;
+    g.grads = grads[0]; g.grads2 = grads[heads - 1];
     g.cnt = ws.cnt; g.pos = ws.pos; g.cursor = ws.cursor; g.items = ws.items;
     g.err = device_error_word();
     MRCNN_CUDA(cudaMemsetAsync(workspace, 0, ws.clear_bytes, stream));
-    const long long walkers = (long long)N * pool * 2;
-    const unsigned wgrid = (unsigned)((walkers + 255) / 256);
     const unsigned ugrid = (unsigned)((g.units + 255) / 256);
-    bwd_items_kernel<false><<<wgrid, 256, 0, stream>>>(g);
-    MRCNN_LAUNCH_CHECK();
-    bwd_alloc_kernel<<<ugrid, 256, 0, stream>>>(g);
-    MRCNN_LAUNCH_CHECK();
-    bwd_items_kernel<true><<<wgrid, 256, 0, stream>>>(g);
-    MRCNN_LAUNCH_CHECK();
+    for (int pass = 0; pass < 2; ++pass) {  // count every head, allocate, fill every head
+        for (int h = 0; h < heads; ++h) {
+            g.ph = pools[h]; g.pw = pools[h];
+            g.head_flag = h ? kOHead2 : 0;
+            const long long walkers = (long long)N * pools[h] * 2;
+            const unsigned wgrid = (unsigned)((walkers + 255) / 256);
+            if (pass == 0) bwd_items_kernel<false><<<wgrid, 256, 0, stream>>>(g);
+            else bwd_items_kernel<true><<<wgrid, 256, 0, stream>>>(g);
+            MRCNN_LAUNCH_CHECK();
+        }
+        if (pass == 0) {
+            bwd_alloc_kernel<<<ugrid, 256, 0, stream>>>(g);
+            MRCNN_LAUNCH_CHECK();
+        }
+    }
     const bool wide = (C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
     const unsigned grid = (unsigned)g.units;
     // U = 2 items per stage, ST = 4 stages: best of the (U, ST) grid measured on B200 (profiles/r01_*gather*)
@@ -993,7 +1010,7 @@ size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const in
     if (!H || !W || B <= 0 || N < 0 || pool <= 0) return 256;
     for (int l = 0; l < 4; ++l)
         if (H[l] <= 0 || W[l] <= 0) return 256;
-    return carve_gather(nullptr, H, W, B, N, pool).bytes;
+    return carve_gather(nullptr, H, W, B, N, (long long)pool * pool).bytes;
 }
 
 int mrcnn_crop_forward(const float* image, int B, int C, int H, int W, int image_layout, const float* boxes,
@@ -1110,7 +1127,7 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
     MRCNN_REQUIRE(algo == MRCNN_BWD_AUTO || algo == MRCNN_BWD_GATHER || algo == MRCNN_BWD_SCATTER,
                   "mrcnn_pyramid_roi_align_backward: unknown algo %d", algo);
     const bool can_gather = image_offsets_host == nullptr &&
-                            gather_eligible(H, W, B, C, N, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
+                            gather_eligible(H, W, B, C, N, (long long)pool * pool, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
     if (algo == MRCNN_BWD_GATHER)
         MRCNN_REQUIRE(can_gather,
                       "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs channels-last grads and gfm, C %% 4 == 0, "
@@ -1118,7 +1135,9 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
                       "mrcnn_pyramid_roi_align_backward_workspace_bytes()");
     if (can_gather && algo != MRCNN_BWD_SCATTER) {
         // tile-owner gather: writes every pixel once (zero fill included), no atomics
-        return launch_bwd_gather(grads, H, W, B, C, boxes, box_index, N, pool, image_area, gfm, zero_fill ? 0 : 1, workspace,
+        const float* const gr[2] = {grads, grads};
+        const int pools[2] = {pool, pool};
+        return launch_bwd_gather(1, gr, pools, H, W, B, C, boxes, box_index, N, image_area, gfm, zero_fill ? 0 : 1, workspace,
                                  stream);
     }
     if (image_offsets_host == nullptr) {
@@ -1156,6 +1175,42 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
         if (int rc = launch_roi(p, gfm_layout, grads_layout, true, stream)) return rc;
     }
     return MRCNN_OK;
+}
+
+size_t mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(const int H[4], const int W[4], int B, int N, int pool_a,
+                                                             int pool_b) {
+    if (!H || !W || B <= 0 || N < 0 || pool_a <= 0 || pool_b <= 0) return 256;
+    for (int l = 0; l < 4; ++l)
+        if (H[l] <= 0 || W[l] <= 0) return 256;
+    return carve_gather(nullptr, H, W, B, N, (long long)pool_a * pool_a + (long long)pool_b * pool_b).bytes;
+}
+
+int mrcnn_pyramid_roi_align_backward_pair(const float* grads_a, int pool_a, const float* grads_b, int pool_b, const int H[4],
+                                          const int W[4], int B, int C, const float* boxes, const int32_t* box_index, int N,
+                                          float image_area, float* const gfm[4], int zero_fill, void* workspace,
+                                          size_t workspace_bytes, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward_pair: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N > 0 && pool_a > 0 && pool_b > 0 && image_area > 0.f,
+                  "mrcnn_pyramid_roi_align_backward_pair: bad sizes");
+    for (int l = 0; l < 4; ++l) {
+        MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_backward_pair: level %d has empty shape", l);
+        MRCNN_REQUIRE_DEV(gfm[l]);
+    }
+    MRCNN_REQUIRE_DEV(grads_a);
+    MRCNN_REQUIRE_DEV(grads_b);
+    MRCNN_REQUIRE_DEV(boxes);
+    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    const long long bins = (long long)pool_a * pool_a + (long long)pool_b * pool_b;
+    const int max_pool = pool_a > pool_b ? pool_a : pool_b;
+    MRCNN_REQUIRE(gather_eligible(H, W, B, C, N, bins, max_pool, MRCNN_NHWC, MRCNN_NHWC, grads_a, gfm, workspace, workspace_bytes) &&
+                      aligned16(grads_b),
+                  "mrcnn_pyramid_roi_align_backward_pair: needs channels-last tensors, C %% 4 == 0, N * pool^2 * C < 2^31 and a "
+                  "256-byte aligned workspace of mrcnn_pyramid_roi_align_backward_pair_workspace_bytes()");
+    MRCNN_REQUIRE(device_error_word() != nullptr, "cannot allocate device error word");
+    const float* const gr[2] = {grads_a, grads_b};
+    const int pools[2] = {pool_a, pool_b};
+    return launch_bwd_gather(2, gr, pools, H, W, B, C, boxes, box_index, N, image_area, gfm, zero_fill ? 0 : 1, workspace,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -365,6 +365,37 @@ def mrn_refine(self, rpn_rois, probs, deltas, window):
         return None, None, None
     dets = dets[0, :d]
     return dets[:, 5].long().unsqueeze(0), dets[:, 4].unsqueeze(0), dets[:, :4].unsqueeze(0)
+
+
+def pyramid_roi_align_backward_pair(grad_a, grad_b, feature_shapes, boxes, box_ind, image_shape, out=None, accumulate=False):
+    """Both heads' RoIAlign backward in one pass: grad_a [N,C,pa,pa] and grad_b [N,C,pb,pb] (channels-last), the same
+    RoIs -> the SUM of the two gradient pyramids, [B,C,H_l,W_l] channels-last per level (what autograd accumulates after
+    the reference's per-head, per-level CropFunction.backward calls, model.py:778 + :889).  feature_shapes = the four
+    (B, C, H, W); `out` = four preallocated channels-last tensors (optional); accumulate adds to them."""
+    _require_cuda(grad_a, "grad_a", torch.float32)
+    _require_cuda(grad_b, "grad_b", torch.float32)
+    _require_cuda(boxes, "boxes", torch.float32)
+    if not (grad_a.is_contiguous(memory_format=torch.channels_last) and grad_b.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("pyramid_roi_align_backward_pair needs channels-last gradients")
+    N, C, pa = grad_a.shape[:3]
+    pb = grad_b.size(2)
+    if boxes.shape != (N, 4) or grad_b.shape[:2] != (N, C) or len(feature_shapes) != 4 or N == 0:
+        raise ValueError("grad_a [N,C,pa,pa], grad_b [N,C,pb,pb], boxes [N,4] with N > 0, four feature shapes")
+    B = int(feature_shapes[0][0])
+    Hs, Ws = [int(s[2]) for s in feature_shapes], [int(s[3]) for s in feature_shapes]
+    boxes = boxes.contiguous()
+    if box_ind is not None:
+        box_ind = _require_cuda(box_ind, "box_ind", torch.int32).contiguous()
+    h, w = float(image_shape[0]), float(image_shape[1])
+    with torch.cuda.device(grad_a.device):
+        gfm = out if out is not None else [_empty4((B, C, hh, ww), NHWC, grad_a) for hh, ww in zip(Hs, Ws)]
+        ws_bytes = lib.mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(_lib.i4(Hs), _lib.i4(Ws), B, N, pa, pb)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad_a.device)
+        check(lib.mrcnn_pyramid_roi_align_backward_pair(grad_a.data_ptr(), pa, grad_b.data_ptr(), pb, _lib.i4(Hs), _lib.i4(Ws), B, C,
+                                                        boxes.data_ptr(), _ptr(box_ind), N, h * w,
+                                                        _lib.vp4([g.data_ptr() for g in gfm]), 0 if accumulate else 1,
+                                                        ws.data_ptr(), ws_bytes, _stream()))
+    return gfm
 
 
 # ------------------------------------------------------------------------------------------------

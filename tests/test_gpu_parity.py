@@ -480,3 +480,29 @@ def test_detection_targets_batched_matches_oracle(ops, B, n_rois, n_gt, train_ro
         _check_targets((o_rois[b, :t], o_cls[b, :t], o_d[b, :t], o_m[b, :t]), want)
         assert float(o_rois[b, t:].abs().sum()) == 0.0 and int(o_cls[b, t:].abs().sum()) == 0 and float(o_m[b, t:].sum()) == 0.0
     ops.check_device_errors()
+
+
+@pytest.mark.parametrize("B,C,size,N", [(3, 256, 256, 150), (2, 96, 200, 90), (1, 512, 128, 40)])
+def test_pyramid_backward_pair_is_the_sum_of_both_heads(ops, B, C, size, N):
+    """One fused row-owner gather for the 7x7 and the 14x14 head == the sum of the two separate backward passes
+    (what autograd accumulates in the reference), and `accumulate` adds on top."""
+    fms = synth.feature_pyramid(B, C, 31 + B, image=size)
+    boxes = synth.random_rois(N, 32 + N, image=float(size), min_size=6, max_size=size * 0.9)
+    boxes[0] += 0.4
+    boxes[1] = boxes[1][[2, 3, 0, 1]]
+    ind = np.random.default_rng(N).integers(0, B, N).astype(np.int32)
+    rng = np.random.default_rng(9)
+    g7 = rng.standard_normal((N, C, 7, 7), dtype=np.float32)
+    g14 = rng.standard_normal((N, C, 14, 14), dtype=np.float32)
+    shapes = [f.shape for f in fms]
+    w7 = oracle.pyramid_roi_align_bwd(g7, shapes, boxes, ind, float(size * size))
+    w14 = oracle.pyramid_roi_align_bwd(g14, shapes, boxes, ind, float(size * size))
+    got = ops.pyramid_roi_align_backward_pair(cl(dev(g7)), cl(dev(g14)), shapes, dev(boxes), dev(ind), (size, size, 3))
+    for t, a, b in zip(got, w7, w14):
+        assert t.is_contiguous(memory_format=torch.channels_last)
+        assert rel_err(t.cpu().numpy(), a + b) <= BWD_TOL
+    again = ops.pyramid_roi_align_backward_pair(cl(dev(g7)), cl(dev(g14)), shapes, dev(boxes), dev(ind), (size, size, 3),
+                                                out=got, accumulate=True)
+    for t, a, b in zip(again, w7, w14):
+        assert rel_err(t.cpu().numpy(), 2 * (a + b)) <= BWD_TOL
+    ops.check_device_errors()
