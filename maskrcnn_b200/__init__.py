@@ -8,7 +8,7 @@
 All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.h).  No CPU fallback.
 """
 from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets,  # noqa: F401
-                  mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, roi_align,
+                  mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, pyramid_roi_align_pair, roi_align,
                   rpn_refine,
                   set_backward_algorithm)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401

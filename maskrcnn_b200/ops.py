@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -396,6 +396,57 @@ def pyramid_roi_align_backward_pair(grad_a, grad_b, feature_shapes, boxes, box_i
                                                         _lib.vp4([g.data_ptr() for g in gfm]), 0 if accumulate else 1,
                                                         ws.data_ptr(), ws_bytes, _stream()))
     return gfm
+
+
+class _PyramidRoiAlignPair(torch.autograd.Function):
+    """Both heads' crops from one autograd node, so that their backward is ONE fused gather."""
+
+    @staticmethod
+    def forward(ctx, boxes, box_ind, pool_a, pool_b, image_area, p2, p3, p4, p5):
+        fms, fl = _pyramid_layout([p2, p3, p4, p5])
+        if fl != NHWC:
+            raise ValueError("pyramid_roi_align_pair needs channels-last feature maps")
+        B, C = fms[0].shape[:2]
+        N = boxes.size(0)
+        Hs = [f.shape[2] for f in fms]
+        Ws = [f.shape[3] for f in fms]
+        outs = []
+        with torch.cuda.device(fms[0].device):
+            for pool in (pool_a, pool_b):
+                out = _empty4((N, C, pool, pool), NHWC, fms[0])
+                check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws), B, C, fl,
+                                                          boxes.data_ptr(), _ptr(box_ind), N, pool, float(image_area),
+                                                          out.data_ptr(), NHWC, None, _stream()))
+                outs.append(out)
+        ctx.save_for_backward(boxes, box_ind)
+        ctx.meta = ([tuple(f.shape) for f in fms], float(image_area), pool_a, pool_b)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, grad_a, grad_b):
+        boxes, box_ind = ctx.saved_tensors
+        shapes, image_area, pool_a, pool_b = ctx.meta
+        N, C = boxes.size(0), shapes[0][1]
+        cl = lambda g, p: (torch.zeros((N, C, p, p), device=boxes.device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+                           if g is None else g.contiguous(memory_format=torch.channels_last))
+        gfm = pyramid_roi_align_backward_pair(cl(grad_a, pool_a), cl(grad_b, pool_b), shapes, boxes, box_ind, (image_area, 1.0))
+        return (None, None, None, None, None) + tuple(gfm)
+
+
+def pyramid_roi_align_pair(feature_maps, boxes, box_ind, pool_sizes, image_shape):
+    """PyramidROIAlign of the same RoIs at two pool sizes (box head 7x7 + mask head 14x14, model.py:778 / :889) as ONE
+    autograd node: returns (crops_a, crops_b), channels-last, and backpropagates both heads with the fused gather
+    (one gradient-pyramid write instead of two plus autograd's add).  Channels-last feature maps, N > 0, C % 4 == 0."""
+    for i, f in enumerate(feature_maps):
+        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
+    _require_cuda(boxes, "boxes", torch.float32)
+    if boxes.dim() != 2 or boxes.size(1) != 4 or boxes.size(0) == 0 or len(pool_sizes) != 2:
+        raise ValueError("boxes must be [N,4] with N > 0 and pool_sizes a pair")
+    boxes = boxes.detach().contiguous()
+    if box_ind is not None:
+        box_ind = _require_cuda(box_ind, "box_ind", torch.int32).contiguous()
+    image_area = float(image_shape[0] * image_shape[1])
+    return _PyramidRoiAlignPair.apply(boxes, box_ind, int(pool_sizes[0]), int(pool_sizes[1]), image_area, *feature_maps)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -506,3 +506,25 @@ def test_pyramid_backward_pair_is_the_sum_of_both_heads(ops, B, C, size, N):
     for t, a, b in zip(again, w7, w14):
         assert rel_err(t.cpu().numpy(), 2 * (a + b)) <= BWD_TOL
     ops.check_device_errors()
+
+
+def test_pyramid_roi_align_pair_autograd(ops):
+    """Both heads from one autograd node: forwards bit-exact, the fused backward == sum of the two oracle backwards."""
+    B, C, size, N = 2, 128, 256, 120
+    fms = synth.feature_pyramid(B, C, 77, image=size)
+    boxes = synth.random_rois(N, 78, image=float(size), min_size=6, max_size=size * 0.9)
+    ind = np.random.default_rng(5).integers(0, B, N).astype(np.int32)
+    ts = [cl(dev(f)).requires_grad_(True) for f in fms]
+    o7, o14 = ops.pyramid_roi_align_pair(ts, dev(boxes), dev(ind), (7, 14), (size, size, 3))
+    w7, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, 7, float(size * size))
+    w14, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, 14, float(size * size))
+    np.testing.assert_array_equal(o7.detach().cpu().numpy(), w7)
+    np.testing.assert_array_equal(o14.detach().cpu().numpy(), w14)
+    rng = np.random.default_rng(6)
+    g7, g14 = rng.standard_normal(w7.shape, dtype=np.float32), rng.standard_normal(w14.shape, dtype=np.float32)
+    (o7 * dev(g7)).sum().add((o14 * dev(g14)).sum()).backward()
+    shapes = [f.shape for f in fms]
+    a = oracle.pyramid_roi_align_bwd(g7, shapes, boxes, ind, float(size * size))
+    b = oracle.pyramid_roi_align_bwd(g14, shapes, boxes, ind, float(size * size))
+    for t, x, y in zip(ts, a, b):
+        assert rel_err(t.grad.cpu().numpy(), x + y) <= BWD_TOL
