@@ -520,6 +520,28 @@ def secondary(torch, wl, hbm):
                                 "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
                                 "note": "3 launches (classify, select, emit); latency-bound: ~4 MB per image"}
     del t_masks
+    # RPN anchor matching (data.rpn_samples), 261,888 anchors x 20 gt boxes
+    import types
+    anc64 = torch.from_numpy(synth.pyramid_anchors((IMAGE, IMAGE)).astype(np.float64)).to(dev)
+    r_cls, r_gt = synth.rpn_target_inputs(20, 77, image=IMAGE, n_crowd=1)
+    r_cls_d, r_gt_d = torch.from_numpy(r_cls).to(dev), torch.from_numpy(r_gt).to(dev)
+    rcfg = types.SimpleNamespace(RPN_TRAIN_ANCHORS_PER_IMAGE=256, RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]))
+    A_ = anc64.size(0)
+    mt_, am_ = torch.empty(A_, dtype=torch.int32, device=dev), torch.empty(A_, dtype=torch.int32, device=dev)
+    wsr = torch.empty(L.lib.mrcnn_rpn_match_workspace_bytes(20), dtype=torch.uint8, device=dev)
+    fk = lambda: L.check(L.lib.mrcnn_rpn_match(anc64.data_ptr(), A_, r_gt_d.data_ptr(), r_cls_d.data_ptr(), 20, mt_.data_ptr(),  # noqa: E731
+                                               am_.data_ptr(), wsr.data_ptr(), wsr.numel(), wl._s()))
+    tk = wl.time_op(fk, iters=20)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        m.rpn_samples(anc64, r_cls_d, r_gt_d, rcfg)
+    torch.cuda.synchronize()
+    td = (time.perf_counter() - t0) / 10
+    out["rpn_anchor_matching"] = {"config": "data.rpn_samples (SURVEY 8f): %d anchors x 20 gt boxes, 256 anchors kept" % A_,
+                                  "match_kernels_us": tk * 1e6, "match_algorithmic_GBps": (A_ * 40 + 20 * 20) / tk / 1e9,
+                                  "dropin_images_per_s": 1.0 / td, "dropin_ms": td * 1e3,
+                                  "note": "drop-in = reference semantics incl. three count read-backs and np.random draws on the host"}
     # configs[2]: forward only, 1000 RoIs x 256 ch on one image
     boxes_np = synth.random_rois(1000, 1234)
     boxes = torch.from_numpy(boxes_np).to(dev)

@@ -199,6 +199,33 @@ MRCNN_API int mrcnn_target_emit(const float* rois, const float* gt_boxes, const 
                                 int mask_w, int T, float* rois_out, int32_t* class_out, float* deltas_out,
                                 float* masks_out, mrcnn_stream_t stream);
 
+/* ---- RPN anchor matching (replaces data.rpn_samples, data.py:449-591) ------------------------------------------ */
+
+/* Steps 1-3 (data.py:495-535): anchors float64 [A,4] px, gt_boxes int32 [G,4] px, gt_class_ids int32 [G] (< 0 crowd).
+ * match int32 [A]: -1 (max IoU < 0.3 and not on a crowd), +1 (max IoU >= 0.7, or the best anchor of a gt box), 0
+ * neutral - BEFORE subsampling; argmax int32 [A] = gt row of the max IoU (first maximum, np.argmax).  IoU is fp32 as in
+ * data.boxes_overlaps (data.py:151-189).  workspace: mrcnn_rpn_match_workspace_bytes(G), 8-byte aligned. */
+MRCNN_API size_t mrcnn_rpn_match_workspace_bytes(int G);
+MRCNN_API int mrcnn_rpn_match(const double* anchors, int A, const int32_t* gt_boxes, const int32_t* gt_class_ids, int G,
+                              int32_t* match, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                              mrcnn_stream_t stream);
+
+/* np.where(values == target)[0] on the device: ids_out int32 [n] receives the ascending indices, count_out (device
+ * int32) their number.  workspace: mrcnn_compact_equal_workspace_bytes(n). */
+MRCNN_API size_t mrcnn_compact_equal_workspace_bytes(int n);
+MRCNN_API int mrcnn_compact_equal(const int32_t* values, int n, int32_t target, int32_t* ids_out, int32_t* count_out,
+                                  void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+/* values[ids[perm[t]]] = fill for t < count: resets the anchors np.random.choice picked (data.py:543-553). */
+MRCNN_API int mrcnn_scatter_fill(int32_t* values, const int32_t* ids, const int32_t* perm, int count, int32_t fill,
+                                 mrcnn_stream_t stream);
+
+/* data.py:557-589: float64 deltas / std for the positive anchors ids[0..*count) (ascending), rows up to T zero;
+ * rpn_bbox_out float64 [T,4], 32-byte aligned. */
+MRCNN_API int mrcnn_rpn_deltas(const double* anchors, const int32_t* gt_boxes, const int32_t* argmax, const int32_t* ids,
+                               const int32_t* count, int T, const double* std4_host, double* rpn_bbox_out,
+                               mrcnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

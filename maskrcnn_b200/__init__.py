@@ -2,6 +2,7 @@
 
     nms, CropFunction                      drop-ins for c++ext/maskrcnn/__init__.py
     roi_align, rpn_refine, mrn_refine, mrn_samples   drop-ins for the model.py functions that call them
+    rpn_samples                            drop-in for data.rpn_samples (RPN anchor matching)
     pyramid_roi_align, proposal_layer, detection_layer, detection_targets   batched, sync-free variants
     patch(model_module)                    swaps the fused versions into an unmodified reference model.py
 
@@ -9,7 +10,7 @@ All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.
 """
 from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets,  # noqa: F401
                   mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, pyramid_roi_align_pair, roi_align,
-                  rpn_refine,
+                  rpn_refine, rpn_samples,
                   set_backward_algorithm)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 

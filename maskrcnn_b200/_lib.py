@@ -31,6 +31,12 @@ SIGNATURES = {
     "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "mrcnn_pyramid_roi_align_backward_pair_workspace_bytes": (_sz, [_i4, _i4, _i, _i, _i, _i]),
     "mrcnn_pyramid_roi_align_backward_pair": (_i, [_vp, _i, _vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _f, _vp4, _i, _vp, _sz, _vp]),
+    "mrcnn_rpn_match_workspace_bytes": (_sz, [_i]),
+    "mrcnn_rpn_match": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_compact_equal_workspace_bytes": (_sz, [_i]),
+    "mrcnn_compact_equal": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_scatter_fill": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mrcnn_rpn_deltas": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_double * 4, _vp, _vp]),
     "mrcnn_target_classify": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mrcnn_target_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mrcnn_target_emit": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f4, _i, _i, _i, _vp, _vp, _vp,

@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -559,3 +559,63 @@ def mrn_samples(rpn_rois, gt_class_ids, gt_boxes, gt_masks, config):
                                                np.asarray(config.BBOX_STD_DEV, dtype=np.float32).reshape(4), config.MASK_SHAPE,
                                                tp + tn)
     return o_rois[0], o_cls[0], o_d[0], o_m[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# RPN anchor matching
+# ------------------------------------------------------------------------------------------------
+def _compact_equal(values, target):
+    n = values.numel()
+    ids = torch.empty(n, dtype=torch.int32, device=values.device)
+    count = torch.empty(1, dtype=torch.int32, device=values.device)
+    ws_bytes = lib.mrcnn_compact_equal_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=values.device)
+    check(lib.mrcnn_compact_equal(values.data_ptr(), n, int(target), ids.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return ids, count
+
+
+def rpn_samples(anchors, gt_class_ids, gt_boxes, config, device=None, return_tensors=False):
+    """Drop-in for data.rpn_samples (data.py:449-591): anchors [A,4] float64 px, gt_class_ids [G] int32, gt_boxes [G,4]
+    int32 px (numpy arrays like the reference's, or CUDA tensors - pass the anchors as a CUDA float64 tensor to avoid
+    re-uploading them for every sample) -> (rpn_match int32 [A], rpn_bbox float64 [RPN_TRAIN_ANCHORS_PER_IMAGE, 4]),
+    numpy like the reference's unless return_tensors.  The two subsampling draws use np.random.permutation, which is what
+    the reference's np.random.choice(ids, extra, replace=False) draws, so a seeded run returns the reference's result."""
+    dev = torch.device(device) if device is not None else (anchors.device if isinstance(anchors, torch.Tensor) else torch.device("cuda"))
+    if dev.type != "cuda":
+        raise TypeError("rpn_samples runs on a CUDA device: maskrcnn_b200 has no CPU path")
+
+    def to_dev(x, dtype):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        return t.to(device=dev, dtype=dtype).contiguous()
+    anc, cls, gtb = to_dev(anchors, torch.float64), to_dev(gt_class_ids, torch.int32), to_dev(gt_boxes, torch.int32)
+    A, G = anc.size(0), gtb.size(0)
+    T = int(config.RPN_TRAIN_ANCHORS_PER_IMAGE)
+    std = np.asarray(config.RPN_BBOX_STD_DEV, dtype=np.float64).reshape(4)
+    with torch.cuda.device(dev):
+        match = torch.empty(A, dtype=torch.int32, device=dev)
+        argmax = torch.empty(A, dtype=torch.int32, device=dev)
+        ws_bytes = lib.mrcnn_rpn_match_workspace_bytes(G)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.mrcnn_rpn_match(anc.data_ptr(), A, gtb.data_ptr(), cls.data_ptr(), G, match.data_ptr(), argmax.data_ptr(),
+                                  ws.data_ptr(), ws_bytes, _stream()))
+        # subsample (data.py:538-553); the counts are read back like the reference's np.where does implicitly
+        ids, count = _compact_equal(match, 1)
+        n_pos = int(count.item())
+        extra = n_pos - T // 2
+        if extra > 0:
+            perm = torch.from_numpy(np.random.permutation(n_pos)[:extra].astype(np.int32)).to(dev)
+            check(lib.mrcnn_scatter_fill(match.data_ptr(), ids.data_ptr(), perm.data_ptr(), extra, 0, _stream()))
+            n_pos -= extra
+        ids, count = _compact_equal(match, -1)
+        n_neg = int(count.item())
+        extra = n_neg - (T - n_pos)
+        if extra > 0:
+            perm = torch.from_numpy(np.random.permutation(n_neg)[:extra].astype(np.int32)).to(dev)
+            check(lib.mrcnn_scatter_fill(match.data_ptr(), ids.data_ptr(), perm.data_ptr(), extra, 0, _stream()))
+        ids, count = _compact_equal(match, 1)
+        bbox = torch.empty((T, 4), dtype=torch.float64, device=dev)
+        check(lib.mrcnn_rpn_deltas(anc.data_ptr(), gtb.data_ptr(), argmax.data_ptr(), ids.data_ptr(), count.data_ptr(), T,
+                                   (ctypes.c_double * 4)(*[float(v) for v in std]), bbox.data_ptr(), _stream()))
+    if return_tensors:
+        return match, bbox
+    return match.cpu().numpy(), bbox.cpu().numpy()

@@ -152,3 +152,14 @@ def target_inputs(n_rois, n_gt, seed, image=1024, n_crowd=0, n_pad=0, positive_f
         cy, cx, ry, rx = (y1 + y2) / 2, (x1 + x2) / 2, max((y2 - y1) / 2, 1.0), max((x2 - x1) / 2, 1.0)
         masks[g] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0).astype(np.float32)
     return rois.astype(np.float32), cls, gt.astype(np.float32), masks
+
+
+def rpn_target_inputs(n_gt, seed, image=1024, n_crowd=0):
+    """gt boxes in pixels (int32, as the dataset yields them) + class ids for the RPN anchor matching (data.py:449)."""
+    rng = np.random.default_rng(seed)
+    gt = np.round(random_rois(n_gt, seed + 1, image=float(image), min_size=image / 32.0, max_size=image * 0.7) * image).astype(np.int32)
+    gt[:, 2:] = np.maximum(gt[:, 2:], gt[:, :2] + 2)
+    cls = rng.integers(1, 81, n_gt).astype(np.int32)
+    if n_crowd:
+        cls[rng.choice(n_gt, n_crowd, replace=False)] = -1
+    return cls, gt

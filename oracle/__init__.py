@@ -57,6 +57,11 @@ def lib():
         L.orc_proposal_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_float, _f32p, ctypes.c_float,
                                          ctypes.c_float, _f32p, _f32p, _i64p]
+        _f64p = ctypes.POINTER(ctypes.c_double)
+        L.orc_rpn_match.restype = None
+        L.orc_rpn_match.argtypes = [_f64p, ctypes.c_int64, _i32p, _i32p, ctypes.c_int64, _i32p, _i32p]
+        L.orc_rpn_deltas.restype = None
+        L.orc_rpn_deltas.argtypes = [_f64p, _i32p, _i32p, _i64p, ctypes.c_int64, _f64p, _f64p]
         L.orc_target_classify.restype = None
         L.orc_target_classify.argtypes = [_f32p, ctypes.c_int64, _f32p, _i32p, ctypes.c_int64, _i64p, _i64p, _i32p, _f32p, _i64p]
         L.orc_target_emit.restype = None
@@ -272,3 +277,31 @@ def mrn_samples(rois, gt_class_ids, gt_boxes, gt_masks, train_rois_per_image, ro
         r = 1.0 / roi_positive_ratio
         sel_neg = neg[np.asarray(randperm(len(neg)), np.int64)[:int(r * len(sel_pos) - len(sel_pos))]]
     return target_emit(rois, gt_class_ids, gt_boxes, gt_masks, sel_pos, sel_neg, assign, std_dev, mask_shape)
+
+
+def rpn_samples(anchors, gt_class_ids, gt_boxes, train_anchors_per_image, std_dev, permutation):
+    """data.py:449-591.  anchors float64 [A,4] px, gt_boxes int32 [G,4] px.  `permutation(n)` stands for the draws inside
+    the reference's two np.random.choice(ids, extra, replace=False) calls (= ids[permutation(len(ids))[:extra]]), in the
+    reference's order: positives (:543) then negatives (:552).  Returns (rpn_match int32 [A], rpn_bbox float64 [T,4])."""
+    f64p = ctypes.POINTER(ctypes.c_double)
+    anchors = np.ascontiguousarray(anchors, np.float64)
+    gtb = np.ascontiguousarray(gt_boxes, np.int32)
+    cls = np.ascontiguousarray(gt_class_ids, np.int32)
+    A, G = len(anchors), len(gtb)
+    match, argmax = np.zeros(A, np.int32), np.zeros(A, np.int32)
+    lib().orc_rpn_match(anchors.ctypes.data_as(f64p), A, _p(gtb, _i32p), _p(cls, _i32p), G, _p(match, _i32p), _p(argmax, _i32p))
+    T = int(train_anchors_per_image)
+    ids = np.where(match == 1)[0]
+    extra = len(ids) - T // 2
+    if extra > 0:
+        match[ids[np.asarray(permutation(len(ids)))[:extra]]] = 0
+    ids = np.where(match == -1)[0]
+    extra = len(ids) - (T - int(np.sum(match == 1)))
+    if extra > 0:
+        match[ids[np.asarray(permutation(len(ids)))[:extra]]] = 0
+    ids = np.ascontiguousarray(np.where(match == 1)[0], np.int64)
+    bbox = np.zeros((T, 4), np.float64)
+    std = np.ascontiguousarray(std_dev, np.float64)
+    lib().orc_rpn_deltas(anchors.ctypes.data_as(f64p), _p(gtb, _i32p), _p(argmax, _i32p), _p(ids, _i64p), len(ids),
+                         std.ctypes.data_as(f64p), bbox.ctypes.data_as(f64p))
+    return match, bbox

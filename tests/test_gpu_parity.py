@@ -528,3 +528,44 @@ def test_pyramid_roi_align_pair_autograd(ops):
     b = oracle.pyramid_roi_align_bwd(g14, shapes, boxes, ind, float(size * size))
     for t, x, y in zip(ts, a, b):
         assert rel_err(t.grad.cpu().numpy(), x + y) <= BWD_TOL
+
+
+# ------------------------------------------------------------------ RPN anchor matching (data.rpn_samples)
+def _f64_ulp(a, b):
+    return np.abs(np.ascontiguousarray(a).view(np.int64) - np.ascontiguousarray(b).view(np.int64)).max() if a.size else 0
+
+
+@pytest.mark.parametrize("image,n_gt,n_crowd,T,seed", [(1024, 20, 0, 256, 1), (1024, 40, 3, 256, 2), (512, 5, 1, 64, 3), (256, 1, 0, 32, 4),
+                                                       (1024, 100, 5, 512, 5)])
+def test_rpn_samples_matches_oracle(ops, image, n_gt, n_crowd, T, seed):
+    """ops.rpn_samples (reference signature, numpy in / numpy out) vs the oracle under the same numpy seed; 261,888 anchors
+    at 1024^2."""
+    import types
+    anchors = synth.pyramid_anchors((image, image)).astype(np.float64)
+    cls, gt = synth.rpn_target_inputs(n_gt, 50 + seed, image=image, n_crowd=n_crowd)
+    cfg = types.SimpleNamespace(RPN_TRAIN_ANCHORS_PER_IMAGE=T, RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]))
+    np.random.seed(seed)
+    w_match, w_bbox = oracle.rpn_samples(anchors, cls, gt, T, [0.1, 0.1, 0.2, 0.2], np.random.permutation)
+    np.random.seed(seed)
+    g_match, g_bbox = ops.rpn_samples(anchors, cls, gt, cfg)
+    assert g_match.dtype == np.int32 and g_bbox.dtype == np.float64 and g_bbox.shape == (T, 4)
+    np.testing.assert_array_equal(g_match, w_match)
+    assert (g_match == 1).sum() >= 1 and (g_match == 1).sum() <= T // 2 and (g_match != 0).sum() <= T
+    np.testing.assert_array_equal(g_bbox[:, :2], w_bbox[:, :2])
+    assert _f64_ulp(g_bbox[:, 2:], w_bbox[:, 2:]) <= 2          # float64 log: CUDA's vs libm's
+    ops.check_device_errors()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_rpn_samples_golden(ops, tag):
+    import os
+    import types
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_rpn_v1.npz"))
+    image = int(g[f"{tag}_in_image"])
+    anchors = torch.from_numpy(synth.pyramid_anchors((image, image)).astype(np.float64)).cuda()    # anchors resident on the device
+    cfg = types.SimpleNamespace(RPN_TRAIN_ANCHORS_PER_IMAGE=int(g[f"{tag}_in_T"]), RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]))
+    np.random.seed(int(g[f"{tag}_in_seed"]))
+    match, bbox = ops.rpn_samples(anchors, g[f"{tag}_in_cls"], g[f"{tag}_in_gt"], cfg)
+    np.testing.assert_array_equal(match, g[f"{tag}_out_match"].astype(np.int32))
+    np.testing.assert_array_equal(bbox[:, :2], g[f"{tag}_out_bbox"][:, :2])
+    assert _f64_ulp(bbox[:, 2:], g[f"{tag}_out_bbox"][:, 2:]) <= 2

@@ -214,3 +214,24 @@ def test_target_layer_no_positive():
                               torch.from_numpy(masks)[None], cfg)
     g = oracle.mrn_samples(rois, cls, gt, masks, 64, 0.33, [0.1, 0.1, 0.2, 0.2], (28, 28), lambda n: torch.randperm(n).numpy())
     assert all(t.numel() == 0 for t in w) and all(len(a) == 0 for a in g)   # model.py:563-574
+
+
+@needs_model
+@pytest.mark.parametrize("image,n_gt,n_crowd,train_anchors,seed", [(256, 6, 0, 256, 1), (256, 9, 2, 64, 2), (512, 15, 1, 256, 3), (128, 1, 0, 32, 4)])
+def test_rpn_samples_matches_data_py(image, n_gt, n_crowd, train_anchors, seed):
+    """data.rpn_samples (unmodified numpy code) vs the oracle under the same numpy seed: the oracle's permutation callback
+    is np.random.permutation, which is what np.random.choice(ids, extra, replace=False) draws internally."""
+    ref = reference.load()
+    import types
+    anchors = synth.pyramid_anchors((image, image)).astype(np.float64)
+    cls, gt = synth.rpn_target_inputs(n_gt, seed, image=image, n_crowd=n_crowd)
+    cfg = types.SimpleNamespace(RPN_TRAIN_ANCHORS_PER_IMAGE=train_anchors, RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]))
+    np.random.seed(200 + seed)
+    w_match, w_bbox = ref.data.rpn_samples(anchors, cls, gt, cfg)
+    np.random.seed(200 + seed)
+    g_match, g_bbox = oracle.rpn_samples(anchors, cls, gt, train_anchors, [0.1, 0.1, 0.2, 0.2], np.random.permutation)
+    np.testing.assert_array_equal(g_match, w_match)
+    assert (g_match == 1).sum() >= 1 and (g_match == -1).sum() >= 1
+    np.testing.assert_array_equal(g_bbox[:, :2], w_bbox[:, :2])
+    a, b = g_bbox[:, 2:].view(np.int64), w_bbox[:, 2:].view(np.int64)
+    assert np.abs(a - b).max() <= 2      # float64 log: numpy's vs libm's
