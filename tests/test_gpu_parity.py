@@ -247,6 +247,39 @@ def test_roialign_linearity_full_size(ops):
         assert err <= 1e-5 * yab.abs().max().item()
 
 
+@pytest.mark.parametrize("algo", ["gather", "scatter"])
+def test_roialign_adjoint_full_size(ops, algo):
+    """Size-independent property at BASELINE configs[3] size (batch 16 x 512 RoIs x 256 ch, 1024^2 pyramid, 7x7 and 14x14):
+    the backward is the adjoint of the forward, <RoIAlign(x), g> == <x, RoIAlign^T(g)>, for both backward algorithms; and
+    the fused two-head backward equals the sum of the two single-head ones."""
+    torch.manual_seed(1)
+    B, C = 16, 256
+    boxes = dev(np.concatenate([synth.random_rois(512, 2000 + i) for i in range(B)]))
+    ind = torch.arange(B, dtype=torch.int32, device="cuda").repeat_interleave(512)
+    ops.set_backward_algorithm(algo)
+    grads = {}
+    try:
+        for pool in (7, 14):
+            x = [cl(torch.randn(B, C, s, s, device="cuda")).requires_grad_(True) for s in (256, 128, 64, 32)]
+            y = ops.pyramid_roi_align(x, boxes, ind, pool, (1024, 1024, 3))
+            g = cl(torch.randn_like(y))
+            lhs = (y.double() * g.double()).sum().item()
+            y.backward(g)
+            rhs = sum((t.detach().double() * t.grad.double()).sum().item() for t in x)
+            scale = (y.double() * g.double()).pow(2).sum().sqrt().item()    # size of a random-sign sum of these terms
+            assert abs(lhs - rhs) <= 1e-5 * scale
+            grads[pool] = (g, [t.grad for t in x])
+            del x, y
+    finally:
+        ops.set_backward_algorithm("auto")
+    if algo == "gather":
+        shapes = [tuple(t.shape) for t in grads[7][1]]
+        both = ops.pyramid_roi_align_backward_pair(grads[7][0], grads[14][0], shapes, boxes, ind, (1024, 1024, 3))
+        for t, a, b in zip(both, grads[7][1], grads[14][1]):
+            ref = a + b
+            assert (t - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
 # ------------------------------------------------------------------ proposal layer
 @pytest.mark.parametrize("size,pre,post,B", [(256, 500, 200, 1), (256, 1000, 300, 3), (512, 6000, 1000, 2), (128, 6000, 1000, 2)])
 def test_proposal_layer_matches_oracle(ops, size, pre, post, B):
