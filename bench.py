@@ -707,8 +707,8 @@ def main():
         U14, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 14, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
         pyr = wl.batch * PYR_ELEMS_PER_IMAGE
         ops = {
-            "roialign_fwd_nhwc_kernel<7,nhwc>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
-            "roialign_fwd_nhwc_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
+            "roialign_fwd_nhwc_col_kernel<7,nhwc>": (lambda: wl.fwd(7, wl.out7), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7)),
+            "roialign_fwd_nhwc_col_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
             "bwd_items x2+bwd_alloc+roialign_bwd_gather_kernel<7,nhwc>": (lambda: wl.bwd(7, wl.g7, wl.gfm7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
             "bwd_items x2+bwd_alloc+roialign_bwd_gather_kernel<14,nhwc>": (lambda: wl.bwd(14, wl.g14, wl.gfm14), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
