@@ -261,11 +261,13 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
 // 67 % with as many shared-memory wavefronts (tap loads) as global ones - this variant removes three quarters of them.
 // Pool 14: 14 of the 16 slots own a column; pool 7: 2 row phases x 7 columns.
 // ------------------------------------------------------------------------------------------------
-template <int POOL, int LANES>  // LANES float4 lanes per bin: the CTA covers 4 * LANES channels with kSlots * LANES threads
-__global__ void __launch_bounds__(kSlots * LANES, 1024 / (kSlots * LANES)) roialign_fwd_nhwc_col_kernel(const RoiParams p) {
+// The CTA covers 4 * LANES channels with SLOTS * LANES threads (small CTAs: more of them resident, so the
+// box -> taps -> barrier prologue of one overlaps the streaming of the others).
+template <int POOL, int LANES, int SLOTS>
+__global__ void __launch_bounds__(SLOTS * LANES, 1024 / (SLOTS * LANES)) roialign_fwd_nhwc_col_kernel(const RoiParams p) {
     __shared__ TapS s_ty[kMaxPool];
     __shared__ TapS s_tx[kMaxPool];
-    constexpr int kPhases = kSlots / POOL;  // rows handled in parallel by different slots
+    constexpr int kPhases = SLOTS / POOL;  // rows handled in parallel by different slots
     static_assert(kPhases >= 1, "pool must not exceed the slot count");
 
     // the channel chunks of one RoI are adjacent in launch order: their 256-byte pieces of the same 1 KB output rows
@@ -924,8 +926,11 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
                 // 16 lanes (64 channels) per CTA measured best on B200: 8 -> 504 us, 16 -> 468 us, 32 -> 490 us, 64 -> 509 us (14x14)
                 const long long flat = (long long)grid.x * grid.y;
                 const bool ok = flat < (1ll << 31);
-                if (ok && p.ph == 7 && p.pw == 7) roialign_fwd_nhwc_col_kernel<7, kLanes><<<(unsigned)flat, kThreads, 0, stream>>>(p);
-                else if (ok && p.ph == 14 && p.pw == 14) roialign_fwd_nhwc_col_kernel<14, kLanes><<<(unsigned)flat, kThreads, 0, stream>>>(p);
+                // pool 7: 128-thread CTAs (7 of 8 slots own a column): 210 -> 178 us, more CTAs resident hide the prologue;
+                // pool 14: 256 threads, 14 of 16 slots; splitting its columns (rows) over two CTAs measured 474 (543) vs 468 us
+                if (ok && p.ph == 7 && p.pw == 7) roialign_fwd_nhwc_col_kernel<7, kLanes, 8><<<(unsigned)flat, 8 * kLanes, 0, stream>>>(p);
+                else if (ok && p.ph == 14 && p.pw == 14)
+                    roialign_fwd_nhwc_col_kernel<14, kLanes, kSlots><<<(unsigned)flat, kThreads, 0, stream>>>(p);
                 else MRCNN_LAUNCH_NHWC((roialign_fwd_nhwc_kernel<0, true>));
             } else MRCNN_DISPATCH_POOL(roialign_fwd_nhwc_kernel, false);
         } else {
