@@ -448,6 +448,24 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end
+    leg are first-touched on the GPU's own NUMA node (8 ranks sharing one node's memory channels cap the host link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber the devices: go through the PCI address
+            import torch
+            pr = torch.cuda.get_device_properties(local)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:  # no NVML / not permitted: keep the inherited affinity
+        return None
+
+
 def ncu_traffic():
     """DRAM bytes per launch of each timed op, from the newest committed ncu summary (profiles/rNN_traffic.json):
     {capture name: MB summed over the kernels the op launches}."""
@@ -684,6 +702,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm, peak_src = hbm_peak()
@@ -733,6 +752,7 @@ def main():
                             "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
                             "kernels": kern}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)
+        line["e2e"]["host_cpus_bound"] = (len(numa) if numa else None)
         line["detection_path_sharded"] = sharded_detection(torch, dist, wl, world, rank, hbm)
         line["rpn_nms"] = rpn_nms(torch, dist, wl, world, rank, hbm)
         if rank == 0 and world == 1:
