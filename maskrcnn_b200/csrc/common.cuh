@@ -139,6 +139,35 @@ __device__ __forceinline__ void box_refine(const float b[4], const float d[4], f
 
 // IoU >= threshold test with the +1 pixel convention, cpu/nms_cpu.cpp:26, :56-65.
 // Boxes are (y1,x1,y2,x2); areas precomputed as ((x2-x1)+1)*((y2-y1)+1).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// `margin` = |thr| * 1e-6 + 1e-37 (hoist it out of loops).  The decision is that of the correctly rounded quotient
+// (NaN -> false, kept, as on the CPU): a ~2-ulp approximate quotient settles it unless it lands within ~8 ulp of the
+// threshold or the denominator is outside the range where the approximation holds; only then divide exactly.
+// Branch-free up to that rare fallback (disjoint boxes give q = 0 < thr - margin).
+__device__ __forceinline__ bool iou_ge_m(const float4 a, float area_a, const float4 b, float area_b, float thr, float margin) {
+    const float yy1 = fmaxf(a.x, b.x);
+    const float xx1 = fmaxf(a.y, b.y);
+    const float yy2 = fminf(a.z, b.z);
+    const float xx2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+    const float inter = __fmul_rn(w, h);
+    const float denom = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float q = __fmul_rn(inter, rcp_approx(denom));
+    const float ad = fabsf(denom);
+    const bool yes = q > __fadd_rn(thr, margin);
+    const bool sure = (yes || q < __fsub_rn(thr, margin)) && ad < 1e37f && ad > 1e-30f;
+    if (sure) return yes;
+    return __fdiv_rn(inter, denom) >= thr;
+}
+
+// The same decision with an early exit for disjoint boxes: cheaper where whole warps are disjoint most of the time
+// (the one-CTA-per-image detection layer), dearer in the dense 64x64 tiles of the proposal mask kernel.
 __device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float4 b, float area_b, float thr) {
     const float yy1 = fmaxf(a.x, b.x);
     const float xx1 = fmaxf(a.y, b.y);
@@ -147,11 +176,8 @@ __device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float
     const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
     const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
     const float inter = __fmul_rn(w, h);
-    // Disjoint boxes (the common case): 0 / x is 0 (or NaN), never >= a positive threshold.
-    if (inter == 0.0f && thr > 0.0f) return false;
+    if (inter == 0.0f && thr > 0.0f) return false;  // 0 / x is 0 (or NaN), never >= a positive threshold
     const float denom = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-    // The decision is that of the correctly rounded quotient (NaN -> false, kept, as on the CPU).  A 2-ulp
-    // approximate quotient settles it unless it lands within ~8 ulp of the threshold; only then divide exactly.
     if (fabsf(denom) < 1e37f && fabsf(denom) > 1e-30f) {
         const float q = __fdividef(inter, denom);
         const float margin = fabsf(thr) * 1e-6f + 1e-37f;

@@ -53,11 +53,29 @@ __device__ __forceinline__ uint64_t suppression_word(const float4 rowbox, float 
                                                      int col0, int ncols, float thr) {
     uint64_t w = 0;
     const int start = (row >= col0) ? (row - col0 + 1) : 0;
-    for (int c = start; c < ncols; ++c) {
-        bool s = iou_ge(rowbox, rowarea, cbox[c], carea[c], thr);
-        if (kClassAware) s = s && (ccls[c] == rowcls);
-        if (s) w |= (1ull << c);
+    const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
+    if (kClassAware) {
+        for (int c = start; c < ncols; ++c) {
+            bool s = iou_ge(rowbox, rowarea, cbox[c], carea[c], thr);
+            s = s && (ccls[c] == rowcls);
+            if (s) w |= (1ull << c);
+        }
+        return w;
     }
+    if (start == 0 && ncols == 64) {  // a full off-diagonal tile: constant bit positions, smem offsets folded into the loads
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (iou_ge_m(rowbox, rowarea, cbox[c], carea[c], thr, margin)) lo |= (1u << c);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (iou_ge_m(rowbox, rowarea, cbox[32 + c], carea[32 + c], thr, margin)) hi |= (1u << c);
+        }
+        return ((uint64_t)hi << 32) | lo;
+    }
+    for (int c = start; c < ncols; ++c)
+        if (iou_ge_m(rowbox, rowarea, cbox[c], carea[c], thr, margin)) w |= (1ull << c);
     return w;
 }
 
