@@ -169,22 +169,22 @@ __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int 
         } else {
             rows = mask + (size_t)c * 64 * W;
         }
-        // --- resolve the 64 boxes of this chunk against each other (warp 0, all lanes redundantly) ---
+        // --- resolve the 64 boxes of this chunk against each other (warp 0).  Only SURVIVORS cost a step: the next
+        //     survivor is the lowest candidate bit, and it removes the boxes it suppresses from the candidates. ---
         if (tid < 32) {
             const int nrows = min(64, n - c * 64);
             const uint64_t d_lo = (tid < nrows) ? rows[(size_t)tid * W + c] : 0ull;
             const uint64_t d_hi = (tid + 32 < nrows) ? rows[(size_t)(tid + 32) * W + c] : 0ull;
-            uint64_t alive = ~sm.remv[c];
-            if (nrows < 64) alive &= ((1ull << nrows) - 1ull);
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const uint64_t d = __shfl_sync(0xffffffffu, d_lo, l);
-                if ((alive >> l) & 1ull) alive &= ~d;
-            }
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const uint64_t d = __shfl_sync(0xffffffffu, d_hi, l);
-                if ((alive >> (l + 32)) & 1ull) alive &= ~d;
+            uint64_t cand = ~sm.remv[c];
+            if (nrows < 64) cand &= ((1ull << nrows) - 1ull);
+            uint64_t alive = 0ull;
+            while (cand) {  // warp-uniform: every lane holds the same cand
+                const int l = __ffsll((long long)cand) - 1;
+                const uint64_t lo = __shfl_sync(0xffffffffu, d_lo, l & 31);
+                const uint64_t hi = __shfl_sync(0xffffffffu, d_hi, l & 31);
+                const uint64_t d = (l < 32) ? lo : hi;  // suppression word of box l inside this chunk (bits above l only)
+                alive |= 1ull << l;
+                cand &= ~(d | (1ull << l));
             }
             if (tid == 0) {
                 sm.kept[c] = alive;
