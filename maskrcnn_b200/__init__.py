@@ -17,12 +17,16 @@ from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 __version__ = "0.1.0"
 
 
-def patch(model_module):
+def patch(model_module, data_module=None):
     """Monkey-patches an imported reference `model` module (model.py) so that its RoI hot path runs on
-    the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine.  The `maskrcnn` package
-    the module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
+    the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine; with the reference's
+    `data` module given as well, data.rpn_samples (the anchor matching the dataset runs per sample - the reference's
+    DataLoader uses num_workers=0, model.py:1528-1532, so it runs in the CUDA process).  The `maskrcnn` package the
+    module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
     model_module.roi_align = roi_align
     model_module.MaskRCNN.rpn_refine = rpn_refine
     model_module.MaskRCNN.mrn_refine = mrn_refine
     model_module.mrn_samples = mrn_samples
+    if data_module is not None:
+        data_module.rpn_samples = rpn_samples
     return model_module
