@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 2
+#define MRCNN_ABI_VERSION 3
 
 #define MRCNN_OK 0
 #define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */
@@ -38,6 +38,7 @@ extern "C" {
 #define MRCNN_E_WORKSPACE (-3)      /* workspace too small                                          */
 #define MRCNN_E_CUDA (-4)           /* a CUDA runtime call / launch failed                          */
 #define MRCNN_E_BOX_INDEX (-5)      /* reported by mrcnn_poll_device_errors: box_index out of range */
+#define MRCNN_E_CLASS_ID (-6)       /* reported by mrcnn_poll_device_errors: class id out of range  */
 
 /* Memory layout of 4-D tensors.  Logical shape is always [N, C, H, W] as in the reference;
  * NHWC means the same tensor stored channels-last (torch.channels_last), which is what the
@@ -59,7 +60,8 @@ MRCNN_API const char* mrcnn_last_error(void); /* thread-local, valid until the n
 /* Kernels flag recoverable data errors (box_index out of range: the reference exit(-1)s on CPU,
  * cpu/crop_cpu.cpp:47-50, and silently skips on CUDA, cuda/crop_cuda.cu:41-44) in a device word;
  * offending boxes produce extrapolation_value / contribute no gradient.  This call synchronises
- * `stream`, returns MRCNN_E_BOX_INDEX if the flag was raised since the last poll, and clears it. */
+ * `stream`, returns MRCNN_E_BOX_INDEX (or MRCNN_E_CLASS_ID: mrcnn_full_masks saw a class id outside [0, NC)) if the
+ * flag was raised since the last poll, and clears it. */
 MRCNN_API int mrcnn_poll_device_errors(mrcnn_stream_t stream);
 
 /* ---- crop_and_resize (replaces crop_forward / crop_backward, crop.h:14-53) -------------------- */
@@ -225,6 +227,18 @@ MRCNN_API int mrcnn_scatter_fill(int32_t* values, const int32_t* ids, const int3
 MRCNN_API int mrcnn_rpn_deltas(const double* anchors, const int32_t* gt_boxes, const int32_t* argmax, const int32_t* ids,
                                const int32_t* count, int T, const double* std4_host, double* rpn_bbox_out,
                                mrcnn_stream_t stream);
+
+/* ---- mask paste-back (replaces data.full_masks, data.py:287-314) ------------------------------------------------ */
+
+/* class_ids int64 [D], boxes [D,4] px (y1,x1,y2,x2; the detection layer's rounded boxes), masks [D,NC,mask_h,mask_w]
+ * (the mask head's sigmoid output, model.py:1188) -> out uint8 [D,H,W], 1 where the detection's mask covers the pixel.
+ * Per detection, exactly what the reference computes through PIL: (mask[class] * 255.0) truncated to 8 bits, resized to
+ * (int(y2 - y1), int(x2 - x1)) with Pillow's 8-bit bilinear resample (22-bit fixed-point weights, horizontal pass into an
+ * 8-bit intermediate, then vertical), pasted at (int(y1), int(x1)) clipped to the image, thresholded '> 127'.  Every
+ * byte of `out` is written once (no pre-zeroing).  An empty box gives an empty mask (PIL raises ValueError there; zero
+ * padded detection rows take this path).  mask_h, mask_w <= 64.  Any D: batches are just more rows. */
+MRCNN_API int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* masks, int D, int NC, int mask_h,
+                               int mask_w, int H, int W, uint8_t* out, mrcnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -3,12 +3,13 @@
     nms, CropFunction                      drop-ins for c++ext/maskrcnn/__init__.py
     roi_align, rpn_refine, mrn_refine, mrn_samples   drop-ins for the model.py functions that call them
     rpn_samples                            drop-in for data.rpn_samples (RPN anchor matching)
+    full_masks                             drop-in for data.full_masks (mask paste-back into the image)
     pyramid_roi_align, proposal_layer, detection_layer, detection_targets   batched, sync-free variants
     patch(model_module)                    swaps the fused versions into an unmodified reference model.py
 
 All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.h).  No CPU fallback.
 """
-from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets,  # noqa: F401
+from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets, full_masks,  # noqa: F401
                   mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, pyramid_roi_align_pair, roi_align,
                   rpn_refine, rpn_samples,
                   set_backward_algorithm)
@@ -29,4 +30,5 @@ def patch(model_module, data_module=None):
     model_module.mrn_samples = mrn_samples
     if data_module is not None:
         data_module.rpn_samples = rpn_samples
+        data_module.full_masks = full_masks
     return model_module

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libmrcnn_b200.so")
 NCHW, NHWC = 0, 1
 OK = 0
 BWD_AUTO, BWD_GATHER, BWD_SCATTER = 0, 1, 2
-E_INVALID_ARG, E_NOT_DEVICE_PTR, E_WORKSPACE, E_CUDA, E_BOX_INDEX = -1, -2, -3, -4, -5
+E_INVALID_ARG, E_NOT_DEVICE_PTR, E_WORKSPACE, E_CUDA, E_BOX_INDEX, E_CLASS_ID = -1, -2, -3, -4, -5, -6
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -45,6 +45,7 @@ SIGNATURES = {
     "mrcnn_nms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_proposal_workspace_bytes": (_sz, [_i, _i, _i]),
     "mrcnn_proposal_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f4, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_full_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mrcnn_detection_workspace_bytes": (_sz, [_i, _i]),
     "mrcnn_detection_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f4, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
@@ -66,7 +67,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mrcnn_abi_version() != 2:
+    if lib.mrcnn_abi_version() != 3:
         raise ImportError("maskrcnn_b200: ABI version mismatch")
     return lib
 

@@ -69,6 +69,7 @@ int mrcnn_poll_device_errors(mrcnn_stream_t stream) {
         MRCNN_CUDA(cudaMemsetAsync(word, 0, sizeof(int), (cudaStream_t)stream));
         MRCNN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
         if (flag & 1) return mrcnn::fail(MRCNN_E_BOX_INDEX, "box_index out of range [0, batch) in a crop/RoIAlign call");
+        if (flag & 2) return mrcnn::fail(MRCNN_E_CLASS_ID, "class id out of range [0, num_classes) in mrcnn_full_masks");
     }
     return MRCNN_OK;
 }

@@ -7,6 +7,9 @@ Reference interface being mirrored (paths relative to /root/reference):
     model.py:276-393                    roi_align(inputs, pool_size, image_shape)
     model.py:1307-1382                  MaskRCNN.rpn_refine(self, rpn_class, rpn_bbox)
     model.py:1389-1487                  MaskRCNN.mrn_refine(self, rpn_rois, probs, deltas, window)
+    model.py:396-576                    mrn_samples(rpn_rois, gt_class_ids, gt_boxes, gt_masks, config)
+    data.py:449-591                     rpn_samples(anchors, gt_class_ids, gt_boxes, config)
+    data.py:287-314                     full_masks(class_id, boxes, masks, height, width)
 
 There is no CPU implementation: CPU tensors raise TypeError, a missing library raises ImportError.
 """
@@ -19,7 +22,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -619,3 +622,31 @@ def rpn_samples(anchors, gt_class_ids, gt_boxes, config, device=None, return_ten
     if return_tensors:
         return match, bbox
     return match.cpu().numpy(), bbox.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# mask paste-back
+# ------------------------------------------------------------------------------------------------
+def full_masks(class_id, boxes, masks, height, width):
+    """Drop-in for data.full_masks (data.py:287-314): class_id [D] integer, boxes [D,4] px (y1,x1,y2,x2), masks
+    [D,NC,mh,mw] float -> bool [D,height,width], bit-identical to the reference's PIL route (mask * 255 -> 8 bit ->
+    Pillow bilinear resize to the box -> paste -> '> 127').  One launch for all detections and no host round trip (the
+    reference does `.item()`, `.tolist()` and a CPU copy per detection); leading batch dimensions are allowed
+    (class_id [...,D], boxes [...,D,4], masks [...,D,NC,mh,mw] -> [...,D,height,width]).  Unlike the reference, which
+    raises ValueError from PIL, an empty box gives an all-False mask (zero-padded detection rows)."""
+    _require_cuda(masks, "masks")
+    _require_cuda(boxes, "boxes")
+    _require_cuda(class_id, "class_id")
+    if masks.dim() < 4 or boxes.shape != masks.shape[:-3] + (4,) or class_id.shape != masks.shape[:-3]:
+        raise ValueError("class_id [...,D], boxes [...,D,4], masks [...,D,NC,mh,mw]")
+    lead = tuple(masks.shape[:-3])
+    NC, mh, mw = (int(v) for v in masks.shape[-3:])
+    D = int(class_id.numel())
+    H, W = int(height), int(width)
+    cls = class_id.reshape(-1).to(torch.int64).contiguous()
+    bx = boxes.reshape(-1, 4).float().contiguous()
+    mk = masks.detach().reshape(-1, NC, mh, mw).float().contiguous()
+    out = torch.empty((D, H, W), dtype=torch.bool, device=masks.device)
+    with torch.cuda.device(masks.device):
+        check(lib.mrcnn_full_masks(cls.data_ptr(), bx.data_ptr(), mk.data_ptr(), D, NC, mh, mw, H, W, out.data_ptr(), _stream()))
+    return out.reshape(lead + (H, W))

@@ -163,3 +163,26 @@ def rpn_target_inputs(n_gt, seed, image=1024, n_crowd=0):
     if n_crowd:
         cls[rng.choice(n_gt, n_crowd, replace=False)] = -1
     return cls, gt
+
+
+def mask_head_outputs(n_det, num_classes, seed, image=1024, mask=28, min_size=None, max_size=None, n_pad=0):
+    """Inputs of the mask paste-back (data.full_masks, data.py:287): class ids int64 [D] in [1, NC), boxes [D,4] =
+    rounded pixel boxes inside the image (what the detection layer emits, model.py:1432) and masks [D,NC,mask,mask] =
+    a sigmoid of a smooth random field per (detection, class), values on both sides of 0.5.  `n_pad` trailing rows are
+    zero padding (class 0, zero box)."""
+    rng = np.random.default_rng(seed)
+    lo = image / 64.0 if min_size is None else min_size
+    hi = image * 0.8 if max_size is None else max_size
+    boxes = np.round(random_rois(n_det, seed + 1, image=float(image), min_size=lo, max_size=hi) * image).astype(np.float32)
+    boxes[:, 2:] = np.minimum(np.maximum(boxes[:, 2:], boxes[:, :2] + 1), image)
+    cls = rng.integers(1, num_classes, n_det).astype(np.int64)
+    yy, xx = np.mgrid[0:mask, 0:mask].astype(np.float32) / mask
+    f = rng.uniform(0.5, 3.0, (n_det, num_classes, 2, 1, 1)).astype(np.float32)
+    ph = rng.uniform(0, 6.28, (n_det, num_classes, 2, 1, 1)).astype(np.float32)
+    field = 2.5 * np.sin(6.28 * f[:, :, 0] * yy + ph[:, :, 0]) * np.cos(6.28 * f[:, :, 1] * xx + ph[:, :, 1])
+    field = field + rng.standard_normal(field.shape).astype(np.float32) * 0.5
+    masks = (1.0 / (1.0 + np.exp(-field))).astype(np.float32)
+    if n_pad:
+        cls[n_det - n_pad:] = 0
+        boxes[n_det - n_pad:] = 0.0
+    return cls, boxes, masks

@@ -71,6 +71,9 @@ def lib():
         L.orc_detection_layer.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64, _f32p,
                                           ctypes.c_float, ctypes.c_float, ctypes.c_int64, _f32p,
                                           ctypes.c_float, ctypes.c_float, _f32p, _i64p]
+        L.orc_full_masks.restype = ctypes.c_int
+        L.orc_full_masks.argtypes = [_i64p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.POINTER(ctypes.c_uint8)]
         L.orc_boxes_refine.restype = None
         L.orc_boxes_refine.argtypes = [_f32p, _f32p, ctypes.c_int64, _f32p]
         _lib = L
@@ -305,3 +308,17 @@ def rpn_samples(anchors, gt_class_ids, gt_boxes, train_anchors_per_image, std_de
     lib().orc_rpn_deltas(anchors.ctypes.data_as(f64p), _p(gtb, _i32p), _p(argmax, _i32p), _p(ids, _i64p), len(ids),
                          std.ctypes.data_as(f64p), bbox.ctypes.data_as(f64p))
     return match, bbox
+
+
+def full_masks(class_ids, boxes, masks, height, width):
+    """data.full_masks (data.py:287-314): class_ids [D], boxes [D,4] px, masks [D,NC,mh,mw] -> bool [D,height,width].
+    Raises ValueError where PIL does (empty box); boxes that leave the image are pasted clipped, as the reference's Pad does."""
+    cls = np.ascontiguousarray(class_ids, np.int64)
+    boxes, masks = _f32(boxes), _f32(masks)
+    d, nc, mh, mw = masks.shape
+    out = np.zeros((d, int(height), int(width)), np.uint8)
+    rc = lib().orc_full_masks(_p(cls, _i64p), _p(boxes), _p(masks), d, nc, mh, mw, int(height), int(width),
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    if rc != 0:
+        raise ValueError("full_masks: detection %d has an empty box" % (-rc - 1))
+    return out.astype(bool)

@@ -39,3 +39,14 @@ def replay_perms(perms):
         assert len(p) == n, "permutation length differs from the reference's draw"
         return p
     return randperm
+
+
+def golden_masks(tag):
+    """(class ids, boxes, masks [D,1,mh,mw], H, W, expected bool [D,H,W]) of tests/golden/golden_masks_v1.npz; only the
+    selected class plane of every detection was stored, so the class ids are all zero here."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_masks_v1.npz"))
+    boxes, sel = g[f"{tag}_in_boxes"], g[f"{tag}_in_masks_sel"]
+    h, w = (int(v) for v in g[f"{tag}_in_hw"])
+    d = len(boxes)
+    want = np.unpackbits(g[f"{tag}_out_bits"])[:d * h * w].reshape(d, h, w).astype(bool)
+    return np.zeros(d, np.int64), boxes, np.ascontiguousarray(sel[:, None]), h, w, want

@@ -602,3 +602,83 @@ def test_rpn_samples_golden(ops, tag):
     np.testing.assert_array_equal(match, g[f"{tag}_out_match"].astype(np.int32))
     np.testing.assert_array_equal(bbox[:, :2], g[f"{tag}_out_bbox"][:, :2])
     assert _f64_ulp(bbox[:, 2:], g[f"{tag}_out_bbox"][:, 2:]) <= 2
+
+
+# ------------------------------------------------------------------ mask paste-back (data.full_masks)
+@pytest.mark.parametrize("D,NC,H,W,lo,hi,seed", [(100, 81, 1024, 1024, 16, 800, 1), (40, 81, 256, 256, 1, 200, 2), (24, 5, 200, 333, 1, 60, 3),
+                                                 (16, 3, 64, 80, 1, 28, 4), (7, 2, 100, 48, 2, 40, 5), (1, 81, 1024, 1024, 1000, 1024, 6)])
+def test_full_masks_matches_oracle(ops, D, NC, H, W, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    cls, boxes, masks = synth.mask_head_outputs(D, NC, 70 + seed, image=min(H, W), min_size=lo, max_size=min(hi, min(H, W)))
+    masks[::5] = masks[::5] * 1.5 - 0.25                      # saturating values (< 0, > 1)
+    if D >= 7:
+        boxes[1, 2] = boxes[1, 0] + 28.0                      # unchanged height: no vertical pass
+        boxes[2, 3] = boxes[2, 1] + 28.0                      # unchanged width: no horizontal pass
+        boxes[3] += np.float32([-9.0, -11.0, -9.0, -11.0])    # leaves the image top / left
+        boxes[4, 2:] = np.maximum(boxes[4, 2:], boxes[4, :2] + 3.0)
+        boxes[4] += rng.choice(np.float32([0.25, 0.5, 0.75]), 4)
+        boxes[5, 2:] = [H + 13.0, W + 5.0]                    # leaves the image bottom / right
+    want = oracle.full_masks(cls, boxes, masks, H, W)
+    got = ops.full_masks(dev(cls), dev(boxes), dev(masks), H, W)
+    assert got.dtype == torch.bool and tuple(got.shape) == (D, H, W)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    ops.check_device_errors()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_full_masks_golden(ops, tag):
+    from helpers import golden_masks
+    cls, boxes, masks, h, w, want = golden_masks(tag)
+    np.testing.assert_array_equal(ops.full_masks(dev(cls), dev(boxes), dev(masks), h, w).cpu().numpy(), want)
+
+
+def test_full_masks_edge_cases(ops):
+    # zero-padded detection rows (empty boxes) give empty masks; batched leading dimension; D = 0
+    cls, boxes, masks = synth.mask_head_outputs(12, 4, 5, image=96, n_pad=4)
+    got = ops.full_masks(dev(cls).view(2, 6), dev(boxes).view(2, 6, 4), dev(masks).view(2, 6, 4, 28, 28), 96, 96)
+    assert tuple(got.shape) == (2, 6, 96, 96)
+    want = oracle.full_masks(cls[:8], boxes[:8], masks[:8], 96, 96)
+    np.testing.assert_array_equal(got.view(12, 96, 96)[:8].cpu().numpy(), want)
+    assert not bool(got.view(12, 96, 96)[8:].any())
+    assert ops.full_masks(dev(cls[:0]), dev(boxes[:0]), dev(masks[:0]), 32, 32).shape == (0, 32, 32)
+    # inverted and fully outside boxes: nothing is pasted
+    boxes[0] = [50.0, 50.0, 20.0, 20.0]
+    boxes[1] = [200.0, 10.0, 260.0, 40.0]
+    got = ops.full_masks(dev(cls), dev(boxes), dev(masks), 96, 96)
+    assert not bool(got[:2].any())
+    # a class id outside [0, NC) raises through the device error word
+    bad = cls.copy()
+    bad[2] = 9
+    ops.full_masks(dev(bad), dev(boxes), dev(masks), 96, 96)
+    with pytest.raises(RuntimeError):
+        ops.check_device_errors()
+    ops.check_device_errors()
+    with pytest.raises(TypeError):
+        ops.full_masks(torch.from_numpy(cls), torch.from_numpy(boxes), torch.from_numpy(masks), 96, 96)
+
+
+def test_full_masks_full_size_properties(ops):
+    """configs[4] size: 64 images x 100 detections would be 6.7 GB of masks; 8 images x 100 here.  Properties: nothing
+    outside the box, translation of a box by whole pixels translates its mask, a constant mask > 127/255 fills the box."""
+    D, H, W = 800, 1024, 1024
+    cls, boxes, masks = synth.mask_head_outputs(D, 81, 99, image=1024)
+    got = ops.full_masks(dev(cls), dev(boxes), dev(masks), H, W)
+    yy = torch.arange(H, device="cuda").view(1, H, 1)
+    xx = torch.arange(W, device="cuda").view(1, 1, W)
+    b = dev(boxes).view(D, 4, 1, 1)
+    inside = (yy >= b[:, 0]) & (yy < b[:, 2]) & (xx >= b[:, 1]) & (xx < b[:, 3])
+    assert not bool((got & ~inside).any())
+    assert int(got.sum()) > 0
+    # constant masks: 0.6 * 255 = 153 > 127 fills the box exactly, 0.4 * 255 = 102 leaves it empty
+    ones = torch.full((D, 81, 28, 28), 0.6, device="cuda")
+    assert bool((ops.full_masks(dev(cls), dev(boxes), ones, H, W) == inside).all())
+    assert not bool(ops.full_masks(dev(cls), dev(boxes), ones * (0.4 / 0.6), H, W).any())
+    # whole-pixel translation
+    sub = slice(0, 16)
+    small = boxes[sub].copy()
+    small[:, [0, 2]] -= small[:, 0:1]
+    small[:, [1, 3]] -= small[:, 1:2]
+    at0 = ops.full_masks(dev(cls[sub]), dev(small), dev(masks[sub]), H, W)
+    for i in range(16):
+        y1, x1, y2, x2 = (int(v) for v in boxes[i])
+        assert torch.equal(at0[i, :y2 - y1, :x2 - x1], got[i, y1:y2, x1:x2])

@@ -235,3 +235,36 @@ def test_rpn_samples_matches_data_py(image, n_gt, n_crowd, train_anchors, seed):
     np.testing.assert_array_equal(g_bbox[:, :2], w_bbox[:, :2])
     a, b = g_bbox[:, 2:].view(np.int64), w_bbox[:, 2:].view(np.int64)
     assert np.abs(a - b).max() <= 2      # float64 log: numpy's vs libm's
+
+
+@needs_model
+@pytest.mark.parametrize("H,W,lo,hi,seed", [(256, 256, 4, 200, 1), (200, 333, 1, 60, 2), (64, 80, 1, 28, 3), (512, 512, 28, 500, 4)])
+def test_full_masks_matches_data_py(H, W, lo, hi, seed):
+    """oracle.full_masks (a restatement of Pillow's 8-bit bilinear resample) against data.full_masks executed here, i.e.
+    against the installed Pillow: upscales, downscales, unchanged sides, boxes leaving the image, fractional coordinates,
+    saturated mask values."""
+    d = reference.load().data
+    rng = np.random.default_rng(seed)
+    cls, boxes, masks = synth.mask_head_outputs(24, 7, 50 + seed, image=min(H, W), min_size=lo, max_size=hi)
+    masks[::5] = masks[::5] * 1.5 - 0.25
+    boxes[1, 2] = boxes[1, 0] + 28.0
+    boxes[2, 3] = boxes[2, 1] + 28.0
+    boxes[3] += np.float32([-9.0, -11.0, -9.0, -11.0])
+    boxes[4, 2:] = np.maximum(boxes[4, 2:], boxes[4, :2] + 3.0)
+    boxes[4] += rng.choice(np.float32([0.25, 0.5, 0.75]), 4)
+    boxes[5, 2:] = [H + 13.0, W + 5.0]
+    want = d.full_masks(torch.from_numpy(cls), torch.from_numpy(boxes), torch.from_numpy(masks), H, W).numpy()
+    got = oracle.full_masks(cls, boxes, masks, H, W)
+    assert want.dtype == np.bool_ and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+
+
+@needs_model
+def test_full_masks_empty_box_raises_like_pil():
+    d = reference.load().data
+    cls, boxes, masks = synth.mask_head_outputs(2, 3, 9, image=64)
+    boxes[1] = [10.0, 10.0, 10.0, 30.0]
+    with pytest.raises(ValueError):
+        d.full_masks(torch.from_numpy(cls), torch.from_numpy(boxes), torch.from_numpy(masks), 64, 64)
+    with pytest.raises(ValueError):
+        oracle.full_masks(cls, boxes, masks, 64, 64)
