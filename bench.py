@@ -560,6 +560,68 @@ def secondary(torch, wl, hbm):
                                   "match_kernels_us": tk * 1e6, "match_algorithmic_GBps": (A_ * 40 + 20 * 20) / tk / 1e9,
                                   "dropin_images_per_s": 1.0 / td, "dropin_ms": td * 1e3,
                                   "note": "drop-in = reference semantics incl. three count read-backs and np.random draws on the host"}
+    # mask paste-back (data.full_masks) - 8 images x 100 detections -> 800 boolean 1024x1024 masks
+    Dm = 800
+    m_cls, m_boxes, m_masks = synth.mask_head_outputs(100, 81, 41, image=IMAGE)
+    m_cls_d = torch.from_numpy(np.tile(m_cls, Dm // 100)).to(dev)
+    m_boxes_d = torch.from_numpy(np.tile(m_boxes, (Dm // 100, 1))).to(dev)
+    m_masks_d = torch.from_numpy(m_masks).to(dev).repeat(Dm // 100, 1, 1, 1)
+    m_out = torch.empty((Dm, IMAGE, IMAGE), dtype=torch.bool, device=dev)
+    fpaste = lambda: L.check(L.lib.mrcnn_full_masks(m_cls_d.data_ptr(), m_boxes_d.data_ptr(), m_masks_d.data_ptr(), Dm, 81, 28, 28, IMAGE,  # noqa: E731
+                                                    IMAGE, m_out.data_ptr(), wl._s()))
+    t = wl.time_op(fpaste, iters=20)
+    t_fill = wl.time_op(lambda: m_out.zero_(), iters=20)   # write-only ceiling: a plain fill of the same buffer
+    by = Dm * (IMAGE * IMAGE + 28 * 28 * 4 + 24)
+    out["full_masks"] = {"config": "data.full_masks (SURVEY 8f): %d detections (8 images x 100) x 81 classes x 28x28 -> bool [%d,%d,%d], one launch"
+                                   % (Dm, Dm, IMAGE, IMAGE), "detections_per_s": Dm / t, "images_per_s": Dm / 100 / t, "ms": t * 1e3,
+                         "algorithmic_MB": by / 1e6, "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+                         "box_area_fraction": float(((m_boxes[:, 2] - m_boxes[:, 0]) * (m_boxes[:, 3] - m_boxes[:, 1])).mean() / IMAGE / IMAGE),
+                         "fill_of_the_same_buffer_ms": t_fill * 1e3, "fill_GBps": Dm * IMAGE * IMAGE / t_fill / 1e9,
+                         "frac_of_write_only_fill": t_fill / t,
+                         "note": "write-bound: H*W bytes per detection written once with 128-bit streaming stores; a write-only stream "
+                                 "tops out well below the copy bandwidth (see the plain fill timed beside it)"}
+    del m_out, m_masks_d
+    # RPN head output plumbing (rpn_detect) - conv outputs of P2..P6 -> [B,A,2] / [B,A,4] / fg [B,A], batch 8
+    Bp = 8
+    g_ = torch.Generator(device=dev)
+    g_.manual_seed(9)
+    sides = [IMAGE // s_ for s_ in (4, 8, 16, 32, 64)]
+    cls_l = [torch.randn((Bp, 6, s_, s_), device=dev, generator=g_) for s_ in sides]
+    box_l = [torch.randn((Bp, 12, s_, s_), device=dev, generator=g_) for s_ in sides]
+    with torch.no_grad():
+        import ctypes
+        A_all = 3 * sum(s_ * s_ for s_ in sides)
+        po = [torch.empty((Bp, A_all, k_), device=dev) for k_ in (2, 2, 4, 1)]
+        lp = (ctypes.c_void_p * 5)(*[x.data_ptr() for x in cls_l])
+        bp = (ctypes.c_void_p * 5)(*[x.data_ptr() for x in box_l])
+        hs = (ctypes.c_int * 5)(*sides)
+        fpack = lambda: L.check(L.lib.mrcnn_rpn_pack(lp, bp, hs, hs, 5, Bp, 3, L.NCHW, po[0].data_ptr(), po[1].data_ptr(),  # noqa: E731
+                                                     po[2].data_ptr(), po[3].data_ptr(), wl._s()))
+        t = wl.time_op(fpack, iters=20)
+        t_api = wl.time_op(lambda: m.rpn_pack(cls_l, box_l), iters=20)
+
+        def torch_chain():   # the reference's launches (model.py:624-641, :1294-1304) on the same device, for scale
+            lg = [x.permute(0, 2, 3, 1).contiguous().view(Bp, -1, 2) for x in cls_l]
+            pr = [torch.softmax(x, 2) for x in lg]
+            bb = [x.permute(0, 2, 3, 1).contiguous().view(Bp, -1, 4) for x in box_l]
+            return torch.cat(lg, 1), torch.cat(pr, 1), torch.cat(bb, 1)
+        t_ref = wl.time_op(torch_chain, iters=20)
+    by = Bp * A_all * (24 + 36)   # 6 floats read, 2 + 2 + 4 + 1 floats written per anchor
+    out["rpn_pack"] = {"config": "MaskRCNN.rpn_detect plumbing (SURVEY 8f): P2..P6 conv outputs of %d images -> logits/probs [B,%d,2], deltas "
+                                 "[B,%d,4], fg [B,%d]; one launch" % (Bp, A_all, A_all, A_all),
+                       "images_per_s": Bp / t, "us": t * 1e6, "algorithmic_MB": by / 1e6, "algorithmic_GBps": by / t / 1e9,
+                       "frac_of_hbm": by / t / 1e9 / hbm, "through_ops_rpn_pack_us": t_api * 1e6, "same_ops_stock_pytorch_us": t_ref * 1e6,
+                       "note": "stock PyTorch chain = 5 x (2 permute copies + softmax) + 3 cat on the same GPU"}
+    anchors_d = torch.from_numpy(synth.pyramid_anchors((IMAGE, IMAGE))).to(dev)
+    rc_, rb_ = zip(*[synth.rpn_outputs(synth.pyramid_anchors((IMAGE, IMAGE)), 500 + i) for i in range(2)])
+    rc_d = torch.from_numpy(np.stack([rc_[i % 2] for i in range(Bp)])).to(dev)
+    rb_d = torch.from_numpy(np.stack([rb_[i % 2] for i in range(Bp)])).to(dev)
+    fg_d = rc_d[:, :, 1].contiguous()
+    t2 = wl.time_op(lambda: m.proposal_layer(rc_d, rb_d, anchors_d, 6000, 1000, 0.7), iters=20)
+    t1 = wl.time_op(lambda: m.proposal_layer(fg_d, rb_d, anchors_d, 6000, 1000, 0.7), iters=20)
+    out["proposal_layer_fg_scores"] = {"config": "configs[1] fed with fg probabilities [B,A] (rpn_pack's fg output) instead of rpn_class [B,A,2]",
+                                       "ms_per_batch_fg": t1 * 1e3, "ms_per_batch_pair": t2 * 1e3, "images_per_s_fg": Bp / t1}
+    del cls_l, box_l, rc_d, rb_d, po
     # configs[2]: forward only, 1000 RoIs x 256 ch on one image
     boxes_np = synth.random_rois(1000, 1234)
     boxes = torch.from_numpy(boxes_np).to(dev)

@@ -155,6 +155,33 @@ MRCNN_API int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox
                          float* rois_out, int32_t* counts_out,
                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
 
+/* The same with the foreground probabilities alone, fg_scores [B,A] (what mrcnn_rpn_pack writes as fg_out): the layer's
+ * only pass over the scores reads half the bytes. */
+MRCNN_API int mrcnn_proposal_layer_fg(const float* fg_scores, const float* rpn_bbox, const float* anchors,
+                            int B, int A, int pre_nms, int post_nms, float nms_threshold,
+                            const float* std4_host, float height, float width,
+                            float* rois_out, int32_t* counts_out,
+                            void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+/* ---- RPN head output plumbing (replaces the permute / view / softmax of RPN.forward, model.py:624-641, and the three
+ *      torch.cat of MaskRCNN.rpn_detect, model.py:1294-1304) ---------------------------------------------------- */
+
+/* logits[l] [B,2K,H[l],W[l]] and bbox[l] [B,4K,H[l],W[l]] = conv_class / conv_bbox outputs of pyramid level l (HOST arrays
+ * of `levels` device pointers; layout MRCNN_NCHW or MRCNN_NHWC for all of them), K = anchors per location.  Writes, in
+ * the reference's anchor order (level-major, then y, x, anchor) with A = K * sum(H*W):
+ *   logits_out [B,A,2] (rpn_class_logits), class_out [B,A,2] = softmax over (bg, fg) (rpn_class), bbox_out [B,A,4]
+ *   (rpn_bbox), fg_out [B,A] = class_out[:,:,1] (input of mrcnn_proposal_layer_fg).  Any output may be NULL. */
+MRCNN_API int mrcnn_rpn_pack(const float* const* logits, const float* const* bbox, const int* H, const int* W, int levels,
+                             int B, int anchors_per_location, int layout, float* logits_out, float* class_out,
+                             float* bbox_out, float* fg_out, mrcnn_stream_t stream);
+
+/* Adjoint of the layout part of mrcnn_rpn_pack, for training: grad_logits [B,A,2] / grad_bbox [B,A,4] (either may be NULL
+ * together with its destinations) written back as g_logits[l] [B,2K,H[l],W[l]] / g_bbox[l] [B,4K,H[l],W[l]] (HOST arrays of
+ * device pointers, `layout` as in the forward).  The probabilities carry no gradient: they only feed the proposal layer. */
+MRCNN_API int mrcnn_rpn_unpack(const float* grad_logits, const float* grad_bbox, const int* H, const int* W, int levels, int B,
+                               int anchors_per_location, int layout, float* const* g_logits, float* const* g_bbox,
+                               mrcnn_stream_t stream);
+
 /* ---- detection layer (replaces MaskRCNN.mrn_refine, model.py:1389-1487; batched) --------------- */
 
 /* rois [B,N,4] normalised, probs [B,N,NC], deltas [B,N,NC,4], windows [B,4] px (device).

@@ -4,6 +4,7 @@
     roi_align, rpn_refine, mrn_refine, mrn_samples   drop-ins for the model.py functions that call them
     rpn_samples                            drop-in for data.rpn_samples (RPN anchor matching)
     full_masks                             drop-in for data.full_masks (mask paste-back into the image)
+    rpn_detect, rpn_pack                   drop-in for MaskRCNN.rpn_detect: RPN head outputs -> [B,A,2] / [B,A,4] in one launch
     pyramid_roi_align, proposal_layer, detection_layer, detection_targets   batched, sync-free variants
     patch(model_module)                    swaps the fused versions into an unmodified reference model.py
 
@@ -11,7 +12,7 @@ All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.
 """
 from .ops import (CropFunction, check_device_errors, crop_and_resize, detection_layer, detection_targets, full_masks,  # noqa: F401
                   mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, pyramid_roi_align_pair, roi_align,
-                  rpn_refine, rpn_samples,
+                  rpn_detect, rpn_pack, rpn_refine, rpn_samples,
                   set_backward_algorithm)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 
@@ -26,6 +27,7 @@ def patch(model_module, data_module=None):
     module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
     model_module.roi_align = roi_align
     model_module.MaskRCNN.rpn_refine = rpn_refine
+    model_module.MaskRCNN.rpn_detect = rpn_detect
     model_module.MaskRCNN.mrn_refine = mrn_refine
     model_module.mrn_samples = mrn_samples
     if data_module is not None:

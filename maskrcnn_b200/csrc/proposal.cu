@@ -27,7 +27,8 @@ constexpr int kSelThreads = 1024;
 constexpr int kMaxPreNms = 8192;
 
 struct ProposalParams {
-    const float* rpn_class;  // [B,A,2]
+    const float* rpn_class;  // [B,A,2] (bg,fg) when sstride == 2, fg scores [B,A] when sstride == 1
+    int sstride;
     const float* rpn_bbox;   // [B,A,4]
     const float* anchors;    // [A,4]
     int B, A;
@@ -113,13 +114,17 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
     const int lo = min(p.A, rank * p.per);
     const int hi = min(p.A, lo + p.per);
     const int n_local = hi - lo;
-    const float* scores = p.rpn_class + ((size_t)img * p.A + lo) * 2 + 1;  // fg prob, model.py:1336
+    const float* scores = p.rpn_class + ((size_t)img * p.A + lo) * p.sstride + (p.sstride - 1);  // fg prob, model.py:1336
 
-    auto key_at = [&](int i) -> uint32_t { return p.staged ? keys[i] : float_to_key(__ldg(scores + (size_t)i * 2)); };
+    auto key_at = [&](int i) -> uint32_t { return p.staged ? keys[i] : float_to_key(__ldg(scores + (size_t)i * p.sstride)); };
 
     if (p.staged) {
-        const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
-        for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(s2 + i).y);
+        if (p.sstride == 2) {
+            const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
+            for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(s2 + i).y);
+        } else {  // fg-only scores (mrcnn_rpn_pack's fg_out): half the bytes of the only HBM pass over the scores
+            for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(scores + i));
+        }
     }
     if (tid == 0) sh.gt_local = 0;
     __syncthreads();
@@ -376,10 +381,10 @@ size_t mrcnn_proposal_workspace_bytes(int B, int A, int pre_nms) {
     return carve_proposal(nullptr, B, A, pre_nms).bytes;
 }
 
-int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors, int B, int A, int pre_nms,
-                         int post_nms, float nms_threshold, const float* std4_host, float height, float width,
-                         float* rois_out, int32_t* counts_out, void* workspace, size_t workspace_bytes,
-                         mrcnn_stream_t stream_) {
+static int proposal_layer_impl(const float* rpn_class, int sstride, const float* rpn_bbox, const float* anchors, int B, int A,
+                               int pre_nms, int post_nms, float nms_threshold, const float* std4_host, float height, float width,
+                               float* rois_out, int32_t* counts_out, void* workspace, size_t workspace_bytes,
+                               mrcnn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(B > 0 && A >= 0 && pre_nms >= 0 && post_nms > 0, "mrcnn_proposal_layer: bad sizes");
     MRCNN_REQUIRE(std4_host != nullptr, "mrcnn_proposal_layer: std4_host is null");
@@ -398,7 +403,7 @@ int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const fl
     MRCNN_REQUIRE_DEV(anchors);
     MRCNN_REQUIRE_DEV(workspace);
     MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "mrcnn_proposal_layer: workspace must be 256-byte aligned");
-    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(rpn_class) & 7u) == 0 && (reinterpret_cast<uintptr_t>(rpn_bbox) & 15u) == 0 &&
+    MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(rpn_class) & (sstride == 2 ? 7u : 3u)) == 0 && (reinterpret_cast<uintptr_t>(rpn_bbox) & 15u) == 0 &&
                       (reinterpret_cast<uintptr_t>(anchors) & 15u) == 0 && (reinterpret_cast<uintptr_t>(rois_out) & 15u) == 0,
                   "mrcnn_proposal_layer: rpn_class/rpn_bbox/anchors/rois_out must be 8/16/16/16-byte aligned");
     const ProposalWorkspace ws = carve_proposal(workspace, B, A, pre_nms);
@@ -406,7 +411,7 @@ int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const fl
         return fail(MRCNN_E_WORKSPACE, "mrcnn_proposal_layer: workspace of %zu bytes < required %zu", workspace_bytes, ws.bytes);
 
     ProposalParams p;
-    p.rpn_class = rpn_class; p.rpn_bbox = rpn_bbox; p.anchors = anchors;
+    p.rpn_class = rpn_class; p.sstride = sstride; p.rpn_bbox = rpn_bbox; p.anchors = anchors;
     p.B = B; p.A = A; p.pre = pre; p.P = next_pow2_i(pre);
     p.per = (A + kClusterSize - 1) / kClusterSize;
     p.std0 = std4_host[0]; p.std1 = std4_host[1]; p.std2 = std4_host[2]; p.std3 = std4_host[3];
@@ -448,6 +453,20 @@ int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const fl
                                                          width, rois_out, counts_out);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
+}
+
+int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors, int B, int A, int pre_nms,
+                         int post_nms, float nms_threshold, const float* std4_host, float height, float width,
+                         float* rois_out, int32_t* counts_out, void* workspace, size_t workspace_bytes, mrcnn_stream_t stream) {
+    return proposal_layer_impl(rpn_class, 2, rpn_bbox, anchors, B, A, pre_nms, post_nms, nms_threshold, std4_host, height, width,
+                               rois_out, counts_out, workspace, workspace_bytes, stream);
+}
+
+int mrcnn_proposal_layer_fg(const float* fg_scores, const float* rpn_bbox, const float* anchors, int B, int A, int pre_nms,
+                            int post_nms, float nms_threshold, const float* std4_host, float height, float width,
+                            float* rois_out, int32_t* counts_out, void* workspace, size_t workspace_bytes, mrcnn_stream_t stream) {
+    return proposal_layer_impl(fg_scores, 1, rpn_bbox, anchors, B, A, pre_nms, post_nms, nms_threshold, std4_host, height, width,
+                               rois_out, counts_out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

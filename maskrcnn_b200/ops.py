@@ -10,6 +10,7 @@ Reference interface being mirrored (paths relative to /root/reference):
     model.py:396-576                    mrn_samples(rpn_rois, gt_class_ids, gt_boxes, gt_masks, config)
     data.py:449-591                     rpn_samples(anchors, gt_class_ids, gt_boxes, config)
     data.py:287-314                     full_masks(class_id, boxes, masks, height, width)
+    model.py:1294-1304 (+ :624-641)     MaskRCNN.rpn_detect(self, rpn_feature_maps)
 
 There is no CPU implementation: CPU tensors raise TypeError, a missing library raises ImportError.
 """
@@ -22,7 +23,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "rpn_pack", "rpn_detect", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -283,13 +284,15 @@ def roi_align(inputs, pool_size, image_shape):
 # ------------------------------------------------------------------------------------------------
 def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, nms_threshold,
                    std=(0.1, 0.1, 0.2, 0.2), image_hw=(1024, 1024)):
-    """Batched proposal layer.  rpn_class [B,A,2], rpn_bbox [B,A,4], anchors [A,4] px ->
-    (rois [B,post,4] normalised & zero padded, counts int32 [B]).  No host synchronisation."""
+    """Batched proposal layer.  rpn_class [B,A,2] - or the foreground probabilities alone, [B,A], as rpn_pack returns
+    them - rpn_bbox [B,A,4], anchors [A,4] px -> (rois [B,post,4] normalised & zero padded, counts int32 [B]).  No host
+    synchronisation."""
     _require_cuda(rpn_class, "rpn_class", torch.float32)
     _require_cuda(rpn_bbox, "rpn_bbox", torch.float32)
     _require_cuda(anchors, "anchors", torch.float32)
-    if rpn_class.dim() != 3 or rpn_class.size(2) != 2 or rpn_bbox.shape != rpn_class.shape[:2] + (4,):
-        raise ValueError("rpn_class must be [B,A,2] and rpn_bbox [B,A,4]")
+    fg_only = rpn_class.dim() == 2
+    if (not fg_only and (rpn_class.dim() != 3 or rpn_class.size(2) != 2)) or rpn_bbox.shape != rpn_class.shape[:2] + (4,):
+        raise ValueError("rpn_class must be [B,A,2] (or fg scores [B,A]) and rpn_bbox [B,A,4]")
     B, A = rpn_class.shape[:2]
     if anchors.shape != (A, 4):
         raise ValueError("anchors must be [A,4]")
@@ -300,11 +303,113 @@ def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, 
         counts = torch.empty(B, dtype=torch.int32, device=rpn_class.device)
         ws_bytes = lib.mrcnn_proposal_workspace_bytes(B, A, int(pre_nms_limit))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rpn_class.device)
-        check(lib.mrcnn_proposal_layer(rpn_class.data_ptr(), rpn_bbox.data_ptr(), anchors.data_ptr(), B, A,
-                                       int(pre_nms_limit), post, float(nms_threshold), _lib.f4(np.float32(std)),
-                                       float(image_hw[0]), float(image_hw[1]), rois.data_ptr(), counts.data_ptr(),
-                                       ws.data_ptr(), ws_bytes, _stream()))
+        fn = lib.mrcnn_proposal_layer_fg if fg_only else lib.mrcnn_proposal_layer
+        check(fn(rpn_class.data_ptr(), rpn_bbox.data_ptr(), anchors.data_ptr(), B, A,
+                 int(pre_nms_limit), post, float(nms_threshold), _lib.f4(np.float32(std)),
+                 float(image_hw[0]), float(image_hw[1]), rois.data_ptr(), counts.data_ptr(),
+                 ws.data_ptr(), ws_bytes, _stream()))
     return rois, counts
+
+
+# ------------------------------------------------------------------------------------------------
+# RPN head output plumbing
+# ------------------------------------------------------------------------------------------------
+def _rpn_levels(logits, bboxes):
+    if len(logits) != len(bboxes) or not 1 <= len(logits) <= 8:
+        raise ValueError("rpn_pack takes 1..8 pyramid levels, one class and one bbox conv output each")
+    B = logits[0].size(0)
+    K, rem = divmod(logits[0].size(1), 2)
+    layouts = set()
+    ls, bs = [], []
+    for lg, bx in zip(logits, bboxes):
+        _require_cuda(lg, "rpn class logits", torch.float32)
+        _require_cuda(bx, "rpn bbox", torch.float32)
+        if lg.dim() != 4 or rem or lg.size(0) != B or lg.size(1) != 2 * K or bx.shape != (B, 4 * K) + tuple(lg.shape[2:]):
+            raise ValueError("per level: class logits [B,2K,H,W] and bbox [B,4K,H,W]")
+        lg, la = _layout4(lg)
+        bx, lb = _layout4(bx)
+        ls.append(lg)
+        bs.append(bx)
+        layouts.update((la, lb))
+    if len(layouts) != 1:   # mixed memory formats: fall back to the conv default for all of them
+        ls = [t.contiguous() for t in ls]
+        bs = [t.contiguous() for t in bs]
+        layouts = {NCHW}
+    return ls, bs, B, K, layouts.pop()
+
+
+def _ptr_array(ts):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+class _RpnPack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, n_levels, want_class, *tensors):
+        ls, bs, B, K, layout = _rpn_levels(tensors[:n_levels], tensors[n_levels:])
+        Hs, Ws = [t.size(2) for t in ls], [t.size(3) for t in ls]
+        A = K * sum(h * w for h, w in zip(Hs, Ws))
+        dev = ls[0].device
+        o_logits = torch.empty((B, A, 2), dtype=torch.float32, device=dev)
+        o_class = torch.empty((B, A, 2), dtype=torch.float32, device=dev) if want_class else None
+        o_bbox = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+        o_fg = torch.empty((B, A), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.mrcnn_rpn_pack(_ptr_array(ls), _ptr_array(bs), _int_array(Hs), _int_array(Ws), n_levels, B, K, layout,
+                                     o_logits.data_ptr(), _ptr(o_class), o_bbox.data_ptr(), o_fg.data_ptr(), _stream()))
+        ctx.geom = (Hs, Ws, B, K, layout, n_levels)
+        ctx.set_materialize_grads(False)   # an output the loss does not read costs no unpack pass
+        if o_class is None:
+            o_class = o_fg.new_empty(0)
+        ctx.mark_non_differentiable(o_class, o_fg)   # the probabilities only feed the proposal layer (no gradient path)
+        return o_logits, o_class, o_bbox, o_fg
+
+    @staticmethod
+    def backward(ctx, g_logits, _g_class, g_bbox, _g_fg):
+        Hs, Ws, B, K, layout, n = ctx.geom
+        need_l = any(ctx.needs_input_grad[2:2 + n]) and g_logits is not None
+        need_b = any(ctx.needs_input_grad[2 + n:]) and g_bbox is not None
+        if not need_l and not need_b:
+            return (None, None) + (None,) * (2 * n)
+        dev = (g_logits if need_l else g_bbox).device
+        mf = torch.channels_last if layout == NHWC else torch.contiguous_format
+        gl = [torch.empty((B, 2 * K, h, w), dtype=torch.float32, device=dev, memory_format=mf) for h, w in zip(Hs, Ws)] if need_l else None
+        gb = [torch.empty((B, 4 * K, h, w), dtype=torch.float32, device=dev, memory_format=mf) for h, w in zip(Hs, Ws)] if need_b else None
+        with torch.cuda.device(dev):
+            check(lib.mrcnn_rpn_unpack(g_logits.contiguous().data_ptr() if need_l else None,
+                                       g_bbox.contiguous().data_ptr() if need_b else None, _int_array(Hs), _int_array(Ws), n, B, K,
+                                       layout, _ptr_array(gl) if need_l else None, _ptr_array(gb) if need_b else None, _stream()))
+        none = [None] * n
+        return (None, None) + tuple(gl if need_l else none) + tuple(gb if need_b else none)
+
+
+def rpn_pack(class_logits, bboxes, want_class=True):
+    """One launch for everything between the RPN head's two 1x1 convolutions and the proposal layer: class_logits[l]
+    [B,2K,H_l,W_l] and bboxes[l] [B,4K,H_l,W_l] (conv outputs of every pyramid level, NCHW or channels-last) ->
+    (rpn_class_logits [B,A,2], rpn_class [B,A,2] = softmax, rpn_bbox [B,A,4], fg [B,A] = rpn_class[..., 1]) in the
+    reference's anchor order (model.py:624-641 per level, torch.cat over levels :1294-1304).  Differentiable w.r.t. the
+    conv outputs through rpn_class_logits and rpn_bbox (what the RPN losses read)."""
+    class_logits, bboxes = list(class_logits), list(bboxes)
+    out = _RpnPack.apply(len(class_logits), bool(want_class), *class_logits, *bboxes)
+    return out[0], (out[1] if want_class else None), out[2], out[3]
+
+
+def rpn_detect(self, rpn_feature_maps):
+    """Drop-in for MaskRCNN.rpn_detect (model.py:1294-1304): runs the RPN head's three convolutions per level on stock
+    PyTorch / cuDNN (self.rpn: padding, conv_shared, relu, conv_class, conv_bbox - model.py:600-641) and replaces the
+    per-level permute / contiguous / view / softmax and the three torch.cat by one rpn_pack launch.  Returns
+    (rpn_class_logits, rpn_class, rpn_bbox) like the reference."""
+    rpn = self.rpn
+    logits, bboxes = [], []
+    for p in rpn_feature_maps:
+        x = rpn.relu(rpn.conv_shared(rpn.padding(p)))
+        logits.append(rpn.conv_class(x))
+        bboxes.append(rpn.conv_bbox(x))
+    rpn_class_logits, rpn_class, rpn_bbox, _ = rpn_pack(logits, bboxes)
+    return rpn_class_logits, rpn_class, rpn_bbox
 
 
 def rpn_refine(self, rpn_class, rpn_bbox, pre_nms_limit=None):

@@ -74,6 +74,8 @@ def lib():
         L.orc_full_masks.restype = ctypes.c_int
         L.orc_full_masks.argtypes = [_i64p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.POINTER(ctypes.c_uint8)]
+        L.orc_rpn_pack.restype = None
+        L.orc_rpn_pack.argtypes = [pp, pp, ip, ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p]
         L.orc_boxes_refine.restype = None
         L.orc_boxes_refine.argtypes = [_f32p, _f32p, ctypes.c_int64, _f32p]
         _lib = L
@@ -322,3 +324,19 @@ def full_masks(class_ids, boxes, masks, height, width):
     if rc != 0:
         raise ValueError("full_masks: detection %d has an empty box" % (-rc - 1))
     return out.astype(bool)
+
+
+def rpn_pack(class_logits, bboxes):
+    """model.py:624-641 + :1294-1304: per-level conv outputs class_logits[l] [B,2K,H,W], bboxes[l] [B,4K,H,W] (NCHW) ->
+    (rpn_class_logits [B,A,2], rpn_class [B,A,2], rpn_bbox [B,A,4])."""
+    ls, bs = [_f32(t) for t in class_logits], [_f32(t) for t in bboxes]
+    n = len(ls)
+    B, K = ls[0].shape[0], ls[0].shape[1] // 2
+    Hs = (ctypes.c_int * n)(*[t.shape[2] for t in ls])
+    Ws = (ctypes.c_int * n)(*[t.shape[3] for t in ls])
+    A = K * sum(t.shape[2] * t.shape[3] for t in ls)
+    o_l, o_c, o_b = np.zeros((B, A, 2), np.float32), np.zeros((B, A, 2), np.float32), np.zeros((B, A, 4), np.float32)
+    lp = (_f32p * n)(*[_p(t) for t in ls])
+    bp = (_f32p * n)(*[_p(t) for t in bs])
+    lib().orc_rpn_pack(lp, bp, Hs, Ws, n, B, K, _p(o_l), _p(o_c), _p(o_b))
+    return o_l, o_c, o_b

@@ -50,3 +50,14 @@ def golden_masks(tag):
     d = len(boxes)
     want = np.unpackbits(g[f"{tag}_out_bits"])[:d * h * w].reshape(d, h, w).astype(bool)
     return np.zeros(d, np.int64), boxes, np.ascontiguousarray(sel[:, None]), h, w, want
+
+
+def golden_rpnhead():
+    """(class-logit conv outputs per level, bbox conv outputs per level, expected logits / class / bbox) of
+    tests/golden/golden_rpnhead_v1.npz."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_rpnhead_v1.npz"))
+    n = sum(1 for k in g.files if k.startswith("in_logits_"))
+    return [g[f"in_logits_{l}"] for l in range(n)], [g[f"in_bbox_{l}"] for l in range(n)], g["out_logits"], g["out_class"], g["out_bbox"]
+
+
+SOFTMAX_TOL = 1e-6  # absolute, on probabilities in [0, 1]: torch's CPU softmax uses an approximate vectorised exp

@@ -682,3 +682,93 @@ def test_full_masks_full_size_properties(ops):
     for i in range(16):
         y1, x1, y2, x2 = (int(v) for v in boxes[i])
         assert torch.equal(at0[i, :y2 - y1, :x2 - x1], got[i, y1:y2, x1:x2])
+
+
+# ------------------------------------------------------------------ RPN head output plumbing (rpn_detect)
+def _rpn_conv_outputs(B, K, sides, seed):
+    rng = np.random.default_rng(seed)
+    ls = [(rng.standard_normal((B, 2 * K, h, w)) * 4.0).astype(np.float32) for h, w in sides]
+    bs = [rng.standard_normal((B, 4 * K, h, w)).astype(np.float32) for h, w in sides]
+    return ls, bs
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("B,K,sides", [(2, 3, [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4)]), (1, 3, [(7, 9), (3, 5)]), (3, 1, [(5, 4)]),
+                                       (2, 5, [(6, 6), (1, 1)])])
+def test_rpn_pack_matches_oracle(ops, B, K, sides, channels_last):
+    ls, bs = _rpn_conv_outputs(B, K, sides, 3 + B + K)
+    want = oracle.rpn_pack(ls, bs)
+    conv = (lambda a: cl(dev(a))) if channels_last else dev
+    logits, cls, bbox, fg = ops.rpn_pack([conv(a) for a in ls], [conv(a) for a in bs])
+    np.testing.assert_array_equal(logits.cpu().numpy(), want[0])
+    np.testing.assert_array_equal(cls.cpu().numpy(), want[1])       # same operation order, correctly rounded exp: bit-exact
+    np.testing.assert_array_equal(bbox.cpu().numpy(), want[2])
+    np.testing.assert_array_equal(fg.cpu().numpy(), want[1][:, :, 1])
+
+
+def test_rpn_pack_golden(ops):
+    from helpers import SOFTMAX_TOL, golden_rpnhead
+    ls, bs, w_logits, w_class, w_bbox = golden_rpnhead()
+    logits, cls, bbox, fg = ops.rpn_pack([dev(a) for a in ls], [dev(a) for a in bs])
+    np.testing.assert_array_equal(logits.cpu().numpy(), w_logits)
+    np.testing.assert_array_equal(bbox.cpu().numpy(), w_bbox)
+    assert np.abs(cls.cpu().numpy() - w_class).max() <= SOFTMAX_TOL
+    assert np.abs(fg.cpu().numpy() - w_class[:, :, 1]).max() <= SOFTMAX_TOL
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_rpn_pack_backward_is_the_inverse_layout(ops, channels_last):
+    """The losses read rpn_class_logits and rpn_bbox: their gradients must come back exactly as autograd returns them for
+    the reference's permute / view / cat chain."""
+    ls, bs = _rpn_conv_outputs(2, 3, [(12, 10), (6, 5), (3, 3)], 21)
+    conv = (lambda a: cl(dev(a))) if channels_last else dev
+    a_l, a_b = [conv(a).requires_grad_(True) for a in ls], [conv(a).requires_grad_(True) for a in bs]
+    r_l, r_b = [dev(a).requires_grad_(True) for a in ls], [dev(a).requires_grad_(True) for a in bs]
+    logits, _, bbox, _ = ops.rpn_pack(a_l, a_b)
+    ref_logits = torch.cat([t.permute(0, 2, 3, 1).contiguous().view(t.size(0), -1, 2) for t in r_l], 1)
+    ref_bbox = torch.cat([t.permute(0, 2, 3, 1).contiguous().view(t.size(0), -1, 4) for t in r_b], 1)
+    assert torch.equal(logits, ref_logits) and torch.equal(bbox, ref_bbox)
+    g1, g2 = torch.randn_like(ref_logits), torch.randn_like(ref_bbox)
+    (logits * g1).sum().backward()
+    (ref_logits * g1).sum().backward()
+    for a, r in zip(a_l, r_l):
+        assert torch.equal(a.grad, r.grad)
+    assert all(t.grad is None for t in a_b)          # bbox unused: no gradient, no launch for it
+    logits, _, bbox, _ = ops.rpn_pack(a_l, a_b)
+    ((bbox * g2).sum() + (logits * g1).sum()).backward()
+    (ref_bbox * g2).sum().backward()
+    for a, r in zip(a_b, r_b):
+        assert torch.equal(a.grad, r.grad)
+
+
+def test_rpn_detect_dropin_and_fg_proposals(ops):
+    """MaskRCNN.rpn_detect drop-in on a stand-in model (the head's convolutions stay on stock PyTorch) against the
+    reference's per-level permute / softmax / cat expressed in torch, and the proposal layer fed with the fg
+    probabilities alone against the [B,A,2] form."""
+    import types
+    torch.manual_seed(3)
+
+    class Pad(torch.nn.Module):
+        def forward(self, x):
+            return torch.nn.functional.pad(x, (1, 1, 1, 1))
+    rpn = types.SimpleNamespace(padding=Pad(), conv_shared=torch.nn.Conv2d(16, 32, 3).cuda(), relu=torch.nn.ReLU(),
+                                conv_class=torch.nn.Conv2d(32, 6, 1).cuda(), conv_bbox=torch.nn.Conv2d(32, 12, 1).cuda())
+    me = types.SimpleNamespace(rpn=rpn)
+    size = 128
+    feats = [torch.randn(2, 16, size // s, size // s, device="cuda") for s in (4, 8, 16, 32, 64)]
+    with torch.no_grad():
+        logits, cls, bbox = ops.rpn_detect(me, feats)
+        want_l, want_c, want_b = [], [], []
+        for p in feats:
+            x = rpn.relu(rpn.conv_shared(rpn.padding(p)))
+            lg = rpn.conv_class(x).permute(0, 2, 3, 1).contiguous().view(2, -1, 2)
+            want_l.append(lg)
+            want_c.append(torch.softmax(lg, 2))
+            want_b.append(rpn.conv_bbox(x).permute(0, 2, 3, 1).contiguous().view(2, -1, 4))
+    assert torch.equal(logits, torch.cat(want_l, 1)) and torch.equal(bbox, torch.cat(want_b, 1))
+    assert float((cls - torch.cat(want_c, 1)).abs().max()) <= 1e-6
+    anchors = dev(synth.pyramid_anchors((size, size)))
+    assert anchors.size(0) == logits.size(1)
+    a = ops.proposal_layer(cls, bbox, anchors, 600, 100, 0.7, image_hw=(size, size))
+    b = ops.proposal_layer(cls[:, :, 1].contiguous(), bbox, anchors, 600, 100, 0.7, image_hw=(size, size))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

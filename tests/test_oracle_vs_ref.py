@@ -268,3 +268,23 @@ def test_full_masks_empty_box_raises_like_pil():
         d.full_masks(torch.from_numpy(cls), torch.from_numpy(boxes), torch.from_numpy(masks), 64, 64)
     with pytest.raises(ValueError):
         oracle.full_masks(cls, boxes, masks, 64, 64)
+
+
+@needs_model
+def test_rpn_pack_matches_model_py():
+    """oracle.rpn_pack against the reference's RPN module (model.py:573-653) and the torch.cat of rpn_detect (:1294-1304)."""
+    m = reference.load().model
+    torch.manual_seed(5)
+    rpn = m.RPN(3, 1, 16)
+    feats = [torch.randn(2, 16, s, s + 2) * 3.0 for s in (16, 8, 4, 2, 1)]
+    with torch.no_grad():
+        want = [torch.cat(list(o), dim=1).numpy() for o in zip(*[rpn(f) for f in feats])]
+        ls, bs = [], []
+        for f in feats:
+            x = rpn.relu(rpn.conv_shared(rpn.padding(f)))
+            ls.append(rpn.conv_class(x).numpy())
+            bs.append(rpn.conv_bbox(x).numpy())
+    got = oracle.rpn_pack(ls, bs)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[2], want[2])
+    assert np.abs(got[1] - want[1]).max() <= 1e-6   # torch's CPU softmax: approximate vectorised exp
