@@ -263,9 +263,12 @@ MRCNN_API int mrcnn_rpn_deltas(const double* anchors, const int32_t* gt_boxes, c
  * (int(y2 - y1), int(x2 - x1)) with Pillow's 8-bit bilinear resample (22-bit fixed-point weights, horizontal pass into an
  * 8-bit intermediate, then vertical), pasted at (int(y1), int(x1)) clipped to the image, thresholded '> 127'.  Every
  * byte of `out` is written once (no pre-zeroing).  An empty box gives an empty mask (PIL raises ValueError there; zero
- * padded detection rows take this path).  mask_h, mask_w <= 64.  Any D: batches are just more rows. */
+ * padded detection rows take this path).  mask_h, mask_w <= 64.  Any D: batches are just more rows.  workspace: 256-byte
+ * aligned, mrcnn_full_masks_workspace_bytes() bytes (per detection: resampling taps + the 8-bit horizontal pass). */
+MRCNN_API size_t mrcnn_full_masks_workspace_bytes(int D, int mask_h, int mask_w, int H, int W);
 MRCNN_API int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* masks, int D, int NC, int mask_h,
-                               int mask_w, int H, int W, uint8_t* out, mrcnn_stream_t stream);
+                               int mask_w, int H, int W, uint8_t* out, void* workspace, size_t workspace_bytes,
+                               mrcnn_stream_t stream);
 
 #ifdef __cplusplus
 }

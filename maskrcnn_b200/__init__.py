@@ -21,9 +21,10 @@ __version__ = "0.1.0"
 
 def patch(model_module, data_module=None):
     """Monkey-patches an imported reference `model` module (model.py) so that its RoI hot path runs on
-    the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine; with the reference's
-    `data` module given as well, data.rpn_samples (the anchor matching the dataset runs per sample - the reference's
-    DataLoader uses num_workers=0, model.py:1528-1532, so it runs in the CUDA process).  The `maskrcnn` package the
+    the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_detect, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine; with
+    the reference's `data` module given as well, data.rpn_samples (the anchor matching the dataset runs per sample - the
+    reference's DataLoader uses num_workers=0, model.py:1528-1532, so it runs in the CUDA process) and data.full_masks (the
+    mask paste-back model.predict calls as datalib.full_masks, model.py:1190).  The `maskrcnn` package the
     module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
     model_module.roi_align = roi_align
     model_module.MaskRCNN.rpn_refine = rpn_refine

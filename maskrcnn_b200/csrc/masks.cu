@@ -3,10 +3,17 @@
 // The reference turns the [D,81,28,28] mask-head output into [D,H,W] boolean image masks one detection at a time on the
 // CPU: `.item()` / `.tolist()` syncs, a PIL image per detection (mask * 255 -> 'F' -> 'L'), torchvision Resize to the box
 // size (Pillow's 8-bit two-pass bilinear resample), Pad to the image, '> 127', stack, copy back to the GPU.  Here the
-// whole batch is one launch and the only HBM traffic that matters is the output itself (H*W bytes per detection, each
-// written exactly once with 128-bit stores): a CTA walks kGroupBands bands of kBandRows image rows of one detection; for a
-// band the box touches it keeps the 8-bit source mask, the horizontal pass of the source rows the band needs and the
-// per-row vertical taps in shared memory and streams the band out; bands that miss the box are pure zero fill.
+// whole batch is two launches and the only HBM traffic that matters is the output itself (H*W bytes per detection, each
+// written exactly once with 128-bit streaming stores):
+//   paste_prepare_kernel  one CTA per detection: box decode, the 8-bit source mask, Pillow's resampling taps in double
+//                         (22-bit fixed-point weights) for the box's rows and columns, and the HORIZONTAL pass of all
+//                         mask rows into an 8-bit intermediate [mask_h][box width] - a few KB per detection, L2-resident;
+//   full_masks_kernel     pure streaming, no shared memory, no barrier, no fp64: a CTA walks 128 image rows of one
+//                         detection; rows / 16-byte chunks outside the box are zero stores, a chunk inside is <= 3
+//                         128-bit loads of the intermediate (vertical taps) + 16 fixed-point MACs per tap, '> 127', store.
+// First version (one kernel, taps + horizontal pass recomputed per 32-row band behind two barriers): 275 us for 800
+// detections at 1024x1024; with a zero-band fast path 221 us; the barrier / fp64 chains of the ~25 % of bands that touch a
+// box were the rest (a plain write-only stream reaches 6.2 TB/s, profiles/r01_bw_mix.txt).
 //
 // Arithmetic = Pillow's (Resample.c precompute_coeffs / normalize_coeffs_8bpc / ImagingResample{Horizontal,Vertical}_8bpc,
 // Convert.c f2l), bit for bit: tap bounds and weights in double, 22-bit fixed-point weights, 8-bit intermediate image.
@@ -15,8 +22,8 @@
 
 namespace mrcnn {
 
-constexpr int kBandRows = 32;
-constexpr int kGroupBands = 4;  // bands per CTA
+constexpr int kGroupRows = 64;   // image rows per CTA of the streaming kernel
+constexpr int kPrepParts = 4;    // CTAs per detection in the prepare kernel
 constexpr int kMaskThreads = 256;
 constexpr int kPrecBits = 22;   // Resample.c: PRECISION_BITS = 32 - 8 - 2
 constexpr int kMaxMaskSide = 64;
@@ -77,135 +84,200 @@ __device__ __forceinline__ int clip8(int v) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-struct RowTaps {  // vertical taps of one band row, relative to the band's first needed source row
-    int lo, n, k0, k1, k2;
+// Per-detection plan written by paste_prepare_kernel (all offsets in bytes from the detection's workspace slice).
+struct PasteHeader {
+    int live;        // box non-empty, class id valid, box intersects the image
+    int y_lo, y_hi;  // visible rows
+    int x_lo, x_hi;  // visible columns
+    int left16;      // x_lo & ~15: column origin of the intermediate image
+    int ksize;       // weight slots per row
+    int pad;
 };
+
+struct PasteLayout {
+    size_t rows_off;     // int4 {lo, n, 0, 0} per image row y            [H]
+    size_t weights_off;  // int32 [visible row][ksize]
+    size_t hrows_off;    // uint8 [mh][hstride]: horizontal pass of every mask row, column x stored at x - left16
+    size_t det_bytes;
+    int hstride;
+};
+
+__host__ __device__ inline PasteLayout paste_layout(int mh, int H, int W) {
+    PasteLayout l;
+    l.hstride = ((W + 15) / 16) * 16 + 16;
+    l.rows_off = 32;
+    l.weights_off = l.rows_off + (size_t)H * 16;
+    // upscale: <= 3 taps per row; downscale (box shorter than the mask, < 64 rows): <= 2 * 64 + 1 taps per row
+    const size_t wcap = (size_t)3 * H > (size_t)64 * 132 ? (size_t)3 * H : (size_t)64 * 132;
+    l.hrows_off = l.weights_off + wcap * 4;
+    l.hrows_off = (l.hrows_off + 15) / 16 * 16;
+    l.det_bytes = (l.hrows_off + (size_t)mh * l.hstride + 255) / 256 * 256;
+    return l;
+}
 
 struct PasteParams {
     const int64_t* class_ids;  // [D]
     const float* boxes;        // [D,4] px
     const float* masks;        // [D,NC,mh,mw]
-    int D, NC, mh, mw, H, W, bands;  // bands = CTAs per detection
-    int tmp_stride;            // bytes per row of the horizontal-pass buffer (multiple of 16)
+    int D, NC, mh, mw, H, W, groups;
+    unsigned char* ws;
     uint8_t* out;              // [D,H,W]
     int* err;
 };
 
-template <bool kVec>
-__global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PasteParams p) {
-    extern __shared__ __align__(16) unsigned char mk_smem[];
-    uint8_t* s_tmp = mk_smem;                                              // [mh][tmp_stride]
-    uint8_t* s_src = mk_smem + (size_t)p.mh * p.tmp_stride;               // [mh*mw]
-    __shared__ RowTaps s_rows[kBandRows];
-    __shared__ AxisTaps s_slow[kBandRows];  // only read for rows with more than 3 taps (downscale)
-    const int tid = threadIdx.x;
-    const int d = blockIdx.x / p.bands, group = blockIdx.x - d * p.bands;
-
+__global__ void __launch_bounds__(kMaskThreads) paste_prepare_kernel(const PasteParams p) {
+    __shared__ uint8_t s_src[kMaxMaskSide * kMaxMaskSide];
+    __shared__ int s_acc[kMaxMaskSide * kMaxMaskSide];  // [mask row][column], downscale path only
+    const int tid = threadIdx.x, d = blockIdx.x / kPrepParts, part = blockIdx.x - d * kPrepParts;
+    const PasteLayout L = paste_layout(p.mh, p.H, p.W);
+    unsigned char* ws = p.ws + (size_t)d * L.det_bytes;
     // data.py:294-300: Python floats, int() truncates towards zero
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.boxes) + d);
     const int bh = (int)__dsub_rn((double)b.z, (double)b.x), bw = (int)__dsub_rn((double)b.w, (double)b.y);
     const int top = (int)b.x, left = (int)b.y;
     const long long cls = __ldg(p.class_ids + d);
     const bool cls_ok = cls >= 0 && cls < p.NC;
-    if (!cls_ok && tid == 0 && group == 0) atomicOr(p.err, 2);
-    const int x_lo = max(0, left), x_hi = min(p.W, left + bw);
-    const int left16 = x_lo & ~15;  // the horizontal-pass buffer is aligned with the 16-byte output chunks
-    bool src_staged = false;
-
-    // a CTA walks kGroupBands bands of kBandRows rows: the box decode above is paid once per 128 KB of output
-    for (int band = group * kGroupBands; band < min((group + 1) * kGroupBands, (p.H + kBandRows - 1) / kBandRows); ++band) {
-    const int r0 = band * kBandRows;
-    const int r1 = min(r0 + kBandRows, p.H);
     // an empty box gives an empty mask (PIL raises ValueError; zero-padded detection rows land here)
-    const int y_lo = max(r0, top), y_hi = min(r1, top + bh);
+    const int y_lo = max(0, top), y_hi = min(p.H, top + bh);
+    const int x_lo = max(0, left), x_hi = min(p.W, left + bw);
     const bool live = cls_ok && bh > 0 && bw > 0 && y_lo < y_hi && x_lo < x_hi;
-    uint8_t* out = p.out + ((size_t)d * p.H + r0) * p.W;
-
-    if (live) {
-        // 'F' -> 'L' (Convert.c f2l) of mask * 255.0 (data.py:291)
-        if (!src_staged) {
-            const float* m = p.masks + ((size_t)d * p.NC + (size_t)cls) * p.mh * p.mw;
-            for (int i = tid; i < p.mh * p.mw; i += kMaskThreads) {
-                const float v = __fmul_rn(__ldg(m + i), 255.0f);
-                s_src[i] = v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (uint8_t)(int)v);
+    const int left16 = x_lo & ~15;
+    const double vscale = (double)p.mh / (double)max(bh, 1);
+    const int ksize = 2 * (int)ceil(vscale < 1.0 ? 1.0 : vscale) + 1;
+    if (tid == 0 && part == 0) {
+        if (!cls_ok) atomicOr(p.err, 2);
+        PasteHeader h = {live ? 1 : 0, y_lo, y_hi, x_lo, x_hi, left16, ksize, 0};
+        *reinterpret_cast<PasteHeader*>(ws) = h;
+    }
+    if (!live || part * kMaskThreads >= (y_hi - y_lo) + (x_hi - x_lo)) return;  // nothing to do for this quarter
+    // 'F' -> 'L' (Convert.c f2l) of mask * 255.0 (data.py:291)
+    const float* m = p.masks + ((size_t)d * p.NC + (size_t)cls) * p.mh * p.mw;
+    for (int i = tid; i < p.mh * p.mw; i += kMaskThreads) {
+        const float v = __fmul_rn(__ldg(m + i), 255.0f);
+        s_src[i] = v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (uint8_t)(int)v);
+    }
+    __syncthreads();
+    // work items of this detection: its visible rows (vertical taps) and its visible columns (horizontal taps + the
+    // horizontal pass of every mask row into the 8-bit intermediate the vertical pass reads); a quarter per CTA
+    int4* rows = reinterpret_cast<int4*>(ws + L.rows_off);
+    int* weights = reinterpret_cast<int*>(ws + L.weights_off);
+    uint8_t* hrows = ws + L.hrows_off;
+    const int n_rows = y_hi - y_lo, n_items = n_rows + (x_hi - x_lo);
+    for (int it = part * kMaskThreads + tid; it < n_items; it += kMaskThreads * kPrepParts) {
+        if (it < n_rows) {
+            const int y = y_lo + it;
+            const AxisTaps t = axis_taps(p.mh, bh, y - top);
+            rows[y] = make_int4(t.lo, t.n, 0, 0);
+            int* w = weights + (size_t)it * ksize;
+            if (t.n <= 3) {
+                w[0] = t.k0;
+                if (t.n > 1) w[1] = t.k1;
+                if (t.n > 2) w[2] = t.k2;
+            } else {
+                for (int j = 0; j < t.n; ++j) w[j] = fixed_weight(t, j);
             }
-            src_staged = true;
-        }
-        // vertical taps of the band's rows
-        if (tid < y_hi - y_lo) {
-            const AxisTaps t = axis_taps(p.mh, bh, y_lo + tid - top);
-            s_rows[tid] = {t.lo, t.n, t.k0, t.k1, t.k2};
-            if (t.n > 3) s_slow[tid] = t;
-        }
-        __syncthreads();
-        const int src_lo = s_rows[0].lo;
-        const int src_hi = s_rows[y_hi - y_lo - 1].lo + s_rows[y_hi - y_lo - 1].n;
-        // horizontal pass of source rows [src_lo, src_hi) for the visible columns -> 8-bit intermediate
-        for (int x = x_lo + tid; x < x_hi; x += kMaskThreads) {
+        } else {
+            const int x = x_lo + (it - n_rows);
             const AxisTaps t = axis_taps(p.mw, bw, x - left);
-            uint8_t* dst = s_tmp + (x - left16);
-            for (int r = src_lo; r < src_hi; ++r) {
-                const uint8_t* s = s_src + r * p.mw + t.lo;
-                int acc = 1 << (kPrecBits - 1);
-                if (t.n <= 3) {
-                    acc += (int)s[0] * t.k0;
+            uint8_t* dst = hrows + (x - left16);
+            if (t.n <= 3) {
+                for (int r = 0; r < p.mh; ++r) {
+                    const uint8_t* s = s_src + r * p.mw + t.lo;
+                    int acc = (1 << (kPrecBits - 1)) + (int)s[0] * t.k0;
                     if (t.n > 1) acc += (int)s[1] * t.k1;
                     if (t.n > 2) acc += (int)s[2] * t.k2;
-                } else {
-                    for (int j = 0; j < t.n; ++j) acc += (int)s[j] * fixed_weight(t, j);
+                    dst[(size_t)r * L.hstride] = (uint8_t)clip8(acc);
                 }
-                dst[(size_t)(r - src_lo) * p.tmp_stride] = (uint8_t)clip8(acc);
+            } else {
+                // downscale (box narrower than the mask, so fewer than kMaxMaskSide columns): tap-major, every fixed-point
+                // weight (an fp64 division) is computed once and the per-row sums live in shared memory
+                int* acc = s_acc + (x - x_lo);
+                for (int r = 0; r < p.mh; ++r) acc[r * kMaxMaskSide] = 1 << (kPrecBits - 1);
+                for (int j = 0; j < t.n; ++j) {
+                    const int k = fixed_weight(t, j);
+                    for (int r = 0; r < p.mh; ++r) acc[r * kMaxMaskSide] += (int)s_src[r * p.mw + t.lo + j] * k;
+                }
+                for (int r = 0; r < p.mh; ++r) dst[(size_t)r * L.hstride] = (uint8_t)clip8(acc[r * kMaxMaskSide]);
             }
         }
-        __syncthreads();
     }
+}
 
+template <bool kVec>
+__global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PasteParams p) {
+    const int tid = threadIdx.x;
+    const int d = blockIdx.x / p.groups, group = blockIdx.x - d * p.groups;
+    const int r0 = group * kGroupRows, r1 = min(r0 + kGroupRows, p.H);
+    const PasteLayout L = paste_layout(p.mh, p.H, p.W);
+    const unsigned char* ws = p.ws + (size_t)d * L.det_bytes;
+    const int4 h0 = __ldg(reinterpret_cast<const int4*>(ws)), h1 = __ldg(reinterpret_cast<const int4*>(ws) + 1);
+    const int y_lo = h0.y, y_hi = h0.z, x_lo = h0.w, x_hi = h1.x, left16 = h1.y, ksize = h1.z;
+    const bool live = h0.x != 0 && y_lo < r1 && y_hi > r0;  // the box touches this CTA's rows
+    uint8_t* out = p.out + ((size_t)d * p.H + r0) * p.W;
+    const int4* rows = reinterpret_cast<const int4*>(ws + L.rows_off);
+    const int* weights = reinterpret_cast<const int*>(ws + L.weights_off);
+    const uint8_t* hrows = ws + L.hrows_off;
     if (kVec) {
         const int chunks = p.W >> 4;  // 16-byte chunks per row
         if (!live) {
-            // a band the box misses (94 % of them at the bench size) is one contiguous block of zeros
+            // rows the box misses (three quarters of the CTAs at the bench size) are one contiguous block of zeros
             uint4* o = reinterpret_cast<uint4*>(out);
             const int n = (r1 - r0) * chunks;
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             for (int i = tid; i < n; i += kMaskThreads) __stcs(o + i, z);
-            continue;
+            return;
         }
-        // warp w owns rows w, w + 8, ...; a lane owns 16-byte chunks lane, lane + 32, ...: every byte is written once
-        const int warp = tid >> 5, lane = tid & 31;
-        const int src_lo = s_rows[0].lo;
+        // (A) zero stores: whole rows above / below the box, then the chunks left / right of it
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const int ya = max(y_lo, r0), yb = min(y_hi, r1);     // box rows of this CTA
         const int c_lo = x_lo >> 4, c_hi = (x_hi + 15) >> 4;  // chunks that intersect the box
-        for (int y = r0 + warp; y < r1; y += kMaskThreads / 32) {
-            uint4* orow = reinterpret_cast<uint4*>(out + (size_t)(y - r0) * p.W);
-            const bool row_live = y >= y_lo && y < y_hi;
-            RowTaps rt = {0, 0, 0, 0, 0};
-            if (row_live) rt = s_rows[y - y_lo];
-            for (int c = lane; c < chunks; c += 32) {
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (row_live && c >= c_lo && c < c_hi) {
-                    const int x0 = c << 4;
-                    int acc[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = 1 << (kPrecBits - 1);
-                    const uint8_t* col = s_tmp + (size_t)(rt.lo - src_lo) * p.tmp_stride + (x0 - left16);
-                    for (int j = 0; j < rt.n; ++j) {
-                        const int k = rt.n <= 3 ? (j == 0 ? rt.k0 : (j == 1 ? rt.k1 : rt.k2)) : fixed_weight(s_slow[y - y_lo], j);
-                        const uint4 v = *reinterpret_cast<const uint4*>(col + (size_t)j * p.tmp_stride);
-                        const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] += (int)((w[i >> 2] >> ((i & 3) * 8)) & 0xffu) * k;
-                    }
-                    unsigned w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int x = x0 + i;
-                        // clip8(acc) > 127 (data.py:307) <=> acc >= 128 << 22: the clamp to 255 cannot change the comparison
-                        const unsigned bit = (x >= x_lo && x < x_hi && acc[i] >= (128 << kPrecBits)) ? 1u : 0u;
-                        w[i >> 2] |= bit << ((i & 3) * 8);
-                    }
-                    o = make_uint4(w[0], w[1], w[2], w[3]);
+        {
+            uint4* o = reinterpret_cast<uint4*>(out);
+            const int n_above = (ya - r0) * chunks;
+            for (int i = tid; i < n_above; i += kMaskThreads) __stcs(o + i, z);
+            uint4* o2 = o + (size_t)(yb - r0) * chunks;
+            const int n_below = (r1 - yb) * chunks;
+            for (int i = tid; i < n_below; i += kMaskThreads) __stcs(o2 + i, z);
+            const int nz = chunks - (c_hi - c_lo);  // zero chunks per box row
+            if (nz > 0) {
+                uint4* o3 = o + (size_t)(ya - r0) * chunks;
+                const int n_side = (yb - ya) * nz;
+                for (int i = tid; i < n_side; i += kMaskThreads) {
+                    const int row = i / nz, j = i - row * nz;
+                    __stcs(o3 + (size_t)row * chunks + (j < c_lo ? j : j - c_lo + c_hi), z);
                 }
-                __stcs(orow + c, o);
             }
+        }
+        // (B) the chunks inside the box, flattened over (row, chunk) so that every thread has live work
+        const int ncl = c_hi - c_lo;
+        const int n_live = (yb - ya) * ncl;
+#pragma unroll 2
+        for (int i = tid; i < n_live; i += kMaskThreads) {
+            const int row = i / ncl, c = c_lo + (i - row * ncl);
+            const int y = ya + row, x0 = c << 4;
+            const int4 rt = __ldg(rows + y);
+            const int* wrow = weights + (size_t)(y - y_lo) * ksize;
+            const uint8_t* col = hrows + (size_t)rt.x * L.hstride + (x0 - left16);
+            int acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = 1 << (kPrecBits - 1);
+            for (int j = 0; j < rt.y; ++j) {
+                const int k = __ldg(wrow + j);
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(col + (size_t)j * L.hstride));
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] += (int)((w[q >> 2] >> ((q & 3) * 8)) & 0xffu) * k;
+            }
+            // clip8(acc) > 127 (data.py:307) <=> acc >= 128 << 22: the clamp to 255 cannot change the comparison
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q >> 2] |= (acc[q] >= (128 << kPrecBits) ? 1u : 0u) << ((q & 3) * 8);
+            if (x0 < x_lo || x0 + 16 > x_hi) {  // a chunk on the box's left / right edge: drop the columns outside
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (x0 + q < x_lo || x0 + q >= x_hi) w[q >> 2] &= ~(0xffu << ((q & 3) * 8));
+            }
+            __stcs(reinterpret_cast<uint4*>(out + (size_t)(y - r0) * p.W) + c, make_uint4(w[0], w[1], w[2], w[3]));
         }
     } else {
         const int n = (r1 - r0) * p.W;
@@ -214,19 +286,15 @@ __global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PastePar
             const int y = r0 + row;
             uint8_t o = 0;
             if (live && y >= y_lo && y < y_hi && x >= x_lo && x < x_hi) {
-                const RowTaps rt = s_rows[y - y_lo];
-                const uint8_t* col = s_tmp + (size_t)(rt.lo - s_rows[0].lo) * p.tmp_stride + (x - left16);
+                const int4 rt = __ldg(rows + y);
+                const int* wrow = weights + (size_t)(y - y_lo) * ksize;
+                const uint8_t* col = hrows + (size_t)rt.x * L.hstride + (x - left16);
                 int acc = 1 << (kPrecBits - 1);
-                for (int j = 0; j < rt.n; ++j) {
-                    const int k = rt.n <= 3 ? (j == 0 ? rt.k0 : (j == 1 ? rt.k1 : rt.k2)) : fixed_weight(s_slow[y - y_lo], j);
-                    acc += (int)col[(size_t)j * p.tmp_stride] * k;
-                }
+                for (int j = 0; j < rt.y; ++j) acc += (int)__ldg(col + (size_t)j * L.hstride) * __ldg(wrow + j);
                 o = clip8(acc) > 127;
             }
             out[idx] = o;
         }
-    }
-    if (live) __syncthreads();  // the next band overwrites s_rows / s_tmp
     }
 }
 
@@ -236,8 +304,14 @@ using namespace mrcnn;
 
 extern "C" {
 
+size_t mrcnn_full_masks_workspace_bytes(int D, int mask_h, int mask_w, int H, int W) {
+    (void)mask_w;
+    if (D <= 0 || mask_h <= 0 || H <= 0 || W <= 0) return 256;
+    return paste_layout(mask_h, H, W).det_bytes * (size_t)D;
+}
+
 int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* masks, int D, int NC, int mask_h, int mask_w,
-                     int H, int W, uint8_t* out, mrcnn_stream_t stream_) {
+                     int H, int W, uint8_t* out, void* workspace, size_t workspace_bytes, mrcnn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(D >= 0 && NC > 0 && H > 0 && W > 0, "mrcnn_full_masks: bad sizes");
     MRCNN_REQUIRE(mask_h > 0 && mask_w > 0 && mask_h <= kMaxMaskSide && mask_w <= kMaxMaskSide,
@@ -247,22 +321,26 @@ int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* 
     MRCNN_REQUIRE_DEV(boxes);
     MRCNN_REQUIRE_DEV(masks);
     MRCNN_REQUIRE_DEV(out);
+    MRCNN_REQUIRE_DEV(workspace);
     MRCNN_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15u) == 0, "mrcnn_full_masks: boxes must be 16-byte aligned");
+    if (workspace_bytes < mrcnn_full_masks_workspace_bytes(D, mask_h, mask_w, H, W) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return fail(MRCNN_E_WORKSPACE, "mrcnn_full_masks: workspace too small or not 256-byte aligned");
     PasteParams p;
     p.class_ids = class_ids; p.boxes = boxes; p.masks = masks;
     p.D = D; p.NC = NC; p.mh = mask_h; p.mw = mask_w; p.H = H; p.W = W;
-    p.bands = (H + kBandRows * kGroupBands - 1) / (kBandRows * kGroupBands);  // CTAs per detection
-    p.tmp_stride = (int)align_up((size_t)W, 16) + 16;
+    p.groups = (H + kGroupRows - 1) / kGroupRows;
+    p.ws = reinterpret_cast<unsigned char*>(workspace);
     p.out = out;
     p.err = device_error_word();
     MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
-    MRCNN_REQUIRE((long long)D * p.bands < (1ll << 31), "mrcnn_full_masks: too many detections");
-    const size_t smem = (size_t)mask_h * p.tmp_stride + align_up((size_t)mask_h * mask_w, 16);
-    MRCNN_REQUIRE(smem <= 200 * 1024, "mrcnn_full_masks: image too wide for the shared-memory row buffer");
+    MRCNN_REQUIRE((long long)D * (p.groups > kPrepParts ? p.groups : kPrepParts) < (1ll << 31), "mrcnn_full_masks: too many detections");
+    paste_prepare_kernel<<<D * kPrepParts, kMaskThreads, 0, stream>>>(p);
+    MRCNN_LAUNCH_CHECK();
     const bool vec = (W % 16 == 0) && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    auto kern = vec ? full_masks_kernel<true> : full_masks_kernel<false>;
-    if (smem > 48 * 1024) MRCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<D * p.bands, kMaskThreads, smem, stream>>>(p);
+    if (vec)
+        full_masks_kernel<true><<<D * p.groups, kMaskThreads, 0, stream>>>(p);
+    else
+        full_masks_kernel<false><<<D * p.groups, kMaskThreads, 0, stream>>>(p);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }

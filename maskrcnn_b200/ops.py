@@ -735,7 +735,7 @@ def rpn_samples(anchors, gt_class_ids, gt_boxes, config, device=None, return_ten
 def full_masks(class_id, boxes, masks, height, width):
     """Drop-in for data.full_masks (data.py:287-314): class_id [D] integer, boxes [D,4] px (y1,x1,y2,x2), masks
     [D,NC,mh,mw] float -> bool [D,height,width], bit-identical to the reference's PIL route (mask * 255 -> 8 bit ->
-    Pillow bilinear resize to the box -> paste -> '> 127').  One launch for all detections and no host round trip (the
+    Pillow bilinear resize to the box -> paste -> '> 127').  Two launches for all detections and no host round trip (the
     reference does `.item()`, `.tolist()` and a CPU copy per detection); leading batch dimensions are allowed
     (class_id [...,D], boxes [...,D,4], masks [...,D,NC,mh,mw] -> [...,D,height,width]).  Unlike the reference, which
     raises ValueError from PIL, an empty box gives an all-False mask (zero-padded detection rows)."""
@@ -753,5 +753,8 @@ def full_masks(class_id, boxes, masks, height, width):
     mk = masks.detach().reshape(-1, NC, mh, mw).float().contiguous()
     out = torch.empty((D, H, W), dtype=torch.bool, device=masks.device)
     with torch.cuda.device(masks.device):
-        check(lib.mrcnn_full_masks(cls.data_ptr(), bx.data_ptr(), mk.data_ptr(), D, NC, mh, mw, H, W, out.data_ptr(), _stream()))
+        ws_bytes = lib.mrcnn_full_masks_workspace_bytes(D, mh, mw, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
+        check(lib.mrcnn_full_masks(cls.data_ptr(), bx.data_ptr(), mk.data_ptr(), D, NC, mh, mw, H, W, out.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, _stream()))
     return out.reshape(lead + (H, W))

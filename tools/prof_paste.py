@@ -26,8 +26,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     out = torch.empty((D, IMAGE, IMAGE), dtype=torch.bool, device=dev)
     from maskrcnn_b200 import _lib as L
     s = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(L.lib.mrcnn_full_masks_workspace_bytes(D, 28, 28, IMAGE, IMAGE), dtype=torch.uint8, device=dev)
     f = lambda: L.check(L.lib.mrcnn_full_masks(cls_d.data_ptr(), boxes_d.data_ptr(), masks_d.data_ptr(), D, 81, 28, 28, IMAGE, IMAGE,
-                                               out.data_ptr(), s))
+                                               out.data_ptr(), ws.data_ptr(), ws.numel(), s))
     for _ in range(3):
         f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,6 +39,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 20 * 1e-3
     print("full_masks %.1f us  %.0f GB/s" % (t * 1e6, D * IMAGE * IMAGE / t / 1e9))
+    boxes_d.zero_()
+    for _ in range(3):
+        f()
+    e0.record()
+    for _ in range(20):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20 * 1e-3
+    print("full_masks, every box empty %.1f us  %.0f GB/s" % (t * 1e6, D * IMAGE * IMAGE / t / 1e9))
     z = lambda: out.zero_()
     z()
     e0.record()
