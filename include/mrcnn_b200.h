@@ -155,6 +155,17 @@ MRCNN_API int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox
                          float* rois_out, int32_t* counts_out,
                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
 
+/* NMS inside the proposal layer (process-wide switch; results are identical):
+ *   MRCNN_PROPOSAL_NMS_MASK  batched 64x64 IoU-bitmask tiles (upper triangle) + one single-CTA sweep per image;
+ *   MRCNN_PROPOSAL_NMS_LAZY  one CTA per image, boxes taken 64 at a time in score order and compared only with the
+ *                            survivors found so far, stopping at the post_nms-th survivor: 64 * sum(survivors so far) IoU
+ *                            tests instead of n^2 / 2;
+ *   MRCNN_PROPOSAL_NMS_AUTO  LAZY when post_nms <= 2048, MASK otherwise (default). */
+#define MRCNN_PROPOSAL_NMS_AUTO 0
+#define MRCNN_PROPOSAL_NMS_MASK 1
+#define MRCNN_PROPOSAL_NMS_LAZY 2
+MRCNN_API int mrcnn_set_proposal_nms(int algo);
+
 /* The same with the foreground probabilities alone, fg_scores [B,A] (what mrcnn_rpn_pack writes as fg_out): the layer's
  * only pass over the scores reads half the bytes. */
 MRCNN_API int mrcnn_proposal_layer_fg(const float* fg_scores, const float* rpn_bbox, const float* anchors,

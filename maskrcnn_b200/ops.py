@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "rpn_pack", "rpn_detect", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -38,6 +38,15 @@ def set_backward_algorithm(name):
     if name not in ("auto", "gather", "scatter"):
         raise ValueError("backward algorithm must be 'auto', 'gather' or 'scatter'")
     BACKWARD_ALGORITHM = name
+
+
+def set_proposal_nms(name):
+    """NMS inside the proposal layer: "auto" (lazy when post_nms <= 2048), "mask" (IoU-bitmask tiles + sweep) or "lazy"
+    (chunks of 64 boxes against the survivors so far, stops at the post_nms-th survivor).  Identical results."""
+    algos = {"auto": 0, "mask": 1, "lazy": 2}
+    if name not in algos:
+        raise ValueError("proposal NMS must be 'auto', 'mask' or 'lazy'")
+    check(lib.mrcnn_set_proposal_nms(algos[name]))
 
 
 def _stream():

@@ -63,8 +63,10 @@ def unique_scores(n, seed, lo=0.0, hi=1.0):
     return v[rng.permutation(n)]
 
 
-def rpn_outputs(anchors, seed, image=1024.0, n_clusters=40, delta_sigma=0.5):
-    """(rpn_class [A,2], rpn_bbox [A,4]) for one image.
+def rpn_outputs(anchors, seed, image=1024.0, n_clusters=40, delta_sigma=0.5, converge=0.0):
+    """(rpn_class [A,2], rpn_bbox [A,4]) for one image.  `converge` in (0, 1]: anchors close to an 'object' (and within a
+    factor two of its size) regress towards the object's box, as a trained RPN's do, so that the top of the ranking is
+    full of near-duplicates and NMS suppresses most of it from the first boxes on (0 = independent random deltas).
 
     Foreground scores are unique; the top of the ranking is concentrated on anchors close to a few
     'object' centres so that, as in a real RPN, most of the top-k proposals overlap and are
@@ -78,14 +80,31 @@ def rpn_outputs(anchors, seed, image=1024.0, n_clusters=40, delta_sigma=0.5):
     affinity = np.zeros(A, dtype=np.float64)
     for (oy, ox), s in zip(centres, sig):
         affinity = np.maximum(affinity, np.exp(-((cy - oy) ** 2 + (cx - ox) ** 2) / (2 * s * s)))
-    rank_key = affinity + 0.35 * rng.uniform(0, 1, A)
+    noise = rng.uniform(0, 1, A)
+    rpn_bbox = (rng.standard_normal((A, 4)) * delta_sigma).astype(np.float32)
+    hit = np.zeros(A, dtype=bool)
+    if converge > 0.0:
+        ah, aw = anchors[:, 2] - anchors[:, 0], anchors[:, 3] - anchors[:, 1]
+        best = np.zeros(A, dtype=np.float64)
+        target = np.zeros((A, 4), dtype=np.float64)
+        for (oy, ox), s in zip(centres, sig):
+            aff = np.exp(-((cy - oy) ** 2 + (cx - ox) ** 2) / (2 * s * s))
+            side = 3.0 * s
+            near = (aff > best) & (np.abs(np.log(side / ah)) < 0.7) & (np.abs(np.log(side / aw)) < 0.7)
+            t = np.stack([(oy - cy) / ah, (ox - cx) / aw, np.log(side / ah), np.log(side / aw)], 1) / np.asarray(RPN_BBOX_STD_DEV)
+            target[near] = t[near]
+            best[near] = aff[near]
+        hit = best > 0.3
+        mix = (converge * target + (1.0 - converge) * rpn_bbox + rng.standard_normal((A, 4)) * 0.05).astype(np.float32)
+        rpn_bbox[hit] = mix[hit]
+    # a trained RPN scores the anchors that match an object in position AND size highest
+    rank_key = affinity + 0.35 * noise + (0.6 * hit if converge > 0.0 else 0.0)
     order = np.argsort(-rank_key, kind="stable")
     vals = np.linspace(1.0, 0.0, A + 2, dtype=np.float64)[1:-1].astype(np.float32)
     assert len(np.unique(vals)) == A
     fg = np.empty(A, dtype=np.float32)
     fg[order] = vals
     rpn_class = np.stack([1.0 - fg, fg], axis=1).astype(np.float32)
-    rpn_bbox = (rng.standard_normal((A, 4)) * delta_sigma).astype(np.float32)
     return rpn_class, rpn_bbox
 
 

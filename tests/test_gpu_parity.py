@@ -281,21 +281,31 @@ def test_roialign_adjoint_full_size(ops, algo):
 
 
 # ------------------------------------------------------------------ proposal layer
-@pytest.mark.parametrize("size,pre,post,B", [(256, 500, 200, 1), (256, 1000, 300, 3), (512, 6000, 1000, 2), (128, 6000, 1000, 2)])
-def test_proposal_layer_matches_oracle(ops, size, pre, post, B):
+@pytest.fixture(params=["lazy", "mask"])
+def nms_algo(request, ops):
+    """Both NMS implementations of the proposal layer must give the oracle's result."""
+    ops.set_proposal_nms(request.param)
+    yield request.param
+    ops.set_proposal_nms("auto")
+
+
+@pytest.mark.parametrize("size,pre,post,B,thr", [(256, 500, 200, 1, 0.7), (256, 1000, 300, 3, 0.7), (512, 6000, 1000, 2, 0.7),
+                                                 (128, 6000, 1000, 2, 0.7), (256, 6000, 2000, 2, 0.3), (256, 777, 1000, 2, 0.9),
+                                                 (256, 3000, 37, 1, 0.5)])
+def test_proposal_layer_matches_oracle(ops, nms_algo, size, pre, post, B, thr):
     anchors = synth.pyramid_anchors((size, size))
     rcs, rbs = zip(*[synth.rpn_outputs(anchors, 50 + i, image=float(size), n_clusters=8) for i in range(B)])
-    rois, counts = ops.proposal_layer(dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors), pre, post, 0.7,
+    rois, counts = ops.proposal_layer(dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors), pre, post, thr,
                                       image_hw=(size, size))
     rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
     for i in range(B):
-        want = oracle.proposal_layer(rcs[i], rbs[i], anchors, pre, post, 0.7, height=float(size), width=float(size))
+        want = oracle.proposal_layer(rcs[i], rbs[i], anchors, pre, post, thr, height=float(size), width=float(size))
         assert counts[i] == len(want)
         np.testing.assert_array_equal(rois[i, :counts[i]], want)       # bit-exact boxes and selection
         assert not rois[i, counts[i]:].any()
 
 
-def test_proposal_layer_with_score_ties(ops):
+def test_proposal_layer_with_score_ties(ops, nms_algo):
     """All-equal and heavily tied scores: the selection must be the stable one (lowest anchor index first)."""
     size = 128
     anchors = synth.pyramid_anchors((size, size))
@@ -309,6 +319,24 @@ def test_proposal_layer_with_score_ties(ops):
         want = oracle.proposal_layer(rc, rb, anchors, 600, 100, 0.7, height=float(size), width=float(size))
         assert int(counts[0]) == len(want)
         np.testing.assert_array_equal(rois[0, :len(want)].cpu().numpy(), want)
+
+
+def test_proposal_nms_algorithms_agree_at_full_size(ops):
+    """configs[1] size (261,888 anchors, 6000 -> 1000, batch 8): lazy and mask + sweep NMS return the same bytes; a low
+    threshold (heavy suppression: the lazy kernel walks all 94 chunks) as well."""
+    anchors = synth.pyramid_anchors((1024, 1024))
+    rc, rb = zip(*[synth.rpn_outputs(anchors, 60 + i) for i in range(2)])
+    rc_d, rb_d, an_d = dev(np.stack([rc[i % 2] for i in range(8)])), dev(np.stack([rb[i % 2] for i in range(8)])), dev(anchors)
+    try:
+        for thr, post in ((0.7, 1000), (0.1, 1000), (0.5, 2048)):
+            out = {}
+            for algo in ("lazy", "mask"):
+                ops.set_proposal_nms(algo)
+                out[algo] = ops.proposal_layer(rc_d, rb_d, an_d, 6000, post, thr)
+            assert torch.equal(out["lazy"][0], out["mask"][0]) and torch.equal(out["lazy"][1], out["mask"][1])
+            assert int(out["lazy"][1].min()) > 0
+    finally:
+        ops.set_proposal_nms("auto")
 
 
 def test_proposal_golden_and_dropin(ops):
