@@ -61,3 +61,15 @@ def golden_rpnhead():
 
 
 SOFTMAX_TOL = 1e-6  # absolute, on probabilities in [0, 1]: torch's CPU softmax uses an approximate vectorised exp
+
+
+def golden_detect():
+    """tests/golden/golden_detect_v1.npz: the reference's predict.py flow (BASELINE configs[0]) recorded at the boundary
+    of every operator this repo replaces (tests/golden/make_golden_detect.py)."""
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_detect_v1.npz"))
+
+
+def detect_flow_expected_masks(g):
+    d = len(g["mask_valid"])
+    h, w = (int(v) for v in g["mask_in_hw"])
+    return np.unpackbits(g["mask_out_bits"])[:d * h * w].reshape(d, h, w).astype(bool)

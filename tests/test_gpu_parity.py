@@ -800,3 +800,60 @@ def test_rpn_detect_dropin_and_fg_proposals(ops):
     a = ops.proposal_layer(cls, bbox, anchors, 600, 100, 0.7, image_hw=(size, size))
     b = ops.proposal_layer(cls[:, :, 1].contiguous(), bbox, anchors, 600, 100, 0.7, image_hw=(size, size))
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------ the whole predict.py flow (BASELINE configs[0])
+def test_detect_flow_golden_dropins(ops):
+    """The reference's predict.py flow on images/car58a54312d.jpg (random-init ResNet-101-FPN, CPU c++ext ops), recorded
+    at the boundary of every operator this repo replaces (tests/golden/make_golden_detect.py), replayed stage by stage
+    through the drop-ins: reference tensors in, reference tensors expected."""
+    import hashlib
+    import types
+    from helpers import SOFTMAX_TOL, detect_flow_expected_masks, golden_detect, ulp_diff
+    g = golden_detect()
+    size = int(g["image_dim"])
+    nl = sum(1 for k in g.files if k.startswith("rpn_in_logits_"))
+    # rpn_detect (model.py:1294-1304): pack of the head's conv outputs
+    logits, cls, bbox, fg = ops.rpn_pack([dev(g[f"rpn_in_logits_{l}"]) for l in range(nl)], [dev(g[f"rpn_in_bbox_{l}"]) for l in range(nl)])
+    assert hashlib.sha256(logits.cpu().numpy().tobytes() + bbox.cpu().numpy().tobytes()).digest() == g["rpn_out_logits_bbox_sha256"].tobytes()
+    assert np.abs(cls.cpu().numpy() - g["rpn_out_class"]).max() <= SOFTMAX_TOL
+    # rpn_refine (model.py:1307-1382) on the de-tied scores (see the generator: the flow's own scores tie at 1.0 by the thousand)
+    pre, post = (int(v) for v in g["prop_in_limits"])
+    cfg = types.SimpleNamespace(RPN_NMS_MAX_ROIS_NUM=post, RPN_NMS_THRESHOLD=float(g["prop_in_thr"]), RPN_BBOX_STD_DEV=[0.1, 0.1, 0.2, 0.2],
+                                IMAGE_SHAPE=np.array([size, size, 3]), GPU_COUNT=1, DETECTION_MIN_CONFIDENCE=float(g["det_in_min_conf"]),
+                                DETECTION_NMS_THRESHOLD=float(g["det_in_thr"]), DETECTION_MAX_INSTANCES=int(g["det_in_limits"][0]))
+    me = types.SimpleNamespace(config=cfg, anchors=dev(g["prop_in_anchors"]))
+    fgd = g["prop_in_fg_detied"]
+    for algo in ("lazy", "mask"):
+        ops.set_proposal_nms(algo)
+        try:
+            rois = ops.rpn_refine(me, dev(np.stack([1.0 - fgd, fgd], 1).astype(np.float32)).unsqueeze(0), bbox)
+        finally:
+            ops.set_proposal_nms("auto")
+        want = g["prop_out_rois_detied"]
+        assert tuple(rois.shape) == want.shape
+        assert ulp_diff(rois.cpu().numpy(), want).max() <= 4           # torch.exp's rounding (SURVEY §7)
+    # the flow's own scores: the tie-break is the documented stable one (lowest anchor index first) = the oracle's
+    rois = ops.rpn_refine(me, dev(g["rpn_out_class"]), bbox)
+    np.testing.assert_array_equal(rois[0].cpu().numpy(), oracle.proposal_layer(g["rpn_out_class"][0], bbox[0].cpu().numpy(), g["prop_in_anchors"], pre,
+                                                                              post, float(g["prop_in_thr"]), height=float(size), width=float(size)))
+    # roi_align (model.py:276-393), both heads, on the reference's own RoIs
+    fms = [dev(g[f"fm_{l}"]) for l in range(4)]
+    for pool in (7, 14):
+        for chl in (False, True):
+            out = ops.roi_align([dev(g[f"pool{pool}_in_rois"])] + [cl(f) if chl else f for f in fms], pool, [size, size, 3])
+            np.testing.assert_array_equal(out.cpu().numpy(), g[f"pool{pool}_out"])
+    # mrn_refine (model.py:1389-1487)
+    ci, sc, bx = ops.mrn_refine(me, dev(g["prop_out_rois"]), dev(g["det_in_probs"]), dev(g["det_in_deltas"]), g["det_in_window"])
+    assert ci.dtype == torch.int64
+    np.testing.assert_array_equal(ci.cpu().numpy(), g["det_out_class_ids"])
+    np.testing.assert_array_equal(sc.cpu().numpy(), g["det_out_scores"])
+    np.testing.assert_array_equal(bx.cpu().numpy(), g["det_out_boxes"])
+    np.testing.assert_array_equal((bx.float() * 1.0 / size).cpu().numpy(), g["pool14_in_rois"])          # model.py:1188
+    # full_masks (data.py:287-314): the reference's masks where it has any (it raises on the empty boxes), empty elsewhere
+    h, w = (int(v) for v in g["mask_in_hw"])
+    want, ok = detect_flow_expected_masks(g), g["mask_valid"]
+    got = ops.full_masks(torch.zeros(len(ok), dtype=torch.int64, device="cuda"), bx[0], dev(g["mask_in_sel"]).unsqueeze(1), h, w).cpu().numpy()
+    np.testing.assert_array_equal(got[ok], want[ok])
+    assert not got[~ok].any()
+    ops.check_device_errors()
