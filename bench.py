@@ -581,7 +581,22 @@ def secondary(torch, wl, hbm):
                          "frac_of_write_only_fill": t_fill / t,
                          "note": "write-bound: H*W bytes per detection written once with 128-bit streaming stores; a write-only stream "
                                  "tops out well below the copy bandwidth (see the plain fill timed beside it)"}
-    del m_out, m_masks_d, m_ws
+    # ... and its downstream half, data.decode_masks: the predict.py frame (1920 x 1200 -> scale 1024 / 1920, window rows
+    # 192..832): 100 of the pasted masks cropped to the window and resized to 1200 x 1920, uint8
+    Dd, dch, dcw, dnh, dnw = 100, 640, IMAGE, 1200, 1920
+    d_out = torch.empty((Dd, dnh, dnw), dtype=torch.uint8, device=dev)
+    d_ws = torch.empty(L.lib.mrcnn_decode_masks_workspace_bytes(dch, dcw, dnh, dnw), dtype=torch.uint8, device=dev)
+    fdec = lambda: L.check(L.lib.mrcnn_decode_masks(m_out.data_ptr(), 1, Dd, IMAGE, IMAGE, (IMAGE - dch) // 2, 0, dch, dcw, dnh, dnw,  # noqa: E731
+                                                    d_out.data_ptr(), d_ws.data_ptr(), d_ws.numel(), wl._s()))
+    fpaste()
+    t = wl.time_op(fdec, iters=20)
+    by = Dd * (dch * dcw + dnh * dnw)
+    out["decode_masks"] = {"config": "data.decode_masks (SURVEY 8f): %d masks, window %dx%d of 1024x1024 -> uint8 [%d,%d,%d] (the predict.py "
+                                     "frame), two launches" % (Dd, dch, dcw, Dd, dnh, dnw), "masks_per_s": Dd / t, "ms": t * 1e3,
+                           "algorithmic_MB": by / 1e6, "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+                           "note": "window read once + output written once; Pillow's two-pass 8-bit resample with the horizontal pass "
+                                   "staged in shared memory"}
+    del m_out, m_masks_d, m_ws, d_out, d_ws
     # RPN head output plumbing (rpn_detect) - conv outputs of P2..P6 -> [B,A,2] / [B,A,4] / fg [B,A], batch 8
     Bp = 8
     g_ = torch.Generator(device=dev)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 3
+#define MRCNN_ABI_VERSION 4
 
 #define MRCNN_OK 0
 #define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */
@@ -280,6 +280,20 @@ MRCNN_API size_t mrcnn_full_masks_workspace_bytes(int D, int mask_h, int mask_w,
 MRCNN_API int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* masks, int D, int NC, int mask_h,
                                int mask_w, int H, int W, uint8_t* out, void* workspace, size_t workspace_bytes,
                                mrcnn_stream_t stream);
+
+/* ---- masks back to the original frame (replaces data.decode_masks, data.py:265-284) ---------------------------- */
+
+/* masks [D,H,W], one byte per pixel: src_is_bool != 0 -> torch.bool bytes, non-zero = 255 (PIL mode '1' -> 'L',
+ * data.py:272), else 'L' pixel values kept as they are.  The window rows [top, top + crop_h) x columns
+ * [left, left + crop_w) of every mask (torchvision CenterCrop, data.py:273-274: the caller computes the origin
+ * int(round((H - crop_h) / 2.0)) with the host language's round-half-even) are resized to out_h x out_w
+ * (data.py:276-278) with Pillow's 8-bit bilinear resample - the same two-pass fixed-point arithmetic as
+ * mrcnn_full_masks - into out uint8 [D,out_h,out_w]; NOT thresholded, like the reference.  Upscales and downscales.
+ * workspace: 256-byte aligned, mrcnn_decode_masks_workspace_bytes() bytes (the taps of one column / row set). */
+MRCNN_API size_t mrcnn_decode_masks_workspace_bytes(int crop_h, int crop_w, int out_h, int out_w);
+MRCNN_API int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int W, int top, int left, int crop_h,
+                                 int crop_w, int out_h, int out_w, uint8_t* out, void* workspace, size_t workspace_bytes,
+                                 mrcnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,8 @@ SIGNATURES = {
     "mrcnn_proposal_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f4, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_full_masks_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mrcnn_full_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "mrcnn_decode_masks_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mrcnn_decode_masks": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mrcnn_set_proposal_nms": (_i, [_i]),
     "mrcnn_proposal_layer_fg": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f4, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_rpn_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -72,7 +74,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mrcnn_abi_version() != 3:
+    if lib.mrcnn_abi_version() != 4:
         raise ImportError("maskrcnn_b200: ABI version mismatch")
     return lib
 

@@ -298,6 +298,169 @@ __global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PastePar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// decode_masks (data.py:265-284): the [D,H,W] image masks back in the original frame.  The reference takes every mask
+// to the CPU, PIL '1' -> 'L' (0 / 255), torchvision CenterCrop to the window, Resize = the same Pillow 8-bit two-pass
+// bilinear resample, np.array, stack, copy back: uint8 [D,nh,nw], not thresholded.
+//   decode_taps_kernel   the taps of every output column and row once per call (they do not depend on the detection):
+//                        {first input position, count} + 22-bit fixed-point weights, in double as Resample.c does;
+//   decode_masks_kernel  CTA = 256 output columns x 32 output rows of one mask: the HORIZONTAL pass of the input rows the
+//                        tile's vertical taps reach goes into shared memory as the 8-bit intermediate Pillow keeps (so the
+//                        double rounding is Pillow's), the vertical pass reads it 16 columns at a time and writes 128-bit
+//                        streaming stores.  HBM traffic = the window read once (+ ~2 rows of halo per tile) and the output
+//                        written once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDecTX = 256;  // output columns per CTA (= threads)
+constexpr int kDecTY = 32;   // output rows per CTA
+
+struct DecodeParams {
+    const uint8_t* masks;  // [D,H,W] 'L' pixels, or bool bytes (src_bool: non-zero -> 255)
+    int src_bool;
+    int D, H, W;
+    int top, left, ch, cw;  // CenterCrop window
+    int nh, nw;             // target size
+    int kx, ky;             // weight slots per output column / row
+    int rmax;               // rows of the shared-memory intermediate
+    const int2* xmeta;      // [nw] {lo, n}
+    const int* xw;          // [nw][kx]
+    const int2* ymeta;      // [nh]
+    const int* yw;          // [nh][ky]
+    uint8_t* out;           // [D,nh,nw]
+};
+
+__global__ void __launch_bounds__(256) decode_taps_kernel(int cw, int nw, int kx, int2* xmeta, int* xw, int ch, int nh, int ky,
+                                                          int2* ymeta, int* yw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw + nh) return;
+    const bool is_x = i < nw;
+    const int pos = is_x ? i : i - nw;
+    const AxisTaps t = is_x ? axis_taps(cw, nw, pos) : axis_taps(ch, nh, pos);
+    int* w = is_x ? xw + (size_t)pos * kx : yw + (size_t)pos * ky;
+    (is_x ? xmeta : ymeta)[pos] = make_int2(t.lo, t.n);
+    if (t.n <= 3) {
+        w[0] = t.k0;
+        if (t.n > 1) w[1] = t.k1;
+        if (t.n > 2) w[2] = t.k2;
+    } else {
+        for (int j = 0; j < t.n; ++j) w[j] = fixed_weight(t, j);
+    }
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams p) {
+    extern __shared__ __align__(16) uint8_t s_tmp[];  // [rmax][kDecTX]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kDecTX, y0 = blockIdx.y * kDecTY, d = blockIdx.z;
+    const int y1 = min(y0 + kDecTY, p.nh);
+    // input rows (window coordinates) the tile's vertical taps reach
+    const int2 mfirst = __ldg(p.ymeta + y0), mlast = __ldg(p.ymeta + (y1 - 1));
+    const int r0 = mfirst.x, r1 = mlast.x + mlast.y;  // lo is non-decreasing in y
+    const uint8_t* src = p.masks + ((size_t)d * p.H + p.top) * p.W + p.left;
+    {   // horizontal pass: column x0 + tid of rows [r0, r1)
+        const int x = x0 + tid;
+        if (x < p.nw) {
+            const int2 m = __ldg(p.xmeta + x);
+            const int* w = p.xw + (size_t)x * p.kx;
+            const uint8_t* s = src + m.x;
+            if (m.y <= 3) {
+                const int k0 = __ldg(w), k1 = m.y > 1 ? __ldg(w + 1) : 0, k2 = m.y > 2 ? __ldg(w + 2) : 0;
+                const int o1 = m.y > 1 ? 1 : 0, o2 = m.y > 2 ? 2 : 0;  // a zero weight on a valid address
+                for (int r = r0; r < r1; ++r) {
+                    const uint8_t* q = s + (size_t)r * p.W;
+                    int a = __ldg(q), b = __ldg(q + o1), c = __ldg(q + o2);
+                    if (p.src_bool) {
+                        a = a ? 255 : 0;
+                        b = b ? 255 : 0;
+                        c = c ? 255 : 0;
+                    }
+                    s_tmp[(r - r0) * kDecTX + tid] = (uint8_t)clip8((1 << (kPrecBits - 1)) + a * k0 + b * k1 + c * k2);
+                }
+            } else {
+                for (int r = r0; r < r1; ++r) {
+                    const uint8_t* q = s + (size_t)r * p.W;
+                    int acc = 1 << (kPrecBits - 1);
+                    for (int j = 0; j < m.y; ++j) {
+                        int v = __ldg(q + j);
+                        if (p.src_bool) v = v ? 255 : 0;
+                        acc += v * __ldg(w + j);
+                    }
+                    s_tmp[(r - r0) * kDecTX + tid] = (uint8_t)clip8(acc);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    uint8_t* out = p.out + (size_t)d * p.nh * p.nw;
+    if (kVec) {  // nw % 16 == 0: 16 columns per thread, 16 rows per sweep
+        const int c = tid & 15, x = x0 + c * 16;
+        if (x < p.nw) {
+            for (int y = y0 + (tid >> 4); y < y1; y += kDecTX / 16) {
+                const int2 m = __ldg(p.ymeta + y);
+                const int* w = p.yw + (size_t)y * p.ky;
+                const uint8_t* col = s_tmp + (m.x - r0) * kDecTX + c * 16;
+                int acc[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = 1 << (kPrecBits - 1);
+                for (int j = 0; j < m.y; ++j) {
+                    const int k = __ldg(w + j);
+                    const uint4 v = *reinterpret_cast<const uint4*>(col + j * kDecTX);
+                    const unsigned vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] += (int)((vw[q >> 2] >> ((q & 3) * 8)) & 0xffu) * k;
+                }
+                unsigned o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 16; ++q) o[q >> 2] |= (unsigned)clip8(acc[q]) << ((q & 3) * 8);
+                __stcs(reinterpret_cast<uint4*>(out + (size_t)y * p.nw + x), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+        }
+    } else {  // any width: one column per thread, byte stores (a warp still writes 32 consecutive bytes)
+        const int x = x0 + tid;
+        if (x < p.nw) {
+            for (int y = y0; y < y1; ++y) {
+                const int2 m = __ldg(p.ymeta + y);
+                const int* w = p.yw + (size_t)y * p.ky;
+                const uint8_t* col = s_tmp + (m.x - r0) * kDecTX + tid;
+                int acc = 1 << (kPrecBits - 1);
+                for (int j = 0; j < m.y; ++j) acc += (int)col[j * kDecTX] * __ldg(w + j);
+                out[(size_t)y * p.nw + x] = (uint8_t)clip8(acc);
+            }
+        }
+    }
+}
+
+struct DecodeLayout {
+    size_t xmeta_off, xw_off, ymeta_off, yw_off, bytes;
+    int kx, ky, rmax;
+};
+
+// Resample.c: ksize = (int)ceil(support) * 2 + 1 with support = max(in / out, 1) for the triangle filter
+static int decode_ksize(int in_size, int out_size) {
+    const double scale = (double)in_size / (double)out_size;
+    return (int)ceil(scale < 1.0 ? 1.0 : scale) * 2 + 1;
+}
+
+static DecodeLayout decode_layout(int ch, int cw, int nh, int nw) {
+    DecodeLayout l;
+    l.kx = decode_ksize(cw, nw);
+    l.ky = decode_ksize(ch, nh);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) / 256 * 256;
+        return at;
+    };
+    l.xmeta_off = take((size_t)nw * sizeof(int2));
+    l.xw_off = take((size_t)nw * l.kx * sizeof(int));
+    l.ymeta_off = take((size_t)nh * sizeof(int2));
+    l.yw_off = take((size_t)nh * l.ky * sizeof(int));
+    l.bytes = off;
+    // input rows under kDecTY output rows: the centres span (kDecTY - 1) * scale, the taps reach `support` either side
+    const double sy = (double)ch / (double)nh;
+    l.rmax = (int)ceil((kDecTY - 1) * sy) + l.ky + 2;
+    return l;
+}
+
 }  // namespace mrcnn
 
 using namespace mrcnn;
@@ -341,6 +504,59 @@ int mrcnn_full_masks(const int64_t* class_ids, const float* boxes, const float* 
         full_masks_kernel<true><<<D * p.groups, kMaskThreads, 0, stream>>>(p);
     else
         full_masks_kernel<false><<<D * p.groups, kMaskThreads, 0, stream>>>(p);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+size_t mrcnn_decode_masks_workspace_bytes(int crop_h, int crop_w, int out_h, int out_w) {
+    if (crop_h <= 0 || crop_w <= 0 || out_h <= 0 || out_w <= 0) return 256;
+    return decode_layout(crop_h, crop_w, out_h, out_w).bytes;
+}
+
+int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int W, int top, int left, int crop_h, int crop_w,
+                       int out_h, int out_w, uint8_t* out, void* workspace, size_t workspace_bytes, mrcnn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRCNN_REQUIRE(D >= 0 && H > 0 && W > 0, "mrcnn_decode_masks: bad sizes");
+    MRCNN_REQUIRE(crop_h > 0 && crop_w > 0 && top >= 0 && left >= 0 && top + crop_h <= H && left + crop_w <= W,
+                  "mrcnn_decode_masks: the crop window must lie inside the mask");
+    MRCNN_REQUIRE(out_h > 0 && out_w > 0, "mrcnn_decode_masks: height and width must be > 0");
+    MRCNN_REQUIRE(D <= 65535, "mrcnn_decode_masks: at most 65535 masks per call");
+    if (D == 0) return MRCNN_OK;
+    MRCNN_REQUIRE_DEV(masks);
+    MRCNN_REQUIRE_DEV(out);
+    MRCNN_REQUIRE_DEV(workspace);
+    const DecodeLayout l = decode_layout(crop_h, crop_w, out_h, out_w);
+    if (workspace_bytes < l.bytes || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return fail(MRCNN_E_WORKSPACE, "mrcnn_decode_masks: workspace too small or not 256-byte aligned");
+    const size_t smem = (size_t)l.rmax * kDecTX;
+    MRCNN_REQUIRE(smem <= 200 * 1024, "mrcnn_decode_masks: downscale factor too large (%d intermediate rows per tile)", l.rmax);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    DecodeParams p;
+    p.masks = masks; p.src_bool = src_is_bool ? 1 : 0;
+    p.D = D; p.H = H; p.W = W;
+    p.top = top; p.left = left; p.ch = crop_h; p.cw = crop_w;
+    p.nh = out_h; p.nw = out_w;
+    p.kx = l.kx; p.ky = l.ky; p.rmax = l.rmax;
+    p.xmeta = reinterpret_cast<const int2*>(ws + l.xmeta_off);
+    p.xw = reinterpret_cast<const int*>(ws + l.xw_off);
+    p.ymeta = reinterpret_cast<const int2*>(ws + l.ymeta_off);
+    p.yw = reinterpret_cast<const int*>(ws + l.yw_off);
+    p.out = out;
+    decode_taps_kernel<<<(out_w + out_h + 255) / 256, 256, 0, stream>>>(crop_w, out_w, l.kx, reinterpret_cast<int2*>(ws + l.xmeta_off),
+                                                                    reinterpret_cast<int*>(ws + l.xw_off), crop_h, out_h, l.ky,
+                                                                    reinterpret_cast<int2*>(ws + l.ymeta_off),
+                                                                    reinterpret_cast<int*>(ws + l.yw_off));
+    MRCNN_LAUNCH_CHECK();
+    const dim3 grid((out_w + kDecTX - 1) / kDecTX, (out_h + kDecTY - 1) / kDecTY, D);
+    MRCNN_REQUIRE(grid.y <= 65535, "mrcnn_decode_masks: target too tall");
+    const bool vec = (out_w % 16 == 0) && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (vec) {
+        if (smem > 48 * 1024) MRCNN_CUDA(cudaFuncSetAttribute(decode_masks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_masks_kernel<true><<<grid, kDecTX, smem, stream>>>(p);
+    } else {
+        if (smem > 48 * 1024) MRCNN_CUDA(cudaFuncSetAttribute(decode_masks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_masks_kernel<false><<<grid, kDecTX, smem, stream>>>(p);
+    }
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "decode_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "check_device_errors",
            "set_backward_algorithm"]
 
 
@@ -767,3 +767,39 @@ def full_masks(class_id, boxes, masks, height, width):
         check(lib.mrcnn_full_masks(cls.data_ptr(), bx.data_ptr(), mk.data_ptr(), D, NC, mh, mw, H, W, out.data_ptr(), ws.data_ptr(),
                                    ws_bytes, _stream()))
     return out.reshape(lead + (H, W))
+
+
+def decode_masks(masks, scale, cropbox):
+    """Drop-in for data.decode_masks (data.py:265-284): masks [D,H,W] torch.bool (what full_masks returns; -> 0 / 255) or
+    torch.uint8 (pixel values kept), scale = the factor the frame was resized by, cropbox = the window (an object with
+    height() / width() like data.Box, or a (height, width) pair) -> uint8 [D,nh,nw]: every mask centre-cropped to the
+    window and resized to round(h / scale) x round(w / scale) with Pillow's 8-bit bilinear resample, bit-identical to the
+    reference's PIL / torchvision route, not thresholded.  Two launches for all masks and no host round trip (the
+    reference copies every mask to the CPU and back).  scale == 1 returns `masks` itself (data.py:267-268)."""
+    if scale == 1:
+        return masks
+    _require_cuda(masks, "masks")
+    if masks.dim() != 3 or masks.dtype not in (torch.bool, torch.uint8):
+        raise ValueError("masks must be [D,H,W] torch.bool or torch.uint8")
+    if hasattr(cropbox, "height"):
+        ch, cw = int(cropbox.height()), int(cropbox.width())
+    else:
+        ch, cw = int(cropbox[0]), int(cropbox[1])
+    D, H, W = (int(v) for v in masks.shape)
+    if ch > H or cw > W:
+        raise ValueError("decode_masks: the crop window is larger than the mask (CenterCrop would pad)")
+    # torchvision center_crop's origin and data.py:276-277's target size, in Python arithmetic like the reference
+    top = int(round((H - ch) / 2.0))
+    left = int(round((W - cw) / 2.0))
+    nh = int(round(ch * 1.0 / scale))
+    nw = int(round(cw * 1.0 / scale))
+    if nh <= 0 or nw <= 0 or ch <= 0 or cw <= 0:
+        raise ValueError("height and width must be > 0")     # PIL's error for the same input
+    m = masks.contiguous()
+    out = torch.empty((D, nh, nw), dtype=torch.uint8, device=masks.device)
+    with torch.cuda.device(masks.device):
+        ws_bytes = lib.mrcnn_decode_masks_workspace_bytes(ch, cw, nh, nw)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
+        check(lib.mrcnn_decode_masks(m.data_ptr(), 1 if masks.dtype == torch.bool else 0, D, H, W, top, left, ch, cw, nh, nw,
+                                     out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return out

@@ -74,6 +74,8 @@ def lib():
         L.orc_full_masks.restype = ctypes.c_int
         L.orc_full_masks.argtypes = [_i64p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.POINTER(ctypes.c_uint8)]
+        L.orc_decode_masks.restype = ctypes.c_int
+        L.orc_decode_masks.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_uint8)]
         L.orc_rpn_pack.restype = None
         L.orc_rpn_pack.argtypes = [pp, pp, ip, ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p]
         L.orc_boxes_refine.restype = None
@@ -324,6 +326,44 @@ def full_masks(class_ids, boxes, masks, height, width):
     if rc != 0:
         raise ValueError("full_masks: detection %d has an empty box" % (-rc - 1))
     return out.astype(bool)
+
+
+def decode_geometry(height, width, scale, crop_hw):
+    """The integer geometry of data.decode_masks (data.py:265-284), computed with Python's own arithmetic as the reference
+    does: torchvision CenterCrop's origin int(round((H - ch) / 2.0)) (transforms/functional.py center_crop; Python's
+    round is half-to-even) and the target size round(ch * 1.0 / scale), round(cw * 1.0 / scale) (data.py:276-277).
+    Returns (top, left, ch, cw, nh, nw)."""
+    ch, cw = int(crop_hw[0]), int(crop_hw[1])
+    if ch > int(height) or cw > int(width):
+        raise ValueError("decode_masks: the crop window is larger than the mask (CenterCrop would pad)")
+    top = int(round((int(height) - ch) / 2.0))
+    left = int(round((int(width) - cw) / 2.0))
+    nh = round(ch * 1.0 / scale)
+    nw = round(cw * 1.0 / scale)
+    return top, left, ch, cw, int(nh), int(nw)
+
+
+def decode_masks(masks, scale, crop_hw):
+    """data.decode_masks (data.py:265-284): masks [D,H,W] bool (-> 0 / 255, PIL mode '1' -> 'L') or uint8 (kept as is),
+    scale = the resize factor encode_image applied, crop_hw = (window height, window width) -> uint8 [D,nh,nw] (8-bit
+    bilinear, not thresholded).  scale == 1 returns the input, as the reference does (data.py:267-268)."""
+    if scale == 1:
+        return masks
+    m = np.ascontiguousarray(masks)
+    if m.dtype == np.bool_:
+        m = m.astype(np.uint8) * np.uint8(255)
+    elif m.dtype != np.uint8:
+        raise TypeError("decode_masks: masks must be bool or uint8")
+    d, H, W = m.shape
+    top, left, ch, cw, nh, nw = decode_geometry(H, W, scale, crop_hw)
+    if nh <= 0 or nw <= 0:
+        raise ValueError("height and width must be > 0")   # PIL's message
+    out = np.zeros((d, nh, nw), np.uint8)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    rc = lib().orc_decode_masks(m.ctypes.data_as(u8p), d, H, W, top, left, ch, cw, nh, nw, out.ctypes.data_as(u8p))
+    if rc != 0:
+        raise ValueError("decode_masks: bad geometry")
+    return out
 
 
 def rpn_pack(class_logits, bboxes):

@@ -12,6 +12,7 @@ the GPU test can replay the whole flow stage by stage (reference tensors in, ref
   mrn_refine   (model.py:1389-1487)  in: rpn_rois, mrn_class, mrn_bbox, window      out: class ids, scores, boxes
   roi_align 14                       in: detections / h, P2..P5                     out: pooled [D,C,14,14]
   full_masks   (data.py:287-314)     in: class ids, boxes, mask head output         out: [D,H,W] masks
+  decode_masks (data.py:265-284)     in: masks, scale, window                       out: sha256 of the uint8 [D,1200,1920]
 
 The image is resized to IMAGE_MAX_DIM = 256 instead of 1024 and only CHANNELS (8) of the 256 pyramid channels are stored
 (crop_and_resize is channel-independent, crop_cpu.cpp:98-110, so the reference's pooled[:, CHANNELS] is exactly the crop
@@ -127,13 +128,25 @@ def run(seed):
         g["mask_out_bits"] = np.packbits(T(out).astype(bool))
         return out
 
+    orig_decode_masks = ref.data.decode_masks
+
+    def decode_masks(masks, scale, cropbox):
+        # the reference on the masks it produced itself (rows with an empty box carry the empty mask, see full_masks above)
+        out = orig_decode_masks(masks, scale, cropbox)
+        ok = g["mask_valid"]
+        g["decode_in_scale"] = np.float64(scale)
+        g["decode_out_hw"] = np.array(out.shape[1:], np.int64)
+        g["decode_out_sha256"] = np.frombuffer(hashlib.sha256(T(out)[ok].tobytes()).digest(), np.uint8).copy()
+        return out
+
+    ref.data.decode_masks = decode_masks
     model.rpn_detect, model.rpn_refine, model.mrn_refine = rpn_detect, rpn_refine, mrn_refine
     ref.model.roi_align, ref.data.full_masks = roi_align, full_masks
     try:
         with torch.no_grad(), reference.quiet_stdout():
             class_ids, scores, boxes, masks = model.detect(img)
     finally:
-        ref.model.roi_align, ref.data.full_masks = orig_roi_align, orig_full_masks
+        ref.model.roi_align, ref.data.full_masks, ref.data.decode_masks = orig_roi_align, orig_full_masks, orig_decode_masks
         h1.remove()
         h2.remove()
     assert class_ids is not None, "no detections: pick another seed"

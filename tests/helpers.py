@@ -73,3 +73,12 @@ def detect_flow_expected_masks(g):
     d = len(g["mask_valid"])
     h, w = (int(v) for v in g["mask_in_hw"])
     return np.unpackbits(g["mask_out_bits"])[:d * h * w].reshape(d, h, w).astype(bool)
+
+
+def golden_decode(tag):
+    """(bool masks [D,H,W], scale, (window height, window width), expected uint8 [D,nh,nw]) of
+    tests/golden/golden_decode_v1.npz (the reference's data.decode_masks, tests/golden/make_golden_decode.py)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_decode_v1.npz"))
+    d, h, w, y1, x1, y2, x2 = (int(v) for v in g[f"{tag}_in_geom"])
+    m = np.unpackbits(g[f"{tag}_in_bits"])[:d * h * w].reshape(d, h, w).astype(bool)
+    return m, float(g[f"{tag}_in_scale"]), (y2 - y1, x2 - x1), g[f"{tag}_out"]

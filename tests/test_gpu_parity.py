@@ -802,6 +802,77 @@ def test_rpn_detect_dropin_and_fg_proposals(ops):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
+# ------------------------------------------------------------------ decode_masks (data.py:265-284)
+def _decode_case(D, H, W, seed):
+    rng = np.random.default_rng(seed)
+    m = np.zeros((D, H, W), bool)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(D):
+        y, x = rng.integers(0, H - 2), rng.integers(0, W - 2)
+        h, w = rng.integers(1, max(2, H - y)), rng.integers(1, max(2, W - x))
+        m[i, y:y + h, x:x + w] = True
+        r = rng.integers(1, max(2, min(H, W) // 3))
+        m[i] ^= (yy - rng.integers(0, H)) ** 2 + (xx - rng.integers(0, W)) ** 2 < r * r
+        m[i, rng.integers(0, H), :] = True
+        m[i, rng.integers(0, H, 20), rng.integers(0, W, 20)] = True
+    return m
+
+
+@pytest.mark.parametrize("D,H,W,crop,scale", [
+    (3, 256, 256, (160, 256), 256 / 1920),      # predict.py geometry at 256 (upscale 7.5; 1920 columns: the 128-bit path)
+    (4, 256, 256, (256, 189), 0.75),            # odd margins, 252 columns (byte path)
+    (4, 200, 200, (173, 200), 0.4161),          # CenterCrop origin 13.5 -> 14 (half-even)
+    (5, 128, 160, (128, 160), 2.0),             # downscale by 2 -> 80 columns (128-bit path, 5 taps)
+    (3, 120, 90, (101, 81), 3.3),               # downscale by 3.3, 9 taps
+    (2, 64, 64, (60, 60), 1.0001),              # same size: both passes are the identity
+    (2, 64, 96, (64, 96), 0.5),                 # exact doubling
+    (1, 1024, 1024, (640, 1024), 1024 / 1920),  # the real predict.py frame: 1024 -> 1200 x 1920
+    (70, 40, 40, (40, 40), 0.3)])               # many small masks
+def test_decode_masks_matches_oracle(ops, D, H, W, crop, scale):
+    m = _decode_case(D, H, W, D + H)
+    want = oracle.decode_masks(m, scale, crop)
+    got = ops.decode_masks(dev(m), scale, crop)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == want.shape
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # uint8 0/1 input keeps its pixel values ("tensor NxHxW with 1/0"); a Box-like window object
+    import types
+    box = types.SimpleNamespace(height=lambda: crop[0], width=lambda: crop[1])
+    np.testing.assert_array_equal(ops.decode_masks(dev(m.astype(np.uint8)), scale, box).cpu().numpy(),
+                                  oracle.decode_masks(m.astype(np.uint8), scale, crop))
+    ops.check_device_errors()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e"])
+def test_decode_masks_golden(ops, tag):
+    from helpers import golden_decode
+    m, scale, crop_hw, want = golden_decode(tag)
+    np.testing.assert_array_equal(ops.decode_masks(dev(m), scale, crop_hw).cpu().numpy(), want)
+
+
+def test_decode_masks_edge_cases(ops):
+    m = dev(_decode_case(2, 32, 48, 3))
+    assert ops.decode_masks(m, 1, (32, 48)) is m                                  # data.py:267-268
+    assert tuple(ops.decode_masks(m[:0], 0.5, (32, 48)).shape) == (0, 64, 96)     # no detections
+    with pytest.raises(ValueError):
+        ops.decode_masks(m, 0.5, (33, 48))                                        # window larger than the mask
+    with pytest.raises(ValueError):
+        ops.decode_masks(m, 100.0, (32, 48))                                      # target rounds to 0 pixels: PIL raises too
+    with pytest.raises(ValueError):
+        ops.decode_masks(m.float(), 0.5, (32, 48))
+    with pytest.raises(TypeError):
+        ops.decode_masks(m.cpu(), 0.5, (32, 48))
+    # a non-contiguous view (full_masks output sliced) and a full-masks -> decode chain against the oracle chain
+    cls, boxes, masks = synth.mask_head_outputs(6, 5, 23, image=128)
+    pasted = ops.full_masks(dev(cls), dev(boxes), dev(masks), 128, 128)
+    got = ops.decode_masks(pasted[::2], 128 / 300, (80, 128)).cpu().numpy()
+    want = oracle.decode_masks(oracle.full_masks(cls, boxes, masks, 128, 128)[::2], 128 / 300, (80, 128))
+    np.testing.assert_array_equal(got, want)
+    # all-False and all-True masks stay constant (the weights of every output pixel sum to 1 in fixed point +- rounding)
+    z = torch.zeros(1, 64, 64, dtype=torch.bool, device="cuda")
+    assert not ops.decode_masks(z, 0.37, (64, 64)).any()
+    assert bool((ops.decode_masks(~z, 0.37, (64, 64)) == 255).all())
+
+
 # ------------------------------------------------------------------ the whole predict.py flow (BASELINE configs[0])
 def test_detect_flow_golden_dropins(ops):
     """The reference's predict.py flow on images/car58a54312d.jpg (random-init ResNet-101-FPN, CPU c++ext ops), recorded
@@ -856,4 +927,10 @@ def test_detect_flow_golden_dropins(ops):
     got = ops.full_masks(torch.zeros(len(ok), dtype=torch.int64, device="cuda"), bx[0], dev(g["mask_in_sel"]).unsqueeze(1), h, w).cpu().numpy()
     np.testing.assert_array_equal(got[ok], want[ok])
     assert not got[~ok].any()
+    # decode_masks (data.py:265-284, model.py:1131): back to the 1920 x 1200 frame
+    y1, x1, y2, x2 = (int(v) for v in g["det_in_window"])
+    dec = ops.decode_masks(dev(want[ok]), float(g["decode_in_scale"]), (y2 - y1, x2 - x1)).cpu().numpy()
+    assert dec.shape[1:] == tuple(int(v) for v in g["decode_out_hw"])
+    import hashlib as _h
+    assert _h.sha256(dec.tobytes()).digest() == g["decode_out_sha256"].tobytes()
     ops.check_device_errors()

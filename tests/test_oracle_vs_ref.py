@@ -270,6 +270,55 @@ def test_full_masks_empty_box_raises_like_pil():
         oracle.full_masks(cls, boxes, masks, 64, 64)
 
 
+def _decode_case(D, H, W, seed):
+    """bool masks [D,H,W]: filled rectangles, discs, thin lines and isolated pixels (every edge gets interpolated)."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((D, H, W), bool)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(D):
+        y, x = rng.integers(0, H - 2), rng.integers(0, W - 2)
+        h, w = rng.integers(1, max(2, H - y)), rng.integers(1, max(2, W - x))
+        m[i, y:y + h, x:x + w] = True
+        r = rng.integers(1, max(2, min(H, W) // 3))
+        m[i] ^= (yy - rng.integers(0, H)) ** 2 + (xx - rng.integers(0, W)) ** 2 < r * r
+        m[i, rng.integers(0, H), :] = True
+        m[i, rng.integers(0, H, 20), rng.integers(0, W, 20)] = True
+    return m
+
+
+@needs_model
+@pytest.mark.parametrize("H,W,window,scale,seed", [
+    (256, 256, (48, 0, 208, 256), 256 / 1920, 1),          # the predict.py geometry at 256: 1920x1200 frame, upscale 7.5
+    (256, 256, (0, 33, 256, 222), 0.75, 2),               # odd margins: CenterCrop's round-half-even origin
+    (200, 200, (13, 0, 186, 200), 0.4161, 3),             # 173 rows: (200 - 173) / 2 = 13.5 -> 14, not the window's 13
+    (128, 160, (0, 0, 128, 160), 2.0, 4),                 # the frame was enlarged (IMAGE_MIN_DIM): downscale by 2
+    (120, 90, (10, 5, 111, 86), 3.3, 5),                  # downscale by 3.3: up to 9 taps
+    (64, 64, (0, 0, 64, 64), 0.5, 6), (64, 64, (2, 2, 62, 62), 1.0001, 7)])
+def test_decode_masks_matches_data_py(H, W, window, scale, seed):
+    """oracle.decode_masks against data.decode_masks executed here (PIL '1' -> 'L', torchvision CenterCrop + Resize)."""
+    d = reference.load().data
+    m = _decode_case(5, H, W, seed)
+    box = d.Box.fromlist(list(window))
+    want = d.decode_masks(torch.from_numpy(m), scale, box).numpy()
+    got = oracle.decode_masks(m, scale, (box.height(), box.width()))
+    assert want.dtype == np.uint8 and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    same_size = want.shape[1:] == (box.height(), box.width())      # Resample skips both passes: a plain crop
+    assert ((want > 0) & (want < 255)).any() or scale > 1.9 or same_size     # interpolated edge values are compared too
+    # uint8 0/1 input ("tensor NxHxW with 1/0"): stays 0/1 through convert('L')
+    want1 = d.decode_masks(torch.from_numpy(m.astype(np.uint8)), scale, box).numpy()
+    np.testing.assert_array_equal(oracle.decode_masks(m.astype(np.uint8), scale, (box.height(), box.width())), want1)
+
+
+@needs_model
+def test_decode_masks_scale_one_is_identity():
+    d = reference.load().data
+    m = _decode_case(2, 32, 32, 1)
+    t = torch.from_numpy(m)
+    assert d.decode_masks(t, 1, d.Box.fromlist([0, 0, 32, 32])) is t
+    assert oracle.decode_masks(m, 1, (32, 32)) is m
+
+
 @needs_model
 def test_rpn_pack_matches_model_py():
     """oracle.rpn_pack against the reference's RPN module (model.py:573-653) and the torch.cat of rpn_detect (:1294-1304)."""
