@@ -121,6 +121,21 @@ MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_lay
                                      void* workspace, size_t workspace_bytes,
                                      mrcnn_stream_t stream);
 
+/* The gather backward in two halves.  Its work-item queues (three small launches, ~60 us at 8192 RoIs) depend on the boxes,
+ * pool, C and the pyramid geometry only - not on the gradients - so a training step can build them on a side stream
+ * while the forward runs and keep the critical path of the backward to the one gather launch:
+ *   _plan     fills `workspace` (mrcnn_pyramid_roi_align_backward_workspace_bytes(), 256-byte aligned) from the boxes;
+ *   _planned  the gather itself: grads [N,C,pool,pool] and gfm channels-last, the SAME H, W, B, C, N, pool as the plan
+ *             (not checked: the plan lives in device memory) and the workspace the plan filled, which it only reads -
+ *             a plan can serve any number of backward calls.  zero_fill == 0 adds to what gfm holds.
+ * Same requirements and same results as MRCNN_BWD_GATHER. */
+MRCNN_API int mrcnn_pyramid_roi_align_backward_plan(const int H[4], const int W[4], int B, int C, const float* boxes,
+                                                    const int32_t* box_index, int N, int pool, float image_area,
+                                                    void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+MRCNN_API int mrcnn_pyramid_roi_align_backward_planned(const float* grads, const int H[4], const int W[4], int B, int C, int N,
+                                                       int pool, float* const gfm[4], int zero_fill, const void* workspace,
+                                                       size_t workspace_bytes, mrcnn_stream_t stream);
+
 /* Both heads at once.  In training the reference pools the SAME RoIs twice from the same pyramid - 7x7 for the box head
  * (model.py:778) and 14x14 for the mask head (model.py:889) - and autograd then adds the two gradient pyramids that
  * CropFunction.backward returned per level.  This entry point takes both upstream gradients (channels-last,

@@ -305,10 +305,12 @@ __global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PastePar
 //   decode_taps_kernel   the taps of every output column and row once per call (they do not depend on the detection):
 //                        {first input position, count} + 22-bit fixed-point weights, in double as Resample.c does;
 //   decode_masks_kernel  CTA = 256 output columns x 32 output rows of one mask: the HORIZONTAL pass of the input rows the
-//                        tile's vertical taps reach goes into shared memory as the 8-bit intermediate Pillow keeps (so the
-//                        double rounding is Pillow's), the vertical pass reads it 16 columns at a time and writes 128-bit
-//                        streaming stores.  HBM traffic = the window read once (+ ~2 rows of halo per tile) and the output
-//                        written once.
+//                        tile's vertical taps reach are staged in shared memory, their HORIZONTAL pass goes into shared memory
+//                        as the 8-bit intermediate Pillow keeps (so the double rounding is Pillow's), the vertical pass
+//                        reads it 16 columns at a time and writes 128-bit
+//                        streaming stores.  A tile whose input bytes are all equal (the inside and the outside of a mask:
+//                        all but the edge tiles) is a constant fill.  HBM traffic = the window read once (+ ~2 rows of halo
+//                        per tile) and the output written once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDecTX = 256;  // output columns per CTA (= threads)
 constexpr int kDecTY = 32;   // output rows per CTA
@@ -321,6 +323,7 @@ struct DecodeParams {
     int nh, nw;             // target size
     int kx, ky;             // weight slots per output column / row
     int rmax;               // rows of the shared-memory intermediate
+    int cstride;            // row pitch of the staged input bytes
     const int2* xmeta;      // [nw] {lo, n}
     const int* xw;          // [nw][kx]
     const int2* ymeta;      // [nh]
@@ -346,51 +349,81 @@ __global__ void __launch_bounds__(256) decode_taps_kernel(int cw, int nw, int kx
     }
 }
 
+// Sums of this file's resampling passes never clip: the weights of a position are >= 0 and sum to 2^22 + e with |e| <= half
+// the tap count, so 2^21 + sum(v * k) < 256 * 2^22 for 8-bit v and clip8() is a plain shift.  With the weights scaled by 4
+// the result is the top byte of an unsigned 32-bit sum: (2^23 + sum(v * 4k)) >> 24.
 template <bool kVec>
 __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams p) {
-    extern __shared__ __align__(16) uint8_t s_tmp[];  // [rmax][kDecTX]
+    extern __shared__ __align__(16) uint8_t s_dec[];
+    uint8_t* s_tmp = s_dec;                               // [rmax][kDecTX]   horizontal pass (Pillow's 8-bit intermediate)
+    uint8_t* s_src = s_dec + (size_t)p.rmax * kDecTX;     // [rmax][cstride]  the input bytes under the tile
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kDecTX, y0 = blockIdx.y * kDecTY, d = blockIdx.z;
     const int y1 = min(y0 + kDecTY, p.nh);
-    // input rows (window coordinates) the tile's vertical taps reach
+    // input rows / columns (window coordinates) the tile's taps reach: lo and lo + n are non-decreasing along an axis
     const int2 mfirst = __ldg(p.ymeta + y0), mlast = __ldg(p.ymeta + (y1 - 1));
-    const int r0 = mfirst.x, r1 = mlast.x + mlast.y;  // lo is non-decreasing in y
+    const int r0 = mfirst.x, r1 = mlast.x + mlast.y;
+    const int x_last = min(x0 + kDecTX, p.nw) - 1;
+    const int2 cx0 = __ldg(p.xmeta + x0), cx1 = __ldg(p.xmeta + x_last);
+    const int c0 = cx0.x, c1 = cx1.x + cx1.y;
     const uint8_t* src = p.masks + ((size_t)d * p.H + p.top) * p.W + p.left;
-    {   // horizontal pass: column x0 + tid of rows [r0, r1)
+    uint8_t* out = p.out + (size_t)d * p.nh * p.nw;
+    {   // stage the input bytes (coalesced), and probe them: a mask is two flat regions and an edge, and if every byte under
+        // the tile's taps is the same value v both passes return v - the tile is a constant fill
+        int v0 = __ldg(src + (size_t)r0 * p.W + c0);
+        if (p.src_bool) v0 = v0 ? 255 : 0;
+        int differs = 0;
+        for (int r = r0 + (tid >> 5); r < r1; r += kDecTX / 32) {
+            const uint8_t* q = src + (size_t)r * p.W;
+            uint8_t* sq = s_src + (r - r0) * p.cstride - c0;
+            for (int c = c0 + (tid & 31); c < c1; c += 32) {
+                int v = __ldg(q + c);
+                if (p.src_bool) v = v ? 255 : 0;
+                sq[c] = (uint8_t)v;
+                differs |= v ^ v0;
+            }
+        }
+        if (!__syncthreads_or(differs)) {
+            const unsigned w = (unsigned)v0 * 0x01010101u;
+            if (kVec) {
+                const int c = tid & 15, x = x0 + c * 16;
+                if (x < p.nw)
+                    for (int y = y0 + (tid >> 4); y < y1; y += kDecTX / 16)
+                        __stcs(reinterpret_cast<uint4*>(out + (size_t)y * p.nw + x), make_uint4(w, w, w, w));
+            } else {
+                const int x = x0 + tid;
+                if (x < p.nw)
+                    for (int y = y0; y < y1; ++y) out[(size_t)y * p.nw + x] = (uint8_t)v0;
+            }
+            return;
+        }
+    }
+    {   // horizontal pass: column x0 + tid of rows [r0, r1), from shared memory into shared memory
         const int x = x0 + tid;
         if (x < p.nw) {
             const int2 m = __ldg(p.xmeta + x);
             const int* w = p.xw + (size_t)x * p.kx;
-            const uint8_t* s = src + m.x;
+            const uint8_t* s = s_src + (m.x - c0);
             if (m.y <= 3) {
-                const int k0 = __ldg(w), k1 = m.y > 1 ? __ldg(w + 1) : 0, k2 = m.y > 2 ? __ldg(w + 2) : 0;
+                const unsigned k0 = (unsigned)__ldg(w) << 2, k1 = m.y > 1 ? (unsigned)__ldg(w + 1) << 2 : 0u,
+                               k2 = m.y > 2 ? (unsigned)__ldg(w + 2) << 2 : 0u;
                 const int o1 = m.y > 1 ? 1 : 0, o2 = m.y > 2 ? 2 : 0;  // a zero weight on a valid address
-                for (int r = r0; r < r1; ++r) {
-                    const uint8_t* q = s + (size_t)r * p.W;
-                    int a = __ldg(q), b = __ldg(q + o1), c = __ldg(q + o2);
-                    if (p.src_bool) {
-                        a = a ? 255 : 0;
-                        b = b ? 255 : 0;
-                        c = c ? 255 : 0;
-                    }
-                    s_tmp[(r - r0) * kDecTX + tid] = (uint8_t)clip8((1 << (kPrecBits - 1)) + a * k0 + b * k1 + c * k2);
+                for (int r = 0; r < r1 - r0; ++r) {
+                    const uint8_t* q = s + r * p.cstride;
+                    const unsigned acc = (1u << (kPrecBits + 1)) + q[0] * k0 + q[o1] * k1 + q[o2] * k2;
+                    s_tmp[r * kDecTX + tid] = (uint8_t)(acc >> 24);
                 }
             } else {
-                for (int r = r0; r < r1; ++r) {
-                    const uint8_t* q = s + (size_t)r * p.W;
+                for (int r = 0; r < r1 - r0; ++r) {
+                    const uint8_t* q = s + r * p.cstride;
                     int acc = 1 << (kPrecBits - 1);
-                    for (int j = 0; j < m.y; ++j) {
-                        int v = __ldg(q + j);
-                        if (p.src_bool) v = v ? 255 : 0;
-                        acc += v * __ldg(w + j);
-                    }
-                    s_tmp[(r - r0) * kDecTX + tid] = (uint8_t)clip8(acc);
+                    for (int j = 0; j < m.y; ++j) acc += (int)q[j] * __ldg(w + j);
+                    s_tmp[r * kDecTX + tid] = (uint8_t)clip8(acc);
                 }
             }
         }
     }
     __syncthreads();
-    uint8_t* out = p.out + (size_t)d * p.nh * p.nw;
     if (kVec) {  // nw % 16 == 0: 16 columns per thread, 16 rows per sweep
         const int c = tid & 15, x = x0 + c * 16;
         if (x < p.nw) {
@@ -398,19 +431,21 @@ __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams
                 const int2 m = __ldg(p.ymeta + y);
                 const int* w = p.yw + (size_t)y * p.ky;
                 const uint8_t* col = s_tmp + (m.x - r0) * kDecTX + c * 16;
-                int acc[16];
+                unsigned acc[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) acc[q] = 1 << (kPrecBits - 1);
+                for (int q = 0; q < 16; ++q) acc[q] = 1u << (kPrecBits + 1);
                 for (int j = 0; j < m.y; ++j) {
-                    const int k = __ldg(w + j);
+                    const unsigned k = (unsigned)__ldg(w + j) << 2;
+                    if (k == 0u) continue;  // an upscale has three taps per row and often a zero weight among them
                     const uint4 v = *reinterpret_cast<const uint4*>(col + j * kDecTX);
                     const unsigned vw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) acc[q] += (int)((vw[q >> 2] >> ((q & 3) * 8)) & 0xffu) * k;
+                    for (int q = 0; q < 16; ++q) acc[q] += __byte_perm(vw[q >> 2], 0u, 0x4440u + (q & 3)) * k;
                 }
-                unsigned o[4] = {0u, 0u, 0u, 0u};
+                unsigned o[4];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) o[q >> 2] |= (unsigned)clip8(acc[q]) << ((q & 3) * 8);
+                for (int q = 0; q < 4; ++q)  // the top bytes of four sums
+                    o[q] = __byte_perm(__byte_perm(acc[4 * q], acc[4 * q + 1], 0x0073u), __byte_perm(acc[4 * q + 2], acc[4 * q + 3], 0x0073u), 0x5410u);
                 __stcs(reinterpret_cast<uint4*>(out + (size_t)y * p.nw + x), make_uint4(o[0], o[1], o[2], o[3]));
             }
         }
@@ -431,7 +466,7 @@ __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams
 
 struct DecodeLayout {
     size_t xmeta_off, xw_off, ymeta_off, yw_off, bytes;
-    int kx, ky, rmax;
+    int kx, ky, rmax, cstride;
 };
 
 // Resample.c: ksize = (int)ceil(support) * 2 + 1 with support = max(in / out, 1) for the triangle filter
@@ -458,6 +493,8 @@ static DecodeLayout decode_layout(int ch, int cw, int nh, int nw) {
     // input rows under kDecTY output rows: the centres span (kDecTY - 1) * scale, the taps reach `support` either side
     const double sy = (double)ch / (double)nh;
     l.rmax = (int)ceil((kDecTY - 1) * sy) + l.ky + 2;
+    const double sx = (double)cw / (double)nw;
+    l.cstride = (((int)ceil((kDecTX - 1) * sx) + l.kx + 2) + 15) / 16 * 16;
     return l;
 }
 
@@ -528,7 +565,7 @@ int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int 
     const DecodeLayout l = decode_layout(crop_h, crop_w, out_h, out_w);
     if (workspace_bytes < l.bytes || (reinterpret_cast<uintptr_t>(workspace) & 255u))
         return fail(MRCNN_E_WORKSPACE, "mrcnn_decode_masks: workspace too small or not 256-byte aligned");
-    const size_t smem = (size_t)l.rmax * kDecTX;
+    const size_t smem = (size_t)l.rmax * (kDecTX + l.cstride);
     MRCNN_REQUIRE(smem <= 200 * 1024, "mrcnn_decode_masks: downscale factor too large (%d intermediate rows per tile)", l.rmax);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     DecodeParams p;
@@ -536,7 +573,7 @@ int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int 
     p.D = D; p.H = H; p.W = W;
     p.top = top; p.left = left; p.ch = crop_h; p.cw = crop_w;
     p.nh = out_h; p.nw = out_w;
-    p.kx = l.kx; p.ky = l.ky; p.rmax = l.rmax;
+    p.kx = l.kx; p.ky = l.ky; p.rmax = l.rmax; p.cstride = l.cstride;
     p.xmeta = reinterpret_cast<const int2*>(ws + l.xmeta_off);
     p.xw = reinterpret_cast<const int*>(ws + l.xw_off);
     p.ymeta = reinterpret_cast<const int2*>(ws + l.ymeta_off);

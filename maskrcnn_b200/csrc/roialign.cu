@@ -1025,17 +1025,12 @@ static bool gather_eligible(const int H[4], const int W[4], int B, int C, int N,
     return true;
 }
 
-// One or two heads (the same boxes pooled at pools[h] x pools[h], upstream gradients grads[h]) into one gradient pyramid.
-static int launch_bwd_gather(int heads, const float* const grads[2], const int pools[2], const int H[4], const int W[4], int B,
-                             int C, const float* boxes, const int32_t* box_index, int N, float image_area, float* const gfm[4],
-                             int accumulate, void* workspace, cudaStream_t stream) {
-    long long bins = 0;
-    for (int h = 0; h < heads; ++h) bins += (long long)pools[h] * pools[h];
-    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, bins);
+// Geometry + workspace pointers of a gather backward (everything but the tensors).
+static GatherParams gather_params(const GatherWorkspace& ws, const int H[4], const int W[4], int B, int C, int N, float image_area) {
     GatherParams g = {};
     int base = 0;
     for (int l = 3; l >= 0; --l) {  // coarse levels first: their units collect the most work
-        g.g[l].ptr = gfm[l];
+        g.g[l].ptr = nullptr;
         g.g[l].H = H[l];
         g.g[l].W = W[l];
         g.g[l].segs = (W[l] + kGTile - 1) / kGTile;
@@ -1045,17 +1040,23 @@ static int launch_bwd_gather(int heads, const float* const grads[2], const int p
     g.units = base;
     g.rule = make_level_rule(image_area);
     g.B = B; g.C = C; g.N = N;
-    g.boxes = boxes; g.box_index = box_index;
-    g.grads = grads[0]; g.grads2 = grads[heads - 1];
     g.cnt = ws.cnt; g.pos = ws.pos; g.cursor = ws.cursor; g.items = ws.items;
     g.err = device_error_word();
+    return g;
+}
+
+// Passes 1-3: the work-item queues of every unit.  They depend on the boxes, the pool sizes, C and the pyramid geometry
+// only - not on the gradients - so a training step can build them while the forward runs (mrcnn_..._backward_plan).
+static int launch_gather_plan(GatherParams g, const GatherWorkspace& ws, void* workspace, int heads, const int pools[2],
+                              const float* boxes, const int32_t* box_index, cudaStream_t stream) {
+    g.boxes = boxes; g.box_index = box_index;
     MRCNN_CUDA(cudaMemsetAsync(workspace, 0, ws.clear_bytes, stream));
     const unsigned ugrid = (unsigned)((g.units + 255) / 256);
     for (int pass = 0; pass < 2; ++pass) {  // count every head, allocate, fill every head
         for (int h = 0; h < heads; ++h) {
             g.ph = pools[h]; g.pw = pools[h];
             g.head_flag = h ? kOHead2 : 0;
-            const long long walkers = (long long)N * pools[h] * 2;
+            const long long walkers = (long long)g.N * pools[h] * 2;
             const unsigned wgrid = (unsigned)((walkers + 255) / 256);
             if (pass == 0) bwd_items_kernel<false><<<wgrid, 256, 0, stream>>>(g);
             else bwd_items_kernel<true><<<wgrid, 256, 0, stream>>>(g);
@@ -1066,7 +1067,15 @@ static int launch_bwd_gather(int heads, const float* const grads[2], const int p
             MRCNN_LAUNCH_CHECK();
         }
     }
-    const bool wide = (C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
+    return MRCNN_OK;
+}
+
+// Pass 4: one warp per unit sums the bins its queue lists and writes its 8 pixels once.
+static int launch_gather_run(GatherParams g, int heads, const float* const grads[2], float* const gfm[4], int accumulate,
+                             cudaStream_t stream) {
+    for (int l = 0; l < 4; ++l) g.g[l].ptr = gfm[l];
+    g.grads = grads[0]; g.grads2 = grads[heads - 1];
+    const bool wide = (g.C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
     const unsigned grid = (unsigned)g.units;
     // U = 2 items per stage, ST = 4 stages: best of the (U, ST) grid measured on B200 (profiles/r01_*gather*)
     if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true><<<grid, 32, 0, stream>>>(g);
@@ -1075,6 +1084,18 @@ static int launch_bwd_gather(int heads, const float* const grads[2], const int p
     else roialign_bwd_gather_kernel<1, 2, 4, false><<<grid, 32, 0, stream>>>(g);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
+}
+
+// One or two heads (the same boxes pooled at pools[h] x pools[h], upstream gradients grads[h]) into one gradient pyramid.
+static int launch_bwd_gather(int heads, const float* const grads[2], const int pools[2], const int H[4], const int W[4], int B,
+                             int C, const float* boxes, const int32_t* box_index, int N, float image_area, float* const gfm[4],
+                             int accumulate, void* workspace, cudaStream_t stream) {
+    long long bins = 0;
+    for (int h = 0; h < heads; ++h) bins += (long long)pools[h] * pools[h];
+    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, bins);
+    const GatherParams g = gather_params(ws, H, W, B, C, N, image_area);
+    if (int rc = launch_gather_plan(g, ws, workspace, heads, pools, boxes, box_index, stream)) return rc;
+    return launch_gather_run(g, heads, grads, gfm, accumulate, stream);
 }
 
 static int check_layout(int v, const char* what) {
@@ -1257,6 +1278,47 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
         if (int rc = launch_roi(p, gfm_layout, grads_layout, true, stream)) return rc;
     }
     return MRCNN_OK;
+}
+
+int mrcnn_pyramid_roi_align_backward_plan(const int H[4], const int W[4], int B, int C, const float* boxes,
+                                          const int32_t* box_index, int N, int pool, float image_area, void* workspace,
+                                          size_t workspace_bytes, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(H && W, "mrcnn_pyramid_roi_align_backward_plan: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N > 0 && pool > 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_backward_plan: bad sizes");
+    for (int l = 0; l < 4; ++l) MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_backward_plan: level %d has empty shape", l);
+    MRCNN_REQUIRE_DEV(boxes);
+    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    MRCNN_REQUIRE_DEV(workspace);
+    const long long bins = (long long)pool * pool;
+    float* const none[4] = {nullptr, nullptr, nullptr, nullptr};
+    MRCNN_REQUIRE(gather_eligible(H, W, B, C, N, bins, pool, MRCNN_NHWC, MRCNN_NHWC, nullptr, none, workspace, workspace_bytes),
+                  "mrcnn_pyramid_roi_align_backward_plan: needs C %% 4 == 0, N * pool^2 * C < 2^31 and a 256-byte aligned workspace "
+                  "of mrcnn_pyramid_roi_align_backward_workspace_bytes()");
+    MRCNN_REQUIRE(device_error_word() != nullptr, "cannot allocate device error word");
+    const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, bins);
+    const int pools[2] = {pool, pool};
+    return launch_gather_plan(gather_params(ws, H, W, B, C, N, image_area), ws, workspace, 1, pools, boxes, box_index,
+                              (cudaStream_t)stream);
+}
+
+int mrcnn_pyramid_roi_align_backward_planned(const float* grads, const int H[4], const int W[4], int B, int C, int N, int pool,
+                                             float* const gfm[4], int zero_fill, const void* workspace, size_t workspace_bytes,
+                                             mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(gfm && H && W, "mrcnn_pyramid_roi_align_backward_planned: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N > 0 && pool > 0, "mrcnn_pyramid_roi_align_backward_planned: bad sizes");
+    for (int l = 0; l < 4; ++l) {
+        MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_backward_planned: level %d has empty shape", l);
+        MRCNN_REQUIRE_DEV(gfm[l]);
+    }
+    MRCNN_REQUIRE_DEV(grads);
+    MRCNN_REQUIRE_DEV(workspace);
+    const long long bins = (long long)pool * pool;
+    MRCNN_REQUIRE(gather_eligible(H, W, B, C, N, bins, pool, MRCNN_NHWC, MRCNN_NHWC, grads, gfm, workspace, workspace_bytes),
+                  "mrcnn_pyramid_roi_align_backward_planned: needs channels-last grads and gfm, C %% 4 == 0, N * pool^2 * C < 2^31 "
+                  "and the workspace mrcnn_pyramid_roi_align_backward_plan() filled");
+    const GatherWorkspace ws = carve_gather(const_cast<void*>(workspace), H, W, B, N, bins);
+    const float* const gr[2] = {grads, grads};
+    return launch_gather_run(gather_params(ws, H, W, B, C, N, 1.0f), 1, gr, gfm, zero_fill ? 0 : 1, (cudaStream_t)stream);
 }
 
 size_t mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(const int H[4], const int W[4], int B, int N, int pool_a,

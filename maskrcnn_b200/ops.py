@@ -24,7 +24,7 @@ from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
            "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "decode_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "check_device_errors",
-           "set_backward_algorithm"]
+           "set_backward_algorithm", "set_backward_planning"]
 
 
 # Backward of the channels-last PyramidROIAlign: "auto" (MRCNN_BWD_AUTO: the row-owner gather whenever the call is
@@ -38,6 +38,26 @@ def set_backward_algorithm(name):
     if name not in ("auto", "gather", "scatter"):
         raise ValueError("backward algorithm must be 'auto', 'gather' or 'scatter'")
     BACKWARD_ALGORITHM = name
+
+
+BACKWARD_PLANNING = True
+_PLAN_STREAMS = {}
+
+
+def set_backward_planning(enabled):
+    """True (default): when a feature map requires grad, pyramid_roi_align's FORWARD also builds the work-item queues of
+    its gather backward (they depend on the boxes only) on a side stream, concurrently with the forward kernel, and the
+    backward is the one gather launch (mrcnn_pyramid_roi_align_backward_plan / _planned).  False: the backward builds
+    them itself.  Results are identical."""
+    global BACKWARD_PLANNING
+    BACKWARD_PLANNING = bool(enabled)
+
+
+def _plan_stream(device):
+    key = torch.device(device).index
+    if key not in _PLAN_STREAMS:
+        _PLAN_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)   # small kernels: let them slip in beside the forward
+    return _PLAN_STREAMS[key]
 
 
 def set_proposal_nms(name):
@@ -219,6 +239,20 @@ class _PyramidRoiAlign(torch.autograd.Function):
                                                           float(image_area), out.data_ptr(), ol, None, _stream()))
         ctx.save_for_backward(boxes, box_ind)
         ctx.meta = (Hs, Ws, B, C, fl, pool, float(image_area), offsets)
+        ctx.plan = None
+        if (BACKWARD_PLANNING and BACKWARD_ALGORITHM != "scatter" and any(ctx.needs_input_grad[6:]) and fl == NHWC and ol == NHWC
+                and C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets):
+            # the backward's item queues need the boxes only: build them next to the forward kernel, on a side stream
+            with torch.cuda.device(out.device):
+                cur, side = torch.cuda.current_stream(), _plan_stream(out.device)
+                ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(_lib.i4(Hs), _lib.i4(Ws), B, N, pool)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
+                side.wait_stream(cur)       # boxes (and the previous user of the workspace block) are ready
+                check(lib.mrcnn_pyramid_roi_align_backward_plan(_lib.i4(Hs), _lib.i4(Ws), B, C, boxes.data_ptr(), _ptr(box_ind), N,
+                                                                pool, float(image_area), ws.data_ptr(), ws_bytes, side.cuda_stream))
+                for t in (ws, boxes) + ((box_ind,) if box_ind is not None else ()):
+                    t.record_stream(side)
+                ctx.plan = (ws, ws_bytes, side.record_event())
         return out
 
     @staticmethod
@@ -228,6 +262,14 @@ class _PyramidRoiAlign(torch.autograd.Function):
         grad, gl = _layout4(grad)
         N = boxes.size(0)
         gfm = [_empty4((B, C, h, w), fl, grad) for h, w in zip(Hs, Ws)]
+        if ctx.plan is not None and gl == NHWC and grad.data_ptr() % 16 == 0:
+            ws, ws_bytes, ready = ctx.plan
+            with torch.cuda.device(grad.device):
+                torch.cuda.current_stream().wait_event(ready)
+                check(lib.mrcnn_pyramid_roi_align_backward_planned(grad.data_ptr(), _lib.i4(Hs), _lib.i4(Ws), B, C, N, pool,
+                                                                   _lib.vp4([g.data_ptr() for g in gfm]), 1, ws.data_ptr(), ws_bytes,
+                                                                   _stream()))
+            return (None, None, None, None, None, None) + tuple(gfm)
         with torch.cuda.device(grad.device):
             gather_ok = fl == NHWC and gl == NHWC and C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets
             algo = {"auto": _lib.BWD_AUTO, "gather": _lib.BWD_GATHER if gather_ok else _lib.BWD_SCATTER,

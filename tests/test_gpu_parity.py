@@ -451,6 +451,54 @@ def test_pyramid_backward_gather(ops, pool, B, C, size, N, mode):
     ops.check_device_errors()
 
 
+@pytest.mark.parametrize("planning", [True, False])
+@pytest.mark.parametrize("pool,B,C,size,N", [(7, 3, 256, 256, 200), (14, 2, 128, 200, 90), (14, 4, 64, 512, 700)])
+def test_backward_planning(ops, planning, pool, B, C, size, N):
+    """The gather backward's item queues built by the FORWARD on a side stream (mrcnn_pyramid_roi_align_backward_plan) and
+    the one-launch backward over them (_planned) against the oracle, next to the unplanned path; a plan serves several
+    backward calls (retain_graph)."""
+    from maskrcnn_b200 import _lib
+    fms = synth.feature_pyramid(B, C, 61 + B, image=size)
+    boxes = synth.random_rois(N, 62 + N, image=float(size), min_size=6, max_size=size * 0.9)
+    boxes[0] += 0.4
+    boxes[1] = boxes[1][[2, 3, 0, 1]]
+    ind = np.random.default_rng(N).integers(0, B, N).astype(np.int32)
+    g = np.random.default_rng(9).standard_normal((N, C, pool, pool), dtype=np.float32)
+    want_g = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, ind, float(size * size))
+    calls = {"plan": 0, "planned": 0}
+    real_plan, real_planned = _lib.lib.mrcnn_pyramid_roi_align_backward_plan, _lib.lib.mrcnn_pyramid_roi_align_backward_planned
+
+    def count(name, fn):
+        def wrapped(*a):
+            calls[name] += 1
+            return fn(*a)
+        return wrapped
+    _lib.lib.mrcnn_pyramid_roi_align_backward_plan = count("plan", real_plan)
+    _lib.lib.mrcnn_pyramid_roi_align_backward_planned = count("planned", real_planned)
+    ops.set_backward_planning(planning)
+    try:
+        ts = [cl(dev(f)).requires_grad_(True) for f in fms]
+        out = ops.pyramid_roi_align(ts, dev(boxes), dev(ind), pool, (size, size, 3), out_channels_last=True)
+        out.backward(cl(dev(g)), retain_graph=True)
+        first = [t.grad.clone() for t in ts]
+        out.backward(cl(dev(g)))                       # the same plan again: gradients accumulate to twice the value
+        # no feature map requires grad -> no plan is built
+        ops.pyramid_roi_align([cl(dev(f)) for f in fms], dev(boxes), dev(ind), pool, (size, size, 3), out_channels_last=True)
+        # an NCHW upstream gradient cannot use the plan: the regular path answers
+        ts2 = [cl(dev(f)).requires_grad_(True) for f in fms]
+        out2 = ops.pyramid_roi_align(ts2, dev(boxes), dev(ind), pool, (size, size, 3), out_channels_last=True)
+        out2.backward(dev(g).contiguous())
+    finally:
+        ops.set_backward_planning(True)
+        _lib.lib.mrcnn_pyramid_roi_align_backward_plan, _lib.lib.mrcnn_pyramid_roi_align_backward_planned = real_plan, real_planned
+    assert calls == ({"plan": 2, "planned": 2} if planning else {"plan": 0, "planned": 0})
+    for a, t, t2, w in zip(first, ts, ts2, want_g):
+        assert rel_err(a.cpu().numpy(), w) <= BWD_TOL
+        assert rel_err(t.grad.cpu().numpy(), 2.0 * w) <= BWD_TOL
+        assert rel_err(t2.grad.cpu().numpy(), w) <= BWD_TOL
+    ops.check_device_errors()
+
+
 # ------------------------------------------------------------------ detection-target layer (mrn_samples)
 def _target_cfg(train_rois):
     import types
