@@ -511,6 +511,8 @@ def ncu_traffic():
     for key, rec in json.load(open(files[-1])).items():
         cap = key.split(":", 1)[0]
         out[cap] = out.get(cap, 0.0) + rec["dram_bytes"] / 1e6
+        if "roialign_bwd_gather_kernel" in key:      # the gather launch alone (the planned backward)
+            out[cap + ":gather"] = rec["dram_bytes"] / 1e6
     return out
 
 
@@ -866,7 +868,7 @@ def main():
             "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
             plan_name: (plans, 2 * wl.N * 20),
         }
-        captures = dict(zip(ops, ("fwd7_nhwc", "fwd14_nhwc", "bwd7_nhwc", "bwd14_nhwc", None, None)))
+        captures = dict(zip(ops, ("fwd7_nhwc", "fwd14_nhwc", "bwd7_nhwc:gather", "bwd14_nhwc:gather", None, None)))
         traffic = ncu_traffic()
         kern = {}
         torch.cuda.synchronize()

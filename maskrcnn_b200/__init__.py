@@ -3,7 +3,7 @@
     nms, CropFunction                      drop-ins for c++ext/maskrcnn/__init__.py
     roi_align, rpn_refine, mrn_refine, mrn_samples   drop-ins for the model.py functions that call them
     rpn_samples                            drop-in for data.rpn_samples (RPN anchor matching)
-    full_masks                             drop-in for data.full_masks (mask paste-back into the image)
+    full_masks, decode_masks               drop-ins for data.full_masks / data.decode_masks (mask paste-back, back to the original frame)
     rpn_detect, rpn_pack                   drop-in for MaskRCNN.rpn_detect: RPN head outputs -> [B,A,2] / [B,A,4] in one launch
     pyramid_roi_align, proposal_layer, detection_layer, detection_targets   batched, sync-free variants
     patch(model_module)                    swaps the fused versions into an unmodified reference model.py
@@ -23,8 +23,9 @@ def patch(model_module, data_module=None):
     """Monkey-patches an imported reference `model` module (model.py) so that its RoI hot path runs on
     the fused kernels: model.roi_align, model.mrn_samples, MaskRCNN.rpn_detect, MaskRCNN.rpn_refine, MaskRCNN.mrn_refine; with
     the reference's `data` module given as well, data.rpn_samples (the anchor matching the dataset runs per sample - the
-    reference's DataLoader uses num_workers=0, model.py:1528-1532, so it runs in the CUDA process) and data.full_masks (the
-    mask paste-back model.predict calls as datalib.full_masks, model.py:1190).  The `maskrcnn` package the
+    reference's DataLoader uses num_workers=0, model.py:1528-1532, so it runs in the CUDA process), data.full_masks (the
+    mask paste-back model.predict calls as datalib.full_masks, model.py:1190) and data.decode_masks (model.detect,
+    model.py:1130).  The `maskrcnn` package the
     module imported (model.py:25) should already be this repo's drop-in (put the repo root on sys.path)."""
     model_module.roi_align = roi_align
     model_module.MaskRCNN.rpn_refine = rpn_refine
@@ -34,4 +35,5 @@ def patch(model_module, data_module=None):
     if data_module is not None:
         data_module.rpn_samples = rpn_samples
         data_module.full_masks = full_masks
+        data_module.decode_masks = decode_masks
     return model_module

@@ -64,3 +64,32 @@ def test_python_api_has_no_cpu_fallback():
         m.proposal_layer(torch.zeros(1, 8, 2), torch.zeros(1, 8, 4), torch.zeros(8, 4), 4, 2, 0.7)
     with pytest.raises(TypeError):
         m.detection_layer(torch.zeros(1, 4, 4), torch.zeros(1, 4, 3), torch.zeros(1, 4, 3, 4), torch.zeros(1, 4), 0, 0.3, 2)
+    with pytest.raises(TypeError):
+        m.full_masks(torch.zeros(1, dtype=torch.int64), torch.zeros(1, 4), torch.zeros(1, 2, 28, 28), 32, 32)
+    with pytest.raises(TypeError):
+        m.decode_masks(torch.zeros(1, 32, 32, dtype=torch.bool), 0.5, (32, 32))
+
+
+def test_patch_swaps_every_replaced_symbol():
+    """patch() on stand-ins for the reference's model / data modules: every function SURVEY 8(a) + 8(f) lists is swapped."""
+    import types
+    import maskrcnn_b200 as m
+    model = types.SimpleNamespace(MaskRCNN=type("MaskRCNN", (), {}), roi_align=None, mrn_samples=None)
+    data = types.SimpleNamespace(rpn_samples=None, full_masks=None, decode_masks=None)
+    assert m.patch(model, data) is model
+    assert model.roi_align is m.roi_align and model.mrn_samples is m.mrn_samples
+    assert model.MaskRCNN.rpn_detect is m.rpn_detect and model.MaskRCNN.rpn_refine is m.rpn_refine and model.MaskRCNN.mrn_refine is m.mrn_refine
+    assert data.rpn_samples is m.rpn_samples and data.full_masks is m.full_masks and data.decode_masks is m.decode_masks
+
+
+def test_decode_masks_arguments_without_a_gpu():
+    from maskrcnn_b200 import _lib
+    L = _lib.lib
+    assert L.mrcnn_decode_masks_workspace_bytes(640, 1024, 1200, 1920) >= (1200 + 1920) * (8 + 3 * 4)
+    rc = L.mrcnn_decode_masks(None, 1, 1, 64, 64, 10, 0, 60, 64, 120, 128, None, None, 0, None)    # window leaves the mask
+    assert rc == _lib.E_INVALID_ARG and b"crop window" in L.mrcnn_last_error()
+    rc = L.mrcnn_decode_masks(None, 1, 1, 64, 64, 0, 0, 64, 64, 0, 128, None, None, 0, None)       # PIL's message
+    assert rc == _lib.E_INVALID_ARG and b"must be > 0" in L.mrcnn_last_error()
+    hw = _lib.i4([64, 32, 16, 8])
+    rc = L.mrcnn_pyramid_roi_align_backward_plan(hw, hw, 1, 6, None, None, 4, 7, 1.0, None, 0, None)
+    assert rc != 0

@@ -975,7 +975,7 @@ def test_detect_flow_golden_dropins(ops):
     got = ops.full_masks(torch.zeros(len(ok), dtype=torch.int64, device="cuda"), bx[0], dev(g["mask_in_sel"]).unsqueeze(1), h, w).cpu().numpy()
     np.testing.assert_array_equal(got[ok], want[ok])
     assert not got[~ok].any()
-    # decode_masks (data.py:265-284, model.py:1131): back to the 1920 x 1200 frame
+    # decode_masks (data.py:265-284, model.py:1130): back to the 1920 x 1200 frame
     y1, x1, y2, x2 = (int(v) for v in g["det_in_window"])
     dec = ops.decode_masks(dev(want[ok]), float(g["decode_in_scale"]), (y2 - y1, x2 - x1)).cpu().numpy()
     assert dec.shape[1:] == tuple(int(v) for v in g["decode_out_hw"])

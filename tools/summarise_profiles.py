@@ -30,6 +30,9 @@ with open(os.path.join(P, "%s_launches_summary.txt" % R), "w") as f:
         share = agg[k][1] / mine if "mrcnn::" in k else float("nan")
         f.write("%-82s %6d %12.1f %10.1f %8.3f\n" % (k, agg[k][0], agg[k][1] / 1e3, agg[k][1] / 1e3 / agg[k][0], share))
 shutil.copy(src, os.path.join(P, "%s_launches.csv" % R))
+nxt = os.path.join(G, "%s_next_launches.csv" % R)       # launch list of tools/prof_next.py (SURVEY 8f kernels)
+if os.path.exists(nxt):
+    shutil.copy(nxt, os.path.join(P, "%s_next_launches.csv" % R))
 
 # 2. per-kernel full captures
 traffic = {}
