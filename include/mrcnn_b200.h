@@ -215,6 +215,11 @@ MRCNN_API int mrcnn_rpn_unpack(const float* grad_logits, const float* grad_bbox,
  * (y1,x1,y2,x2,score,class) score-descending, zero padded; counts_out int32 [B] (0 = the reference's
  * (None,None,None)); index_out optional int32 [B,max_inst] = source RoI of each detection. */
 MRCNN_API size_t mrcnn_detection_workspace_bytes(int B, int N);
+/* NMS inside the detection layer, same constants and meaning as mrcnn_set_proposal_nms (results are identical): LAZY =
+ * chunks of 64 boxes in score order against the same-class survivors so far, stopping at the max_inst-th survivor (no
+ * N x N mask); MASK = class-aware suppression words + sweep; AUTO (default) = LAZY when max_inst <= 1024.  With MASK
+ * and N > 1024 the workspace above is required; LAZY never needs it. */
+MRCNN_API int mrcnn_set_detection_nms(int algo);
 MRCNN_API int mrcnn_detection_layer(const float* rois, const float* probs, const float* deltas,
                           const float* windows, int B, int N, int NC,
                           float min_confidence, float nms_threshold, int max_inst,

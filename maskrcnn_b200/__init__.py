@@ -13,7 +13,7 @@ All compute is hand-written CUDA in libmrcnn_b200.so (C ABI: include/mrcnn_b200.
 from .ops import (CropFunction, check_device_errors, crop_and_resize, decode_masks, detection_layer, detection_targets, full_masks,  # noqa: F401
                   mrn_refine, mrn_samples, nms, proposal_layer, pyramid_roi_align, pyramid_roi_align_backward_pair, pyramid_roi_align_pair, roi_align,
                   rpn_detect, rpn_pack, rpn_refine, rpn_samples,
-                  set_backward_algorithm, set_backward_planning, set_proposal_nms)
+                  set_backward_algorithm, set_backward_planning, set_detection_nms, set_proposal_nms)
 from ._lib import LIB_PATH, MrcnnError  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mrcnn_decode_masks_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mrcnn_decode_masks": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mrcnn_set_proposal_nms": (_i, [_i]),
+    "mrcnn_set_detection_nms": (_i, [_i]),
     "mrcnn_proposal_layer_fg": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f4, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "mrcnn_rpn_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mrcnn_rpn_unpack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
-           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "decode_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "check_device_errors",
+           "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "decode_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "set_detection_nms", "check_device_errors",
            "set_backward_algorithm", "set_backward_planning"]
 
 
@@ -67,6 +67,16 @@ def set_proposal_nms(name):
     if name not in algos:
         raise ValueError("proposal NMS must be 'auto', 'mask' or 'lazy'")
     check(lib.mrcnn_set_proposal_nms(algos[name]))
+
+
+def set_detection_nms(name):
+    """NMS inside the detection layer: "auto" (lazy when max_instances <= 1024), "mask" (class-aware IoU words + sweep) or
+    "lazy" (chunks of 64 boxes against the same-class survivors so far, stops at the max_instances-th survivor).
+    Identical results."""
+    algos = {"auto": 0, "mask": 1, "lazy": 2}
+    if name not in algos:
+        raise ValueError("detection NMS must be 'auto', 'mask' or 'lazy'")
+    check(lib.mrcnn_set_detection_nms(algos[name]))
 
 
 def _stream():

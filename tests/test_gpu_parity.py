@@ -355,9 +355,19 @@ def test_proposal_golden_and_dropin(ops):
 
 
 # ------------------------------------------------------------------ detection layer
-@pytest.mark.parametrize("N,B,min_conf,D", [(1000, 3, 0.0, 100), (400, 2, 0.7, 50), (70, 1, 0.0, 100), (1500, 2, 0.0, 100)])
-def test_detection_layer_matches_oracle(ops, N, B, min_conf, D):
-    NC = 81
+@pytest.fixture(params=["lazy", "mask"])
+def det_algo(request, ops):
+    """Both NMS implementations of the detection layer must give the oracle's result."""
+    ops.set_detection_nms(request.param)
+    yield request.param
+    ops.set_detection_nms("auto")
+
+
+@pytest.mark.parametrize("N,B,min_conf,D,NC", [(1000, 3, 0.0, 100, 81), (400, 2, 0.7, 50, 81), (70, 1, 0.0, 100, 81), (1500, 2, 0.0, 100, 81),
+                                               (1000, 2, 0.0, 300, 3), (1000, 2, 0.0, 1000, 2), (640, 1, 0.0, 7, 5), (129, 2, 0.0, 1024, 4)])
+def test_detection_layer_matches_oracle(ops, det_algo, N, B, min_conf, D, NC):
+    """81 classes (COCO) and few-class cases, where nearly every pair of boxes shares a class: heavy suppression, the lazy
+    NMS walks many chunks; max_inst from 7 to more than the number of RoIs."""
     rois = np.stack([synth.random_rois(N, 300 + i) for i in range(B)])
     pd = [synth.head_outputs(N, NC, 400 + i) for i in range(B)]
     probs = np.stack([p for p, _ in pd])
@@ -375,7 +385,30 @@ def test_detection_layer_matches_oracle(ops, N, B, min_conf, D):
         assert not dets[i, counts[i]:].any()
 
 
-def test_detection_golden_and_dropin(ops):
+def test_detection_nms_algorithms_agree_at_full_size(ops):
+    """configs[4] size (64 images x 1000 RoIs x 81 classes, top-100) and a 2-class variant at several thresholds: lazy and
+    mask + sweep return the same bytes."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    B, N = 64, 1000
+    rois = dev(np.stack([synth.random_rois(N, 500 + i) for i in range(B)]))
+    win = torch.tensor([[0, 0, 1024, 1024]], dtype=torch.float32, device="cuda").repeat(B, 1)
+    try:
+        for NC, thr, D in ((81, 0.3, 100), (2, 0.3, 100), (2, 0.05, 50), (3, 0.7, 600)):
+            probs = torch.softmax(3 * torch.randn(B, N, NC, device="cuda", generator=g), -1)
+            deltas = 0.1 * torch.randn(B, N, NC, 4, device="cuda", generator=g)
+            out = {}
+            for algo in ("lazy", "mask"):
+                ops.set_detection_nms(algo)
+                out[algo] = ops.detection_layer(rois, probs, deltas, win, 0.0, thr, D, return_index=True)
+            for a, b in zip(out["lazy"], out["mask"]):
+                assert torch.equal(a, b)
+            assert int(out["lazy"][1].min()) > 0
+    finally:
+        ops.set_detection_nms("auto")
+
+
+def test_detection_golden_and_dropin(ops, det_algo):
     import types
     g = golden()
     cfg = types.SimpleNamespace(RPN_BBOX_STD_DEV=np.array([0.1, 0.1, 0.2, 0.2]), IMAGE_SHAPE=np.array([1024, 1024, 3]),
