@@ -1,5 +1,5 @@
 """Runs the SURVEY 8(f) kernels a few times each (for ncu): proposal layer with both NMS algorithms, rpn_pack, full_masks,
-decode_masks, detection layer, detection-target layer.  usage: prof_next.py"""
+decode_masks, detection layer with both NMS algorithms.  usage: prof_next.py"""
 import os
 import sys
 
@@ -34,5 +34,15 @@ cls_d, boxes_d, masks_d = (torch.from_numpy(a).to(dev) for a in (cls, boxes, mas
 for _ in range(2):
     pasted = m.full_masks(cls_d, boxes_d, masks_d, IMAGE, IMAGE)
     dec = m.decode_masks(pasted, IMAGE / 1920.0, (640, IMAGE))
+B, N, NC = 64, 1000, 81
+rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(B)])).to(dev)
+probs = torch.softmax(3 * torch.randn(B, N, NC, device=dev, generator=g), -1)
+deltas = 0.1 * torch.randn(B, N, NC, 4, device=dev, generator=g)
+win = torch.tensor([[0, 0, IMAGE, IMAGE]], dtype=torch.float32, device=dev).repeat(B, 1)
+for algo in ("lazy", "mask"):
+    m.set_detection_nms(algo)
+    for _ in range(2):
+        dets, dc = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, 100)
+m.set_detection_nms("auto")
 torch.cuda.synchronize()
-print("done", counts.tolist(), int(pasted.sum()), tuple(dec.shape))
+print("done", counts.tolist(), int(pasted.sum()), tuple(dec.shape), dc[:4].tolist())
