@@ -88,7 +88,7 @@ static ProposalWorkspace carve_proposal(void* base, int B, int A, int pre_nms) {
 // ---- 1. select + sort + decode --------------------------------------------------------------------
 
 struct SelShared {
-    int hist[256];
+    int hist[2][256];  // double-buffered by pass: a peer may still read pass p's histogram while pass p + 1 fills the other
     int tot[256];
     int loc_above[256];  // # local keys (matching the prefix) with a digit greater than d
     int warp_sums[32];
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
     int k_rem = p.pre;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int i = tid; i < 256; i += kSelThreads) sh.hist[i] = 0;
+        int* hist = sh.hist[pass & 1];
+        for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
         __syncthreads();
         const int iters = (n_local + kSelThreads - 1) / kSelThreads;
         for (int it = 0; it < iters; ++it) {
@@ -148,16 +149,22 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
             const unsigned digit = (key >> shift) & 255u;
             // warp-aggregated histogram update: one shared-memory atomic per distinct digit in the warp
             const unsigned active = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const unsigned peers = __match_any_sync(active, digit);
-                if (lane == (__ffs(peers) - 1)) atomicAdd(&sh.hist[digit], __popc(peers));
+            if (pass == 0) {
+                // the top byte of a score is sign + 7 exponent bits: a handful of distinct digits per warp, so one
+                // shared-memory atomic per distinct digit (match_any costs one round per distinct value)
+                if (in) {
+                    const unsigned peers = __match_any_sync(active, digit);
+                    if (lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
+                }
+            } else if (in) {
+                atomicAdd(&hist[digit], 1);  // mantissa digits are spread over the 256 bins: plain atomics rarely collide
             }
         }
         cluster.sync();  // every CTA's histogram of this pass is complete and visible
         if (tid < 256) {
             int s = 0;
 #pragma unroll
-            for (int r = 0; r < kClusterSize; ++r) s += *cluster.map_shared_rank(&sh.hist[tid], r);
+            for (int r = 0; r < kClusterSize; ++r) s += *cluster.map_shared_rank(&hist[tid], r);
             sh.tot[tid] = s;
         }
         __syncthreads();
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
             const int half = tid >> 8;     // 0: totals, 1: local
             const int t = tid & 255;
             const int d = 255 - t;         // thread order = descending digit, so a prefix scan is a suffix sum
-            const int v = half ? sh.hist[d] : sh.tot[d];
+            const int v = half ? hist[d] : sh.tot[d];
             int incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -191,12 +198,15 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
         const int d = sh.digit;
         if (tid == 0) {
             sh.gt_local += sh.loc_above[d];
-            if (pass == 3) sh.eq_local = sh.hist[d];
+            if (pass == 3) sh.eq_local = hist[d];
         }
         k_rem -= sh.above;
         prefix = (prefix << 8) | (uint32_t)d;
-        cluster.sync();  // all remote reads of hist done before it is cleared / gt,eq published
+        // no cluster barrier here: the next pass fills the OTHER histogram, and the barrier in the middle of that pass
+        // orders this pass's remote reads before the pass after it clears this buffer again
+        __syncthreads();  // sh.digit / sh.above are rewritten by the next pass
     }
+    cluster.sync();  // gt_local / eq_local of every CTA are published
     const uint32_t T = prefix;  // the k-th largest key; k_rem (>= 1) keys equal to T are still needed
 
     // ---- output offsets: ranks in order, keys > T first then this rank's share of the == T keys ----
