@@ -305,6 +305,21 @@ def test_proposal_layer_matches_oracle(ops, nms_algo, size, pre, post, B, thr):
         assert not rois[i, counts[i]:].any()
 
 
+def test_proposal_layer_many_images(ops, nms_algo):
+    """40 images in one call: 320 CTAs in 8-CTA clusters, several waves of clusters on the 148 SMs."""
+    size, B = 128, 40
+    anchors = synth.pyramid_anchors((size, size))
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 90 + i, image=float(size), n_clusters=5) for i in range(4)])
+    rc = np.stack([rcs[i % 4] for i in range(B)])
+    rb = np.stack([rbs[(i * 3) % 4] for i in range(B)])
+    rois, counts = ops.proposal_layer(dev(rc), dev(rb), dev(anchors), 2000, 300, 0.6, image_hw=(size, size))
+    rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
+    for i in range(B):
+        want = oracle.proposal_layer(rc[i], rb[i], anchors, 2000, 300, 0.6, height=float(size), width=float(size))
+        assert counts[i] == len(want)
+        np.testing.assert_array_equal(rois[i, :counts[i]], want)
+
+
 def test_proposal_layer_with_score_ties(ops, nms_algo):
     """All-equal and heavily tied scores: the selection must be the stable one (lowest anchor index first)."""
     size = 128

@@ -17,9 +17,5 @@ for spec in "fwd 7" "fwd 14" "bwd 7" "bwd 14"; do
 done
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:"roialign_bwd_nhwc|zero_levels" -c 2 \
     -o $O/${R}_bwd14_nhwc_scatter python tools/prof_one.py bwd 14 nhwc > $O/${R}_bwd14_scatter.log 2>&1
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:"proposal_|nms_|rpn_pack|full_masks|paste_prepare|decode_|detection_" -c 28 \
-    -o $O/${R}_next python tools/prof_next.py > $O/${R}_next.log 2>&1
-tail -1 $O/${R}_next.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_next_launches.csv \
-    python tools/prof_next.py > $O/${R}_next_launches.log 2>&1
+# the 8(f) / proposal / detection kernels: tools/collect_next.sh (a separate gpurun call: 64 MiB return limit)
 ls -la $O | tail -20
