@@ -840,10 +840,19 @@ def main():
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION on the pool's boxes) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries ONE JSON line: NCCL prints its "NCCL version ..." banner with a bare printf when the first
+        # communicator comes up, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     hbm, peak_src = hbm_peak()
     wl = Workload(torch, torch.device("cuda", local))
 
