@@ -75,6 +75,67 @@ def test_nms_properties_full_size(ops):
     np.testing.assert_array_equal(again, np.arange(len(k)))
 
 
+def test_nms_hypothesis_properties(ops):
+    """Property tests on random box sets drawn by hypothesis, unique scores: the CUDA keep list equals the
+    oracle's, is ascending, is a fixed point (NMS of the survivors keeps them all), and does not change when boxes that a
+    survivor suppresses are appended with lower scores."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(n=st.integers(1, 300), seed=st.integers(0, 10 ** 6), thr=st.sampled_from([0.0, 0.1, 0.3, 0.5, 0.7, 0.95, 1.0]),
+           cluster=st.booleans(), scale=st.sampled_from([64.0, 1024.0]))
+    def check(n, seed, thr, cluster, scale):
+        rng = np.random.default_rng(seed)
+        b = synth.random_rois(n, seed, image=scale, min_size=scale / 64, max_size=scale / 2) * scale
+        if cluster and n > 3:
+            h = n // 2
+            b[h:] = b[: n - h] + rng.uniform(-scale / 128, scale / 128, (n - h, 4)).astype(np.float32)
+        if n > 5:
+            b[rng.integers(0, n)] = b[rng.integers(0, n)]                      # an exact duplicate (IoU = 1)
+        dets = np.concatenate([b, synth.unique_scores(n, seed + 1)[:, None]], 1).astype(np.float32)
+        want = oracle.nms(dets, thr)
+        keep = ops.nms(dev(dets), thr).cpu().numpy()
+        np.testing.assert_array_equal(keep, want)
+        assert np.all(np.diff(keep) > 0)
+        np.testing.assert_array_equal(ops.nms(dev(dets[keep]), thr).cpu().numpy(), np.arange(len(keep)))
+        if 0.0 < thr < 1.0:
+            # copies of survivors' boxes with scores below every existing one: IoU = 1 >= thr with a higher-scoring
+            # survivor, so each is suppressed and nothing else changes
+            extra = dets[keep[: min(5, len(keep))]].copy()
+            extra[:, 4] = dets[:, 4].min() * np.linspace(0.5, 0.1, len(extra)).astype(np.float32)
+            more = np.concatenate([dets, extra]).astype(np.float32)
+            np.testing.assert_array_equal(ops.nms(dev(more), thr).cpu().numpy(), keep)
+    check()
+
+
+def test_roialign_hypothesis_adjoint_and_linearity(ops):
+    """Property tests on random shapes: <RoIAlign(x), g> == <x, RoIAlign^T(g)> and RoIAlign(a x + y) ==
+    a RoIAlign(x) + RoIAlign(y) up to fp32 rounding, for pools / channel counts / level sizes drawn by hypothesis."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(pool=st.sampled_from([1, 2, 7, 14]), C=st.sampled_from([4, 12, 64, 132]), size=st.sampled_from([64, 128, 192]),
+           N=st.integers(1, 60), B=st.integers(1, 3), seed=st.integers(0, 10 ** 6), chl=st.booleans())
+    def check(pool, C, size, N, B, seed, chl):
+        fms = synth.feature_pyramid(B, C, seed, image=size)
+        boxes = synth.random_rois(N, seed + 1, image=float(size), min_size=4, max_size=size * 0.9)
+        ind = np.random.default_rng(seed).integers(0, B, N).astype(np.int32)
+        conv = (lambda a: cl(dev(a))) if chl else dev
+        xs = [conv(f).requires_grad_(True) for f in fms]
+        out = ops.pyramid_roi_align(xs, dev(boxes), dev(ind), pool, (size, size, 3))
+        g = torch.randn_like(out)
+        out.backward(g)
+        lhs = float((out.detach().double() * g.double()).sum())
+        rhs = float(sum((x.detach().double() * x.grad.double()).sum() for x in xs))
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+        ys = [torch.randn_like(x) for x in xs]
+        with torch.no_grad():
+            oy = ops.pyramid_roi_align(ys, dev(boxes), dev(ind), pool, (size, size, 3))
+            oz = ops.pyramid_roi_align([2.5 * x + y for x, y in zip(xs, ys)], dev(boxes), dev(ind), pool, (size, size, 3))
+        assert float((oz - (2.5 * out.detach() + oy)).abs().max()) <= 1e-4 * float(oz.abs().max() + 1.0)
+    check()
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_nms_golden(ops, tag):
     g = golden()
