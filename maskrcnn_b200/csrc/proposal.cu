@@ -4,12 +4,16 @@
 //   fg score -> top pre_nms (the reference full-sorts all 261,888 anchors, :1346) -> decode -> clip
 //   -> NMS(thr) -> first post_nms -> normalise.
 //
-// Three launches per batch, no host synchronisation:
+// Two launches per batch (three with the mask + sweep NMS), no host synchronisation:
 //   1. proposal_select_kernel : one 8-CTA thread-block CLUSTER per image.  Each CTA stages its 1/8 of the
 //      fg-score keys in shared memory ONCE (the only HBM pass over rpn_class), then a 4-pass 8-bit radix
-//      SELECT finds the exact k-th key; per-pass 256-bin histograms are combined across the cluster
-//      through distributed shared memory.  Survivors are compacted, rank 0 bitonic-sorts the <= 8192
-//      winners, gathers their anchors/deltas, decodes (fp64 exp, correctly rounded) and clips.
+//      SELECT finds the exact k-th key; per-pass 256-bin histograms (double-buffered) are combined across the
+//      cluster through distributed shared memory.  Winners are compacted, the CLUSTER bitonic-sorts them
+//      together (each CTA owns 1/8 of the network, remote stages through distributed shared memory), and each
+//      CTA gathers anchors/deltas for its slice of the ranking, decodes (fp64 exp, correctly rounded) and clips.
+//   2'. proposal_lazy_nms_kernel (default, post_nms <= 2048): one 8-CTA cluster per image, 64 boxes at a time
+//      against the survivors found so far, stops at the post_nms-th survivor; emits normalised RoIs + counts.
+//   -- or (mrcnn_set_proposal_nms) --
 //   2. proposal_mask_kernel   : upper-triangular IoU>=thr suppression words, all images in one grid.
 //   3. proposal_sweep_kernel  : one CTA per image: TMA-staged greedy sweep with early exit at post_nms,
 //      emits normalised RoIs (zero padded) + counts.
