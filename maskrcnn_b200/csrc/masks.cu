@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PastePar
 // bilinear resample, np.array, stack, copy back: uint8 [D,nh,nw], not thresholded.
 //   decode_taps_kernel   the taps of every output column and row once per call (they do not depend on the detection):
 //                        {first input position, count} + 22-bit fixed-point weights, in double as Resample.c does;
-//   decode_masks_kernel  CTA = 256 output columns x 32 output rows of one mask: the HORIZONTAL pass of the input rows the
+//   decode_masks_kernel  CTA = 256 output columns x 64 output rows of one mask: the HORIZONTAL pass of the input rows the
 //                        tile's vertical taps reach are staged in shared memory, their HORIZONTAL pass goes into shared memory
 //                        as the 8-bit intermediate Pillow keeps (so the double rounding is Pillow's), the vertical pass
 //                        reads it 16 columns at a time and writes 128-bit
@@ -313,15 +313,18 @@ __global__ void __launch_bounds__(kMaskThreads) full_masks_kernel(const PastePar
 //                        per tile) and the output written once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDecTX = 256;  // output columns per CTA (= threads)
-constexpr int kDecTY = 32;   // output rows per CTA
+constexpr int kDecTY = 64;   // output rows per CTA (32 / 64 / 128 measured 143 / 126 / 122 us on the bench case); halved for
+                             // downscales until the intermediate rows fit in shared memory (DecodeParams::ty)
 
 struct DecodeParams {
     const uint8_t* masks;  // [D,H,W] 'L' pixels, or bool bytes (src_bool: non-zero -> 255)
     int src_bool;
+    int src_vec4;          // rows are 32-bit aligned: W % 4 == 0 and a 4-byte aligned base
     int D, H, W;
     int top, left, ch, cw;  // CenterCrop window
     int nh, nw;             // target size
     int kx, ky;             // weight slots per output column / row
+    int ty;                 // output rows per CTA
     int rmax;               // rows of the shared-memory intermediate
     int cstride;            // row pitch of the staged input bytes
     const int2* xmeta;      // [nw] {lo, n}
@@ -358,29 +361,77 @@ __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams
     uint8_t* s_tmp = s_dec;                               // [rmax][kDecTX]   horizontal pass (Pillow's 8-bit intermediate)
     uint8_t* s_src = s_dec + (size_t)p.rmax * kDecTX;     // [rmax][cstride]  the input bytes under the tile
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kDecTX, y0 = blockIdx.y * kDecTY, d = blockIdx.z;
-    const int y1 = min(y0 + kDecTY, p.nh);
+    const int x0 = blockIdx.x * kDecTX, y0 = blockIdx.y * p.ty, d = blockIdx.z;
+    const int y1 = min(y0 + p.ty, p.nh);
     // input rows / columns (window coordinates) the tile's taps reach: lo and lo + n are non-decreasing along an axis
     const int2 mfirst = __ldg(p.ymeta + y0), mlast = __ldg(p.ymeta + (y1 - 1));
     const int r0 = mfirst.x, r1 = mlast.x + mlast.y;
     const int x_last = min(x0 + kDecTX, p.nw) - 1;
     const int2 cx0 = __ldg(p.xmeta + x0), cx1 = __ldg(p.xmeta + x_last);
     const int c0 = cx0.x, c1 = cx1.x + cx1.y;
-    const uint8_t* src = p.masks + ((size_t)d * p.H + p.top) * p.W + p.left;
+    const uint8_t* rows = p.masks + ((size_t)d * p.H + p.top) * p.W;  // window row r, absolute column a: rows[r * W + a]
     uint8_t* out = p.out + (size_t)d * p.nh * p.nw;
+    // staged columns [s0, s1) in absolute coordinates: the tap range [a0, a1), widened to whole 32-bit words when the rows
+    // are word-aligned (W % 4 == 0), so that the staging loop moves four pixels per instruction
+    const int a0 = p.left + c0, a1 = p.left + c1;
+    const int s0 = p.src_vec4 ? (a0 & ~3) : a0;
     {   // stage the input bytes (coalesced), and probe them: a mask is two flat regions and an edge, and if every byte under
         // the tile's taps is the same value v both passes return v - the tile is a constant fill
-        int v0 = __ldg(src + (size_t)r0 * p.W + c0);
+        int v0 = __ldg(rows + (size_t)r0 * p.W + a0);
         if (p.src_bool) v0 = v0 ? 255 : 0;
-        int differs = 0;
-        for (int r = r0 + (tid >> 5); r < r1; r += kDecTX / 32) {
-            const uint8_t* q = src + (size_t)r * p.W;
-            uint8_t* sq = s_src + (r - r0) * p.cstride - c0;
-            for (int c = c0 + (tid & 31); c < c1; c += 32) {
-                int v = __ldg(q + c);
-                if (p.src_bool) v = v ? 255 : 0;
-                sq[c] = (uint8_t)v;
-                differs |= v ^ v0;
+        unsigned differs = 0;
+        if (p.src_vec4) {
+            const int nwords = (((a1 + 3) & ~3) - s0) >> 2;
+            const unsigned v0w = (unsigned)v0 * 0x01010101u;
+            auto consume = [&](unsigned w, int r, int wi) {
+                if (p.src_bool) w = __vcmpne4(w, 0u);  // per byte: non-zero -> 0xff
+                reinterpret_cast<unsigned*>(s_src + (r - r0) * p.cstride)[wi] = w;
+                unsigned diff = w ^ v0w;
+                const int col = s0 + 4 * wi;  // the bytes of this word that lie outside [a0, a1) do not count
+                if (col < a0) diff &= 0xffffffffu << (8 * (a0 - col));
+                if (col + 4 > a1) diff &= 0xffffffffu >> (8 * (col + 4 - a1));
+                differs |= diff;
+            };
+            constexpr int kRI = 5, kWI = 2;  // rows / words per thread of the register-staged form
+            if (nwords <= 32 * kWI && r1 - r0 <= (kDecTX / 32) * kRI) {
+                // every load of the thread is issued before the first one is used (a warp stalls at the first use of a
+                // load: the plain loop below keeps ONE load in flight per warp and the tile pays DRAM latency per row)
+                unsigned w[kRI][kWI];
+#pragma unroll
+                for (int i = 0; i < kRI; ++i) {
+                    const int r = r0 + (tid >> 5) + (kDecTX / 32) * i;
+                    const unsigned* q = reinterpret_cast<const unsigned*>(rows + (size_t)min(r, r1 - 1) * p.W + s0);
+#pragma unroll
+                    for (int j = 0; j < kWI; ++j) {
+                        const int wi = (tid & 31) + 32 * j;
+                        w[i][j] = __ldg(q + min(wi, nwords - 1));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kRI; ++i) {
+                    const int r = r0 + (tid >> 5) + (kDecTX / 32) * i;
+#pragma unroll
+                    for (int j = 0; j < kWI; ++j) {
+                        const int wi = (tid & 31) + 32 * j;
+                        if (r < r1 && wi < nwords) consume(w[i][j], r, wi);
+                    }
+                }
+            } else {
+                for (int r = r0 + (tid >> 5); r < r1; r += kDecTX / 32) {
+                    const unsigned* q = reinterpret_cast<const unsigned*>(rows + (size_t)r * p.W + s0);
+                    for (int wi = tid & 31; wi < nwords; wi += 32) consume(__ldg(q + wi), r, wi);
+                }
+            }
+        } else {
+            for (int r = r0 + (tid >> 5); r < r1; r += kDecTX / 32) {
+                const uint8_t* q = rows + (size_t)r * p.W;
+                uint8_t* sq = s_src + (r - r0) * p.cstride - s0;
+                for (int a = a0 + (tid & 31); a < a1; a += 32) {
+                    int v = __ldg(q + a);
+                    if (p.src_bool) v = v ? 255 : 0;
+                    sq[a] = (uint8_t)v;
+                    differs |= (unsigned)(v ^ v0);
+                }
             }
         }
         if (!__syncthreads_or(differs)) {
@@ -403,7 +454,7 @@ __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams
         if (x < p.nw) {
             const int2 m = __ldg(p.xmeta + x);
             const int* w = p.xw + (size_t)x * p.kx;
-            const uint8_t* s = s_src + (m.x - c0);
+            const uint8_t* s = s_src + (p.left + m.x - s0);
             if (m.y <= 3) {
                 const unsigned k0 = (unsigned)__ldg(w) << 2, k1 = m.y > 1 ? (unsigned)__ldg(w + 1) << 2 : 0u,
                                k2 = m.y > 2 ? (unsigned)__ldg(w + 2) << 2 : 0u;
@@ -466,7 +517,7 @@ __global__ void __launch_bounds__(kDecTX) decode_masks_kernel(const DecodeParams
 
 struct DecodeLayout {
     size_t xmeta_off, xw_off, ymeta_off, yw_off, bytes;
-    int kx, ky, rmax, cstride;
+    int kx, ky, ty, rmax, cstride;
 };
 
 // Resample.c: ksize = (int)ceil(support) * 2 + 1 with support = max(in / out, 1) for the triangle filter
@@ -490,11 +541,16 @@ static DecodeLayout decode_layout(int ch, int cw, int nh, int nw) {
     l.ymeta_off = take((size_t)nh * sizeof(int2));
     l.yw_off = take((size_t)nh * l.ky * sizeof(int));
     l.bytes = off;
-    // input rows under kDecTY output rows: the centres span (kDecTY - 1) * scale, the taps reach `support` either side
+    // input rows under ty output rows: the centres span (ty - 1) * scale, the taps reach `support` either side
     const double sy = (double)ch / (double)nh;
-    l.rmax = (int)ceil((kDecTY - 1) * sy) + l.ky + 2;
     const double sx = (double)cw / (double)nw;
-    l.cstride = (((int)ceil((kDecTX - 1) * sx) + l.kx + 2) + 15) / 16 * 16;
+    l.cstride = (((int)ceil((kDecTX - 1) * sx) + l.kx + 2 + 8) + 15) / 16 * 16;  // + 8: widening to whole words
+    l.ty = kDecTY;
+    for (;;) {
+        l.rmax = (int)ceil((l.ty - 1) * sy) + l.ky + 2;
+        if ((size_t)l.rmax * (kDecTX + l.cstride) <= 96 * 1024 || l.ty <= 4) break;
+        l.ty >>= 1;
+    }
     return l;
 }
 
@@ -570,10 +626,11 @@ int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int 
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     DecodeParams p;
     p.masks = masks; p.src_bool = src_is_bool ? 1 : 0;
+    p.src_vec4 = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(masks) & 3u) == 0) ? 1 : 0;
     p.D = D; p.H = H; p.W = W;
     p.top = top; p.left = left; p.ch = crop_h; p.cw = crop_w;
     p.nh = out_h; p.nw = out_w;
-    p.kx = l.kx; p.ky = l.ky; p.rmax = l.rmax; p.cstride = l.cstride;
+    p.kx = l.kx; p.ky = l.ky; p.ty = l.ty; p.rmax = l.rmax; p.cstride = l.cstride;
     p.xmeta = reinterpret_cast<const int2*>(ws + l.xmeta_off);
     p.xw = reinterpret_cast<const int*>(ws + l.xw_off);
     p.ymeta = reinterpret_cast<const int2*>(ws + l.ymeta_off);
@@ -584,7 +641,7 @@ int mrcnn_decode_masks(const uint8_t* masks, int src_is_bool, int D, int H, int 
                                                                     reinterpret_cast<int2*>(ws + l.ymeta_off),
                                                                     reinterpret_cast<int*>(ws + l.yw_off));
     MRCNN_LAUNCH_CHECK();
-    const dim3 grid((out_w + kDecTX - 1) / kDecTX, (out_h + kDecTY - 1) / kDecTY, D);
+    const dim3 grid((out_w + kDecTX - 1) / kDecTX, (out_h + l.ty - 1) / l.ty, D);
     MRCNN_REQUIRE(grid.y <= 65535, "mrcnn_decode_masks: target too tall");
     const bool vec = (out_w % 16 == 0) && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     if (vec) {
