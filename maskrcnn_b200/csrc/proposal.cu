@@ -124,10 +124,25 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
 
     if (p.staged) {
         if (p.sstride == 2) {
+            // eight loads in flight per thread (a warp stalls at the first use of a load; the scores come from DRAM)
             const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
-            for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(s2 + i).y);
+            for (int i0 = tid; i0 < n_local; i0 += 8 * kSelThreads) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(s2 + min(i0 + u * kSelThreads, n_local - 1)).y;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * kSelThreads < n_local) keys[i0 + u * kSelThreads] = float_to_key(v[u]);
+            }
         } else {  // fg-only scores (mrcnn_rpn_pack's fg_out): half the bytes of the only HBM pass over the scores
-            for (int i = tid; i < n_local; i += kSelThreads) keys[i] = float_to_key(__ldg(scores + i));
+            for (int i0 = tid; i0 < n_local; i0 += 8 * kSelThreads) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(scores + min(i0 + u * kSelThreads, n_local - 1));
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * kSelThreads < n_local) keys[i0 + u * kSelThreads] = float_to_key(v[u]);
+            }
         }
     }
     if (tid == 0) sh.gt_local = 0;
