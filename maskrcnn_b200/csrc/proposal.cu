@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(1024) proposal_sweep_kernel(const uint64_t* __
 //   pull     the chunk's 64 boxes against the S survivors found so far: 64 columns x 128 survivor slices spread over the
 //            8 CTAs of the cluster (a column stops at its first hit); each CTA sends its 64 hit bits to every peer through
 //            distributed shared memory, one cluster barrier per chunk;
-//   diagonal the 64 x 64 tile of the chunk itself (4 tests per thread, words combined with shuffles), in every CTA;
+//   diagonal the 64 x 64 tile of the chunk itself, one eighth (8 interleaved columns) per CTA, sent along with the hit bits;
 //   resolve  warp 0 of every CTA walks the candidates (one dependent step per survivor) and appends the survivors' boxes
 //            to ITS copy of the survivor list (replicated state, no second exchange); rank 0 writes the normalised rows.
 // The loop ends as soon as `post` survivors exist.  Same IoU decision (iou_ge_m), same greedy order as the mask + sweep
@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
     __shared__ float4 s_cbox[64];
     __shared__ float s_carea[64];
     __shared__ int s_hit[64];
-    __shared__ uint64_t s_d[64];
+    __shared__ uint64_t s_d[2][64];               // column i: the rows j < i of the chunk that suppress box i (double-buffered)
+    __shared__ uint32_t s_dpart[8][2];            // this CTA's eight columns of the tile, two 32-row halves each
     __shared__ uint64_t s_peer[2][kLazyCluster];  // hit words of the 8 CTAs, double-buffered by chunk parity
     __shared__ uint64_t s_bar[2];                 // mbarriers: 8 arrivals (one per CTA of the cluster) per chunk
     __shared__ int s_S;
@@ -547,33 +548,29 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
                 }
             }
         }
-        {   // diagonal tile, by COLUMN: word i = the rows j < i of the chunk that suppress box i.  Thread = (column i, rows
-            // 4q .. 4q + 3); the 16 lanes of a column are contiguous in a warp and OR their nibbles with shuffles.
-            const int i = tid >> 4, q = tid & 15;
-            const float4 cb = s_cbox[i];
-            const float ca = s_carea[i];
-            uint32_t nib = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int row = 4 * q + k;
-                if (row < i && i < ncols && iou_ge_m(s_cbox[row], s_carea[row], cb, ca, thr, margin)) nib |= 1u << k;
-            }
-            uint32_t lo = q < 8 ? nib << (4 * q) : 0u, hi = q >= 8 ? nib << (4 * (q - 8)) : 0u;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                lo |= __shfl_xor_sync(0xffffffffu, lo, o);
-                hi |= __shfl_xor_sync(0xffffffffu, hi, o);
-            }
-            if (q == 0) s_d[i] = ((uint64_t)hi << 32) | lo;
+        if (tid < 512) {
+            // diagonal tile, split over the cluster: this CTA computes the columns i = 8 k + rank (k = 0..7; interleaved, so
+            // every CTA gets the same share of the triangle), one (column, row) test per thread, a ballot per 32 rows.  The
+            // eight words travel with the hit word below.  (Every CTA computing the whole 64 x 64 tile was ~1.3 us of the
+            // ~4.3 us a chunk takes.)
+            const int k = tid >> 6, row = tid & 63;
+            const int i = 8 * k + rank;
+            const bool sup = row < i && i < ncols && iou_ge_m(s_cbox[row], s_carea[row], s_cbox[i], s_carea[i], thr, margin);
+            const uint32_t bits = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0) s_dpart[k][(tid >> 5) & 1] = bits;
         }
-        __syncthreads();  // s_hit, s_d
+        __syncthreads();  // s_hit, s_dpart
         if (tid < 32) {
             // this CTA's 64 hit bits go to every CTA of the cluster (its own copy included): one 8-byte store into the
             // peer's shared memory + one arrive on the peer's mbarrier per lane; then wait for the 8 words sent to us
             const uint32_t h_lo = __ballot_sync(0xffffffffu, s_hit[lane] != 0);
             const uint32_t h_hi = __ballot_sync(0xffffffffu, s_hit[lane + 32] != 0);
-            if (lane < kLazyCluster) {
+            if (lane < kLazyCluster) {  // lane p serves peer p: nine 8-byte stores, then one arrive (release) on its mbarrier
                 st_cluster_u64(mapa_u32(smem_u32(&s_peer[c & 1][rank]), (uint32_t)lane), ((uint64_t)h_hi << 32) | h_lo);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    st_cluster_u64(mapa_u32(smem_u32(&s_d[c & 1][8 * k + rank]), (uint32_t)lane),
+                                   ((uint64_t)s_dpart[k][1] << 32) | s_dpart[k][0]);
                 mbar_arrive_remote(mapa_u32(smem_u32(&s_bar[c & 1]), (uint32_t)lane));
             }
             mbar_wait_cluster(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
@@ -586,7 +583,7 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
             for (int k = 0; k < kLazyCluster; ++k) hits |= s_peer[c & 1][k];
             uint64_t cand = ~hits;
             if (ncols < 64) cand &= (1ull << ncols) - 1ull;
-            const uint64_t col_lo = s_d[lane], col_hi = s_d[lane + 32];  // bits are rows below the column by construction
+            const uint64_t col_lo = s_d[c & 1][lane], col_hi = s_d[c & 1][lane + 32];  // bits are rows below the column by construction
             const bool c_lo = (cand >> lane) & 1ull, c_hi = (cand >> (lane + 32)) & 1ull;
             uint64_t alive = cand;
             for (;;) {
