@@ -123,25 +123,32 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
     auto key_at = [&](int i) -> uint32_t { return p.staged ? keys[i] : float_to_key(__ldg(scores + (size_t)i * p.sstride)); };
 
     if (p.staged) {
-        if (p.sstride == 2) {
-            // eight loads in flight per thread (a warp stalls at the first use of a load; the scores come from DRAM)
-            const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
-            for (int i0 = tid; i0 < n_local; i0 += 8 * kSelThreads) {
-                float v[8];
+        // One pass over the scores: eight loads in flight per thread (a warp stalls at the first use of a load; the scores
+        // come from DRAM), keys into shared memory, and the histogram of the FIRST radix pass on the way (the top byte of
+        // a score is sign + 7 exponent bits - a handful of distinct digits per warp - so one shared-memory atomic per
+        // distinct digit: match_any costs one round per distinct value).
+        for (int i = tid; i < 256; i += kSelThreads) sh.hist[0][i] = 0;
+        __syncthreads();
+        const float2* s2 = reinterpret_cast<const float2*>(p.rpn_class + ((size_t)img * p.A + lo) * 2);
+        for (int b0 = 0; b0 < n_local; b0 += 8 * kSelThreads) {  // warp-uniform bounds: the ballots below need every lane
+            float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(s2 + min(i0 + u * kSelThreads, n_local - 1)).y;
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (i0 + u * kSelThreads < n_local) keys[i0 + u * kSelThreads] = float_to_key(v[u]);
+            for (int u = 0; u < 8; ++u) {
+                const int i = min(b0 + u * kSelThreads + tid, n_local - 1);
+                v[u] = (p.sstride == 2) ? __ldg(s2 + i).y : __ldg(scores + i);  // fg-only scores: half the bytes
             }
-        } else {  // fg-only scores (mrcnn_rpn_pack's fg_out): half the bytes of the only HBM pass over the scores
-            for (int i0 = tid; i0 < n_local; i0 += 8 * kSelThreads) {
-                float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(scores + min(i0 + u * kSelThreads, n_local - 1));
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (i0 + u * kSelThreads < n_local) keys[i0 + u * kSelThreads] = float_to_key(v[u]);
+            for (int u = 0; u < 8; ++u) {
+                const int i = b0 + u * kSelThreads + tid;
+                const bool ok = i < n_local;
+                const uint32_t key = float_to_key(v[u]);
+                if (ok) keys[i] = key;
+                const unsigned act = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const unsigned digit = key >> 24;
+                    const unsigned peers = __match_any_sync(act, digit);
+                    if (lane == (__ffs(peers) - 1)) atomicAdd(&sh.hist[0][digit], __popc(peers));
+                }
             }
         }
     }
@@ -154,12 +161,16 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         int* hist = sh.hist[pass & 1];
-        for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
-        __syncthreads();
+        if (!(p.staged && pass == 0)) {  // the staged first pass was histogrammed while the keys were loaded
+            for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+            __syncthreads();
+        }
         // 32 warps share one SM here, so these sweeps are issue-bound: the staged (shared-memory keys) form keeps the loop
         // body to a load, a shift / compare and the histogram update (the general form below measured ~430 cycles per
         // 1024-key iteration, ~50 instructions per warp)
-        if (p.staged && pass > 0) {
+        if (p.staged && pass == 0) {
+            // done above
+        } else if (p.staged) {
             const int up = shift + 8;
 #pragma unroll 4
             for (int i = tid; i < n_local; i += kSelThreads) {
