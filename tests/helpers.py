@@ -82,3 +82,60 @@ def golden_decode(tag):
     d, h, w, y1, x1, y2, x2 = (int(v) for v in g[f"{tag}_in_geom"])
     m = np.unpackbits(g[f"{tag}_in_bits"])[:d * h * w].reshape(d, h, w).astype(bool)
     return m, float(g[f"{tag}_in_scale"]), (y2 - y1, x2 - x1), g[f"{tag}_out"]
+
+
+def check_detect_flow_with_oracle(g):
+    """Replays a recorded predict.py flow (tests/golden/make_golden_detect.py) stage by stage with the oracle on the
+    reference's own tensors; returns the number of detections whose masks the reference produced."""
+    import hashlib
+    import pytest
+    import oracle
+    from maskrcnn_b200 import synth
+    size = int(g["image_dim"])
+    keys = g.files if hasattr(g, "files") else list(g)
+    nl = sum(1 for k in keys if k.startswith("rpn_in_logits_"))
+    # rpn_detect (model.py:1294-1304)
+    logits, cls, bbox = oracle.rpn_pack([g[f"rpn_in_logits_{l}"] for l in range(nl)], [g[f"rpn_in_bbox_{l}"] for l in range(nl)])
+    assert hashlib.sha256(logits.tobytes() + bbox.tobytes()).digest() == g["rpn_out_logits_bbox_sha256"].tobytes()
+    assert np.abs(cls - g["rpn_out_class"]).max() <= SOFTMAX_TOL
+    # rpn_refine (model.py:1307-1382).  The flow's own rpn_class has thousands of anchors tied at fg = 1.0 (saturated
+    # random-init softmax), where the reference's result is decided by torch's unstable sort; the recording holds a second
+    # reference run with the ties broken in the order that sort chose (make_golden_detect.py)
+    np.testing.assert_array_equal(synth.pyramid_anchors((size, size)), g["prop_in_anchors"])
+    pre, post = (int(v) for v in g["prop_in_limits"])
+    fg = g["prop_in_fg_detied"]
+    rois = oracle.proposal_layer(np.stack([1.0 - fg, fg], 1).astype(np.float32), bbox[0], g["prop_in_anchors"], pre, post,
+                                 float(g["prop_in_thr"]), height=float(size), width=float(size))
+    assert rois.shape == g["prop_out_rois_detied"][0].shape
+    assert ulp_diff(rois, g["prop_out_rois_detied"][0]).max() <= 4     # torch.exp's rounding (SURVEY §7)
+    # roi_align 7x7 and 14x14 (model.py:276-393)
+    fms = [g[f"fm_{l}"] for l in range(4)]
+    for pool in (7, 14):
+        out, _ = oracle.pyramid_roi_align_fwd(fms, g[f"pool{pool}_in_rois"][0], None, pool, float(size * size))
+        np.testing.assert_array_equal(out, g[f"pool{pool}_out"])
+    # mrn_refine (model.py:1389-1487)
+    det = oracle.detection_layer(g["prop_out_rois"][0], g["det_in_probs"], g["det_in_deltas"], g["det_in_window"],
+                                 float(g["det_in_min_conf"]), float(g["det_in_thr"]), int(g["det_in_limits"][0]),
+                                 height=float(size), width=float(size))
+    np.testing.assert_array_equal(det[:, :4], g["det_out_boxes"][0])
+    np.testing.assert_array_equal(det[:, 4], g["det_out_scores"][0])
+    np.testing.assert_array_equal(det[:, 5].astype(np.int64), g["det_out_class_ids"][0])
+    np.testing.assert_array_equal(g["pool14_in_rois"][0], g["det_out_boxes"][0] / np.float32(size))   # model.py:1188
+    # full_masks (data.py:287-314).  Random-init heads give some detections an empty (rounded, window-clipped) box, on
+    # which the reference raises from PIL - and so does the oracle; the recording holds the reference's masks of the others
+    d = len(det)
+    h, w = (int(v) for v in g["mask_in_hw"])
+    want, ok = detect_flow_expected_masks(g), g["mask_valid"]
+    sel = np.ascontiguousarray(g["mask_in_sel"][:, None])
+    if not ok.all():
+        with pytest.raises(ValueError):
+            oracle.full_masks(np.zeros(d, np.int64), g["det_out_boxes"][0], sel, h, w)
+    got = oracle.full_masks(np.zeros(int(ok.sum()), np.int64), g["det_out_boxes"][0][ok], sel[ok], h, w)
+    np.testing.assert_array_equal(got, want[ok])
+    assert not want[~ok].any()
+    # decode_masks (data.py:265-284) back to the original frame
+    y1, x1, y2, x2 = (int(v) for v in g["det_in_window"])
+    dec = oracle.decode_masks(want[ok], float(g["decode_in_scale"]), (y2 - y1, x2 - x1))
+    assert dec.shape[1:] == tuple(int(v) for v in g["decode_out_hw"])
+    assert hashlib.sha256(dec.tobytes()).digest() == g["decode_out_sha256"].tobytes()
+    return int(ok.sum())

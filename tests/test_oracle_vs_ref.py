@@ -2,6 +2,8 @@
 the reference's compiled CPU extension (oracle/_ref, built unmodified from /root/reference) and the
 reference's unmodified model.py.  Skipped where the reference is absent (the GPU box); the same
 comparisons are frozen as golden vectors in tests/golden/ (tests/test_oracle_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -337,3 +339,17 @@ def test_rpn_pack_matches_model_py():
     np.testing.assert_array_equal(got[0], want[0])
     np.testing.assert_array_equal(got[2], want[2])
     assert np.abs(got[1] - want[1]).max() <= 1e-6   # torch's CPU softmax: approximate vectorised exp
+
+
+@needs_model
+@pytest.mark.parametrize("image_name,dim,seed", [("girl.jpg", 192, 7), ("messi.jpg", 320, 11)])
+def test_detect_flow_live(image_name, dim, seed):
+    """The reference's whole predict.py flow executed HERE on other images / frame sizes / seeds than the committed
+    fixture (tests/golden/make_golden_detect.py records it at every replaced operator's boundary), replayed stage by
+    stage with the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_detect
+    from helpers import check_detect_flow_with_oracle
+    g = make_golden_detect.run(seed, image_name=image_name, image_dim=dim, save=False)
+    assert check_detect_flow_with_oracle(g) >= 1
