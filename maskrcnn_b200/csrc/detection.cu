@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const D
 
     // shared-memory carve-up
     unsigned char* ptr = smem_raw;
-    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(ptr);  ptr += (size_t)p.P * 8;
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(ptr);  ptr += (size_t)p.P * (p.P == kDetThreads ? 16 : 8);  // + exchange buffer
     float4* rbox = reinterpret_cast<float4*>(ptr);          ptr += (size_t)N * 16;   // refined box per RoI (input order)
     float4* sbox = reinterpret_cast<float4*>(ptr);          ptr += (size_t)N * 16;   // boxes in score order
     float* sarea = reinterpret_cast<float*>(ptr);           ptr += (size_t)N * 4;
@@ -165,7 +165,16 @@ __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const D
     const int M = s_count;  // RoIs entering NMS
 
     // ---- C. sort by score (descending; ties -> lower RoI index) and gather ----
-    block_bitonic_desc(sortbuf, p.P, 0u, 2u, 1u, (unsigned)p.P);
+    if (p.P == kDetThreads) {  // up to 1024 RoIs: one key per thread, register / shuffle network
+        const uint64_t mine = sortbuf[tid];
+        __syncthreads();  // every key is in a register before sortbuf is reused as the exchange buffer
+        const uint64_t sorted = block_bitonic_desc_1024_reg(mine, sortbuf);
+        __syncthreads();  // the last exchange stage has been read
+        sortbuf[tid] = sorted;
+        __syncthreads();
+    } else {
+        block_bitonic_desc(sortbuf, p.P, 0u, 2u, 1u, (unsigned)p.P);
+    }
     for (int i = tid; i < M; i += kDetThreads) {
         const int n = (int)sort_key_index(sortbuf[i]);
         const float4 b = rbox[n];
@@ -331,7 +340,7 @@ __global__ void detection_empty_kernel(float* dets, size_t n, int32_t* counts, i
 static int g_detection_nms_algo = MRCNN_PROPOSAL_NMS_AUTO;
 
 static size_t det_smem_bytes(int N, int P, int W, bool mask_in_smem) {
-    size_t b = (size_t)P * 8 + (size_t)N * (16 + 16 + 4 + 4 + 4 + 4) + (size_t)W * 16;
+    size_t b = (size_t)P * (P == kDetThreads ? 16 : 8) + (size_t)N * (16 + 16 + 4 + 4 + 4 + 4) + (size_t)W * 16;
     if (mask_in_smem) b += (size_t)(W * 64) * W * 8;
     return align_up(b, 16);
 }

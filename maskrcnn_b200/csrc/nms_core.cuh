@@ -42,6 +42,37 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P, unsigned 
     }
 }
 
+// 1024 keys, 1024 threads, ONE key per thread kept in a register: a stage of the network with stride j exchanges with
+// lane ^ j by shuffle when j < 32 (no barrier: 40 of the 55 stages) and through a double-buffered shared-memory array
+// otherwise (one __syncthreads per stage).  Fully unrolled, so k and j are constants and a shuffle stage is ~10
+// instructions: with 32 warps on one SM the sort is issue-bound (the rolled shared-memory form above costs ~380 cycles per
+// stage, this one ~90).  Returns the key of descending rank threadIdx.x.  buf: 2 x 1024 keys of shared memory.
+__device__ __forceinline__ uint64_t block_bitonic_desc_1024_reg(uint64_t v, uint64_t* buf) {
+    const unsigned tid = threadIdx.x;
+    int b = 0;
+#pragma unroll
+    for (int lk = 1; lk <= 10; ++lk) {
+        const unsigned k = 1u << lk;
+        const bool desc = (tid & k) == 0u;
+#pragma unroll
+        for (int lj = lk - 1; lj >= 0; --lj) {
+            const unsigned j = 1u << lj;
+            uint64_t pv;
+            if (j >= 32u) {
+                buf[b * 1024 + tid] = v;
+                __syncthreads();
+                pv = buf[b * 1024 + (tid ^ j)];
+                b ^= 1;
+            } else {
+                pv = __shfl_xor_sync(0xffffffffu, v, (int)j);
+            }
+            const bool want_max = (((tid & j) == 0u) == desc);
+            v = want_max ? (v > pv ? v : pv) : (v < pv ? v : pv);
+        }
+    }
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // suppression word: bit c set iff box (col0 + c) is suppressed by `rowbox` (IoU >= thr) and comes
 // later in the order (col index > row index).  Column boxes/areas are read from shared memory.
