@@ -149,6 +149,14 @@ struct SelectParams {
 // perm[0..n) = stable argsort(keys[0..n)) ascending
 __device__ __forceinline__ void block_argsort_asc(const float* keys, int n, int P2, uint64_t* s, int32_t* perm) {
     const int tid = threadIdx.x;
+    if (P2 == kTgtThreads) {  // up to 1024 proposals: one key per thread, register / shuffle network (s holds 2 x 1024 keys)
+        uint64_t kv = 0ull;
+        if (tid < n) kv = ~(((uint64_t)float_to_key(__ldg(keys + tid)) << 32) | (uint32_t)tid);
+        kv = block_bitonic_desc_1024_reg(kv, s);
+        if (tid < n) perm[tid] = (int32_t)((~kv) & 0xffffffffu);
+        __syncthreads();  // the exchange buffer is reused by the next call
+        return;
+    }
     for (int i = tid; i < P2; i += blockDim.x) {
         // descending sort of ~(key, index) == ascending (key, index); padding sorts last
         uint64_t kv = 0ull;
@@ -309,7 +317,7 @@ int mrcnn_target_select(const int32_t* counts, const float* keys_pos, const floa
     MRCNN_REQUIRE_DEV(perm_neg);
     MRCNN_REQUIRE_DEV(take);
     SelectParams p = {counts, keys_pos, keys_neg, neg_table, B, N, pos_cap, next_pow2(N), perm_pos, perm_neg, take};
-    const size_t smem = (size_t)p.P2 * 8;
+    const size_t smem = (size_t)p.P2 * (p.P2 == kTgtThreads ? 16 : 8);  // + exchange buffer of the register network
     if (smem > 48 * 1024)
         MRCNN_CUDA(cudaFuncSetAttribute(target_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     target_select_kernel<<<B, kTgtThreads, smem, (cudaStream_t)stream>>>(p);
