@@ -172,9 +172,9 @@ MRCNN_API int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox
 
 /* NMS inside the proposal layer (process-wide switch; results are identical):
  *   MRCNN_PROPOSAL_NMS_MASK  batched 64x64 IoU-bitmask tiles (upper triangle) + one single-CTA sweep per image;
- *   MRCNN_PROPOSAL_NMS_LAZY  one CTA per image, boxes taken 64 at a time in score order and compared only with the
- *                            survivors found so far, stopping at the post_nms-th survivor: 64 * sum(survivors so far) IoU
- *                            tests instead of n^2 / 2;
+ *   MRCNN_PROPOSAL_NMS_LAZY  one 8-CTA cluster per image, boxes taken 64 at a time in score order and compared only with
+ *                            the survivors found so far, stopping at the post_nms-th survivor: 64 * sum(survivors so
+ *                            far) IoU tests instead of n^2 / 2; no N x N mask, no workspace traffic;
  *   MRCNN_PROPOSAL_NMS_AUTO  LAZY when post_nms <= 2048, MASK otherwise (default). */
 #define MRCNN_PROPOSAL_NMS_AUTO 0
 #define MRCNN_PROPOSAL_NMS_MASK 1
