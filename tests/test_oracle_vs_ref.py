@@ -86,6 +86,45 @@ def test_crop_fwd_bwd_bit_exact(B, C, H, W, N, ch, cw, ev):
                                   _ref_crop_bwd(g, boxes, ind, img.shape))
 
 
+def test_nms_and_crop_hypothesis_against_the_compiled_reference():
+    """Random sizes / thresholds / boxes drawn by hypothesis: the C restatement against the reference's own compiled
+    nms / crop_forward / crop_backward (oracle/_ref), bit for bit."""
+    from hypothesis import given, settings, strategies as st
+    C = reference.ref_C()
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(n=st.integers(1, 400), seed=st.integers(0, 10 ** 6), thr=st.sampled_from([0.0, 0.05, 0.3, 0.5, 0.7, 0.99, 1.0]),
+           jitter=st.sampled_from([0.0, 0.5, 4.0, 40.0]), integer=st.booleans())
+    def check_nms(n, seed, thr, jitter, integer):
+        rng = np.random.default_rng(seed)
+        b = _boxes_px(n, seed, size=256.0)
+        if n > 1:
+            h = n // 2
+            b[h:] = b[: n - h] + rng.uniform(-jitter, jitter, (n - h, 4)).astype(np.float32)
+        if integer:
+            b = np.round(b)       # rounded pixel boxes as the detection layer emits: exact-threshold IoUs become likely
+        dets = np.concatenate([b, synth.unique_scores(n, seed + 1)[:, None]], 1).astype(np.float32)
+        np.testing.assert_array_equal(oracle.nms(dets, thr), C.nms(torch.from_numpy(dets), thr).numpy())
+    check_nms()
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(B=st.integers(1, 3), Cc=st.integers(1, 5), H=st.integers(1, 40), W=st.integers(1, 40), N=st.integers(1, 12),
+           ch=st.integers(1, 15), cw=st.integers(1, 15), ev=st.sampled_from([0.0, -1.5, 3.0]), seed=st.integers(0, 10 ** 6))
+    def check_crop(B, Cc, H, W, N, ch, cw, ev, seed):
+        rng = np.random.default_rng(seed)
+        img = rng.standard_normal((B, Cc, H, W), dtype=np.float32)
+        boxes = rng.uniform(-0.3, 1.3, (N, 4)).astype(np.float32)          # inverted, outside, degenerate: everything goes
+        if N > 2:
+            boxes[0] = [0.0, 0.0, 1.0, 1.0]
+            boxes[1, 2:] = boxes[1, :2]
+        ind = rng.integers(0, B, N).astype(np.int32)
+        want = _ref_crop_fwd(img, boxes, ind, ch, cw, ev)
+        np.testing.assert_array_equal(oracle.crop_forward(img, boxes, ind, ch, cw, ev), want)
+        g = rng.standard_normal(want.shape, dtype=np.float32)
+        np.testing.assert_array_equal(oracle.crop_backward(g, boxes, ind, img.shape), _ref_crop_bwd(g, boxes, ind, img.shape))
+    check_crop()
+
+
 def test_crop_bad_box_index():
     img = np.zeros((1, 1, 4, 4), np.float32)
     with pytest.raises(oracle.OracleError):
@@ -326,6 +365,46 @@ def test_decode_masks_scale_one_is_identity():
     t = torch.from_numpy(m)
     assert d.decode_masks(t, 1, d.Box.fromlist([0, 0, 32, 32])) is t
     assert oracle.decode_masks(m, 1, (32, 32)) is m
+
+
+@needs_model
+def test_masks_hypothesis_against_data_py():
+    """Random geometry drawn by hypothesis through the reference's PIL / torchvision route (data.full_masks,
+    data.decode_masks executed here) against the oracle's restatement of Pillow's resample: bit for bit."""
+    from hypothesis import given, settings, strategies as st
+    d = reference.load().data
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(H=st.integers(8, 96), W=st.integers(8, 96), mh=st.sampled_from([7, 14, 28]), seed=st.integers(0, 10 ** 6),
+           n=st.integers(1, 6))
+    def check_paste(H, W, mh, seed, n):
+        rng = np.random.default_rng(seed)
+        y1 = rng.integers(-4, H - 1, n)
+        x1 = rng.integers(-4, W - 1, n)
+        boxes = np.stack([y1, x1, y1 + rng.integers(1, H + 6, n), x1 + rng.integers(1, W + 6, n)], 1).astype(np.float32)
+        boxes += rng.choice(np.float32([0.0, 0.0, 0.25, 0.5]), (n, 4))           # rounded boxes mostly, some fractional
+        boxes[:, 2:] = np.maximum(boxes[:, 2:], boxes[:, :2] + 1.0)
+        cls = rng.integers(0, 3, n).astype(np.int64)
+        masks = rng.uniform(-0.2, 1.2, (n, 3, mh, mh)).astype(np.float32)
+        want = d.full_masks(torch.from_numpy(cls), torch.from_numpy(boxes), torch.from_numpy(masks), H, W).numpy()
+        np.testing.assert_array_equal(oracle.full_masks(cls, boxes, masks, H, W), want)
+    check_paste()
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(H=st.integers(4, 80), W=st.integers(4, 80), seed=st.integers(0, 10 ** 6),
+           scale=st.sampled_from([0.2, 0.3333, 0.5, 0.53333336, 0.77, 0.999, 1.25, 1.7, 2.0, 3.1]))
+    def check_decode(H, W, seed, scale):
+        rng = np.random.default_rng(seed)
+        m = rng.random((2, H, W)) < rng.uniform(0.1, 0.9)
+        m[0, H // 4:H // 2 + 1, W // 4:W // 2 + 1] = True
+        ch, cw = int(rng.integers(1, H + 1)), int(rng.integers(1, W + 1))
+        y0, x0 = (H - ch) // 2, (W - cw) // 2
+        box = d.Box.fromlist([y0, x0, y0 + ch, x0 + cw])
+        if round(ch * 1.0 / scale) < 1 or round(cw * 1.0 / scale) < 1:
+            return                                                              # PIL raises; covered by the edge-case tests
+        want = d.decode_masks(torch.from_numpy(m), scale, box).numpy()
+        np.testing.assert_array_equal(oracle.decode_masks(m, scale, (ch, cw)), want)
+    check_decode()
 
 
 @needs_model
