@@ -458,6 +458,8 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
+    if os.environ.get("MRCNN_BENCH_REF_PROCS"):        # tests: a small arm (the JSON says how many processes ran)
+        procs = max(1, min(procs, int(os.environ["MRCNN_BENCH_REF_PROCS"])))
     per_step_images = procs                       # one image per worker per step
     arm = CpuArm(procs)                           # spawns, imports, synthesizes inputs and warms up: untimed
     for _ in range(max(0, min(args.warmup, 2) - 1)):

@@ -1,0 +1,44 @@
+"""bench.py's reference arm runs without a GPU: its JSON line must carry the contract's keys (the own arm's line is
+checked on the GPU box by the driver; its keys are asserted here against a recorded line in profiles/)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def test_reference_arm_line():
+    env = dict(os.environ, MRCNN_BENCH_REF_PROCS="2", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must be exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["metric"] == "roialign_train_rois_per_s" and d["unit"] == "RoIs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] == 0 and "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 2 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_recorded_own_arm_line_has_the_contract_keys():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
+    assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline"} <= set(d)
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32" and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
