@@ -220,6 +220,23 @@ class CropFunction(object):
 # ------------------------------------------------------------------------------------------------
 # PyramidROIAlign
 # ------------------------------------------------------------------------------------------------
+def _check_pyramid_args(feature_maps, boxes, box_ind):
+    """Shapes the kernels rely on without being able to see them: one (B, C) for the four levels, one index per box."""
+    if len(feature_maps) != 4:
+        raise ValueError("expected the four pyramid levels P2..P5")
+    for i, f in enumerate(feature_maps):
+        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
+        if f.dim() != 4 or f.shape[:2] != feature_maps[0].shape[:2] or f.device != feature_maps[0].device:
+            raise ValueError("feature_maps must be four [B,C,H_l,W_l] tensors with the same B and C on one device")
+    _require_cuda(boxes, "boxes", torch.float32)
+    if boxes.dim() != 2 or boxes.size(1) != 4:
+        raise ValueError("boxes must be [N,4]")
+    if box_ind is not None:
+        _require_cuda(box_ind, "box_ind", torch.int32)
+        if box_ind.dim() != 1 or box_ind.size(0) != boxes.size(0):
+            raise ValueError("box_ind must be int32 [N], one image index per box")
+
+
 def _pyramid_layout(fms):
     if len(fms) != 4:
         raise ValueError("expected the four pyramid levels P2..P5")
@@ -304,14 +321,10 @@ def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_
     memory format follows the feature maps unless out_channels_last is given.
     rois_per_image: optional host-side list of B counts (or one int) stating that boxes are grouped by image in
     order (box_ind, if given, must agree); lets the backward clear + scatter image by image (L2-resident)."""
-    for i, f in enumerate(feature_maps):
-        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
-    _require_cuda(boxes, "boxes", torch.float32)
-    if boxes.dim() != 2 or boxes.size(1) != 4:
-        raise ValueError("boxes must be [N,4]")
+    feature_maps = list(feature_maps)
+    _check_pyramid_args(feature_maps, boxes, box_ind)
     boxes = boxes.detach().contiguous()
     if box_ind is not None:
-        _require_cuda(box_ind, "box_ind", torch.int32)
         box_ind = box_ind.contiguous()
     image_area = float(image_shape[0] * image_shape[1])  # model.py:331
     ol = None if out_channels_last is None else (NHWC if out_channels_last else NCHW)
@@ -555,6 +568,15 @@ def pyramid_roi_align_backward_pair(grad_a, grad_b, feature_shapes, boxes, box_i
     boxes = boxes.contiguous()
     if box_ind is not None:
         box_ind = _require_cuda(box_ind, "box_ind", torch.int32).contiguous()
+        if box_ind.shape != (N,):
+            raise ValueError("box_ind must be int32 [N], one image index per box")
+    if out is not None:
+        if len(out) != 4:
+            raise ValueError("out must hold the four gradient levels")
+        for g, hh, ww in zip(out, Hs, Ws):
+            _require_cuda(g, "out", torch.float32)
+            if g.shape != (B, C, hh, ww) or not g.is_contiguous(memory_format=torch.channels_last):
+                raise ValueError("out[l] must be a channels-last [B,C,H_l,W_l] tensor matching feature_shapes")
     h, w = float(image_shape[0]), float(image_shape[1])
     with torch.cuda.device(grad_a.device):
         gfm = out if out is not None else [_empty4((B, C, hh, ww), NHWC, grad_a) for hh, ww in zip(Hs, Ws)]
@@ -606,14 +628,13 @@ def pyramid_roi_align_pair(feature_maps, boxes, box_ind, pool_sizes, image_shape
     """PyramidROIAlign of the same RoIs at two pool sizes (box head 7x7 + mask head 14x14, model.py:778 / :889) as ONE
     autograd node: returns (crops_a, crops_b), channels-last, and backpropagates both heads with the fused gather
     (one gradient-pyramid write instead of two plus autograd's add).  Channels-last feature maps, N > 0, C % 4 == 0."""
-    for i, f in enumerate(feature_maps):
-        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
-    _require_cuda(boxes, "boxes", torch.float32)
-    if boxes.dim() != 2 or boxes.size(1) != 4 or boxes.size(0) == 0 or len(pool_sizes) != 2:
+    feature_maps = list(feature_maps)
+    _check_pyramid_args(feature_maps, boxes, box_ind)
+    if boxes.size(0) == 0 or len(pool_sizes) != 2:
         raise ValueError("boxes must be [N,4] with N > 0 and pool_sizes a pair")
     boxes = boxes.detach().contiguous()
     if box_ind is not None:
-        box_ind = _require_cuda(box_ind, "box_ind", torch.int32).contiguous()
+        box_ind = box_ind.contiguous()
     image_area = float(image_shape[0] * image_shape[1])
     return _PyramidRoiAlignPair.apply(boxes, box_ind, int(pool_sizes[0]), int(pool_sizes[1]), image_area, *feature_maps)
 

@@ -1091,3 +1091,37 @@ def test_detect_flow_golden_dropins(ops):
     import hashlib as _h
     assert _h.sha256(dec.tobytes()).digest() == g["decode_out_sha256"].tobytes()
     ops.check_device_errors()
+
+
+def test_pyramid_arguments_are_validated(ops):
+    """Shapes the kernels cannot see (one index per box, one (B, C) for the four levels, the preallocated gradient
+    pyramid of the fused backward) are rejected on the host instead of being read out of bounds."""
+    fms = [torch.zeros((2, 8, s, s), device="cuda") for s in (16, 8, 4, 2)]
+    boxes = torch.tensor([[0.1, 0.1, 0.6, 0.6], [0.2, 0.3, 0.9, 0.8], [0.0, 0.0, 1.0, 1.0]], device="cuda")
+    ind = torch.tensor([0, 1, 1], dtype=torch.int32, device="cuda")
+    assert ops.pyramid_roi_align(fms, boxes, ind, 7, (64, 64, 3)).shape == (3, 8, 7, 7)
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align(fms, boxes, ind[:2], 7, (64, 64, 3))                       # an index short
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align(fms, boxes, ind.reshape(3, 1), 7, (64, 64, 3))
+    with pytest.raises(TypeError):
+        ops.pyramid_roi_align(fms, boxes, ind.long(), 7, (64, 64, 3))                    # __init__.py:34-35: int32
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align(fms[:3] + [torch.zeros((2, 4, 2, 2), device="cuda")], boxes, ind, 7, (64, 64, 3))
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align(fms[:3] + [torch.zeros((1, 8, 2, 2), device="cuda")], boxes, ind, 7, (64, 64, 3))
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align(fms[:3], boxes, ind, 7, (64, 64, 3))
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align_pair([cl(f) for f in fms], boxes, ind[:1], (7, 14), (64, 64, 3))
+    g7, g14 = cl(torch.zeros((3, 8, 7, 7), device="cuda")), cl(torch.zeros((3, 8, 14, 14), device="cuda"))
+    shapes = [tuple(f.shape) for f in fms]
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align_backward_pair(g7, g14, shapes, boxes, ind[:2], (64, 64, 3))
+    with pytest.raises(ValueError):
+        ops.pyramid_roi_align_backward_pair(g7, g14, shapes, boxes, ind, (64, 64, 3), out=[cl(f) for f in fms[:3]])
+    with pytest.raises(ValueError):                                                      # NCHW gradient pyramid
+        ops.pyramid_roi_align_backward_pair(g7, g14, shapes, boxes, ind, (64, 64, 3), out=[f.clone() for f in fms])
+    out = ops.pyramid_roi_align_backward_pair(g7, g14, shapes, boxes, ind, (64, 64, 3), out=[cl(f) for f in fms])
+    assert all(float(g.abs().max()) == 0.0 for g in out)
+    ops.check_device_errors()
