@@ -811,6 +811,35 @@ def rpn_nms(torch, dist, wl, world, rank, hbm):
             variants["converged_inputs_kept_mean"] = float(g()[1].float().mean().item())
     finally:
         m.set_proposal_nms("auto")
+    # one batch of 8 occupies 64 of the SMs (an 8-CTA cluster per image): two independent batches of 8 on two streams, as
+    # a server that pipelines batches would issue them.  Reported beside the headline, never instead of it; rank-local.
+    try:
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        rc_b, rb_b = rc.flip(0).contiguous(), rb.flip(0).contiguous()
+        lanes = ((s1, rc, rb), (s2, rc_b, rb_b))
+
+        def in_flight(iters):
+            cur = torch.cuda.current_stream()
+            for s, _, _ in lanes:
+                s.wait_stream(cur)
+            for _ in range(iters):
+                for s, c, b in lanes:
+                    with torch.cuda.stream(s):
+                        m.proposal_layer(c, b, an, 6000, 1000, 0.7)
+            for s, _, _ in lanes:
+                cur.wait_stream(s)
+        in_flight(3)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        in_flight(20)
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = e0.elapsed_time(e1) / 20 * 1e-3
+        variants["two_batches_in_flight"] = {"ms_per_two_batches": t2 * 1e3, "images_per_s_per_gpu": 16 / t2,
+                                             "note": "two streams, 8 images each, no join between iterations"}
+    except Exception as e:  # an extra: it must never cost the line
+        variants["two_batches_in_flight"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1:
         tt = torch.tensor([t], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
