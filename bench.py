@@ -860,6 +860,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="timed steps only (use under ncu)")
+    ap.add_argument("--graph-step", action="store_true",
+                    help="experiment, off by default: also time the step replayed from one CUDA graph (launch gaps removed)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -962,6 +964,19 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": 1, "kind": arm.kind, "host_cores": cores,
                                     "sample": "8 images x %d RoIs (same five ops), single thread as the reference ships, %.1f s" % (ROIS_PER_IMAGE, dt)}
             line["also"] = secondary(torch, wl, hbm)
+    if args.graph_step:
+        # the step is ~60 us above the sum of its kernels; one captured graph (side-stream plans included) shows
+        # how much of that is launch gaps.  Never part of the default run: the default line is the eager step.
+        try:
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                wl.step()
+            t_graph = wl.time_op(graph.replay, iters=max(10, min(args.steps, 50)))
+            line["graph_step"] = {"ms_per_step": t_graph * 1e3, "rois_per_s": wl.N / t_graph, "note": "one CUDA graph replay per step"}
+        except Exception as e:
+            line["graph_step"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
