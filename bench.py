@@ -452,6 +452,18 @@ class CpuArm(object):
             self.pool.join()
 
 
+def cpu_model():
+    """The host CPU's model string (stated next to every CPU number), or None."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -478,7 +490,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "roialign_train_rois_per_s", "value": value, "unit": "RoIs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-            "cpu_baseline": {"value": value, "unit": "RoIs/s", "cores": procs, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "RoIs/s", "cores": procs, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cores": cores}
     print(json.dumps(line), flush=True)
@@ -961,7 +973,7 @@ def main():
             arm = CpuArm(1)
             arm.measure(1)                                   # warm-up image
             v, dt = arm.measure(8)
-            line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": 1, "kind": arm.kind, "host_cores": cores,
+            line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": 1, "kind": arm.kind, "host_cores": cores, "cpu_model": cpu_model(),
                                     "sample": "8 images x %d RoIs (same five ops), single thread as the reference ships, %.1f s" % (ROIS_PER_IMAGE, dt)}
             line["also"] = secondary(torch, wl, hbm)
     if args.graph_step:
