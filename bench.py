@@ -786,13 +786,23 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
     torch.cuda.synchronize()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
     ms, ms_mean, ms_max = per[iters // 2], sum(per) / iters, per[-1]
+
+    # the rank-local part and the exchange timed apart (means of 20 back-to-back calls each, max over ranks)
+    def local_part():
+        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
+        m.pyramid_roi_align(wl.fm, (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4), ind, 14, (IMAGE, IMAGE, 3))
+        return dets, counts
+    ms_local = wl.time_op(local_part, iters=iters) * 1e3
+    dets_l, counts_l = local_part()
+    ms_gather = wl.time_op(lambda: mdist.gather_detections(dets_l, counts_l, n_images=TOTAL), iters=iters) * 1e3
     if world > 1:
-        t = torch.tensor([ms, ms_mean, ms_max], device=dev)
+        t = torch.tensor([ms, ms_mean, ms_max, ms_local, ms_gather], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_mean, ms_max = (float(v) for v in t.tolist())
+        ms, ms_mean, ms_max, ms_local, ms_gather = (float(v) for v in t.tolist())
     return {"config": "configs[4]: 64 images sharded over %d GPU(s): detection layer + 14x14 mask RoIAlign + one all-gather" % world,
             "images_per_s": TOTAL / (ms * 1e-3), "ms_per_64_images": ms, "ms_per_64_images_mean": ms_mean, "ms_per_64_images_max": ms_max,
             "statistic": "median of %d iterations, max over ranks" % iters, "scaling": "strong",
+            "ms_rank_local_part": ms_local, "ms_all_gather": ms_gather,
             "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item())}
 
 
