@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs ON THE GPU BOX (gpurun): the bench without ncu first, then the ncu launch list of the same command and one
-# `ncu --set full` capture per RoIAlign kernel.  Outputs land in gpurun_out/; tools/summarise_profiles.sh turns
+# `ncu --set full` capture per RoIAlign kernel.  Outputs land in gpurun_out/; tools/summarise_profiles.py turns
 # them into the text summaries committed under profiles/.
 set -u
 R=${1:-r01}
