@@ -93,3 +93,82 @@ def test_decode_masks_arguments_without_a_gpu():
     hw = _lib.i4([64, 32, 16, 8])
     rc = L.mrcnn_pyramid_roi_align_backward_plan(hw, hw, 1, 6, None, None, 4, 7, 1.0, None, 0, None)
     assert rc != 0
+
+
+def _prototypes():
+    """name -> (return type, [parameter declarations]) parsed from include/mrcnn_b200.h."""
+    text = open(os.path.join(ROOT, "include", "mrcnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    out = {}
+    for ret, name, params in re.findall(r"MRCNN_API\s+([\w\s\*]+?)\b(mrcnn_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = " ".join(params.split())
+        out[name] = (" ".join(ret.split()), [] if params == "void" else [p.strip() for p in params.split(",")])
+    return out
+
+
+def _c_kind(decl):
+    if "*" in decl or "[" in decl or "mrcnn_stream_t" in decl:
+        return "pointer"
+    for word, kind in (("size_t", "size_t"), ("double", "double"), ("float", "float"), ("int32_t", "int"), ("int", "int")):
+        if re.search(r"\b%s\b" % word, decl):
+            return kind
+    raise AssertionError("unclassified parameter: %r" % decl)
+
+
+def _ctypes_kind(t):
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes.Array):
+        return "pointer"
+    return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_double: "double", ctypes.c_size_t: "size_t"}[t]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """A ctypes binding is unchecked at load time: a missing or mistyped argument would silently shift every later one.
+    Every binding's argument kinds (pointer / int / float / size_t, in order) and return type are the header's."""
+    from maskrcnn_b200 import _lib
+    protos = _prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES) == _declared()
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert [_c_kind(p) for p in params] == [_ctypes_kind(a) for a in args], name
+        assert _ctypes_kind(res) == _c_kind(ret + " "), name
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C program with no torch / Python in sight links
+    against libmrcnn_b200.so, loads it and gets the documented answers from the calls that need no GPU."""
+    import shutil
+    import subprocess
+    from maskrcnn_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "mrcnn_b200.h"
+int main(void) {
+    int hw[4] = {256, 128, 64, 32};
+    if (mrcnn_abi_version() != MRCNN_ABI_VERSION) return 1;
+    if (mrcnn_nms_workspace_bytes(6000) == 0) return 2;
+    if (mrcnn_pyramid_roi_align_backward_workspace_bytes(hw, hw, 16, 8192, 14) == 0) return 3;
+    /* a host pointer is refused: there is no CPU path behind the ABI */
+    {
+        float dets[5] = {0, 0, 1, 1, 0.5f};
+        int64_t keep[1];
+        int32_t count[1];
+        int rc = mrcnn_nms(dets, 1, 0.5f, keep, count, NULL, 0, NULL);
+        if (rc != MRCNN_E_NOT_DEVICE_PTR && rc != MRCNN_E_INVALID_ARG && rc != MRCNN_E_CUDA) return 4;
+        if (strlen(mrcnn_last_error()) == 0) return 5;
+    }
+    if (mrcnn_crop_forward(NULL, 0, 1, 1, 1, MRCNN_NCHW, NULL, NULL, 1, 0.0f, 7, 7, NULL, MRCNN_NCHW, NULL) != MRCNN_E_INVALID_ARG) return 6;
+    printf("abi %d ok\n", mrcnn_abi_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libmrcnn_b200.so", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.strip() == "abi 4 ok"
