@@ -172,3 +172,24 @@ int main(void) {
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     assert run.stdout.strip() == "abi 4 ok"
+
+
+def test_device_code_is_sm_100a_only_and_holds_the_hot_path_kernels():
+    """One architecture, no PTX to JIT for another, no multi-backend dispatch: every cubin in the library is sm_100a, and
+    the kernels DESIGN.md section 3 names are in it (a library that lost one would fall back to nothing: there is no fallback)."""
+    import shutil
+    import subprocess
+    from maskrcnn_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    elfs = re.findall(r"ELF file\s+\d+:\s+(\S+)", subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout)
+    assert len(elfs) >= 9 and all(e.endswith(".sm_100a.cubin") for e in elfs), elfs
+    ptx = subprocess.run(["cuobjdump", "-lptx", _lib.LIB_PATH], capture_output=True, text=True)
+    assert "PTX file" not in ptx.stdout
+    symbols = subprocess.run(["cuobjdump", "-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = set(re.findall(r"\.text\.(\w+)", symbols))
+    for name in ("roialign_fwd_nhwc_col_kernel", "roialign_fwd_nhwc_kernel", "roialign_bwd_gather_kernel", "roialign_bwd_nhwc", "bwd_items_kernel",
+                 "bwd_alloc_kernel", "crop_generic_kernel", "proposal_select_kernel", "proposal_lazy_nms_kernel", "proposal_mask_kernel",
+                 "proposal_sweep_kernel", "detection_layer_kernel", "nms_prepare_small_kernel", "target_select_kernel", "rpn_match_kernel",
+                 "rpn_pack_kernel", "full_masks_kernel", "paste_prepare_kernel"):
+        assert any(name in k for k in kernels), "%s is not in libmrcnn_b200.so" % name
