@@ -699,7 +699,27 @@ def secondary(torch, wl, hbm):
         by = roofline.roialign_fwd_bytes(1000, CHANNELS, pool, U)
         out["roialign_fwd_%dx%d" % (pool, pool)] = {"config": "configs[2]: 1000 RoIs x 256 ch, one image (warm L2: 89 MB pyramid fits)",
                                                     "rois_per_s": 1000 / t, "us": t * 1e6, "algorithmic_MB": by / 1e6,
-                                                    "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm}
+                                                    "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
+                                                    "note": "through ops.pyramid_roi_align with NCHW crops: at 1000 RoIs the kernel is "
+                                                            "shorter than the Python call that issues it (autograd node, allocation, "
+                                                            "ctypes), so this figure is bounded by the host; `direct_abi` has the kernel"}
+        # the same launch straight through the C ABI into a preallocated output (what wl.fwd does for the headline), for
+        # both crop layouts: takes the host-side call overhead out of a ~20 us kernel.  Guarded: an extra.
+        try:
+            La = wl.L
+            ptrs = La.vp4([f_.data_ptr() for f_ in fm1])
+            direct = {}
+            for lname, lay, mf in (("nchw_crops", La.NCHW, torch.contiguous_format), ("channels_last_crops", La.NHWC, torch.channels_last)):
+                o_ = torch.empty((1000, CHANNELS, pool, pool), device=dev, memory_format=mf)
+
+                def launch(o_=o_, lay=lay, pool=pool):
+                    La.check(La.lib.mrcnn_pyramid_roi_align_forward(ptrs, wl.Hs, wl.Ws, 1, CHANNELS, La.NHWC, boxes.data_ptr(), None, 1000,
+                                                                    pool, wl.area, o_.data_ptr(), lay, None, wl._s()))
+                td = wl.time_op(launch, iters=50)
+                direct[lname] = {"us": td * 1e6, "rois_per_s": 1000 / td, "algorithmic_GBps": by / td / 1e9, "frac_of_hbm": by / td / 1e9 / hbm}
+            out["roialign_fwd_%dx%d" % (pool, pool)]["direct_abi"] = direct
+        except Exception as e:
+            out["roialign_fwd_%dx%d" % (pool, pool)]["direct_abi"] = {"error": "%s: %s" % (type(e).__name__, e)}
     # the same training step with NCHW-contiguous crops and upstream gradients (the reference's physical layout;
     # the kernels then transpose through shared memory)
     o7, o14 = wl.out7.contiguous(), wl.out14.contiguous()
