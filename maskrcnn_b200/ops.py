@@ -197,6 +197,8 @@ def crop_and_resize(image, boxes, box_ind, crop_height, crop_width, extrapolatio
     _require_cuda(box_ind, "box_ind", torch.int32)  # __init__.py:34-35
     if boxes.dim() != 2 or boxes.size(1) != 4 or box_ind.dim() != 1 or box_ind.size(0) != boxes.size(0):
         raise ValueError("boxes must be [N,4] and box_ind [N]")
+    if not (torch.is_grad_enabled() and image.requires_grad):   # inference: the same launch without the autograd node
+        return _crop_forward(image, boxes.contiguous(), box_ind.contiguous(), int(crop_height), int(crop_width), float(extrapolation_value))
     return _CropAndResize.apply(image, boxes, box_ind, int(crop_height), int(crop_width), float(extrapolation_value))
 
 
@@ -221,18 +223,29 @@ class CropFunction(object):
 # PyramidROIAlign
 # ------------------------------------------------------------------------------------------------
 def _check_pyramid_args(feature_maps, boxes, box_ind):
-    """Shapes the kernels rely on without being able to see them: one (B, C) for the four levels, one index per box."""
+    """Shapes the kernels rely on without being able to see them: one (B, C) for the four levels, one index per box.
+    Written for the host-bound small calls (batch-1 inference issues a ~20 us kernel): the passing case touches each tensor
+    once; anything unexpected goes through _require_cuda for the message."""
     if len(feature_maps) != 4:
         raise ValueError("expected the four pyramid levels P2..P5")
+    f32 = torch.float32
+    B = C = dev = None
     for i, f in enumerate(feature_maps):
-        _require_cuda(f, "feature_maps[%d]" % i, torch.float32)
-        if f.dim() != 4 or f.shape[:2] != feature_maps[0].shape[:2] or f.device != feature_maps[0].device:
+        if not (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype is f32):
+            _require_cuda(f, "feature_maps[%d]" % i, f32)
+        if f.dim() != 4:
             raise ValueError("feature_maps must be four [B,C,H_l,W_l] tensors with the same B and C on one device")
-    _require_cuda(boxes, "boxes", torch.float32)
+        if i == 0:
+            B, C, dev = f.size(0), f.size(1), f.get_device()
+        elif f.size(0) != B or f.size(1) != C or f.get_device() != dev:
+            raise ValueError("feature_maps must be four [B,C,H_l,W_l] tensors with the same B and C on one device")
+    if not (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype is f32):
+        _require_cuda(boxes, "boxes", f32)
     if boxes.dim() != 2 or boxes.size(1) != 4:
         raise ValueError("boxes must be [N,4]")
     if box_ind is not None:
-        _require_cuda(box_ind, "box_ind", torch.int32)
+        if not (isinstance(box_ind, torch.Tensor) and box_ind.is_cuda and box_ind.dtype is torch.int32):
+            _require_cuda(box_ind, "box_ind", torch.int32)
         if box_ind.dim() != 1 or box_ind.size(0) != boxes.size(0):
             raise ValueError("box_ind must be int32 [N], one image index per box")
 
@@ -338,7 +351,26 @@ def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_
         if box_ind is None and B > 1:
             box_ind = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=boxes.device),
                                               torch.tensor(counts, device=boxes.device))
+    if not (torch.is_grad_enabled() and any(f.requires_grad for f in feature_maps)):
+        # nothing to differentiate (inference, torch.no_grad): the same launch without the autograd node around it
+        return _pyramid_forward_nograd(boxes, box_ind, int(pool_size), image_area, ol, feature_maps)
     return _PyramidRoiAlign.apply(boxes, box_ind, int(pool_size), image_area, ol, offsets, *feature_maps)
+
+
+def _pyramid_forward_nograd(boxes, box_ind, pool, image_area, out_layout, feature_maps):
+    """_PyramidRoiAlign.forward without the bookkeeping of a backward that will not run."""
+    fms, fl = _pyramid_layout(feature_maps)
+    f0 = fms[0]
+    B, C = f0.size(0), f0.size(1)
+    N = boxes.size(0)
+    ol = fl if out_layout is None else out_layout
+    out = _empty4((N, C, pool, pool), ol, f0)
+    if N:
+        with torch.cuda.device(out.device):
+            check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4([f.size(2) for f in fms]),
+                                                      _lib.i4([f.size(3) for f in fms]), B, C, fl, boxes.data_ptr(), _ptr(box_ind), N,
+                                                      pool, image_area, out.data_ptr(), ol, None, _stream()))
+    return out
 
 
 def roi_align(inputs, pool_size, image_shape):

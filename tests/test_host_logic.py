@@ -130,6 +130,14 @@ def test_crop_function_mirrors_the_reference_object(fake):
     # no boxes: an empty result without a launch
     fake.calls.clear()
     assert f(image, boxes[:0], ind[:0]).shape == (0, 4, 7, 9) and not fake.named("mrcnn_crop_forward")
+    # nothing to differentiate: the same call without an autograd node
+    fake.calls.clear()
+    plain = f(image.detach(), boxes, ind)
+    with torch.no_grad():
+        quiet = f(image, boxes, ind)
+    assert plain.grad_fn is None and quiet.grad_fn is None and f(image, boxes, ind).grad_fn is not None
+    x, y, z = fake.named("mrcnn_crop_forward")
+    assert (x[:12], x[13:]) == (y[:12], y[13:]) == (z[:12], z[13:])      # everything but the output pointer
     with pytest.raises(TypeError):
         f(image, boxes, ind.long())                                       # __init__.py:34-35: box_ind is int32
     with pytest.raises(ValueError):
@@ -359,3 +367,37 @@ def test_rpn_pack_geometry_and_argument_errors(fake):
         ops.rpn_pack([torch.zeros(2, 5, 8, 8)], [torch.zeros(2, 10, 8, 8)])             # odd class channels
     with pytest.raises(ValueError):
         ops.rpn_pack(logits, [torch.zeros(2, 4 * K, s, s + 1) for s in sizes])
+
+
+def test_pyramid_roi_align_skips_the_autograd_node_when_nothing_needs_a_gradient(fake):
+    """Inference issues a kernel shorter than an autograd.Function.apply: without a feature map that requires grad (or under
+    torch.no_grad) the same launch is made directly.  Both routes marshal the same arguments."""
+    boxes = torch.rand(5, 4)
+    ind = torch.tensor([0, 0, 1, 1, 1], dtype=torch.int32)
+    plain = _pyramid()
+    out = ops.pyramid_roi_align(plain, boxes, ind, 7, (64, 48, 3))
+    assert out.grad_fn is None and out.shape == (5, 8, 7, 7)
+    needs = [f.clone().requires_grad_() for f in plain]
+    out_g = ops.pyramid_roi_align(needs, boxes, ind, 7, (64, 48, 3))
+    assert out_g.grad_fn is not None
+    with torch.no_grad():
+        out_n = ops.pyramid_roi_align(needs, boxes, ind, 7, (64, 48, 3))
+    assert out_n.grad_fn is None
+    a, b, c = fake.named("mrcnn_pyramid_roi_align_forward")
+
+    def scalars(args):   # everything but the pointers
+        return ([list(args[1]), list(args[2])], args[3:6], args[8:11], args[12:14])
+    assert scalars(a) == scalars(b) == scalars(c)
+    assert list(a[0]) == [f.data_ptr() for f in plain] and list(b[0]) == list(c[0]) == [f.data_ptr() for f in needs]
+    assert a[6] == b[6] == c[6] and a[7] == b[7] == c[7] == ind.data_ptr()
+    # the gradient route still reaches the backward entry point
+    out_g.backward(torch.ones_like(out_g))
+    assert len(fake.named("mrcnn_pyramid_roi_align_backward")) == 1 and all(f.grad is not None for f in needs)
+    # channels-last / explicit output layout / no boxes behave the same on the direct route
+    fake.calls.clear()
+    cl_fms = [cl(f) for f in plain]
+    assert ops.pyramid_roi_align(cl_fms, boxes, ind, 14, (64, 64, 3)).is_contiguous(memory_format=torch.channels_last)
+    assert ops.pyramid_roi_align(cl_fms, boxes, ind, 14, (64, 64, 3), out_channels_last=False).is_contiguous()
+    assert [x[12] for x in fake.named("mrcnn_pyramid_roi_align_forward")] == [_lib.NHWC, _lib.NCHW]
+    fake.calls.clear()
+    assert ops.pyramid_roi_align(plain, boxes[:0], None, 7, (64, 64, 3)).shape == (0, 8, 7, 7) and not fake.calls
