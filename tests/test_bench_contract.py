@@ -23,6 +23,7 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["gpu_launches"] == 0 and "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 2 and cb["value"] == d["value"] and cb["sample"]
+    assert "cpu_model" in cb and d["host_cores"] >= 1                          # the host is named next to the number
     assert d["e2e"] == {"value": d["value"], "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
