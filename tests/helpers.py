@@ -139,3 +139,13 @@ def check_detect_flow_with_oracle(g):
     assert dec.shape[1:] == tuple(int(v) for v in g["decode_out_hw"])
     assert hashlib.sha256(dec.tobytes()).digest() == g["decode_out_sha256"].tobytes()
     return int(ok.sum())
+
+
+def golden_pyr_wide():
+    """tests/golden/golden_pyr_wide_v1.npz (make_golden_pyr_wide.py): the reference's model.roi_align forward + autograd
+    backward on a C = 40 pyramid -> (feature maps fp32 [1,40,s,s] x 4, boxes, image_shape, {pool: (out, grads_in, [gfm x 4])})."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_pyr_wide_v1.npz"))
+    fms = [g[f"in_fm{l}"].astype(np.float32) for l in range(4)]
+    pools = {p: (g[f"pool{p}_out"], g[f"pool{p}_in_grads"].astype(np.float32), [g[f"pool{p}_out_gfm{l}"] for l in range(4)])
+             for p in (7, 14)}
+    return fms, g["in_boxes"], [int(v) for v in g["in_image_shape"]], pools

@@ -1,0 +1,254 @@
+"""GPU parity at the EXACT sizes of BASELINE.json's configs, against the oracle and - where oracle/_ref travelled to the
+box - against the reference's own compiled CPU extension (vision.cpp:11-15 crop_forward / crop_backward / nms):
+
+  configs[1]  proposal layer, 261,888 anchors, top-6000 -> NMS 0.7 -> 1000, batch 8 (eight distinct images), both NMS
+              algorithms                                                    model.py:1307-1382, nms_cpu.cpp:11-70
+  configs[2]  PyramidROIAlign forward, 1000 RoIs x 256 ch on the 1024^2 pyramid, 7x7 and 14x14, NCHW and channels-last
+              pyramids, NCHW and channels-last crops                        model.py:276-393, crop_cpu.cpp:119-164
+  configs[3]  training step geometry: batch 16 x 512 RoIs x 256 ch launched as ONE call; images 3 and 15 checked in full
+              (forward bit-exact, gather and scatter backward <= 1e-5)      crop_cpu.cpp:167-265
+  configs[4]  detection layer 64 images x 1000 RoIs x 81 classes + 14x14 mask RoIAlign of the detections
+
+Bit-exact for selections and the forward interpolation; <= 1e-5 relative (scale = max |reference|) for the backward, the
+tolerance north_star states."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden_pyr_wide, rel_err
+from maskrcnn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+BWD_TOL = 1e-5
+IMAGE = 1024
+LEVEL_HW = [(256, 256), (128, 128), (64, 64), (32, 32)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import maskrcnn_b200
+    return maskrcnn_b200
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def ref_C_or_none():
+    from oracle import reference
+    return reference.ref_C() if reference.ref_C_available() else None
+
+
+# ------------------------------------------------------------------ configs[1]
+@pytest.mark.parametrize("algo", ["lazy", "mask"])
+def test_proposal_layer_config1_vs_oracle(ops, algo):
+    """261,888 anchors, 6000 -> 1000 at IoU 0.7, batch 8: every image's proposals bit-exact against the oracle; the NMS
+    input of image 0 (the 6000 decoded, clipped boxes in score order) also goes through the reference's own nms."""
+    anchors = synth.pyramid_anchors((IMAGE, IMAGE))
+    assert len(anchors) == 261888
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 4100 + i) for i in range(8)])
+    ops.set_proposal_nms(algo)
+    try:
+        rois, counts = ops.proposal_layer(dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors), 6000, 1000, 0.7)
+    finally:
+        ops.set_proposal_nms("auto")
+    rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
+    for i in range(8):
+        want = oracle.proposal_layer(rcs[i], rbs[i], anchors, 6000, 1000, 0.7, height=float(IMAGE), width=float(IMAGE))
+        assert counts[i] == len(want), "image %d: %d proposals, oracle %d" % (i, counts[i], len(want))
+        np.testing.assert_array_equal(rois[i, :counts[i]], want)
+        assert not rois[i, counts[i]:].any()
+    C = ref_C_or_none()
+    if C is not None:
+        # the reference's own NMS on the oracle's pre-NMS boxes of image 0 (model.py:1364-1366), then :1371-1374
+        _, d5, _ = oracle.proposal_layer(rcs[0], rbs[0], anchors, 6000, 1000, 0.7, height=float(IMAGE), width=float(IMAGE),
+                                         return_intermediate=True)                    # [6000,5] boxes px + score, score order
+        keep = C.nms(torch.from_numpy(d5), 0.7).numpy()[:1000]
+        want = d5[keep, :4] / np.array([IMAGE, IMAGE, IMAGE, IMAGE], np.float32)
+        np.testing.assert_array_equal(rois[0, :counts[0]], want)
+
+
+# ------------------------------------------------------------------ configs[2]
+@pytest.mark.parametrize("pool", [7, 14])
+def test_roialign_forward_config2_vs_oracle_and_reference(ops, pool):
+    """1000 RoIs x 256 channels on P2..P5 of a 1024^2 image: all four (pyramid layout, crop layout) combinations bit-exact
+    against the oracle, and the oracle's rows of every level bit-exact against the reference's crop_forward."""
+    fms = synth.feature_pyramid(1, 256, 77)
+    boxes = synth.random_rois(1000, 1234)
+    want, lv = oracle.pyramid_roi_align_fwd(fms, boxes, None, pool, float(IMAGE * IMAGE))
+    assert want.shape == (1000, 256, pool, pool) and len(np.unique(lv)) == 4
+    C = ref_C_or_none()
+    if C is not None:
+        from oracle import reference
+        for l in range(4):
+            sel = np.nonzero(lv == l + 2)[0]
+            crops = torch.zeros(1)
+            with reference.quiet_stdout():
+                C.crop_forward(torch.from_numpy(fms[l]), torch.from_numpy(boxes[sel]), torch.zeros(len(sel), dtype=torch.int32),
+                               0.0, pool, pool, crops)
+            np.testing.assert_array_equal(want[sel], crops.numpy())
+    b = dev(boxes)
+    for pyr_cl in (True, False):
+        ts = [cl(dev(f)) if pyr_cl else dev(f) for f in fms]
+        for out_cl in (True, False):
+            out = ops.pyramid_roi_align(ts, b, None, pool, (IMAGE, IMAGE, 3), out_channels_last=out_cl)
+            assert out.is_contiguous(memory_format=torch.channels_last if out_cl else torch.contiguous_format)
+            np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg="pyramid cl=%s crops cl=%s" % (pyr_cl, out_cl))
+        # the reference-shaped call (model.py:276: inputs = [boxes [1,N,4], P2..P5])
+        out = ops.roi_align([b.unsqueeze(0)] + ts, pool, [IMAGE, IMAGE, 3])
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+    ops.check_device_errors()
+
+
+# ------------------------------------------------------------------ configs[3]
+def _train_inputs(B=16, R=512):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4242)
+    fm = [torch.randn((B, 256, h, w), device="cuda", generator=g) for h, w in LEVEL_HW]          # NCHW master copy
+    boxes = np.concatenate([synth.random_rois(R, 7000 + 13 * i) for i in range(B)], 0)
+    ind = np.repeat(np.arange(B, dtype=np.int32), R)
+    return fm, boxes, ind
+
+
+@pytest.mark.parametrize("pool", [7, 14])
+@pytest.mark.parametrize("pyr_cl", [True, False])
+def test_train_step_config3_vs_oracle(ops, pool, pyr_cl):
+    """batch 16 x 512 RoIs x 256 ch as ONE launch (8192 RoIs, 1.43 GB pyramid): images 3 and 15 compared in full with the
+    oracle - forward bit-exact, backward (every algorithm the layout offers) <= 1e-5 of max |reference|; image 15 also
+    against the reference's own crop_backward."""
+    B, R = 16, 512
+    fm, boxes, ind = _train_inputs(B, R)
+    check = (3, 15)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99 + pool)
+    ts = [(cl(f) if pyr_cl else f.clone()).requires_grad_(True) for f in fm]
+    grad = torch.randn((B * R, 256, pool, pool), device="cuda", generator=g)
+    if pyr_cl:
+        grad = cl(grad)
+    algos = ("gather", "scatter") if pyr_cl else ("auto",)
+    got = {}
+    for algo in algos:
+        ops.set_backward_algorithm(algo)
+        try:
+            for t in ts:
+                t.grad = None
+            out = ops.pyramid_roi_align(ts, dev(boxes), dev(ind), pool, (IMAGE, IMAGE, 3))
+            out.backward(grad)
+            got[algo] = (out.detach(), [t.grad for t in ts])
+        finally:
+            ops.set_backward_algorithm("auto")
+    C = ref_C_or_none()
+    for i in check:
+        rs = slice(i * R, (i + 1) * R)
+        f_i = [f[i:i + 1].cpu().numpy() for f in fm]
+        want, lv = oracle.pyramid_roi_align_fwd(f_i, boxes[rs], None, pool, float(IMAGE * IMAGE))
+        g_i = grad[rs].cpu().numpy()
+        want_g = oracle.pyramid_roi_align_bwd(g_i, [f.shape for f in f_i], boxes[rs], None, float(IMAGE * IMAGE))
+        if C is not None and i == 15:
+            for l in range(4):
+                sel = np.nonzero(lv == l + 2)[0]
+                gi = torch.zeros((1, 256) + LEVEL_HW[l])
+                C.crop_backward(torch.from_numpy(np.ascontiguousarray(g_i[sel])), torch.from_numpy(boxes[rs][sel]),
+                                torch.zeros(len(sel), dtype=torch.int32), gi)
+                np.testing.assert_array_equal(want_g[l], gi.numpy())       # the oracle IS the reference here
+        for algo, (out, grads) in got.items():
+            np.testing.assert_array_equal(out[rs].cpu().numpy(), want, err_msg="image %d forward (%s)" % (i, algo))
+            for l in range(4):
+                e = rel_err(grads[l][i:i + 1].cpu().numpy(), want_g[l])
+                assert e <= BWD_TOL, "image %d level %d backward (%s): %.3g" % (i, l, algo, e)
+    ops.check_device_errors()
+
+
+def test_train_step_config3_pair_backward_vs_oracle(ops):
+    """The fused two-head backward (7x7 + 14x14 into one gradient pyramid) at configs[3] size: image 9 against the sum of
+    the oracle's two backward passes."""
+    B, R = 16, 512
+    fm, boxes, ind = _train_inputs(B, R)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    g7 = cl(torch.randn((B * R, 256, 7, 7), device="cuda", generator=g))
+    g14 = cl(torch.randn((B * R, 256, 14, 14), device="cuda", generator=g))
+    both = ops.pyramid_roi_align_backward_pair(g7, g14, [tuple(f.shape) for f in fm], dev(boxes), dev(ind), (IMAGE, IMAGE, 3))
+    i = 9
+    rs = slice(i * R, (i + 1) * R)
+    shapes = [(1, 256) + hw for hw in LEVEL_HW]
+    a = oracle.pyramid_roi_align_bwd(g7[rs].cpu().numpy(), shapes, boxes[rs], None, float(IMAGE * IMAGE))
+    b = oracle.pyramid_roi_align_bwd(g14[rs].cpu().numpy(), shapes, boxes[rs], None, float(IMAGE * IMAGE))
+    for l in range(4):
+        assert rel_err(both[l][i:i + 1].cpu().numpy(), a[l] + b[l]) <= BWD_TOL
+
+
+def test_mask_targets_config3_vs_oracle(ops):
+    """28x28 mask targets of configs[3]: 168 positives per image cropped out of [G,1,1024,1024] gt masks by (image,
+    instance) index (model.py:492-507), two images' worth, bit-exact (round half to even included)."""
+    G, P = 8, 168
+    rng = np.random.default_rng(31)
+    gt = np.zeros((2 * G, 1, IMAGE, IMAGE), np.float32)
+    for k in range(2 * G):
+        y, x = rng.integers(0, IMAGE - 64, 2)
+        h, w = rng.integers(32, 512, 2)
+        gt[k, 0, y:y + h, x:x + w] = 1.0
+    boxes = np.concatenate([synth.random_rois(P, 800 + i) for i in range(2)], 0)
+    ind = (np.repeat(np.arange(2), P) * G + rng.integers(0, G, 2 * P)).astype(np.int32)
+    want = oracle.crop_forward(gt, boxes, ind, 28, 28, 0.0)
+    got = ops.CropFunction(28, 28, 0)(dev(gt), dev(boxes), dev(ind))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(torch.round(got).cpu().numpy(), np.round(want))           # model.py:507
+
+
+# ------------------------------------------------------------------ configs[4]
+def test_detection_path_config4_vs_oracle(ops):
+    """64 images x 1000 RoIs x 81 classes, NMS 0.3, top-100, then the 14x14 mask RoIAlign of the detections: every image's
+    detections bit-exact against the oracle; the mask-head crops of images 0 and 63 bit-exact."""
+    B, N, NC, D = 64, 1000, 81, 100
+    rois = np.stack([synth.random_rois(N, 300 + i) for i in range(B)])
+    heads = [synth.head_outputs(N, NC, 900 + i) for i in range(B)]
+    probs, deltas = np.stack([h[0] for h in heads]), np.stack([h[1] for h in heads])
+    win = np.tile(np.array([[0, 0, IMAGE, IMAGE]], np.float32), (B, 1))
+    dets, counts = ops.detection_layer(dev(rois), dev(probs), dev(deltas), dev(win), 0.0, 0.3, D)
+    dn, cn = dets.cpu().numpy(), counts.cpu().numpy()
+    for i in range(B):
+        want = oracle.detection_layer(rois[i], probs[i], deltas[i], win[i], 0.0, 0.3, D, height=float(IMAGE), width=float(IMAGE))
+        assert cn[i] == len(want)
+        np.testing.assert_array_equal(dn[i, :cn[i]], want)
+        assert not dn[i, cn[i]:].any()
+    fms = synth.feature_pyramid(2, 256, 5)
+    ts = [cl(dev(f)) for f in fms]
+    pick = (0, 63)
+    b = (dets[list(pick), :, :4] / float(IMAGE)).reshape(-1, 4)
+    ind = torch.arange(2, dtype=torch.int32, device="cuda").repeat_interleave(D)
+    out = ops.pyramid_roi_align(ts, b, ind, 14, (IMAGE, IMAGE, 3)).cpu().numpy()
+    for k, i in enumerate(pick):
+        bb = dn[i, :, :4] / np.float32(IMAGE)                                              # model.py:1188
+        want, _ = oracle.pyramid_roi_align_fwd([f[k:k + 1] for f in fms], bb, None, 14, float(IMAGE * IMAGE))
+        np.testing.assert_array_equal(out[k * D:(k + 1) * D], want)
+
+
+# ------------------------------------------------------------------ reference-held vector on the vectorised kernels
+@pytest.mark.parametrize("pool", [7, 14])
+@pytest.mark.parametrize("pyr_cl", [True, False])
+@pytest.mark.parametrize("algo", ["gather", "scatter"])
+def test_roi_align_dropin_wide_golden(ops, pool, pyr_cl, algo):
+    """golden_pyr_wide_v1.npz: the reference's own roi_align forward + backward with C = 40 (C % 4 == 0: the channel-vectorised
+    kernels, one partially filled 64-channel chunk), through the drop-in, both pyramid layouts, both backward algorithms."""
+    fms, boxes, shape, pools = golden_pyr_wide()
+    want, grads, want_g = pools[pool]
+    ts = [(cl(dev(f)) if pyr_cl else dev(f)).requires_grad_(True) for f in fms]
+    ops.set_backward_algorithm(algo)
+    try:
+        out = ops.roi_align([dev(boxes).unsqueeze(0)] + ts, pool, shape)
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
+        out.backward(dev(grads) if not pyr_cl else cl(dev(grads)))
+    finally:
+        ops.set_backward_algorithm("auto")
+    for l in range(4):
+        assert rel_err(ts[l].grad.cpu().numpy(), want_g[l]) <= BWD_TOL
