@@ -102,32 +102,60 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_boxes(batch, seed):
+def image_inputs(image_id, pyramid=True):
+    """The synthetic inputs of ONE image of the headline workload, a function of the image id alone: the GPU arm (rank r
+    owns images r * BATCH ... r * BATCH + BATCH - 1) and the CPU reference arm (worker w owns image w % BATCH) build their
+    batches from the same images.  NCHW fp32 numpy, the reference's layout."""
     from maskrcnn_b200 import synth
-    boxes = np.concatenate([synth.random_rois(ROIS_PER_IMAGE, seed + 17 * i) for i in range(batch)], 0)
-    ind = np.repeat(np.arange(batch, dtype=np.int32), ROIS_PER_IMAGE)
-    mboxes = np.concatenate([synth.random_rois(MASK_POS, seed + 1000 + i) for i in range(batch)], 0)
-    rng = np.random.default_rng(seed)
-    mind = (np.repeat(np.arange(batch), MASK_POS) * GT_PER_IMAGE + rng.integers(0, GT_PER_IMAGE, batch * MASK_POS)).astype(np.int32)
-    return boxes, ind, mboxes, mind
+    rng = np.random.default_rng(SEED * 1000 + image_id)
+    st = {"fms": [rng.standard_normal((1, CHANNELS, h, w), dtype=np.float32) for h, w in LEVEL_HW] if pyramid else None}
+    st["boxes"] = synth.random_rois(ROIS_PER_IMAGE, SEED + 17 * image_id)
+    st["mboxes"] = synth.random_rois(MASK_POS, SEED + 1000 + image_id)
+    rects = []
+    for _ in range(GT_PER_IMAGE):                      # gt masks: filled rectangles
+        y, x = rng.integers(0, IMAGE - 64, 2)
+        h, w = rng.integers(32, 512, 2)
+        rects.append((int(y), int(x), int(h), int(w)))
+    st["rects"] = rects
+    st["mind"] = rng.integers(0, GT_PER_IMAGE, MASK_POS).astype(np.int32)      # instance of every positive RoI, image-local
+    return st
+
+
+def gt_masks_of(rects):
+    gt = np.zeros((len(rects), 1, IMAGE, IMAGE), np.float32)
+    for k, (y, x, h, w) in enumerate(rects):
+        gt[k, 0, y:y + h, x:x + w] = 1.0
+    return gt
 
 
 class Workload(object):
     """Device-resident buffers + the five launches of one step, straight through the C ABI."""
 
-    def __init__(self, torch, device, batch=BATCH, seed=SEED, crops_channels_last=True):
+    def __init__(self, torch, device, batch=BATCH, seed=SEED, crops_channels_last=True, first_image=0):
         from maskrcnn_b200 import _lib
         self.torch, self.L, self.batch = torch, _lib, batch
         self.cl_crops = crops_channels_last
         self.crop_layout = _lib.NHWC if crops_channels_last else _lib.NCHW
         cfmt = torch.channels_last if crops_channels_last else torch.contiguous_format
         g = torch.Generator(device=device)
-        g.manual_seed(seed)
+        g.manual_seed(seed + first_image)
         cl = torch.channels_last
-        self.fm = [torch.randn((batch, CHANNELS, h, w), device=device, generator=g).contiguous(memory_format=cl) for h, w in LEVEL_HW]
+        self.fm = [torch.empty((batch, CHANNELS, h, w), device=device, memory_format=cl) for h, w in LEVEL_HW]
+        self.gt = torch.zeros((batch * GT_PER_IMAGE, 1, IMAGE, IMAGE), device=device)
+        boxes, mboxes, mind = [], [], []
+        for i in range(batch):                      # every image is a function of its id (see image_inputs)
+            st = image_inputs(first_image + i)
+            for l in range(4):
+                self.fm[l][i].copy_(torch.from_numpy(st["fms"][l][0]).to(device))
+            for k, (y, x, h, w) in enumerate(st["rects"]):
+                self.gt[i * GT_PER_IMAGE + k, 0, y:y + h, x:x + w] = 1.0
+            boxes.append(st["boxes"])
+            mboxes.append(st["mboxes"])
+            mind.append(st["mind"] + i * GT_PER_IMAGE)
+        boxes, mboxes, mind = np.concatenate(boxes, 0), np.concatenate(mboxes, 0), np.concatenate(mind, 0).astype(np.int32)
+        ind = np.repeat(np.arange(batch, dtype=np.int32), ROIS_PER_IMAGE)
         self.gfm7 = [torch.empty_like(f) for f in self.fm]
         self.gfm14 = [torch.empty_like(f) for f in self.fm]
-        boxes, ind, mboxes, mind = make_boxes(batch, seed)
         self.boxes_np, self.ind_np = boxes, ind
         self.boxes = torch.from_numpy(boxes).to(device)
         self.ind = torch.from_numpy(ind).to(device)
@@ -137,12 +165,6 @@ class Workload(object):
         self.g7 = torch.randn((self.N, CHANNELS, 7, 7), device=device, generator=g).contiguous(memory_format=cfmt)
         self.g14 = torch.randn((self.N, CHANNELS, 14, 14), device=device, generator=g).contiguous(memory_format=cfmt)
         # mask targets: gt masks [batch*G,1,1024,1024] (binary rectangles), crop 28x28 by (image, instance) index
-        self.gt = torch.zeros((batch * GT_PER_IMAGE, 1, IMAGE, IMAGE), device=device)
-        rng = np.random.default_rng(seed + 5)
-        for k in range(batch * GT_PER_IMAGE):
-            y, x = rng.integers(0, IMAGE - 64, 2)
-            h, w = rng.integers(32, 512, 2)
-            self.gt[k, 0, y:y + h, x:x + w] = 1.0
         self.mboxes = torch.from_numpy(mboxes).to(device)
         self.mind = torch.from_numpy(mind).to(device)
         self.mt = torch.empty((len(mboxes), 1, 28, 28), device=device)
@@ -358,40 +380,47 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
 _CPU = {}
 
 
-def _cpu_init(img_seed, use_ref):
-    """Per-process setup, outside every timed region: import torch, synthesize one image's inputs."""
+def _cpu_init(counter, use_ref):
+    """Per-process setup, outside every timed region: import torch, take a worker number, synthesize that worker's image
+    (image id = worker % BATCH: the images of the GPU arm's rank-0 batch, see image_inputs).  Imports only the host-side
+    helpers of maskrcnn_b200 (synth / roofline): the CUDA library is not mapped into a CPU worker."""
     import torch
     torch.set_num_threads(1)
-    from maskrcnn_b200 import synth
     from maskrcnn_b200.roofline import roi_levels
-    rng = np.random.default_rng(img_seed)
-    st = {"use_ref": use_ref}
-    st["fms"] = [rng.standard_normal((1, CHANNELS, h, w), dtype=np.float32) for h, w in LEVEL_HW]
-    st["boxes"] = synth.random_rois(ROIS_PER_IMAGE, img_seed)
-    st["mboxes"] = synth.random_rois(MASK_POS, img_seed + 1)
-    gt = np.zeros((GT_PER_IMAGE, 1, IMAGE, IMAGE), np.float32)
-    gt[:, :, 100:600, 200:700] = 1.0
-    st["gt"] = gt
-    st["mind"] = rng.integers(0, GT_PER_IMAGE, MASK_POS).astype(np.int32)
+    if counter is None:
+        worker = 0
+    else:
+        with counter.get_lock():
+            worker = counter.value
+            counter.value += 1
+    st = image_inputs(worker % BATCH)
+    st["use_ref"] = use_ref
+    st["gt"] = gt_masks_of(st["rects"])
     lv = roi_levels(st["boxes"], float(IMAGE * IMAGE))
+    st["lv"] = lv
     if use_ref:
         from oracle import reference
         st["C"] = reference.ref_C()
         st["tf"] = [torch.from_numpy(f) for f in st["fms"]]
-        st["tb"] = torch.from_numpy(st["boxes"])
-        st["sel"] = [torch.from_numpy(np.nonzero(lv == l)[0]) for l in (2, 3, 4, 5)]
-        st["tgt"], st["tmb"], st["tmi"] = torch.from_numpy(gt), torch.from_numpy(st["mboxes"]), torch.from_numpy(st["mind"])
+        st["tgt"] = torch.from_numpy(st["gt"])
     _CPU.clear()
     _CPU.update(st)
 
 
-def _cpu_worker(_):
-    """One image: 512 RoIs, 7x7 + 14x14 forward and backward + 168 mask-target crops.  Returns seconds."""
+def _cpu_worker(rois):
+    """One image: the first `rois` of its 512 RoIs (all of them unless the run had to be bounded), 7x7 + 14x14 forward and
+    backward, + the matching share of the 168 mask-target crops.  Returns seconds."""
     import torch
     st = _CPU
+    n = int(rois)
+    m = max(1, (MASK_POS * n) // ROIS_PER_IMAGE)
+    boxes, lv = st["boxes"][:n], st["lv"][:n]
     if st["use_ref"]:
         from oracle import reference
-        C, tf, tb, sel = st["C"], st["tf"], st["tb"], st["sel"]
+        C, tf = st["C"], st["tf"]
+        tb = torch.from_numpy(boxes)
+        sel = [torch.from_numpy(np.nonzero(lv == l)[0]) for l in (2, 3, 4, 5)]
+        tmb, tmi = torch.from_numpy(st["mboxes"][:m]), torch.from_numpy(st["mind"][:m])
         t0 = time.perf_counter()
         with reference.quiet_stdout():
             for pool in (7, 14):
@@ -406,15 +435,15 @@ def _cpu_worker(_):
                     gi = torch.zeros_like(g).resize_(*tf[l].shape)       # __init__.py:52
                     C.crop_backward(g, lb, ind, gi)
             mt = torch.zeros(1)
-            C.crop_forward(st["tgt"], st["tmb"], st["tmi"], 0.0, 28, 28, mt)
+            C.crop_forward(st["tgt"], tmb, tmi, 0.0, 28, 28, mt)
         return time.perf_counter() - t0
     import oracle
-    fms, boxes = st["fms"], st["boxes"]
+    fms = st["fms"]
     t0 = time.perf_counter()
     for pool in (7, 14):
         out, _ = oracle.pyramid_roi_align_fwd(fms, boxes, None, pool, float(IMAGE * IMAGE))
         oracle.pyramid_roi_align_bwd(np.ones_like(out), [f.shape for f in fms], boxes, None, float(IMAGE * IMAGE))
-    oracle.crop_forward(st["gt"], st["mboxes"], st["mind"], 28, 28, 0.0)
+    oracle.crop_forward(st["gt"], st["mboxes"][:m], st["mind"][:m], 28, 28, 0.0)
     return time.perf_counter() - t0
 
 
@@ -429,22 +458,24 @@ class CpuArm(object):
         self.procs = max(1, procs)
         self.pool = None
         if self.procs == 1:
-            _cpu_init(SEED, self.use_ref)
+            _cpu_init(None, self.use_ref)
         else:
             import multiprocessing as mp
-            self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_init, initargs=(SEED, self.use_ref))
-            self.pool.map(_cpu_worker, range(self.procs), chunksize=1)   # warm every worker
+            ctx = mp.get_context("spawn")
+            self.pool = ctx.Pool(self.procs, initializer=_cpu_init, initargs=(ctx.Value("i", 0), self.use_ref))
+        self.measure(self.procs)                                         # warm every worker (first touch of its buffers) ...
+        self.warm_s = self.measure(self.procs)[1]                        # ... then one full image each: seconds per full step
 
-    def measure(self, images):
+    def measure(self, images, rois=ROIS_PER_IMAGE):
         """RoIs/s (wall clock over the whole batch of images) and seconds."""
         t0 = time.perf_counter()
         if self.pool is None:
-            for i in range(images):
-                _cpu_worker(i)
+            for _ in range(images):
+                _cpu_worker(rois)
         else:
-            self.pool.map(_cpu_worker, range(images), chunksize=1)
+            self.pool.map(_cpu_worker, [rois] * images, chunksize=1)
         dt = time.perf_counter() - t0
-        return images * ROIS_PER_IMAGE / dt, dt
+        return images * rois / dt, dt
 
     def close(self):
         if self.pool is not None:
@@ -464,7 +495,15 @@ def cpu_model():
     return None
 
 
+REF_ARM_BUDGET_S = 150.0     # the whole --impl reference run is sized to end within a few minutes
+
+
 def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU extension (oracle/_ref: vision.cpp + cpu/*.cpp compiled from
+    /root/reference, unmodified) on all host cores, on the GPU arm's config, metric and images.  Runs EXACTLY --steps timed
+    steps after --warmup untimed ones; a step is one image per worker process.  When steps x (seconds per full image)
+    would not fit REF_ARM_BUDGET_S, every step processes the first R of each image's 512 RoIs (and the matching share of
+    the mask crops) - the `sample` field says which R."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -473,27 +512,228 @@ def run_reference_arm(args):
     if os.environ.get("MRCNN_BENCH_REF_PROCS"):        # tests: a small arm (the JSON says how many processes ran)
         procs = max(1, min(procs, int(os.environ["MRCNN_BENCH_REF_PROCS"])))
     per_step_images = procs                       # one image per worker per step
-    arm = CpuArm(procs)                           # spawns, imports, synthesizes inputs and warms up: untimed
-    for _ in range(max(0, min(args.warmup, 2) - 1)):
-        arm.measure(per_step_images)
-    steps = max(1, min(args.steps, 3))
+    arm = CpuArm(procs)                           # spawns, imports, synthesizes inputs and warms up (one full image per worker): untimed
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget = float(os.environ.get("MRCNN_BENCH_REF_BUDGET_S", REF_ARM_BUDGET_S))
+    rois = ROIS_PER_IMAGE
+    if (steps + warmup) * arm.warm_s > budget:
+        rois = int(max(8, min(ROIS_PER_IMAGE, ROIS_PER_IMAGE * budget / ((steps + warmup) * arm.warm_s))))
+    for _ in range(warmup):
+        arm.measure(per_step_images, rois)
     vals, secs = [], []
     kind = arm.kind
+    t0 = time.perf_counter()
     for _ in range(steps):
-        v, dt = arm.measure(per_step_images)
+        v, dt = arm.measure(per_step_images, rois)
         vals.append(v)
         secs.append(dt)
+    total = time.perf_counter() - t0
     arm.close()
-    value = float(np.mean(vals))
-    sample = "%d images x %d RoIs per step (7x7+14x14 fwd+bwd + %d mask crops each), image-parallel over %d processes" % (
-        per_step_images, ROIS_PER_IMAGE, MASK_POS, procs)
+    value = per_step_images * rois * steps / total
+    sample = "%d images x %d of %d RoIs per step (7x7+14x14 fwd+bwd + mask crops each), image-parallel over %d processes, images " \
+             "0..%d of the GPU arm's batch%s" % (per_step_images, rois, ROIS_PER_IMAGE, procs, min(procs, BATCH) - 1,
+                                               "" if rois == ROIS_PER_IMAGE else
+                                               "; bounded sample: the per-call zero-fill of the gradient maps is spread over fewer RoIs, "
+                                               "which lowers RoIs/s (full images: %.0f RoIs/s in the warm-up)" % (procs * ROIS_PER_IMAGE / arm.warm_s))
     line = {"impl": "reference", "metric": "roialign_train_rois_per_s", "value": value, "unit": "RoIs/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": total / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
             "cpu_baseline": {"value": value, "unit": "RoIs/s", "cores": procs, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_cores": cores}
+            "gpu_launches": 0, "host_cores": cores, "step_rois_per_s_min_max": [float(min(vals)), float(max(vals))]}
     print(json.dumps(line), flush=True)
+
+
+def cpu_config_baselines():
+    """CPU baselines for the other BASELINE configs, on the box's host cores, rank 0 /
+    N = 1 only, each a bounded sample (a few seconds).  kind "reference": the reference's own code runs - its compiled
+    extension (oracle/_ref) under its unmodified Python (baseline/_ref/model.py, data.py via tools/refmodel.py):
+      configs[1]  MaskRCNN.rpn_refine's steps (model.py:1336-1374) with the canonical 6000 / 1000 limits - the fork's
+                  rpn_refine hard-codes 500 (model.py:1345), so the slice / sort lines are restated around the reference's
+                  data.boxes_scale / boxes_refine / boxes_clamp_ and maskrcnn.nms
+      configs[2]  model.roi_align (model.py:276-393), 1000 RoIs, 7x7 and 14x14
+      configs[4]  MaskRCNN.mrn_refine (model.py:1389-1487) + model.roi_align(..., 14) of its detections, per image
+    Falls back to the oracle port (kind "port") where the reference's Python did not travel."""
+    import torch
+    from maskrcnn_b200 import synth
+    out = {}
+    threads = torch.get_num_threads()
+    host = {"cores_native_ops": 1, "torch_threads": threads, "host_cores": os.cpu_count() or 1, "cpu_model": cpu_model()}
+    ref = None
+    try:
+        from oracle import reference
+        from tools import refmodel
+        if reference.ref_C_available() and refmodel.available():
+            ref = refmodel.load(reference.make_maskrcnn_shim())
+            quiet = reference.quiet_stdout
+    except Exception:
+        ref = None
+    import types
+    anchors = synth.pyramid_anchors((IMAGE, IMAGE))
+    # ---- configs[1]
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 1235 + i) for i in range(2)])
+    if ref is not None:
+        ta = torch.from_numpy(anchors)
+        std = np.array([0.1, 0.1, 0.2, 0.2])
+
+        def rpn_refine_6000(rc, rb):
+            scores = rc[:, 1]                                                                  # model.py:1336
+            deltas = ref.data.boxes_scale(rb, std)                                             # :1341
+            scores, order = scores.sort(descending=True)                                       # :1346
+            order, scores = order[:6000], scores[:6000]                                        # :1347-1350
+            boxes = ref.data.boxes_refine(ta[order, :], deltas[order, :])                      # :1354
+            ref.data.boxes_clamp_(boxes, [0, 0, IMAGE, IMAGE])                                 # :1358 (in place)
+            keep = ref.maskrcnn.nms(torch.cat((boxes, scores.unsqueeze(1)), 1), 0.7)[:1000]    # :1364-1366
+            return boxes[keep, :] / torch.tensor([IMAGE, IMAGE, IMAGE, IMAGE], dtype=torch.float32)   # :1371-1374
+        t0 = time.perf_counter()
+        n = 0
+        while n < 4 or time.perf_counter() - t0 < 3.0:
+            rpn_refine_6000(torch.from_numpy(rcs[n % 2]), torch.from_numpy(rbs[n % 2]))
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        kind = "reference"
+    else:
+        import oracle
+        t0 = time.perf_counter()
+        n = 0
+        while n < 4 or time.perf_counter() - t0 < 3.0:
+            oracle.proposal_layer(rcs[n % 2], rbs[n % 2], anchors, 6000, 1000, 0.7)
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        kind = "port"
+    out["configs[1]"] = dict(host, value=1.0 / dt, unit="images/s", kind=kind, sample="%d images, 261,888 anchors, 6000 -> NMS 0.7 -> 1000, one at a time" % n)
+    # ---- configs[2] and configs[4]
+    rng = np.random.default_rng(SEED)
+    fms = [rng.standard_normal((1, CHANNELS, h, w), dtype=np.float32) for h, w in LEVEL_HW]
+    boxes = synth.random_rois(1000, 1234)
+    N, NC, D = 1000, 81, 100
+    if ref is not None:
+        tf = [torch.from_numpy(f) for f in fms]
+        for pool in (7, 14):
+            t0 = time.perf_counter()
+            with quiet(), torch.no_grad():
+                ref.model.roi_align([torch.from_numpy(boxes).unsqueeze(0)] + list(tf), pool, [IMAGE, IMAGE, 3])
+            dt = time.perf_counter() - t0
+            out["configs[2] %dx%d" % (pool, pool)] = dict(host, value=1000 / dt, unit="RoIs/s", kind="reference",
+                                                         sample="model.roi_align, 1000 RoIs x 256 ch, one call, %.2f s" % dt)
+        cfg = type("C", (ref.config.CocoInferenceConfig,), {"GPU_COUNT": 0, "DETECTION_MAX_INSTANCES": D})()
+        me = types.SimpleNamespace(config=cfg)
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or time.perf_counter() - t0 < 3.0:
+            pr, de = synth.head_outputs(N, NC, 700 + n)
+            rois = torch.from_numpy(synth.random_rois(N, 300 + n)).unsqueeze(0)
+            with quiet(), torch.no_grad():
+                cls_, sc_, bx_ = ref.model.MaskRCNN.mrn_refine(me, rois, torch.from_numpy(pr), torch.from_numpy(de), (0, 0, IMAGE, IMAGE))
+                if cls_ is not None:
+                    ref.model.roi_align([bx_.float() / IMAGE] + list(tf), 14, [IMAGE, IMAGE, 3])   # model.py:1188-1189 -> :889
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        out["configs[4]"] = dict(host, value=1.0 / dt, unit="images/s", kind="reference",
+                                 sample="%d images: MaskRCNN.mrn_refine (1000 RoIs, 81 classes, top-100) + model.roi_align(14) of the detections" % n)
+    else:
+        import oracle
+        for pool in (7, 14):
+            t0 = time.perf_counter()
+            oracle.pyramid_roi_align_fwd(fms, boxes, None, pool, float(IMAGE * IMAGE))
+            dt = time.perf_counter() - t0
+            out["configs[2] %dx%d" % (pool, pool)] = dict(host, value=1000 / dt, unit="RoIs/s", kind="port", sample="1000 RoIs x 256 ch, one call")
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or time.perf_counter() - t0 < 3.0:
+            pr, de = synth.head_outputs(N, NC, 700 + n)
+            d = oracle.detection_layer(synth.random_rois(N, 300 + n), pr, de, np.array([0, 0, IMAGE, IMAGE], np.float32), 0.0, 0.3, D)
+            oracle.pyramid_roi_align_fwd(fms, d[:, :4] / np.float32(IMAGE), None, 14, float(IMAGE * IMAGE))
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        out["configs[4]"] = dict(host, value=1.0 / dt, unit="images/s", kind="port", sample="%d images" % n)
+    return out
+
+
+def predict_flow(torch):
+    """BASELINE configs[0]: predict.py's flow (predict.py:43-60 -> MaskRCNN.detect) on images/car58a54312d.jpg with a
+    random-init ResNet-101-FPN: the reference's UNMODIFIED model.py (baseline/_ref) on the B200 with this repo's drop-in,
+    (a) package only, (b) patch() + channels_last; and the same flow on the host CPU with the reference's own extension.
+    Seconds per image (median of 5 after 2 warm-ups), with the time inside the RoI-path operators measured by CUDA events."""
+    from tools import refmodel
+    if not refmodel.available() or refmodel.image_path() is None:
+        return {"unavailable": "baseline/_ref (the reference's model.py + demo image) did not travel"}
+    import maskrcnn as product
+    import maskrcnn_b200 as m
+    img = refmodel.pil_imread(refmodel.image_path())
+    out = {"config": "configs[0]: model.detect on images/car58a54312d.jpg (1920x1200 -> 1024x1024), random-init ResNet-101-FPN, seed 2026"}
+
+    def timed(fn, spans):
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            spans.append((e0, e1))
+            return r
+        return wrapped
+
+    for mode in ("package_only", "patched_channels_last"):
+        ref = refmodel.load(product)
+        spans = []
+        if mode == "patched_channels_last":
+            m.patch(ref.model, ref.data)
+            M = ref.model.MaskRCNN
+            ref.model.roi_align = timed(ref.model.roi_align, spans)
+            for name in ("rpn_refine", "mrn_refine", "rpn_detect"):
+                f = getattr(M, name)
+                setattr(M, name, (lambda f: lambda self, *a: timed(lambda *b: f(self, *b), spans)(*a))(f))
+            ref.data.full_masks = timed(ref.data.full_masks, spans)
+            ref.data.decode_masks = timed(ref.data.decode_masks, spans)
+        else:
+            refmodel.tolerate_empty_boxes(ref)
+            ref.model.roi_align = timed(ref.model.roi_align, spans)
+            M = ref.model.MaskRCNN
+            for name in ("rpn_refine", "mrn_refine"):
+                f = getattr(M, name)
+                setattr(M, name, (lambda f: lambda self, *a: timed(lambda *b: f(self, *b), spans)(*a))(f))
+        cfg = refmodel.make_config(ref, gpu=True)
+        model = refmodel.make_model(ref, cfg, 2026)
+        if mode == "patched_channels_last":
+            model = model.to(memory_format=torch.channels_last)
+        ts, roi = [], []
+        n_det = None
+        try:
+            with torch.no_grad():
+                for it in range(7):
+                    del spans[:]
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    res = model.detect(img)
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+                    roi.append(sum(a.elapsed_time(b) for a, b in spans) * 1e-3)
+                    n_det = None if res[0] is None else len(res[0])
+            k = int(np.argsort(ts[2:])[len(ts[2:]) // 2]) + 2
+            out[mode] = {"s_per_image": ts[k], "s_in_roi_path_ops": roi[k], "detections": n_det,
+                         "note": ("roi_align, rpn_refine, mrn_refine as the reference's own Python over maskrcnn.nms / CropFunction"
+                                  if mode == "package_only" else
+                                  "fused rpn_detect, rpn_refine, roi_align x2, mrn_refine, full_masks, decode_masks")}
+        except Exception as e:   # an extra: it must never cost the line
+            out[mode] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        del model
+        torch.cuda.empty_cache()
+    try:
+        from oracle import reference
+        if reference.ref_C_available():
+            ref = refmodel.load(reference.make_maskrcnn_shim())
+            refmodel.tolerate_empty_boxes(ref)
+            model = refmodel.make_model(ref, refmodel.make_config(ref, gpu=False), 2026)
+            with torch.no_grad(), reference.quiet_stdout():
+                t0 = time.perf_counter()
+                res = model.detect(img)
+                dt = time.perf_counter() - t0
+            out["cpu_reference"] = {"s_per_image": dt, "detections": None if res[0] is None else len(res[0]), "kind": "reference",
+                                    "torch_threads": torch.get_num_threads(), "host_cores": os.cpu_count(), "cpu_model": cpu_model(),
+                                    "sample": "one image, convolutions on all torch threads, c++ext ops single-threaded as shipped"}
+    except Exception as e:
+        out["cpu_reference"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    return out
 
 
 def bind_to_gpu_numa_node(local):
@@ -739,6 +979,77 @@ def secondary(torch, wl, hbm):
     out["train_step_nchw_crops"] = {"config": "configs[3] with NCHW-contiguous crops and gradients (smem-transposed)", "rois_per_s": wl.N / t,
                                     "ms_per_step": t * 1e3}
     del o7, o14, g7, g14
+    # NCHW feature pyramids - what an UNMODIFIED model.py produces (no channels_last): the literal drop-in's layout.
+    try:
+        fm_nchw = [f_.contiguous() for f_ in wl.fm]                       # [16,256,H,W] NCHW copies of the same pyramid
+        nchw = {}
+        for pool in (7, 14):
+            fm1n = [f_[:1] for f_ in fm_nchw]
+            U, _ = roofline.unique_taps(boxes_np, None, pool, (IMAGE, IMAGE), LEVEL_HW, 1)
+            by = roofline.roialign_fwd_bytes(1000, CHANNELS, pool, U)
+            o_ = torch.empty((1000, CHANNELS, pool, pool), device=dev)
+            pt = L.vp4([f_.data_ptr() for f_ in fm1n])
+            td = wl.time_op(lambda: L.check(L.lib.mrcnn_pyramid_roi_align_forward(pt, wl.Hs, wl.Ws, 1, CHANNELS, L.NCHW, boxes.data_ptr(), None,
+                                                                                  1000, pool, wl.area, o_.data_ptr(), L.NCHW, None, wl._s())), iters=50)
+            ta = wl.time_op(lambda: m.pyramid_roi_align(fm1n, boxes, None, pool, (IMAGE, IMAGE, 3)), iters=50)
+            nchw["fwd_%dx%d_1000_rois" % (pool, pool)] = {"direct_abi_us": td * 1e6, "through_ops_us": ta * 1e6, "algorithmic_MB": by / 1e6,
+                                                          "frac_of_hbm_direct": by / td / 1e9 / hbm, "frac_of_hbm_ops": by / ta / 1e9 / hbm}
+        # configs[3] on the NCHW pyramid: NCHW crops and gradients too (the reference's layouts end to end)
+        o7, o14 = torch.empty((wl.N, CHANNELS, 7, 7), device=dev), torch.empty((wl.N, CHANNELS, 14, 14), device=dev)
+        g7, g14 = wl.g7.contiguous(), wl.g14.contiguous()
+        gfn = [torch.empty_like(f_) for f_ in fm_nchw]
+        pf, pg = L.vp4([f_.data_ptr() for f_ in fm_nchw]), L.vp4([f_.data_ptr() for f_ in gfn])
+
+        def fwd_n(pool, o):
+            L.check(L.lib.mrcnn_pyramid_roi_align_forward(pf, wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NCHW, wl.boxes.data_ptr(), wl.ind.data_ptr(),
+                                                          wl.N, pool, wl.area, o.data_ptr(), L.NCHW, None, wl._s()))
+
+        def bwd_n(pool, g):
+            L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NCHW, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
+                                                           wl.ind.data_ptr(), wl.N, pool, wl.area, pg, L.NCHW, 1, None, L.BWD_AUTO,
+                                                           wl.ws.data_ptr(), wl.ws.numel(), wl._s()))
+
+        def step_n():
+            fwd_n(7, o7)
+            fwd_n(14, o14)
+            wl.mask_targets()
+            bwd_n(14, g14)
+            bwd_n(7, g7)
+        parts = {"fwd7": lambda: fwd_n(7, o7), "fwd14": lambda: fwd_n(14, o14), "bwd7": lambda: bwd_n(7, g7), "bwd14": lambda: bwd_n(14, g14)}
+        U7, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 7, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
+        U14, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, 14, (IMAGE, IMAGE), LEVEL_HW, wl.batch)
+        pyr = wl.batch * PYR_ELEMS_PER_IMAGE
+        alg = {"fwd7": roofline.roialign_fwd_bytes(wl.N, CHANNELS, 7, U7), "fwd14": roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14),
+               "bwd7": roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr), "bwd14": roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)}
+        for k_, fn in parts.items():
+            tp = wl.time_op(fn, iters=10)
+            nchw["train_" + k_] = {"ms": tp * 1e3, "algorithmic_MB": alg[k_] / 1e6, "frac_of_hbm": alg[k_] / tp / 1e9 / hbm}
+        tstep = wl.time_op(step_n, iters=10)
+        nchw["train_step_nchw_pyramid"] = {"ms_per_step": tstep * 1e3, "rois_per_s": wl.N / tstep,
+                                           "step_frac_of_hbm": (sum(alg.values()) + wl.mt.numel() * 4) / tstep / 1e9 / hbm,
+                                           "config": "configs[3] with the pyramid, crops and gradients all NCHW-contiguous (same algorithmic bytes)"}
+        out["nchw_pyramid"] = nchw
+        del fm_nchw, o7, o14, g7, g14, gfn
+    except Exception as e:
+        out["nchw_pyramid"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    # the standalone drop-in nms (c++ext/maskrcnn/__init__.py:21-22) at the proposal layer's size: 6000 boxes, IoU 0.7
+    try:
+        rng_ = np.random.default_rng(11)      # clustered boxes (every box has a jittered twin) in descending score order, like rpn_refine's call
+        b_ = synth.random_rois(6000, 11, image=float(IMAGE), min_size=16, max_size=500) * float(IMAGE)
+        b_[3000:] = b_[:3000] + rng_.uniform(-8, 8, (3000, 4)).astype(np.float32)
+        d5 = np.concatenate([b_, np.sort(synth.unique_scores(6000, 11))[::-1][:, None]], 1).astype(np.float32)
+        d5 = torch.from_numpy(d5).to(dev)
+        keep = torch.empty(6000, dtype=torch.int64, device=dev)
+        cnt = torch.empty(1, dtype=torch.int32, device=dev)
+        wsn = torch.empty(L.lib.mrcnn_nms_workspace_bytes(6000), dtype=torch.uint8, device=dev)
+        tk = wl.time_op(lambda: L.check(L.lib.mrcnn_nms(d5.data_ptr(), 6000, 0.7, keep.data_ptr(), cnt.data_ptr(), wsn.data_ptr(), wsn.numel(), wl._s())),
+                        iters=50)
+        tn = wl.time_op(lambda: m.nms(d5, 0.7), iters=50)
+        out["nms_standalone"] = {"config": "maskrcnn.nms on 6000 clustered boxes in score order, IoU 0.7", "kernels_us": tk * 1e6,
+                                 "dropin_us_incl_count_readback": tn * 1e6, "kept": int(cnt.item()),
+                                 "algorithmic_GBps": (6000 * 20 + int(cnt.item()) * 8) / tk / 1e9}
+    except Exception as e:
+        out["nms_standalone"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     # configs[4]: detection layer + mask RoIAlign on the detections, 64 images
     B, N, NC = 64, 1000, 81
     rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(B)])).to(dev)
@@ -775,13 +1086,16 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
     TOTAL, N, NC, D = 64, 1000, 81, 100
     b, e = mdist.shard_range(TOTAL, rank, world)
     Bl = e - b
-    rois = torch.from_numpy(np.stack([synth.random_rois(N, 300 + i) for i in range(b, e)])).to(dev)
-    g_ = torch.Generator(device=dev)
-    g_.manual_seed(7 + rank)
-    probs = torch.softmax(3.0 * torch.randn((Bl, N, NC), device=dev, generator=g_), -1)
-    deltas = 0.1 * torch.randn((Bl, N, NC, 4), device=dev, generator=g_)
+
+    def image_heads(i):          # every per-image input is a function of the image id alone: G-invariant results
+        pr, de = synth.head_outputs(N, NC, 700 + i)
+        return synth.random_rois(N, 300 + i), pr, de
+    per = [image_heads(i) for i in range(b, e)]
+    rois = torch.from_numpy(np.stack([p_[0] for p_ in per])).to(dev)
+    probs = torch.from_numpy(np.stack([p_[1] for p_ in per])).to(dev)
+    deltas = torch.from_numpy(np.stack([p_[2] for p_ in per])).to(dev)
     win = torch.tensor([[0., 0., IMAGE, IMAGE]], device=dev).repeat(Bl, 1)
-    ind = (torch.arange(Bl, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(D)
+    ind = (torch.arange(b, e, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(D)   # image i reads pyramid i % 16
 
     def run():
         dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
@@ -815,6 +1129,19 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
     ms_local = wl.time_op(local_part, iters=iters) * 1e3
     dets_l, counts_l = local_part()
     ms_gather = wl.time_op(lambda: mdist.gather_detections(dets_l, counts_l, n_images=TOTAL), iters=iters) * 1e3
+    # G-invariance: the gathered [64, D, 6] must equal, bit for bit and in image order, what ONE GPU computes
+    # image by image.  Rank 0 recomputes all 64 images one call at a time (batch 1, no sharding, no collective) and compares.
+    g_invariant = None
+    if rank == 0:
+        all_dets, all_counts = out[1], out[2]
+        ok = tuple(all_dets.shape) == (TOTAL, D, 6)
+        one = torch.tensor([[0., 0., IMAGE, IMAGE]], device=dev)
+        for i in range(TOTAL):
+            r_, p_, d_ = image_heads(i)
+            di, ci = m.detection_layer(torch.from_numpy(r_)[None].to(dev), torch.from_numpy(p_)[None].to(dev),
+                                       torch.from_numpy(d_)[None].to(dev), one, 0.0, 0.3, D)
+            ok = ok and bool(torch.equal(di[0], all_dets[i])) and int(ci[0]) == int(all_counts[i])
+        g_invariant = bool(ok)
     if world > 1:
         t = torch.tensor([ms, ms_mean, ms_max, ms_local, ms_gather], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -823,7 +1150,10 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
             "images_per_s": TOTAL / (ms * 1e-3), "ms_per_64_images": ms, "ms_per_64_images_mean": ms_mean, "ms_per_64_images_max": ms_max,
             "statistic": "median of %d iterations, max over ranks" % iters, "scaling": "strong",
             "ms_rank_local_part": ms_local, "ms_all_gather": ms_gather,
-            "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item())}
+            "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item()),
+            "g_invariant": g_invariant,
+            "g_invariant_check": "rank 0: gathered detections of all 64 images == the same images computed one by one on one GPU "
+                                 "(torch.equal on [D,6] rows and counts); inputs are functions of the image id"}
 
 
 def rpn_nms(torch, dist, wl, world, rank, hbm):
@@ -934,7 +1264,7 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     hbm, peak_src = hbm_peak()
-    wl = Workload(torch, torch.device("cuda", local))
+    wl = Workload(torch, torch.device("cuda", local), first_image=rank * BATCH)
 
     with ClockSampler(local) as cs:
         ms = timed_steps(torch, dist, wl, args.steps, args.warmup, world)
@@ -1000,12 +1330,19 @@ def main():
         line["rpn_nms"] = rpn_nms(torch, dist, wl, world, rank, hbm)
         if rank == 0 and world == 1:
             cores = os.cpu_count() or 1
-            arm = CpuArm(1)
-            arm.measure(1)                                   # warm-up image
+            arm = CpuArm(1)                                  # warms up on one full image
             v, dt = arm.measure(8)
             line["cpu_baseline"] = {"value": v, "unit": "RoIs/s", "cores": 1, "kind": arm.kind, "host_cores": cores, "cpu_model": cpu_model(),
-                                    "sample": "8 images x %d RoIs (same five ops), single thread as the reference ships, %.1f s" % (ROIS_PER_IMAGE, dt)}
+                                    "sample": "8 passes over image 0 of the GPU arm's batch x %d RoIs (same five ops), single thread as the reference ships, %.1f s" % (ROIS_PER_IMAGE, dt)}
             line["also"] = secondary(torch, wl, hbm)
+            try:
+                line["also"]["cpu_baselines_other_configs"] = cpu_config_baselines()
+            except Exception as e:   # extras must never cost the line
+                line["also"]["cpu_baselines_other_configs"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            try:
+                line["also"]["predict_flow"] = predict_flow(torch)
+            except Exception as e:
+                line["also"]["predict_flow"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if args.graph_step:
         # the step is ~60 us above the sum of its kernels; one captured graph (side-stream plans included) shows
         # how much of that is launch gaps.  Never part of the default run: the default line is the eager step.
