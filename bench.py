@@ -696,21 +696,28 @@ def predict_flow(torch):
         model = refmodel.make_model(ref, cfg, 2026)
         if mode == "patched_channels_last":
             model = model.to(memory_format=torch.channels_last)
-        ts, roi = [], []
+        pspans = []
+        model.predict = timed(model.predict, pspans)           # detect = resize/mold on the host + predict + decode + .tolist()
+        ts, roi, pred = [], [], []
         n_det = None
         try:
             with torch.no_grad():
                 for it in range(7):
                     del spans[:]
+                    del pspans[:]
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     res = model.detect(img)
                     torch.cuda.synchronize()
                     ts.append(time.perf_counter() - t0)
                     roi.append(sum(a.elapsed_time(b) for a, b in spans) * 1e-3)
+                    pred.append(sum(a.elapsed_time(b) for a, b in pspans) * 1e-3)
                     n_det = None if res[0] is None else len(res[0])
             k = int(np.argsort(ts[2:])[len(ts[2:]) // 2]) + 2
-            out[mode] = {"s_per_image": ts[k], "s_in_roi_path_ops": roi[k], "detections": n_det,
+            out[mode] = {"s_per_image": ts[k], "s_in_model_predict": pred[k], "s_in_roi_path_ops": roi[k], "detections": n_det,
+                         "host_note": "s_per_image is the reference's whole detect(): it ends with mrn_masks.cpu().tolist() of [D,1200,1920] "
+                                      "uint8 masks (model.py:1136), ~1 s of Python list building that is neither network nor RoI path; "
+                                      "s_in_model_predict is FPN + RPN + heads + RoI path + full_masks on the device (CUDA events)",
                          "note": ("roi_align, rpn_refine, mrn_refine as the reference's own Python over maskrcnn.nms / CropFunction"
                                   if mode == "package_only" else
                                   "fused rpn_detect, rpn_refine, roi_align x2, mrn_refine, full_masks, decode_masks")}

@@ -749,6 +749,292 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NCHW feature maps (what an unmodified model.py produces: conv outputs in torch's default memory format) with NCHW
+// crops - the literal drop-in's layouts.  In a channel plane one bilinear tap is 4 bytes; what IS contiguous is the
+// footprint row of a RoI: the p bin columns of one output row read two short runs (x_lo / x_hi of every bin) of ONE
+// feature row.  The kernels below therefore put the bin COLUMNS on lanes and walk the bin ROWS:
+//
+//   forward   CTA = RoI x 64 channels, warp = 8 consecutive channels, lane = (channel group, bin column), K channels per
+//             thread.  The blend is evaluated separably, exactly as crop_cpu.cpp:107-110 writes it: top = H(y_lo),
+//             bot = H(y_hi) with H(r) = v[r][x_lo] + (v[r][x_hi] - v[r][x_lo]) * x_lerp - the same three roundings, so the
+//             result is bit-identical - and H of a feature row is kept in registers while consecutive bin rows reuse it
+//             (an up-sampled RoI touches ~p + 1 rows, not 2p: 2 loads per NEW row instead of 4 per bin).  All row
+//             decisions are warp-uniform (one RoI per CTA).  The warp's 8 x p x p outputs are staged in shared memory in
+//             the output's own order and leave with ONE bulk async copy (cp.async.bulk.global.shared::cta, TMA; SASS
+//             UBLKCP): whole 16-byte-aligned runs, no partial sectors, no LSU store traffic.
+//   backward  CTA = RoI x 64 channels; the CTA's [64][p*p] slice of the upstream gradient is contiguous in NCHW and
+//             arrives with one bulk async copy (mbarrier complete_tx).  warp = channel, lane = FEATURE COLUMN of the
+//             RoI's footprint: a lane sums the bins that touch its column (their x_lo == column, or x_hi == column), walks
+//             the bin rows keeping the sums of the current and the next feature row in registers, and flushes a row when
+//             the walk leaves it - one coalesced red.global.add.f32 per (channel, feature row) run of columns instead of
+//             four scattered atomics per bin (crop_cuda.cu:151-168's design).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_taps_nchw(const RoiCtx& ctx, const float4 box, int ph, int pw, TapS* s_ty, TapS* s_tx) {
+    const int tid = threadIdx.x;
+    if (tid < ph) {
+        const AxisTap t = axis_tap(box.x, box.z, ctx.H, ph, tid);
+        TapS o;
+        o.valid = (t.lo >= 0) && ctx.ok;
+        o.lo = o.valid ? t.lo * ctx.W : 0;   // element offset of the row inside a channel plane
+        o.hi = o.valid ? t.hi * ctx.W : 0;
+        o.lerp = t.lerp;
+        s_ty[tid] = o;
+    } else if (tid >= 64 && tid < 64 + pw) {
+        const AxisTap t = axis_tap(box.y, box.w, ctx.W, pw, tid - 64);
+        TapS o;
+        o.valid = (t.lo >= 0) && ctx.ok;
+        o.lo = o.valid ? t.lo : 0;
+        o.hi = o.valid ? t.hi : 0;
+        o.lerp = t.lerp;
+        s_tx[tid - 64] = o;
+    }
+}
+
+// dst (global) <- src (shared), `bytes` a multiple of 16, both 16-byte aligned: one TMA bulk copy issued by the calling
+// thread, which also waits until the source has been read (the CTA may then exit or reuse the buffer).
+__device__ __forceinline__ void bulk_s2g_and_wait(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy smem writes above -> visible to the async proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+constexpr int kNchwCW = 8;  // channels per warp
+
+template <int POOL>
+__global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams p) {
+    constexpr int LG = (POOL > 8) ? 16 : 8;  // lanes per channel group (>= POOL)
+    constexpr int G = 32 / LG;               // channel groups per warp
+    constexpr int K = kNchwCW / G;           // channels per thread
+    constexpr int P2 = POOL * POOL;
+    static_assert(POOL <= 16, "bin columns live on the lanes of a channel group");
+    extern __shared__ __align__(128) float s_out[];  // [8 warps][8 channels][P2]: the outputs in global order
+    __shared__ TapS s_ty[POOL];
+    __shared__ TapS s_tx[POOL];
+
+    const int chunks = (p.C + kChunk - 1) / kChunk;
+    const int n = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x - n * chunks) * kChunk;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps_nchw(ctx, box, POOL, POOL, s_ty, s_tx);
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int cw0 = c0 + warp * kNchwCW;              // the warp's first channel
+    const int cc = min(kNchwCW, C - cw0);             // channels this warp owns (<= 0: nothing)
+    if (cc <= 0) return;
+    const int g = lane / LG, x = lane - g * LG;
+    float* wout = s_out + warp * (kNchwCW * P2);
+    const bool col = x < POOL;
+    const TapS tx = s_tx[col ? x : 0];
+    const bool x_in = col && tx.valid;
+    const size_t plane = (size_t)ctx.H * ctx.W;
+    const float* src[K];
+    bool live[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int cl = g * K + k;                     // channel inside the warp's 8: banks of the groups do not collide
+        live[k] = x_in && cl < cc;
+        src[k] = ctx.base + (size_t)(cw0 + (cl < cc ? cl : 0)) * plane;
+    }
+
+    int ra = -1, rb = -1;  // feature rows (as plane offsets) whose horizontal blends Ha / Hb hold
+    float Ha[K], Hb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) Ha[k] = Hb[k] = 0.f;
+
+#pragma unroll 1
+    for (int y = 0; y < POOL; ++y) {
+        const TapS ty = s_ty[y];  // warp-uniform
+        float v[K];
+        if (ty.valid) {
+            if (ty.lo == rb) {            // the walk moved down one row: yesterday's bottom is today's top
+#pragma unroll
+                for (int k = 0; k < K; ++k) Ha[k] = Hb[k];
+                ra = rb;
+                rb = -1;
+            } else if (ty.lo != ra) {
+                float lo[K], hi[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    lo[k] = live[k] ? __ldg(src[k] + ty.lo + tx.lo) : 0.f;
+                    hi[k] = live[k] ? __ldg(src[k] + ty.lo + tx.hi) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) Ha[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
+                ra = ty.lo;
+            }
+            if (ty.hi == ra) {            // y_lerp == 0: the ceil row is the floor row
+#pragma unroll
+                for (int k = 0; k < K; ++k) Hb[k] = Ha[k];
+                rb = ra;
+            } else if (ty.hi != rb) {
+                float lo[K], hi[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    lo[k] = live[k] ? __ldg(src[k] + ty.hi + tx.lo) : 0.f;
+                    hi[k] = live[k] ? __ldg(src[k] + ty.hi + tx.hi) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) Hb[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
+                rb = ty.hi;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                v[k] = x_in ? __fadd_rn(Ha[k], __fmul_rn(__fsub_rn(Hb[k], Ha[k]), ty.lerp)) : p.extrap;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = p.extrap;
+        }
+        if (col) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) wout[(g * K + k) * P2 + y * POOL + x] = v[k];
+        }
+    }
+    __syncwarp();
+    float* dst = p.crops + ((size_t)n * C + cw0) * P2;
+    const uint32_t bytes = (uint32_t)(cc * P2 * sizeof(float));
+    if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
+        if (lane == 0) bulk_s2g_and_wait(dst, wout, bytes);
+    } else {  // odd channel counts / unaligned outputs: plain coalesced stores
+        for (int i = lane; i < cc * P2; i += 32) __stcs(dst + i, wout[i]);
+    }
+}
+
+// Backward for NCHW gradient maps and NCHW upstream gradients.  grid = N x ceil(C / 64), 256 threads; dynamic smem =
+// the CTA's gradient slice [64][P2] + column tables.
+constexpr int kMaxFootCols = 288;  // widest footprint handled by the column tables (feature maps up to 288 px wide rows)
+
+template <int POOL>
+__global__ void __launch_bounds__(256) roialign_bwd_nchw_kernel(const RoiParams p) {
+    constexpr int P2 = POOL * POOL;
+    extern __shared__ __align__(128) float s_g[];  // [64][P2] upstream gradient slice, global order
+    __shared__ TapS s_ty[POOL];
+    __shared__ TapS s_tx[POOL];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_xmin, s_ncols;
+
+    const int chunks = (p.C + kChunk - 1) / kChunk;
+    const int n = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x - n * chunks) * kChunk;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+    const int cc_cta = min(kChunk, C - c0);
+
+    const float* gsrc = p.crops + ((size_t)n * C + c0) * P2;
+    const uint32_t bytes = (uint32_t)(cc_cta * P2 * sizeof(float));
+    const bool bulk = ((reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) == 0;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (bulk) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_g, gsrc, bytes, &s_bar);
+        }
+    } else {
+        for (int i = tid; i < cc_cta * P2; i += 256) s_g[i] = __ldcs(gsrc + i);
+    }
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps_nchw(ctx, box, POOL, POOL, s_ty, s_tx);
+    __syncthreads();
+    if (tid == 0) {  // footprint columns [xmin, xmin + ncols): x taps are non-decreasing in the bin index
+        int xmin = INT_MAX, xmax = -1;
+        for (int x = 0; x < POOL; ++x)
+            if (s_tx[x].valid) {
+                xmin = min(xmin, s_tx[x].lo);
+                xmax = max(xmax, s_tx[x].hi);
+            }
+        s_xmin = xmin;
+        s_ncols = (xmax >= 0) ? xmax - xmin + 1 : 0;
+    }
+    __syncthreads();
+    if (bulk) mbar_wait(&s_bar, 0);
+    if (!ctx.ok) return;
+    const int ncols = s_ncols, xmin = s_xmin;
+    if (ncols == 0) return;
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const size_t plane = (size_t)ctx.H * ctx.W;
+
+    for (int j0 = 0; j0 < ncols; j0 += 32) {  // 32 footprint columns per pass (one pass unless the box is very wide)
+        const int j = j0 + lane;
+        const int colx = xmin + j;
+        const bool act = j < ncols;
+        // the bins whose floor column is colx (weight 1 - lerp) and whose ceil column is colx (weight lerp): two short runs
+        int a0 = POOL, a1 = POOL, b0 = POOL, b1 = POOL;   // [a0,a1): x_lo == colx ; [b0,b1): x_lo == colx - 1 and lerp != 0
+        if (act) {
+            a0 = a1 = b0 = b1 = 0;
+            bool fa = false, fb = false;
+            for (int x = 0; x < POOL; ++x) {
+                const TapS t = s_tx[x];
+                if (!t.valid) continue;
+                if (t.lo == colx) {
+                    if (!fa) { a0 = x; fa = true; }
+                    a1 = x + 1;
+                }
+                if (t.hi == colx && t.hi != t.lo) {
+                    if (!fb) { b0 = x; fb = true; }
+                    b1 = x + 1;
+                }
+            }
+        }
+        for (int cl = warp; cl < cc_cta; cl += 8) {
+            const float* grow = s_g + cl * P2;
+            float* dplane = ctx.base + (size_t)(c0 + cl) * plane + colx;
+            int ra = -1;  // plane offset of the feature row accumulated in A; B is the row below it
+            float A = 0.f, Bn = 0.f;
+            bool hasB = false;
+#pragma unroll 1
+            for (int y = 0; y < POOL; ++y) {
+                const TapS ty = s_ty[y];  // warp-uniform
+                if (!ty.valid) continue;
+                float s = 0.f;
+                for (int x = a0; x < a1; ++x) {
+                    const TapS t = s_tx[x];
+                    if (t.valid && t.lo == colx) s = fmaf(__fsub_rn(1.0f, t.lerp), grow[y * POOL + x], s);
+                }
+                for (int x = b0; x < b1; ++x) {
+                    const TapS t = s_tx[x];
+                    if (t.valid && t.hi == colx && t.hi != t.lo) s = fmaf(t.lerp, grow[y * POOL + x], s);
+                }
+                if (ty.lo != ra) {
+                    if (ra >= 0) {
+                        if (act) atomicAdd(dplane + ra, A);
+                        if (hasB && ty.lo != ra + ctx.W) {
+                            if (act) atomicAdd(dplane + ra + ctx.W, Bn);
+                            hasB = false;
+                        }
+                    }
+                    A = (ra >= 0 && hasB) ? Bn : 0.f;   // hasB survives only if the walk moved to exactly the next row
+                    Bn = 0.f;
+                    hasB = false;
+                    ra = ty.lo;
+                }
+                A = fmaf(__fsub_rn(1.0f, ty.lerp), s, A);
+                if (ty.lerp != 0.0f) {  // <=> hi == lo + one row
+                    Bn = fmaf(ty.lerp, s, Bn);
+                    hasB = true;
+                }
+            }
+            if (ra >= 0) {
+                if (act) atomicAdd(dplane + ra, A);
+                if (hasB && act) atomicAdd(dplane + ra + ctx.W, Bn);
+            }
+        }
+    }
+}
+
 // Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
 struct ZeroParams {
     float4* ptr[4];
@@ -906,6 +1192,31 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
     for (int l = 0; l < (p.pyramid ? 4 : 1); ++l)  // the vectorised kernels use 32-bit element offsets inside one image
         if ((long long)p.lv[l].H * p.lv[l].W * p.C >= (1ll << 31)) fast = false;
     if ((long long)P2 * p.C >= (1ll << 31)) fast = false;
+    // NCHW feature maps with NCHW crops / gradients at the two head sizes: the row-walking kernels
+    bool nchw_fast = image_layout == MRCNN_NCHW && crops_layout == MRCNN_NCHW && p.ph == p.pw && (p.ph == 7 || p.ph == 14);
+    for (int l = 0; l < (p.pyramid ? 4 : 1); ++l)
+        if ((long long)p.lv[l].H * p.lv[l].W >= (1ll << 31)) nchw_fast = false;
+    const long long nchw_grid = (long long)p.N * ((p.C + kChunk - 1) / kChunk);
+    if (nchw_grid >= (1ll << 31)) nchw_fast = false;
+    if (nchw_fast) {
+        const size_t smem_n = sizeof(float) * kChunk * (size_t)P2;
+#define MRCNN_LAUNCH_NCHW(KERNEL)                                                                                \
+    do {                                                                                                         \
+        if (smem_n > 48 * 1024)                                                                                  \
+            MRCNN_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n));  \
+        KERNEL<<<(unsigned)nchw_grid, 256, smem_n, stream>>>(p);                                                 \
+    } while (0)
+        if (!backward) {
+            if (p.ph == 7) MRCNN_LAUNCH_NCHW(roialign_fwd_nchw_kernel<7>);
+            else MRCNN_LAUNCH_NCHW(roialign_fwd_nchw_kernel<14>);
+        } else {
+            if (p.ph == 7) MRCNN_LAUNCH_NCHW(roialign_bwd_nchw_kernel<7>);
+            else MRCNN_LAUNCH_NCHW(roialign_bwd_nchw_kernel<14>);
+        }
+#undef MRCNN_LAUNCH_NCHW
+        MRCNN_LAUNCH_CHECK();
+        return MRCNN_OK;
+    }
     if (fast) {
         const dim3 grid(p.N, (p.C + kChunk - 1) / kChunk);
         if (grid.y > 65535) return fail(MRCNN_E_INVALID_ARG, "C too large");

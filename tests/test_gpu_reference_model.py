@@ -264,8 +264,15 @@ def test_predict_flow_patched_channels_last(ops):
 
 
 # ------------------------------------------------------------------ training step
-def _train_step(ref, cfg, model):
-    inputs = refmodel.train_inputs(ref, cfg, 5)
+def _train_step(ref, cfg, model, rec):
+    """One sample through MaskRCNN.train_epoch.  The ground truth is made of the network's own proposals for the image
+    (refmodel.proposals_of: an untrained RPN proposes nothing that overlaps a random ground truth), found by a dry forward
+    pass whose recorded calls are dropped."""
+    probe = refmodel.train_inputs(ref, cfg, 5)
+    gt = refmodel.gt_from_proposals(refmodel.proposals_of(model, probe[0]))
+    for v in rec.values():
+        del v[:]
+    inputs = refmodel.train_inputs(ref, cfg, 5, gt_boxes=gt)
     opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
     torch.manual_seed(3)
     loss = model.train_epoch([inputs], opt, 1)
@@ -282,7 +289,7 @@ def test_train_step_package_only(ops):
     ref = refmodel.load(recording_package(product, rec))
     cfg = refmodel.make_config(ref, gpu=True, train=True)
     model = refmodel.make_model(ref, cfg, SEED)
-    _train_step(ref, cfg, model)
+    _train_step(ref, cfg, model, rec)
     assert {e["args"][0] for e in rec["crop"]} == {7, 14, 28}
     assert check_package_calls(rec) >= 2                            # at least one level per head received a gradient
     ops.check_device_errors()
@@ -297,7 +304,7 @@ def test_train_step_patched_channels_last(ops):
     wrap_fused(ref, ops, rec)
     cfg = refmodel.make_config(ref, gpu=True, train=True)
     model = refmodel.make_model(ref, cfg, SEED).to(memory_format=torch.channels_last)
-    _train_step(ref, cfg, model)
+    _train_step(ref, cfg, model, rec)
     assert [e["pool"] for e in rec["roi_align"]] == [7, 14] and len(rec["mrn_samples"]) == 1
     assert check_fused_calls(rec, cfg, expect_channels_last=True) == 2
     ops.check_device_errors()

@@ -117,20 +117,27 @@ def make_model(ref, cfg, seed):
     return model
 
 
-def train_inputs(ref, cfg, seed, n_gt=6):
+def train_inputs(ref, cfg, seed, n_gt=6, gt_boxes=None):
     """One synthetic training sample in the format CocoMaskRCNNDataset.__getitem__ returns (data.py:710-737), batched by 1
-    like the DataLoader does (model.py:1528-1532): [images, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks]."""
+    like the DataLoader does (model.py:1528-1532): [images, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks].
+    gt_boxes: optional [G,4] pixel boxes (rectangular instances); random ones otherwise."""
     import torch
     rng = np.random.default_rng(seed)
     size = int(cfg.IMAGE_MAX_DIM)
     image = torch.from_numpy(rng.standard_normal((3, size, size)).astype(np.float32))
-    boxes = np.zeros((n_gt, 4), np.float32)
+    if gt_boxes is None:
+        boxes = np.zeros((n_gt, 4), np.float32)
+        for k in range(n_gt):
+            h, w = rng.integers(size // 8, size // 2, 2)
+            y, x = rng.integers(0, size - h), rng.integers(0, size - w)
+            boxes[k] = [y, x, y + h, x + w]
+    else:
+        boxes = np.asarray(gt_boxes, np.float32).reshape(-1, 4)
+        n_gt = len(boxes)
     masks = np.zeros((n_gt, size, size), np.float32)
     for k in range(n_gt):
-        h, w = rng.integers(size // 8, size // 2, 2)
-        y, x = rng.integers(0, size - h), rng.integers(0, size - w)
-        boxes[k] = [y, x, y + h, x + w]
-        masks[k, y:y + h, x:x + w] = 1.0
+        y1, x1, y2, x2 = (int(v) for v in boxes[k])
+        masks[k, y1:y2, x1:x2] = 1.0
     class_ids = rng.integers(1, 81, n_gt).astype(np.int32)
     anchors = ref.utils.create_pyramid_anchors(cfg.RPN_ANCHOR_SCALES, cfg.RPN_ANCHOR_RATIOS, cfg.BACKBONE_SHAPES,
                                                cfg.BACKBONE_STRIDES, cfg.RPN_ANCHOR_STRIDE)
@@ -139,6 +146,46 @@ def train_inputs(ref, cfg, seed, n_gt=6):
     return [image.unsqueeze(0), torch.from_numpy(np.asarray(rpn_match))[:, None].unsqueeze(0).int(),
             torch.from_numpy(np.asarray(rpn_bbox)).float().unsqueeze(0), torch.from_numpy(class_ids).unsqueeze(0),
             torch.from_numpy(boxes).unsqueeze(0), torch.from_numpy(masks).unsqueeze(0)]
+
+
+def proposals_of(model, image):
+    """The proposals [K,4] (pixels, numpy) the network makes for `image` [1,3,S,S] - the same ones MaskRCNN.extract will see
+    (batch norm runs in eval mode there too, model.py:1218-1224).  The random-init harness takes its ground-truth boxes from
+    them: an untrained RPN's proposals overlap no random ground truth, and a training step without a positive RoI never
+    reaches the RoIAlign heads (model.py:1272-1282)."""
+    import torch
+    was = model.training
+    dev = next(model.parameters()).device
+    with torch.no_grad():
+        model.eval()
+        p2, p3, p4, p5, p6 = model.fpn(image.to(dev))
+        _, rpn_class, rpn_bbox = model.rpn_detect([p2, p3, p4, p5, p6])
+        rois = model.rpn_refine(rpn_class, rpn_bbox)
+    model.train(was)
+    size = float(model.config.IMAGE_SHAPE[0])
+    return rois[0].detach().cpu().numpy() * size
+
+
+def gt_from_proposals(rois_px, n_gt=6, min_side=24):
+    """n_gt well separated proposals, rounded outwards to whole pixels, as ground-truth boxes."""
+    b = np.asarray(rois_px, np.float32)
+    side = np.minimum(b[:, 2] - b[:, 0], b[:, 3] - b[:, 1])
+    pick = []
+    for i in np.argsort(-side):
+        if side[i] < min_side or len(pick) == n_gt:
+            break
+        if all(_iou(b[i], b[j]) < 0.3 for j in pick):
+            pick.append(i)
+    assert pick, "no proposal is large enough to serve as ground truth"
+    g = b[pick]
+    return np.stack([np.floor(g[:, 0]), np.floor(g[:, 1]), np.ceil(g[:, 2]), np.ceil(g[:, 3])], 1).astype(np.float32)
+
+
+def _iou(a, b):
+    y1, x1, y2, x2 = max(a[0], b[0]), max(a[1], b[1]), min(a[2], b[2]), min(a[3], b[3])
+    inter = max(0.0, y2 - y1) * max(0.0, x2 - x1)
+    ua = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return inter / ua if ua > 0 else 0.0
 
 
 def tolerate_empty_boxes(ref):
