@@ -794,8 +794,13 @@ __device__ __forceinline__ void stage_taps_nchw(const RoiCtx& ctx, const float4 
 // dst (global) <- src (shared), `bytes` a multiple of 16, both 16-byte aligned: one TMA bulk copy issued by the calling
 // thread, which also waits until the source has been read (the CTA may then exit or reuse the buffer).
 __device__ __forceinline__ void bulk_s2g_and_wait(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    // the crops are a write-once stream (1.6 GB per configs[3] forward): evict-first in L2, so that they do not push out the
+    // feature maps other RoIs of the image are about to read
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy smem writes above -> visible to the async proxy
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -834,14 +839,18 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     const bool col = x < POOL;
     const TapS tx = s_tx[col ? x : 0];
     const bool x_in = col && tx.valid;
-    const size_t plane = (size_t)ctx.H * ctx.W;
-    const float* src[K];
+    // 32-bit element offsets from the image's base (the launcher guarantees C * H * W < 2^31): one IMAD.WIDE per load
+    const unsigned plane = (unsigned)(ctx.H * ctx.W);
+    const float* base = ctx.base;
+    unsigned olo[K], ohi[K];
     bool live[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int cl = g * K + k;                     // channel inside the warp's 8: banks of the groups do not collide
         live[k] = x_in && cl < cc;
-        src[k] = ctx.base + (size_t)(cw0 + (cl < cc ? cl : 0)) * plane;
+        const unsigned o = (unsigned)(cw0 + (cl < cc ? cl : 0)) * plane;
+        olo[k] = o + (unsigned)tx.lo;
+        ohi[k] = o + (unsigned)tx.hi;
     }
 
     int ra = -1, rb = -1;  // feature rows (as plane offsets) whose horizontal blends Ha / Hb hold
@@ -863,8 +872,8 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 float lo[K], hi[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    lo[k] = live[k] ? __ldg(src[k] + ty.lo + tx.lo) : 0.f;
-                    hi[k] = live[k] ? __ldg(src[k] + ty.lo + tx.hi) : 0.f;
+                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.lo)) : 0.f;
+                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.lo)) : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) Ha[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
@@ -878,8 +887,8 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 float lo[K], hi[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    lo[k] = live[k] ? __ldg(src[k] + ty.hi + tx.lo) : 0.f;
-                    hi[k] = live[k] ? __ldg(src[k] + ty.hi + tx.hi) : 0.f;
+                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.hi)) : 0.f;
+                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.hi)) : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) Hb[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
@@ -908,17 +917,25 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
 }
 
 // Backward for NCHW gradient maps and NCHW upstream gradients.  grid = N x ceil(C / 64), 256 threads; dynamic smem =
-// the CTA's gradient slice [64][P2] + column tables.
-constexpr int kMaxFootCols = 288;  // widest footprint handled by the column tables (feature maps up to 288 px wide rows)
-
+// the CTA's gradient slice [64][P2] (one bulk async copy).  Same thread layout as the forward: lane = (channel group,
+// bin column), K channels per thread, bin rows walked top to bottom.  The adjoint is applied separably: a thread first
+// sums, down its bin column, everything that lands on one FEATURE ROW (running sums for the current row and the one below,
+// flushed when the walk leaves a row - an up-sampled RoI has ~p + 1 rows for 2p taps), then spreads a finished row sum over
+// its two feature columns: two red.global.add.f32 per thread and finished row, lanes on neighbouring addresses of one
+// plane row.  History (configs[3] 14x14 backward, kernel time; profiles/r02_nchw_history.txt): lanes on feature columns with
+// per-lane bin lists 5.3 ms (issue-bound); this version 1.19 ms (L1/TEX red requests: 112 M); a third one that regrouped a
+// finished row by feature column through shared memory (39 M requests) 1.81 ms - the extra shared-memory reads and 85
+// registers cost more than the saved requests.
 template <int POOL>
 __global__ void __launch_bounds__(256) roialign_bwd_nchw_kernel(const RoiParams p) {
+    constexpr int LG = (POOL > 8) ? 16 : 8;
+    constexpr int G = 32 / LG;
+    constexpr int K = kNchwCW / G;
     constexpr int P2 = POOL * POOL;
     extern __shared__ __align__(128) float s_g[];  // [64][P2] upstream gradient slice, global order
     __shared__ TapS s_ty[POOL];
     __shared__ TapS s_tx[POOL];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_xmin, s_ncols;
 
     const int chunks = (p.C + kChunk - 1) / kChunk;
     const int n = blockIdx.x / chunks;
@@ -948,90 +965,85 @@ __global__ void __launch_bounds__(256) roialign_bwd_nchw_kernel(const RoiParams 
     const RoiCtx ctx = select_level(p, n, box);
     stage_taps_nchw(ctx, box, POOL, POOL, s_ty, s_tx);
     __syncthreads();
-    if (tid == 0) {  // footprint columns [xmin, xmin + ncols): x taps are non-decreasing in the bin index
-        int xmin = INT_MAX, xmax = -1;
-        for (int x = 0; x < POOL; ++x)
-            if (s_tx[x].valid) {
-                xmin = min(xmin, s_tx[x].lo);
-                xmax = max(xmax, s_tx[x].hi);
-            }
-        s_xmin = xmin;
-        s_ncols = (xmax >= 0) ? xmax - xmin + 1 : 0;
-    }
-    __syncthreads();
     if (bulk) mbar_wait(&s_bar, 0);
     if (!ctx.ok) return;
-    const int ncols = s_ncols, xmin = s_xmin;
-    if (ncols == 0) return;
 
     const int warp = tid >> 5, lane = tid & 31;
+    const int cw = warp * kNchwCW;                    // first channel of the warp inside the CTA's slice
+    const int cc = min(kNchwCW, cc_cta - cw);
+    if (cc <= 0) return;
+    const int g = lane / LG, x = lane - g * LG;
+    const bool col = x < POOL;
+    const TapS tx = s_tx[col ? x : 0];
+    const bool x_in = col && tx.valid;
+    const float wl = __fsub_rn(1.0f, tx.lerp), wh = tx.lerp;
+    const bool two_cols = tx.lerp != 0.0f;            // <=> hi == lo + 1
     const size_t plane = (size_t)ctx.H * ctx.W;
+    const int W = ctx.W;
+    float* dlo[K];
+    const float* gk[K];
+    bool live[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int cl = g * K + k;
+        live[k] = x_in && cl < cc;
+        dlo[k] = ctx.base + (size_t)(c0 + cw + (cl < cc ? cl : 0)) * plane + tx.lo;
+        gk[k] = s_g + (cw + (cl < cc ? cl : 0)) * P2 + (col ? x : 0);
+    }
+    const int dx = tx.hi - tx.lo;
 
-    for (int j0 = 0; j0 < ncols; j0 += 32) {  // 32 footprint columns per pass (one pass unless the box is very wide)
-        const int j = j0 + lane;
-        const int colx = xmin + j;
-        const bool act = j < ncols;
-        // the bins whose floor column is colx (weight 1 - lerp) and whose ceil column is colx (weight lerp): two short runs
-        int a0 = POOL, a1 = POOL, b0 = POOL, b1 = POOL;   // [a0,a1): x_lo == colx ; [b0,b1): x_lo == colx - 1 and lerp != 0
-        if (act) {
-            a0 = a1 = b0 = b1 = 0;
-            bool fa = false, fb = false;
-            for (int x = 0; x < POOL; ++x) {
-                const TapS t = s_tx[x];
-                if (!t.valid) continue;
-                if (t.lo == colx) {
-                    if (!fa) { a0 = x; fa = true; }
-                    a1 = x + 1;
-                }
-                if (t.hi == colx && t.hi != t.lo) {
-                    if (!fb) { b0 = x; fb = true; }
-                    b1 = x + 1;
-                }
+    int ra = -1;           // plane offset of the feature row summed in A; Bn is the row below it
+    bool hasB = false;
+    float A[K], Bn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) A[k] = Bn[k] = 0.f;
+
+    auto flush = [&](const float (&V)[K], int row) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (live[k]) {
+                atomicAdd(dlo[k] + row, __fmul_rn(wl, V[k]));
+                if (two_cols) atomicAdd(dlo[k] + row + dx, __fmul_rn(wh, V[k]));
             }
         }
-        for (int cl = warp; cl < cc_cta; cl += 8) {
-            const float* grow = s_g + cl * P2;
-            float* dplane = ctx.base + (size_t)(c0 + cl) * plane + colx;
-            int ra = -1;  // plane offset of the feature row accumulated in A; B is the row below it
-            float A = 0.f, Bn = 0.f;
-            bool hasB = false;
+    };
+
 #pragma unroll 1
-            for (int y = 0; y < POOL; ++y) {
-                const TapS ty = s_ty[y];  // warp-uniform
-                if (!ty.valid) continue;
-                float s = 0.f;
-                for (int x = a0; x < a1; ++x) {
-                    const TapS t = s_tx[x];
-                    if (t.valid && t.lo == colx) s = fmaf(__fsub_rn(1.0f, t.lerp), grow[y * POOL + x], s);
-                }
-                for (int x = b0; x < b1; ++x) {
-                    const TapS t = s_tx[x];
-                    if (t.valid && t.hi == colx && t.hi != t.lo) s = fmaf(t.lerp, grow[y * POOL + x], s);
-                }
-                if (ty.lo != ra) {
-                    if (ra >= 0) {
-                        if (act) atomicAdd(dplane + ra, A);
-                        if (hasB && ty.lo != ra + ctx.W) {
-                            if (act) atomicAdd(dplane + ra + ctx.W, Bn);
-                            hasB = false;
-                        }
-                    }
-                    A = (ra >= 0 && hasB) ? Bn : 0.f;   // hasB survives only if the walk moved to exactly the next row
-                    Bn = 0.f;
-                    hasB = false;
-                    ra = ty.lo;
-                }
-                A = fmaf(__fsub_rn(1.0f, ty.lerp), s, A);
-                if (ty.lerp != 0.0f) {  // <=> hi == lo + one row
-                    Bn = fmaf(ty.lerp, s, Bn);
-                    hasB = true;
-                }
-            }
+    for (int y = 0; y < POOL; ++y) {
+        const TapS ty = s_ty[y];  // warp-uniform
+        if (!ty.valid) continue;
+        float gv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) gv[k] = gk[k][y * POOL];
+        if (ty.lo != ra) {
+            bool carry = false;
             if (ra >= 0) {
-                if (act) atomicAdd(dplane + ra, A);
-                if (hasB && act) atomicAdd(dplane + ra + ctx.W, Bn);
+                flush(A, ra);
+                if (hasB) {
+                    if (ty.lo == ra + W) carry = true;   // the walk moved down exactly one row: B becomes A
+                    else flush(Bn, ra + W);
+                }
             }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                A[k] = carry ? Bn[k] : 0.f;
+                Bn[k] = 0.f;
+            }
+            hasB = false;
+            ra = ty.lo;
         }
+        const float w0 = __fsub_rn(1.0f, ty.lerp);
+#pragma unroll
+        for (int k = 0; k < K; ++k) A[k] = fmaf(w0, gv[k], A[k]);
+        if (ty.lerp != 0.0f) {  // <=> hi == lo + one row
+#pragma unroll
+            for (int k = 0; k < K; ++k) Bn[k] = fmaf(ty.lerp, gv[k], Bn[k]);
+            hasB = true;
+        }
+    }
+    if (ra >= 0) {
+        flush(A, ra);
+        if (hasB) flush(Bn, ra + W);
     }
 }
 
@@ -1195,7 +1207,7 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
     // NCHW feature maps with NCHW crops / gradients at the two head sizes: the row-walking kernels
     bool nchw_fast = image_layout == MRCNN_NCHW && crops_layout == MRCNN_NCHW && p.ph == p.pw && (p.ph == 7 || p.ph == 14);
     for (int l = 0; l < (p.pyramid ? 4 : 1); ++l)
-        if ((long long)p.lv[l].H * p.lv[l].W >= (1ll << 31)) nchw_fast = false;
+        if ((long long)p.C * p.lv[l].H * p.lv[l].W >= (1ll << 31)) nchw_fast = false;   // 32-bit element offsets inside one image
     const long long nchw_grid = (long long)p.N * ((p.C + kChunk - 1) / kChunk);
     if (nchw_grid >= (1ll << 31)) nchw_fast = false;
     if (nchw_fast) {
