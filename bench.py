@@ -255,9 +255,36 @@ class Workload(object):
         return a.elapsed_time(b) / iters * 1e-3
 
 
-def timed_steps(torch, dist, wl, steps, warmup, world):
+def capture_step(torch, wl):
+    """The step as ONE CUDA graph (the five ops and the side-stream queue building, fork / join included): launch gaps and
+    the host's launch work leave the timed region.  Returns a callable, or None when capture is not possible."""
+    try:
+        for _ in range(2):
+            wl.step()
+        torch.cuda.synchronize()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        before = wl.launches
+        with torch.cuda.graph(graph, stream=cap):
+            wl.step()
+        per_step = wl.launches - before
+        torch.cuda.current_stream().wait_stream(cap)
+
+        def replay():
+            graph.replay()
+            wl.launches += per_step
+        replay.graph = graph
+        return replay
+    except Exception as e:   # never cost the line: fall back to eager launches
+        sys.stderr.write("CUDA graph capture of the step failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
+        return None
+
+
+def timed_steps(torch, dist, wl, steps, warmup, world, step=None):
+    step = step or wl.step
     for _ in range(warmup):
-        wl.step()
+        step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -266,7 +293,7 @@ def timed_steps(torch, dist, wl, steps, warmup, world):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-        wl.step()
+        step()
     b.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -777,6 +804,23 @@ def ncu_traffic():
     return out
 
 
+def mask_target_bytes(wl):
+    """Algorithmic bytes of the 28x28 mask-target crop: outputs written once + the UNIQUE mask pixels the taps touch (4 B each)
+    + boxes and indices.  (Round 1 credited five floats per output; taps of neighbouring bins coincide for small boxes.)"""
+    mb, mi = wl.mboxes.cpu().numpy(), wl.mind.cpu().numpy()
+    sm1 = np.float32(IMAGE - 1)
+    i = np.arange(28, dtype=np.float32)
+    unique = 0
+    for k in range(len(mb)):
+        taps = []
+        for a1, a2 in ((mb[k, 0], mb[k, 2]), (mb[k, 1], mb[k, 3])):
+            pos = (a1 * sm1 + i * (((a2 - a1) * sm1) / np.float32(27))).astype(np.float32)
+            ok = (pos >= 0) & (pos <= sm1)
+            taps.append(len(np.unique(np.concatenate([np.floor(pos[ok]), np.ceil(pos[ok])]))))
+        unique += taps[0] * taps[1]
+    return wl.mt.numel() * 4 + unique * 4 + len(mb) * 20
+
+
 def workload_config():
     return {"workload": "BASELINE configs[3]: training-mode PyramidROIAlign fwd+bwd, batch %d x %d RoIs x %d ch, P2-P5 of %dx%d, "
                         "7x7 + 14x14 + %d 28x28 mask-target crops/img" % (BATCH, ROIS_PER_IMAGE, CHANNELS, IMAGE, IMAGE, MASK_POS),
@@ -1239,8 +1283,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="timed steps only (use under ncu)")
-    ap.add_argument("--graph-step", action="store_true",
-                    help="experiment, off by default: also time the step replayed from one CUDA graph (launch gaps removed)")
+    ap.add_argument("--eager", action="store_true",
+                    help="time eagerly launched steps instead of replaying the step's CUDA graph (the default)")
+    ap.add_argument("--graph-step", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -1273,8 +1318,9 @@ def main():
     hbm, peak_src = hbm_peak()
     wl = Workload(torch, torch.device("cuda", local), first_image=rank * BATCH)
 
+    step_fn = None if args.eager else capture_step(torch, wl)
     with ClockSampler(local) as cs:
-        ms = timed_steps(torch, dist, wl, args.steps, args.warmup, world)
+        ms = timed_steps(torch, dist, wl, args.steps, args.warmup, world, step_fn)
     launches = wl.launches
     clocks = cs.summary()
     per_step = ms / args.steps
@@ -1283,6 +1329,8 @@ def main():
     line = {"metric": "roialign_train_rois_per_s", "value": value, "unit": "RoIs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(), "clocks": clocks, "gpu_launches": launches}
+    line["config"]["launch"] = ("one CUDA graph replay per step (11 kernels: 2 forwards, mask-target crop, 2 x 3 queue kernels on a side "
+                                "stream, 2 gathers)" if step_fn is not None else "eager launches")
 
     if not args.no_extras:
         from maskrcnn_b200 import roofline
@@ -1299,7 +1347,7 @@ def main():
             "roialign_fwd_nhwc_col_kernel<14,nhwc>": (lambda: wl.fwd(14, wl.out14), roofline.roialign_fwd_bytes(wl.N, CHANNELS, 14, U14)),
             "roialign_bwd_gather_kernel<7,nhwc>": (lambda: wl.bwd_planned(7, wl.g7, wl.gfm7, wl.ws7), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 7, pyr)),
             "roialign_bwd_gather_kernel<14,nhwc>": (lambda: wl.bwd_planned(14, wl.g14, wl.gfm14, wl.ws), roofline.roialign_bwd_bytes(wl.N, CHANNELS, 14, pyr)),
-            "crop_generic_kernel<28x28 mask targets>": (wl.mask_targets, wl.mt.numel() * 4 * 5 + wl.mt.shape[0] * 20),
+            "crop_plane_fwd_kernel<28x28 mask targets>": (wl.mask_targets, mask_target_bytes(wl)),
             plan_name: (plans, 2 * wl.N * 20),
         }
         captures = dict(zip(ops, ("fwd7_nhwc", "fwd14_nhwc", "bwd7_nhwc:gather", "bwd14_nhwc:gather", None, None)))
@@ -1316,6 +1364,8 @@ def main():
         for k in kern.values():
             k["share_of_step"] = k["ms"] / total
         # the same step with each backward building its own queues on the main stream (mrcnn_pyramid_roi_align_backward)
+        t_eager = wl.time_op(wl.step, iters=20)
+        line["eager_step"] = {"ms_per_step": t_eager * 1e3, "rois_per_s": wl.N / t_eager, "note": "the same step launched kernel by kernel from Python"}
         t_unplanned = wl.time_op(wl.step_unplanned, iters=10)
         t_bwd14 = wl.time_op(lambda: wl.bwd(14, wl.g14, wl.gfm14))
         t_bwd7 = wl.time_op(lambda: wl.bwd(7, wl.g7, wl.gfm7))
@@ -1350,19 +1400,6 @@ def main():
                 line["also"]["predict_flow"] = predict_flow(torch)
             except Exception as e:
                 line["also"]["predict_flow"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
-    if args.graph_step:
-        # the step is ~60 us above the sum of its kernels; one captured graph (side-stream plans included) shows
-        # how much of that is launch gaps.  Never part of the default run: the default line is the eager step.
-        try:
-            cap = torch.cuda.Stream()
-            cap.wait_stream(torch.cuda.current_stream())
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=cap):
-                wl.step()
-            t_graph = wl.time_op(graph.replay, iters=max(10, min(args.steps, 50)))
-            line["graph_step"] = {"ms_per_step": t_graph * 1e3, "rois_per_s": wl.N / t_graph, "note": "one CUDA graph replay per step"}
-        except Exception as e:
-            line["graph_step"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -98,6 +98,14 @@ def vp4(vals):
     return _vp4(*[int(v) for v in vals])
 
 
+def i4_cached(vals, _cache={}):
+    key = tuple(int(v) for v in vals)
+    a = _cache.get(key)
+    if a is None:
+        a = _cache[key] = _i4(*key)
+    return a
+
+
 def i32_array(vals):
     """Host int32 array (e.g. image_offsets_host) or None."""
     if vals is None:

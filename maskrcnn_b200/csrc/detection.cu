@@ -19,7 +19,7 @@
 namespace mrcnn {
 
 constexpr int kDetThreads = 1024;
-constexpr int kDetMaxN = 4096;
+constexpr int kDetMaxN = 3968;  // 32768 + 48 N + 16 ceil(N / 64) bytes of shared memory must fit the 220 KB the kernel may opt into
 constexpr int kDetLazyMaxInst = 1024;   // lazy NMS up to this many wanted detections
 constexpr int kDetSmemMaskMaxN = 1024;  // suppression words kept in shared memory up to this many RoIs
 

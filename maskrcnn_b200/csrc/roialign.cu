@@ -18,6 +18,8 @@
 //
 // HBM-bound: algorithmic bytes per RoI = C*p*p*4 (output) + unique taps*C*4, see DESIGN.md.
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "api_util.h"
 #include "nms_core.cuh"
@@ -324,6 +326,324 @@ __global__ void __launch_bounds__(SLOTS * LANES, 1024 / (SLOTS * LANES)) roialig
             stg_f4_stream(out + (unsigned)(y1 * POOL * C), vb);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, channels-last in and out, row-walking (the mask head's 14x14): a thread owns ONE bin column and K x 4 channels
+// and walks the bin rows top to bottom.  The blend is separable exactly as crop_cpu.cpp:107-110 writes it - top = H(y_lo),
+// bot = H(y_hi), H(r) = v[r][x_lo] + (v[r][x_hi] - v[r][x_lo]) * x_lerp, the same three roundings per value - so H of a feature
+// row is computed once and kept in registers while the walk stays on that row: an up-sampled RoI (14 bin rows over ~10-20
+// feature rows) touches ~p + 1 rows instead of 2p, 2 x K loads per NEW row instead of 4 per bin (-40 % L1/TEX wavefronts;
+// the column-stationary kernel above was L1/TEX- and latency-bound at 76 % of HBM with DRAM traffic already at the algorithmic
+// minimum).  Row decisions are warp-uniform (one RoI per CTA).  K float4 per thread keep 2K..4K loads in flight.
+// ------------------------------------------------------------------------------------------------
+template <int POOL, int K>
+__global__ void __launch_bounds__(256) roialign_fwd_nhwc_row_kernel(const RoiParams p) {
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
+    static_assert(POOL <= 16, "one slot per bin column");
+    constexpr int kCh = 64 * K;  // channels per CTA
+    const int chunks = (p.C + kCh - 1) / kCh;
+    const int n = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x - n * chunks) * kCh;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps(p, ctx, box, POOL, POOL, s_ty, s_tx);
+    __syncthreads();
+
+    const int lane = tid & 15, x = tid >> 4;
+    if (x >= POOL) return;
+    const TapS tx = s_tx[x];
+    const float4 ext = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+    bool live[K];
+    const float* slo[K];
+    const float* shi[K];
+    float* out[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = c0 + 64 * k + 4 * lane;
+        live[k] = c < C;                                  // C % 4 == 0 is guaranteed by the launcher
+        const int cs = live[k] ? c : 0;
+        slo[k] = ctx.base + cs + (unsigned)tx.lo;
+        shi[k] = ctx.base + cs + (unsigned)tx.hi;
+        out[k] = p.crops + ((size_t)n * (POOL * POOL) + x) * C + cs;
+    }
+    const unsigned long long nz = pack2(p.negzero, p.negzero), x2 = pack2(tx.lerp, tx.lerp);
+
+    // horizontal blend of one feature row (element offset `row`) for the thread's K x 4 channels
+    auto hblend = [&](unsigned row, float4 (&H)[K]) {
+        float4 a[K], b[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (live[k]) {
+                a[k] = ldg_f4(slo[k] + row);
+                b[k] = ldg_f4(shi[k] + row);
+            } else {
+                a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            unpack2(lerp2(pack2(a[k].x, a[k].y), pack2(b[k].x, b[k].y), x2, nz), H[k].x, H[k].y);
+            unpack2(lerp2(pack2(a[k].z, a[k].w), pack2(b[k].z, b[k].w), x2, nz), H[k].z, H[k].w);
+        }
+    };
+
+    int ra = -1, rb = -1;
+    float4 Ha[K], Hb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) Ha[k] = Hb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+    for (int y = 0; y < POOL; ++y) {
+        const TapS ty = s_ty[y];  // warp-uniform
+        const bool in = ty.valid && tx.valid;
+        if (ty.valid && tx.valid) {
+            if (ty.lo == rb) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Ha[k] = Hb[k];
+                ra = rb;
+                rb = -1;
+            } else if (ty.lo != ra) {
+                hblend((unsigned)ty.lo, Ha);
+                ra = ty.lo;
+            }
+            if (ty.hi == ra) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Hb[k] = Ha[k];
+                rb = ra;
+            } else if (ty.hi != rb) {
+                hblend((unsigned)ty.hi, Hb);
+                rb = ty.hi;
+            }
+        }
+        const unsigned long long y2 = pack2(ty.lerp, ty.lerp);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float4 v = ext;
+            if (in) {
+                unpack2(lerp2(pack2(Ha[k].x, Ha[k].y), pack2(Hb[k].x, Hb[k].y), y2, nz), v.x, v.y);
+                unpack2(lerp2(pack2(Ha[k].z, Ha[k].w), pack2(Hb[k].z, Hb[k].w), y2, nz), v.z, v.w);
+            }
+            if (live[k]) stg_f4_stream(out[k] + (unsigned)(y * POOL * C), v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, channels-last in and out, TMA-pipelined (the mask head's 14x14 at C * 4 bytes per pixel a multiple of 16).
+//
+// In channels-last memory the footprint of a RoI on ONE feature row - pixels x_min .. x_max, all C channels - is one
+// contiguous run of ncols * C * 4 bytes (15 KB for a typical 15-column footprint at C = 256), and one output row of the crop
+// (p bins x C channels) is one contiguous run of p * C * 4 bytes (14 KB).  So the whole data movement of a RoI is a few dozen
+// large 1-D bulk copies, and the SM's load/store pipe only ever touches shared memory:
+//
+//   producer  one thread.  Walks the RoI's feature rows in the order the blend needs them (the row list is built once per CTA
+//             by the same walk the consumers do) and issues one cp.async.bulk global -> shared per row into a ring of slots,
+//             each tracked by a "full" mbarrier (expect_tx = row bytes); it re-uses a slot when the consumers' "empty"
+//             mbarrier of that slot completes.  The ring is 64 KB: 2 .. 8 rows in flight per CTA, two CTAs per SM.
+//   consumers 256 threads, thread = (bin column, 4-channel lane), C / 64 channel quarters each.  Wait for the row, read their two
+//             taps (x_lo, x_hi) from the slot, blend horizontally - H(r) exactly as crop_cpu.cpp:107-108 - release the slot,
+//             and keep H of the current and previous row in registers (the separable form of the row-walking kernel above,
+//             bit-identical).  Every finished output row is staged in shared memory in the output's own order and leaves as
+//             ONE bulk copy shared -> global with an L2 evict-first hint (three staging rows: the store of row y is still
+//             reading while row y + 1 is blended).
+//
+// DRAM sees long sequential bursts in both directions instead of 256-byte pieces from four CTAs per RoI; nothing waits on a
+// register load.  RoIs whose footprint is wider than the ring allows (ncols * C * 4 * 2 > ring) take the in-kernel fallback:
+// the column-stationary register path, chunk by chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaRingBytes = 64 * 1024;
+constexpr int kTmaMaxSlots = 8;
+constexpr int kTmaOutBufs = 3;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(288) roialign_fwd_nhwc_tma_kernel(const RoiParams p) {
+    constexpr int kMaxQ = 4;  // channel quarters of 64 per thread: C <= 256
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float* ring = reinterpret_cast<float*>(s_raw);                                    // [slots][ncols][C]
+    float* outb = reinterpret_cast<float*>(s_raw + kTmaRingBytes);                    // [kTmaOutBufs][POOL][C]
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
+    __shared__ int s_rows[2 * POOL];     // element offsets (row * W * C) of the feature rows, in consumption order
+    __shared__ int s_nrows, s_xmin, s_ncols;
+    __shared__ __align__(8) uint64_t s_full[kTmaMaxSlots], s_empty[kTmaMaxSlots];
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps(p, ctx, box, POOL, POOL, s_ty, s_tx);
+    __syncthreads();
+    if (tid == 0) {
+        int xmin = INT_MAX, xmax = -1;
+        for (int x = 0; x < POOL; ++x)
+            if (s_tx[x].valid) {
+                xmin = min(xmin, s_tx[x].lo);
+                xmax = max(xmax, s_tx[x].hi);
+            }
+        int nr = 0;
+        if (xmax >= 0) {  // the walk of the consumers, rows only: which feature row is fetched when
+            int ra = -1, rb = -1;
+            for (int y = 0; y < POOL; ++y) {
+                const TapS ty = s_ty[y];
+                if (!ty.valid) continue;
+                if (ty.lo == rb) { ra = rb; rb = -1; }
+                else if (ty.lo != ra) { s_rows[nr++] = ty.lo; ra = ty.lo; }
+                if (ty.hi == ra) rb = ra;
+                else if (ty.hi != rb) { s_rows[nr++] = ty.hi; rb = ty.hi; }
+            }
+        }
+        s_nrows = nr;
+        s_xmin = (xmax >= 0) ? xmin : 0;          // element offset (x * C)
+        s_ncols = (xmax >= 0) ? (xmax - xmin) / C + 1 : 0;
+        for (int i = 0; i < kTmaMaxSlots; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 8);            // one arrival per consumer warp
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int nrows = s_nrows, ncols = s_ncols, xmin = s_xmin;
+    const uint32_t row_bytes = (uint32_t)ncols * (uint32_t)C * 4u;
+    int slots = row_bytes ? (int)(kTmaRingBytes / row_bytes) : kTmaMaxSlots;
+    if (slots > kTmaMaxSlots) slots = kTmaMaxSlots;
+    const bool piped = slots >= 2;                // else: footprint too wide for the ring -> register path below
+    const int P2 = POOL * POOL;
+    float* crop = p.crops + (size_t)n * P2 * C;
+
+    if (!piped) {  // ---- fallback: column-stationary register path over all channels (rare: very wide boxes)
+        if (tid >= 256) return;
+        const int lane = tid & 15, slot = tid >> 4;
+        const float4 ext = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+        for (int c = 4 * lane; c < C; c += 64) {
+            for (int b = slot; b < P2; b += 16) {
+                const int y = b / POOL, x = b - y * POOL;
+                const TapS ty = s_ty[y], tx = s_tx[x];
+                float4 v = ext;
+                if (ty.valid && tx.valid) {
+                    const float* src = ctx.base + c;
+                    v = bilerp4(ldg_f4(src + (ty.lo + tx.lo)), ldg_f4(src + (ty.lo + tx.hi)), ldg_f4(src + (ty.hi + tx.lo)),
+                                ldg_f4(src + (ty.hi + tx.hi)), tx.lerp, ty.lerp, p.negzero);
+                }
+                stg_f4_stream(crop + (size_t)b * C + c, v);
+            }
+        }
+        return;
+    }
+
+    if (tid >= 256) {  // ---- producer
+        if (tid == 256) {
+            const float* src = ctx.base + xmin;
+            for (int i = 0; i < nrows; ++i) {
+                const int sl = i % slots;
+                const int k = i / slots;
+                if (k > 0) mbar_wait(&s_empty[sl], (uint32_t)((k - 1) & 1));
+                mbar_expect_tx(&s_full[sl], row_bytes);
+                bulk_g2s(reinterpret_cast<unsigned char*>(ring) + (size_t)sl * row_bytes, src + (unsigned)s_rows[i], row_bytes, &s_full[sl]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const int lane = tid & 15, x = tid >> 4, wlane = tid & 31;
+    const bool colv = x < POOL;
+    const TapS tx = s_tx[colv ? x : 0];
+    const bool x_in = colv && tx.valid;
+    const int nq = (C + 63) / 64;                                     // <= kMaxQ by the launcher
+    const int jlo = x_in ? (tx.lo - xmin) : 0, jhi = x_in ? (tx.hi - xmin) : 0;   // element offsets inside a ring row
+    const unsigned long long nz = pack2(p.negzero, p.negzero), x2 = pack2(tx.lerp, tx.lerp);
+    const float4 ext = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    int next = 0;  // next entry of s_rows to consume
+    auto take_row = [&](float4 (&H)[kMaxQ]) {
+        const int sl = next % slots;
+        mbar_wait(&s_full[sl], (uint32_t)((next / slots) & 1));
+        const float* row = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)sl * row_bytes);
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            const int c = 64 * q + 4 * lane;
+            if (q < nq && c < C && x_in) {
+                const float4 a = *reinterpret_cast<const float4*>(row + jlo + c);
+                const float4 b = *reinterpret_cast<const float4*>(row + jhi + c);
+                unpack2(lerp2(pack2(a.x, a.y), pack2(b.x, b.y), x2, nz), H[q].x, H[q].y);
+                unpack2(lerp2(pack2(a.z, a.w), pack2(b.z, b.w), x2, nz), H[q].z, H[q].w);
+            }
+        }
+        __syncwarp();
+        if (wlane == 0) mbar_arrive(&s_empty[sl]);
+        ++next;
+    };
+
+    int ra = -1, rb = -1;
+    float4 Ha[kMaxQ], Hb[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) Ha[q] = Hb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool any_col = ncols > 0;
+
+#pragma unroll 1
+    for (int y = 0; y < POOL; ++y) {
+        const TapS ty = s_ty[y];  // CTA-uniform
+        if (ty.valid && any_col) {
+            if (ty.lo == rb) {
+#pragma unroll
+                for (int q = 0; q < kMaxQ; ++q) Ha[q] = Hb[q];
+                ra = rb;
+                rb = -1;
+            } else if (ty.lo != ra) {
+                take_row(Ha);
+                ra = ty.lo;
+            }
+            if (ty.hi == ra) {
+#pragma unroll
+                for (int q = 0; q < kMaxQ; ++q) Hb[q] = Ha[q];
+                rb = ra;
+            } else if (ty.hi != rb) {
+                take_row(Hb);
+                rb = ty.hi;
+            }
+        }
+        float* ob = outb + (size_t)(y % kTmaOutBufs) * POOL * C;
+        if (colv) {
+            const bool in = ty.valid && x_in;
+            const unsigned long long y2 = pack2(ty.lerp, ty.lerp);
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                const int c = 64 * q + 4 * lane;
+                if (q < nq && c < C) {
+                    float4 v = ext;
+                    if (in) {
+                        unpack2(lerp2(pack2(Ha[q].x, Ha[q].y), pack2(Hb[q].x, Hb[q].y), y2, nz), v.x, v.y);
+                        unpack2(lerp2(pack2(Ha[q].z, Ha[q].w), pack2(Hb[q].z, Hb[q].w), y2, nz), v.z, v.w);
+                    }
+                    *reinterpret_cast<float4*>(ob + x * C + c) = v;
+                }
+            }
+        }
+        fence_proxy_async();                             // this thread's row piece -> visible to the async proxy (the bulk store)
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the row is complete in shared memory
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(crop + (size_t)y * POOL * C),
+                         "r"(smem_u32(ob)), "r"((uint32_t)(POOL * C * 4)), "l"(policy)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // at most one store still reading: the buffer written two rows from now (the one of row y - 1) is free by then
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -906,6 +1226,7 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
             for (int k = 0; k < K; ++k) wout[(g * K + k) * P2 + y * POOL + x] = v[k];
         }
     }
+    fence_proxy_async();   // every lane's staged outputs -> visible to the async proxy before lane 0 issues the bulk store
     __syncwarp();
     float* dst = p.crops + ((size_t)n * C + cw0) * P2;
     const uint32_t bytes = (uint32_t)(cc * P2 * sizeof(float));
@@ -1044,6 +1365,57 @@ __global__ void __launch_bounds__(256) roialign_bwd_nchw_kernel(const RoiParams 
     if (ra >= 0) {
         flush(A, ra);
         if (hasB) flush(Bn, ra + W);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Few-channel NCHW crops (the 28x28 mask targets of mrn_samples, model.py:501-502: C = 1, image = [P,1,1024,1024] gt masks):
+// one CTA per (crop, channel plane).  The box and the ph + pw axis taps are computed ONCE per crop (the strided kernel below
+// recomputes both divisions per output scalar); every thread then blends four bins per pass with its 16 tap loads in flight
+// together.  Output runs are contiguous ([n][c][y][x]).  Latency-bound by construction - 784 outputs per crop, taps scattered
+// over a 4 MB mask - so the point is to start all of a crop's loads at once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) crop_plane_fwd_kernel(const RoiParams p) {
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
+    const int C = p.C;
+    const int n = blockIdx.x / C;
+    const int c = blockIdx.x - n * C;
+    const int tid = threadIdx.x;
+    const int ph = p.ph, pw = p.pw, P2 = ph * pw;
+
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps_nchw(ctx, box, ph, pw, s_ty, s_tx);
+    __syncthreads();
+    const float* plane = ctx.base + (size_t)c * ctx.H * ctx.W;
+    float* out = p.crops + ((size_t)n * C + c) * P2;
+    for (int b0 = tid; b0 < P2; b0 += 4 * 256) {
+        float tl[4], tr[4], bl[4], br[4], xl[4], yl[4];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * 256;
+            in[u] = false;
+            if (b < P2) {
+                const int y = b / pw, x = b - y * pw;
+                const TapS ty = s_ty[y], tx = s_tx[x];
+                in[u] = ty.valid && tx.valid;
+                if (in[u]) {
+                    tl[u] = __ldg(plane + ty.lo + tx.lo);
+                    tr[u] = __ldg(plane + ty.lo + tx.hi);
+                    bl[u] = __ldg(plane + ty.hi + tx.lo);
+                    br[u] = __ldg(plane + ty.hi + tx.hi);
+                    xl[u] = tx.lerp;
+                    yl[u] = ty.lerp;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * 256;
+            if (b < P2) out[b] = in[u] ? bilerp(tl[u], tr[u], bl[u], br[u], xl[u], yl[u]) : p.extrap;
+        }
     }
 }
 
@@ -1189,6 +1561,19 @@ static LevelRule make_level_rule(float image_area) {
     return r;
 }
 
+// Which forward kernel serves channels-last 14x14: 0 = column-stationary (round 1), K = row-walking with K x 64 channels per
+// CTA.  Fixed at first use; MRCNN_FWD14 overrides the default for experiments (results are identical).
+static int fwd14_variant() {
+    const char* e = getenv("MRCNN_FWD14");
+    if (e == nullptr) return 0;
+    if (!strcmp(e, "col")) return 0;
+    if (!strcmp(e, "row1")) return 1;
+    if (!strcmp(e, "row4")) return 4;
+    if (!strcmp(e, "row2")) return 2;
+    if (!strcmp(e, "tma")) return 9;
+    return 0;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout, bool backward, cudaStream_t stream) {
@@ -1210,6 +1595,18 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
         if ((long long)p.C * p.lv[l].H * p.lv[l].W >= (1ll << 31)) nchw_fast = false;   // 32-bit element offsets inside one image
     const long long nchw_grid = (long long)p.N * ((p.C + kChunk - 1) / kChunk);
     if (nchw_grid >= (1ll << 31)) nchw_fast = false;
+    // few-channel NCHW forward (mask targets): one CTA per (crop, plane)
+    if (!backward && !nchw_fast && image_layout == MRCNN_NCHW && crops_layout == MRCNN_NCHW && p.C <= 4 && p.ph <= kMaxPool &&
+        p.pw <= kMaxPool && (long long)p.N * p.C < (1ll << 31)) {
+        bool fits = true;
+        for (int l = 0; l < (p.pyramid ? 4 : 1); ++l)
+            if ((long long)p.lv[l].H * p.lv[l].W >= (1ll << 31)) fits = false;
+        if (fits) {
+            crop_plane_fwd_kernel<<<(unsigned)(p.N * p.C), 256, 0, stream>>>(p);
+            MRCNN_LAUNCH_CHECK();
+            return MRCNN_OK;
+        }
+    }
     if (nchw_fast) {
         const size_t smem_n = sizeof(float) * kChunk * (size_t)P2;
 #define MRCNN_LAUNCH_NCHW(KERNEL)                                                                                \
@@ -1252,8 +1649,21 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
                 // pool 7: 128-thread CTAs (7 of 8 slots own a column): 210 -> 178 us, more CTAs resident hide the prologue;
                 // pool 14: 256 threads, 14 of 16 slots; splitting its columns (rows) over two CTAs measured 474 (543) vs 468 us
                 if (ok && p.ph == 7 && p.pw == 7) roialign_fwd_nhwc_col_kernel<7, kLanes, 8><<<(unsigned)flat, 8 * kLanes, 0, stream>>>(p);
-                else if (ok && p.ph == 14 && p.pw == 14)
-                    roialign_fwd_nhwc_col_kernel<14, kLanes, kSlots><<<(unsigned)flat, kThreads, 0, stream>>>(p);
+                else if (ok && p.ph == 14 && p.pw == 14) {
+                    // row-walking kernel, K x 64 channels per CTA (tools/exp_fwd14.py: MRCNN_FWD14 = col | row1 | row2 | row4)
+                    static const int variant = fwd14_variant();
+                    const int K = variant;
+                    const unsigned grid_k = K ? (unsigned)((long long)p.N * ((p.C + 64 * K - 1) / (64 * K))) : 0;
+                    if (variant == 9 && p.C <= 256 && (long long)p.N < (1ll << 31)) {
+                        const size_t smem_t = kTmaRingBytes + (size_t)kTmaOutBufs * 14 * p.C * sizeof(float);
+                        MRCNN_CUDA(cudaFuncSetAttribute(roialign_fwd_nhwc_tma_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                        roialign_fwd_nhwc_tma_kernel<14><<<(unsigned)p.N, 288, smem_t, stream>>>(p);
+                    } else
+                    if (K == 1) roialign_fwd_nhwc_row_kernel<14, 1><<<grid_k, 256, 0, stream>>>(p);
+                    else if (K == 2) roialign_fwd_nhwc_row_kernel<14, 2><<<grid_k, 256, 0, stream>>>(p);
+                    else if (K == 4) roialign_fwd_nhwc_row_kernel<14, 4><<<grid_k, 256, 0, stream>>>(p);
+                    else roialign_fwd_nhwc_col_kernel<14, kLanes, kSlots><<<(unsigned)flat, kThreads, 0, stream>>>(p);
+                }
                 else MRCNN_LAUNCH_NHWC((roialign_fwd_nhwc_kernel<0, true>));
             } else MRCNN_DISPATCH_POOL(roialign_fwd_nhwc_kernel, false);
         } else {

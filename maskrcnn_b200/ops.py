@@ -116,6 +116,39 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+class _NoGuard(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Device guard for a launch: torch.cuda.device(...) costs several microseconds per use, more than the argument checks of
+    a small call; when the tensor already lives on the current device (the single-GPU-per-process case) nothing is switched."""
+    if device.type != "cuda" or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
+_GEOM = {}
+
+
+def _geometry(fms):
+    """(Hs, Ws) ctypes arrays of a pyramid, cached by shape: a batch-1 inference call issues a ~20 us kernel, so building two
+    ctypes arrays per call is measurable."""
+    key = (fms[0].shape[2], fms[0].shape[3], fms[1].shape[2], fms[1].shape[3], fms[2].shape[2], fms[2].shape[3], fms[3].shape[2],
+           fms[3].shape[3])
+    g = _GEOM.get(key)
+    if g is None:
+        g = _GEOM[key] = (_lib.i4(key[0::2]), _lib.i4(key[1::2]))
+    return g
+
+
 def check_device_errors():
     """Synchronises and raises if a kernel saw a box_index outside [0, batch) since the last call
     (the reference exit(-1)s, cpu/crop_cpu.cpp:47-50)."""
@@ -253,6 +286,12 @@ def _check_pyramid_args(feature_maps, boxes, box_ind):
 def _pyramid_layout(fms):
     if len(fms) != 4:
         raise ValueError("expected the four pyramid levels P2..P5")
+    cl = torch.channels_last
+    # the two common cases first: every level channels-last (and not also NCHW-dense), or every level NCHW-contiguous
+    if all(f.is_contiguous(memory_format=cl) and not f.is_contiguous() for f in fms):
+        return list(fms), NHWC
+    if all(f.is_contiguous() and not (f.size(2) == 1 and f.size(3) == 1) for f in fms):
+        return list(fms), NCHW
     outs, layouts = zip(*[_layout4(f) for f in fms])
     outs = list(outs)
     if len(set(layouts)) != 1:  # mixed: settle on channels-last (the fast path)
@@ -272,27 +311,29 @@ class _PyramidRoiAlign(torch.autograd.Function):
         out = _empty4((N, C, pool, pool), ol, fms[0])
         Hs = [f.shape[2] for f in fms]
         Ws = [f.shape[3] for f in fms]
-        if N:
-            with torch.cuda.device(out.device):
-                check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws),
-                                                          B, C, fl, boxes.data_ptr(), _ptr(box_ind), N, pool,
-                                                          float(image_area), out.data_ptr(), ol, None, _stream()))
         ctx.save_for_backward(boxes, box_ind)
         ctx.meta = (Hs, Ws, B, C, fl, pool, float(image_area), offsets)
         ctx.plan = None
         if (BACKWARD_PLANNING and BACKWARD_ALGORITHM != "scatter" and any(ctx.needs_input_grad[6:]) and fl == NHWC and ol == NHWC
                 and C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets):
-            # the backward's item queues need the boxes only: build them next to the forward kernel, on a side stream
+            # the backward's item queues need the boxes only: build them on a side stream NEXT TO the forward kernel.  The side
+            # stream forks here, before the forward is enqueued, so it waits for the boxes (and the previous user of the
+            # workspace block) and not for the forward itself.
             with torch.cuda.device(out.device):
                 cur, side = torch.cuda.current_stream(), _plan_stream(out.device)
                 ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(_lib.i4(Hs), _lib.i4(Ws), B, N, pool)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
-                side.wait_stream(cur)       # boxes (and the previous user of the workspace block) are ready
+                side.wait_stream(cur)
                 check(lib.mrcnn_pyramid_roi_align_backward_plan(_lib.i4(Hs), _lib.i4(Ws), B, C, boxes.data_ptr(), _ptr(box_ind), N,
                                                                 pool, float(image_area), ws.data_ptr(), ws_bytes, side.cuda_stream))
                 for t in (ws, boxes) + ((box_ind,) if box_ind is not None else ()):
                     t.record_stream(side)
                 ctx.plan = (ws, ws_bytes, side.record_event())
+        if N:
+            with torch.cuda.device(out.device):
+                check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws),
+                                                          B, C, fl, boxes.data_ptr(), _ptr(box_ind), N, pool,
+                                                          float(image_area), out.data_ptr(), ol, None, _stream()))
         return out
 
     @staticmethod
@@ -333,11 +374,15 @@ def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_
     model.py:358), box_ind [N] int32 image index or None (all image 0).  Returns [N,C,pool,pool] in box order;
     memory format follows the feature maps unless out_channels_last is given.
     rois_per_image: optional host-side list of B counts (or one int) stating that boxes are grouped by image in
-    order (box_ind, if given, must agree); lets the backward clear + scatter image by image (L2-resident)."""
+    order; box_ind is then derived from the counts and must not be passed as well; lets the backward clear + scatter image
+    by image (L2-resident)."""
     feature_maps = list(feature_maps)
     _check_pyramid_args(feature_maps, boxes, box_ind)
-    boxes = boxes.detach().contiguous()
-    if box_ind is not None:
+    if boxes.requires_grad:
+        boxes = boxes.detach()
+    if not boxes.is_contiguous():
+        boxes = boxes.contiguous()
+    if box_ind is not None and not box_ind.is_contiguous():
         box_ind = box_ind.contiguous()
     image_area = float(image_shape[0] * image_shape[1])  # model.py:331
     ol = None if out_channels_last is None else (NHWC if out_channels_last else NCHW)
@@ -348,7 +393,11 @@ def pyramid_roi_align(feature_maps, boxes, box_ind, pool_size, image_shape, out_
         if len(counts) != B or sum(counts) != boxes.size(0):
             raise ValueError("rois_per_image must list one count per image and sum to the number of boxes")
         offsets = tuple(int(v) for v in np.concatenate([[0], np.cumsum(counts)]))
-        if box_ind is None and B > 1:
+        if box_ind is not None:
+            # the image-by-image backward scatters box i into the image the counts say, the forward reads the image box_ind
+            # says: one source of truth, or a mismatch would silently put gradients into another image than the forward read
+            raise ValueError("give either box_ind or rois_per_image (which implies box_ind = repeat(arange(B), counts)), not both")
+        if B > 1:
             box_ind = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=boxes.device),
                                               torch.tensor(counts, device=boxes.device))
     if not (torch.is_grad_enabled() and any(f.requires_grad for f in feature_maps)):
@@ -364,12 +413,16 @@ def _pyramid_forward_nograd(boxes, box_ind, pool, image_area, out_layout, featur
     B, C = f0.size(0), f0.size(1)
     N = boxes.size(0)
     ol = fl if out_layout is None else out_layout
-    out = _empty4((N, C, pool, pool), ol, f0)
+    out = torch.empty((N, C, pool, pool), dtype=torch.float32, device=f0.device,
+                      memory_format=torch.channels_last if ol == NHWC else torch.contiguous_format)
     if N:
-        with torch.cuda.device(out.device):
-            check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4([f.size(2) for f in fms]),
-                                                      _lib.i4([f.size(3) for f in fms]), B, C, fl, boxes.data_ptr(), _ptr(box_ind), N,
-                                                      pool, image_area, out.data_ptr(), ol, None, _stream()))
+        Hs, Ws = _geometry(fms)
+        with _on(f0.device):
+            rc = lib.mrcnn_pyramid_roi_align_forward(_lib._vp4(fms[0].data_ptr(), fms[1].data_ptr(), fms[2].data_ptr(), fms[3].data_ptr()),
+                                                     Hs, Ws, B, C, fl, boxes.data_ptr(), None if box_ind is None else box_ind.data_ptr(),
+                                                     N, pool, image_area, out.data_ptr(), ol, None, _stream())
+        if rc:
+            check(rc)
     return out
 
 
@@ -380,7 +433,7 @@ def roi_align(inputs, pool_size, image_shape):
     if boxes.dim() == 3:
         if boxes.size(0) != 1:
             raise ValueError("roi_align drop-in is batch-1 like the reference (model.py:296); use pyramid_roi_align")
-        boxes = boxes.squeeze(0)
+        boxes = boxes[0]
     fms = [f if f.dim() == 4 else f.unsqueeze(0) for f in inputs[1:5]]
     return pyramid_roi_align(fms, boxes, None, pool_size, image_shape)
 
@@ -507,7 +560,12 @@ def rpn_detect(self, rpn_feature_maps):
     """Drop-in for MaskRCNN.rpn_detect (model.py:1294-1304): runs the RPN head's three convolutions per level on stock
     PyTorch / cuDNN (self.rpn: padding, conv_shared, relu, conv_class, conv_bbox - model.py:600-641) and replaces the
     per-level permute / contiguous / view / softmax and the three torch.cat by one rpn_pack launch.  Returns
-    (rpn_class_logits, rpn_class, rpn_bbox) like the reference."""
+    (rpn_class_logits, rpn_class, rpn_bbox) like the reference.
+
+    DIFFERENCE FROM THE REFERENCE: rpn_class (the softmax) is returned without a gradient path - requires_grad is False.  In
+    the reference it is an ordinary differentiable tensor, but nothing differentiates it: the RPN losses read
+    rpn_class_logits and rpn_bbox (model.py:652-718) and the proposal layer detaches.  A loss built on rpn_class would get no
+    gradient here; build it on rpn_class_logits (torch.softmax(rpn_class_logits, 2) is differentiable and equal)."""
     rpn = self.rpn
     logits, bboxes = [], []
     for p in rpn_feature_maps:

@@ -170,6 +170,8 @@ def test_pyramid_roi_align_marshalling(fake):
         ops.pyramid_roi_align(fms, boxes, None, 7, (64, 64, 3), rois_per_image=[2, 2])
     with pytest.raises(ValueError):
         ops.pyramid_roi_align(fms, boxes, None, 7, (64, 64, 3), rois_per_image=[5])
+    with pytest.raises(ValueError):      # one source of truth for the image of a box: the counts OR box_ind, never both
+        ops.pyramid_roi_align(fms, boxes, ind, 7, (64, 64, 3), rois_per_image=[2, 3])
     with pytest.raises(ValueError):
         ops.pyramid_roi_align(fms, boxes, ind[:4], 7, (64, 64, 3))
     with pytest.raises(ValueError):
