@@ -952,6 +952,8 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// (No minimum-blocks bound: forcing 24 / 28 / 32 CTAs per SM - 80 / 72 / 64 registers - spills and measured 0.61 / 0.75 / 0.89 ms
+// against 0.58 ms for the configs[3] 14x14 backward; U = 3 or ST = 6 are slower too.  profiles/r02_experiments.txt)
 template <int NV, int U, int ST, bool kAccumulate>
 __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherParams p) {
     __shared__ QItem s_items[32 + U];
@@ -1561,15 +1563,14 @@ static LevelRule make_level_rule(float image_area) {
     return r;
 }
 
-// Which forward kernel serves channels-last 14x14: 0 = column-stationary (round 1), K = row-walking with K x 64 channels per
-// CTA.  Fixed at first use; MRCNN_FWD14 overrides the default for experiments (results are identical).
+// Which forward kernel serves channels-last 14x14: 0 = column-stationary (the default: fastest measured), 2 = row-walking with
+// 128 channels per CTA, 9 = TMA ring pipeline.  Fixed at first use; MRCNN_FWD14 selects the alternatives for experiments and for
+// the bit-identity test (results are identical).
 static int fwd14_variant() {
     const char* e = getenv("MRCNN_FWD14");
     if (e == nullptr) return 0;
     if (!strcmp(e, "col")) return 0;
-    if (!strcmp(e, "row1")) return 1;
-    if (!strcmp(e, "row4")) return 4;
-    if (!strcmp(e, "row2")) return 2;
+    if (!strcmp(e, "row")) return 2;
     if (!strcmp(e, "tma")) return 9;
     return 0;
 }
@@ -1650,18 +1651,16 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
                 // pool 14: 256 threads, 14 of 16 slots; splitting its columns (rows) over two CTAs measured 474 (543) vs 468 us
                 if (ok && p.ph == 7 && p.pw == 7) roialign_fwd_nhwc_col_kernel<7, kLanes, 8><<<(unsigned)flat, 8 * kLanes, 0, stream>>>(p);
                 else if (ok && p.ph == 14 && p.pw == 14) {
-                    // row-walking kernel, K x 64 channels per CTA (tools/exp_fwd14.py: MRCNN_FWD14 = col | row1 | row2 | row4)
+                    // MRCNN_FWD14 = col (default) | row | tma: the measured alternatives (profiles/r02_experiments.txt), bit-identical
                     static const int variant = fwd14_variant();
-                    const int K = variant;
+                    const int K = (variant == 2) ? 2 : 0;
                     const unsigned grid_k = K ? (unsigned)((long long)p.N * ((p.C + 64 * K - 1) / (64 * K))) : 0;
                     if (variant == 9 && p.C <= 256 && (long long)p.N < (1ll << 31)) {
                         const size_t smem_t = kTmaRingBytes + (size_t)kTmaOutBufs * 14 * p.C * sizeof(float);
                         MRCNN_CUDA(cudaFuncSetAttribute(roialign_fwd_nhwc_tma_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
                         roialign_fwd_nhwc_tma_kernel<14><<<(unsigned)p.N, 288, smem_t, stream>>>(p);
                     } else
-                    if (K == 1) roialign_fwd_nhwc_row_kernel<14, 1><<<grid_k, 256, 0, stream>>>(p);
-                    else if (K == 2) roialign_fwd_nhwc_row_kernel<14, 2><<<grid_k, 256, 0, stream>>>(p);
-                    else if (K == 4) roialign_fwd_nhwc_row_kernel<14, 4><<<grid_k, 256, 0, stream>>>(p);
+                    if (K == 2) roialign_fwd_nhwc_row_kernel<14, 2><<<grid_k, 256, 0, stream>>>(p);
                     else roialign_fwd_nhwc_col_kernel<14, kLanes, kSlots><<<(unsigned)flat, kThreads, 0, stream>>>(p);
                 }
                 else MRCNN_LAUNCH_NHWC((roialign_fwd_nhwc_kernel<0, true>));

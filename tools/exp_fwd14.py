@@ -31,5 +31,5 @@ if __name__ == "__main__":
         ref = "/tmp/exp_fwd14_ref.pt"
         if os.path.exists(ref):
             os.remove(ref)
-        for v in (sys.argv[1:] or ["col", "tma"]):
+        for v in (sys.argv[1:] or ["col", "row", "tma"]):
             subprocess.call([sys.executable, os.path.abspath(__file__), "one"], env=dict(os.environ, MRCNN_FWD14=v, EXP_REF=ref))
