@@ -1148,38 +1148,89 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
     win = torch.tensor([[0., 0., IMAGE, IMAGE]], device=dev).repeat(Bl, 1)
     ind = (torch.arange(b, e, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(D)   # image i reads pyramid i % 16
 
+    ex = mdist.DetectionExchange(TOTAL, D)
+    L = wl.L
+    masks_in = torch.empty((Bl * D, CHANNELS, 14, 14), device=dev, memory_format=torch.channels_last)
+    fmp = L.vp4([f.data_ptr() for f in wl.fm])
+
     def run():
-        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
-        masks_in = m.pyramid_roi_align(wl.fm, (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4), ind, 14, (IMAGE, IMAGE, 3))
-        all_dets, all_counts = mdist.gather_detections(dets, counts, n_images=TOTAL)
+        """Three launches: detection layer fused with the sending half of the exchange (it also writes the mask head's RoIs),
+        the 14x14 RoIAlign of the detections, the collecting half."""
+        ex.run(rois, probs, deltas, win, 0.0, 0.3, ind_offset=b, ind_mod=wl.batch)
+        L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC, ex.mask_boxes.data_ptr(),
+                                                      ex.mask_box_ind.data_ptr(), Bl * D, 14, wl.area, masks_in.data_ptr(), L.NHWC, None, wl._s()))
+        all_dets, all_counts = ex.collect()
         return masks_in, all_dets, all_counts
+
+    def run_nccl():
+        """Round 1's path for comparison: detection layer, torch glue, RoIAlign through ops, torch.cat + all_gather_into_tensor."""
+        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
+        mi = m.pyramid_roi_align(wl.fm, (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4), ind, 14, (IMAGE, IMAGE, 3))
+        all_dets, all_counts = mdist.gather_detections(dets, counts, n_images=TOTAL)
+        return mi, all_dets, all_counts
 
     for _ in range(3):
         run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    # every iteration is timed on its own (events on the launching stream) and the MEDIAN is reported: the path is a dozen
-    # small launches per iteration, and one host hiccup (the pool's boxes share their cores) in a 20-iteration window
-    # otherwise decides the number (seen twice: 2.4 and 5.3 ms against the usual 0.4 - 0.7); mean and max are kept beside it
+    # the three launches as one CUDA graph per rank (every rank replays the same number of times)
+    step, mode = run, "eager launches"
+    try:
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            run()
+        torch.cuda.current_stream().wait_stream(cap)
+        step, mode = graph.replay, "one CUDA graph replay (3 kernels)"
+    except Exception as e_:
+        sys.stderr.write("detection path: graph capture failed (%s: %s)\n" % (type(e_).__name__, e_))
+    ok_flag = torch.tensor([1 if step is not run else 0], device=dev)
+    if world > 1:   # all ranks must agree (a rank replaying a graph while another launches eagerly would still be correct, but keep it uniform)
+        dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+    if int(ok_flag.item()) == 0:
+        step, mode = run, "eager launches"
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    # every iteration is timed on its own (events on the launching stream) and the MEDIAN is reported: one host hiccup (the
+    # pool's boxes share their cores) in a 20-iteration window otherwise decides the number; mean and max are kept beside it
     iters = 20
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     evs[0].record()
     for i in range(iters):
-        out = run()
+        step()
         evs[i + 1].record()
     torch.cuda.synchronize()
+    out = (masks_in, ex.dets_all, ex.counts_all)
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
     ms, ms_mean, ms_max = per[iters // 2], sum(per) / iters, per[-1]
+    if world > 1:
+        dist.barrier()
 
-    # the rank-local part and the exchange timed apart (means of 20 back-to-back calls each, max over ranks)
+    # SURVEY 8(e): the rank-local part and the exchange timed apart
     def local_part():
-        dets, counts = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
-        m.pyramid_roi_align(wl.fm, (dets[:, :, :4] / float(IMAGE)).reshape(-1, 4), ind, 14, (IMAGE, IMAGE, 3))
-        return dets, counts
+        m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
+        L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC, ex.mask_boxes.data_ptr(),
+                                                      ex.mask_box_ind.data_ptr(), Bl * D, 14, wl.area, masks_in.data_ptr(), L.NHWC, None, wl._s()))
     ms_local = wl.time_op(local_part, iters=iters) * 1e3
-    dets_l, counts_l = local_part()
-    ms_gather = wl.time_op(lambda: mdist.gather_detections(dets_l, counts_l, n_images=TOTAL), iters=iters) * 1e3
+
+    def exchange_only():         # what the exchange adds to the rank-local part: the fused epilogue's peer stores + the collect kernel
+        ex.run(rois, probs, deltas, win, 0.0, 0.3, ind_offset=b, ind_mod=wl.batch)
+        ex.collect()
+    t_ex = wl.time_op(exchange_only, iters=iters) * 1e3
+    t_det = wl.time_op(lambda: m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D), iters=iters) * 1e3
+    ms_gather = max(t_ex - t_det, 0.0)
+    if world > 1:
+        dist.barrier()
+    ms_nccl = wl.time_op(run_nccl, iters=iters) * 1e3
+    dets_l, counts_l = m.detection_layer(rois, probs, deltas, win, 0.0, 0.3, D)
+    ms_nccl_gather = wl.time_op(lambda: mdist.gather_detections(dets_l, counts_l, n_images=TOTAL), iters=iters) * 1e3
+    nccl_dets, nccl_counts = mdist.gather_detections(dets_l, counts_l, n_images=TOTAL)
+    same_as_nccl = bool(torch.equal(nccl_dets, ex.dets_all)) and bool(torch.equal(nccl_counts, ex.counts_all))
     # G-invariance (SURVEY 4 / 8e): the gathered [64, D, 6] must equal, bit for bit and in image order, what ONE GPU computes
     # image by image.  Rank 0 recomputes all 64 images one call at a time (batch 1, no sharding, no collective) and compares.
     g_invariant = None
@@ -1194,13 +1245,20 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
             ok = ok and bool(torch.equal(di[0], all_dets[i])) and int(ci[0]) == int(all_counts[i])
         g_invariant = bool(ok)
     if world > 1:
-        t = torch.tensor([ms, ms_mean, ms_max, ms_local, ms_gather], device=dev)
+        t = torch.tensor([ms, ms_mean, ms_max, ms_local, ms_gather, ms_nccl, ms_nccl_gather, 0.0 if same_as_nccl else 1.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_mean, ms_max, ms_local, ms_gather = (float(v) for v in t.tolist())
+        ms, ms_mean, ms_max, ms_local, ms_gather, ms_nccl, ms_nccl_gather, bad = (float(v) for v in t.tolist())
+        same_as_nccl = bad == 0.0
     return {"config": "configs[4]: 64 images sharded over %d GPU(s): detection layer + 14x14 mask RoIAlign + one all-gather" % world,
             "images_per_s": TOTAL / (ms * 1e-3), "ms_per_64_images": ms, "ms_per_64_images_mean": ms_mean, "ms_per_64_images_max": ms_max,
-            "statistic": "median of %d iterations, max over ranks" % iters, "scaling": "strong",
+            "statistic": "median of %d iterations, max over ranks" % iters, "scaling": "strong", "launch": mode,
             "ms_rank_local_part": ms_local, "ms_all_gather": ms_gather,
+            "exchange": "fused: the detection kernel stores every image's packed row into all ranks' receive buffers (NVLink peer stores, "
+                        "%d B per image per peer) and raises a flag; mrcnn_detection_collect waits per image and copies out.  ms_all_gather = "
+                        "(fused detection + collect) - (plain detection layer), eager, mean of %d" % ((D * 6 + 1) * 4, iters),
+            "nvlink_bytes_per_rank": int((world - 1) * Bl * (D * 6 + 1) * 4),
+            "nccl_path": {"ms_per_64_images": ms_nccl, "ms_all_gather": ms_nccl_gather, "identical_results": same_as_nccl,
+                          "note": "round 1's path: detection layer + torch glue + ops RoIAlign + torch.cat / all_gather_into_tensor, eager, mean"},
             "gathered_images": int(out[1].shape[0]), "mean_detections": float(out[2].float().mean().item()),
             "g_invariant": g_invariant,
             "g_invariant_check": "rank 0: gathered detections of all 64 images == the same images computed one by one on one GPU "

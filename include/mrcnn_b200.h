@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 4
+#define MRCNN_ABI_VERSION 5
 
 #define MRCNN_OK 0
 #define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */
@@ -226,6 +226,34 @@ MRCNN_API int mrcnn_detection_layer(const float* rois, const float* probs, const
                           const float* std4_host, float height, float width,
                           float* dets_out, int32_t* counts_out, int32_t* index_out,
                           void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+
+/* ---- detection layer fused with what follows it (BASELINE configs[4]: 64 images sharded over the GPUs of one box) ----------
+ * Replaces, on top of mrcnn_detection_layer: `mrn_rois = mrn_boxes.float() * 1.0 / h` (model.py:1188), the box_ind the mask
+ * head's roi_align needs, and - there is no counterpart in the single-GPU reference - the all-gather of the detections over
+ * the ranks, as ONE kernel: every CTA (= image) stores its packed row [max_inst * 6 detections, count] straight into the
+ * exchange buffer of every rank through peer-mapped pointers (NVLink / NVSwitch stores), the rank's last CTA raises the rank's
+ * flag on every rank (release at system scope).  mrcnn_detection_collect is the consuming half: per image, wait for the owner
+ * rank's flag (acquire load from local memory) and copy the row into [total, max_inst, 6] / [total], image order = rank order
+ * (contiguous balanced shards: the first total % world ranks own one image more).
+ *
+ * peer_bufs_host: HOST array of `world` device pointers, buffer of rank r mapped into this process (own buffer at [rank]); each
+ * holds mrcnn_detection_exchange_bytes() bytes, zero-initialised once: [2 parities][total][max_inst * 6 + 1] floats, then [world]
+ * uint32 flags.  state: two int32 of LOCAL device memory, zero-initialised once ([0] epoch, [1] CTA counter).  Successive
+ * exchanges alternate parity, so a rank may run one exchange ahead of its peers; the results of exchange k must be consumed
+ * (stream order is enough) before this rank issues exchange k + 2.  world == 0: no exchange (peer_bufs_host / state may be
+ * NULL).  mask_boxes [B * max_inst, 4] / mask_box_ind [B * max_inst] (= (ind_offset + image) % ind_mod) may be NULL.
+ * Every rank must issue the same sequence of exchanges; a rank that stops leaves the others spinning in the collect kernel. */
+MRCNN_API size_t mrcnn_detection_exchange_bytes(int world, int total_images, int max_inst);
+MRCNN_API int mrcnn_detection_layer_exchange(const float* rois, const float* probs, const float* deltas,
+                          const float* windows, int B, int N, int NC,
+                          float min_confidence, float nms_threshold, int max_inst,
+                          const float* std4_host, float height, float width,
+                          float* dets_out, int32_t* counts_out,
+                          float* mask_boxes, int32_t* mask_box_ind, int ind_offset, int ind_mod,
+                          void* const* peer_bufs_host, int world, int rank, int image_offset, int total_images,
+                          int32_t* state, void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
+MRCNN_API int mrcnn_detection_collect(const void* local_buf, int world, int total_images, int max_inst,
+                          const int32_t* state, float* dets_all, int32_t* counts_all, mrcnn_stream_t stream);
 
 /* ---- detection-target layer (replaces mrn_samples, model.py:396-576; data.boxes_overlaps data.py:151-189;
  *      data.boxes_deltas data.py:103-121) ------------------------------------------------------------------- */

@@ -58,6 +58,10 @@ SIGNATURES = {
     "mrcnn_rpn_unpack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mrcnn_detection_workspace_bytes": (_sz, [_i, _i]),
     "mrcnn_detection_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f4, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mrcnn_detection_exchange_bytes": (_sz, [_i, _i, _i]),
+    "mrcnn_detection_layer_exchange": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f4, _f, _f, _vp, _vp, _vp, _vp, _i, _i,
+                                            _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "mrcnn_detection_collect": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -77,7 +81,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mrcnn_abi_version() != 4:
+    if lib.mrcnn_abi_version() != 5:
         raise ImportError("maskrcnn_b200: ABI version mismatch")
     return lib
 

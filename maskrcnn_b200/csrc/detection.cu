@@ -22,6 +22,7 @@ constexpr int kDetThreads = 1024;
 constexpr int kDetMaxN = 3968;  // 32768 + 48 N + 16 ceil(N / 64) bytes of shared memory must fit the 220 KB the kernel may opt into
 constexpr int kDetLazyMaxInst = 1024;   // lazy NMS up to this many wanted detections
 constexpr int kDetSmemMaskMaxN = 1024;  // suppression words kept in shared memory up to this many RoIs
+constexpr int kDetMaxWorld = 8;         // ranks of the fused exchange (one NVSwitch domain)
 
 struct DetParams {
     const float* rois;     // [B,N,4] normalised
@@ -39,7 +40,30 @@ struct DetParams {
     uint64_t* gmask;      // [B][N64][W] (used when N > kDetSmemMaskMaxN)
     int mask_in_smem;
     int lazy;  // lazy NMS (no N x N mask)
+    // mask-head RoIs of the detections (model.py:1188 mrn_boxes.float() * 1.0 / h), written by the same kernel
+    float* mask_boxes;       // [B*max_inst,4] or null
+    int32_t* mask_box_ind;   // [B*max_inst] or null: image index of every row = (ind_offset + img) % ind_mod
+    int ind_offset, ind_mod;
+    // fused all-gather over peer memory (NVLink / NVSwitch): every CTA stores its image's packed row straight into the receive
+    // buffer of EVERY rank; the last CTA to finish raises this rank's flag on every rank.  world == 0: no exchange.
+    float* peer[kDetMaxWorld];          // rank r's exchange buffer, mapped into this process (own buffer included)
+    int world, rank, image_offset, total_images;
+    int32_t* state;                     // local: [0] epoch of the last finished exchange, [1] CTAs done in this launch
 };
+
+// Exchange buffer of one rank, floats: [2 parities][total_images][max_inst * 6 + 1] packed rows (detections, zero padded, then
+// the count), followed by [world] uint32 flags: flags[r] = epoch of the last exchange whose rows rank r has delivered here.
+__device__ __host__ inline size_t det_row_width(int max_inst) { return (size_t)max_inst * 6 + 1; }
+__device__ __host__ inline size_t det_flags_offset(int total_images, int max_inst) { return 2 * (size_t)total_images * det_row_width(max_inst); }
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const DetParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -328,6 +352,65 @@ __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const D
     if (iout)
         for (int r = D + tid; r < p.max_inst; r += kDetThreads) iout[r] = -1;
     if (tid == 0) p.counts_out[img] = D;
+    if (p.mask_boxes == nullptr && p.world == 0) return;
+
+    // ---- G. what follows the detection layer, without a launch in between
+    __syncthreads();   // the image's rows are complete in global memory (written by this CTA)
+    if (p.mask_boxes) {
+        // model.py:1188: mrn_rois = mrn_boxes.float() * 1.0 / h  (all four coordinates by the image height)
+        for (int e = tid; e < p.max_inst * 4; e += kDetThreads) {
+            const int r = e >> 2, k = e & 3;
+            p.mask_boxes[((size_t)img * p.max_inst + r) * 4 + k] = __fdiv_rn(out[(size_t)r * 6 + k], p.height);
+        }
+        if (p.mask_box_ind)
+            for (int r = tid; r < p.max_inst; r += kDetThreads)
+                p.mask_box_ind[(size_t)img * p.max_inst + r] = (p.ind_offset + img) % p.ind_mod;
+    }
+    if (p.world > 0) {
+        const int epoch0 = p.state[0];                   // every CTA reads it before any CTA of this launch can bump it
+        const size_t width = det_row_width(p.max_inst);
+        const size_t row = ((size_t)((epoch0 + 1) & 1) * p.total_images + (size_t)(p.image_offset + img)) * width;
+        for (int e = tid; e < (int)width; e += kDetThreads) {
+            const float v = (e < p.max_inst * 6) ? out[e] : (float)D;
+#pragma unroll
+            for (int r = 0; r < kDetMaxWorld; ++r)
+                if (r < p.world) p.peer[r][row + e] = v;    // peer stores: NVLink writes into rank r's memory
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.state + 1, 1);
+            if (done == p.B - 1) {                       // last CTA of this rank: all of the rank's rows are on their way
+                p.state[1] = 0;
+                __threadfence_system();
+                const size_t fo = det_flags_offset(p.total_images, p.max_inst);
+                for (int r = 0; r < p.world; ++r)
+                    st_release_sys(reinterpret_cast<uint32_t*>(p.peer[r] + fo) + p.rank, (uint32_t)(epoch0 + 1));
+                p.state[0] = epoch0 + 1;
+            }
+        }
+    }
+}
+
+// Second half of the fused all-gather: CTA i waits until the rank that owns image i has raised its flag for the current epoch
+// (a peer's release store, observed with an acquire load from LOCAL memory), then copies the image's packed row out of the
+// receive buffer into the caller's [total, max_inst, 6] / [total] tensors.  Image order = rank order (contiguous shards).
+__global__ void __launch_bounds__(128) detection_collect_kernel(const float* buf, int world, int total, int max_inst, const int32_t* state,
+                                                                float* dets_all, int32_t* counts_all) {
+    const int img = blockIdx.x;
+    const uint32_t epoch = (uint32_t)state[0];           // bumped by this rank's detection kernel earlier in the stream
+    const int base = total / world, rem = total % world; // shard_range(): the first `rem` ranks own base + 1 images
+    const int cut = rem * (base + 1);
+    const int owner = (img < cut) ? img / (base + 1) : rem + (img - cut) / (base > 0 ? base : 1);
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(buf + det_flags_offset(total, max_inst));
+    if (threadIdx.x == 0) {
+        while ((int32_t)(ld_acquire_sys(flags + owner) - epoch) < 0) __nanosleep(64);
+    }
+    __syncthreads();
+    const size_t width = det_row_width(max_inst);
+    const float* row = buf + ((size_t)(epoch & 1u) * total + img) * width;
+    for (int e = threadIdx.x; e < max_inst * 6; e += blockDim.x) dets_all[(size_t)img * max_inst * 6 + e] = __ldcv(row + e);
+    if (threadIdx.x == 0) counts_all[img] = (int32_t)__ldcv(row + max_inst * 6);
 }
 
 __global__ void detection_empty_kernel(float* dets, size_t n, int32_t* counts, int32_t* index, int B, int max_inst) {
@@ -364,10 +447,23 @@ size_t mrcnn_detection_workspace_bytes(int B, int N) {
     return align_up((size_t)B * N64 * (N64 / 64) * 8, 256);
 }
 
-int mrcnn_detection_layer(const float* rois, const float* probs, const float* deltas, const float* windows, int B, int N,
-                          int NC, float min_confidence, float nms_threshold, int max_inst, const float* std4_host,
-                          float height, float width, float* dets_out, int32_t* counts_out, int32_t* index_out,
-                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream_) {
+}  // extern "C"
+
+namespace mrcnn {
+
+struct DetExtras {
+    float* mask_boxes = nullptr;
+    int32_t* mask_box_ind = nullptr;
+    int ind_offset = 0, ind_mod = 1;
+    void* const* peer_bufs_host = nullptr;
+    int world = 0, rank = 0, image_offset = 0, total_images = 0;
+    int32_t* state = nullptr;
+};
+
+static int detection_launch(const float* rois, const float* probs, const float* deltas, const float* windows, int B, int N,
+                            int NC, float min_confidence, float nms_threshold, int max_inst, const float* std4_host,
+                            float height, float width, float* dets_out, int32_t* counts_out, int32_t* index_out,
+                            void* workspace, size_t workspace_bytes, const DetExtras& x, mrcnn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRCNN_REQUIRE(B > 0 && N >= 0 && NC > 0 && max_inst > 0, "mrcnn_detection_layer: bad sizes");
     MRCNN_REQUIRE(N <= kDetMaxN, "mrcnn_detection_layer: N = %d RoIs per image exceeds the supported %d", N, kDetMaxN);
@@ -376,6 +472,7 @@ int mrcnn_detection_layer(const float* rois, const float* probs, const float* de
     MRCNN_REQUIRE_DEV(counts_out);
     if (index_out) MRCNN_REQUIRE_DEV(index_out);
     if (N == 0) {
+        MRCNN_REQUIRE(x.world == 0 && x.mask_boxes == nullptr, "mrcnn_detection_layer_exchange: N must be positive");
         const size_t n = (size_t)B * max_inst * 6;
         detection_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dets_out, n, counts_out, index_out, B, max_inst);
         MRCNN_LAUNCH_CHECK();
@@ -398,6 +495,9 @@ int mrcnn_detection_layer(const float* rois, const float* probs, const float* de
     p.std0 = std4_host[0]; p.std1 = std4_host[1]; p.std2 = std4_host[2]; p.std3 = std4_host[3];
     p.height = height; p.width = width;
     p.dets_out = dets_out; p.counts_out = counts_out; p.index_out = index_out;
+    p.mask_boxes = x.mask_boxes; p.mask_box_ind = x.mask_box_ind; p.ind_offset = x.ind_offset; p.ind_mod = x.ind_mod > 0 ? x.ind_mod : 1;
+    p.world = x.world; p.rank = x.rank; p.image_offset = x.image_offset; p.total_images = x.total_images; p.state = x.state;
+    for (int r = 0; r < kDetMaxWorld; ++r) p.peer[r] = (r < x.world) ? (float*)x.peer_bufs_host[r] : nullptr;
     p.lazy = (g_detection_nms_algo == MRCNN_PROPOSAL_NMS_LAZY ||
               (g_detection_nms_algo == MRCNN_PROPOSAL_NMS_AUTO && max_inst <= kDetLazyMaxInst)) ? 1 : 0;
     MRCNN_REQUIRE(!p.lazy || max_inst <= kDetLazyMaxInst, "mrcnn_detection_layer: max_inst too large for the lazy NMS (use MRCNN_PROPOSAL_NMS_MASK)");
@@ -414,6 +514,62 @@ int mrcnn_detection_layer(const float* rois, const float* probs, const float* de
     MRCNN_REQUIRE(smem <= 220 * 1024, "mrcnn_detection_layer: shared memory need %zu exceeds the SM", smem);
     MRCNN_CUDA(cudaFuncSetAttribute(detection_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     detection_layer_kernel<<<B, kDetThreads, smem, stream>>>(p);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
+}
+
+}  // namespace mrcnn
+
+extern "C" {
+
+int mrcnn_detection_layer(const float* rois, const float* probs, const float* deltas, const float* windows, int B, int N,
+                          int NC, float min_confidence, float nms_threshold, int max_inst, const float* std4_host,
+                          float height, float width, float* dets_out, int32_t* counts_out, int32_t* index_out,
+                          void* workspace, size_t workspace_bytes, mrcnn_stream_t stream) {
+    return detection_launch(rois, probs, deltas, windows, B, N, NC, min_confidence, nms_threshold, max_inst, std4_host, height, width,
+                            dets_out, counts_out, index_out, workspace, workspace_bytes, DetExtras(), stream);
+}
+
+size_t mrcnn_detection_exchange_bytes(int world, int total_images, int max_inst) {
+    if (world <= 0 || total_images <= 0 || max_inst <= 0) return 0;
+    return align_up((det_flags_offset(total_images, max_inst) + (size_t)world) * sizeof(float), 256);
+}
+
+int mrcnn_detection_layer_exchange(const float* rois, const float* probs, const float* deltas, const float* windows, int B, int N,
+                                   int NC, float min_confidence, float nms_threshold, int max_inst, const float* std4_host,
+                                   float height, float width, float* dets_out, int32_t* counts_out, float* mask_boxes,
+                                   int32_t* mask_box_ind, int ind_offset, int ind_mod, void* const* peer_bufs_host, int world,
+                                   int rank, int image_offset, int total_images, int32_t* state, void* workspace,
+                                   size_t workspace_bytes, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(world >= 0 && world <= kDetMaxWorld, "mrcnn_detection_layer_exchange: world must be 0..%d", kDetMaxWorld);
+    DetExtras x;
+    if (mask_boxes) {
+        MRCNN_REQUIRE_DEV(mask_boxes);
+        if (mask_box_ind) MRCNN_REQUIRE_DEV(mask_box_ind);
+        MRCNN_REQUIRE(ind_mod > 0, "mrcnn_detection_layer_exchange: ind_mod must be positive");
+        x.mask_boxes = mask_boxes; x.mask_box_ind = mask_box_ind; x.ind_offset = ind_offset; x.ind_mod = ind_mod;
+    }
+    if (world > 0) {
+        MRCNN_REQUIRE(peer_bufs_host != nullptr && rank >= 0 && rank < world, "mrcnn_detection_layer_exchange: bad rank / peer table");
+        MRCNN_REQUIRE(image_offset >= 0 && B > 0 && image_offset + B <= total_images, "mrcnn_detection_layer_exchange: images outside [0, total)");
+        MRCNN_REQUIRE_DEV(state);
+        for (int r = 0; r < world; ++r) MRCNN_REQUIRE(peer_bufs_host[r] != nullptr, "mrcnn_detection_layer_exchange: peer buffer %d is null", r);
+        x.peer_bufs_host = peer_bufs_host; x.world = world; x.rank = rank; x.image_offset = image_offset; x.total_images = total_images;
+        x.state = state;
+    }
+    return detection_launch(rois, probs, deltas, windows, B, N, NC, min_confidence, nms_threshold, max_inst, std4_host, height, width,
+                            dets_out, counts_out, nullptr, workspace, workspace_bytes, x, stream);
+}
+
+int mrcnn_detection_collect(const void* local_buf, int world, int total_images, int max_inst, const int32_t* state, float* dets_all,
+                            int32_t* counts_all, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(world > 0 && world <= kDetMaxWorld && total_images > 0 && max_inst > 0, "mrcnn_detection_collect: bad sizes");
+    MRCNN_REQUIRE_DEV(local_buf);
+    MRCNN_REQUIRE_DEV(state);
+    MRCNN_REQUIRE_DEV(dets_all);
+    MRCNN_REQUIRE_DEV(counts_all);
+    detection_collect_kernel<<<total_images, 128, 0, (cudaStream_t)stream>>>((const float*)local_buf, world, total_images, max_inst, state,
+                                                                               dets_all, counts_all);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }

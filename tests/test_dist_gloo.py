@@ -70,3 +70,14 @@ def test_gather_is_identity_without_process_group():
     d, c = torch.zeros(2, 3, 6), torch.zeros(2, dtype=torch.int32)
     a, b = mdist.gather_detections(d, c)
     assert a is d and b is c
+
+
+def test_owner_rank_is_the_inverse_of_shard_range():
+    """detection_collect_kernel finds the rank that owns an image with this formula; it must invert shard_range()."""
+    from maskrcnn_b200 import dist as mdist
+    for n in (1, 7, 8, 63, 64, 65):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                b, e = mdist.shard_range(n, r, world)
+                for i in range(b, e):
+                    assert mdist.owner_rank(i, n, world) == r

@@ -252,3 +252,26 @@ def test_roi_align_dropin_wide_golden(ops, pool, pyr_cl, algo):
         ops.set_backward_algorithm("auto")
     for l in range(4):
         assert rel_err(ts[l].grad.cpu().numpy(), want_g[l]) <= BWD_TOL
+
+
+def test_detection_exchange_single_rank_matches_detection_layer(ops):
+    """The fused detection layer + exchange (mrcnn_detection_layer_exchange / mrcnn_detection_collect) with one rank: the same
+    detections as mrcnn_detection_layer, the mask-head RoIs of model.py:1188, and the collected copy - three exchanges in a row
+    (both buffer parities, flags carried over)."""
+    from maskrcnn_b200 import dist as mdist
+    B, N, NC, D = 12, 1000, 81, 100
+    ex = mdist.DetectionExchange(B, D)
+    assert (ex.world, ex.rank, ex.begin, ex.end) == (1, 0, 0, B)
+    win = dev(np.tile(np.array([[0, 0, IMAGE, IMAGE]], np.float32), (B, 1)))
+    for it in range(3):
+        rois = np.stack([synth.random_rois(N, 40 + 10 * it + i) for i in range(B)])
+        heads = [synth.head_outputs(N, NC, 60 + 10 * it + i) for i in range(B)]
+        probs, deltas = dev(np.stack([h[0] for h in heads])), dev(np.stack([h[1] for h in heads]))
+        want, want_c = ops.detection_layer(dev(rois), probs, deltas, win, 0.0, 0.3, D)
+        dets, counts = ex.run(dev(rois), probs, deltas, win, 0.0, 0.3, ind_offset=5, ind_mod=7)
+        assert torch.equal(dets, want) and torch.equal(counts, want_c)
+        assert torch.equal(ex.mask_boxes.view(B, D, 4), want[:, :, :4] / float(IMAGE))                      # model.py:1188
+        assert torch.equal(ex.mask_box_ind.view(B, D), ((torch.arange(B, device="cuda") + 5) % 7).int()[:, None].expand(B, D))
+        all_d, all_c = ex.collect()
+        assert torch.equal(all_d, want) and torch.equal(all_c, want_c)
+    assert int(ex.state[0]) == 3 and int(ex.state[1]) == 0
