@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrcnn_b200.so")
+# MRCNN_B200_DEBUG=1 selects the -DMRCNN_DEBUG build (`make -C maskrcnn_b200/csrc debug`: device-side index asserts)
+LIB_PATH = os.path.join(_HERE, "libmrcnn_b200_debug.so" if os.environ.get("MRCNN_B200_DEBUG") == "1" else "libmrcnn_b200.so")
 
 NCHW, NHWC = 0, 1
 OK = 0

@@ -8,6 +8,16 @@
 #include <math.h>
 #include <stdint.h>
 
+// -DMRCNN_DEBUG (make debug -> libmrcnn_b200_debug.so, loaded when MRCNN_B200_DEBUG=1): device-side asserts on the shared-memory,
+// distributed-shared-memory, ring-slot and workspace indices of the cluster / mbarrier / bulk-copy protocols.  compute-sanitizer
+// is closed on the GPU pool, so the whole GPU suite is run once under this build instead (profiles/r02_debug_build.txt).
+#ifdef MRCNN_DEBUG
+#include <assert.h>
+#define MRCNN_DBG(cond) assert(cond)
+#else
+#define MRCNN_DBG(cond) ((void)0)
+#endif
+
 namespace mrcnn {
 
 // Device-side error word (bit 0: box_index out of range): a 4-byte device allocation owned by api.cu,

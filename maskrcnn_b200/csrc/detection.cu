@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const D
         const uint64_t kw = kept[i >> 6];
         if ((kw >> (i & 63)) & 1ull) {
             const int r = s_prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+            MRCNN_DBG(r >= 0 && i < M);
             if (r < p.max_inst) {
                 const float4 b = sbox[i];
                 float* o = out + (size_t)r * 6;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) detection_layer_kernel(const D
     if (p.world > 0) {
         const int epoch0 = p.state[0];                   // every CTA reads it before any CTA of this launch can bump it
         const size_t width = det_row_width(p.max_inst);
+        MRCNN_DBG(p.image_offset + img < p.total_images && p.rank < p.world && epoch0 >= 0);
         const size_t row = ((size_t)((epoch0 + 1) & 1) * p.total_images + (size_t)(p.image_offset + img)) * width;
         for (int e = tid; e < (int)width; e += kDetThreads) {
             const float v = (e < p.max_inst * 6) ? out[e] : (float)D;
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(128) detection_collect_kernel(const float* buf
     const int base = total / world, rem = total % world; // shard_range(): the first `rem` ranks own base + 1 images
     const int cut = rem * (base + 1);
     const int owner = (img < cut) ? img / (base + 1) : rem + (img - cut) / (base > 0 ? base : 1);
+    MRCNN_DBG(owner >= 0 && owner < world);
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(buf + det_flags_offset(total, max_inst));
     if (threadIdx.x == 0) {
         while ((int32_t)(ld_acquire_sys(flags + owner) - epoch) < 0) __nanosleep(64);

@@ -79,6 +79,39 @@ __global__ void __launch_bounds__(1024) nms_prepare_small_kernel(const float* __
     for (int i = threadIdx.x; i < N; i += blockDim.x) gather_sorted(dets, skeys[i], i, sbox, sarea, order);
 }
 
+// 1024 < P <= kSortTile: P / 1024 CTAs sort one 1024-key tile each with the one-key-per-thread register / shuffle network
+// (~3 us, all tiles at once), then every element finds its global rank as its rank inside its tile plus, for every other tile, the
+// number of keys there that beat it (a binary search over the tile in shared memory; keys are unique: score, then index).  Two short
+// launches instead of one CTA grinding through the 91 stages of an 8192-key network (75 us).
+__global__ void __launch_bounds__(1024) nms_tile_sort_kernel(const float* __restrict__ dets, int N, uint64_t* __restrict__ tiles) {
+    __shared__ uint64_t buf[2 * 1024];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const uint64_t key = (i < N) ? make_sort_key(__ldg(dets + (size_t)i * 5 + 4), (uint32_t)i) : 0ull;   // 0 = padding: below every real key
+    tiles[i] = block_bitonic_desc_1024_reg(key, buf);
+}
+
+__global__ void __launch_bounds__(1024) nms_rank_gather_kernel(const float* __restrict__ dets, const uint64_t* __restrict__ tiles, int N,
+                                                               int T, float4* sbox, float* sarea, int32_t* order) {
+    extern __shared__ __align__(16) uint64_t skeys[];   // all T tiles
+    for (int i = threadIdx.x; i < T * 1024; i += 1024) skeys[i] = tiles[i];
+    __syncthreads();
+    const uint64_t key = skeys[blockIdx.x * 1024 + threadIdx.x];
+    if (key == 0ull) return;   // padding
+    int rank = threadIdx.x;
+    for (int t = 0; t < T; ++t) {
+        if (t == (int)blockIdx.x) continue;
+        const uint64_t* tile = skeys + t * 1024;   // descending
+        int lo = 0, hi = 1024;                     // first position whose key is below `key`
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tile[mid] > key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    MRCNN_DBG(rank >= 0 && rank < N && (int)sort_key_index(key) < N);
+    gather_sorted(dets, key, rank, sbox, sarea, order);
+}
+
 // N > kSortTile: multi-CTA bitonic network over a global key buffer.
 __global__ void nms_fill_keys_kernel(const float* __restrict__ dets, int N, int P, uint64_t* keys) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,11 +160,22 @@ __global__ void nms_gather_kernel(const float* __restrict__ dets, const uint64_t
 
 // ---- 2. mask ------------------------------------------------------------------------------------
 
-// grid = (W, W) (column block, row block), block = 64 threads = the 64 row boxes of the tile.
+// Upper triangle only, folded so that every CTA has a tile: row block r has W - r tiles, row block W - 1 - r has r + 1, together
+// W + 1.  grid = (W + 1, ceil(W / 2)), block = 64 threads = the 64 row boxes of the tile.  (The W x W grid of round 1 launched
+// 8836 CTAs for 6000 boxes and sent half of them home at once.)
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
                                                       int W, float thr, uint64_t* __restrict__ mask) {
-    const int cb = blockIdx.x, rb = blockIdx.y;
-    if (cb < rb) return;  // lower triangle is never read
+    const int r = blockIdx.y, i = blockIdx.x;
+    int rb, cb;
+    if (i < W - r) {
+        rb = r;
+        cb = r + i;
+    } else {
+        rb = W - 1 - r;
+        if (rb == r) return;  // odd W: the middle row block was served by the first branch
+        cb = rb + (i - (W - r));
+    }
+    MRCNN_DBG(rb >= 0 && rb < W && cb >= rb && cb < W);
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     const int t = threadIdx.x;
@@ -235,7 +279,15 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
     const int P = next_pow2(N);
     const int W = (N + 63) / 64;
 
-    if (P <= kSortTile) {
+    if (P > 1024 && P <= kSortTile) {
+        const int T = P / 1024;
+        nms_tile_sort_kernel<<<T, 1024, 0, stream>>>(dets, N, ws.sortbuf);
+        MRCNN_LAUNCH_CHECK();
+        const size_t smem = (size_t)P * 8;
+        MRCNN_CUDA(cudaFuncSetAttribute(nms_rank_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8));
+        nms_rank_gather_kernel<<<T, 1024, smem, stream>>>(dets, ws.sortbuf, N, T, ws.sbox, ws.sarea, ws.order);
+        MRCNN_LAUNCH_CHECK();
+    } else if (P <= kSortTile) {
         const size_t smem = (size_t)P * 8;
         MRCNN_CUDA(cudaFuncSetAttribute(nms_prepare_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8));
         const int threads = P >= 2048 ? 1024 : (P >= 64 ? P / 2 : 32);
@@ -257,7 +309,7 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
         MRCNN_LAUNCH_CHECK();
     }
 
-    nms_mask_kernel<<<dim3(W, W), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask);
+    nms_mask_kernel<<<dim3(W + 1, (W + 1) / 2), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask);
     MRCNN_LAUNCH_CHECK();
 
     const bool staged = W <= kSweepStageMaxW;
@@ -266,6 +318,7 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
     MRCNN_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int threads = (W + 31) / 32 * 32;
     threads = threads < 128 ? 128 : (threads > 1024 ? 1024 : threads);
+    if (W >= 8) threads = 1024;   // the propagate step spreads the survivors of a chunk over the warps
     nms_sweep_kernel<<<1, threads, smem, stream>>>(ws.mask, ws.order, N, W, staged ? 1 : 0, ws.flags, keep_out, count_out);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
             int s = 0;
 #pragma unroll
             for (int r = 0; r < kClusterSize; ++r) s += *cluster.map_shared_rank(&hist[tid], r);
+            MRCNN_DBG(s >= 0 && tid < 256);
             sh.tot[tid] = s;
         }
         __syncthreads();
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
                 if (j >= (unsigned)kSelThreads) {
                     Rb[rb * kSelThreads + tid] = v;
                     cluster.sync();
+                    MRCNN_DBG(((unsigned)rank ^ (j / kSelThreads)) < (unsigned)kClusterSize && (rb == 0 || rb == 1) && tid < kSelThreads);
                     pv = cluster.map_shared_rank(Rb + rb * kSelThreads, (unsigned)rank ^ (j / kSelThreads))[tid];
                     rb ^= 1;
                 } else if (j >= 32u) {
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) proposal_select_kernel(const P
             cluster.sync();  // the partners' local stages are complete
             for (unsigned j = k >> 1; j >= (unsigned)T; j >>= 1) {
                 const unsigned pbit = j / (unsigned)T;
+                MRCNN_DBG(((unsigned)rank ^ pbit) < (unsigned)kClusterSize && pbit != 0u);
                 const uint64_t* rem = cluster.map_shared_rank(cur, (unsigned)rank ^ pbit);
                 const bool lower = ((unsigned)rank & pbit) == 0u;  // this CTA holds the pair's lower index
                 for (int t = tid; t < T; t += kSelThreads) {
@@ -657,6 +660,7 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
             // peer's shared memory + one arrive on the peer's mbarrier per lane; then wait for the 8 words sent to us
             const uint32_t h_lo = __ballot_sync(0xffffffffu, s_hit[lane] != 0);
             const uint32_t h_hi = __ballot_sync(0xffffffffu, s_hit[lane + 32] != 0);
+            MRCNN_DBG(rank >= 0 && rank < kLazyCluster);
             if (lane < kLazyCluster) {  // lane p serves peer p: nine 8-byte stores, then one arrive (release) on its mbarrier
                 st_cluster_u64(mapa_u32(smem_u32(&s_peer[c & 1][rank]), (uint32_t)lane), ((uint64_t)h_hi << 32) | h_lo);
 #pragma unroll

@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(288) roialign_fwd_nhwc_tma_kernel(const RoiPar
                 else if (ty.hi != rb) { s_rows[nr++] = ty.hi; rb = ty.hi; }
             }
         }
+        MRCNN_DBG(nr >= 0 && nr <= 2 * POOL);
         s_nrows = nr;
         s_xmin = (xmax >= 0) ? xmin : 0;          // element offset (x * C)
         s_ncols = (xmax >= 0) ? (xmax - xmin) / C + 1 : 0;
@@ -548,6 +549,8 @@ __global__ void __launch_bounds__(288) roialign_fwd_nhwc_tma_kernel(const RoiPar
                 const int sl = i % slots;
                 const int k = i / slots;
                 if (k > 0) mbar_wait(&s_empty[sl], (uint32_t)((k - 1) & 1));
+                MRCNN_DBG(sl >= 0 && sl < slots && (size_t)(sl + 1) * row_bytes <= (size_t)kTmaRingBytes && (row_bytes & 15u) == 0);
+                MRCNN_DBG((unsigned)s_rows[i] + (unsigned)xmin + (unsigned)ncols * (unsigned)C <= (unsigned)(ctx.H * ctx.W * C));
                 mbar_expect_tx(&s_full[sl], row_bytes);
                 bulk_g2s(reinterpret_cast<unsigned char*>(ring) + (size_t)sl * row_bytes, src + (unsigned)s_rows[i], row_bytes, &s_full[sl]);
             }
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(288) roialign_fwd_nhwc_tma_kernel(const RoiPar
     int next = 0;  // next entry of s_rows to consume
     auto take_row = [&](float4 (&H)[kMaxQ]) {
         const int sl = next % slots;
+        MRCNN_DBG(next < nrows && jlo >= 0 && jhi >= jlo && (unsigned)(jhi + C) * 4u <= row_bytes);
         mbar_wait(&s_full[sl], (uint32_t)((next / slots) & 1));
         const float* row = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)sl * row_bytes);
 #pragma unroll
@@ -978,6 +982,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
         }
         return;
     }
+    MRCNN_DBG(n > 0 && __ldg(p.pos + u) - n >= 0);
     const QItem* items = p.items + (__ldg(p.pos + u) - n);
     if (wl < U) {  // permanent no-op padding behind the 32 staged items
         QItem z;
@@ -1194,6 +1199,7 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 float lo[K], hi[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
+                    MRCNN_DBG(!live[k] || ohi[k] + (unsigned)ty.lo < (unsigned)C * plane);
                     lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.lo)) : 0.f;
                     hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.lo)) : 0.f;
                 }
@@ -1225,7 +1231,10 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
         }
         if (col) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) wout[(g * K + k) * P2 + y * POOL + x] = v[k];
+            for (int k = 0; k < K; ++k) {
+                MRCNN_DBG((g * K + k) * P2 + y * POOL + x < kNchwCW * P2);
+                wout[(g * K + k) * P2 + y * POOL + x] = v[k];
+            }
         }
     }
     fence_proxy_async();   // every lane's staged outputs -> visible to the async proxy before lane 0 issues the bulk store
