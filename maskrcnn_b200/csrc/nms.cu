@@ -11,6 +11,7 @@
 //   3. sweep   : one CTA, mask row-blocks streamed through shared memory by bulk async copies,
 //                then an in-CTA prefix scan emits the surviving original indices in ascending order.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "api_util.h"
 #include "nms_core.cuh"
@@ -26,6 +27,7 @@ struct NmsWorkspace {
     int32_t* order;     // [N64] original index of the i-th best box
     uint64_t* mask;     // [N64][W]
     uint8_t* flags;     // [N64] survivor flag per ORIGINAL index
+    uint64_t* diag_t;   // [N64] diagonal tiles transposed: which earlier boxes of its chunk suppress box i
     size_t bytes;
 };
 
@@ -52,6 +54,7 @@ static NmsWorkspace carve_nms(void* base, int N) {
     w.order = (int32_t*)take(N64 * 4);
     w.mask = (uint64_t*)take(N64 * W * 8);
     w.flags = (uint8_t*)take(N64);
+    w.diag_t = (uint64_t*)take(N64 * 8);
     w.bytes = off;
     return w;
 }
@@ -164,7 +167,7 @@ __global__ void nms_gather_kernel(const float* __restrict__ dets, const uint64_t
 // W + 1.  grid = (W + 1, ceil(W / 2)), block = 64 threads = the 64 row boxes of the tile.  (The W x W grid of round 1 launched
 // 8836 CTAs for 6000 boxes and sent half of them home at once.)
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
-                                                      int W, float thr, uint64_t* __restrict__ mask) {
+                                                      int W, float thr, uint64_t* __restrict__ mask, uint64_t* __restrict__ diag_t) {
     const int r = blockIdx.y, i = blockIdx.x;
     int rb, cb;
     if (i < W - r) {
@@ -187,16 +190,28 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     }
     __syncthreads();
     const int row = rb * 64 + t;
-    if (row >= N) return;
-    const uint64_t w = suppression_word<false>(sbox[row], sarea[row], 0, row, cbox, carea, nullptr, col0, ncols, thr);
-    mask[(size_t)row * W + cb] = w;
+    uint64_t w = 0ull;
+    if (row < N) {
+        w = suppression_word<false>(sbox[row], sarea[row], 0, row, cbox, carea, nullptr, col0, ncols, thr);
+        mask[(size_t)row * W + cb] = w;
+    }
+    if (cb == rb) {  // diagonal tile: also store it transposed (the sweep's chunk resolve wants "who suppresses me")
+        __shared__ uint64_t s_w[64];
+        s_w[t] = w;
+        __syncthreads();
+        uint64_t col = 0ull;
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) col |= ((s_w[j] >> t) & 1ull) << j;
+        diag_t[row] = col;   // rows up to N64 - 1: the workspace holds N64 words
+    }
 }
 
 // ---- 3. sweep + ascending emit ------------------------------------------------------------------
 
 __global__ void __launch_bounds__(1024) nms_sweep_kernel(const uint64_t* __restrict__ mask, const int32_t* __restrict__ order,
                                                          int N, int W, int staged, uint8_t* __restrict__ flags,
-                                                         int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
+                                                         int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out,
+                                                         const uint64_t* __restrict__ diag_t) {
     extern __shared__ __align__(16) uint64_t sm_raw[];
     __shared__ uint64_t bars[2];
     __shared__ int s_total;
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const uint64_t* __restr
     sm.total = &s_total;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < N; i += nt) flags[i] = 0;
-    block_nms_sweep(mask, N, W, sm, staged != 0, INT_MAX);
+    block_nms_sweep(mask, N, W, sm, staged != 0, INT_MAX, diag_t);
     // survivors (score order) -> flags by original index
     for (int i = tid; i < N; i += nt)
         if ((sm.kept[i >> 6] >> (i & 63)) & 1ull) flags[order[i]] = 1;
@@ -309,17 +324,25 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
         MRCNN_LAUNCH_CHECK();
     }
 
-    nms_mask_kernel<<<dim3(W + 1, (W + 1) / 2), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask);
+    nms_mask_kernel<<<dim3(W + 1, (W + 1) / 2), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.diag_t);
     MRCNN_LAUNCH_CHECK();
 
-    const bool staged = W <= kSweepStageMaxW;
+    // MRCNN_NMS_STAGED=0: the propagate step reads the survivors' rows straight from L2 instead of from the staged block
+    // (measured slower at 6000 boxes: 388 us against 207 us before the prefetch of the transposed diagonal words).
+    static const bool no_stage = getenv("MRCNN_NMS_STAGED") != nullptr && getenv("MRCNN_NMS_STAGED")[0] == '0';
+    const bool staged = !no_stage && W <= kSweepStageMaxW;
     const size_t smem = sweep_smem_bytes(W, staged);
     MRCNN_REQUIRE(smem <= 220 * 1024, "mrcnn_nms: N too large for the single-CTA sweep");
     MRCNN_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int threads = (W + 31) / 32 * 32;
     threads = threads < 128 ? 128 : (threads > 1024 ? 1024 : threads);
-    if (W >= 8) threads = 1024;   // the propagate step spreads the survivors of a chunk over the warps
-    nms_sweep_kernel<<<1, threads, smem, stream>>>(ws.mask, ws.order, N, W, staged ? 1 : 0, ws.flags, keep_out, count_out);
+    // the propagate step spreads a chunk's survivors over several threads per word; measured on B200 (tools/time_nms.py, whole
+    // nms call): 6000 boxes 342 / 246 / 207 / 230 us with 128 / 256 / 512 / 1024 threads, 2000 boxes 68 us with 256 (81 with 1024)
+    if (W >= 64) threads = 512;
+    else if (W >= 8) threads = 256;
+    static const int force_threads = getenv("MRCNN_NMS_THREADS") ? atoi(getenv("MRCNN_NMS_THREADS")) : 0;   // experiment knob
+    if (force_threads >= 128 && force_threads <= 1024 && force_threads % 32 == 0) threads = force_threads;
+    nms_sweep_kernel<<<1, threads, smem, stream>>>(ws.mask, ws.order, N, W, staged ? 1 : 0, ws.flags, keep_out, count_out, ws.diag_t);
     MRCNN_LAUNCH_CHECK();
     return MRCNN_OK;
 }

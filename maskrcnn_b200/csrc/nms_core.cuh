@@ -163,8 +163,10 @@ struct SweepSmem {
     int* total;  // one int
 };
 
+// diag_t (optional): [rows] words, bit j of diag_t[i] set iff box j of i's chunk (j < i within the chunk) suppresses box i - the
+// diagonal tiles transposed, written by the mask kernel; without it warp 0 transposes each diagonal tile itself (64 broadcast loads).
 __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int W, const SweepSmem sm,
-                                               bool staged, int max_keep) {
+                                               bool staged, int max_keep, const uint64_t* diag_t = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int w = tid; w < W; w += nt) {
         sm.remv[w] = 0;
@@ -185,6 +187,16 @@ __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int 
         bulk_g2s(sm.stage, mask, block_bytes, &sm.bars[0]);
     }
     int total = 0;
+    // warp 0 keeps the transposed diagonal words of the NEXT chunk in registers: the two global loads are off the critical path
+    uint64_t pa = 0ull, pb = 0ull;
+    if (diag_t != nullptr && tid < 32 && W > 0) {
+        if (tid < n) pa = __ldg(diag_t + tid);
+        if (tid + 32 < n) pb = __ldg(diag_t + tid + 32);
+    }
+    // threads per word in the propagate step: a power of two <= 16, fixed for the sweep (W - 1 words at most)
+    int lp = 0;
+    while (lp < 4 && (2 << lp) * max(W - 1, 1) <= nt) ++lp;
+    const int parts = 1 << lp, span = 64 >> lp;
     for (int c = 0; c < W; ++c) {
         const uint64_t* rows;  // 64 rows x W words of chunk c
         if (staged) {
@@ -210,10 +222,19 @@ __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int 
         if (tid < 32) {
             const int nrows = min(64, n - c * 64);
             uint64_t ca = 0ull, cb = 0ull;   // earlier boxes of the chunk that suppress box tid / box tid + 32 (column view)
-            for (int j = 0; j < nrows; ++j) {
-                const uint64_t d = rows[(size_t)j * W + c];   // row j of the diagonal tile (bits above j only), same word for all lanes
-                ca |= ((d >> tid) & 1ull) << j;
-                cb |= ((d >> (tid + 32)) & 1ull) << j;
+            if (diag_t != nullptr) {
+                ca = pa;
+                cb = pb;
+                pa = pb = 0ull;
+                const int nn = n - (c + 1) * 64;   // rows of the next chunk
+                if (tid < nn) pa = __ldg(diag_t + (size_t)(c + 1) * 64 + tid);
+                if (tid + 32 < nn) pb = __ldg(diag_t + (size_t)(c + 1) * 64 + tid + 32);
+            } else {
+                for (int j = 0; j < nrows; ++j) {
+                    const uint64_t d = rows[(size_t)j * W + c];   // row j of the diagonal tile (bits above j only), same word for all lanes
+                    ca |= ((d >> tid) & 1ull) << j;
+                    cb |= ((d >> (tid + 32)) & 1ull) << j;
+                }
             }
             uint64_t cand = ~sm.remv[c];
             if (nrows < 64) cand &= ((1ull << nrows) - 1ull);
@@ -239,26 +260,31 @@ __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int 
             if (staged && c + 1 < W) mbar_wait(&sm.bars[(c + 1) & 1], (uint32_t)(((c + 1) >> 1) & 1));
             break;
         }
-        // --- propagate: every later word ORs in the rows of the survivors of this chunk.  The words are spread over the lanes
-        //     of a warp and the survivors over the warps; partial ORs meet in shared memory (atomicOr). ---
+        // --- propagate: every later word ORs in the rows of the survivors of this chunk: `parts` threads per word, each owning a
+        //     contiguous slice of the chunk's 64 rows (four independent loads per round); partial ORs meet in shared memory ---
         {
             const int later = W - (c + 1);
-            if (later > 0 && later <= nt) {
-                const int parts = min(nt / later, 16);   // threads per word (>= 1)
-                const int wi = tid % later, part = tid / later;
-                if (part < parts) {
+            if (later * parts <= nt) {
+                const int part = tid & (parts - 1), wi = tid >> lp;
+                if (wi < later) {
                     const int w = c + 1 + wi;
                     MRCNN_DBG(w > c && w < W);
+                    const uint64_t k = (kept >> (part * span)) & (span == 64 ? ~0ull : ((1ull << span) - 1ull));
+                    const uint64_t* base = rows + (size_t)(part * span) * W + w;
                     uint64_t acc = 0;
-                    uint64_t k = kept;
-                    int idx = 0;
-                    while (k) {
-                        const int r = __ffsll((long long)k) - 1;
-                        k &= k - 1;
-                        MRCNN_DBG(r >= 0 && r < 64);
-                        if ((idx++ % parts) == part) acc |= rows[(size_t)r * W + w];
+                    for (int r0 = 0; r0 < span && (k >> r0) != 0ull; r0 += 4) {
+                        const unsigned m4 = (unsigned)(k >> r0) & 15u;
+                        MRCNN_DBG(part * span + r0 + 3 < 64);
+                        const uint64_t v0 = (m4 & 1u) ? base[(size_t)(r0 + 0) * W] : 0ull;
+                        const uint64_t v1 = (m4 & 2u) ? base[(size_t)(r0 + 1) * W] : 0ull;
+                        const uint64_t v2 = (m4 & 4u) ? base[(size_t)(r0 + 2) * W] : 0ull;
+                        const uint64_t v3 = (m4 & 8u) ? base[(size_t)(r0 + 3) * W] : 0ull;
+                        acc |= (v0 | v1) | (v2 | v3);
                     }
-                    if (acc) atomicOr(reinterpret_cast<unsigned long long*>(&sm.remv[w]), (unsigned long long)acc);
+                    if (acc) {
+                        if (parts == 1) sm.remv[w] |= acc;
+                        else atomicOr(reinterpret_cast<unsigned long long*>(&sm.remv[w]), (unsigned long long)acc);
+                    }
                 }
             } else {
                 for (int w = c + 1 + tid; w < W; w += nt) {   // more words than threads: one thread per word, all survivors
