@@ -307,8 +307,10 @@ def timed_steps(torch, dist, wl, steps, warmup, world, step=None):
 
 
 # ---------------------------------------------------------------------------------------------------
-def e2e_run(torch, dist, wl, steps, warmup, world):
-    """Host buffers in, host buffers out, every step: per image H2D -> 5 launches -> D2H over three streams."""
+def e2e_run(torch, dist, wl, steps, warmup, world, fused_backward=False):
+    """Host buffers in, host buffers out, every step: per image H2D -> 5 launches -> D2H over three streams.
+    fused_backward: both heads' backward as ONE gather into ONE gradient pyramid (mrcnn_pyramid_roi_align_backward_pair: what
+    autograd accumulates in a training step), so one pyramid of gradients (1.43 GB) crosses the host link instead of two."""
     L = wl.L
     B = wl.batch
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()  # noqa: E731
@@ -334,8 +336,12 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
     gf14_nhwc = [f.permute(0, 2, 3, 1) for f in wl.gfm14]
     h2d = sum(t.numel() * 4 for t in h_fm) + h_boxes.numel() * 4 + h_g7.numel() * 4 + h_g14.numel() * 4 + \
         h_mboxes.numel() * 4 + h_mind.numel() * 4
-    d2h = h_out7.numel() * 4 + h_out14.numel() * 4 + h_mt.numel() * 4 + 2 * sum(t.numel() * 4 for t in h_fm)
+    d2h = h_out7.numel() * 4 + h_out14.numel() * 4 + h_mt.numel() * 4 + (1 if fused_backward else 2) * sum(t.numel() * 4 for t in h_fm)
     launches = [0]
+    ws_pair = None
+    if fused_backward:   # one image at a time: a per-image workspace, reused (the stream orders the uses)
+        ws_pair = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(wl.Hs, wl.Ws, 1, ROIS_PER_IMAGE, 7, 14), dtype=torch.uint8,
+                              device=wl.boxes.device)
 
     def one_step():
         ev_in = [torch.cuda.Event() for _ in range(B)]
@@ -363,11 +369,17 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                                                               wl.out14[rs].data_ptr(), wl.crop_layout, None, st))
                 L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
                                                  wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
-                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
-                L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
-                                                               wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
-                launches[0] += 7
+                if fused_backward:
+                    L.check(L.lib.mrcnn_pyramid_roi_align_backward_pair(wl.g7[rs].data_ptr(), 7, wl.g14[rs].data_ptr(), 14, wl.Hs, wl.Ws, 1, CHANNELS,
+                                                                        bp, None, R, wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), 1,
+                                                                        ws_pair.data_ptr(), ws_pair.numel(), st))
+                    launches[0] += 9
+                else:
+                    L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
+                                                                   wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
+                    L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
+                                                                   wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
+                    launches[0] += 7
                 ev_run[i].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[i])
@@ -375,7 +387,8 @@ def e2e_run(torch, dist, wl, steps, warmup, world):
                 h_out14[rs].copy_(d_out14[rs], non_blocking=True)
                 h_mt[ms].copy_(wl.mt[ms], non_blocking=True)
                 for l in range(4):
-                    h_gf7[l][i].copy_(gf7_nhwc[l][i], non_blocking=True)
+                    if not fused_backward:
+                        h_gf7[l][i].copy_(gf7_nhwc[l][i], non_blocking=True)
                     h_gf14[l][i].copy_(gf14_nhwc[l][i], non_blocking=True)
         torch.cuda.synchronize()
 
@@ -1055,10 +1068,13 @@ def secondary(torch, wl, hbm):
             L.check(L.lib.mrcnn_pyramid_roi_align_forward(pf, wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NCHW, wl.boxes.data_ptr(), wl.ind.data_ptr(),
                                                           wl.N, pool, wl.area, o.data_ptr(), L.NCHW, None, wl._s()))
 
+        ws_n = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes_ex(wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.N, 14, L.NCHW),
+                           dtype=torch.uint8, device=dev)   # queues + the transposed copy of the NCHW upstream gradients
+
         def bwd_n(pool, g):
             L.check(L.lib.mrcnn_pyramid_roi_align_backward(g.data_ptr(), L.NCHW, wl.Hs, wl.Ws, wl.batch, CHANNELS, wl.boxes.data_ptr(),
                                                            wl.ind.data_ptr(), wl.N, pool, wl.area, pg, L.NCHW, 1, None, L.BWD_AUTO,
-                                                           wl.ws.data_ptr(), wl.ws.numel(), wl._s()))
+                                                           ws_n.data_ptr(), ws_n.numel(), wl._s()))
 
         def step_n():
             fwd_n(7, o7)
@@ -1080,7 +1096,7 @@ def secondary(torch, wl, hbm):
                                            "step_frac_of_hbm": (sum(alg.values()) + wl.mt.numel() * 4) / tstep / 1e9 / hbm,
                                            "config": "configs[3] with the pyramid, crops and gradients all NCHW-contiguous (same algorithmic bytes)"}
         out["nchw_pyramid"] = nchw
-        del fm_nchw, o7, o14, g7, g14, gfn
+        del fm_nchw, o7, o14, g7, g14, gfn, ws_n
     except Exception as e:
         out["nchw_pyramid"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     # the standalone drop-in nms (c++ext/maskrcnn/__init__.py:21-22) at the proposal layer's size: 6000 boxes, IoU 0.7
@@ -1442,6 +1458,13 @@ def main():
                             "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
                             "kernels": kern}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)
+        if wl.cl_crops:
+            try:
+                line["e2e_fused_backward"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world, fused_backward=True)
+                line["e2e_fused_backward"]["note"] = ("not the headline: the two heads' gradient pyramids leave the device summed (what a training step "
+                                                      "accumulates), so 1.43 GB less crosses the host link per step")
+            except Exception as e_:
+                line["e2e_fused_backward"] = {"error": "%s: %s" % (type(e_).__name__, str(e_)[:300])}
         line["e2e"]["host_cpus_bound"] = (len(numa) if numa else None)
         line["detection_path_sharded"] = sharded_detection(torch, dist, wl, world, rank, hbm)
         line["rpn_nms"] = rpn_nms(torch, dist, wl, world, rank, hbm)

@@ -98,9 +98,9 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
  * algo:
  *   MRCNN_BWD_GATHER   row-owner gather: every run of 8 pixels of every gradient-map row is owned by one warp that
  *                      sums, in registers, the bins reaching it and writes each pixel exactly once - no atomics on
- *                      gradient data, no zero-fill pass, no read-modify-write of the pyramid.  Needs channels-last
- *                      grads and gfm, C % 4 == 0, N > 0, N * pool^2 * C < 2^31, image_offsets_host == NULL and a
- *                      256-byte aligned workspace of mrcnn_pyramid_roi_align_backward_workspace_bytes() bytes.
+ *                      gradient data, no zero-fill pass, no read-modify-write of the pyramid.  Needs C % 4 == 0,
+ *                      N > 0, N * pool^2 * C < 2^31, image_offsets_host == NULL and a 256-byte aligned workspace of
+ *                      mrcnn_pyramid_roi_align_backward_workspace_bytes_ex() bytes.  Either layout of grads and gfm.
  *   MRCNN_BWD_SCATTER  clear, then scatter with column-aggregated 128-bit vector reductions
  *                      (red.global.add.v4.f32) for a channels-last gfm, scalar atomics for an NCHW gfm.
  *                      workspace may be NULL.
@@ -113,6 +113,12 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
 #define MRCNN_BWD_SCATTER 2
 MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const int W[4], int B, int N,
                                                                   int pool);
+/* The same with the upstream-gradient layout taken into account: MRCNN_BWD_GATHER also serves NCHW gradient maps (every unit of
+ * 8 pixels is one aligned 32-byte sector per channel plane, written once) and NCHW upstream gradients (what torch's conv
+ * backward hands to an unmodified model.py), which it first transposes to [N][pool^2][C] in the tail of the workspace:
+ * N * C * pool^2 * 4 more bytes.  For channels-last gradients it equals mrcnn_pyramid_roi_align_backward_workspace_bytes(). */
+MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes_ex(const int H[4], const int W[4], int B, int C, int N,
+                                                                     int pool, int grads_layout);
 MRCNN_API int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout,
                                      const int H[4], const int W[4], int B, int C,
                                      const float* boxes, const int32_t* box_index, int N, int pool,

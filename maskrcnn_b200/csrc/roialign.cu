@@ -812,6 +812,7 @@ struct GatherParams {
     const float* grads;   // [N][ph*pw][C]
     const float* grads2;  // second head of a fused two-head backward (items tagged kOHead2), else == grads
     int head_flag;        // 0 or kOHead2: ORed into the items the fill pass writes
+    int out_nchw;         // 1: the gradient maps are NCHW (a unit = 8 consecutive pixels of every channel plane = one 32-byte sector each)
     int* cnt;             // [units] items per unit
     int* pos;            // [units] after alloc: first item; after fill: one past the last item
     unsigned int* cursor;
@@ -958,7 +959,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // (No minimum-blocks bound: forcing 24 / 28 / 32 CTAs per SM - 80 / 72 / 64 registers - spills and measured 0.61 / 0.75 / 0.89 ms
 // against 0.58 ms for the configs[3] 14x14 backward; U = 3 or ST = 6 are slower too.  profiles/r02_experiments.txt)
-template <int NV, int U, int ST, bool kAccumulate>
+template <int NV, int U, int ST, bool kAccumulate, bool kOutNCHW = false>
 __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherParams p) {
     __shared__ QItem s_items[32 + U];
     __shared__ __align__(16) float4 s_data[ST][U][NV][32];
@@ -974,11 +975,28 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
     const int npx = min(kGTile, G.W - seg * kGTile);
     float* out = G.ptr + ((size_t)rowid * G.W + seg * kGTile) * C;
 
+    // NCHW gradient maps: channel ch of this unit = the 8 floats at ((img * C + ch) * H + y) * W + 8 * seg - one aligned sector
+    const int img_ = rowid / G.H, y_ = rowid - img_ * G.H;
+    float* out_nchw = G.ptr + (((size_t)img_ * C) * G.H + y_) * G.W + seg * kGTile;
+    const size_t plane_ = (size_t)G.H * G.W;
+    const bool vec8 = kOutNCHW && npx == kGTile && ((reinterpret_cast<uintptr_t>(out_nchw) | (plane_ * 4)) & 15u) == 0;
     const int n = __ldg(p.cnt + u);
     if (n == 0) {  // nothing reaches this unit: it is all zeros
         if (!kAccumulate) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 4 * wl; i < npx * C; i += 128) stg_f4_stream(out + i, z);
+            if (!kOutNCHW) {
+                for (int i = 4 * wl; i < npx * C; i += 128) stg_f4_stream(out + i, z);
+            } else {
+                for (int ch = wl; ch < C; ch += 32) {
+                    float* o = out_nchw + (size_t)ch * plane_;
+                    if (vec8) {
+                        stg_f4_stream(o, z);
+                        stg_f4_stream(o + 4, z);
+                    } else {
+                        for (int j = 0; j < npx; ++j) o[j] = 0.f;
+                    }
+                }
+            }
         }
         return;
     }
@@ -1055,7 +1073,35 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
             cp_async_wait<0>();
         }
 
-        if (live) {
+        if (kOutNCHW && live) {
+            // every channel the lane holds: its 8 pixel sums are one sector of that channel's plane
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float* o = out_nchw + (size_t)(c + 128 * k + q) * plane_;
+                    float v[kGTile];
+#pragma unroll
+                    for (int j = 0; j < kGTile; ++j) {
+                        const float4 a = acc.a[j][k];
+                        v[j] = (q == 0) ? a.x : (q == 1) ? a.y : (q == 2) ? a.z : a.w;
+                    }
+                    if (kAccumulate) {
+#pragma unroll
+                        for (int j = 0; j < kGTile; ++j)
+                            if (j < npx) v[j] += o[j];
+                    }
+                    if (vec8) {
+                        stg_f4_stream(o, make_float4(v[0], v[1], v[2], v[3]));
+                        stg_f4_stream(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kGTile; ++j)
+                            if (j < npx) o[j] = v[j];
+                    }
+                }
+            }
+        } else if (live) {
             float* o = out + c;
 #pragma unroll
             for (int j = 0; j < kGTile; ++j) {
@@ -1145,6 +1191,8 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     extern __shared__ __align__(128) float s_out[];  // [8 warps][8 channels][P2]: the outputs in global order
     __shared__ TapS s_ty[POOL];
     __shared__ TapS s_tx[POOL];
+    __shared__ int s_rows[2 * POOL];   // plane offsets of the feature rows in the order the walk fetches them
+    __shared__ int s_nrows;
 
     const int chunks = (p.C + kChunk - 1) / kChunk;
     const int n = blockIdx.x / chunks;
@@ -1156,6 +1204,20 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     const RoiCtx ctx = select_level(p, n, box);
     stage_taps_nchw(ctx, box, POOL, POOL, s_ty, s_tx);
     __syncthreads();
+    if (tid == 0) {  // the walk below, rows only: which feature row is fetched when (so that fetches can run ahead of it)
+        int nr = 0, ra = -1, rb = -1;
+        for (int y = 0; y < POOL; ++y) {
+            const TapS ty = s_ty[y];
+            if (!ty.valid) continue;
+            if (ty.lo == rb) { ra = rb; rb = -1; }
+            else if (ty.lo != ra) { s_rows[nr++] = ty.lo; ra = ty.lo; }
+            if (ty.hi == ra) rb = ra;
+            else if (ty.hi != rb) { s_rows[nr++] = ty.hi; rb = ty.hi; }
+        }
+        MRCNN_DBG(nr <= 2 * POOL);
+        s_nrows = nr;
+    }
+    __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int cw0 = c0 + warp * kNchwCW;              // the warp's first channel
@@ -1166,6 +1228,7 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     const bool col = x < POOL;
     const TapS tx = s_tx[col ? x : 0];
     const bool x_in = col && tx.valid;
+    const int nrows = s_nrows;
     // 32-bit element offsets from the image's base (the launcher guarantees C * H * W < 2^31): one IMAD.WIDE per load
     const unsigned plane = (unsigned)(ctx.H * ctx.W);
     const float* base = ctx.base;
@@ -1179,6 +1242,36 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
         olo[k] = o + (unsigned)tx.lo;
         ohi[k] = o + (unsigned)tx.hi;
     }
+
+    // two feature rows of taps are always in flight (registers A and B, alternating): the row the walk needs next and the one
+    // after it were requested one and two steps ago
+    float alo[K], ahi[K], blo[K], bhi[K];
+    auto fetch = [&](int i, float (&lo)[K], float (&hi)[K]) {
+        if (i < nrows) {
+            const unsigned row = (unsigned)s_rows[i];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                MRCNN_DBG(!live[k] || ohi[k] + row < (unsigned)C * plane);
+                lo[k] = live[k] ? __ldg(base + (olo[k] + row)) : 0.f;
+                hi[k] = live[k] ? __ldg(base + (ohi[k] + row)) : 0.f;
+            }
+        }
+    };
+    fetch(0, alo, ahi);
+    fetch(1, blo, bhi);
+    int next = 0;
+    auto take = [&](float (&H)[K]) {   // H of the next row of the list; its registers go back to work for the row two ahead
+        if ((next & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) H[k] = __fadd_rn(alo[k], __fmul_rn(__fsub_rn(ahi[k], alo[k]), tx.lerp));
+            fetch(next + 2, alo, ahi);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) H[k] = __fadd_rn(blo[k], __fmul_rn(__fsub_rn(bhi[k], blo[k]), tx.lerp));
+            fetch(next + 2, blo, bhi);
+        }
+        ++next;
+    };
 
     int ra = -1, rb = -1;  // feature rows (as plane offsets) whose horizontal blends Ha / Hb hold
     float Ha[K], Hb[K];
@@ -1196,15 +1289,8 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 ra = rb;
                 rb = -1;
             } else if (ty.lo != ra) {
-                float lo[K], hi[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    MRCNN_DBG(!live[k] || ohi[k] + (unsigned)ty.lo < (unsigned)C * plane);
-                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.lo)) : 0.f;
-                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.lo)) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) Ha[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
+                MRCNN_DBG(next < nrows && s_rows[next] == ty.lo);
+                take(Ha);
                 ra = ty.lo;
             }
             if (ty.hi == ra) {            // y_lerp == 0: the ceil row is the floor row
@@ -1212,14 +1298,8 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 for (int k = 0; k < K; ++k) Hb[k] = Ha[k];
                 rb = ra;
             } else if (ty.hi != rb) {
-                float lo[K], hi[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.hi)) : 0.f;
-                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.hi)) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) Hb[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
+                MRCNN_DBG(next < nrows && s_rows[next] == ty.hi);
+                take(Hb);
                 rb = ty.hi;
             }
 #pragma unroll
@@ -1428,6 +1508,25 @@ __global__ void __launch_bounds__(256) crop_plane_fwd_kernel(const RoiParams p) 
             if (b < P2) out[b] = in[u] ? bilerp(tl[u], tr[u], bl[u], br[u], xl[u], yl[u]) : p.extrap;
         }
     }
+}
+
+// Upstream gradients [N][C][P2] (NCHW-contiguous, what torch's conv backward hands to an unmodified model.py) -> [N][P2][C]
+// for the gather backward: one CTA per (RoI, 64 channels); the slice is contiguous on the way in (coalesced 128-bit loads into
+// a padded shared tile) and 256-byte pieces on the way out.
+__global__ void __launch_bounds__(kThreads) grads_nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int P2) {
+    extern __shared__ __align__(16) float tile[];
+    const int n = blockIdx.x, c0 = blockIdx.y * kChunk;
+    const int cc = min(kChunk, C - c0);
+    const int P2pad = P2 | 1;
+    tile_copy<true>(tile, const_cast<float*>(src) + ((size_t)n * C + c0) * P2, cc * P2, P2, P2pad);
+    __syncthreads();
+    const int lane = threadIdx.x & (kLanes - 1), slot = threadIdx.x >> 4;
+    const int c = 4 * lane;
+    if (c >= cc) return;   // C % 4 == 0
+    float* o = dst + (size_t)n * P2 * C + c0 + c;
+    const float* t = tile + c * P2pad;
+    for (int b = slot; b < P2; b += kSlots)
+        stg_f4_stream(o + (size_t)b * C, make_float4(t[b], t[P2pad + b], t[2 * P2pad + b], t[3 * P2pad + b]));
 }
 
 // Zero-fills up to four buffers in one launch (per-image slices of the gradient pyramid).
@@ -1753,13 +1852,20 @@ static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], 
 static bool gather_eligible(const int H[4], const int W[4], int B, int C, int N, long long bins, int max_pool, int gfm_layout,
                             int grads_layout, const float* grads, float* const gfm[4], const void* workspace,
                             size_t workspace_bytes) {
-    if (gfm_layout != MRCNN_NHWC || grads_layout != MRCNN_NHWC) return false;
+    // NCHW gradient maps are written sector-wise by the gather itself; NCHW upstream gradients are transposed into the tail of the
+    // workspace first (carve_gather_ex).  Both need W % 8 == 0 for aligned sectors to be the common case (any W is handled).
+    (void)gfm_layout;
+    if (grads_layout == MRCNN_NCHW && sizeof(float) * kChunk * (size_t)((max_pool * max_pool) | 1) > 200 * 1024) return false;
     if ((C % 4) != 0 || N <= 0) return false;
     if ((long long)N * max_pool * max_pool * C >= (1ll << 31)) return false;  // 32-bit element offsets into grads
     if ((long long)4 * N * bins >= (1ll << 31)) return false;                 // 32-bit item positions
     if (gather_units(H, W, B) >= (1ll << 31) - 8) return false;
     if ((long long)N * max_pool * 2 >= (1ll << 31) * 256) return false;
-    if (workspace == nullptr || workspace_bytes < carve_gather(nullptr, H, W, B, N, bins).bytes) return false;
+    {
+        size_t need = carve_gather(nullptr, H, W, B, N, bins).bytes;
+        if (grads_layout == MRCNN_NCHW) need += align_up((size_t)N * C * (size_t)bins * sizeof(float), 256);
+        if (workspace == nullptr || workspace_bytes < need) return false;
+    }
     if (!aligned16(grads) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return false;
     for (int l = 0; l < 4; ++l)
         if (!aligned16(gfm[l])) return false;
@@ -1813,13 +1919,19 @@ static int launch_gather_plan(GatherParams g, const GatherWorkspace& ws, void* w
 
 // Pass 4: one warp per unit sums the bins its queue lists and writes its 8 pixels once.
 static int launch_gather_run(GatherParams g, int heads, const float* const grads[2], float* const gfm[4], int accumulate,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int out_nchw = 0) {
+    g.out_nchw = out_nchw;
     for (int l = 0; l < 4; ++l) g.g[l].ptr = gfm[l];
     g.grads = grads[0]; g.grads2 = grads[heads - 1];
     const bool wide = (g.C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
     const unsigned grid = (unsigned)g.units;
     // U = 2 items per stage, ST = 4 stages: best of the (U, ST) grid measured on B200 (profiles/r01_*gather*)
-    if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true><<<grid, 32, 0, stream>>>(g);
+    if (out_nchw) {
+        if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true, true><<<grid, 32, 0, stream>>>(g);
+        else if (wide) roialign_bwd_gather_kernel<2, 2, 4, false, true><<<grid, 32, 0, stream>>>(g);
+        else if (accumulate) roialign_bwd_gather_kernel<1, 2, 4, true, true><<<grid, 32, 0, stream>>>(g);
+        else roialign_bwd_gather_kernel<1, 2, 4, false, true><<<grid, 32, 0, stream>>>(g);
+    } else if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true><<<grid, 32, 0, stream>>>(g);
     else if (wide) roialign_bwd_gather_kernel<2, 2, 4, false><<<grid, 32, 0, stream>>>(g);
     else if (accumulate) roialign_bwd_gather_kernel<1, 2, 4, true><<<grid, 32, 0, stream>>>(g);
     else roialign_bwd_gather_kernel<1, 2, 4, false><<<grid, 32, 0, stream>>>(g);
@@ -1830,13 +1942,30 @@ static int launch_gather_run(GatherParams g, int heads, const float* const grads
 // One or two heads (the same boxes pooled at pools[h] x pools[h], upstream gradients grads[h]) into one gradient pyramid.
 static int launch_bwd_gather(int heads, const float* const grads[2], const int pools[2], const int H[4], const int W[4], int B,
                              int C, const float* boxes, const int32_t* box_index, int N, float image_area, float* const gfm[4],
-                             int accumulate, void* workspace, cudaStream_t stream) {
+                             int accumulate, void* workspace, cudaStream_t stream, int grads_layout = MRCNN_NHWC,
+                             int gfm_layout = MRCNN_NHWC) {
     long long bins = 0;
     for (int h = 0; h < heads; ++h) bins += (long long)pools[h] * pools[h];
     const GatherWorkspace ws = carve_gather(workspace, H, W, B, N, bins);
     const GatherParams g = gather_params(ws, H, W, B, C, N, image_area);
+    const float* gr[2] = {grads[0], grads[1]};
+    if (grads_layout == MRCNN_NCHW) {
+        // NCHW upstream gradients: transposed to [N][bins][C] in the tail of the workspace, one head after the other
+        float* t = reinterpret_cast<float*>(static_cast<char*>(workspace) + ws.bytes);
+        for (int h = 0; h < heads; ++h) {
+            const int P2 = pools[h] * pools[h];
+            const size_t smem = sizeof(float) * kChunk * (size_t)(P2 | 1);
+            if (smem > 48 * 1024)
+                MRCNN_CUDA(cudaFuncSetAttribute(grads_nchw_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            grads_nchw_to_nhwc_kernel<<<dim3(N, (C + kChunk - 1) / kChunk), kThreads, smem, stream>>>(grads[h], t, C, P2);
+            MRCNN_LAUNCH_CHECK();
+            gr[h] = t;
+            t += (size_t)N * C * P2;
+        }
+        if (heads == 1) gr[1] = gr[0];
+    }
     if (int rc = launch_gather_plan(g, ws, workspace, heads, pools, boxes, box_index, stream)) return rc;
-    return launch_gather_run(g, heads, grads, gfm, accumulate, stream);
+    return launch_gather_run(g, heads, gr, gfm, accumulate, stream, gfm_layout == MRCNN_NCHW ? 1 : 0);
 }
 
 static int check_layout(int v, const char* what) {
@@ -1849,6 +1978,15 @@ static int check_layout(int v, const char* what) {
 using namespace mrcnn;
 
 extern "C" {
+
+size_t mrcnn_pyramid_roi_align_backward_workspace_bytes_ex(const int H[4], const int W[4], int B, int C, int N, int pool, int grads_layout) {
+    if (!H || !W || B <= 0 || C <= 0 || N < 0 || pool <= 0) return 256;
+    for (int l = 0; l < 4; ++l)
+        if (H[l] <= 0 || W[l] <= 0) return 256;
+    size_t b = carve_gather(nullptr, H, W, B, N, (long long)pool * pool).bytes;
+    if (grads_layout == MRCNN_NCHW) b += align_up((size_t)(N > 0 ? N : 1) * C * (size_t)pool * pool * sizeof(float), 256);
+    return b;
+}
 
 size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const int W[4], int B, int N, int pool) {
     if (!H || !W || B <= 0 || N < 0 || pool <= 0) return 256;
@@ -1974,15 +2112,14 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
                             gather_eligible(H, W, B, C, N, (long long)pool * pool, pool, gfm_layout, grads_layout, grads, gfm, workspace, workspace_bytes);
     if (algo == MRCNN_BWD_GATHER)
         MRCNN_REQUIRE(can_gather,
-                      "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs channels-last grads and gfm, C %% 4 == 0, "
-                      "N > 0, N * pool^2 * C < 2^31, no image_offsets_host and a 256-byte aligned workspace of "
-                      "mrcnn_pyramid_roi_align_backward_workspace_bytes()");
+                      "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs C %% 4 == 0, N > 0, N * pool^2 * C < 2^31, no "
+                      "image_offsets_host and a 256-byte aligned workspace of mrcnn_pyramid_roi_align_backward_workspace_bytes_ex()");
     if (can_gather && algo != MRCNN_BWD_SCATTER) {
         // tile-owner gather: writes every pixel once (zero fill included), no atomics
         const float* const gr[2] = {grads, grads};
         const int pools[2] = {pool, pool};
         return launch_bwd_gather(1, gr, pools, H, W, B, C, boxes, box_index, N, image_area, gfm, zero_fill ? 0 : 1, workspace,
-                                 stream);
+                                 stream, grads_layout, gfm_layout);
     }
     if (image_offsets_host == nullptr) {
         if (zero_fill) {

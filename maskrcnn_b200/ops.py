@@ -352,12 +352,14 @@ class _PyramidRoiAlign(torch.autograd.Function):
                                                                    _stream()))
             return (None, None, None, None, None, None) + tuple(gfm)
         with torch.cuda.device(grad.device):
-            gather_ok = fl == NHWC and gl == NHWC and C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets
+            # the gather serves every layout combination (NCHW gradient maps sector-wise, NCHW upstream gradients through a
+            # transposed copy in its workspace); the scatter remains for C % 4 != 0, huge RoI sets and the image-by-image mode
+            gather_ok = C % 4 == 0 and N > 0 and N * pool * pool * C < 2 ** 31 and not offsets
             algo = {"auto": _lib.BWD_AUTO, "gather": _lib.BWD_GATHER if gather_ok else _lib.BWD_SCATTER,
                     "scatter": _lib.BWD_SCATTER}[BACKWARD_ALGORITHM]
             ws_bytes, ws = 0, None
             if gather_ok and algo != _lib.BWD_SCATTER:
-                ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(_lib.i4(Hs), _lib.i4(Ws), B, N, pool)
+                ws_bytes = lib.mrcnn_pyramid_roi_align_backward_workspace_bytes_ex(_lib.i4(Hs), _lib.i4(Ws), B, C, N, pool, gl)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad.device)
             check(lib.mrcnn_pyramid_roi_align_backward(_ptr(grad) if N else None, gl, _lib.i4(Hs), _lib.i4(Ws), B, C,
                                                        _ptr(boxes) if N else None, _ptr(box_ind), N, pool, image_area,

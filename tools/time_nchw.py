@@ -56,8 +56,13 @@ def main():
                                                                           out.data_ptr(), L.NCHW, None, st)))
         res["fwd%d" % pool] = {"ms": t * 1e3, "frac_of_hbm": fb / t / 1e9 / hbm}
         t = time_op(lambda: L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, Hs, Ws, B, C, boxes.data_ptr(), ind.data_ptr(), N,
-                                                                           pool, area, pg, L.NCHW, 1, None, L.BWD_AUTO, None, 0, st)))
-        res["bwd%d_whole_batch" % pool] = {"ms": t * 1e3, "frac_of_hbm": bb / t / 1e9 / hbm}
+                                                                           pool, area, pg, L.NCHW, 1, None, L.BWD_SCATTER, None, 0, st)))
+        res["bwd%d_scatter" % pool] = {"ms": t * 1e3, "frac_of_hbm": bb / t / 1e9 / hbm}
+        ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes_ex(Hs, Ws, B, C, N, pool, L.NCHW), dtype=torch.uint8, device=dev)
+        t = time_op(lambda: L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, Hs, Ws, B, C, boxes.data_ptr(), ind.data_ptr(), N,
+                                                                           pool, area, pg, L.NCHW, 1, None, L.BWD_GATHER, ws.data_ptr(), ws.numel(), st)))
+        res["bwd%d_gather" % pool] = {"ms": t * 1e3, "frac_of_hbm": bb / t / 1e9 / hbm}
+        del ws
         t = time_op(lambda: L.check(L.lib.mrcnn_pyramid_roi_align_backward(grad.data_ptr(), L.NCHW, Hs, Ws, B, C, boxes.data_ptr(), None, N,
                                                                            pool, area, pg, L.NCHW, 1, offs_p, L.BWD_AUTO, None, 0, st)))
         res["bwd%d_image_by_image" % pool] = {"ms": t * 1e3, "frac_of_hbm": bb / t / 1e9 / hbm}
