@@ -1179,6 +1179,8 @@ __device__ __forceinline__ void bulk_s2g_and_wait(void* dst_gmem, const void* sr
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// (Fetching two feature rows ahead of the walk - registers A / B alternating, 64 registers - measured slower: 7x7 0.424 ms against
+// 0.335 ms, 14x14 0.881 against 0.859 at the configs[3] geometry; the simple walk below stays.)
 constexpr int kNchwCW = 8;  // channels per warp
 
 template <int POOL>
@@ -1191,8 +1193,6 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     extern __shared__ __align__(128) float s_out[];  // [8 warps][8 channels][P2]: the outputs in global order
     __shared__ TapS s_ty[POOL];
     __shared__ TapS s_tx[POOL];
-    __shared__ int s_rows[2 * POOL];   // plane offsets of the feature rows in the order the walk fetches them
-    __shared__ int s_nrows;
 
     const int chunks = (p.C + kChunk - 1) / kChunk;
     const int n = blockIdx.x / chunks;
@@ -1204,20 +1204,6 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     const RoiCtx ctx = select_level(p, n, box);
     stage_taps_nchw(ctx, box, POOL, POOL, s_ty, s_tx);
     __syncthreads();
-    if (tid == 0) {  // the walk below, rows only: which feature row is fetched when (so that fetches can run ahead of it)
-        int nr = 0, ra = -1, rb = -1;
-        for (int y = 0; y < POOL; ++y) {
-            const TapS ty = s_ty[y];
-            if (!ty.valid) continue;
-            if (ty.lo == rb) { ra = rb; rb = -1; }
-            else if (ty.lo != ra) { s_rows[nr++] = ty.lo; ra = ty.lo; }
-            if (ty.hi == ra) rb = ra;
-            else if (ty.hi != rb) { s_rows[nr++] = ty.hi; rb = ty.hi; }
-        }
-        MRCNN_DBG(nr <= 2 * POOL);
-        s_nrows = nr;
-    }
-    __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int cw0 = c0 + warp * kNchwCW;              // the warp's first channel
@@ -1228,7 +1214,6 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
     const bool col = x < POOL;
     const TapS tx = s_tx[col ? x : 0];
     const bool x_in = col && tx.valid;
-    const int nrows = s_nrows;
     // 32-bit element offsets from the image's base (the launcher guarantees C * H * W < 2^31): one IMAD.WIDE per load
     const unsigned plane = (unsigned)(ctx.H * ctx.W);
     const float* base = ctx.base;
@@ -1242,36 +1227,6 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
         olo[k] = o + (unsigned)tx.lo;
         ohi[k] = o + (unsigned)tx.hi;
     }
-
-    // two feature rows of taps are always in flight (registers A and B, alternating): the row the walk needs next and the one
-    // after it were requested one and two steps ago
-    float alo[K], ahi[K], blo[K], bhi[K];
-    auto fetch = [&](int i, float (&lo)[K], float (&hi)[K]) {
-        if (i < nrows) {
-            const unsigned row = (unsigned)s_rows[i];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                MRCNN_DBG(!live[k] || ohi[k] + row < (unsigned)C * plane);
-                lo[k] = live[k] ? __ldg(base + (olo[k] + row)) : 0.f;
-                hi[k] = live[k] ? __ldg(base + (ohi[k] + row)) : 0.f;
-            }
-        }
-    };
-    fetch(0, alo, ahi);
-    fetch(1, blo, bhi);
-    int next = 0;
-    auto take = [&](float (&H)[K]) {   // H of the next row of the list; its registers go back to work for the row two ahead
-        if ((next & 1) == 0) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) H[k] = __fadd_rn(alo[k], __fmul_rn(__fsub_rn(ahi[k], alo[k]), tx.lerp));
-            fetch(next + 2, alo, ahi);
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) H[k] = __fadd_rn(blo[k], __fmul_rn(__fsub_rn(bhi[k], blo[k]), tx.lerp));
-            fetch(next + 2, blo, bhi);
-        }
-        ++next;
-    };
 
     int ra = -1, rb = -1;  // feature rows (as plane offsets) whose horizontal blends Ha / Hb hold
     float Ha[K], Hb[K];
@@ -1289,8 +1244,15 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 ra = rb;
                 rb = -1;
             } else if (ty.lo != ra) {
-                MRCNN_DBG(next < nrows && s_rows[next] == ty.lo);
-                take(Ha);
+                float lo[K], hi[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    MRCNN_DBG(!live[k] || ohi[k] + (unsigned)ty.lo < (unsigned)C * plane);
+                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.lo)) : 0.f;
+                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.lo)) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) Ha[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
                 ra = ty.lo;
             }
             if (ty.hi == ra) {            // y_lerp == 0: the ceil row is the floor row
@@ -1298,8 +1260,14 @@ __global__ void __launch_bounds__(256) roialign_fwd_nchw_kernel(const RoiParams 
                 for (int k = 0; k < K; ++k) Hb[k] = Ha[k];
                 rb = ra;
             } else if (ty.hi != rb) {
-                MRCNN_DBG(next < nrows && s_rows[next] == ty.hi);
-                take(Hb);
+                float lo[K], hi[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    lo[k] = live[k] ? __ldg(base + (olo[k] + (unsigned)ty.hi)) : 0.f;
+                    hi[k] = live[k] ? __ldg(base + (ohi[k] + (unsigned)ty.hi)) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) Hb[k] = __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), tx.lerp));
                 rb = ty.hi;
             }
 #pragma unroll
@@ -2114,7 +2082,17 @@ int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const
         MRCNN_REQUIRE(can_gather,
                       "mrcnn_pyramid_roi_align_backward: MRCNN_BWD_GATHER needs C %% 4 == 0, N > 0, N * pool^2 * C < 2^31, no "
                       "image_offsets_host and a 256-byte aligned workspace of mrcnn_pyramid_roi_align_backward_workspace_bytes_ex()");
-    if (can_gather && algo != MRCNN_BWD_SCATTER) {
+    // With an NCHW gradient pyramid or NCHW upstream gradients the gather pays a transposed copy of the gradients and
+    // sector-scattered pyramid writes: measured on B200 at the configs[3] geometry it wins for the 7x7 head (0.81 ms against 1.10 ms
+    // for clear + scatter) and loses for the 14x14 head (1.64 against 1.44).  MRCNN_BWD_AUTO takes it when the upstream gradients
+    // are smaller than the pyramid they scatter into.
+    bool prefer_gather = true;
+    if (gfm_layout == MRCNN_NCHW || grads_layout == MRCNN_NCHW) {
+        double pyr = 0;
+        for (int l = 0; l < 4; ++l) pyr += (double)per_image[l] * B;
+        prefer_gather = (double)N * C * pool * pool < pyr;
+    }
+    if (can_gather && algo != MRCNN_BWD_SCATTER && (prefer_gather || algo == MRCNN_BWD_GATHER)) {
         // tile-owner gather: writes every pixel once (zero fill included), no atomics
         const float* const gr[2] = {grads, grads};
         const int pools[2] = {pool, pool};
