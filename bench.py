@@ -1167,6 +1167,7 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
     ind = (torch.arange(b, e, device=dev, dtype=torch.int32) % wl.batch).repeat_interleave(D)   # image i reads pyramid i % 16
 
     ex = mdist.DetectionExchange(TOTAL, D)
+    side_c = torch.cuda.Stream()
     L = wl.L
     masks_in = torch.empty((Bl * D, CHANNELS, 14, 14), device=dev, memory_format=torch.channels_last)
     fmp = L.vp4([f.data_ptr() for f in wl.fm])
@@ -1175,9 +1176,13 @@ def sharded_detection(torch, dist, wl, world, rank, hbm):
         """Three launches: detection layer fused with the sending half of the exchange (it also writes the mask head's RoIs),
         the 14x14 RoIAlign of the detections, the collecting half."""
         ex.run(rois, probs, deltas, win, 0.0, 0.3, ind_offset=b, ind_mod=wl.batch)
+        cur = torch.cuda.current_stream()
+        side_c.wait_stream(cur)
+        with torch.cuda.stream(side_c):          # the collecting half runs beside the RoIAlign: it only needs the peers' flags
+            all_dets, all_counts = ex.collect()
         L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, wl.batch, CHANNELS, L.NHWC, ex.mask_boxes.data_ptr(),
                                                       ex.mask_box_ind.data_ptr(), Bl * D, 14, wl.area, masks_in.data_ptr(), L.NHWC, None, wl._s()))
-        all_dets, all_counts = ex.collect()
+        cur.wait_stream(side_c)
         return masks_in, all_dets, all_counts
 
     def run_nccl():

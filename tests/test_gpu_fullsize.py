@@ -275,3 +275,34 @@ def test_detection_exchange_single_rank_matches_detection_layer(ops):
         all_d, all_c = ex.collect()
         assert torch.equal(all_d, want) and torch.equal(all_c, want_c)
     assert int(ex.state[0]) == 3 and int(ex.state[1]) == 0
+
+
+@pytest.mark.parametrize("variant", ["row", "tma"])
+def test_fwd14_kernel_variants_are_bit_identical(variant):
+    """The two measured alternatives to the default 14x14 channels-last forward kernel (MRCNN_FWD14=row: row-walking with the
+    separable blend cached per feature row; =tma: producer thread + mbarrier ring of bulk row loads, bulk row stores) produce
+    the default kernel's bytes at the configs[3] geometry.  The choice is fixed per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, hashlib, numpy as np, torch
+sys.path.insert(0, %r)
+import maskrcnn_b200 as m
+from maskrcnn_b200 import synth
+g = torch.Generator(device="cuda"); g.manual_seed(7)
+fms = [torch.randn((4, 256, s, s), device="cuda", generator=g).contiguous(memory_format=torch.channels_last) for s in (256, 128, 64, 32)]
+boxes = np.concatenate([synth.random_rois(512, 50 + i) for i in range(4)])
+boxes[0] = [0.0, 0.0, 1.0, 1.0]; boxes[1] = [0.2, -0.3, 0.9, 1.4]; boxes[2] = [0.5, 0.5, 0.5, 0.5]; boxes[3] = [0.9, 0.1, 0.1, 0.9]
+ind = torch.arange(4, dtype=torch.int32, device="cuda").repeat_interleave(512)
+out = m.pyramid_roi_align(fms, torch.from_numpy(boxes).cuda(), ind, 14, (1024, 1024, 3))
+m.check_device_errors()
+print(hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest())
+''' % root
+    digests = {}
+    for v in ("col", variant):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MRCNN_FWD14=v), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[v] = r.stdout.strip().splitlines()[-1]
+    assert digests["col"] == digests[variant]
