@@ -997,16 +997,22 @@ def secondary(torch, wl, hbm):
     boxes = torch.from_numpy(boxes_np).to(dev)
     fm1 = [f_[:1] for f_ in wl.fm]
     for pool in (7, 14):
-        g = lambda: m.pyramid_roi_align(fm1, boxes, None, pool, (IMAGE, IMAGE, 3), out_channels_last=False)  # noqa: E731
+        inputs1 = [boxes.unsqueeze(0)] + list(fm1)
+        g = lambda: m.roi_align(inputs1, pool, [IMAGE, IMAGE, 3])  # noqa: E731   (the reference's call, model.py:276)
         t = wl.time_op(g, iters=50)
+        g_nchw = lambda: m.pyramid_roi_align(fm1, boxes, None, pool, (IMAGE, IMAGE, 3), out_channels_last=False)  # noqa: E731
+        t_nchw = wl.time_op(g_nchw, iters=50)
         U, _ = roofline.unique_taps(boxes_np, None, pool, (IMAGE, IMAGE), LEVEL_HW, 1)
         by = roofline.roialign_fwd_bytes(1000, CHANNELS, pool, U)
         out["roialign_fwd_%dx%d" % (pool, pool)] = {"config": "configs[2]: 1000 RoIs x 256 ch, one image (warm L2: 89 MB pyramid fits)",
                                                     "rois_per_s": 1000 / t, "us": t * 1e6, "algorithmic_MB": by / 1e6,
                                                     "algorithmic_GBps": by / t / 1e9, "frac_of_hbm": by / t / 1e9 / hbm,
-                                                    "note": "through ops.pyramid_roi_align with NCHW crops: at 1000 RoIs the kernel is "
-                                                            "shorter than the Python call that issues it (autograd node, allocation, "
-                                                            "ctypes), so this figure is bounded by the host; `direct_abi` has the kernel"}
+                                                    "through_ops_nchw_crops": {"us": t_nchw * 1e6, "rois_per_s": 1000 / t_nchw,
+                                                                               "frac_of_hbm": by / t_nchw / 1e9 / hbm},
+                                                    "note": "through the drop-in ops.roi_align(inputs, pool, image_shape) on a channels-last "
+                                                            "pyramid: the crops follow the pyramid's memory format (channels-last, what the "
+                                                            "heads' cuDNN convolutions take natively); `through_ops_nchw_crops` forces "
+                                                            "NCHW-contiguous crops (out_channels_last=False), `direct_abi` is the bare C call"}
         # the same launch straight through the C ABI into a preallocated output (what wl.fwd does for the headline), for
         # both crop layouts: takes the host-side call overhead out of a ~20 us kernel.  Guarded: an extra.
         try:

@@ -237,6 +237,15 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
                 }
                 if (kOutNHWC) {
                     stg_f4_stream(out_nhwc + b * C, v);
+                } else if (POOL == 7 || POOL == 14) {
+                    // the tile mirrors the output ([channel][bin], the four channels of a lane adjacent): it leaves with bulk
+                    // copies.  Rows are P2 floats apart; at 14x14 (P2 = 196 = 4 mod 32) every group of four rows is skewed by
+                    // four more floats, which keeps the stores at the 2-way bank conflict an odd pitch would give
+                    float* t = tile + (4 * lane) * P2 + (POOL == 14 ? 4 * lane : 0) + b;
+                    t[0] = v.x;
+                    t[P2] = v.y;
+                    t[2 * P2] = v.z;
+                    t[3 * P2] = v.w;
                 } else {
                     float* t = tile + ((4 * lane) * P2pad + b);
                     t[0] = v.x;
@@ -248,10 +257,34 @@ __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_kernel(const Ro
         }
     }
     if (!kOutNHWC) {
-        __syncthreads();
         const int cc = min(kChunk, C - c0);
-        // contiguous [cc][P2] block of the NCHW output
-        tile_copy<false>(tile, p.crops + ((size_t)n * C + c0) * P2, cc * P2, P2, P2pad);
+        float* dst = p.crops + ((size_t)n * C + c0) * P2;   // contiguous [cc][P2] block of the NCHW output
+        if (POOL == 7 || POOL == 14) {
+            // TMA epilogue: no second pass through the load/store pipe.  7x7: the whole [cc][49] block is one copy; 14x14: one copy
+            // per group of four channel rows (3136 bytes each, 16-byte aligned on both sides)
+            fence_proxy_async();
+            __syncthreads();
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            if (POOL == 7) {
+                if (tid == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(tile)),
+                                 "r"((uint32_t)(cc * P2 * 4)), "l"(policy)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+            } else if (tid < cc / 4) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + (size_t)tid * 4 * P2),
+                             "r"(smem_u32(tile + tid * (4 * P2 + 4))), "r"((uint32_t)(4 * P2 * 4)), "l"(policy)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
+            __syncthreads();
+            tile_copy<false>(tile, dst, cc * P2, P2, P2pad);
+        }
     }
 }
 
