@@ -35,7 +35,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 def test_recorded_own_arm_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")))
     assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline"} <= set(d)
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32" and d["gpu_launches"] > 0
     r = d["roofline"]

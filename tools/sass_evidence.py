@@ -1,5 +1,5 @@
 """Per-kernel counts of the SASS mnemonics that show which hardware paths libmrcnn_b200.so uses (cuobjdump -sass; no GPU
-needed).  usage: python tools/sass_evidence.py  ->  profiles/r01_sass_evidence.txt"""
+needed).  usage: python tools/sass_evidence.py  ->  profiles/r02_sass_evidence.txt"""
 import os
 import re
 import subprocess
@@ -22,7 +22,7 @@ def main():
         name = part.split("\n", 1)[0].strip()
         dem = subprocess.run(["c++filt", "-p", name], capture_output=True, text=True).stdout.strip() or name
         rows.append((dem.replace("mrcnn::", ""), {k: len(re.findall(v, part)) for k, v in PATS.items()}))
-    out = os.path.join(ROOT, "profiles", "r01_sass_evidence.txt")
+    out = os.path.join(ROOT, "profiles", "r02_sass_evidence.txt")
     with open(out, "w") as f:
         f.write("# cuobjdump -sass maskrcnn_b200/libmrcnn_b200.so (sm_100a): per kernel, how many instructions of each kind\n"
                 "# (only the mnemonics that show which hardware path a kernel uses).  Regenerate: python tools/sass_evidence.py\n\n")
