@@ -92,6 +92,15 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const in
                                     float image_area, float* out, int out_layout,
                                     int32_t* levels_out, mrcnn_stream_t stream);
 
+/* Both heads' forward in ONE launch: the same RoIs pooled at 7x7 (box head, model.py:778) and 14x14 (mask head, model.py:889)
+ * from a channels-last pyramid into channels-last crops out7 [N,C,7,7] / out14 [N,C,14,14] (C % 4 == 0, everything 16-byte
+ * aligned).  Each CTA computes a RoI's 14x14 bins and then its 7x7 bins, whose taps lie inside the footprint the first pass has
+ * just read: the second head costs its output bytes and almost no DRAM reads.  Bit-identical to two
+ * mrcnn_pyramid_roi_align_forward calls (pool 7 and pool 14, extrapolation value 0). */
+MRCNN_API int mrcnn_pyramid_roi_align_forward_pair(const float* const fm[4], const int H[4], const int W[4],
+                                    int B, int C, const float* boxes, const int32_t* box_index, int N,
+                                    float image_area, float* out7, float* out14, mrcnn_stream_t stream);
+
 /* Adjoint of the forward: grads [N,C,pool,pool] (grads_layout) accumulated into gfm[l] [B,C,H[l],W[l]]
  * (gfm_layout), which is cleared first when zero_fill != 0 (what CropFunction.backward does per level,
  * c++ext/maskrcnn/__init__.py:52).  No gradient w.r.t. boxes (model.py:358).

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mrcnn_crop_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _i, _vp]),
     "mrcnn_crop_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrcnn_pyramid_roi_align_forward": (_i, [_vp4, _i4, _i4, _i, _i, _i, _vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp]),
+    "mrcnn_pyramid_roi_align_forward_pair": (_i, [_vp4, _i4, _i4, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "mrcnn_pyramid_roi_align_backward_workspace_bytes": (_sz, [_i4, _i4, _i, _i, _i]),
     "mrcnn_pyramid_roi_align_backward_workspace_bytes_ex": (_sz, [_i4, _i4, _i, _i, _i, _i, _i]),
     "mrcnn_pyramid_roi_align_backward": (_i, [_vp, _i, _i4, _i4, _i, _i, _vp, _vp, _i, _i, _f, _vp4, _i, _i, _vp, _i, _vp, _sz, _vp]),

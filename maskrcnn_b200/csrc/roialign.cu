@@ -42,6 +42,7 @@ struct RoiParams {
     int ph, pw;
     float extrap;
     float* crops;  // forward: output; backward: incoming gradient (read-only)
+    float* crops_b;  // fused two-head forward: the second head's output (pool 7), else unused
     float negzero;  // -0.0f, opaque to ptxas (see bilerp4)
     int32_t* levels_out;
     int* err;
@@ -359,6 +360,92 @@ __global__ void __launch_bounds__(SLOTS * LANES, 1024 / (SLOTS * LANES)) roialig
             stg_f4_stream(out + (unsigned)(y1 * POOL * C), vb);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward of BOTH heads in one launch (training and inference pool the same RoIs twice from the same pyramid: 7x7 for the box
+// head, model.py:778, and 14x14 for the mask head, model.py:889).  Same CTA (RoI x 64 channels) and the same column-stationary
+// threads as above, first the 14x14 bins, then the 7x7 bins of the same RoI: the 7x7 taps lie inside the footprint the 14x14
+// pass has just pulled through L1 / L2, so the second head costs its output bytes and (almost) no DRAM reads - 0.58 GB of the
+// 8.29 GB a configs[3] step moves.  The arithmetic per bin is the single-head kernel's, so both outputs are bit-identical to it.
+// ------------------------------------------------------------------------------------------------
+template <int POOL, int SLOTS>
+__device__ __forceinline__ void col_pass(const RoiParams& p, const RoiCtx& ctx, const TapS* s_ty, const TapS* s_tx, int n, int c, float* crops) {
+    constexpr int kPhases = SLOTS / POOL;
+    const int slot = threadIdx.x / kLanes;
+    if (slot >= POOL * kPhases) return;
+    const int C = p.C;
+    const int phase = slot / POOL;
+    const int x = slot - phase * POOL;
+    const TapS tx = s_tx[x];
+    const float* src_lo = ctx.base + c + (unsigned)tx.lo;
+    const float* src_hi = ctx.base + c + (unsigned)tx.hi;
+    float* out = crops + ((size_t)n * (POOL * POOL) + x) * C + c;
+    const float4 ext = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+#pragma unroll 1
+    for (int y0 = phase; y0 < POOL; y0 += 2 * kPhases) {
+        const int y1 = y0 + kPhases;
+        const bool has1 = y1 < POOL;
+        const TapS ta = s_ty[y0];
+        const TapS tb = s_ty[has1 ? y1 : y0];
+        const bool in_a = ta.valid && tx.valid;
+        const bool in_b = has1 && tb.valid && tx.valid;
+        float4 tl0, tr0, bl0, br0, tl1, tr1, bl1, br1;
+        if (in_a) {
+            tl0 = ldg_f4(src_lo + (unsigned)ta.lo);
+            tr0 = ldg_f4(src_hi + (unsigned)ta.lo);
+            bl0 = ldg_f4(src_lo + (unsigned)ta.hi);
+            br0 = ldg_f4(src_hi + (unsigned)ta.hi);
+        }
+        if (in_b) {
+            tl1 = ldg_f4(src_lo + (unsigned)tb.lo);
+            tr1 = ldg_f4(src_hi + (unsigned)tb.lo);
+            bl1 = ldg_f4(src_lo + (unsigned)tb.hi);
+            br1 = ldg_f4(src_hi + (unsigned)tb.hi);
+        }
+        const float4 va = in_a ? bilerp4(tl0, tr0, bl0, br0, tx.lerp, ta.lerp, p.negzero) : ext;
+        stg_f4_stream(out + (unsigned)(y0 * POOL * C), va);
+        if (has1) {
+            const float4 vb = in_b ? bilerp4(tl1, tr1, bl1, br1, tx.lerp, tb.lerp, p.negzero) : ext;
+            stg_f4_stream(out + (unsigned)(y1 * POOL * C), vb);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_pair_kernel(const RoiParams p) {
+    __shared__ TapS s_ty14[14], s_tx14[14], s_ty7[8], s_tx7[8];
+    const int chunks = (p.C + kChunk - 1) / kChunk;
+    const int n = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x - n * chunks) * kChunk;
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps(p, ctx, box, 14, 14, s_ty14, s_tx14);
+    // the 7x7 taps: threads [32, 39) rows, [96, 103) columns (stage_taps uses [0, ph) and [64, 64 + pw))
+    {
+        const int tid = threadIdx.x;
+        if (tid >= 32 && tid < 39) {
+            const AxisTap t = axis_tap(box.x, box.z, ctx.H, 7, tid - 32);
+            TapS o;
+            o.valid = (t.lo >= 0) && ctx.ok;
+            o.lo = o.valid ? t.lo * ctx.W * p.C : 0;
+            o.hi = o.valid ? t.hi * ctx.W * p.C : 0;
+            o.lerp = t.lerp;
+            s_ty7[tid - 32] = o;
+        } else if (tid >= 96 && tid < 103) {
+            const AxisTap t = axis_tap(box.y, box.w, ctx.W, 7, tid - 96);
+            TapS o;
+            o.valid = (t.lo >= 0) && ctx.ok;
+            o.lo = o.valid ? t.lo * p.C : 0;
+            o.hi = o.valid ? t.hi * p.C : 0;
+            o.lerp = t.lerp;
+            s_tx7[tid - 96] = o;
+        }
+    }
+    __syncthreads();
+    const int c = c0 + 4 * (threadIdx.x % kLanes);
+    if (c >= p.C) return;  // C % 4 == 0 is guaranteed by the launcher
+    col_pass<14, kSlots>(p, ctx, s_ty14, s_tx14, n, c, p.crops);
+    col_pass<7, kSlots>(p, ctx, s_ty7, s_tx7, n, c, p.crops_b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2075,6 +2162,43 @@ int mrcnn_pyramid_roi_align_forward(const float* const fm[4], const int H[4], co
     p.err = device_error_word();
     MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
     return launch_roi(p, fm_layout, out_layout, false, (cudaStream_t)stream);
+}
+
+int mrcnn_pyramid_roi_align_forward_pair(const float* const fm[4], const int H[4], const int W[4], int B, int C,
+                                         const float* boxes, const int32_t* box_index, int N, float image_area, float* out7,
+                                         float* out14, mrcnn_stream_t stream) {
+    MRCNN_REQUIRE(fm && H && W, "mrcnn_pyramid_roi_align_forward_pair: null level tables");
+    MRCNN_REQUIRE(B > 0 && C > 0 && N >= 0 && image_area > 0.f, "mrcnn_pyramid_roi_align_forward_pair: bad sizes");
+    MRCNN_REQUIRE((C % 4) == 0, "mrcnn_pyramid_roi_align_forward_pair: channels-last tensors with C %% 4 == 0");
+    if (N == 0) return MRCNN_OK;
+    RoiParams p = {};
+    for (int l = 0; l < 4; ++l) {
+        MRCNN_REQUIRE(H[l] > 0 && W[l] > 0, "mrcnn_pyramid_roi_align_forward_pair: level %d has empty shape", l);
+        MRCNN_REQUIRE_DEV(fm[l]);
+        MRCNN_REQUIRE(aligned16(fm[l]), "mrcnn_pyramid_roi_align_forward_pair: level %d is not 16-byte aligned", l);
+        MRCNN_REQUIRE((long long)H[l] * W[l] * C < (1ll << 31), "mrcnn_pyramid_roi_align_forward_pair: level %d too large for 32-bit offsets", l);
+        p.lv[l] = {const_cast<float*>(fm[l]), H[l], W[l]};
+    }
+    MRCNN_REQUIRE_DEV(boxes);
+    MRCNN_REQUIRE_DEV(out7);
+    MRCNN_REQUIRE_DEV(out14);
+    if (box_index) MRCNN_REQUIRE_DEV(box_index);
+    MRCNN_REQUIRE(aligned16(out7) && aligned16(out14), "mrcnn_pyramid_roi_align_forward_pair: outputs must be 16-byte aligned");
+    const long long grid = (long long)N * ((C + kChunk - 1) / kChunk);
+    MRCNN_REQUIRE(grid < (1ll << 31) && (long long)196 * C < (1ll << 31), "mrcnn_pyramid_roi_align_forward_pair: too many RoIs");
+    p.pyramid = 1;
+    p.rule = make_level_rule(image_area);
+    p.B = B; p.C = C;
+    p.boxes = boxes; p.box_index = box_index; p.N = N;
+    p.ph = 14; p.pw = 14; p.extrap = 0.f;
+    p.crops = out14;
+    p.crops_b = out7;
+    p.negzero = -0.0f;
+    p.err = device_error_word();
+    MRCNN_REQUIRE(p.err != nullptr, "cannot allocate device error word");
+    roialign_fwd_nhwc_pair_kernel<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+    MRCNN_LAUNCH_CHECK();
+    return MRCNN_OK;
 }
 
 int mrcnn_pyramid_roi_align_backward(const float* grads, int grads_layout, const int H[4], const int W[4], int B,

@@ -694,8 +694,16 @@ class _PyramidRoiAlignPair(torch.autograd.Function):
         Hs = [f.shape[2] for f in fms]
         Ws = [f.shape[3] for f in fms]
         outs = []
+        if {pool_a, pool_b} == {7, 14} and C % 4 == 0 and N > 0:
+            # the two heads of Mask R-CNN: ONE launch (each CTA pools its RoI at 14x14, then at 7x7 from the footprint it just read)
+            o7, o14 = _empty4((N, C, 7, 7), NHWC, fms[0]), _empty4((N, C, 14, 14), NHWC, fms[0])
+            with torch.cuda.device(fms[0].device):
+                check(lib.mrcnn_pyramid_roi_align_forward_pair(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws), B, C,
+                                                               boxes.data_ptr(), _ptr(box_ind), N, float(image_area), o7.data_ptr(),
+                                                               o14.data_ptr(), _stream()))
+            outs = [o7, o14] if pool_a == 7 else [o14, o7]
         with torch.cuda.device(fms[0].device):
-            for pool in (pool_a, pool_b):
+            for pool in (() if outs else (pool_a, pool_b)):
                 out = _empty4((N, C, pool, pool), NHWC, fms[0])
                 check(lib.mrcnn_pyramid_roi_align_forward(_lib.vp4([f.data_ptr() for f in fms]), _lib.i4(Hs), _lib.i4(Ws), B, C, fl,
                                                           boxes.data_ptr(), _ptr(box_ind), N, pool, float(image_area),

@@ -306,3 +306,22 @@ print(hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest())
         assert r.returncode == 0, r.stderr[-2000:]
         digests[v] = r.stdout.strip().splitlines()[-1]
     assert digests["col"] == digests[variant]
+
+
+def test_fused_two_head_forward_config3_and_wide_golden(ops):
+    """mrcnn_pyramid_roi_align_forward_pair (both heads in one launch, what the bench step issues): at the configs[3] geometry its
+    two outputs are the bytes of the two single-head launches; on the reference-recorded C = 40 pyramid (one partially filled
+    channel chunk) they are the reference's own roi_align outputs."""
+    fm, boxes, ind = _train_inputs(16, 512)
+    ts = [cl(f) for f in fm]
+    b, i = dev(boxes), dev(ind)
+    o7, o14 = ops.pyramid_roi_align_pair(ts, b, i, (7, 14), (IMAGE, IMAGE, 3))
+    assert torch.equal(o7, ops.pyramid_roi_align(ts, b, i, 7, (IMAGE, IMAGE, 3)))
+    assert torch.equal(o14, ops.pyramid_roi_align(ts, b, i, 14, (IMAGE, IMAGE, 3)))
+    o14b, o7b = ops.pyramid_roi_align_pair(ts, b, i, (14, 7), (IMAGE, IMAGE, 3))           # either order of the pool sizes
+    assert torch.equal(o7b, o7) and torch.equal(o14b, o14)
+    fms, gboxes, shape, pools = golden_pyr_wide()
+    g7, g14 = ops.pyramid_roi_align_pair([cl(dev(f)) for f in fms], dev(gboxes), None, (7, 14), shape)
+    np.testing.assert_array_equal(g7.cpu().numpy(), pools[7][0])
+    np.testing.assert_array_equal(g14.cpu().numpy(), pools[14][0])
+    ops.check_device_errors()

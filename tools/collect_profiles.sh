@@ -8,6 +8,8 @@ O=gpurun_out
 python bench.py --steps 20 --warmup 3 --no-extras > $O/${R}_bench_noextras.json 2> $O/${R}_bench_noextras.err || { echo "bench failed"; tail -5 $O/${R}_bench_noextras.err; exit 1; }
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $O/${R}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-extras > $O/${R}_launches.log 2>&1
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:"roialign_fwd_nhwc_pair" -c 2 \
+    -o $O/${R}_fwd_pair_nhwc python tools/prof_one.py pair 14 nhwc > $O/${R}_fwd_pair_nhwc.log 2>&1
 for spec in "fwd 7" "fwd 14" "bwd 7" "bwd 14"; do
     set -- $spec
     extra=""; [ "$1" = "bwd" ] && extra="gather"

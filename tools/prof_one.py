@@ -1,4 +1,4 @@
-"""Runs one RoIAlign variant a few times (for ncu).  usage: prof_one.py <fwd|bwd> <pool> <nchw|nhwc> [gather]"""
+"""Runs one RoIAlign variant a few times (for ncu).  usage: prof_one.py <fwd|bwd|pair> <pool> <nchw|nhwc> [gather]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +18,9 @@ if lay == "nhwc":
     o, g = o.contiguous(memory_format=cl), g.contiguous(memory_format=cl)
 ws = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_workspace_bytes(wl.Hs, wl.Ws, wl.batch, wl.N, pool), dtype=torch.uint8, device="cuda")
 for _ in range(3):
-    if kind == "fwd":
+    if kind == "pair":
+        wl.fwd_pair()
+    elif kind == "fwd":
         L.check(L.lib.mrcnn_pyramid_roi_align_forward(L.vp4([f.data_ptr() for f in wl.fm]), wl.Hs, wl.Ws, wl.batch, bench.CHANNELS, L.NHWC,
                                                       wl.boxes.data_ptr(), wl.ind.data_ptr(), wl.N, pool, wl.area, o.data_ptr(), lay_id, None, wl._s()))
     else:
