@@ -881,8 +881,7 @@ def secondary(torch, wl, hbm):
                                                             L.vp4([x.data_ptr() for x in wl.gfm14]), 1, ws2.data_ptr(), ws2.numel(), wl._s()))
 
     def step_fused():
-        wl.fwd(7, wl.out7)
-        wl.fwd(14, wl.out14)
+        wl.fwd_pair()
         wl.mask_targets()
         bwd_pair()
     if wl.cl_crops:
@@ -890,8 +889,8 @@ def secondary(torch, wl, hbm):
         ts = wl.time_op(step_fused, iters=20)
         by = (wl.g7.numel() + wl.g14.numel() + wl.batch * PYR_ELEMS_PER_IMAGE) * 4
         out["train_step_fused_backward"] = {
-            "config": "configs[3] with ONE backward for both heads: d/dP2..P5 = 7x7 head + 14x14 head, written once "
-                      "(mrcnn_pyramid_roi_align_backward_pair)", "rois_per_s": wl.N / ts, "ms_per_step": ts * 1e3,
+            "config": "configs[3] with ONE forward launch and ONE backward for both heads: d/dP2..P5 = 7x7 head + 14x14 head, written once "
+                      "(mrcnn_pyramid_roi_align_forward_pair + mrcnn_pyramid_roi_align_backward_pair = what ops.pyramid_roi_align_pair runs)", "rois_per_s": wl.N / ts, "ms_per_step": ts * 1e3,
             "backward_pair_ms": tb * 1e3, "backward_pair_algorithmic_MB": by / 1e6, "backward_pair_frac_of_hbm": by / tb / 1e9 / hbm,
             "note": "not the headline: the headline step returns the two heads' gradient pyramids separately, like the reference ops"}
     del ws2
