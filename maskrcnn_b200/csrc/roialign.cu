@@ -1084,7 +1084,13 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
     __shared__ QItem s_items[32 + U];
     __shared__ __align__(16) float4 s_data[ST][U][NV][32];
     const int wl = threadIdx.x;
-    const int u = blockIdx.x;
+    if (wl < U) {  // permanent no-op padding behind the 32 staged items
+        QItem z;
+        z.off = 0; z.wa = 0.f; z.wb = 0.f; z.idx = kONoop;
+        s_items[32 + wl] = z;
+    }
+    // The default grid has one CTA per unit (one trip through this loop); a smaller, persistent grid strides over the units.
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
 
     const int l = (u < p.g[2].unit_base) ? 3 : (u < p.g[1].unit_base) ? 2 : (u < p.g[0].unit_base) ? 1 : 0;
     const UnitGeom G = (l == 0) ? p.g[0] : (l == 1) ? p.g[1] : (l == 2) ? p.g[2] : p.g[3];
@@ -1118,16 +1124,10 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
                 }
             }
         }
-        return;
+        continue;
     }
     MRCNN_DBG(n > 0 && __ldg(p.pos + u) - n >= 0);
     const QItem* items = p.items + (__ldg(p.pos + u) - n);
-    if (wl < U) {  // permanent no-op padding behind the 32 staged items
-        QItem z;
-        z.off = 0; z.wa = 0.f; z.wb = 0.f; z.idx = kONoop;
-        s_items[32 + wl] = z;
-    }
-
     for (int cbase = 0; cbase < C; cbase += 128 * NV) {
         const int c = cbase + 4 * wl;
         const bool live = c < C;
@@ -1240,6 +1240,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
             }
         }
     }
+    }  // units
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2012,7 +2013,12 @@ static int launch_gather_run(GatherParams g, int heads, const float* const grads
     for (int l = 0; l < 4; ++l) g.g[l].ptr = gfm[l];
     g.grads = grads[0]; g.grads2 = grads[heads - 1];
     const bool wide = (g.C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
-    const unsigned grid = (unsigned)g.units;
+    // One one-warp CTA per unit: the block scheduler balances the uneven units (coarse levels collect most items) better than a
+    // persistent grid striding over them - MRCNN_GATHER_CTAS = 16 / 24 / 32 / 64 CTAs per SM measured 0.84 / 0.82 / 0.73 / 0.65 ms
+    // against 0.58 ms for the configs[3] 14x14 backward (profiles/r02_experiments.txt).  The kernel loops over units all the same.
+    static const int per_sm = getenv("MRCNN_GATHER_CTAS") ? atoi(getenv("MRCNN_GATHER_CTAS")) : 0;
+    const long long want = per_sm > 0 ? (long long)sm_count() * per_sm : (long long)g.units;
+    const unsigned grid = (unsigned)(want < (long long)g.units ? want : (long long)g.units);
     // U = 2 items per stage, ST = 4 stages: best of the (U, ST) grid measured on B200 (profiles/r01_*gather*)
     if (out_nchw) {
         if (wide && accumulate) roialign_bwd_gather_kernel<2, 2, 4, true, true><<<grid, 32, 0, stream>>>(g);
