@@ -1091,6 +1091,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
     }
     // The default grid has one CTA per unit (one trip through this loop); a smaller, persistent grid strides over the units.
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        do {  // one unit
 
     const int l = (u < p.g[2].unit_base) ? 3 : (u < p.g[1].unit_base) ? 2 : (u < p.g[0].unit_base) ? 1 : 0;
     const UnitGeom G = (l == 0) ? p.g[0] : (l == 1) ? p.g[1] : (l == 2) ? p.g[2] : p.g[3];
@@ -1124,7 +1125,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
                 }
             }
         }
-        continue;
+        break;
     }
     MRCNN_DBG(n > 0 && __ldg(p.pos + u) - n >= 0);
     const QItem* items = p.items + (__ldg(p.pos + u) - n);
@@ -1240,6 +1241,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
             }
         }
     }
+        } while (0);
     }  // units
 }
 
@@ -2015,7 +2017,8 @@ static int launch_gather_run(GatherParams g, int heads, const float* const grads
     const bool wide = (g.C % 256) == 0;  // 8 channels per lane: one pass covers 256 channels
     // One one-warp CTA per unit: the block scheduler balances the uneven units (coarse levels collect most items) better than a
     // persistent grid striding over them - MRCNN_GATHER_CTAS = 16 / 24 / 32 / 64 CTAs per SM measured 0.84 / 0.82 / 0.73 / 0.65 ms
-    // against 0.58 ms for the configs[3] 14x14 backward (profiles/r02_experiments.txt).  The kernel loops over units all the same.
+    // against 0.58 ms for the configs[3] 14x14 backward, and taking units from an atomic counter 0.66 ms (0.55 ms for the 7x7 head
+    // against 0.31: 174,080 atomics on one word) - profiles/r02_experiments.txt.  The kernel loops over units all the same.
     static const int per_sm = getenv("MRCNN_GATHER_CTAS") ? atoi(getenv("MRCNN_GATHER_CTAS")) : 0;
     const long long want = per_sm > 0 ? (long long)sm_count() * per_sm : (long long)g.units;
     const unsigned grid = (unsigned)(want < (long long)g.units ? want : (long long)g.units);
