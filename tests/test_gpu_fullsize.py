@@ -325,3 +325,31 @@ def test_fused_two_head_forward_config3_and_wide_golden(ops):
     np.testing.assert_array_equal(g7.cpu().numpy(), pools[7][0])
     np.testing.assert_array_equal(g14.cpu().numpy(), pools[14][0])
     ops.check_device_errors()
+
+
+@pytest.mark.parametrize("pool", [7, 14])
+@pytest.mark.parametrize("counts,C", [([40, 0, 25], 72), ([3, 130], 64), ([200], 136), ([0, 0, 9, 1], 8)])
+def test_nchw_backward_image_by_image_vs_oracle(ops, pool, counts, C):
+    """NCHW pyramid + NCHW gradients with the boxes grouped by image (rois_per_image: clear + scatter image by image) against the
+    oracle; images without boxes, partial channel chunks, stale values in the gradient buffers."""
+    size, B = 256, len(counts)
+    N = sum(counts)
+    fms = synth.feature_pyramid(B, C, 11 + C, image=size)
+    boxes = synth.random_rois(N, 12 + N, image=float(size), min_size=6, max_size=size * 0.9)
+    ind = np.repeat(np.arange(B, dtype=np.int32), counts)
+    ts = [dev(f).requires_grad_(True) for f in fms]
+    for t in ts:   # stale values: the kernel must clear every slice itself, also those of images without boxes
+        t.grad = torch.full_like(t, 3.0)
+    ops.set_backward_algorithm("scatter")
+    try:
+        out = ops.pyramid_roi_align(ts, dev(boxes), None, pool, (size, size, 3), rois_per_image=counts)
+        want, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, pool, float(size * size))
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
+        g = np.random.default_rng(pool + C).standard_normal(want.shape, dtype=np.float32)
+        grads = torch.autograd.grad(out, ts, dev(g))
+    finally:
+        ops.set_backward_algorithm("auto")
+    want_g = oracle.pyramid_roi_align_bwd(g, [f.shape for f in fms], boxes, ind, float(size * size))
+    for got, w in zip(grads, want_g):
+        assert rel_err(got.cpu().numpy(), w) <= BWD_TOL
+    ops.check_device_errors()
