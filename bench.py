@@ -329,89 +329,29 @@ def timed_steps(torch, dist, wl, steps, warmup, world, step=None):
 
 # ---------------------------------------------------------------------------------------------------
 def e2e_run(torch, dist, wl, steps, warmup, world, fused_backward=False):
-    """Host buffers in, host buffers out, every step: per image H2D -> 5 launches -> D2H over three streams.
-    fused_backward: both heads' backward as ONE gather into ONE gradient pyramid (mrcnn_pyramid_roi_align_backward_pair: what
-    autograd accumulates in a training step), so one pyramid of gradients (1.43 GB) crosses the host link instead of two."""
-    L = wl.L
-    B = wl.batch
+    """Host buffers in, host buffers out, every step, through the product's host-memory API (maskrcnn_b200.hoststep.HostTrainStep:
+    per image H2D -> kernels -> D2H over three streams).  fused_backward: both heads' backward as ONE gather into ONE gradient
+    pyramid (what autograd accumulates in a training step), so one pyramid of gradients (1.43 GB) crosses the host link, not two."""
+    from maskrcnn_b200.hoststep import HostTrainStep
+    hs = HostTrainStep(wl.batch, ROIS_PER_IMAGE, CHANNELS, LEVEL_HW, (IMAGE, IMAGE), fused_backward=fused_backward, device=wl.boxes.device)
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()  # noqa: E731
-    # host side: NHWC pyramid per level, boxes, upstream grads; results
-    h_fm = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
+    # host side (pinned, the device's physical order): pyramid, boxes, upstream gradients; results
+    h_fm = [hs.pinned_like(f) for f in wl.fm]
     for hf, f in zip(h_fm, wl.fm):
         hf.copy_(f.permute(0, 2, 3, 1))
     h_boxes = wl.boxes.cpu().pin_memory()
-    # crops / upstream gradients: host buffers in the device's physical order (views make both sides plain memcpys)
-    phys = (lambda t: t.permute(0, 2, 3, 1)) if wl.cl_crops else (lambda t: t)
-    d_g7, d_g14, d_out7, d_out14 = phys(wl.g7), phys(wl.g14), phys(wl.out7), phys(wl.out14)
-    h_g7, h_g14 = pin(d_g7), pin(d_g14)
-    h_g7.copy_(d_g7)
-    h_g14.copy_(d_g14)
-    h_out7, h_out14 = pin(d_out7), pin(d_out14)
-    h_gf7 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
-    h_gf14 = [pin(f.permute(0, 2, 3, 1)) for f in wl.fm]
-    h_mboxes, h_mind, h_mt = wl.mboxes.cpu().pin_memory(), wl.mind.cpu().pin_memory(), pin(wl.mt)
-    R, M = ROIS_PER_IMAGE, MASK_POS
-    s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    fm_nhwc = [f.permute(0, 2, 3, 1) for f in wl.fm]        # views on the device buffers (physically NHWC)
-    gf7_nhwc = [f.permute(0, 2, 3, 1) for f in wl.gfm7]
-    gf14_nhwc = [f.permute(0, 2, 3, 1) for f in wl.gfm14]
-    h2d = sum(t.numel() * 4 for t in h_fm) + h_boxes.numel() * 4 + h_g7.numel() * 4 + h_g14.numel() * 4 + \
-        h_mboxes.numel() * 4 + h_mind.numel() * 4
-    d2h = h_out7.numel() * 4 + h_out14.numel() * 4 + h_mt.numel() * 4 + (1 if fused_backward else 2) * sum(t.numel() * 4 for t in h_fm)
-    launches = [0]
-    ws_pair = None
-    if fused_backward:   # one image at a time: a per-image workspace, reused (the stream orders the uses)
-        ws_pair = torch.empty(L.lib.mrcnn_pyramid_roi_align_backward_pair_workspace_bytes(wl.Hs, wl.Ws, 1, ROIS_PER_IMAGE, 7, 14), dtype=torch.uint8,
-                              device=wl.boxes.device)
+    h_g7, h_g14 = hs.pinned_like(wl.g7), hs.pinned_like(wl.g14)
+    h_g7.copy_(wl.g7.permute(0, 2, 3, 1))
+    h_g14.copy_(wl.g14.permute(0, 2, 3, 1))
+    h_out7, h_out14 = hs.pinned_like(wl.out7), hs.pinned_like(wl.out14)
+    h_gfa = [hs.pinned_like(f) for f in wl.fm]
+    h_gfb = None if fused_backward else [hs.pinned_like(f) for f in wl.fm]
+    mask = {"d_images": wl.gt, "h_boxes": wl.mboxes.cpu().pin_memory(), "h_index": wl.mind.cpu().pin_memory(), "d_boxes": wl.mboxes,
+            "d_index": wl.mind, "d_targets": wl.mt, "h_targets": pin(wl.mt)}
+    h2d, d2h = hs.h2d_bytes(mask), hs.d2h_bytes(mask)
 
     def one_step():
-        ev_in = [torch.cuda.Event() for _ in range(B)]
-        ev_run = [torch.cuda.Event() for _ in range(B)]
-        for i in range(B):
-            rs = slice(i * R, (i + 1) * R)
-            ms = slice(i * M, (i + 1) * M)
-            with torch.cuda.stream(s_in):
-                for l in range(4):
-                    fm_nhwc[l][i].copy_(h_fm[l][i], non_blocking=True)
-                wl.boxes[rs].copy_(h_boxes[rs], non_blocking=True)
-                d_g7[rs].copy_(h_g7[rs], non_blocking=True)
-                d_g14[rs].copy_(h_g14[rs], non_blocking=True)
-                wl.mboxes[ms].copy_(h_mboxes[ms], non_blocking=True)
-                wl.mind[ms].copy_(h_mind[ms], non_blocking=True)
-                ev_in[i].record(s_in)
-            with torch.cuda.stream(s_run):
-                s_run.wait_event(ev_in[i])
-                st = s_run.cuda_stream
-                fmp = L.vp4([f[i].data_ptr() for f in wl.fm])
-                bp = wl.boxes[rs].data_ptr()
-                L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 7, wl.area,
-                                                              wl.out7[rs].data_ptr(), wl.crop_layout, None, st))
-                L.check(L.lib.mrcnn_pyramid_roi_align_forward(fmp, wl.Hs, wl.Ws, 1, CHANNELS, L.NHWC, bp, None, R, 14, wl.area,
-                                                              wl.out14[rs].data_ptr(), wl.crop_layout, None, st))
-                L.check(L.lib.mrcnn_crop_forward(wl.gt.data_ptr(), wl.gt.shape[0], 1, IMAGE, IMAGE, L.NCHW, wl.mboxes[ms].data_ptr(),
-                                                 wl.mind[ms].data_ptr(), M, 0.0, 28, 28, wl.mt[ms].data_ptr(), L.NCHW, st))
-                if fused_backward:
-                    L.check(L.lib.mrcnn_pyramid_roi_align_backward_pair(wl.g7[rs].data_ptr(), 7, wl.g14[rs].data_ptr(), 14, wl.Hs, wl.Ws, 1, CHANNELS,
-                                                                        bp, None, R, wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), 1,
-                                                                        ws_pair.data_ptr(), ws_pair.numel(), st))
-                    launches[0] += 9
-                else:
-                    L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g14[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 14,
-                                                                   wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm14]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
-                    L.check(L.lib.mrcnn_pyramid_roi_align_backward(wl.g7[rs].data_ptr(), wl.crop_layout, wl.Hs, wl.Ws, 1, CHANNELS, bp, None, R, 7,
-                                                                   wl.area, L.vp4([g[i].data_ptr() for g in wl.gfm7]), L.NHWC, 1, None, L.BWD_AUTO, None, 0, st))
-                    launches[0] += 7
-                ev_run[i].record(s_run)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_run[i])
-                h_out7[rs].copy_(d_out7[rs], non_blocking=True)
-                h_out14[rs].copy_(d_out14[rs], non_blocking=True)
-                h_mt[ms].copy_(wl.mt[ms], non_blocking=True)
-                for l in range(4):
-                    if not fused_backward:
-                        h_gf7[l][i].copy_(gf7_nhwc[l][i], non_blocking=True)
-                    h_gf14[l][i].copy_(gf14_nhwc[l][i], non_blocking=True)
-        torch.cuda.synchronize()
+        hs.run(h_fm, h_boxes, h_g7, h_g14, h_out7, h_out14, h_gfa, h_gfb, mask)
 
     for _ in range(max(1, min(warmup, 2))):
         one_step()
@@ -431,7 +371,7 @@ def e2e_run(torch, dist, wl, steps, warmup, world, fused_backward=False):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     return {"value": world * wl.N / dt, "unit": "RoIs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": dt * 1e3, "steps": n,
+            "ms_per_step": dt * 1e3, "steps": n, "api": "maskrcnn_b200.hoststep.HostTrainStep.run",
             "note": "PCIe-bound: every input and every result crosses the host link each step; per-image 3-stream pipeline"}
 
 

@@ -353,3 +353,53 @@ def test_nchw_backward_image_by_image_vs_oracle(ops, pool, counts, C):
     for got, w in zip(grads, want_g):
         assert rel_err(got.cpu().numpy(), w) <= BWD_TOL
     ops.check_device_errors()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_host_train_step_matches_device_ops(ops, fused):
+    """maskrcnn_b200.hoststep.HostTrainStep (pinned host tensors in and out, per-image three-stream pipeline: what bench.py's e2e leg
+    times) against the oracle: crops bit-exact, gradient pyramids <= 1e-5 (their sum when the two heads' backward is fused), mask
+    targets bit-exact."""
+    from maskrcnn_b200.hoststep import HostTrainStep
+    B, R, C, size, P, G = 3, 40, 72, 256, 6, 4
+    level_hw = [(size // s, size // s) for s in (4, 8, 16, 32)]
+    hs = HostTrainStep(B, R, C, level_hw, (size, size), fused_backward=fused)
+    rng = np.random.default_rng(3)
+    fms = synth.feature_pyramid(B, C, 21, image=size)
+    boxes = np.concatenate([synth.random_rois(R, 30 + i, image=float(size), min_size=6, max_size=size * 0.9) for i in range(B)])
+    ind = np.repeat(np.arange(B, dtype=np.int32), R)
+    g7 = rng.standard_normal((B * R, C, 7, 7), dtype=np.float32)
+    g14 = rng.standard_normal((B * R, C, 14, 14), dtype=np.float32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    nhwc = lambda a: pin(a.transpose(0, 2, 3, 1))  # noqa: E731
+    h_out7, h_out14 = hs.pinned_like(hs.out7), hs.pinned_like(hs.out14)
+    h_ga = [hs.pinned_like(f) for f in hs.fm]
+    h_gb = None if fused else [hs.pinned_like(f) for f in hs.fm]
+    gt = np.zeros((B * G, 1, size, size), np.float32)
+    for k in range(B * G):
+        y, x = rng.integers(0, size - 40, 2)
+        gt[k, 0, y:y + 40, x:x + 60] = 1.0
+    mboxes = np.concatenate([synth.random_rois(P, 70 + i, image=float(size), min_size=6, max_size=size * 0.9) for i in range(B)])
+    mind = (np.repeat(np.arange(B), P) * G + rng.integers(0, G, B * P)).astype(np.int32)
+    mask = {"d_images": dev(gt), "h_boxes": pin(mboxes), "h_index": pin(mind), "d_boxes": torch.empty((B * P, 4), device="cuda"),
+            "d_index": torch.empty(B * P, dtype=torch.int32, device="cuda"), "d_targets": torch.empty((B * P, 1, 28, 28), device="cuda"),
+            "h_targets": torch.empty((B * P, 1, 28, 28)).pin_memory()}
+    for _ in range(2):      # twice: buffers and workspaces are reused
+        hs.run([nhwc(f) for f in fms], pin(boxes), nhwc(g7), nhwc(g14), h_out7, h_out14, h_ga, h_gb, mask)
+    area = float(size * size)
+    w7, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, 7, area)
+    w14, _ = oracle.pyramid_roi_align_fwd(fms, boxes, ind, 14, area)
+    np.testing.assert_array_equal(h_out7.numpy().transpose(0, 3, 1, 2), w7)
+    np.testing.assert_array_equal(h_out14.numpy().transpose(0, 3, 1, 2), w14)
+    shapes = [f.shape for f in fms]
+    b7 = oracle.pyramid_roi_align_bwd(g7, shapes, boxes, ind, area)
+    b14 = oracle.pyramid_roi_align_bwd(g14, shapes, boxes, ind, area)
+    for l in range(4):
+        if fused:
+            assert rel_err(h_ga[l].numpy().transpose(0, 3, 1, 2), b7[l] + b14[l]) <= BWD_TOL
+        else:
+            assert rel_err(h_ga[l].numpy().transpose(0, 3, 1, 2), b14[l]) <= BWD_TOL
+            assert rel_err(h_gb[l].numpy().transpose(0, 3, 1, 2), b7[l]) <= BWD_TOL
+    np.testing.assert_array_equal(mask["h_targets"].numpy(), oracle.crop_forward(gt, mboxes, mind, 28, 28, 0.0))
+    assert hs.h2d_bytes(mask) > 0 and hs.d2h_bytes(mask) > 0
+    ops.check_device_errors()
