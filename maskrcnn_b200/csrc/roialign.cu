@@ -412,6 +412,93 @@ __device__ __forceinline__ void col_pass(const RoiParams& p, const RoiCtx& ctx, 
     }
 }
 
+// Channels-last pyramid -> NCHW crops with the column-stationary threads of the kernels above: the blended float4 of a bin goes
+// into a shared-memory tile laid out like the output block ([channel][bin]; at 14x14 every group of four rows skewed by 16 bytes,
+// see roialign_fwd_nhwc_kernel) and the tile leaves with bulk copies.  Replaces the slot-strided loop of the general kernel for
+// the two head sizes: fewer shared-memory tap loads per bin, the same epilogue.
+// LANES = 16: 64 channels per CTA (256 threads, 50 KB tile at 14x14: 4 CTAs per SM); LANES = 8: 32 channels per CTA (128 threads, 25 KB:
+// 8 per SM) - for small launches (an inference call: 1000 RoIs), where more and shorter CTAs overlap their phases better.
+template <int POOL, int LANES>
+__global__ void __launch_bounds__(16 * LANES) roialign_fwd_nhwc_colt_kernel(const RoiParams p) {
+    constexpr int P2 = POOL * POOL;
+    constexpr int kPhases = kSlots / POOL;
+    constexpr int kCh = 4 * LANES;
+    extern __shared__ __align__(16) float tile[];
+    __shared__ TapS s_ty[kMaxPool];
+    __shared__ TapS s_tx[kMaxPool];
+    const int chunks = (p.C + kCh - 1) / kCh;
+    const int n = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x - n * chunks) * kCh;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+    float4 box;
+    const RoiCtx ctx = select_level(p, n, box);
+    stage_taps(p, ctx, box, POOL, POOL, s_ty, s_tx);
+    __syncthreads();
+    const int lane = tid % LANES, slot = tid / LANES;
+    const int c = c0 + 4 * lane;
+    if (c < C && slot < POOL * kPhases) {
+        const int phase = slot / POOL;
+        const int x = slot - phase * POOL;
+        const TapS tx = s_tx[x];
+        const float* src_lo = ctx.base + c + (unsigned)tx.lo;
+        const float* src_hi = ctx.base + c + (unsigned)tx.hi;
+        float* t = tile + (4 * lane) * P2 + (POOL == 14 ? 4 * lane : 0) + x;
+        const float4 ext = make_float4(p.extrap, p.extrap, p.extrap, p.extrap);
+#pragma unroll 1
+        for (int y0 = phase; y0 < POOL; y0 += 2 * kPhases) {
+            const int y1 = y0 + kPhases;
+            const bool has1 = y1 < POOL;
+            const TapS ta = s_ty[y0];
+            const TapS tb = s_ty[has1 ? y1 : y0];
+            const bool in_a = ta.valid && tx.valid;
+            const bool in_b = has1 && tb.valid && tx.valid;
+            float4 tl0, tr0, bl0, br0, tl1, tr1, bl1, br1;
+            if (in_a) {
+                tl0 = ldg_f4(src_lo + (unsigned)ta.lo);
+                tr0 = ldg_f4(src_hi + (unsigned)ta.lo);
+                bl0 = ldg_f4(src_lo + (unsigned)ta.hi);
+                br0 = ldg_f4(src_hi + (unsigned)ta.hi);
+            }
+            if (in_b) {
+                tl1 = ldg_f4(src_lo + (unsigned)tb.lo);
+                tr1 = ldg_f4(src_hi + (unsigned)tb.lo);
+                bl1 = ldg_f4(src_lo + (unsigned)tb.hi);
+                br1 = ldg_f4(src_hi + (unsigned)tb.hi);
+            }
+            const float4 va = in_a ? bilerp4(tl0, tr0, bl0, br0, tx.lerp, ta.lerp, p.negzero) : ext;
+            float* o = t + y0 * POOL;
+            o[0] = va.x; o[P2] = va.y; o[2 * P2] = va.z; o[3 * P2] = va.w;
+            if (has1) {
+                const float4 vb = in_b ? bilerp4(tl1, tr1, bl1, br1, tx.lerp, tb.lerp, p.negzero) : ext;
+                float* o1 = t + y1 * POOL;
+                o1[0] = vb.x; o1[P2] = vb.y; o1[2 * P2] = vb.z; o1[3 * P2] = vb.w;
+            }
+        }
+    }
+    const int cc = min(kCh, C - c0);
+    float* dst = p.crops + ((size_t)n * C + c0) * P2;
+    fence_proxy_async();
+    __syncthreads();
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (POOL == 7) {
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(tile)),
+                         "r"((uint32_t)(cc * P2 * 4)), "l"(policy)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (tid < cc / 4) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + (size_t)tid * 4 * P2),
+                     "r"(smem_u32(tile + tid * (4 * P2 + 4))), "r"((uint32_t)(4 * P2 * 4)), "l"(policy)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 4) roialign_fwd_nhwc_pair_kernel(const RoiParams p) {
     __shared__ TapS s_ty14[14], s_tx14[14], s_ty7[8], s_tx7[8];
     const int chunks = (p.C + kChunk - 1) / kChunk;
@@ -1863,6 +1950,22 @@ static int launch_roi(const RoiParams& p_in, int image_layout, int crops_layout,
                     else roialign_fwd_nhwc_col_kernel<14, kLanes, kSlots><<<(unsigned)flat, kThreads, 0, stream>>>(p);
                 }
                 else MRCNN_LAUNCH_NHWC((roialign_fwd_nhwc_kernel<0, true>));
+            } else if ((p.ph == 7 && p.pw == 7) || (p.ph == 14 && p.pw == 14)) {
+                const long long flat = (long long)grid.x * grid.y;
+                if (flat >= (1ll << 31)) return fail(MRCNN_E_INVALID_ARG, "too many RoIs");
+                // stage_taps uses threads [0, pool) and [64, 64 + pool): 128-thread CTAs are enough
+                const bool narrow = p.N <= 4096;     // small launches: 32-channel CTAs (twice as many, half the tile)
+                const size_t smem_t = narrow ? smem / 2 + 64 : smem;
+                const unsigned grid_t = narrow ? (unsigned)((long long)p.N * ((p.C + 31) / 32)) : (unsigned)flat;
+                if (p.ph == 7) {
+                    if (narrow) roialign_fwd_nhwc_colt_kernel<7, 8><<<grid_t, 128, smem_t, stream>>>(p);
+                    else roialign_fwd_nhwc_colt_kernel<7, 16><<<grid_t, 256, smem_t, stream>>>(p);
+                } else if (narrow) {
+                    roialign_fwd_nhwc_colt_kernel<14, 8><<<grid_t, 128, smem_t, stream>>>(p);
+                } else {
+                    MRCNN_CUDA(cudaFuncSetAttribute(roialign_fwd_nhwc_colt_kernel<14, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                    roialign_fwd_nhwc_colt_kernel<14, 16><<<grid_t, 256, smem_t, stream>>>(p);
+                }
             } else MRCNN_DISPATCH_POOL(roialign_fwd_nhwc_kernel, false);
         } else {
             if (crops_layout == MRCNN_NHWC) MRCNN_DISPATCH_POOL(roialign_bwd_nhwc_kernel, true);
