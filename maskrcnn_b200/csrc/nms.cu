@@ -19,6 +19,7 @@
 namespace mrcnn {
 
 constexpr int kSortTile = 8192;  // elements sorted per CTA in shared memory (64 KB)
+constexpr int kFixpointMinW = 8;  // chunks of 64 boxes from which the grid-wide fixed-point route is taken
 
 struct NmsWorkspace {
     uint64_t* sortbuf;  // [P]
@@ -28,6 +29,10 @@ struct NmsWorkspace {
     uint64_t* mask;     // [N64][W]
     uint8_t* flags;     // [N64] survivor flag per ORIGINAL index
     uint64_t* diag_t;   // [N64] diagonal tiles transposed: which earlier boxes of its chunk suppress box i
+    // fixed-point path (nms_fixpoint_kernel): `mask` then holds the LOWER triangle, tile-major
+    uint64_t* keepw;    // [W] survivor words in score order (the iterate)
+    uint32_t* obits;    // [N64 / 32] survivor bits by ORIGINAL index
+    unsigned long long* gbar;  // grid barrier word: arrivals | changes of odd passes << 20 | changes of even passes << 42
     size_t bytes;
 };
 
@@ -55,6 +60,9 @@ static NmsWorkspace carve_nms(void* base, int N) {
     w.mask = (uint64_t*)take(N64 * W * 8);
     w.flags = (uint8_t*)take(N64);
     w.diag_t = (uint64_t*)take(N64 * 8);
+    w.keepw = (uint64_t*)take(W * 8);
+    w.obits = (uint32_t*)take(N64 / 8);
+    w.gbar = (unsigned long long*)take(8);
     w.bytes = off;
     return w;
 }
@@ -259,6 +267,211 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const uint64_t* __restr
     if (tid == nt - 1) *count_out = pos;  // the last thread's end position is the total
 }
 
+// ---- 2b + 3b. the parallel route: lower-triangle mask + a grid-wide fixed-point iteration ------------------------------
+//
+// Greedy NMS is the unique solution of a triangular system: keep[i] = no KEPT earlier box suppresses box i.  The serial sweep
+// above walks it chunk by chunk on one SM (~1.7 us per chunk of 64 boxes, all of it barrier latency: 160 us at 6000 boxes).
+// Here every chunk is owned by a CTA and all chunks are re-evaluated AT ONCE from the previous pass's survivor words
+// (Jacobi across chunks, exact inside a chunk), with a grid barrier per pass, until a pass changes nothing.  Chunk c is final
+// after pass c + 1 at the latest (its predecessors are), so W + 1 passes bound the worst case - a chain in which every box only
+// overlaps its successor - and real inputs settle in 6-10 passes (tools/sim_nms_fixpoint.py).  The fixed point IS the greedy
+// answer, so the result is bit-identical to the sweep.
+//
+// The pull form wants "who suppresses me": word (rb, cb <= rb) of row box i holds the EARLIER boxes of column block cb with
+// IoU >= thr (iou_ge_m is symmetric in its two boxes: fmax / fmin / a + b commute).  Stored tile-major - tile q = rb (rb + 1) / 2 +
+// cb, 64 consecutive words - so that the rows of chunk c are one contiguous block [c + 1][64] (the diagonal tile last).
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
+                                                            int W, float thr, uint64_t* __restrict__ lower,
+                                                            uint64_t* __restrict__ keepw, uint32_t* __restrict__ obits,
+                                                            unsigned long long* __restrict__ gbar) {
+    const int q = blockIdx.x, t = threadIdx.x;
+    int rb = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while ((rb + 1) * (rb + 2) / 2 <= q) ++rb;
+    while (rb * (rb + 1) / 2 > q) --rb;
+    const int cb = q - rb * (rb + 1) / 2;
+    MRCNN_DBG(rb >= 0 && rb < W && cb >= 0 && cb <= rb);
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const int col0 = cb * 64;
+    if (col0 + t < N) {
+        cbox[t] = sbox[col0 + t];
+        carea[t] = sarea[col0 + t];
+    }
+    __syncthreads();
+    const int row = rb * 64 + t;
+    uint64_t w = 0ull;
+    if (row < N) {
+        const float4 b = sbox[row];
+        const float a = sarea[row];
+        const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
+        if (cb < rb) {   // every column box is earlier and exists: constant bit positions
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) lo |= (1u << c);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (iou_ge_m(cbox[32 + c], carea[32 + c], b, a, thr, margin)) hi |= (1u << c);
+            w = ((uint64_t)hi << 32) | lo;
+        } else {
+            for (int c = 0; c < t; ++c)
+                if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
+        }
+    }
+    lower[(size_t)q * 64 + t] = w;
+    // the state the fixed-point kernel starts from (a kernel boundary orders it): every box kept, no survivor bits, barrier at 0
+    if (cb == rb && t == 0) {
+        const int nrows = min(64, N - rb * 64);
+        keepw[rb] = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+    }
+    const int owords = W * 2;
+    for (int i = q * 64 + t; i < owords; i += gridDim.x * 64) obits[i] = 0u;
+    if (q == 0 && t == 0) *gbar = 0ull;
+}
+
+// All CTAs of the (cooperative) grid meet; `changed` is folded into the barrier word, in the field of this pass's parity (a
+// CTA that is already one pass ahead adds to the OTHER field, never to the one a straggler is about to read).  Returns the
+// barrier word as read after everybody arrived.  Thread 0 arrives for its CTA; the __syncthreads pair orders the CTA's
+// global writes before the arrival (fence + relaxed atomic = release) and its later reads after the acquire.
+__device__ __forceinline__ unsigned long long grid_meet(unsigned long long* gbar, unsigned long long* s_word, unsigned pass,
+                                                        bool changed) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(gbar, 1ull | (changed ? ((pass & 1u) ? (1ull << 20) : (1ull << 42)) : 0ull));
+        const unsigned long long target = (unsigned long long)gridDim.x * pass;
+        unsigned long long v;
+        do {
+            v = ld_acquire_u64(gbar);
+        } while ((v & 0xfffffull) < target);
+        *s_word = v;
+    }
+    __syncthreads();
+    return *s_word;
+}
+
+__global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __restrict__ lower, const int32_t* __restrict__ order, int N,
+                                                            int W, int rows_in_smem, uint64_t* __restrict__ keepw,
+                                                            uint32_t* __restrict__ obits, unsigned long long* __restrict__ gbar,
+                                                            int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
+    extern __shared__ __align__(16) uint64_t s_rows[];   // rows_in_smem: the [c][64] words of this CTA's only chunk
+    __shared__ unsigned s_sup[2];
+    __shared__ unsigned long long s_word;
+    __shared__ int s_warp_sums[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int S = nt >> 6, box = tid & 63, slice = tid >> 6;
+    const int G = gridDim.x;
+    if (rows_in_smem) {
+        const int c = blockIdx.x;
+        const uint64_t* src = lower + (size_t)c * (c + 1) / 2 * 64;
+        for (int i = tid; i < c * 64; i += nt) s_rows[i] = __ldg(src + i);
+    }
+    unsigned seen[2] = {0u, 0u};   // the change counts of odd / even passes at the last look
+    unsigned pass = 0;
+    for (;;) {
+        ++pass;
+        bool changed = false;
+        for (int c = blockIdx.x; c < W; c += G) {
+            if (tid < 2) s_sup[tid] = 0u;
+            __syncthreads();
+            const uint64_t* tiles = lower + (size_t)c * (c + 1) / 2 * 64;
+            const uint64_t* rows = rows_in_smem ? s_rows : tiles;
+            uint64_t acc = 0ull;
+            for (int w = slice; w < c; w += S) {
+                MRCNN_DBG(w >= 0 && w < W && w * 64 + box < (c + 1) * 64);
+                acc |= rows[w * 64 + box] & ld_relaxed_u64(keepw + w);
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, acc != 0ull);
+            if (lane == 0 && hit) atomicOr(&s_sup[warp & 1], hit);   // warp -> boxes (warp & 1) * 32 ..
+            __syncthreads();
+            if (warp == 0) {
+                const int nrows = min(64, N - c * 64);
+                const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+                const uint64_t cand = valid & ~((uint64_t)s_sup[0] | ((uint64_t)s_sup[1] << 32));
+                const uint64_t ca = __ldg(tiles + (size_t)c * 64 + lane);        // earlier boxes of the chunk that suppress box lane
+                const uint64_t cb = __ldg(tiles + (size_t)c * 64 + lane + 32);   // ... box lane + 32
+                uint64_t alive = cand;
+                for (;;) {   // warp-uniform (same rule as block_nms_sweep's chunk resolve)
+                    const unsigned sa = __ballot_sync(0xffffffffu, (ca & alive) != 0ull);
+                    const unsigned sb = __ballot_sync(0xffffffffu, (cb & alive) != 0ull);
+                    const uint64_t next = cand & ~((uint64_t)sa | ((uint64_t)sb << 32));
+                    if (next == alive) break;
+                    alive = next;
+                }
+                if (lane == 0 && alive != ld_relaxed_u64(keepw + c)) {
+                    st_relaxed_u64(keepw + c, alive);
+                    changed = true;   // thread 0 is the one that arrives at the barrier
+                }
+            }
+        }
+        const unsigned long long v = grid_meet(gbar, &s_word, pass, changed);
+        const unsigned field = (pass & 1u) ? (unsigned)((v >> 20) & 0x3fffffu) : (unsigned)((v >> 42) & 0x3fffffu);
+        if (field == seen[pass & 1u]) break;   // nobody changed a word in this pass: the fixed point
+        seen[pass & 1u] = field;
+    }
+    // survivors (score order) -> bits by ORIGINAL index
+    for (int c = blockIdx.x; c < W; c += G) {
+        const uint64_t alive = ld_relaxed_u64(keepw + c);
+        if (tid < 64 && ((alive >> tid) & 1ull)) {
+            const int o = order[c * 64 + tid];
+            MRCNN_DBG(o >= 0 && o < N);
+            atomicOr(obits + (o >> 5), 1u << (o & 31));
+        }
+    }
+    grid_meet(gbar, &s_word, pass + 1, false);
+    if (blockIdx.x != 0) return;
+    // ascending compaction by CTA 0: thread t owns the contiguous words [t * per, (t + 1) * per)
+    const int words = (N + 31) >> 5;
+    const int per = (words + nt - 1) / nt;
+    const int beg = min(words, tid * per), end = min(words, beg + per);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) cnt += __popc(__ldcg(obits + i));
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int u = (lane < (nt >> 5)) ? s_warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, u, o);
+            if (lane >= o) u += x;
+        }
+        s_warp_sums[lane] = u;
+    }
+    __syncthreads();
+    int pos = incl - cnt + (warp > 0 ? s_warp_sums[warp - 1] : 0);
+    for (int i = beg; i < end; ++i) {
+        unsigned b = __ldcg(obits + i);
+        while (b) {
+            const int j = __ffs((int)b) - 1;
+            b &= b - 1;
+            MRCNN_DBG(pos < N);
+            keep_out[pos++] = (int64_t)i * 32 + j;
+        }
+    }
+    if (tid == nt - 1) *count_out = pos;   // the last thread's end position is the total
+}
+
 __global__ void nms_empty_kernel(int32_t* count_out) { *count_out = 0; }
 
 static size_t sweep_smem_bytes(int W, bool staged) {
@@ -322,6 +535,33 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
         }
         nms_gather_kernel<<<(N + 255) / 256, 256, 0, stream>>>(dets, ws.sortbuf, N, ws.sbox, ws.sarea, ws.order);
         MRCNN_LAUNCH_CHECK();
+    }
+
+    // Route: the grid-wide fixed-point iteration from kFixpointMinW chunks on (MRCNN_NMS_SWEEP=serial|fixpoint forces one);
+    // below that the single-CTA sweep has fewer barriers to pay than the cooperative launch costs.
+    static const char* route_env = getenv("MRCNN_NMS_SWEEP");
+    const bool fixpoint = route_env && route_env[0] == 's' ? false : (route_env && route_env[0] == 'f' ? true : W >= kFixpointMinW);
+    if (fixpoint) {
+        const int tiles = W * (W + 1) / 2;
+        nms_mask_lower_kernel<<<tiles, 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.keepw, ws.obits, ws.gbar);
+        MRCNN_LAUNCH_CHECK();
+        const int G = min(W, sm_count());
+        int rows_in_smem = (W <= G) ? 1 : 0;
+        size_t smem = rows_in_smem ? (size_t)(W > 1 ? W - 1 : 1) * 512 : 0;
+        static const int fp_threads = getenv("MRCNN_NMS_THREADS") ? atoi(getenv("MRCNN_NMS_THREADS")) : 0;   // experiment knob
+        int threads = W > 32 ? 512 : 256;
+        if (fp_threads >= 64 && fp_threads <= 1024 && fp_threads % 64 == 0) threads = fp_threads;
+        MRCNN_CUDA(cudaFuncSetAttribute(nms_fixpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 512));
+        const uint64_t* lower = ws.mask;
+        const int32_t* order = ws.order;
+        uint64_t* keepw = ws.keepw;
+        uint32_t* obits = ws.obits;
+        unsigned long long* gbar = ws.gbar;
+        int n = N, w = W;
+        void* args[] = {(void*)&lower, (void*)&order, (void*)&n, (void*)&w, (void*)&rows_in_smem, (void*)&keepw,
+                        (void*)&obits, (void*)&gbar, (void*)&keep_out, (void*)&count_out};
+        MRCNN_CUDA(cudaLaunchCooperativeKernel((const void*)nms_fixpoint_kernel, dim3(G), dim3(threads), args, smem, stream));
+        return MRCNN_OK;
     }
 
     nms_mask_kernel<<<dim3(W + 1, (W + 1) / 2), 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.diag_t);

@@ -66,6 +66,48 @@ def test_nms_edge_cases(ops):
     np.testing.assert_array_equal(ops.nms(dev(d), 0.5).cpu().numpy(), np.arange(300))
 
 
+def _chain(n, step=20.0, side=100.0):
+    """Boxes in a row, each overlapping only its neighbours above the threshold (IoU 0.67 with the next, 0.43 with the one after),
+    scores descending along the row: the survivors alternate, and box i's fate hangs on box i - 1's - the longest dependency chain
+    there is (the worst case for the grid-wide fixed-point route: one pass per chunk)."""
+    x = np.arange(n, dtype=np.float32) * step
+    b = np.stack([np.zeros(n, np.float32), x, np.full(n, side, np.float32), x + side], 1)
+    return np.concatenate([b, np.linspace(0.99, 0.01, n, dtype=np.float32)[:, None]], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [449, 1000, 6000, 10000])
+def test_nms_longest_dependency_chain(ops, n):
+    dets = _chain(n)
+    want = oracle.nms(dets, 0.5)
+    assert len(want) > n // 3
+    np.testing.assert_array_equal(ops.nms(dev(dets), 0.5).cpu().numpy(), want)
+    perm = np.random.default_rng(n).permutation(n)          # the same chain with the boxes stored in a random order
+    np.testing.assert_array_equal(ops.nms(dev(dets[perm]), 0.5).cpu().numpy(), oracle.nms(dets[perm], 0.5))
+
+
+def test_nms_routes_agree():
+    """The single-CTA sweep and the grid-wide fixed-point iteration (MRCNN_NMS_SWEEP, read once per process) give the same list."""
+    import subprocess, sys, os
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); import maskrcnn_b200 as m; from maskrcnn_b200 import synth\n"
+            "out = []\n"
+            "for n, thr in ((449, 0.5), (2000, 0.3), (6000, 0.7), (12000, 0.6)):\n"
+            "    rng = np.random.default_rng(n); b = synth.random_rois(n, n, image=1024.0, min_size=16, max_size=500) * 1024.0\n"
+            "    b[n // 2:] = b[: n - n // 2] + rng.uniform(-8, 8, (n - n // 2, 4)).astype(np.float32)\n"
+            "    d = np.concatenate([b, synth.unique_scores(n, n)[:, None]], 1).astype(np.float32)\n"
+            "    out.append(m.nms(torch.from_numpy(d).cuda(), thr).cpu().numpy())\n"
+            "np.save(sys.argv[1], np.concatenate(out))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    got = {}
+    for route in ("serial", "fixpoint"):
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "k.npy")
+            env = dict(os.environ, MRCNN_NMS_SWEEP=route)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+            got[route] = np.load(path)
+    assert len(got["serial"]) > 5000
+    np.testing.assert_array_equal(got["serial"], got["fixpoint"])
+
+
 def test_nms_properties_full_size(ops):
     dets = _dets(6000, 77)
     keep = ops.nms(dev(dets), 0.7)
