@@ -295,6 +295,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
+// IoU >= thr decided without the division for all but the borderline pairs: for positive areas and thr > 0,
+//   inter / (S - inter) >= thr  <=>  inter (1 + thr) >= thr S,   S = area_a + area_b,
+// and thr S splits into a share per box, so a pair costs two adds and two compares after the intersection.  The band
+// [thr (1 - e) S, thr (1 + e) S] with e = 4e-6 is ~20 times wider than every rounding on either side put together (the few
+// fp32 operations here, and in the reference's own expression the sum, the difference and the division: ~2^-22 relative),
+// so outside it the reference's decision is certain; inside it - and for non-positive or non-finite areas and thr <= 0, whose
+// shares are NaN so that neither compare holds - the pair goes through iou_ge_m, the reference's expression.
+__device__ __forceinline__ float2 decision_band(float area, float thr) {
+    const bool ok = area > 0.0f && area < 1e37f && thr > 0.0f && thr < 1e6f;
+    const float nan = __int_as_float(0x7fc00000);
+    return ok ? make_float2(__fmul_rn(__fmul_rn(thr, 1.000004f), area), __fmul_rn(__fmul_rn(thr, 0.999996f), area)) : make_float2(nan, nan);
+}
+// bit 0: certainly >= thr; bit 1: not certainly below (certain pairs and borderline ones)
+__device__ __forceinline__ void iou_banded(const float4 a, const float2 band_a, const float4 b, const float2 band_b, float k1, bool& yes,
+                                           bool& not_no) {
+    const float yy1 = fmaxf(a.x, b.x);
+    const float xx1 = fmaxf(a.y, b.y);
+    const float yy2 = fminf(a.z, b.z);
+    const float xx2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+    const float lhs = __fmul_rn(__fmul_rn(w, h), k1);
+    yes = lhs > __fadd_rn(band_a.x, band_b.x);
+    not_no = !(lhs < __fadd_rn(band_a.y, band_b.y));
+}
+
 __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
                                                             int W, float thr, uint64_t* __restrict__ lower,
                                                             uint64_t* __restrict__ keepw, uint32_t* __restrict__ obits,
@@ -307,10 +333,13 @@ __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __rest
     MRCNN_DBG(rb >= 0 && rb < W && cb >= 0 && cb <= rb);
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
+    __shared__ float2 cband[64];   // thr (1 + e) area, thr (1 - e) area: the column's share of the decision band
     const int col0 = cb * 64;
     if (col0 + t < N) {
         cbox[t] = sbox[col0 + t];
-        carea[t] = sarea[col0 + t];
+        const float a = sarea[col0 + t];
+        carea[t] = a;
+        cband[t] = decision_band(a, thr);
     }
     __syncthreads();
     const int row = rb * 64 + t;
@@ -318,16 +347,32 @@ __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __rest
     if (row < N) {
         const float4 b = sbox[row];
         const float a = sarea[row];
+        const float2 band = decision_band(a, thr);
+        const float k1 = __fadd_rn(1.0f, thr);
         const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
         if (cb < rb) {   // every column box is earlier and exists: constant bit positions
-            uint32_t lo = 0, hi = 0;
+            uint32_t lo = 0, hi = 0, nlo = 0, nhi = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) lo |= (1u << c);
+            for (int c = 0; c < 32; ++c) {
+                bool yes, not_no;
+                iou_banded(cbox[c], cband[c], b, band, k1, yes, not_no);
+                if (yes) lo |= (1u << c);
+                if (not_no) nlo |= (1u << c);
+            }
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (iou_ge_m(cbox[32 + c], carea[32 + c], b, a, thr, margin)) hi |= (1u << c);
+            for (int c = 0; c < 32; ++c) {
+                bool yes, not_no;
+                iou_banded(cbox[32 + c], cband[32 + c], b, band, k1, yes, not_no);
+                if (yes) hi |= (1u << c);
+                if (not_no) nhi |= (1u << c);
+            }
             w = ((uint64_t)hi << 32) | lo;
+            uint64_t unsure = (((uint64_t)nhi << 32) | nlo) & ~w;   // inside the band (or NaN shares): the reference's expression decides
+            while (unsure) {
+                const int c = __ffsll((long long)unsure) - 1;
+                unsure &= unsure - 1;
+                if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
+            }
         } else {
             for (int c = 0; c < t; ++c)
                 if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
@@ -369,7 +414,9 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
                                                             int W, int rows_in_smem, uint64_t* __restrict__ keepw,
                                                             uint32_t* __restrict__ obits, unsigned long long* __restrict__ gbar,
                                                             int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
-    extern __shared__ __align__(16) uint64_t s_rows[];   // rows_in_smem: the [c][64] words of this CTA's only chunk
+    extern __shared__ __align__(16) uint64_t s_dyn[];
+    uint64_t* s_keep = s_dyn;        // [W] the survivor words as read at the start of a pass
+    uint64_t* s_rows = s_dyn + W;    // rows_in_smem: the [c][64] words of this CTA's only chunk
     __shared__ unsigned s_sup[2];
     __shared__ unsigned long long s_word;
     __shared__ int s_warp_sums[32];
@@ -388,13 +435,16 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
         bool changed = false;
         for (int c = blockIdx.x; c < W; c += G) {
             if (tid < 2) s_sup[tid] = 0u;
+            // the survivor words of the earlier chunks, all fetched at once (one L2 round trip; read one by one inside the
+            // loop below they cost a round trip each: 41 us for the kernel against ~20)
+            for (int w = tid; w < c; w += nt) s_keep[w] = ld_relaxed_u64(keepw + w);
             __syncthreads();
             const uint64_t* tiles = lower + (size_t)c * (c + 1) / 2 * 64;
             const uint64_t* rows = rows_in_smem ? s_rows : tiles;
             uint64_t acc = 0ull;
             for (int w = slice; w < c; w += S) {
                 MRCNN_DBG(w >= 0 && w < W && w * 64 + box < (c + 1) * 64);
-                acc |= rows[w * 64 + box] & ld_relaxed_u64(keepw + w);
+                acc |= rows[w * 64 + box] & s_keep[w];
             }
             const unsigned hit = __ballot_sync(0xffffffffu, acc != 0ull);
             if (lane == 0 && hit) atomicOr(&s_sup[warp & 1], hit);   // warp -> boxes (warp & 1) * 32 ..
@@ -547,11 +597,11 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
         MRCNN_LAUNCH_CHECK();
         const int G = min(W, sm_count());
         int rows_in_smem = (W <= G) ? 1 : 0;
-        size_t smem = rows_in_smem ? (size_t)(W > 1 ? W - 1 : 1) * 512 : 0;
+        size_t smem = (size_t)W * 8 + (rows_in_smem ? (size_t)(W > 1 ? W - 1 : 1) * 512 : 0);
         static const int fp_threads = getenv("MRCNN_NMS_THREADS") ? atoi(getenv("MRCNN_NMS_THREADS")) : 0;   // experiment knob
         int threads = W > 32 ? 512 : 256;
         if (fp_threads >= 64 && fp_threads <= 1024 && fp_threads % 64 == 0) threads = fp_threads;
-        MRCNN_CUDA(cudaFuncSetAttribute(nms_fixpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 512));
+        MRCNN_CUDA(cudaFuncSetAttribute(nms_fixpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 512 + 160 * 8));
         const uint64_t* lower = ws.mask;
         const int32_t* order = ws.order;
         uint64_t* keepw = ws.keepw;
