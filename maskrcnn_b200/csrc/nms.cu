@@ -10,6 +10,7 @@
 //   2. mask    : 64x64 tiles of IoU>=thr suppression words, upper triangle only
 //   3. sweep   : one CTA, mask row-blocks streamed through shared memory by bulk async copies,
 //                then an in-CTA prefix scan emits the surviving original indices in ascending order.
+#include <algorithm>
 #include <limits.h>
 #include <stdlib.h>
 
@@ -33,6 +34,7 @@ struct NmsWorkspace {
     uint64_t* keepw;    // [W] survivor words in score order (the iterate)
     uint32_t* obits;    // [N64 / 32] survivor bits by ORIGINAL index
     unsigned long long* gbar;  // grid barrier word: arrivals | changes of odd passes << 20 | changes of even passes << 42
+    uint64_t* pub;      // [2][W][2] published survivor half-words, each with its pass tag (nms_fixpoint_pub_kernel)
     size_t bytes;
 };
 
@@ -63,6 +65,7 @@ static NmsWorkspace carve_nms(void* base, int N) {
     w.keepw = (uint64_t*)take(W * 8);
     w.obits = (uint32_t*)take(N64 / 8);
     w.gbar = (unsigned long long*)take(8);
+    w.pub = (uint64_t*)take(W * 32);
     w.bytes = off;
     return w;
 }
@@ -101,16 +104,21 @@ __global__ void __launch_bounds__(1024) nms_tile_sort_kernel(const float* __rest
     tiles[i] = block_bitonic_desc_1024_reg(key, buf);
 }
 
-__global__ void __launch_bounds__(1024) nms_rank_gather_kernel(const float* __restrict__ dets, const uint64_t* __restrict__ tiles, int N,
-                                                               int T, float4* sbox, float* sarea, int32_t* order) {
+// kRankSplit CTAs per tile: the binary searches are random 8-byte shared-memory reads (conflict-bound: 70 of them per key), and a
+// quarter of a tile per SM spreads them over four times as many load pipes (one 1024-thread CTA per tile: 11 us; this: see DESIGN 3.3).
+constexpr int kRankSplit = 4;
+__global__ void __launch_bounds__(1024 / kRankSplit) nms_rank_gather_kernel(const float* __restrict__ dets, const uint64_t* __restrict__ tiles,
+                                                                            int N, int T, float4* sbox, float* sarea, int32_t* order) {
     extern __shared__ __align__(16) uint64_t skeys[];   // all T tiles
-    for (int i = threadIdx.x; i < T * 1024; i += 1024) skeys[i] = tiles[i];
+    constexpr int kThreads = 1024 / kRankSplit;
+    for (int i = threadIdx.x; i < T * 1024; i += kThreads) skeys[i] = tiles[i];
     __syncthreads();
-    const uint64_t key = skeys[blockIdx.x * 1024 + threadIdx.x];
+    const int mine = blockIdx.x / kRankSplit, in_tile = (blockIdx.x % kRankSplit) * kThreads + threadIdx.x;
+    const uint64_t key = skeys[mine * 1024 + in_tile];
     if (key == 0ull) return;   // padding
-    int rank = threadIdx.x;
+    int rank = in_tile;
     for (int t = 0; t < T; ++t) {
-        if (t == (int)blockIdx.x) continue;
+        if (t == mine) continue;
         const uint64_t* tile = skeys + t * 1024;   // descending
         int lo = 0, hi = 1024;                     // first position whose key is below `key`
         while (lo < hi) {
@@ -324,7 +332,7 @@ __device__ __forceinline__ void iou_banded(const float4 a, const float2 band_a, 
 __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
                                                             int W, float thr, uint64_t* __restrict__ lower,
                                                             uint64_t* __restrict__ keepw, uint32_t* __restrict__ obits,
-                                                            unsigned long long* __restrict__ gbar) {
+                                                            unsigned long long* __restrict__ gbar, uint64_t* __restrict__ pub) {
     const int q = blockIdx.x, t = threadIdx.x;
     int rb = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
     while ((rb + 1) * (rb + 2) / 2 <= q) ++rb;
@@ -382,7 +390,13 @@ __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __rest
     // the state the fixed-point kernel starts from (a kernel boundary orders it): every box kept, no survivor bits, barrier at 0
     if (cb == rb && t == 0) {
         const int nrows = min(64, N - rb * 64);
-        keepw[rb] = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+        const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+        keepw[rb] = valid;
+        // pass 0 of the published form: tag = pass * 2 + changed
+        pub[2 * rb] = (1ull << 32) | (valid & 0xffffffffull);
+        pub[2 * rb + 1] = (1ull << 32) | (valid >> 32);
+        pub[2 * W + 2 * rb] = 0ull;
+        pub[2 * W + 2 * rb + 1] = 0ull;
     }
     const int owords = W * 2;
     for (int i = q * 64 + t; i < owords; i += gridDim.x * 64) obits[i] = 0u;
@@ -430,6 +444,17 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
     }
     unsigned seen[2] = {0u, 0u};   // the change counts of odd / even passes at the last look
     unsigned pass = 0;
+    // one chunk per CTA: its diagonal words and its own survivor word stay in registers (every global read in the pass loop is
+    // an L2 round trip on the critical path: ~1000 cycles each, three of them per pass before this)
+    uint64_t own_ca = 0ull, own_cb = 0ull, own_word = 0ull;
+    if (rows_in_smem && warp == 0) {
+        const int c = blockIdx.x;
+        const uint64_t* tiles = lower + (size_t)c * (c + 1) / 2 * 64;
+        own_ca = __ldg(tiles + (size_t)c * 64 + lane);
+        own_cb = __ldg(tiles + (size_t)c * 64 + lane + 32);
+        const int nrows = min(64, N - c * 64);
+        own_word = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);   // what nms_mask_lower_kernel wrote
+    }
     for (;;) {
         ++pass;
         bool changed = false;
@@ -453,8 +478,8 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
                 const int nrows = min(64, N - c * 64);
                 const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
                 const uint64_t cand = valid & ~((uint64_t)s_sup[0] | ((uint64_t)s_sup[1] << 32));
-                const uint64_t ca = __ldg(tiles + (size_t)c * 64 + lane);        // earlier boxes of the chunk that suppress box lane
-                const uint64_t cb = __ldg(tiles + (size_t)c * 64 + lane + 32);   // ... box lane + 32
+                const uint64_t ca = rows_in_smem ? own_ca : __ldg(tiles + (size_t)c * 64 + lane);        // earlier boxes of the chunk that suppress box lane
+                const uint64_t cb = rows_in_smem ? own_cb : __ldg(tiles + (size_t)c * 64 + lane + 32);   // ... box lane + 32
                 uint64_t alive = cand;
                 for (;;) {   // warp-uniform (same rule as block_nms_sweep's chunk resolve)
                     const unsigned sa = __ballot_sync(0xffffffffu, (ca & alive) != 0ull);
@@ -463,10 +488,12 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
                     if (next == alive) break;
                     alive = next;
                 }
-                if (lane == 0 && alive != ld_relaxed_u64(keepw + c)) {
-                    st_relaxed_u64(keepw + c, alive);
+                const uint64_t before = rows_in_smem ? own_word : ld_relaxed_u64(keepw + c);   // this CTA is the word's only writer
+                if (lane == 0 && alive != before) {
+                    atomicExch(reinterpret_cast<unsigned long long*>(keepw + c), (unsigned long long)alive);   // see nms_fixpoint_pub_kernel
                     changed = true;   // thread 0 is the one that arrives at the barrier
                 }
+                own_word = alive;
             }
         }
         const unsigned long long v = grid_meet(gbar, &s_word, pass, changed);
@@ -522,6 +549,138 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
     if (tid == nt - 1) *count_out = pos;   // the last thread's end position is the total
 }
 
+// The same iteration for W <= SM count (one chunk per CTA, up to ~9400 boxes) WITHOUT a central barrier: a CTA publishes its
+// survivor word as two 64-bit values (32 survivor bits | pass tag | changed bit) into the buffer of the pass's parity, and
+// every CTA polls all 2 W values of the previous pass - the data IS the flag, so a pass costs one store-to-load trip through L2
+// instead of fence + arrival + poll + reload (~3.6 k cycles -> ~2 k).  Everybody reads the same published values, so everybody
+// sees the same "nothing changed in the last pass" and stops together; a buffer is only overwritten two passes later, when every
+// CTA has read it (it published the pass in between).  CTA 0 then holds the final words in shared memory and emits the list.
+__global__ void __launch_bounds__(1024) nms_fixpoint_pub_kernel(const uint64_t* __restrict__ lower, const int32_t* __restrict__ order,
+                                                                int N, int W, uint64_t* __restrict__ pub,
+                                                                int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
+    extern __shared__ __align__(16) uint64_t s_dyn[];
+    uint64_t* s_keep = s_dyn;        // [W]
+    uint64_t* s_rows = s_dyn + W;    // [c][64]; CTA 0 reuses it for the survivor bits by original index
+    __shared__ unsigned s_sup[2];
+    __shared__ int s_any[2];   // by pass parity: did any chunk change in the pass just read
+    __shared__ int s_warp_sums[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int S = nt >> 6, box = tid & 63, slice = tid >> 6;
+    const int c = blockIdx.x;
+    const uint64_t* tiles = lower + (size_t)c * (c + 1) / 2 * 64;
+    for (int i = tid; i < c * 64; i += nt) s_rows[i] = __ldg(tiles + i);
+    uint64_t own_ca = 0ull, own_cb = 0ull, own_word = 0ull;
+    if (warp == 0) {
+        own_ca = __ldg(tiles + (size_t)c * 64 + lane);
+        own_cb = __ldg(tiles + (size_t)c * 64 + lane + 32);
+        const int nrows = min(64, N - c * 64);
+        own_word = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+    }
+    if (tid < 2) s_any[tid] = 0;
+    // CTA 0 has no rows to stage (nothing precedes chunk 0): it uses the room for the score order -> original index map and, later,
+    // the survivor bits by original index, so that the emit at the end never leaves shared memory
+    int* s_order = reinterpret_cast<int*>(s_rows + W);
+    if (c == 0) {
+        for (int i = tid; i < N; i += nt) s_order[i] = __ldg(order + i);
+        for (int i = tid; i < 2 * W; i += nt) reinterpret_cast<unsigned*>(s_rows)[i] = 0u;
+    }
+    __syncthreads();
+    for (unsigned pass = 1;; ++pass) {
+        if (tid < 2) s_sup[tid] = 0u;
+        for (int i = tid; i < 2 * W; i += nt) {
+            const uint64_t* src = pub + (size_t)((pass - 1) & 1u) * 2 * W + i;
+            uint64_t v;
+            do {
+                v = ld_relaxed_u64(src);
+            } while ((unsigned)(v >> 33) != pass - 1);
+            reinterpret_cast<unsigned*>(s_keep)[i] = (unsigned)v;   // little endian: halves 2 w, 2 w + 1 make word w
+            if ((v >> 32) & 1ull) s_any[pass & 1u] = 1;
+        }
+        __syncthreads();
+        if (pass > 1 && s_any[pass & 1u] == 0) break;   // the previous pass changed nothing: s_keep is the answer
+        if (tid == 0) s_any[(pass + 1u) & 1u] = 0;   // last read one pass ago, before that pass's second barrier; next set after this pass's
+        uint64_t acc = 0ull;
+        for (int w = slice; w < c; w += S) {
+            MRCNN_DBG(w >= 0 && w < W && w * 64 + box < c * 64);
+            acc |= s_rows[w * 64 + box] & s_keep[w];
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, acc != 0ull);
+        if (lane == 0 && hit) atomicOr(&s_sup[warp & 1], hit);
+        __syncthreads();
+        if (warp == 0) {
+            const int nrows = min(64, N - c * 64);
+            const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+            const uint64_t cand = valid & ~((uint64_t)s_sup[0] | ((uint64_t)s_sup[1] << 32));
+            uint64_t alive = cand;
+            for (;;) {
+                const unsigned sa = __ballot_sync(0xffffffffu, (own_ca & alive) != 0ull);
+                const unsigned sb = __ballot_sync(0xffffffffu, (own_cb & alive) != 0ull);
+                const uint64_t next = cand & ~((uint64_t)sa | ((uint64_t)sb << 32));
+                if (next == alive) break;
+                alive = next;
+            }
+            if (lane < 2) {
+                const uint64_t tag = (uint64_t)(pass * 2u + (alive != own_word ? 1u : 0u)) << 32;
+                // an atomic exchange, not a store: measured on B200, a plain (even .relaxed.gpu) store took ~3 us to reach the
+                // pollers of the other SMs, the atomic is performed at L2 at once (pass time 4.4 -> 1.7 us)
+                atomicExch(reinterpret_cast<unsigned long long*>(pub + (size_t)(pass & 1u) * 2 * W + 2 * c + lane),
+                           (unsigned long long)(tag | ((alive >> (32 * lane)) & 0xffffffffull)));
+            }
+            own_word = alive;
+        }
+    }
+    if (c != 0) return;
+    // CTA 0: survivors (score order) -> bits by original index in shared memory -> ascending list, one thread per index
+    unsigned* s_obits = reinterpret_cast<unsigned*>(s_rows);   // zeroed at kernel start
+    const int words = (N + 31) >> 5;
+    for (int i = tid; i < N; i += nt)
+        if ((s_keep[i >> 6] >> (i & 63)) & 1ull) {
+            const int o = s_order[i];
+            MRCNN_DBG(o >= 0 && o < N);
+            atomicOr(s_obits + (o >> 5), 1u << (o & 31));
+        }
+    __syncthreads();
+    // exclusive prefix of the per-word counts: thread t owns the contiguous words [t * per, (t + 1) * per)
+    int* s_base = reinterpret_cast<int*>(s_keep);   // [words] (the survivor words are not needed any more; W * 8 bytes = 2 W ints)
+    const int per = (words + nt - 1) / nt;
+    const int beg = min(words, tid * per), end = min(words, beg + per);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) cnt += __popc(s_obits[i]);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int u = (lane < (nt >> 5)) ? s_warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, u, o);
+            if (lane >= o) u += x;
+        }
+        s_warp_sums[lane] = u;
+    }
+    __syncthreads();
+    int pos = incl - cnt + (warp > 0 ? s_warp_sums[warp - 1] : 0);
+    for (int i = beg; i < end; ++i) {
+        s_base[i] = pos;
+        pos += __popc(s_obits[i]);
+    }
+    if (tid == nt - 1) *count_out = pos;   // the last thread's end position is the total
+    __syncthreads();
+    for (int i = tid; i < words * 32; i += nt) {   // a warp per word: coalesced stores
+        const unsigned b = s_obits[i >> 5];
+        if ((b >> lane) & 1u) {
+            const int at = s_base[i >> 5] + __popc(b & ((1u << lane) - 1u));
+            MRCNN_DBG(at < N && i < N);
+            keep_out[at] = (int64_t)i;
+        }
+    }
+}
+
 __global__ void nms_empty_kernel(int32_t* count_out) { *count_out = 0; }
 
 static size_t sweep_smem_bytes(int W, bool staged) {
@@ -563,7 +722,7 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
         MRCNN_LAUNCH_CHECK();
         const size_t smem = (size_t)P * 8;
         MRCNN_CUDA(cudaFuncSetAttribute(nms_rank_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8));
-        nms_rank_gather_kernel<<<T, 1024, smem, stream>>>(dets, ws.sortbuf, N, T, ws.sbox, ws.sarea, ws.order);
+        nms_rank_gather_kernel<<<T * kRankSplit, 1024 / kRankSplit, smem, stream>>>(dets, ws.sortbuf, N, T, ws.sbox, ws.sarea, ws.order);
         MRCNN_LAUNCH_CHECK();
     } else if (P <= kSortTile) {
         const size_t smem = (size_t)P * 8;
@@ -593,14 +752,25 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
     const bool fixpoint = route_env && route_env[0] == 's' ? false : (route_env && route_env[0] == 'f' ? true : W >= kFixpointMinW);
     if (fixpoint) {
         const int tiles = W * (W + 1) / 2;
-        nms_mask_lower_kernel<<<tiles, 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.keepw, ws.obits, ws.gbar);
+        nms_mask_lower_kernel<<<tiles, 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.keepw, ws.obits, ws.gbar, ws.pub);
         MRCNN_LAUNCH_CHECK();
         const int G = min(W, sm_count());
         int rows_in_smem = (W <= G) ? 1 : 0;
-        size_t smem = (size_t)W * 8 + (rows_in_smem ? (size_t)(W > 1 ? W - 1 : 1) * 512 : 0);
+        size_t smem = (size_t)W * 8 + (rows_in_smem ? std::max((size_t)(W > 1 ? W - 1 : 1) * 512, (size_t)W * 8 + (size_t)W * 256) : 0);
         static const int fp_threads = getenv("MRCNN_NMS_THREADS") ? atoi(getenv("MRCNN_NMS_THREADS")) : 0;   // experiment knob
         int threads = W > 32 ? 512 : 256;
         if (fp_threads >= 64 && fp_threads <= 1024 && fp_threads % 64 == 0) threads = fp_threads;
+        static const bool no_pub = getenv("MRCNN_NMS_PUB") != nullptr && getenv("MRCNN_NMS_PUB")[0] == '0';   // experiment knob
+        if (rows_in_smem && !no_pub) {
+            MRCNN_CUDA(cudaFuncSetAttribute(nms_fixpoint_pub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 512 + 160 * 8));
+            const uint64_t* lower = ws.mask;
+            const int32_t* order = ws.order;
+            uint64_t* pub = ws.pub;
+            int n = N, w = W;
+            void* args[] = {(void*)&lower, (void*)&order, (void*)&n, (void*)&w, (void*)&pub, (void*)&keep_out, (void*)&count_out};
+            MRCNN_CUDA(cudaLaunchCooperativeKernel((const void*)nms_fixpoint_pub_kernel, dim3(G), dim3(threads), args, smem, stream));
+            return MRCNN_OK;
+        }
         MRCNN_CUDA(cudaFuncSetAttribute(nms_fixpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 512 + 160 * 8));
         const uint64_t* lower = ws.mask;
         const int32_t* order = ws.order;

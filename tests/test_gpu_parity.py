@@ -86,7 +86,8 @@ def test_nms_longest_dependency_chain(ops, n):
 
 
 def test_nms_routes_agree():
-    """The single-CTA sweep and the grid-wide fixed-point iteration (MRCNN_NMS_SWEEP, read once per process) give the same list."""
+    """The single-CTA sweep and both forms of the grid-wide fixed-point iteration (MRCNN_NMS_SWEEP, MRCNN_NMS_PUB; read once per
+    process) give the same list."""
     import subprocess, sys, os
     code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); import maskrcnn_b200 as m; from maskrcnn_b200 import synth\n"
             "out = []\n"
@@ -98,14 +99,15 @@ def test_nms_routes_agree():
             "np.save(sys.argv[1], np.concatenate(out))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import tempfile
     got = {}
-    for route in ("serial", "fixpoint"):
+    for route, extra in (("serial", {}), ("fixpoint", {}), ("fixpoint-barrier", {"MRCNN_NMS_PUB": "0"})):
         with tempfile.TemporaryDirectory() as tmp:
             path = os.path.join(tmp, "k.npy")
-            env = dict(os.environ, MRCNN_NMS_SWEEP=route)
+            env = dict(os.environ, MRCNN_NMS_SWEEP=route.split("-")[0], **extra)
             subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
             got[route] = np.load(path)
     assert len(got["serial"]) > 5000
-    np.testing.assert_array_equal(got["serial"], got["fixpoint"])
+    np.testing.assert_array_equal(got["serial"], got["fixpoint"])             # published words, no central barrier (<= 148 chunks)
+    np.testing.assert_array_equal(got["serial"], got["fixpoint-barrier"])     # the grid-barrier form (what larger inputs run)
 
 
 def test_nms_properties_full_size(ops):
