@@ -104,29 +104,41 @@ __global__ void __launch_bounds__(1024) nms_tile_sort_kernel(const float* __rest
     tiles[i] = block_bitonic_desc_1024_reg(key, buf);
 }
 
-// kRankSplit CTAs per tile: the binary searches are random 8-byte shared-memory reads (conflict-bound: 70 of them per key), and a
-// quarter of a tile per SM spreads them over four times as many load pipes (one 1024-thread CTA per tile: 11 us; this: see DESIGN 3.3).
+// kRankSplit CTAs per tile.  The tiles arrive in shared memory by one bulk copy (a per-thread copy loop was 8 dependent round trips
+// for 64 KB), and a key's searches in the other tiles advance in lockstep - T - 1 independent shared-memory reads per step instead
+// of (T - 1) x 10 dependent ones.
 constexpr int kRankSplit = 4;
+constexpr int kRankMaxT = kSortTile / 1024;
 __global__ void __launch_bounds__(1024 / kRankSplit) nms_rank_gather_kernel(const float* __restrict__ dets, const uint64_t* __restrict__ tiles,
                                                                             int N, int T, float4* sbox, float* sarea, int32_t* order) {
-    extern __shared__ __align__(16) uint64_t skeys[];   // all T tiles
+    extern __shared__ __align__(128) uint64_t skeys[];   // all T tiles
+    __shared__ uint64_t bar;
     constexpr int kThreads = 1024 / kRankSplit;
-    for (int i = threadIdx.x; i < T * 1024; i += kThreads) skeys[i] = tiles[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bar, (uint32_t)T * 8192u);
+        for (int t = 0; t < T; ++t) bulk_g2s(skeys + t * 1024, tiles + t * 1024, 8192u, &bar);
+    }
     __syncthreads();
+    mbar_wait(&bar, 0u);
     const int mine = blockIdx.x / kRankSplit, in_tile = (blockIdx.x % kRankSplit) * kThreads + threadIdx.x;
     const uint64_t key = skeys[mine * 1024 + in_tile];
     if (key == 0ull) return;   // padding
-    int rank = in_tile;
-    for (int t = 0; t < T; ++t) {
-        if (t == mine) continue;
-        const uint64_t* tile = skeys + t * 1024;   // descending
-        int lo = 0, hi = 1024;                     // first position whose key is below `key`
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (tile[mid] > key) lo = mid + 1; else hi = mid;
-        }
-        rank += lo;
+    // lo[t]: first position of tile t (descending) whose key is below `key` = how many keys of tile t beat it
+    int lo[kRankMaxT];
+#pragma unroll
+    for (int t = 0; t < kRankMaxT; ++t) lo[t] = 0;
+#pragma unroll
+    for (int half = 512; half >= 1; half >>= 1) {   // branch-free lower bound over 1024 = 2^10 entries, all tiles at once
+#pragma unroll
+        for (int t = 0; t < kRankMaxT; ++t)
+            if (t < T && skeys[t * 1024 + lo[t] + half - 1] > key) lo[t] += half;
     }
+    int rank = in_tile;
+#pragma unroll
+    for (int t = 0; t < kRankMaxT; ++t)
+        if (t < T && t != mine) rank += lo[t] + ((lo[t] == 1023 && skeys[t * 1024 + 1023] > key) ? 1 : 0);
     MRCNN_DBG(rank >= 0 && rank < N && (int)sort_key_index(key) < N);
     gather_sorted(dets, key, rank, sbox, sarea, order);
 }
@@ -303,51 +315,56 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-// IoU >= thr decided without the division for all but the borderline pairs: for positive areas and thr > 0,
-//   inter / (S - inter) >= thr  <=>  inter (1 + thr) >= thr S,   S = area_a + area_b,
-// and thr S splits into a share per box, so a pair costs two adds and two compares after the intersection.  The band
-// [thr (1 - e) S, thr (1 + e) S] with e = 4e-6 is ~20 times wider than every rounding on either side put together (the few
-// fp32 operations here, and in the reference's own expression the sum, the difference and the division: ~2^-22 relative),
-// so outside it the reference's decision is certain; inside it - and for non-positive or non-finite areas and thr <= 0, whose
-// shares are NaN so that neither compare holds - the pair goes through iou_ge_m, the reference's expression.
-__device__ __forceinline__ float2 decision_band(float area, float thr) {
+// IoU >= thr, "certainly not" decided without the division: for positive areas and thr > 0,
+//   inter / (S - inter) >= thr  <=>  inter >= thr / (1 + thr) S,   S = area_a + area_b,
+// and the right side splits into a share per box, so a pair costs one add and one compare after the intersection.  A pair below
+// (1 - e) of that bound, e = 4e-6, is below the threshold in the reference's own expression too: e is ~8 times every rounding
+// on either side put together (the few fp32 operations here; the sum, the difference and the division there: ~2^-22 relative).
+// Everything else - the real overlaps, the borderline pairs, and non-positive or non-finite areas or thr <= 0, whose shares
+// are NaN so that the compare fails - goes through iou_ge_m, the reference's expression, in a second loop that is nearly
+// always short (an overlap above the threshold is one pair in thousands).
+__device__ __forceinline__ float no_share(float area, float thr) {
     const bool ok = area > 0.0f && area < 1e37f && thr > 0.0f && thr < 1e6f;
-    const float nan = __int_as_float(0x7fc00000);
-    return ok ? make_float2(__fmul_rn(__fmul_rn(thr, 1.000004f), area), __fmul_rn(__fmul_rn(thr, 0.999996f), area)) : make_float2(nan, nan);
+    return ok ? __fmul_rn(__fdiv_rn(__fmul_rn(thr, 0.999996f), __fadd_rn(1.0f, thr)), area) : __int_as_float(0x7fc00000);
 }
-// bit 0: certainly >= thr; bit 1: not certainly below (certain pairs and borderline ones)
-__device__ __forceinline__ void iou_banded(const float4 a, const float2 band_a, const float4 b, const float2 band_b, float k1, bool& yes,
-                                           bool& not_no) {
+// false: certainly below the threshold.  One clamp is enough: with w clamped at 0 a negative h gives a product <= 0.
+__device__ __forceinline__ bool iou_maybe(const float4 a, float share_a, const float4 b, float share_b) {
     const float yy1 = fmaxf(a.x, b.x);
     const float xx1 = fmaxf(a.y, b.y);
     const float yy2 = fminf(a.z, b.z);
     const float xx2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
-    const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
-    const float lhs = __fmul_rn(__fmul_rn(w, h), k1);
-    yes = lhs > __fadd_rn(band_a.x, band_b.x);
-    not_no = !(lhs < __fadd_rn(band_a.y, band_b.y));
+    const float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.0f);
+    return !(__fmul_rn(w, h) < __fadd_rn(share_a, share_b));
 }
 
-__global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea, int N,
-                                                            int W, float thr, uint64_t* __restrict__ lower,
-                                                            uint64_t* __restrict__ keepw, uint32_t* __restrict__ obits,
-                                                            unsigned long long* __restrict__ gbar, uint64_t* __restrict__ pub) {
-    const int q = blockIdx.x, t = threadIdx.x;
+// kMaskTiles tiles per CTA (64 threads each): 4465 two-warp CTAs for 6000 boxes spent a third of the kernel ramping up
+// (sm__cycles_active 39.8 k against 22.4 k issue cycles per scheduler).
+constexpr int kMaskTiles = 4;
+__global__ void __launch_bounds__(64 * kMaskTiles) nms_mask_lower_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                                                                         int N, int W, float thr, uint64_t* __restrict__ lower,
+                                                                         uint64_t* __restrict__ keepw, uint32_t* __restrict__ obits,
+                                                                         unsigned long long* __restrict__ gbar, uint64_t* __restrict__ pub) {
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int tiles = W * (W + 1) / 2;
+    const int q = min(blockIdx.x * kMaskTiles + g, tiles - 1);   // a spare group repeats the last tile (same values, same addresses)
     int rb = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
     while ((rb + 1) * (rb + 2) / 2 <= q) ++rb;
     while (rb * (rb + 1) / 2 > q) --rb;
     const int cb = q - rb * (rb + 1) / 2;
     MRCNN_DBG(rb >= 0 && rb < W && cb >= 0 && cb <= rb);
-    __shared__ float4 cbox[64];
-    __shared__ float carea[64];
-    __shared__ float2 cband[64];   // thr (1 + e) area, thr (1 - e) area: the column's share of the decision band
+    __shared__ float4 cbox_[kMaskTiles][64];
+    __shared__ float carea_[kMaskTiles][64];
+    __shared__ float cshare_[kMaskTiles][64];   // the column's share of the "certainly not" bound
+    float4* cbox = cbox_[g];
+    float* carea = carea_[g];
+    float* cshare = cshare_[g];
     const int col0 = cb * 64;
     if (col0 + t < N) {
         cbox[t] = sbox[col0 + t];
         const float a = sarea[col0 + t];
         carea[t] = a;
-        cband[t] = decision_band(a, thr);
+        cshare[t] = no_share(a, thr);
     }
     __syncthreads();
     const int row = rb * 64 + t;
@@ -355,30 +372,20 @@ __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __rest
     if (row < N) {
         const float4 b = sbox[row];
         const float a = sarea[row];
-        const float2 band = decision_band(a, thr);
-        const float k1 = __fadd_rn(1.0f, thr);
+        const float share = no_share(a, thr);
         const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
         if (cb < rb) {   // every column box is earlier and exists: constant bit positions
-            uint32_t lo = 0, hi = 0, nlo = 0, nhi = 0;
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                bool yes, not_no;
-                iou_banded(cbox[c], cband[c], b, band, k1, yes, not_no);
-                if (yes) lo |= (1u << c);
-                if (not_no) nlo |= (1u << c);
-            }
+            for (int c = 0; c < 32; ++c)
+                if (iou_maybe(cbox[c], cshare[c], b, share)) lo |= (1u << c);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                bool yes, not_no;
-                iou_banded(cbox[32 + c], cband[32 + c], b, band, k1, yes, not_no);
-                if (yes) hi |= (1u << c);
-                if (not_no) nhi |= (1u << c);
-            }
-            w = ((uint64_t)hi << 32) | lo;
-            uint64_t unsure = (((uint64_t)nhi << 32) | nlo) & ~w;   // inside the band (or NaN shares): the reference's expression decides
-            while (unsure) {
-                const int c = __ffsll((long long)unsure) - 1;
-                unsure &= unsure - 1;
+            for (int c = 0; c < 32; ++c)
+                if (iou_maybe(cbox[32 + c], cshare[32 + c], b, share)) hi |= (1u << c);
+            uint64_t maybe = ((uint64_t)hi << 32) | lo;
+            while (maybe) {   // the reference's expression decides
+                const int c = __ffsll((long long)maybe) - 1;
+                maybe &= maybe - 1;
                 if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
             }
         } else {
@@ -399,8 +406,8 @@ __global__ void __launch_bounds__(64) nms_mask_lower_kernel(const float4* __rest
         pub[2 * W + 2 * rb + 1] = 0ull;
     }
     const int owords = W * 2;
-    for (int i = q * 64 + t; i < owords; i += gridDim.x * 64) obits[i] = 0u;
-    if (q == 0 && t == 0) *gbar = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < owords; i += gridDim.x * blockDim.x) obits[i] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *gbar = 0ull;
 }
 
 // All CTAs of the (cooperative) grid meet; `changed` is folded into the barrier word, in the field of this pass's parity (a
@@ -556,19 +563,25 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_kernel(const uint64_t* __re
 // sees the same "nothing changed in the last pass" and stops together; a buffer is only overwritten two passes later, when every
 // CTA has read it (it published the pass in between).  CTA 0 then holds the final words in shared memory and emits the list.
 __global__ void __launch_bounds__(1024) nms_fixpoint_pub_kernel(const uint64_t* __restrict__ lower, const int32_t* __restrict__ order,
-                                                                int N, int W, uint64_t* __restrict__ pub,
+                                                                int N, int W, int keep_off, uint64_t* __restrict__ pub,
                                                                 int64_t* __restrict__ keep_out, int32_t* __restrict__ count_out) {
-    extern __shared__ __align__(16) uint64_t s_dyn[];
-    uint64_t* s_keep = s_dyn;        // [W]
-    uint64_t* s_rows = s_dyn + W;    // [c][64]; CTA 0 reuses it for the survivor bits by original index
+    extern __shared__ __align__(128) uint64_t s_dyn[];
+    uint64_t* s_rows = s_dyn;               // [c][64]; CTA 0 (no rows) keeps the order map and the survivor bits by original index here
+    uint64_t* s_keep = s_dyn + keep_off;    // [W]
     __shared__ unsigned s_sup[2];
     __shared__ int s_any[2];   // by pass parity: did any chunk change in the pass just read
     __shared__ int s_warp_sums[32];
+    __shared__ uint64_t s_bar;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int S = nt >> 6, box = tid & 63, slice = tid >> 6;
     const int c = blockIdx.x;
     const uint64_t* tiles = lower + (size_t)c * (c + 1) / 2 * 64;
-    for (int i = tid; i < c * 64; i += nt) s_rows[i] = __ldg(tiles + i);
+    if (tid == 0 && c > 0) {   // the chunk's rows: one bulk copy, waited for just before their first use
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&s_bar, (uint32_t)c * 512u);
+        bulk_g2s(s_rows, tiles, (uint32_t)c * 512u, &s_bar);
+    }
     uint64_t own_ca = 0ull, own_cb = 0ull, own_word = 0ull;
     if (warp == 0) {
         own_ca = __ldg(tiles + (size_t)c * 64 + lane);
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_pub_kernel(const uint64_t* 
     if (tid < 2) s_any[tid] = 0;
     // CTA 0 has no rows to stage (nothing precedes chunk 0): it uses the room for the score order -> original index map and, later,
     // the survivor bits by original index, so that the emit at the end never leaves shared memory
-    int* s_order = reinterpret_cast<int*>(s_rows + W);
+    int* s_order = reinterpret_cast<int*>(s_rows + W);   // after the 2 W survivor-bit words
     if (c == 0) {
         for (int i = tid; i < N; i += nt) s_order[i] = __ldg(order + i);
         for (int i = tid; i < 2 * W; i += nt) reinterpret_cast<unsigned*>(s_rows)[i] = 0u;
@@ -599,7 +612,9 @@ __global__ void __launch_bounds__(1024) nms_fixpoint_pub_kernel(const uint64_t* 
         __syncthreads();
         if (pass > 1 && s_any[pass & 1u] == 0) break;   // the previous pass changed nothing: s_keep is the answer
         if (tid == 0) s_any[(pass + 1u) & 1u] = 0;   // last read one pass ago, before that pass's second barrier; next set after this pass's
+        if (pass == 1 && c > 0) mbar_wait(&s_bar, 0u);
         uint64_t acc = 0ull;
+#pragma unroll 4
         for (int w = slice; w < c; w += S) {
             MRCNN_DBG(w >= 0 && w < W && w * 64 + box < c * 64);
             acc |= s_rows[w * 64 + box] & s_keep[w];
@@ -752,7 +767,7 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
     const bool fixpoint = route_env && route_env[0] == 's' ? false : (route_env && route_env[0] == 'f' ? true : W >= kFixpointMinW);
     if (fixpoint) {
         const int tiles = W * (W + 1) / 2;
-        nms_mask_lower_kernel<<<tiles, 64, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.keepw, ws.obits, ws.gbar, ws.pub);
+        nms_mask_lower_kernel<<<(tiles + kMaskTiles - 1) / kMaskTiles, 64 * kMaskTiles, 0, stream>>>(ws.sbox, ws.sarea, N, W, threshold, ws.mask, ws.keepw, ws.obits, ws.gbar, ws.pub);
         MRCNN_LAUNCH_CHECK();
         const int G = min(W, sm_count());
         int rows_in_smem = (W <= G) ? 1 : 0;
@@ -767,7 +782,8 @@ int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int3
             const int32_t* order = ws.order;
             uint64_t* pub = ws.pub;
             int n = N, w = W;
-            void* args[] = {(void*)&lower, (void*)&order, (void*)&n, (void*)&w, (void*)&pub, (void*)&keep_out, (void*)&count_out};
+            int keep_off = (int)((smem - (size_t)W * 8) / 8);
+            void* args[] = {(void*)&lower, (void*)&order, (void*)&n, (void*)&w, (void*)&keep_off, (void*)&pub, (void*)&keep_out, (void*)&count_out};
             MRCNN_CUDA(cudaLaunchCooperativeKernel((const void*)nms_fixpoint_pub_kernel, dim3(G), dim3(threads), args, smem, stream));
             return MRCNN_OK;
         }
