@@ -795,6 +795,24 @@ def mask_target_bytes(wl):
     return wl.mt.numel() * 4 + unique * 4 + len(mb) * 20
 
 
+def mask_target_sector_bytes(wl):
+    """The same crop counted in the unit DRAM moves: the UNIQUE 32-byte sectors the taps touch (a mask row starts on a 4 KB
+    boundary, so a pixel x lies in sector x // 8 of its row) + the outputs.  The taps of a 28-bin crop of a box wider than ~220
+    pixels are more than 8 pixels apart, so every tap pair drags a whole sector in: ~3x the unique-pixel bytes."""
+    mb = wl.mboxes.cpu().numpy()
+    sm1 = np.float32(IMAGE - 1)
+    i = np.arange(28, dtype=np.float32)
+    sectors = 0
+    for k in range(len(mb)):
+        def taps(a1, a2):
+            pos = (a1 * sm1 + i * (((a2 - a1) * sm1) / np.float32(27))).astype(np.float32)
+            ok = (pos >= 0) & (pos <= sm1)
+            return np.unique(np.concatenate([np.floor(pos[ok]), np.ceil(pos[ok])]))
+        rows, cols = taps(mb[k, 0], mb[k, 2]), taps(mb[k, 1], mb[k, 3])
+        sectors += len(rows) * len(np.unique(cols // 8))
+    return wl.mt.numel() * 4 + sectors * 32 + len(mb) * 20
+
+
 def workload_config():
     return {"workload": "BASELINE configs[3]: training-mode PyramidROIAlign fwd+bwd, batch %d x %d RoIs x %d ch, P2-P5 of %dx%d, "
                         "7x7 + 14x14 + %d 28x28 mask-target crops/img" % (BATCH, ROIS_PER_IMAGE, CHANNELS, IMAGE, IMAGE, MASK_POS),
@@ -1407,6 +1425,13 @@ def main():
             kern[name] = {"ms": t * 1e3, "algorithmic_MB": by / 1e6, "GBps": by / t / 1e9, "frac": by / t / 1e9 / hbm,
                           "ncu_dram_MB": traffic.get(captures[name])}
         kern[plan_name]["note"] = "not on the main stream: runs beside the forward kernels; its bytes (boxes) are not credited"
+        mt_name = "crop_plane_fwd_kernel<28x28 mask targets>"
+        sec = mask_target_sector_bytes(wl)
+        kern[mt_name].update({"ncu_dram_MB": traffic.get("mask_targets"), "unique_sector_MB": sec / 1e6,
+                              "frac_in_sectors": sec / (kern[mt_name]["ms"] * 1e-3) / 1e9 / hbm,
+                              "note": "algorithmic_MB counts 4 bytes per unique mask pixel; DRAM moves 32-byte sectors and the taps of a "
+                                      "large box are further apart than that, so the kernel's floor is unique_sector_MB (ncu_dram_MB is "
+                                      "what it moved: profiles/r02_mask_targets_ncu_summary.txt)"})
         kern["roialign_fwd_nhwc_pair_kernel<7+14,nhwc>"]["note"] = (
             "both heads in one launch; algorithmic bytes = the two heads' bytes as SURVEY 8(d) defines them (each head's unique taps "
             "counted), while the launch reads the shared footprint once - its DRAM traffic is below that sum")

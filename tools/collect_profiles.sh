@@ -19,5 +19,7 @@ for spec in "fwd 7" "fwd 14" "bwd 7" "bwd 14"; do
 done
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:"roialign_bwd_nhwc|zero_levels" -c 2 \
     -o $O/${R}_bwd14_nhwc_scatter python tools/prof_one.py bwd 14 nhwc > $O/${R}_bwd14_scatter.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:"crop_plane_fwd" -s 2 -c 1 \
+    -o $O/${R}_mask_targets python tools/prof_mask_targets.py > $O/${R}_mask_targets.log 2>&1
 # the 8(f) / proposal / detection kernels: tools/collect_next.sh (a separate gpurun call: 64 MiB return limit)
 ls -la $O | tail -20
