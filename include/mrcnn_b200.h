@@ -110,6 +110,10 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward_pair(const float* const fm[4], con
  *                      gradient data, no zero-fill pass, no read-modify-write of the pyramid.  Needs C % 4 == 0,
  *                      N > 0, N * pool^2 * C < 2^31, image_offsets_host == NULL and a 256-byte aligned workspace of
  *                      mrcnn_pyramid_roi_align_backward_workspace_bytes_ex() bytes.  Either layout of grads and gfm.
+ *                      Summation order: a unit's bins are queued in the order the planning threads reach it (atomic
+ *                      cursors), so two PLANS of the same boxes may add a pixel's terms in different orders and differ
+ *                      in the last bits (tests bound it at 1e-5 relative); replaying one plan is bit-reproducible.
+ *                      The scatter's reductions are unordered by nature.
  *   MRCNN_BWD_SCATTER  clear, then scatter with column-aggregated 128-bit vector reductions
  *                      (red.global.add.v4.f32) for a channels-last gfm, scalar atomics for an NCHW gfm.
  *                      workspace may be NULL.
