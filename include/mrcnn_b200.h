@@ -194,10 +194,14 @@ MRCNN_API int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox
  *   MRCNN_PROPOSAL_NMS_LAZY  one 8-CTA cluster per image, boxes taken 64 at a time in score order and compared only with
  *                            the survivors found so far, stopping at the post_nms-th survivor: 64 * sum(survivors so
  *                            far) IoU tests instead of n^2 / 2; no N x N mask, no workspace traffic;
- *   MRCNN_PROPOSAL_NMS_AUTO  LAZY when post_nms <= 2048, MASK otherwise (default). */
+ *   MRCNN_PROPOSAL_NMS_HYBRID the first 1.25 post_nms boxes of every image resolved AT ONCE by a grid-wide fixed-point
+ *                            iteration (lower-triangle IoU tiles, one CTA per 64 boxes, all images in one cooperative
+ *                            launch), the lazy kernel only for images that still lack survivors after that prefix;
+ *   MRCNN_PROPOSAL_NMS_AUTO  HYBRID when post_nms <= 2048, MASK otherwise (default). */
 #define MRCNN_PROPOSAL_NMS_AUTO 0
 #define MRCNN_PROPOSAL_NMS_MASK 1
 #define MRCNN_PROPOSAL_NMS_LAZY 2
+#define MRCNN_PROPOSAL_NMS_HYBRID 3
 MRCNN_API int mrcnn_set_proposal_nms(int algo);
 
 /* The same with the foreground probabilities alone, fg_scores [B,A] (what mrcnn_rpn_pack writes as fg_out): the layer's

@@ -305,6 +305,85 @@ __device__ __forceinline__ int block_nms_sweep(const uint64_t* mask, int n, int 
     return total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// IoU >= thr, "certainly not" decided without the division: for positive areas and thr > 0,
+//   inter / (S - inter) >= thr  <=>  inter >= thr / (1 + thr) S,   S = area_a + area_b,
+// and the right side splits into a share per box, so a pair costs one add and one compare after the intersection.  A pair below
+// (1 - e) of that bound, e = 4e-6, is below the threshold in the reference's own expression too: e is ~8 times every rounding
+// on either side put together (the few fp32 operations here; the sum, the difference and the division there: ~2^-22 relative).
+// Everything else - the real overlaps, the borderline pairs, and non-positive or non-finite areas or thr <= 0, whose shares
+// are NaN so that the compare fails - goes through iou_ge_m, the reference's expression, in a second loop that is nearly
+// always short (an overlap above the threshold is one pair in thousands).
+__device__ __forceinline__ float no_share(float area, float thr) {
+    const bool ok = area > 0.0f && area < 1e37f && thr > 0.0f && thr < 1e6f;
+    return ok ? __fmul_rn(__fdiv_rn(__fmul_rn(thr, 0.999996f), __fadd_rn(1.0f, thr)), area) : __int_as_float(0x7fc00000);
+}
+// false: certainly below the threshold.  One clamp is enough: with w clamped at 0 a negative h gives a product <= 0.
+__device__ __forceinline__ bool iou_maybe(const float4 a, float share_a, const float4 b, float share_b) {
+    const float yy1 = fmaxf(a.x, b.x);
+    const float xx1 = fmaxf(a.y, b.y);
+    const float yy2 = fminf(a.z, b.z);
+    const float xx2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    const float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.0f);
+    return !(__fmul_rn(w, h) < __fadd_rn(share_a, share_b));
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Lower-triangle suppression tiles ("who suppresses me"), tile-major: tile q = rb (rb + 1) / 2 + cb (cb <= rb) holds, for each of
+// the 64 row boxes of block rb, the EARLIER boxes of column block cb with IoU >= thr.  Shared by nms.cu and proposal.cu.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lower_tile_coords(int q, int& rb, int& cb) {
+    rb = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while ((rb + 1) * (rb + 2) / 2 <= q) ++rb;
+    while (rb * (rb + 1) / 2 > q) --rb;
+    cb = q - rb * (rb + 1) / 2;
+}
+
+// The word of row box `row` = rb * 64 + t (box b, area a; row < n) of tile (rb, cb); the 64 column boxes of block cb are staged in
+// shared memory (cbox / carea / cshare = no_share of the column).  Off the diagonal every column is earlier and exists.
+__device__ __forceinline__ uint64_t lower_tile_word(const float4 b, float a, bool diagonal, int t, const float4* cbox, const float* carea,
+                                                    const float* cshare, float thr) {
+    const float share = no_share(a, thr);
+    const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
+    uint64_t w = 0ull;
+    if (!diagonal) {   // constant bit positions
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (iou_maybe(cbox[c], cshare[c], b, share)) lo |= (1u << c);
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (iou_maybe(cbox[32 + c], cshare[32 + c], b, share)) hi |= (1u << c);
+        uint64_t maybe = ((uint64_t)hi << 32) | lo;
+        while (maybe) {   // the reference's expression decides
+            const int c = __ffsll((long long)maybe) - 1;
+            maybe &= maybe - 1;
+            if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
+        }
+    } else {
+        for (int c = 0; c < t; ++c)
+            if (iou_ge_m(cbox[c], carea[c], b, a, thr, margin)) w |= (1ull << c);
+    }
+    return w;
+}
+
+// .gpu-scope accesses for values exchanged between CTAs of one grid (they bypass L1)
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Largest W for which the double-buffered staging (2 * 64 * W * 8 bytes) fits next to the rest.
 constexpr int kSweepStageMaxW = 160;  // 160 KB of staging
 

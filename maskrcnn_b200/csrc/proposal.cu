@@ -19,6 +19,9 @@
 //      emits normalised RoIs (zero padded) + counts.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <stdlib.h>
+
 #include "api_util.h"
 #include "nms_core.cuh"
 
@@ -29,6 +32,7 @@ namespace mrcnn {
 constexpr int kClusterSize = 8;
 constexpr int kSelThreads = 1024;
 constexpr int kMaxPreNms = 8192;
+constexpr int kHybridMaxPost = 2048;   // the lazy / hybrid NMS serve post_nms up to this
 
 struct ProposalParams {
     const float* rpn_class;  // [B,A,2] (bg,fg) when sstride == 2, fg scores [B,A] when sstride == 1
@@ -57,7 +61,11 @@ struct ProposalWorkspace {
     float* sarea;
     float* sscore;
     int32_t* sorder;
-    uint64_t* mask;  // [B][pre64][W]
+    uint64_t* mask;  // [B][pre64][W]  (the hybrid NMS keeps its lower-triangle prefix tiles here)
+    uint64_t* pub;   // [B][2][W][2] published survivor half-words of the prefix fixed point
+    float4* kbox;    // [B][kHybridMaxPost + 64] survivors of the prefix, in order (what the lazy tail starts from)
+    float* karea;    // [B][kHybridMaxPost + 64]
+    int32_t* tail;   // [B] survivors so far when the lazy tail has work to do, -1 when the image is finished
     size_t bytes;
 };
 
@@ -85,6 +93,10 @@ static ProposalWorkspace carve_proposal(void* base, int B, int A, int pre_nms) {
     w.sscore = (float*)take((size_t)B * pre64 * 4);
     w.sorder = (int32_t*)take((size_t)B * pre64 * 4);
     w.mask = (uint64_t*)take((size_t)B * pre64 * W * 8);
+    w.pub = (uint64_t*)take((size_t)B * W * 32);
+    w.kbox = (float4*)take((size_t)B * (kHybridMaxPost + 64) * 16);
+    w.karea = (float*)take((size_t)B * (kHybridMaxPost + 64) * 4);
+    w.tail = (int32_t*)take((size_t)B * 4);
     w.bytes = off;
     return w;
 }
@@ -576,7 +588,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 
 __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* __restrict__ sbox_all, const float* __restrict__ sarea_all,
                                                                  int n, int pre64, float thr, int post, float height, float width,
-                                                                 float* __restrict__ rois_out, int32_t* __restrict__ counts_out) {
+                                                                 float* __restrict__ rois_out, int32_t* __restrict__ counts_out,
+                                                                 const int32_t* __restrict__ tail_all, const float4* __restrict__ kbox_all,
+                                                                 const float* __restrict__ karea_all, int start_chunk) {
+    // tail_all != nullptr: the hybrid route - the first start_chunk chunks were resolved by the prefix fixed point, which left the
+    // survivors' boxes in kbox / karea and their count in tail[img] (-1: the image is finished, the whole cluster leaves at once)
+    int S = 0;
+    const int c0 = tail_all ? start_chunk : 0;
+    if (tail_all) {
+        S = tail_all[blockIdx.x / kLazyCluster];
+        if (S < 0) return;
+    }
     extern __shared__ __align__(16) unsigned char lz_smem[];
     float4* s_kbox = reinterpret_cast<float4*>(lz_smem);             // [post + 64] survivors, in order
     float* s_karea = reinterpret_cast<float*>(s_kbox + post + 64);   // [post + 64]
@@ -596,23 +618,31 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
     float4* rois = reinterpret_cast<float4*>(rois_out + (size_t)img * post * 4);
     const float margin = __fadd_rn(__fmul_rn(fabsf(thr), 1e-6f), 1e-37f);
     if (tid == 0) {
-        s_S = 0;
+        s_S = S;
         mbar_init(&s_bar[0], kLazyCluster);
         mbar_init(&s_bar[1], kLazyCluster);
         fence_barrier_init();
     }
-    int S = 0;
+    if (S > 0) {   // every CTA keeps its own copy of the survivor list
+        const float4* kb = kbox_all + (size_t)img * (kHybridMaxPost + 64);
+        const float* ka = karea_all + (size_t)img * (kHybridMaxPost + 64);
+        for (int i = tid; i < S; i += blockDim.x) {
+            s_kbox[i] = kb[i];
+            s_karea[i] = ka[i];
+        }
+    }
     const int nchunks = (n + 63) >> 6;
     cluster.sync();  // every CTA of the cluster is resident (and its barriers initialised) before a peer writes into it
     // the chunk's boxes are fetched one chunk ahead (registers of threads 0..63), so their latency hides behind the
     // previous chunk's resolve
     float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
     float na = 0.f;
-    if (tid < 64 && tid < n) {
-        nb = sbox[tid];
-        na = sarea[tid];
+    if (tid < 64 && c0 * 64 + tid < n) {
+        nb = sbox[c0 * 64 + tid];
+        na = sarea[c0 * 64 + tid];
     }
-    for (int c = 0; c < nchunks && S < post; ++c) {
+    for (int c = c0; c < nchunks && S < post; ++c) {
+        const int lc = c - c0;   // buffers and barrier phases alternate from the first chunk this kernel handles
         const int ncols = min(64, n - c * 64);
         if (tid < 64) {
             s_cbox[tid] = nb;
@@ -662,24 +692,24 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
             const uint32_t h_hi = __ballot_sync(0xffffffffu, s_hit[lane + 32] != 0);
             MRCNN_DBG(rank >= 0 && rank < kLazyCluster);
             if (lane < kLazyCluster) {  // lane p serves peer p: nine 8-byte stores, then one arrive (release) on its mbarrier
-                st_cluster_u64(mapa_u32(smem_u32(&s_peer[c & 1][rank]), (uint32_t)lane), ((uint64_t)h_hi << 32) | h_lo);
+                st_cluster_u64(mapa_u32(smem_u32(&s_peer[lc & 1][rank]), (uint32_t)lane), ((uint64_t)h_hi << 32) | h_lo);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    st_cluster_u64(mapa_u32(smem_u32(&s_d[c & 1][8 * k + rank]), (uint32_t)lane),
+                    st_cluster_u64(mapa_u32(smem_u32(&s_d[lc & 1][8 * k + rank]), (uint32_t)lane),
                                    ((uint64_t)s_dpart[k][1] << 32) | s_dpart[k][0]);
-                mbar_arrive_remote(mapa_u32(smem_u32(&s_bar[c & 1]), (uint32_t)lane));
+                mbar_arrive_remote(mapa_u32(smem_u32(&s_bar[lc & 1]), (uint32_t)lane));
             }
-            mbar_wait_cluster(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
+            mbar_wait_cluster(&s_bar[lc & 1], (uint32_t)((lc >> 1) & 1));
             // resolve: box i survives iff it is a candidate and no SURVIVING earlier box of the chunk suppresses it.  The
             // dependency is triangular, so the Jacobi iteration below has exactly one fixed point - the greedy answer - and
             // reaches it after (longest suppression chain + 1) rounds of two ballots each, instead of one dependent step
             // per survivor.
             uint64_t hits = 0ull;
 #pragma unroll
-            for (int k = 0; k < kLazyCluster; ++k) hits |= s_peer[c & 1][k];
+            for (int k = 0; k < kLazyCluster; ++k) hits |= s_peer[lc & 1][k];
             uint64_t cand = ~hits;
             if (ncols < 64) cand &= (1ull << ncols) - 1ull;
-            const uint64_t col_lo = s_d[c & 1][lane], col_hi = s_d[c & 1][lane + 32];  // bits are rows below the column by construction
+            const uint64_t col_lo = s_d[lc & 1][lane], col_hi = s_d[lc & 1][lane + 32];  // bits are rows below the column by construction
             const bool c_lo = (cand >> lane) & 1ull, c_hi = (cand >> (lane + 32)) & 1ull;
             uint64_t alive = cand;
             for (;;) {
@@ -720,6 +750,187 @@ __global__ void __launch_bounds__(1024) proposal_lazy_nms_kernel(const float4* _
     }
 }
 
+// ---- 2''+3''. hybrid NMS: a grid-wide fixed point over the first Wp chunks, the lazy kernel for what is left ------------------
+//
+// The lazy kernel walks the chunks one after the other (~3 us each: a cluster exchange and a resolve per chunk), 18 of them for
+// the bench inputs.  The prefix that will hold the first `post` survivors with some margin (Wp = 1.25 post / 64 chunks) can be
+// resolved all at once instead - the same fixed-point iteration as the standalone nms (nms.cu: lower-triangle tiles, one CTA per
+// chunk, survivor words published with their pass tag, 6-10 passes of ~1.7 us) - on (Wp x B) CTAs instead of 8 B.  CTA (0, img)
+// then emits the survivors; if fewer than `post` were found and boxes remain, it leaves their boxes and count for the lazy
+// kernel, which continues from chunk Wp (tail[img] = -1 otherwise, and that image's cluster leaves at once).  Same decisions
+// (iou_ge_m behind the "certainly not" bound), same greedy order: identical results.
+constexpr int kPrefixTiles = 4;   // tiles per CTA of the prefix mask kernel
+constexpr int kFixThreads = 256;
+
+__global__ void __launch_bounds__(64 * kPrefixTiles) proposal_prefix_mask_kernel(const float4* __restrict__ sbox_all,
+                                                                                 const float* __restrict__ sarea_all, int n, int pre64,
+                                                                                 int Wp, float thr, size_t lower_stride,
+                                                                                 uint64_t* __restrict__ lower_all,
+                                                                                 uint64_t* __restrict__ pub_all) {
+    const int img = blockIdx.y;
+    const float4* sbox = sbox_all + (size_t)img * pre64;
+    const float* sarea = sarea_all + (size_t)img * pre64;
+    uint64_t* lower = lower_all + (size_t)img * lower_stride;
+    uint64_t* pub = pub_all + (size_t)img * 4 * Wp;
+    const int np = min(n, Wp * 64);
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int tiles = Wp * (Wp + 1) / 2;
+    const int q = min(blockIdx.x * kPrefixTiles + g, tiles - 1);   // a spare group repeats the last tile
+    int rb, cb;
+    lower_tile_coords(q, rb, cb);
+    MRCNN_DBG(rb >= 0 && rb < Wp && cb >= 0 && cb <= rb);
+    __shared__ float4 cbox_[kPrefixTiles][64];
+    __shared__ float carea_[kPrefixTiles][64];
+    __shared__ float cshare_[kPrefixTiles][64];
+    float4* cbox = cbox_[g];
+    float* carea = carea_[g];
+    float* cshare = cshare_[g];
+    const int col0 = cb * 64;
+    if (col0 + t < np) {
+        cbox[t] = sbox[col0 + t];
+        const float a = sarea[col0 + t];
+        carea[t] = a;
+        cshare[t] = no_share(a, thr);
+    }
+    __syncthreads();
+    const int row = rb * 64 + t;
+    uint64_t w = 0ull;
+    if (row < np) w = lower_tile_word(sbox[row], sarea[row], cb == rb, t, cbox, carea, cshare, thr);
+    lower[(size_t)q * 64 + t] = w;
+    if (cb == rb && t == 0) {   // pass 0 of the published survivor words: every box kept (tag = pass * 2 + changed)
+        const int nrows = max(0, min(64, np - rb * 64));
+        const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+        pub[2 * rb] = (1ull << 32) | (valid & 0xffffffffull);
+        pub[2 * rb + 1] = (1ull << 32) | (valid >> 32);
+        pub[2 * Wp + 2 * rb] = 0ull;
+        pub[2 * Wp + 2 * rb + 1] = 0ull;
+    }
+}
+
+// grid (Wp, images of this launch), cooperative: every CTA must be resident, they wait for each other's published words.
+__global__ void __launch_bounds__(kFixThreads) proposal_fixpoint_kernel(const uint64_t* __restrict__ lower_all, size_t lower_stride,
+                                                                        const float4* __restrict__ sbox_all,
+                                                                        const float* __restrict__ sarea_all, int n, int pre64, int Wp,
+                                                                        int img0, uint64_t* __restrict__ pub_all, int post, float height,
+                                                                        float width, float* __restrict__ rois_out,
+                                                                        int32_t* __restrict__ counts_out, float4* __restrict__ kbox_all,
+                                                                        float* __restrict__ karea_all, int32_t* __restrict__ tail_all) {
+    extern __shared__ __align__(128) uint64_t fx_dyn[];
+    uint64_t* s_rows = fx_dyn;                        // [c][64]
+    uint64_t* s_keep = fx_dyn + (size_t)Wp * 64;      // [Wp]
+    __shared__ unsigned s_sup[2];
+    __shared__ int s_any[2];
+    __shared__ uint64_t s_bar;
+    __shared__ int s_prefix[kMaxPreNms / 64 + 1];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int S_ = nt >> 6, box = tid & 63, slice = tid >> 6;
+    const int c = blockIdx.x, img = img0 + blockIdx.y;
+    const int np = min(n, Wp * 64);
+    const uint64_t* tiles = lower_all + (size_t)img * lower_stride + (size_t)c * (c + 1) / 2 * 64;
+    uint64_t* pub = pub_all + (size_t)img * 4 * Wp;
+    if (tid == 0 && c > 0) {
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&s_bar, (uint32_t)c * 512u);
+        bulk_g2s(s_rows, tiles, (uint32_t)c * 512u, &s_bar);
+    }
+    uint64_t own_ca = 0ull, own_cb = 0ull, own_word = 0ull;
+    const int nrows = max(0, min(64, np - c * 64));
+    const uint64_t valid = nrows == 64 ? ~0ull : ((1ull << nrows) - 1ull);
+    if (warp == 0) {
+        own_ca = __ldg(tiles + (size_t)c * 64 + lane);
+        own_cb = __ldg(tiles + (size_t)c * 64 + lane + 32);
+        own_word = valid;
+    }
+    if (tid < 2) s_any[tid] = 0;
+    __syncthreads();
+    for (unsigned pass = 1;; ++pass) {
+        if (tid < 2) s_sup[tid] = 0u;
+        for (int i = tid; i < 2 * Wp; i += nt) {
+            const uint64_t* src = pub + (size_t)((pass - 1) & 1u) * 2 * Wp + i;
+            uint64_t v;
+            do {
+                v = ld_relaxed_u64(src);
+            } while ((unsigned)(v >> 33) != pass - 1);
+            reinterpret_cast<unsigned*>(s_keep)[i] = (unsigned)v;
+            if ((v >> 32) & 1ull) s_any[pass & 1u] = 1;
+        }
+        __syncthreads();
+        if (pass > 1 && s_any[pass & 1u] == 0) break;   // the previous pass changed nothing: s_keep is the answer
+        if (tid == 0) s_any[(pass + 1u) & 1u] = 0;
+        if (pass == 1 && c > 0) mbar_wait(&s_bar, 0u);
+        uint64_t acc = 0ull;
+#pragma unroll 4
+        for (int w = slice; w < c; w += S_) {
+            MRCNN_DBG(w >= 0 && w < Wp && w * 64 + box < c * 64);
+            acc |= s_rows[w * 64 + box] & s_keep[w];
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, acc != 0ull);
+        if (lane == 0 && hit) atomicOr(&s_sup[warp & 1], hit);
+        __syncthreads();
+        if (warp == 0) {
+            const uint64_t cand = valid & ~((uint64_t)s_sup[0] | ((uint64_t)s_sup[1] << 32));
+            uint64_t alive = cand;
+            for (;;) {
+                const unsigned sa = __ballot_sync(0xffffffffu, (own_ca & alive) != 0ull);
+                const unsigned sb = __ballot_sync(0xffffffffu, (own_cb & alive) != 0ull);
+                const uint64_t next = cand & ~((uint64_t)sa | ((uint64_t)sb << 32));
+                if (next == alive) break;
+                alive = next;
+            }
+            if (lane < 2) {   // an atomic exchange, not a store: see nms_fixpoint_pub_kernel
+                const uint64_t tag = (uint64_t)(pass * 2u + (alive != own_word ? 1u : 0u)) << 32;
+                atomicExch(reinterpret_cast<unsigned long long*>(pub + (size_t)(pass & 1u) * 2 * Wp + 2 * c + lane),
+                           (unsigned long long)(tag | ((alive >> (32 * lane)) & 0xffffffffull)));
+            }
+            own_word = alive;
+        }
+    }
+    if (c != 0) return;
+    // CTA (0, img): the survivors of the prefix, in score order
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < Wp; ++w) {
+            s_prefix[w] = run;
+            run += __popcll(s_keep[w]);
+        }
+        s_prefix[Wp] = run;
+    }
+    __syncthreads();
+    const int S = s_prefix[Wp];
+    const bool finished = S >= post || np >= n;   // else the lazy kernel goes on from chunk Wp
+    const float4* sbox = sbox_all + (size_t)img * pre64;
+    const float* sarea = sarea_all + (size_t)img * pre64;
+    float4* rois = reinterpret_cast<float4*>(rois_out + (size_t)img * post * 4);
+    float4* kbox = kbox_all + (size_t)img * (kHybridMaxPost + 64);
+    float* karea = karea_all + (size_t)img * (kHybridMaxPost + 64);
+    for (int i = tid; i < np; i += nt) {
+        const uint64_t kw = s_keep[i >> 6];
+        if ((kw >> (i & 63)) & 1ull) {
+            const int r = s_prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+            if (r < post) {
+                const float4 b = sbox[i];
+                float4 o;  // model.py:1371-1374 boxes / [h, w, h, w]
+                o.x = __fdiv_rn(b.x, height);
+                o.y = __fdiv_rn(b.y, width);
+                o.z = __fdiv_rn(b.z, height);
+                o.w = __fdiv_rn(b.w, width);
+                rois[r] = o;
+                if (!finished) {   // S < post: every survivor is one the tail has to test against
+                    kbox[r] = b;
+                    karea[r] = sarea[i];
+                }
+            }
+        }
+    }
+    if (finished) {
+        const int total = min(S, post);  // model.py:1366 keep[:proposal_count]
+        for (int r = total + tid; r < post; r += nt) rois[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid == 0) counts_out[img] = total;
+    }
+    if (tid == 0) tail_all[img] = finished ? -1 : S;
+}
+
 __global__ void proposal_empty_kernel(float* rois, size_t n, int32_t* counts, int B) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) rois[i] = 0.f;
@@ -735,7 +946,8 @@ static int g_proposal_nms_algo = MRCNN_PROPOSAL_NMS_AUTO;
 extern "C" {
 
 int mrcnn_set_proposal_nms(int algo) {
-    MRCNN_REQUIRE(algo == MRCNN_PROPOSAL_NMS_AUTO || algo == MRCNN_PROPOSAL_NMS_MASK || algo == MRCNN_PROPOSAL_NMS_LAZY,
+    MRCNN_REQUIRE(algo == MRCNN_PROPOSAL_NMS_AUTO || algo == MRCNN_PROPOSAL_NMS_MASK || algo == MRCNN_PROPOSAL_NMS_LAZY ||
+                      algo == MRCNN_PROPOSAL_NMS_HYBRID,
                   "mrcnn_set_proposal_nms: unknown algorithm %d", algo);
     g_proposal_nms_algo = algo;
     return MRCNN_OK;
@@ -805,8 +1017,47 @@ static int proposal_layer_impl(const float* rpn_class, int sstride, const float*
     cfg.numAttrs = 1;
     MRCNN_CUDA(cudaLaunchKernelEx(&cfg, proposal_select_kernel, p));
 
-    // NMS: lazy pull-style kernel when only a few survivors are wanted, the N x N mask + sweep otherwise
-    const bool lazy = g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_LAZY || (g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_AUTO && post_nms <= 2048);
+    // NMS: when only a few survivors are wanted, the prefix fixed point + lazy tail (hybrid) or the lazy kernel alone; the N x N
+    // mask + sweep otherwise
+    const int W = p.pre64 / 64;
+    const bool few = post_nms <= kHybridMaxPost;
+    const bool hybrid = W >= 2 && (g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_HYBRID || (g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_AUTO && few));
+    const bool lazy = hybrid || g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_LAZY || (g_proposal_nms_algo == MRCNN_PROPOSAL_NMS_AUTO && few);
+    int Wp = 0;
+    if (hybrid) {
+        MRCNN_REQUIRE(few, "mrcnn_proposal_layer: post_nms too large for the hybrid NMS (use MRCNN_PROPOSAL_NMS_MASK)");
+        static const int pct = getenv("MRCNN_PROPOSAL_PREFIX_PCT") ? atoi(getenv("MRCNN_PROPOSAL_PREFIX_PCT")) : 125;   // experiment knob
+        Wp = std::min(W, std::max(2, (int)(((long long)post_nms * pct / 100 + 63) / 64)));
+        const int tiles = Wp * (Wp + 1) / 2;
+        const size_t lower_stride = (size_t)p.pre64 * W;   // words per image in ws.mask (>= tiles * 64)
+        proposal_prefix_mask_kernel<<<dim3((tiles + kPrefixTiles - 1) / kPrefixTiles, B), 64 * kPrefixTiles, 0, stream>>>(
+            ws.sbox, ws.sarea, pre, p.pre64, Wp, nms_threshold, lower_stride, ws.mask, ws.pub);
+        MRCNN_LAUNCH_CHECK();
+        const size_t smem_f = (size_t)Wp * 512 + (size_t)Wp * 8;
+        MRCNN_CUDA(cudaFuncSetAttribute(proposal_fixpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kMaxPreNms / 64) * 520)));
+        int per_sm = 0;
+        MRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, proposal_fixpoint_kernel, kFixThreads, smem_f));
+        const int cap = per_sm * sm_count() / Wp;   // images whose CTAs can all be resident at once
+        MRCNN_REQUIRE(cap >= 1, "mrcnn_proposal_layer: the prefix fixed point does not fit the device");
+        for (int img0 = 0; img0 < B; img0 += cap) {
+            const uint64_t* lower = ws.mask;
+            const float4* sb = ws.sbox;
+            const float* sa = ws.sarea;
+            size_t ls = lower_stride;
+            int n_ = pre, pre64_ = p.pre64, wp_ = Wp, i0 = img0, post_ = post_nms;
+            float h_ = height, w_ = width;
+            uint64_t* pub = ws.pub;
+            float4* kb = ws.kbox;
+            float* ka = ws.karea;
+            int32_t* tl = ws.tail;
+            void* args[] = {(void*)&lower, (void*)&ls, (void*)&sb, (void*)&sa, (void*)&n_, (void*)&pre64_, (void*)&wp_, (void*)&i0,
+                            (void*)&pub, (void*)&post_, (void*)&h_, (void*)&w_, (void*)&rois_out, (void*)&counts_out, (void*)&kb,
+                            (void*)&ka, (void*)&tl};
+            MRCNN_CUDA(cudaLaunchCooperativeKernel((const void*)proposal_fixpoint_kernel, dim3(Wp, std::min(cap, B - img0)), dim3(kFixThreads),
+                                                   args, smem_f, stream));
+        }
+        if (Wp >= W) return MRCNN_OK;   // the prefix was everything
+    }
     if (lazy) {
         const size_t smem_l = (size_t)(post_nms + 64) * 20;
         MRCNN_REQUIRE(smem_l <= 200 * 1024, "mrcnn_proposal_layer: post_nms too large for the lazy NMS (use MRCNN_PROPOSAL_NMS_MASK)");
@@ -825,10 +1076,10 @@ static int proposal_layer_impl(const float* rpn_class, int sstride, const float*
         lcfg.attrs = lattr;
         lcfg.numAttrs = 1;
         MRCNN_CUDA(cudaLaunchKernelEx(&lcfg, proposal_lazy_nms_kernel, (const float4*)ws.sbox, (const float*)ws.sarea, pre, p.pre64,
-                                      nms_threshold, post_nms, height, width, rois_out, counts_out));
+                                      nms_threshold, post_nms, height, width, rois_out, counts_out,
+                                      (const int32_t*)(hybrid ? ws.tail : nullptr), (const float4*)ws.kbox, (const float*)ws.karea, Wp));
         return MRCNN_OK;
     }
-    const int W = p.pre64 / 64;
     proposal_mask_kernel<<<dim3(W, W, B), 64, 0, stream>>>(ws.sbox, ws.sarea, pre, p.pre64, W, nms_threshold, ws.mask);
     MRCNN_LAUNCH_CHECK();
 

@@ -61,11 +61,12 @@ def _plan_stream(device):
 
 
 def set_proposal_nms(name):
-    """NMS inside the proposal layer: "auto" (lazy when post_nms <= 2048), "mask" (IoU-bitmask tiles + sweep) or "lazy"
-    (chunks of 64 boxes against the survivors so far, stops at the post_nms-th survivor).  Identical results."""
-    algos = {"auto": 0, "mask": 1, "lazy": 2}
+    """NMS inside the proposal layer: "auto" (hybrid when post_nms <= 2048), "mask" (IoU-bitmask tiles + sweep), "lazy"
+    (chunks of 64 boxes against the survivors so far, stops at the post_nms-th survivor) or "hybrid" (the first 1.25 post_nms
+    boxes resolved at once by a grid-wide fixed-point iteration, the lazy kernel for what is left).  Identical results."""
+    algos = {"auto": 0, "mask": 1, "lazy": 2, "hybrid": 3}
     if name not in algos:
-        raise ValueError("proposal NMS must be 'auto', 'mask' or 'lazy'")
+        raise ValueError("proposal NMS must be 'auto', 'mask', 'lazy' or 'hybrid'")
     check(lib.mrcnn_set_proposal_nms(algos[name]))
 
 

@@ -49,7 +49,7 @@ def ref_C_or_none():
 
 
 # ------------------------------------------------------------------ configs[1]
-@pytest.mark.parametrize("algo", ["lazy", "mask"])
+@pytest.mark.parametrize("algo", ["lazy", "mask", "hybrid"])
 def test_proposal_layer_config1_vs_oracle(ops, algo):
     """261,888 anchors, 6000 -> 1000 at IoU 0.7, batch 8: every image's proposals bit-exact against the oracle; the NMS
     input of image 0 (the 6000 decoded, clipped boxes in score order) also goes through the reference's own nms."""

@@ -386,9 +386,9 @@ def test_roialign_adjoint_full_size(ops, algo):
 
 
 # ------------------------------------------------------------------ proposal layer
-@pytest.fixture(params=["lazy", "mask"])
+@pytest.fixture(params=["lazy", "mask", "hybrid"])
 def nms_algo(request, ops):
-    """Both NMS implementations of the proposal layer must give the oracle's result."""
+    """Every NMS implementation of the proposal layer must give the oracle's result."""
     ops.set_proposal_nms(request.param)
     yield request.param
     ops.set_proposal_nms("auto")
@@ -441,19 +441,51 @@ def test_proposal_layer_with_score_ties(ops, nms_algo):
         np.testing.assert_array_equal(rois[0, :len(want)].cpu().numpy(), want)
 
 
+def test_proposal_hybrid_tail_and_image_groups(ops):
+    """The hybrid NMS on inputs whose top boxes pile up on a few objects (synth.rpn_outputs(converge=0.9): ~600 survivors in 6000
+    boxes, so the prefix never holds post_nms survivors and every image goes on into the lazy tail), mixed in one batch with
+    ordinary images that finish inside the prefix; and 70 images in one call (more than one cooperative launch can hold)."""
+    size = 256
+    anchors = synth.pyramid_anchors((size, size))
+    ops.set_proposal_nms("hybrid")
+    try:
+        rcs, rbs = zip(*[synth.rpn_outputs(anchors, 300 + i, image=float(size), n_clusters=4, converge=0.9 if i % 2 else 0.0) for i in range(6)])
+        for pre, post, thr in ((6000, 1000, 0.7), (3000, 200, 0.5), (6000, 2048, 0.7)):
+            rois, counts = ops.proposal_layer(dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors), pre, post, thr, image_hw=(size, size))
+            rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
+            for i in range(6):
+                want = oracle.proposal_layer(rcs[i], rbs[i], anchors, pre, post, thr, height=float(size), width=float(size))
+                assert counts[i] == len(want), (pre, post, thr, i, counts[i], len(want))
+                np.testing.assert_array_equal(rois[i, :counts[i]], want)
+                assert not rois[i, counts[i]:].any()
+        B = 70
+        rc = np.stack([rcs[i % 6] for i in range(B)])
+        rb = np.stack([rbs[(i * 5) % 6] for i in range(B)])
+        rois, counts = ops.proposal_layer(dev(rc), dev(rb), dev(anchors), 6000, 1000, 0.7, image_hw=(size, size))
+        rois, counts = rois.cpu().numpy(), counts.cpu().numpy()
+        for i in range(0, B, 3):
+            want = oracle.proposal_layer(rc[i], rb[i], anchors, 6000, 1000, 0.7, height=float(size), width=float(size))
+            assert counts[i] == len(want)
+            np.testing.assert_array_equal(rois[i, :counts[i]], want)
+    finally:
+        ops.set_proposal_nms("auto")
+
+
 def test_proposal_nms_algorithms_agree_at_full_size(ops):
-    """configs[1] size (261,888 anchors, 6000 -> 1000, batch 8): lazy and mask + sweep NMS return the same bytes; a low
-    threshold (heavy suppression: the lazy kernel walks all 94 chunks) as well."""
+    """configs[1] size (261,888 anchors, 6000 -> 1000, batch 8): lazy, hybrid and mask + sweep NMS return the same bytes; a low
+    threshold (heavy suppression: the lazy kernel walks all 94 chunks, the hybrid's prefix leaves most of the work to its tail) as
+    well."""
     anchors = synth.pyramid_anchors((1024, 1024))
     rc, rb = zip(*[synth.rpn_outputs(anchors, 60 + i) for i in range(2)])
     rc_d, rb_d, an_d = dev(np.stack([rc[i % 2] for i in range(8)])), dev(np.stack([rb[i % 2] for i in range(8)])), dev(anchors)
     try:
         for thr, post in ((0.7, 1000), (0.1, 1000), (0.5, 2048)):
             out = {}
-            for algo in ("lazy", "mask"):
+            for algo in ("lazy", "mask", "hybrid"):
                 ops.set_proposal_nms(algo)
                 out[algo] = ops.proposal_layer(rc_d, rb_d, an_d, 6000, post, thr)
             assert torch.equal(out["lazy"][0], out["mask"][0]) and torch.equal(out["lazy"][1], out["mask"][1])
+            assert torch.equal(out["hybrid"][0], out["mask"][0]) and torch.equal(out["hybrid"][1], out["mask"][1])
             assert int(out["lazy"][1].min()) > 0
     finally:
         ops.set_proposal_nms("auto")
@@ -1096,7 +1128,7 @@ def test_detect_flow_golden_dropins(ops):
                                 DETECTION_NMS_THRESHOLD=float(g["det_in_thr"]), DETECTION_MAX_INSTANCES=int(g["det_in_limits"][0]))
     me = types.SimpleNamespace(config=cfg, anchors=dev(g["prop_in_anchors"]))
     fgd = g["prop_in_fg_detied"]
-    for algo in ("lazy", "mask"):
+    for algo in ("lazy", "mask", "hybrid"):
         ops.set_proposal_nms(algo)
         try:
             rois = ops.rpn_refine(me, dev(np.stack([1.0 - fgd, fgd], 1).astype(np.float32)).unsqueeze(0), bbox)
