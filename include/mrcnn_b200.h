@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 5
+#define MRCNN_ABI_VERSION 6
 
 #define MRCNN_OK 0
 #define MRCNN_E_INVALID_ARG (-1)    /* bad size / null pointer / unsupported combination            */
@@ -112,7 +112,8 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward_pair(const float* const fm[4], con
  *                      mrcnn_pyramid_roi_align_backward_workspace_bytes_ex() bytes.  Either layout of grads and gfm.
  *                      Summation order: a unit's bins are queued in the order the planning threads reach it (atomic
  *                      cursors), so two PLANS of the same boxes may add a pixel's terms in different orders and differ
- *                      in the last bits (tests bound it at 1e-5 relative); replaying one plan is bit-reproducible.
+ *                      in the last bits (tests bound it at 1e-5 relative); replaying one plan is bit-reproducible, and
+ *                      mrcnn_set_deterministic(1) makes every plan order its items (bit-identical gradients).
  *                      The scatter's reductions are unordered by nature.
  *   MRCNN_BWD_SCATTER  clear, then scatter with column-aggregated 128-bit vector reductions
  *                      (red.global.add.v4.f32) for a channels-last gfm, scalar atomics for an NCHW gfm.
@@ -124,6 +125,12 @@ MRCNN_API int mrcnn_pyramid_roi_align_forward_pair(const float* const fm[4], con
 #define MRCNN_BWD_AUTO 0
 #define MRCNN_BWD_GATHER 1
 #define MRCNN_BWD_SCATTER 2
+/* Deterministic gather plans (process-wide; default off, or MRCNN_DETERMINISTIC=1 in the environment): every plan ends with a
+ * pass that orders each unit's items by (gradient offset, column), so that two plans of the same boxes sum in the same order and
+ * MRCNN_BWD_GATHER gradients are bit-reproducible across calls.  Set it BEFORE querying workspace sizes: the plan needs a second
+ * item array (a plan given the smaller workspace fails with MRCNN_E_WORKSPACE).  No counterpart in the reference (its CPU loop has
+ * one fixed order, its CUDA atomicAdd path none). */
+MRCNN_API int mrcnn_set_deterministic(int on);
 MRCNN_API size_t mrcnn_pyramid_roi_align_backward_workspace_bytes(const int H[4], const int W[4], int B, int N,
                                                                   int pool);
 /* The same with the upstream-gradient layout taken into account: MRCNN_BWD_GATHER also serves NCHW gradient maps (every unit of

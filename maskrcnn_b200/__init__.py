@@ -19,7 +19,7 @@ import importlib
 _OPS = ("CropFunction", "check_device_errors", "crop_and_resize", "decode_masks", "detection_layer", "detection_targets",
         "full_masks", "mrn_refine", "mrn_samples", "nms", "proposal_layer", "pyramid_roi_align", "pyramid_roi_align_backward_pair",
         "pyramid_roi_align_pair", "roi_align", "rpn_detect", "rpn_pack", "rpn_refine", "rpn_samples", "set_backward_algorithm",
-        "set_backward_planning", "set_detection_nms", "set_proposal_nms")
+        "set_backward_planning", "set_detection_nms", "set_proposal_nms", "set_deterministic")
 _LIB = ("LIB_PATH", "MrcnnError")
 __all__ = list(_OPS) + list(_LIB) + ["patch"]
 

@@ -23,6 +23,7 @@ _f4 = ctypes.c_float * 4
 # name -> (restype, argtypes); must list every symbol include/mrcnn_b200.h declares (tests/test_abi.py)
 SIGNATURES = {
     "mrcnn_abi_version": (_i, []),
+    "mrcnn_set_deterministic": (_i, [_i]),
     "mrcnn_last_error": (ctypes.c_char_p, []),
     "mrcnn_poll_device_errors": (_i, [_vp]),
     "mrcnn_crop_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _i, _i, _vp, _i, _vp]),
@@ -84,7 +85,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mrcnn_abi_version() != 5:
+    if lib.mrcnn_abi_version() != 6:
         raise ImportError("maskrcnn_b200: ABI version mismatch")
     return lib
 

@@ -2013,9 +2013,24 @@ struct GatherWorkspace {
     int* pos;
     unsigned int* cursor;
     QItem* items;
+    QItem* sorted;       // deterministic plans only: scratch of the per-unit item sort, same capacity as items
+    int* heavy;          // deterministic plans only: [units] queue of the units sorted by a whole CTA (its length: cursor[1])
     size_t clear_bytes;  // cnt + cursor are cleared before every call (they are adjacent)
     size_t bytes;
 };
+
+// Deterministic plans (mrcnn_set_deterministic / MRCNN_DETERMINISTIC=1): the fill pass places a unit's items through atomic
+// cursors, so their order - the fp32 summation order of the gather - depends on scheduling.  With the switch on, every plan ends
+// with a pass that rewrites each unit's items in ascending (gradient offset, column) order: two plans of the same boxes then give
+// bit-identical gradients.  It costs a second item array in the workspace and one short kernel per plan.
+static int g_deterministic = -1;
+static bool deterministic_plans() {
+    if (g_deterministic < 0) {
+        const char* e = getenv("MRCNN_DETERMINISTIC");
+        g_deterministic = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_deterministic == 1;
+}
 
 static long long gather_units(const int H[4], const int W[4], int B) {
     long long units = 0;
@@ -2032,12 +2047,15 @@ static GatherWorkspace carve_gather(void* base, const int H[4], const int W[4], 
         off += align_up(bytes, 256);
         return q;
     };
-    w.cursor = (unsigned int*)take(4);
+    w.cursor = (unsigned int*)take(8);   // [0] the fill cursor, [1] the length of the heavy-unit queue (deterministic plans)
     w.cnt = (int*)take(units * 4);
     w.clear_bytes = off;
     w.pos = (int*)take(units * 4);
     // every bin yields at most four work items (two rows x a unit boundary); bins = sum of pool^2 over the heads
-    w.items = (QItem*)take((size_t)4 * (size_t)(N > 0 ? N : 1) * (size_t)bins * sizeof(QItem));
+    const size_t item_bytes = (size_t)4 * (size_t)(N > 0 ? N : 1) * (size_t)bins * sizeof(QItem);
+    w.items = (QItem*)take(item_bytes);
+    w.sorted = deterministic_plans() ? (QItem*)take(item_bytes) : nullptr;
+    w.heavy = deterministic_plans() ? (int*)take(units * 4) : nullptr;
     w.bytes = off;
     return w;
 }
@@ -2086,6 +2104,108 @@ static GatherParams gather_params(const GatherWorkspace& ws, const int H[4], con
     return g;
 }
 
+// Deterministic plans: every unit's items rewritten in ascending (gradient offset, column | head) order, through the scratch array
+// and back.  Keys are unique inside a unit (a bin reaches a unit at most once as a main item and never also as a spill item); the
+// index tie-break keeps the light pass a permutation even if they were not.
+//   light units (<= kSortLight items: nearly all of them, ~30 items on average): one warp per unit, rank sort (every item counts
+//     the items that precede it);
+//   heavy units (the coarse levels collect thousands of items per unit): queued by the light pass, then one CTA per unit -
+//     a bitonic network over (key, position) pairs in shared memory up to kSortCap items, a CTA-wide rank sort beyond.
+constexpr int kSortLight = 64;
+constexpr int kSortCap = 4096;
+
+__device__ __forceinline__ uint64_t item_key(const QItem& it) { return ((uint64_t)(uint32_t)it.off << 32) | (uint32_t)it.idx; }
+
+__global__ void __launch_bounds__(256) bwd_sort_items_kernel(const GatherParams p, QItem* __restrict__ scratch, int* __restrict__ heavy,
+                                                             unsigned int* __restrict__ heavy_count) {
+    const int u = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (u >= p.units) return;
+    const int n = p.cnt[u];
+    if (n < 2) return;
+    if (n > kSortLight) {
+        if (lane == 0) heavy[atomicAdd(heavy_count, 1u)] = u;   // the ORDER of this queue does not matter: units are independent
+        return;
+    }
+    const int beg = p.pos[u] - n;
+    MRCNN_DBG(beg >= 0);
+    QItem* src = p.items + beg;
+    QItem* tmp = scratch + beg;
+    for (int i = lane; i < n; i += 32) {
+        const QItem it = src[i];
+        const uint64_t key = item_key(it);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint64_t kj = item_key(src[j]);   // the same address for every lane: one broadcast load
+            rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+        }
+        MRCNN_DBG(rank >= 0 && rank < n);
+        tmp[rank] = it;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) src[i] = tmp[i];
+}
+
+__global__ void __launch_bounds__(256) bwd_sort_heavy_kernel(const GatherParams p, QItem* __restrict__ scratch, const int* __restrict__ heavy,
+                                                             const unsigned int* __restrict__ heavy_count) {
+    __shared__ uint64_t s_key[kSortCap];
+    __shared__ uint16_t s_idx[kSortCap];
+    const int tid = threadIdx.x;
+    const int count = (int)*heavy_count;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int u = heavy[q];
+        const int n = p.cnt[u];
+        const int beg = p.pos[u] - n;
+        MRCNN_DBG(u >= 0 && u < p.units && n > kSortLight && beg >= 0);
+        QItem* src = p.items + beg;
+        QItem* tmp = scratch + beg;
+        if (n <= kSortCap) {
+            int P = 128;
+            while (P < n) P <<= 1;
+            for (int i = tid; i < P; i += 256) {
+                s_key[i] = i < n ? item_key(src[i]) : ~0ull;   // padding sorts to the end (a real key never has all bits set: idx <= 31)
+                s_idx[i] = (uint16_t)i;
+            }
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (P >> 1); t += 256) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int l = i | j;
+                        const bool up = (i & k) == 0;
+                        const uint64_t a = s_key[i], b = s_key[l];
+                        if ((a > b) == up) {
+                            s_key[i] = b;
+                            s_key[l] = a;
+                            const uint16_t x = s_idx[i];
+                            s_idx[i] = s_idx[l];
+                            s_idx[l] = x;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < n; i += 256) {
+                MRCNN_DBG(s_idx[i] < n);
+                tmp[i] = src[s_idx[i]];
+            }
+        } else {   // beyond the shared-memory network: every item counts its predecessors (n^2 / 256 steps per thread)
+            for (int i = tid; i < n; i += 256) {
+                const QItem it = src[i];
+                const uint64_t key = item_key(it);
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const uint64_t kj = item_key(src[j]);
+                    rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+                }
+                tmp[rank] = it;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) src[i] = tmp[i];
+        __syncthreads();
+    }
+}
+
 // Passes 1-3: the work-item queues of every unit.  They depend on the boxes, the pool sizes, C and the pyramid geometry
 // only - not on the gradients - so a training step can build them while the forward runs (mrcnn_..._backward_plan).
 static int launch_gather_plan(GatherParams g, const GatherWorkspace& ws, void* workspace, int heads, const int pools[2],
@@ -2107,6 +2227,12 @@ static int launch_gather_plan(GatherParams g, const GatherWorkspace& ws, void* w
             bwd_alloc_kernel<<<ugrid, 256, 0, stream>>>(g);
             MRCNN_LAUNCH_CHECK();
         }
+    }
+    if (ws.sorted != nullptr) {
+        bwd_sort_items_kernel<<<(unsigned)(((long long)g.units * 32 + 255) / 256), 256, 0, stream>>>(g, ws.sorted, ws.heavy, ws.cursor + 1);
+        MRCNN_LAUNCH_CHECK();
+        bwd_sort_heavy_kernel<<<sm_count() * 4, 256, 0, stream>>>(g, ws.sorted, ws.heavy, ws.cursor + 1);
+        MRCNN_LAUNCH_CHECK();
     }
     return MRCNN_OK;
 }
@@ -2480,6 +2606,11 @@ int mrcnn_pyramid_roi_align_backward_pair(const float* grads_a, int pool_a, cons
     const int pools[2] = {pool_a, pool_b};
     return launch_bwd_gather(2, gr, pools, H, W, B, C, boxes, box_index, N, image_area, gfm, zero_fill ? 0 : 1, workspace,
                              (cudaStream_t)stream);
+}
+
+int mrcnn_set_deterministic(int on) {
+    g_deterministic = on ? 1 : 0;
+    return MRCNN_OK;
 }
 
 }  // extern "C"

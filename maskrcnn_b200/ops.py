@@ -24,7 +24,7 @@ from ._lib import NCHW, NHWC, check, lib
 
 __all__ = ["nms", "CropFunction", "crop_and_resize", "pyramid_roi_align", "roi_align", "proposal_layer",
            "rpn_refine", "detection_layer", "mrn_refine", "detection_targets", "mrn_samples", "pyramid_roi_align_backward_pair", "pyramid_roi_align_pair", "rpn_samples", "full_masks", "decode_masks", "rpn_pack", "rpn_detect", "set_proposal_nms", "set_detection_nms", "check_device_errors",
-           "set_backward_algorithm", "set_backward_planning"]
+           "set_backward_algorithm", "set_backward_planning", "set_deterministic"]
 
 
 # Backward of the channels-last PyramidROIAlign: "auto" (MRCNN_BWD_AUTO: the row-owner gather whenever the call is
@@ -51,6 +51,15 @@ def set_backward_planning(enabled):
     them itself.  Results are identical."""
     global BACKWARD_PLANNING
     BACKWARD_PLANNING = bool(enabled)
+
+
+def set_deterministic(enabled):
+    """True: every gather-backward plan ends with a pass that orders each unit's work items, so the gradients of the gather
+    backward are bit-reproducible from call to call (the default plan fills the queues through atomic cursors: same values to
+    ~1e-7 relative, last bits depend on scheduling).  Process-wide; set it before the first backward (workspaces grow by a
+    second item array).  The scatter backward (NCHW 14x14 by default, `set_backward_algorithm("scatter")`) sums through
+    unordered reductions and is not covered."""
+    check(lib.mrcnn_set_deterministic(1 if enabled else 0))
 
 
 def _plan_stream(device):

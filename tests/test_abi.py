@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_abi_version_and_workspace_queries():
     from maskrcnn_b200 import _lib
     L = _lib.lib
-    assert L.mrcnn_abi_version() == 5
+    assert L.mrcnn_abi_version() == 6
     assert L.mrcnn_nms_workspace_bytes(6000) >= 6000 * 94 * 8
     assert L.mrcnn_proposal_workspace_bytes(8, 261888, 6000) >= 8 * 6016 * 94 * 8
     assert L.mrcnn_detection_workspace_bytes(64, 1000) == 256          # mask lives in shared memory up to 1024 RoIs
@@ -171,7 +171,7 @@ int main(void) {
                     "-L", libdir, "-l:libmrcnn_b200.so", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
-    assert run.stdout.strip() == "abi 5 ok"
+    assert run.stdout.strip() == "abi 6 ok"
 
 
 def test_device_code_is_sm_100a_only_and_holds_the_hot_path_kernels():

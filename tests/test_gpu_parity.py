@@ -1201,3 +1201,33 @@ def test_pyramid_arguments_are_validated(ops):
     out = ops.pyramid_roi_align_backward_pair(g7, g14, shapes, boxes, ind, (64, 64, 3), out=[cl(f) for f in fms])
     assert all(float(g.abs().max()) == 0.0 for g in out)
     ops.check_device_errors()
+
+
+def test_deterministic_gather_plans(ops):
+    """ops.set_deterministic(True): two backward calls (two plans of the same boxes) give bit-identical gradients, the fused
+    two-head backward as well; the values agree with the default plan's to rounding and stay within the oracle's tolerance."""
+    C, N, B = 64, 600, 3
+    fms = [cl(torch.randn(B, C, s, s, device="cuda")) for s in (64, 32, 16, 8)]
+    boxes_np = np.concatenate([synth.random_rois(N // B, 900 + i) for i in range(B)], 0)
+    boxes_np[N // 2:N // 2 + 100] = boxes_np[N // 2]          # a hundred RoIs on one spot: long item lists in a few units
+    boxes, ind = dev(boxes_np), torch.arange(B, device="cuda", dtype=torch.int32).repeat_interleave(N // B)
+
+    def grads(pool):
+        leaves = [f.clone().requires_grad_(True) for f in fms]
+        out = ops.pyramid_roi_align(leaves, boxes, ind, pool, (256, 256, 3))
+        g = torch.randn(out.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)).contiguous(memory_format=torch.channels_last)
+        out.backward(g)
+        return [l.grad.clone() for l in leaves]
+
+    try:
+        ops.set_deterministic(True)
+        for pool in (7, 14):
+            a, b = grads(pool), grads(pool)
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+        det = grads(14)
+    finally:
+        ops.set_deterministic(False)
+    plain = grads(14)
+    for x, y in zip(det, plain):       # a hundred coinciding RoIs: sums of hundreds of terms, so relative to the largest value
+        assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(x.abs().max()))
