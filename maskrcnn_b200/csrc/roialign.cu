@@ -1167,15 +1167,10 @@ __device__ __forceinline__ void cp_async_wait() {
 // (No minimum-blocks bound: forcing 24 / 28 / 32 CTAs per SM - 80 / 72 / 64 registers - spills and measured 0.61 / 0.75 / 0.89 ms
 // against 0.58 ms for the configs[3] 14x14 backward; U = 3 or ST = 6 are slower too.  profiles/r02_experiments.txt)
 template <int NV, int U, int ST, bool kAccumulate, bool kOutNCHW = false>
-__global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherParams p) {
-    __shared__ QItem s_items[32 + U];
+__global__ void __launch_bounds__(32, 20) roialign_bwd_gather_kernel(const GatherParams p) {
+    __shared__ QItem s_items[64];
     __shared__ __align__(16) float4 s_data[ST][U][NV][32];
     const int wl = threadIdx.x;
-    if (wl < U) {  // permanent no-op padding behind the 32 staged items
-        QItem z;
-        z.off = 0; z.wa = 0.f; z.wb = 0.f; z.idx = kONoop;
-        s_items[32 + wl] = z;
-    }
     // The default grid has one CTA per unit (one trip through this loop); a smaller, persistent grid strides over the units.
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         do {  // one unit
@@ -1195,6 +1190,7 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
     const size_t plane_ = (size_t)G.H * G.W;
     const bool vec8 = kOutNCHW && npx == kGTile && ((reinterpret_cast<uintptr_t>(out_nchw) | (plane_ * 4)) & 15u) == 0;
     const int n = __ldg(p.cnt + u);
+    const int item_end = __ldg(p.pos + u);   // requested together with n: one round trip instead of two in front of the item loads
     if (n == 0) {  // nothing reaches this unit: it is all zeros
         if (!kAccumulate) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1214,8 +1210,8 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
         }
         break;
     }
-    MRCNN_DBG(n > 0 && __ldg(p.pos + u) - n >= 0);
-    const QItem* items = p.items + (__ldg(p.pos + u) - n);
+    MRCNN_DBG(n > 0 && item_end - n >= 0);
+    const QItem* items = p.items + (item_end - n);
     for (int cbase = 0; cbase < C; cbase += 128 * NV) {
         const int c = cbase + 4 * wl;
         const bool live = c < C;
@@ -1227,59 +1223,71 @@ __global__ void __launch_bounds__(32) roialign_bwd_gather_kernel(const GatherPar
         const float* gbase = p.grads + (live ? c : 0);
         const float* gbase2 = p.grads2 + (live ? c : 0);
 
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            QItem mine;
-            mine.off = 0; mine.wa = 0.f; mine.wb = 0.f; mine.idx = kONoop;
-            if (i0 + wl < n) {
-                const int4 raw = __ldg(reinterpret_cast<const int4*>(items + i0 + wl));
-                mine.off = raw.x; mine.wa = __int_as_float(raw.y); mine.wb = __int_as_float(raw.z); mine.idx = raw.w;
+        // The unit's items are ONE stream through a 64-entry ring in shared memory: while the groups of batch b (32 items) are
+        // consumed, batch b + 1 is already staged and batch b + 2 sits in a register of every lane, so neither the item loads nor
+        // a pipeline drain / refill interrupt the cp.async ring at a batch boundary (the first version staged 32 items at a time
+        // and emptied the ring after each batch: two exposed round trips per 32 items for the units of the coarse levels, which
+        // hold hundreds of items each).  Entries past n are no-ops (weight 0, offset 0).
+        static_assert(32 % U == 0 && (ST - 1) * U <= 32, "a group never straddles a batch; the ring looks at most one batch ahead");
+        auto load_batch = [&](int bch) -> QItem {
+            QItem q;
+            q.off = 0; q.wa = 0.f; q.wb = 0.f; q.idx = kONoop;
+            const int i = 32 * bch + wl;
+            if (i < n) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(items + i));
+                q.off = raw.x; q.wa = __int_as_float(raw.y); q.wb = __int_as_float(raw.z); q.idx = raw.w;
             }
-            __syncwarp();
-            s_items[wl] = mine;
-            __syncwarp();
-            const int m = min(32, n - i0);
-            const int ngroups = (m + U - 1) / U;
-            // prologue: ST - 1 stages in flight
+            return q;
+        };
+        auto issue = [&](int grp) {
+            const int st = grp % ST;
 #pragma unroll
-            for (int sgi = 0; sgi < ST - 1; ++sgi) {
-                if (sgi < ngroups) {
+            for (int e = 0; e < U; ++e) {
+                const QItem it = s_items[(grp * U + e) & 63];
+                const float* src = ((it.idx & kOHead2) ? gbase2 : gbase) + it.off;
 #pragma unroll
-                    for (int e = 0; e < U; ++e) {
-                        const QItem it = s_items[sgi * U + e];
-                        const float* src = ((it.idx & kOHead2) ? gbase2 : gbase) + it.off;
-#pragma unroll
-                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[sgi][e][k][wl], src + 128 * k);
-                    }
-                }
-                cp_async_commit();
+                for (int k = 0; k < NV; ++k) cp_async16(&s_data[st][e][k][wl], src + 128 * k);
             }
-#pragma unroll 1
-            for (int gi = 0; gi < ngroups; ++gi) {
-                const int nxt = gi + ST - 1;
-                if (nxt < ngroups) {
-                    const int st = nxt % ST;
-#pragma unroll
-                    for (int e = 0; e < U; ++e) {
-                        const QItem it = s_items[nxt * U + e];
-                        const float* src = ((it.idx & kOHead2) ? gbase2 : gbase) + it.off;
-#pragma unroll
-                        for (int k = 0; k < NV; ++k) cp_async16(&s_data[st][e][k][wl], src + 128 * k);
-                    }
-                }
-                cp_async_commit();
-                cp_async_wait<ST - 1>();
-                const int st = gi % ST;
-#pragma unroll
-                for (int e = 0; e < U; ++e) {
-                    const QItem it = s_items[gi * U + e];
-                    float4 v[NV];
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) v[k] = s_data[st][e][k][wl];
-                    owner_accumulate<NV>(acc, it.idx & 15, it.wa, it.wb, v);
-                }
-            }
-            cp_async_wait<0>();
+        };
+        {
+            const QItem r0 = load_batch(0), r1 = load_batch(1);
+            __syncwarp();   // every lane is done with the ring's previous contents
+            s_items[wl] = r0;
+            s_items[32 + wl] = r1;
         }
+        QItem ahead = load_batch(2);
+        __syncwarp();
+        const int ngroups = (n + U - 1) / U;
+        // prologue: ST - 1 stages in flight
+#pragma unroll
+        for (int sgi = 0; sgi < ST - 1; ++sgi) {
+            if (sgi < ngroups) issue(sgi);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int gi = 0; gi < ngroups; ++gi) {
+            if (gi > 0 && ((gi * U) & 31) == 0) {   // batch b = gi U / 32 starts: batch b - 1 is consumed, its half takes batch b + 1
+                const int bch = (gi * U) >> 5;
+                __syncwarp();
+                s_items[((bch + 1) & 1) * 32 + wl] = ahead;
+                ahead = load_batch(bch + 2);
+                __syncwarp();
+            }
+            const int nxt = gi + ST - 1;
+            if (nxt < ngroups) issue(nxt);
+            cp_async_commit();
+            cp_async_wait<ST - 1>();
+            const int st = gi % ST;
+#pragma unroll
+            for (int e = 0; e < U; ++e) {
+                const QItem it = s_items[(gi * U + e) & 63];
+                float4 v[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = s_data[st][e][k][wl];
+                owner_accumulate<NV>(acc, it.idx & 15, it.wa, it.wb, v);
+            }
+        }
+        cp_async_wait<0>();
 
         if (kOutNCHW && live) {
             // every channel the lane holds: its 8 pixel sums are one sector of that channel's plane
