@@ -6,10 +6,14 @@
 //
 // Pipeline (all on `stream`, no host round trip — the reference's CUDA path copies the whole mask to
 // the host and sweeps there):
-//   1. prepare : composite keys (score, index) -> bitonic sort -> boxes/areas gathered in score order
-//   2. mask    : 64x64 tiles of IoU>=thr suppression words, upper triangle only
-//   3. sweep   : one CTA, mask row-blocks streamed through shared memory by bulk async copies,
-//                then an in-CTA prefix scan emits the surviving original indices in ascending order.
+//   1. prepare : composite keys (score, index) -> tile sort + rank merge (bitonic above 8192 keys) -> boxes/areas gathered in
+//                score order
+//   2 + 3, from 8 chunks of 64 boxes on (nms_mask_lower_kernel, nms_fixpoint_pub_kernel / nms_fixpoint_kernel):
+//                lower-triangle tile-major mask ("who suppresses me") and a GRID-WIDE fixed-point iteration - every chunk owned by
+//                a CTA, all chunks re-evaluated at once from the previous pass's survivor words until a pass changes nothing;
+//                the fixed point is the greedy answer.  Cooperative launch; CTA 0 emits the ascending list.
+//   2 + 3, below that (nms_mask_kernel, nms_sweep_kernel): upper-triangle mask, one CTA sweeps it chunk by chunk (row blocks
+//                streamed through shared memory by bulk async copies), then an in-CTA prefix scan emits the list.
 #include <algorithm>
 #include <limits.h>
 #include <stdlib.h>

@@ -4,16 +4,20 @@
 //   fg score -> top pre_nms (the reference full-sorts all 261,888 anchors, :1346) -> decode -> clip
 //   -> NMS(thr) -> first post_nms -> normalise.
 //
-// Two launches per batch (three with the mask + sweep NMS), no host synchronisation:
+// Four launches per batch with the default (hybrid) NMS, no host synchronisation:
 //   1. proposal_select_kernel : one 8-CTA thread-block CLUSTER per image.  Each CTA stages its 1/8 of the
 //      fg-score keys in shared memory ONCE (the only HBM pass over rpn_class), then a 4-pass 8-bit radix
 //      SELECT finds the exact k-th key; per-pass 256-bin histograms (double-buffered) are combined across the
 //      cluster through distributed shared memory.  Winners are compacted, the CLUSTER bitonic-sorts them
 //      together (each CTA owns 1/8 of the network, remote stages through distributed shared memory), and each
 //      CTA gathers anchors/deltas for its slice of the ranking, decodes (fp64 exp, correctly rounded) and clips.
-//   2'. proposal_lazy_nms_kernel (default, post_nms <= 2048): one 8-CTA cluster per image, 64 boxes at a time
-//      against the survivors found so far, stops at the post_nms-th survivor; emits normalised RoIs + counts.
-//   -- or (mrcnn_set_proposal_nms) --
+//   2''. proposal_prefix_mask_kernel + proposal_fixpoint_kernel (default, post_nms <= 2048): the first 1.25 post_nms boxes of
+//      every image resolved at once by a grid-wide fixed-point iteration (lower-triangle tiles, one CTA per 64 boxes and image,
+//      cooperative launch), then
+//   2'. proposal_lazy_nms_kernel: one 8-CTA cluster per image, 64 boxes at a time against the survivors found so far, stops at
+//      the post_nms-th survivor; emits normalised RoIs + counts.  After the prefix it only runs for images still short of
+//      survivors (the others' clusters leave at once); selectable on its own (mrcnn_set_proposal_nms).
+//   -- or --
 //   2. proposal_mask_kernel   : upper-triangular IoU>=thr suppression words, all images in one grid.
 //   3. proposal_sweep_kernel  : one CTA per image: TMA-staged greedy sweep with early exit at post_nms,
 //      emits normalised RoIs (zero padded) + counts.
