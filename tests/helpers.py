@@ -149,3 +149,33 @@ def golden_pyr_wide():
     pools = {p: (g[f"pool{p}_out"], g[f"pool{p}_in_grads"].astype(np.float32), [g[f"pool{p}_out_gfm{l}"] for l in range(4)])
              for p in (7, 14)}
     return fms, g["in_boxes"], [int(v) for v in g["in_image_shape"]], pools
+
+
+def nms_edge_inputs(n=1500):
+    """Box sets that stress the NMS decision at a size the grid-wide fixed-point route takes: {name: dets [n,5]} - identical boxes,
+    disjoint boxes, degenerate (zero-height, inverted, duplicated) boxes, coordinates whose areas overflow, NaN coordinates, and a
+    plain clustered set.  Scores are unique."""
+    import numpy as np
+    from maskrcnn_b200 import synth
+    rng = np.random.default_rng(8)
+    base = synth.random_rois(n, 8, image=1024.0, min_size=16, max_size=400) * 1024.0
+    base[n // 2:] = base[:n - n // 2] + rng.uniform(-6, 6, (n - n // 2, 4)).astype(np.float32)
+    scores = synth.unique_scores(n, 9)[:, None]
+    cases = {"clustered": base}
+    cases["identical"] = np.tile(np.array([[10, 10, 50, 50]], np.float32), (n, 1))
+    cases["disjoint"] = np.stack([np.arange(n) * 20.0, np.zeros(n), np.arange(n) * 20.0 + 10, np.full(n, 10.0)], 1).astype(np.float32)
+    deg = base.copy()
+    deg[::7, 2] = deg[::7, 0] - 1.0                      # height 0 with the +1 convention
+    deg[3::11, [0, 2]] = deg[3::11, [2, 0]]              # inverted in y: negative area
+    deg[5::13] = deg[4::13][: len(deg[5::13])]           # exact duplicates
+    cases["degenerate"] = deg
+    big = base.copy()
+    big[::5] *= 1e18                                     # areas overflow to inf
+    cases["huge"] = big
+    nan = base.copy()
+    nan[::9, 1] = np.nan
+    cases["nan"] = nan
+    return {k: np.concatenate([v, scores], 1).astype(np.float32) for k, v in cases.items()}
+
+
+NMS_EDGE_THRESHOLDS = (0.5, 0.0, 1.0, 0.7, float("nan"), -0.5)

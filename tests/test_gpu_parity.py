@@ -85,6 +85,17 @@ def test_nms_longest_dependency_chain(ops, n):
     np.testing.assert_array_equal(ops.nms(dev(dets[perm]), 0.5).cpu().numpy(), oracle.nms(dets[perm], 0.5))
 
 
+def test_nms_edge_cases_fixed_point_route(ops):
+    """The edge cases of test_nms_edge_cases at a size that takes the grid-wide fixed-point route (1500 boxes): identical boxes,
+    disjoint boxes, thresholds 0, 1, negative and NaN, degenerate (inverted, zero-area, duplicated) boxes, huge coordinates, NaN
+    coordinates - the division-free "certainly not" bound must hand every such pair to the reference's expression.  (The oracle is
+    pinned against the reference's compiled nms on the same inputs: tests/test_oracle_vs_ref.py.)"""
+    import helpers
+    for name, d in helpers.nms_edge_inputs().items():
+        for thr in helpers.NMS_EDGE_THRESHOLDS:
+            np.testing.assert_array_equal(ops.nms(dev(d), thr).cpu().numpy(), oracle.nms(d, thr), err_msg="%s thr=%s" % (name, thr))
+
+
 def test_nms_routes_agree():
     """The single-CTA sweep and both forms of the grid-wide fixed-point iteration (MRCNN_NMS_SWEEP, MRCNN_NMS_PUB; read once per
     process) give the same list."""

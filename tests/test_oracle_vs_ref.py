@@ -49,6 +49,16 @@ def test_nms_bit_exact(n, thr):
     assert 0 < len(want) <= n
 
 
+def test_nms_edge_inputs_at_fixed_point_size():
+    """1500-box sets with degenerate, huge, NaN and duplicated boxes and thresholds 0 / 1 / negative / NaN: the oracle follows the
+    reference's compiled nms on every one (the GPU test test_nms_edge_cases_fixed_point_route checks the CUDA path against it)."""
+    import helpers
+    C = reference.ref_C()
+    for name, d in helpers.nms_edge_inputs().items():
+        for thr in helpers.NMS_EDGE_THRESHOLDS:
+            np.testing.assert_array_equal(oracle.nms(d, thr), C.nms(torch.from_numpy(d), thr).numpy(), err_msg="%s thr=%s" % (name, thr))
+
+
 def test_nms_edge_cases():
     C = reference.ref_C()
     assert len(oracle.nms(np.zeros((0, 5), np.float32), 0.5)) == 0
