@@ -453,6 +453,10 @@ def roi_align(inputs, pool_size, image_shape):
 # ------------------------------------------------------------------------------------------------
 # proposal layer
 # ------------------------------------------------------------------------------------------------
+_PROPOSAL_WS = {}   # (B, A, pre_nms) -> workspace bytes
+_STD4 = {}          # std tuple -> ctypes float[4]
+
+
 def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, nms_threshold,
                    std=(0.1, 0.1, 0.2, 0.2), image_hw=(1024, 1024)):
     """Batched proposal layer.  rpn_class [B,A,2] - or the foreground probabilities alone, [B,A], as rpn_pack returns
@@ -469,14 +473,21 @@ def proposal_layer(rpn_class, rpn_bbox, anchors, pre_nms_limit, post_nms_limit, 
         raise ValueError("anchors must be [A,4]")
     rpn_class, rpn_bbox, anchors = rpn_class.contiguous(), rpn_bbox.contiguous(), anchors.contiguous()
     post = int(post_nms_limit)
-    with torch.cuda.device(rpn_class.device):
+    with _on(rpn_class.device):   # the layer is ~65 us of kernels for a batch of 8: the Python around the call is kept short
         rois = torch.empty((B, post, 4), dtype=torch.float32, device=rpn_class.device)
         counts = torch.empty(B, dtype=torch.int32, device=rpn_class.device)
-        ws_bytes = lib.mrcnn_proposal_workspace_bytes(B, A, int(pre_nms_limit))
+        key = (B, A, int(pre_nms_limit))
+        ws_bytes = _PROPOSAL_WS.get(key)
+        if ws_bytes is None:
+            ws_bytes = _PROPOSAL_WS[key] = lib.mrcnn_proposal_workspace_bytes(*key)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rpn_class.device)
+        std = tuple(float(v) for v in std)
+        std4 = _STD4.get(std)
+        if std4 is None:
+            std4 = _STD4[std] = _lib.f4(np.float32(std))
         fn = lib.mrcnn_proposal_layer_fg if fg_only else lib.mrcnn_proposal_layer
         check(fn(rpn_class.data_ptr(), rpn_bbox.data_ptr(), anchors.data_ptr(), B, A,
-                 int(pre_nms_limit), post, float(nms_threshold), _lib.f4(np.float32(std)),
+                 int(pre_nms_limit), post, float(nms_threshold), std4,
                  float(image_hw[0]), float(image_hw[1]), rois.data_ptr(), counts.data_ptr(),
                  ws.data_ptr(), ws_bytes, _stream()))
     return rois, counts
