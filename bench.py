@@ -1434,9 +1434,16 @@ def main():
                               "note": "algorithmic_MB counts 4 bytes per unique mask pixel; DRAM moves 32-byte sectors and the taps of a "
                                       "large box are further apart than that, so the kernel's floor is unique_sector_MB (ncu_dram_MB is "
                                       "what it moved: profiles/r02_mask_targets_ncu_summary.txt)"})
+        # the same launch with the footprint both heads share counted ONCE (what the kernel actually has to read): the conservative figure
+        U_both, _ = roofline.unique_taps(wl.boxes_np, wl.ind_np, (7, 14), (IMAGE, IMAGE), LEVEL_HW, wl.batch)
+        by_once = wl.N * CHANNELS * (49 + 196) * 4 + 4 * CHANNELS * U_both + wl.N * 20
+        pk = kern["roialign_fwd_nhwc_pair_kernel<7+14,nhwc>"]
+        pk["footprint_once_MB"] = by_once / 1e6
+        pk["frac_footprint_once"] = by_once / (pk["ms"] * 1e-3) / 1e9 / hbm
         kern["roialign_fwd_nhwc_pair_kernel<7+14,nhwc>"]["note"] = (
             "both heads in one launch; algorithmic bytes = the two heads' bytes as SURVEY 8(d) defines them (each head's unique taps "
-            "counted), while the launch reads the shared footprint once - its DRAM traffic is below that sum")
+            "counted), while the launch reads the shared footprint once - its DRAM traffic is below that sum; footprint_once_MB / "
+            "frac_footprint_once count the shared footprint once")
         # the single-head forward kernels, timed alone for comparison (not launches of the step)
         single = {}
         for pool, o_, U_ in ((7, wl.out7, U7), (14, wl.out14, U14)):
@@ -1466,6 +1473,8 @@ def main():
                                               "ncu --set full captures summarised in profiles/*_traffic.json",
                             "peak_source": peak_src,
                             "step_frac": sum(k["algorithmic_MB"] for k in kern.values()) / 1e3 / (per_step * 1e-3) / hbm,
+                            "step_frac_footprint_once": sum(k.get("footprint_once_MB", k["algorithmic_MB"]) for k in kern.values()) / 1e3 /
+                                                        (per_step * 1e-3) / hbm,
                             "kernels": kern, "single_head_forward_kernels": single,
                             "step_with_one_forward_per_head": {"ms_per_step": t_two * 1e3, "rois_per_s": wl.N / t_two}}
         line["e2e"] = e2e_run(torch, dist, wl, args.steps, args.warmup, world)

@@ -40,7 +40,9 @@ def _axis_taps(a1, a2, size, crop):
 
 
 def unique_taps(boxes, box_ind, pool, image_hw, level_hw, batch):
-    """U = number of distinct (image, level, y, x) feature-map positions read by PyramidROIAlign."""
+    """U = number of distinct (image, level, y, x) feature-map positions read by PyramidROIAlign.  `pool` may be a tuple of
+    pool sizes: the positions read by ANY of those heads, each counted once (a fused multi-head forward)."""
+    pools = tuple(pool) if isinstance(pool, (tuple, list)) else (pool,)
     boxes = np.asarray(boxes, np.float32)
     lv = roi_levels(boxes, float(image_hw[0] * image_hw[1]))
     ind = np.zeros(len(boxes), np.int64) if box_ind is None else np.asarray(box_ind, np.int64)
@@ -48,13 +50,14 @@ def unique_taps(boxes, box_ind, pool, image_hw, level_hw, batch):
     for n in range(len(boxes)):
         l = lv[n] - 2
         H, W = level_hw[l]
-        ylo, yhi = _axis_taps(boxes[n, 0], boxes[n, 2], H, pool)
-        xlo, xhi = _axis_taps(boxes[n, 1], boxes[n, 3], W, pool)
-        ys = np.unique(np.concatenate([ylo, yhi]))
-        xs = np.unique(np.concatenate([xlo, xhi]))
-        ys, xs = ys[ys >= 0], xs[xs >= 0]
-        if len(ys) and len(xs):
-            masks[l][ind[n]][np.ix_(ys, xs)] = True
+        for pl in pools:
+            ylo, yhi = _axis_taps(boxes[n, 0], boxes[n, 2], H, pl)
+            xlo, xhi = _axis_taps(boxes[n, 1], boxes[n, 3], W, pl)
+            ys = np.unique(np.concatenate([ylo, yhi]))
+            xs = np.unique(np.concatenate([xlo, xhi]))
+            ys, xs = ys[ys >= 0], xs[xs >= 0]
+            if len(ys) and len(xs):
+                masks[l][ind[n]][np.ix_(ys, xs)] = True
     return int(sum(m.sum() for m in masks)), lv
 
 
