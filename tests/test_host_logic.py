@@ -403,3 +403,24 @@ def test_pyramid_roi_align_skips_the_autograd_node_when_nothing_needs_a_gradient
     assert [x[12] for x in fake.named("mrcnn_pyramid_roi_align_forward")] == [_lib.NHWC, _lib.NCHW]
     fake.calls.clear()
     assert ops.pyramid_roi_align(plain, boxes[:0], None, 7, (64, 64, 3)).shape == (0, 8, 7, 7) and not fake.calls
+
+
+def test_roofline_unique_taps_single_and_fused_heads():
+    """roofline.unique_taps: the positions one head reads, and - for a fused two-head forward - the positions EITHER head reads,
+    each counted once: at least what the larger head reads alone, at most the sum; a single RoI that covers one level entirely
+    touches every position of its footprint rows / columns."""
+    import numpy as np
+    from maskrcnn_b200 import roofline, synth
+    level_hw = [(64, 64), (32, 32), (16, 16), (8, 8)]
+    boxes = np.concatenate([synth.random_rois(40, 70 + i) for i in range(2)], 0)
+    ind = np.repeat(np.arange(2), 40)
+    u7, lv = roofline.unique_taps(boxes, ind, 7, (256, 256), level_hw, 2)
+    u14, _ = roofline.unique_taps(boxes, ind, 14, (256, 256), level_hw, 2)
+    both, _ = roofline.unique_taps(boxes, ind, (7, 14), (256, 256), level_hw, 2)
+    assert 0 < u7 <= u14 <= both <= u7 + u14
+    assert both < u7 + u14                                   # the heads share most of their footprint
+    assert set(np.unique(lv)) <= {2, 3, 4, 5}
+    whole = np.array([[0.0, 0.0, 1.0, 1.0]], np.float32)     # the whole 256 x 256 image: level 4 (16 x 16); 7 taps per axis at i * 15 / 6
+    # -> 0, 2.5, 5, 7.5, 10, 12.5, 15: ten distinct floor / ceil positions per axis
+    u, lvw = roofline.unique_taps(whole, None, 7, (256, 256), level_hw, 1)
+    assert lvw[0] == 4 and u == 100
