@@ -179,7 +179,10 @@ MRCNN_API int mrcnn_pyramid_roi_align_backward_pair(const float* grads_a, int po
 
 /* dets [N,5] = (y1,x1,y2,x2,score), any order.  Suppress iff IoU >= threshold (the CPU rule,
  * nms_cpu.cpp:65 — the reference's own CUDA kernel uses '>').  keep_out: int64 [N], receives the
- * ASCENDING original indices of the survivors in its first *count_out entries (device int32). */
+ * ASCENDING original indices of the survivors in its first *count_out entries (device int32).
+ * From 449 boxes on the survivors are found by a grid-wide fixed-point iteration (one cooperative launch: it needs the
+ * device to itself for a few microseconds at a time, like any cooperative kernel; it can be captured in a CUDA graph);
+ * below that by a single-CTA sweep.  Both give the greedy result of nms_cpu.cpp bit for bit. */
 MRCNN_API size_t mrcnn_nms_workspace_bytes(int N);
 MRCNN_API int mrcnn_nms(const float* dets, int N, float threshold, int64_t* keep_out, int32_t* count_out,
               void* workspace, size_t workspace_bytes, mrcnn_stream_t stream);
