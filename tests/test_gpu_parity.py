@@ -1242,3 +1242,35 @@ def test_deterministic_gather_plans(ops):
     plain = grads(14)
     for x, y in zip(det, plain):       # a hundred coinciding RoIs: sums of hundreds of terms, so relative to the largest value
         assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(x.abs().max()))
+
+
+def test_cooperative_kernels_in_a_cuda_graph(ops):
+    """The fixed-point nms and the hybrid proposal NMS are cooperative launches: captured in a CUDA graph and replayed they give
+    what the eager launches give (a serving loop replays the proposal layer from a graph)."""
+    from maskrcnn_b200 import _lib as L
+    n = 3000
+    d = dev(_dets(n, 31))
+    keep = torch.empty(n, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(L.lib.mrcnn_nms_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    anchors = synth.pyramid_anchors((256, 256))
+    rcs, rbs = zip(*[synth.rpn_outputs(anchors, 40 + i, image=256.0, n_clusters=6) for i in range(3)])
+    rc, rb, an = dev(np.stack(rcs)), dev(np.stack(rbs)), dev(anchors)
+    want_keep = ops.nms(d, 0.6)
+    want_rois, want_counts = ops.proposal_layer(rc, rb, an, 3000, 500, 0.7, image_hw=(256, 256))
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        L.check(L.lib.mrcnn_nms(d.data_ptr(), n, 0.6, keep.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                torch.cuda.current_stream().cuda_stream))
+        rois, counts = ops.proposal_layer(rc, rb, an, 3000, 500, 0.7, image_hw=(256, 256))
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        keep.zero_(); cnt.zero_(); rois.zero_(); counts.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    k = int(cnt.item())
+    assert k == want_keep.numel() and torch.equal(keep[:k], want_keep)
+    assert torch.equal(rois, want_rois) and torch.equal(counts, want_counts)
