@@ -5,6 +5,7 @@ C ABI, the reference's Python arithmetic restated on the host (decode_masks' cro
 count and the two permutation draws of mrn_samples), un-padding of the padded results and the error paths.
 The kernels themselves are covered by tests/test_gpu_parity.py."""
 import contextlib
+import os
 import ctypes
 import types
 
@@ -424,3 +425,27 @@ def test_roofline_unique_taps_single_and_fused_heads():
     # -> 0, 2.5, 5, 7.5, 10, 12.5, 15: ten distinct floor / ceil positions per axis
     u, lvw = roofline.unique_taps(whole, None, 7, (256, 256), level_hw, 1)
     assert lvw[0] == 4 and u == 100
+
+
+def test_algorithm_knobs_reach_the_library(fake):
+    """set_proposal_nms / set_detection_nms / set_deterministic: names map onto the header's constants, unknown names raise before
+    anything reaches the library."""
+    for name, code in (("auto", 0), ("mask", 1), ("lazy", 2), ("hybrid", 3)):
+        ops.set_proposal_nms(name)
+        assert fake.named("mrcnn_set_proposal_nms")[-1] == (code,)
+    for name, code in (("auto", 0), ("mask", 1), ("lazy", 2)):
+        ops.set_detection_nms(name)
+        assert fake.named("mrcnn_set_detection_nms")[-1] == (code,)
+    n = len(fake.calls)
+    with pytest.raises(ValueError):
+        ops.set_proposal_nms("fixpoint")
+    with pytest.raises(ValueError):
+        ops.set_detection_nms("hybrid")
+    assert len(fake.calls) == n
+    ops.set_deterministic(True)
+    ops.set_deterministic(0)
+    assert fake.named("mrcnn_set_deterministic") == [(1,), (0,)]
+    # the header's constants are the ones ops.py sends
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mrcnn_b200.h")).read()
+    for macro, code in (("MRCNN_PROPOSAL_NMS_AUTO", 0), ("MRCNN_PROPOSAL_NMS_MASK", 1), ("MRCNN_PROPOSAL_NMS_LAZY", 2), ("MRCNN_PROPOSAL_NMS_HYBRID", 3)):
+        assert "#define %s %d" % (macro, code) in hdr
